@@ -1,0 +1,150 @@
+// Error plumbing, device probe and the small elementwise plumbing kernels (cast, fill, column sums).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace vvae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return VVAE_ERR_CUDA;
+  }
+  return VVAE_OK;
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (; i < n; i += stride) {
+    if (i + 3 < n) {
+      float v0 = to_f(src[i]), v1 = to_f(src[i + 1]), v2 = to_f(src[i + 2]), v3 = to_f(src[i + 3]);
+      dst[i] = from_f<D>(v0);
+      dst[i + 1] = from_f<D>(v1);
+      dst[i + 2] = from_f<D>(v2);
+      dst[i + 3] = from_f<D>(v3);
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = from_f<D>(to_f(src[j]));
+    }
+  }
+}
+
+// fp32 -> bf16 with 16-byte accesses on both sides (the per-step parameter shadow copy).
+__global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long n8) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n8; i += stride) {
+    float4 a = src[2 * i], b = src[2 * i + 1];
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&p0);
+    o.y = *reinterpret_cast<uint32_t*>(&p1);
+    o.z = *reinterpret_cast<uint32_t*>(&p2);
+    o.w = *reinterpret_cast<uint32_t*>(&p3);
+    dst[i] = o;
+  }
+}
+
+__global__ void fill_kernel(float* dst, float v, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = v;
+}
+
+// out[n] += sum_rows x[row, n].  Block = 32 x 8: each warp owns 32 consecutive columns (coalesced),
+// the 8 warps of a block stride over a slab of rows; partials meet in smem, one atomic per column per block.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long ld, long long rows, int n, float* __restrict__ out,
+                              int rows_per_block) {
+  __shared__ float part[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  if (col < n)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f(x[r * ld + col]);
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += part[j][threadIdx.x];
+    atomicAdd(out + col, s);
+  }
+}
+
+}  // namespace vvae
+
+using namespace vvae;
+
+extern "C" {
+
+const char* vvae_last_error(void) { return g_err; }
+int vvae_version(void) { return 100; }
+
+int vvae_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10 ? 1 : 0;
+}
+
+int vvae_cast(const void* src, int sd, void* dst, int dd, long long n, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  cudaStream_t s = as_stream(stream);
+  int threads = 256;
+  if (sd == VVAE_F32 && dd == VVAE_BF16 && n % 8 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
+    long long n8 = n / 8;
+    int blocks = (int)std::min<long long>(cdiv(n8, threads), 148 * 16);
+    cast_f32_bf16_vec_kernel<<<blocks, threads, 0, s>>>((const float4*)src, (uint4*)dst, n8);
+    return check_launch("cast");
+  }
+  int blocks = (int)std::min<long long>(cdiv(n, threads * 4), 148 * 16);
+  if (sd == VVAE_F32 && dd == VVAE_BF16) cast_kernel<<<blocks, threads, 0, s>>>((const float*)src, (bf16*)dst, n);
+  else if (sd == VVAE_BF16 && dd == VVAE_F32) cast_kernel<<<blocks, threads, 0, s>>>((const bf16*)src, (float*)dst, n);
+  else if (sd == VVAE_F32 && dd == VVAE_F32) cast_kernel<<<blocks, threads, 0, s>>>((const float*)src, (float*)dst, n);
+  else if (sd == VVAE_BF16 && dd == VVAE_BF16) cast_kernel<<<blocks, threads, 0, s>>>((const bf16*)src, (bf16*)dst, n);
+  else VVAE_REQUIRE(false, "vvae_cast: bad dtypes %d -> %d", sd, dd);
+  return check_launch("cast");
+}
+
+int vvae_fill_f32(float* dst, float value, long long n, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  int blocks = (int)std::min<long long>(cdiv(n, 256), 148 * 16);
+  fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dst, value, n);
+  return check_launch("fill");
+}
+
+int vvae_colsum(const void* x, long long ld, long long rows, int n, float* out, int dtype, vvae_stream_t stream) {
+  if (rows <= 0 || n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(x && out, "vvae_colsum: null pointer");
+  int col_blocks = (int)cdiv(n, 32);
+  // enough row slabs to fill the machine a few times over, at least 64 rows each
+  long long want = cdiv(148 * 8, col_blocks);
+  long long rpb = std::max<long long>(64, cdiv(rows, want));
+  int row_blocks = (int)cdiv(rows, rpb);
+  dim3 grid(col_blocks, row_blocks), block(32, 8);
+  VVAE_DISPATCH_DTYPE(dtype, T,
+                      (colsum_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, ld, rows, n, out, (int)rpb)));
+  return check_launch("colsum");
+}
+
+}  // extern "C"

@@ -1,0 +1,579 @@
+// HBM-bound elementwise / reduction kernels of the hot path: patchify & pixel shuffle, max-pool, channel-slice copy,
+// latent head (softplus-log, selection gate, reparameterisation + gate, fused backward with KL gradient),
+// masked reconstruction / KL losses, and the fused Adam step.
+#include "common.cuh"
+
+namespace vvae {
+
+// ---------------- Philox4x32-10 (counter-based RNG; one 128-bit block per (offset, index)) ----------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ Philox(unsigned long long seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __device__ __forceinline__ uint4 operator()(unsigned long long ctr_lo, unsigned long long ctr_hi) const {
+    uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32), c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+__device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
+  float u1 = u01(a), u2 = u01(b);
+  return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+}
+
+// ---------------- tokens <-> voxels rearrangement ----------------
+// tokens [BT, (h w), (p1 p2 c)]  <->  voxels [BT, (h p1), (w p2), c];  runs of P*C elements are contiguous on both sides.
+template <typename TI, typename TO>
+__global__ void rearrange_kernel(const TI* __restrict__ src, TO* __restrict__ dst, long long total, int H, int W, int C,
+                                 int P, int to_tokens) {
+  const int hp = H / P, wp = W / P, run = P * C;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    // decode the token-side index
+    int r = (int)(i % run);            // (p2, c)
+    long long t1 = i / run;
+    int p1 = (int)(t1 % P);
+    long long t2 = t1 / P;
+    int w = (int)(t2 % wp);
+    long long t3 = t2 / wp;
+    int h = (int)(t3 % hp);
+    long long bt = t3 / hp;
+    long long vox = ((bt * H + (long long)h * P + p1) * W + (long long)w * P) * C + r;
+    if (to_tokens) dst[i] = from_f<TO>(to_f(src[vox]));
+    else           dst[vox] = from_f<TO>(to_f(src[i]));
+  }
+}
+// same mapping, 16 bytes per thread (same dtype both sides; run*sizeof(T) % 16 == 0)
+template <typename T>
+__global__ void rearrange_vec_kernel(const T* __restrict__ src, T* __restrict__ dst, long long total_vec, int H, int W,
+                                     int C, int P, int to_tokens) {
+  constexpr int V = Vec16<T>::N;
+  const int hp = H / P, wp = W / P, runv = P * C / V;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total_vec; i += stride) {
+    int r = (int)(i % runv);
+    long long t1 = i / runv;
+    int p1 = (int)(t1 % P);
+    long long t2 = t1 / P;
+    int w = (int)(t2 % wp);
+    long long t3 = t2 / wp;
+    int h = (int)(t3 % hp);
+    long long bt = t3 / hp;
+    long long vox = ((bt * H + (long long)h * P + p1) * W + (long long)w * P) * C + (long long)r * V;
+    Vec16<T> v;
+    if (to_tokens) { v.load(src + vox); v.store(dst + i * V); }
+    else           { v.load(src + i * V); v.store(dst + vox); }
+  }
+}
+
+// ---------------- max-pool (1,2,2) ----------------
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long x_ld, T* __restrict__ y, long long total, int H,
+                                   int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int c = (int)(i % C);
+    long long t1 = i / C;
+    int j = (int)(t1 % Wo);
+    long long t2 = t1 / Wo;
+    int ii = (int)(t2 % Ho);
+    long long bt = t2 / Ho;
+    const T* p = x + ((bt * H + 2 * ii) * W + 2 * j) * x_ld + c;
+    float m = to_f(p[0]);
+    m = fmaxf(m, to_f(p[x_ld]));
+    m = fmaxf(m, to_f(p[(long long)W * x_ld]));
+    m = fmaxf(m, to_f(p[(long long)W * x_ld + x_ld]));
+    y[i] = from_f<T>(m);
+  }
+}
+template <typename T>
+__global__ void maxpool_bwd_kernel(const T* __restrict__ x, long long x_ld, const T* __restrict__ dy,
+                                   const T* __restrict__ dskip, long long dskip_ld, T* __restrict__ dx, long long total,
+                                   int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int c = (int)(i % C);
+    long long t1 = i / C;
+    int j = (int)(t1 % Wo);
+    long long t2 = t1 / Wo;
+    int ii = (int)(t2 % Ho);
+    long long bt = t2 / Ho;
+    const long long pix = (bt * H + 2 * ii) * W + 2 * j;
+    const long long offs[4] = {0, 1, (long long)W, (long long)W + 1};
+    float vals[4];
+    int arg = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      vals[k] = to_f(x[(pix + offs[k]) * x_ld + c]);
+      if (vals[k] > vals[arg]) arg = k;  // strict: first maximum wins
+    }
+    const float g = to_f(dy[i]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = (k == arg) ? g : 0.f;
+      if (dskip) v += to_f(dskip[(pix + offs[k]) * dskip_ld + c]);
+      dx[(pix + offs[k]) * C + c] = from_f<T>(v);
+    }
+  }
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(const T* __restrict__ src, long long src_ld, long long src_off, T* __restrict__ dst,
+                                     long long dst_ld, long long dst_off, long long total, int C) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    long long r = i / C;
+    int c = (int)(i % C);
+    dst[r * dst_ld + dst_off + c] = src[r * src_ld + src_off + c];
+  }
+}
+
+// ---------------- latent head ----------------
+__device__ __forceinline__ float softplusf_(float a) { return a > 20.f ? a : log1pf(__expf(a)); }
+
+template <typename T>
+__global__ void softplus_log_fwd_kernel(const T* __restrict__ a, T* __restrict__ lv, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) lv[i] = from_f<T>(__logf(round_to<T>(softplusf_(to_f(a[i])))));
+}
+template <typename T>
+__global__ void softplus_log_bwd_kernel(const T* __restrict__ dlv, const T* __restrict__ a, T* __restrict__ da,
+                                        long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float x = to_f(a[i]);
+    da[i] = from_f<T>(to_f(dlv[i]) * sigmoidf_(x) / softplusf_(x));
+  }
+}
+
+// one block per frame: logit = s1[frame,:] . w2 + b2 + 1 ; p = sigmoid((logit + logistic noise)/temp) ; sel = rint(p)
+template <typename T>
+__global__ void selection_fwd_kernel(const T* __restrict__ s1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                     const float* __restrict__ u, unsigned long long seed, unsigned long long offset,
+                                     int train, float temperature, float* __restrict__ logit, float* __restrict__ p_out,
+                                     float* __restrict__ sel, int hw) {
+  __shared__ float scratch[33];
+  const int f = blockIdx.x;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) acc += to_f(s1[(long long)f * hw + i]) * round_to<T>(w2[i]);
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) {
+    float lg = round_to<T>(round_to<T>(round_to<T>(acc) + round_to<T>(b2[0])) + 1.f);
+    float z = lg;
+    if (train) {
+      float uu = u ? u[f] : u01(Philox(seed)(offset + (unsigned long long)f, 0x5e1ec7ull).x);
+      uu = fminf(fmaxf(uu, 1e-20f), 1.0f - 1e-20f);
+      z += __logf(uu / (1.f - uu));
+    }
+    float p = 1.f / (1.f + expf(-z / temperature));
+    logit[f] = lg;
+    p_out[f] = p;
+    sel[f] = rintf(p);  // round half to even, as jnp.round
+  }
+}
+
+template <typename T>
+__global__ void reparam_gate_fwd_kernel(const T* __restrict__ mean, const T* __restrict__ logvar,
+                                        const float* __restrict__ eps, unsigned long long seed,
+                                        unsigned long long offset, float* __restrict__ eps_out,
+                                        const float* __restrict__ sel, const float* __restrict__ fill,
+                                        float* __restrict__ c32, T* __restrict__ cT, long long n, int tok_per_frame,
+                                        int Dl, int train) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  Philox rng(seed);
+  for (; i < n; i += stride) {
+    const long long tok = i / Dl;
+    const int d = (int)(i % Dl);
+    const float s = sel[tok / tok_per_frame];
+    float z = to_f(mean[i]);
+    if (train) {
+      float e;
+      if (eps) e = eps[i];
+      else {
+        uint4 r = rng(offset + (unsigned long long)i, 0x9a55ull);
+        e = normal_from(r.x, r.y);
+      }
+      if (eps_out) eps_out[i] = e;
+      float sd = round_to<T>(__expf(round_to<T>(to_f(logvar[i]) * 0.5f)));
+      z += e * sd;
+    }
+    float c = fill[d] * (1.f - s) + z * s;
+    if (c32) c32[i] = c;
+    if (cT) cT[i] = from_f<T>(c);
+  }
+}
+
+// blockDim.x is a multiple of Dl: a thread keeps one latent channel d, walks the tokens of one frame slab.
+template <typename T>
+__global__ void reparam_gate_bwd_kernel(const T* __restrict__ dc, const T* __restrict__ mean,
+                                        const T* __restrict__ logvar, const float* __restrict__ eps,
+                                        const float* __restrict__ sel, const float* __restrict__ fill,
+                                        const T* dmean_in, const T* dlogvar_in, T* dmean, T* dlogvar,
+                                        float* __restrict__ dfill, float* __restrict__ dsel, int tok_per_frame, int Dl,
+                                        int train, int slabs) {
+  __shared__ float scratch[33];
+  const int frame = blockIdx.x / slabs, slab = blockIdx.x % slabs;
+  const int d = threadIdx.x % Dl, r = threadIdx.x / Dl, rpi = blockDim.x / Dl;
+  const int per_slab = (tok_per_frame + slabs - 1) / slabs;
+  const int t0 = slab * per_slab, t1 = min(t0 + per_slab, tok_per_frame);
+  const float s = sel[frame], f = fill[d];
+  float afill = 0.f, asel = 0.f;
+  for (int t = t0 + r; t < t1; t += rpi) {
+    const long long i = ((long long)frame * tok_per_frame + t) * Dl + d;
+    const float g = to_f(dc[i]);
+    const float mu = to_f(mean[i]), lv = to_f(logvar[i]);
+    float z = mu, dlv = dlogvar_in ? to_f(dlogvar_in[i]) : 0.f;
+    if (train) {
+      const float sd = round_to<T>(__expf(round_to<T>(lv * 0.5f)));
+      const float e = eps[i];
+      z += e * sd;
+      dlv += g * s * e * 0.5f * sd;
+    }
+    dmean[i] = from_f<T>(g * s + (dmean_in ? to_f(dmean_in[i]) : 0.f));
+    dlogvar[i] = from_f<T>(dlv);
+    afill += g * (1.f - s);
+    asel += g * (z - f);
+  }
+  if (dfill) atomicAdd(dfill + d, afill);  // few blocks per channel; contention is negligible
+  asel = block_sum(asel, scratch);
+  if (threadIdx.x == 0 && dsel) atomicAdd(dsel + frame, asel);
+}
+
+// ---------------- losses ----------------
+// one thread per (b, p) position: time-sum in fp32, rounded to T (XLA reduces bf16 with fp32 accumulation), / len.
+template <typename TV, typename T>
+__global__ void recon_loss_fwd_kernel(const TV* __restrict__ video, const T* __restrict__ recon,
+                                      const float* __restrict__ fmask, const float* __restrict__ inv_len,
+                                      float* __restrict__ out2, int B, int Tn, long long per_frame) {
+  __shared__ float scratch[33];
+  const long long total = (long long)B * per_frame;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float a_sq = 0.f, a_ab = 0.f;
+  for (; i < total; i += stride) {
+    const int b = (int)(i / per_frame);
+    const long long p = i % per_frame;
+    float ssq = 0.f, sab = 0.f;
+    for (int t = 0; t < Tn; ++t) {
+      const float m = fmask[b * Tn + t];
+      if (m == 0.f) continue;
+      const long long idx = ((long long)b * Tn + t) * per_frame + p;
+      float e = round_to<T>(round_to<T>(to_f(video[idx])) - to_f(recon[idx]));
+      ssq += round_to<T>(e * e);
+      sab += fabsf(e);
+    }
+    a_sq += round_to<T>(ssq) * inv_len[b];
+    a_ab += round_to<T>(sab) * inv_len[b];
+  }
+  a_sq = block_sum(a_sq, scratch);
+  a_ab = block_sum(a_ab, scratch);
+  if (threadIdx.x == 0) {
+    atomicAdd(out2, a_sq);
+    atomicAdd(out2 + 1, a_ab);
+  }
+}
+template <typename TV, typename T>
+__global__ void recon_loss_bwd_kernel(const TV* __restrict__ video, const T* __restrict__ recon,
+                                      const float* __restrict__ fmask, const float* __restrict__ inv_len, float w_mse,
+                                      float w_mae, float inv_count, T* __restrict__ drecon, int Tn, long long per_frame,
+                                      long long total) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long frame = i / per_frame;
+    const float m = fmask[frame];
+    float g = 0.f;
+    if (m != 0.f) {
+      float e = round_to<T>(to_f(video[i])) - to_f(recon[i]);
+      float sg = e > 0.f ? 1.f : (e < 0.f ? -1.f : 0.f);
+      g = -(2.f * w_mse * e + w_mae * sg) * inv_len[frame / Tn] * inv_count;
+    }
+    drecon[i] = from_f<T>(g);
+  }
+}
+template <typename T>
+__global__ void kl_fwd_kernel(const T* __restrict__ mean, const T* __restrict__ logvar, const float* __restrict__ frame_w,
+                              float* __restrict__ out1, long long n, long long per_frame_el) {
+  __shared__ float scratch[33];
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (; i < n; i += stride) {
+    const float w = frame_w[i / per_frame_el];
+    if (w == 0.f) continue;
+    const float mu = to_f(mean[i]), lv = to_f(logvar[i]);
+    acc += round_to<T>(0.5f * (__expf(lv) - 1.f - lv + mu * mu)) * w;
+  }
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(out1, acc);
+}
+
+template <typename T>
+__global__ void kl_bwd_kernel(const T* __restrict__ mean, const T* __restrict__ logvar, const float* __restrict__ frame_w,
+                              float scale, T* __restrict__ dmean, T* __restrict__ dlogvar, long long n,
+                              long long per_frame_el) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float w = frame_w[i / per_frame_el] * scale;
+    dmean[i] = from_f<T>(w * to_f(mean[i]));
+    dlogvar[i] = from_f<T>(w * 0.5f * (__expf(to_f(logvar[i])) - 1.f));
+  }
+}
+
+// ---------------- optimizer ----------------
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  __shared__ float scratch[33];
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (; i < n; i += stride) acc += g[i] * g[i];
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
+                            float bc2, const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+  float scale = grad_scale;
+  if (gnorm_sq) {
+    float gn = sqrtf(*gnorm_sq) * grad_scale;
+    if (gn > clip) scale *= clip / gn;  // optax.clip_by_global_norm
+  }
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float gi = g[i] * scale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  }
+}
+
+static inline int ew_blocks(long long n, int threads = 256) { return (int)std::min<long long>(cdiv(n, threads), 148LL * 16); }
+
+}  // namespace vvae
+
+using namespace vvae;
+
+template <typename TI, typename TO>
+static int rearrange_launch(const void* src, void* dst, long long total, int H, int W, int C, int P, int to_tokens,
+                            cudaStream_t s) {
+  rearrange_kernel<TI, TO><<<ew_blocks(total), 256, 0, s>>>((const TI*)src, (TO*)dst, total, H, W, C, P, to_tokens);
+  return check_launch("rearrange");
+}
+template <typename T>
+static int rearrange_same(const void* src, void* dst, long long total, int H, int W, int C, int P, int to_tokens,
+                          cudaStream_t s) {
+  constexpr int V = Vec16<T>::N;
+  if ((P * C) % V == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
+    rearrange_vec_kernel<T><<<ew_blocks(total / V), 256, 0, s>>>((const T*)src, (T*)dst, total / V, H, W, C, P, to_tokens);
+    return check_launch("rearrange_vec");
+  }
+  return rearrange_launch<T, T>(src, dst, total, H, W, C, P, to_tokens, s);
+}
+
+extern "C" {
+
+int vvae_patchify(const void* video, int in_dtype, void* tokens, int b_t, int H, int W, int C, int P, int dtype,
+                  vvae_stream_t stream) {
+  if (b_t <= 0) return VVAE_OK;
+  VVAE_REQUIRE(video && tokens && P > 0 && H % P == 0 && W % P == 0, "patchify: bad arguments (H=%d W=%d P=%d)", H, W, P);
+  const long long total = (long long)b_t * H * W * C;
+  cudaStream_t s = as_stream(stream);
+  if (in_dtype == dtype) {
+    VVAE_DISPATCH_DTYPE(dtype, T, return rearrange_same<T>(video, tokens, total, H, W, C, P, 1, s));
+  }
+  if (in_dtype == VVAE_F32 && dtype == VVAE_BF16) return rearrange_launch<float, bf16>(video, tokens, total, H, W, C, P, 1, s);
+  if (in_dtype == VVAE_BF16 && dtype == VVAE_F32) return rearrange_launch<bf16, float>(video, tokens, total, H, W, C, P, 1, s);
+  VVAE_REQUIRE(false, "patchify: bad dtypes %d -> %d", in_dtype, dtype);
+  return VVAE_ERR_INVALID;
+}
+
+int vvae_pixel_shuffle(const void* src, void* dst, int b_t, int H, int W, int CU, int P, int dir, int dtype,
+                       vvae_stream_t stream) {
+  if (b_t <= 0) return VVAE_OK;
+  VVAE_REQUIRE(src && dst && P > 0 && H % P == 0 && W % P == 0, "pixel_shuffle: bad arguments");
+  const long long total = (long long)b_t * H * W * CU;
+  VVAE_DISPATCH_DTYPE(dtype, T, return rearrange_same<T>(src, dst, total, H, W, CU, P, dir, as_stream(stream)));
+  return VVAE_OK;
+}
+
+int vvae_maxpool122_fwd(const void* x, long long x_ld, void* y, int b_t, int H, int W, int C, int dtype,
+                        vvae_stream_t stream) {
+  if (b_t <= 0) return VVAE_OK;
+  VVAE_REQUIRE(x && y && H % 2 == 0 && W % 2 == 0 && x_ld >= C, "maxpool122_fwd: bad arguments");
+  const long long total = (long long)b_t * (H / 2) * (W / 2) * C;
+  VVAE_DISPATCH_DTYPE(dtype, T, (maxpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+                                    (const T*)x, x_ld, (T*)y, total, H, W, C)));
+  return check_launch("maxpool_fwd");
+}
+
+int vvae_maxpool122_bwd(const void* x, long long x_ld, const void* dy, const void* dskip, long long dskip_ld, void* dx,
+                        int b_t, int H, int W, int C, int dtype, vvae_stream_t stream) {
+  if (b_t <= 0) return VVAE_OK;
+  VVAE_REQUIRE(x && dy && dx && H % 2 == 0 && W % 2 == 0 && x_ld >= C, "maxpool122_bwd: bad arguments");
+  const long long total = (long long)b_t * (H / 2) * (W / 2) * C;
+  VVAE_DISPATCH_DTYPE(dtype, T, (maxpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+                                    (const T*)x, x_ld, (const T*)dy, (const T*)dskip, dskip_ld, (T*)dx, total, H, W, C)));
+  return check_launch("maxpool_bwd");
+}
+
+int vvae_copy_channels(const void* src, long long src_ld, long long src_off, void* dst, long long dst_ld,
+                       long long dst_off, long long rows, int C, int dtype, vvae_stream_t stream) {
+  if (rows <= 0 || C <= 0) return VVAE_OK;
+  VVAE_REQUIRE(src && dst, "copy_channels: null pointer");
+  const long long total = rows * C;
+  VVAE_DISPATCH_DTYPE(dtype, T, (copy_channels_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+                                    (const T*)src, src_ld, src_off, (T*)dst, dst_ld, dst_off, total, C)));
+  return check_launch("copy_channels");
+}
+
+int vvae_softplus_log_fwd(const void* a, void* lv, long long n, int dtype, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(a && lv, "softplus_log_fwd: null pointer");
+  VVAE_DISPATCH_DTYPE(dtype, T, (softplus_log_fwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>((const T*)a, (T*)lv, n)));
+  return check_launch("softplus_log_fwd");
+}
+
+int vvae_softplus_log_bwd(const void* dlv, const void* a, void* da, long long n, int dtype, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(dlv && a && da, "softplus_log_bwd: null pointer");
+  VVAE_DISPATCH_DTYPE(dtype, T, (softplus_log_bwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
+                                    (const T*)dlv, (const T*)a, (T*)da, n)));
+  return check_launch("softplus_log_bwd");
+}
+
+int vvae_selection_fwd(const void* s1, const float* w2, const float* b2, const float* u, unsigned long long seed,
+                       unsigned long long offset, int train, float temperature, float* logit, float* p, float* sel,
+                       int bt, int hw, int dtype, vvae_stream_t stream) {
+  if (bt <= 0) return VVAE_OK;
+  VVAE_REQUIRE(s1 && w2 && b2 && logit && p && sel && hw > 0 && temperature > 0.f, "selection_fwd: bad arguments");
+  VVAE_DISPATCH_DTYPE(dtype, T, (selection_fwd_kernel<T><<<bt, 128, 0, as_stream(stream)>>>(
+                                    (const T*)s1, w2, b2, u, seed, offset, train, temperature, logit, p, sel, hw)));
+  return check_launch("selection_fwd");
+}
+
+int vvae_reparam_gate_fwd(const void* mean, const void* logvar, const float* eps, unsigned long long seed,
+                          unsigned long long offset, float* eps_out, const float* sel, const float* fill, float* c32,
+                          void* cT, long long n_tok, int tok_per_frame, int Dl, int train, int dtype,
+                          vvae_stream_t stream) {
+  if (n_tok <= 0) return VVAE_OK;
+  VVAE_REQUIRE(mean && logvar && sel && fill && (c32 || cT) && tok_per_frame > 0 && Dl > 0, "reparam_gate_fwd: bad arguments");
+  const long long n = n_tok * Dl;
+  VVAE_DISPATCH_DTYPE(dtype, T, (reparam_gate_fwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
+                                    (const T*)mean, (const T*)logvar, eps, seed, offset, eps_out, sel, fill, c32, (T*)cT, n,
+                                    tok_per_frame, Dl, train)));
+  return check_launch("reparam_gate_fwd");
+}
+
+int vvae_reparam_gate_bwd(const void* dc, const void* mean, const void* logvar, const float* eps, const float* sel,
+                          const float* fill, const void* dmean_in, const void* dlogvar_in, void* dmean, void* dlogvar,
+                          float* dfill, float* dsel, long long n_tok, int tok_per_frame, int Dl, int train, int dtype,
+                          vvae_stream_t stream) {
+  if (n_tok <= 0) return VVAE_OK;
+  VVAE_REQUIRE(dc && mean && logvar && sel && fill && dmean && dlogvar && (!train || eps), "reparam_gate_bwd: null pointer");
+  VVAE_REQUIRE(Dl > 0 && Dl <= 1024 && n_tok % tok_per_frame == 0, "reparam_gate_bwd: bad extents");
+  const int frames = (int)(n_tok / tok_per_frame);
+  const int threads = Dl * std::max(1, 256 / Dl);
+  const int slabs = (int)std::max<long long>(1, std::min<long long>(tok_per_frame / (threads / Dl), (148LL * 4) / frames));
+  VVAE_DISPATCH_DTYPE(dtype, T, (reparam_gate_bwd_kernel<T><<<frames * slabs, threads, 0, as_stream(stream)>>>(
+                                    (const T*)dc, (const T*)mean, (const T*)logvar, eps, sel, fill, (const T*)dmean_in,
+                                    (const T*)dlogvar_in, (T*)dmean, (T*)dlogvar, dfill, dsel, tok_per_frame, Dl, train,
+                                    slabs)));
+  return check_launch("reparam_gate_bwd");
+}
+
+int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
+                        const float* inv_len, float* out2, int B, int T, long long per_frame, int dtype,
+                        vvae_stream_t stream) {
+  if (B <= 0) return VVAE_OK;
+  VVAE_REQUIRE(video && recon && frame_mask && inv_len && out2, "recon_loss_fwd: null pointer");
+  const int blocks = ew_blocks((long long)B * per_frame);
+  cudaStream_t s = as_stream(stream);
+#define RL_FWD(TV, TT) recon_loss_fwd_kernel<TV, TT><<<blocks, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask, inv_len, out2, B, T, per_frame)
+  if (video_dtype == VVAE_F32 && dtype == VVAE_F32) RL_FWD(float, float);
+  else if (video_dtype == VVAE_F32 && dtype == VVAE_BF16) RL_FWD(float, bf16);
+  else if (video_dtype == VVAE_BF16 && dtype == VVAE_BF16) RL_FWD(bf16, bf16);
+  else if (video_dtype == VVAE_BF16 && dtype == VVAE_F32) RL_FWD(bf16, float);
+  else VVAE_REQUIRE(false, "recon_loss_fwd: bad dtypes");
+#undef RL_FWD
+  return check_launch("recon_loss_fwd");
+}
+
+int vvae_recon_loss_bwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
+                        const float* inv_len, float w_mse, float w_mae, float inv_count, void* drecon, int B, int T,
+                        long long per_frame, int dtype, vvae_stream_t stream) {
+  if (B <= 0) return VVAE_OK;
+  VVAE_REQUIRE(video && recon && frame_mask && inv_len && drecon, "recon_loss_bwd: null pointer");
+  const long long total = (long long)B * T * per_frame;
+  const int blocks = ew_blocks(total);
+  cudaStream_t s = as_stream(stream);
+#define RL_BWD(TV, TT) recon_loss_bwd_kernel<TV, TT><<<blocks, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask, inv_len, w_mse, w_mae, inv_count, (TT*)drecon, T, per_frame, total)
+  if (video_dtype == VVAE_F32 && dtype == VVAE_F32) RL_BWD(float, float);
+  else if (video_dtype == VVAE_F32 && dtype == VVAE_BF16) RL_BWD(float, bf16);
+  else if (video_dtype == VVAE_BF16 && dtype == VVAE_BF16) RL_BWD(bf16, bf16);
+  else if (video_dtype == VVAE_BF16 && dtype == VVAE_F32) RL_BWD(bf16, float);
+  else VVAE_REQUIRE(false, "recon_loss_bwd: bad dtypes");
+#undef RL_BWD
+  return check_launch("recon_loss_bwd");
+}
+
+int vvae_kl_fwd(const void* mean, const void* logvar, const float* frame_w, float* out1, long long n_tok,
+                int tok_per_frame, int Dl, int dtype, vvae_stream_t stream) {
+  if (n_tok <= 0) return VVAE_OK;
+  VVAE_REQUIRE(mean && logvar && frame_w && out1, "kl_fwd: null pointer");
+  const long long n = n_tok * Dl;
+  VVAE_DISPATCH_DTYPE(dtype, T, (kl_fwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
+                                    (const T*)mean, (const T*)logvar, frame_w, out1, n, (long long)tok_per_frame * Dl)));
+  return check_launch("kl_fwd");
+}
+
+int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, void* dmean, void* dlogvar,
+                long long n_tok, int tok_per_frame, int Dl, int dtype, vvae_stream_t stream) {
+  if (n_tok <= 0) return VVAE_OK;
+  VVAE_REQUIRE(mean && logvar && frame_w && dmean && dlogvar, "kl_bwd: null pointer");
+  const long long n = n_tok * Dl;
+  VVAE_DISPATCH_DTYPE(dtype, T, (kl_bwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
+                                    (const T*)mean, (const T*)logvar, frame_w, scale, (T*)dmean, (T*)dlogvar, n,
+                                    (long long)tok_per_frame * Dl)));
+  return check_launch("kl_bwd");
+}
+
+int vvae_sumsq_f32(const float* g, long long n, float* out1, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(g && out1, "sumsq: null pointer");
+  sumsq_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(g, n, out1);
+  return check_launch("sumsq");
+}
+
+int vvae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                   int step, const float* gnorm_sq, float clip, float grad_scale, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(p && g && m && v && step >= 1, "adam_step: bad arguments");
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  adam_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, gnorm_sq, clip, grad_scale);
+  return check_launch("adam_step");
+}
+
+}  // extern "C"

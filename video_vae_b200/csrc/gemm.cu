@@ -1,0 +1,56 @@
+// vvae_gemm: dispatch between the tcgen05 kernel (bf16, aligned shapes) and the generic SIMT kernel.
+#include "gemm_simt.cuh"
+
+namespace vvae {
+bool sm100_gemm_supported(const vvae_gemm_args& a);
+int sm100_gemm(const vvae_gemm_args& a, cudaStream_t s);
+
+template <typename T, typename TO>
+static int gemm_simt_typed(const vvae_gemm_args& a, cudaStream_t s) {
+  EpiStore<TO, T> ep{(TO*)a.C, a.ldc, a.bias, a.epilogue, (const T*)a.aux_in, a.ld_aux_in, (T*)a.aux_out, a.ld_aux_out, 0};
+  int splits = 1;
+  if (a.accumulate) {
+    ep.atomic = 1;
+    long long tiles = cdiv(a.M, SG_BM) * cdiv(a.N, SG_BN);
+    if (tiles < 148 * 2) splits = (int)std::max<long long>(1, std::min<long long>((148 * 4) / tiles, a.K / 256));
+  }
+  const T* A = (const T*)a.A;
+  const T* B = (const T*)a.B;
+  if (!a.transA && !a.transB)
+    return launch_gemm_simt(RowMajorLoader<T>{A, a.lda}, RowMajorLoader<T>{B, a.ldb}, ep, a.M, a.N, a.K, splits, s);
+  if (!a.transA && a.transB)
+    return launch_gemm_simt(RowMajorLoader<T>{A, a.lda}, ColMajorLoader<T>{B, a.ldb}, ep, a.M, a.N, a.K, splits, s);
+  if (a.transA && !a.transB)
+    return launch_gemm_simt(ColMajorLoader<T>{A, a.lda}, RowMajorLoader<T>{B, a.ldb}, ep, a.M, a.N, a.K, splits, s);
+  return launch_gemm_simt(ColMajorLoader<T>{A, a.lda}, ColMajorLoader<T>{B, a.ldb}, ep, a.M, a.N, a.K, splits, s);
+}
+}  // namespace vvae
+
+using namespace vvae;
+
+extern "C" int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream) {
+  VVAE_REQUIRE(args, "vvae_gemm: null args");
+  const vvae_gemm_args& a = *args;
+  VVAE_REQUIRE(a.M >= 0 && a.N >= 0 && a.K >= 0, "vvae_gemm: negative extent");
+  if (a.M == 0 || a.N == 0) return VVAE_OK;
+  VVAE_REQUIRE(a.A && a.B && a.C, "vvae_gemm: null operand");
+  VVAE_REQUIRE(a.dtype == VVAE_F32 || a.dtype == VVAE_BF16, "vvae_gemm: bad dtype %d", a.dtype);
+  VVAE_REQUIRE(a.out_dtype == a.dtype || a.out_dtype == VVAE_F32, "vvae_gemm: out_dtype must be dtype or f32");
+  VVAE_REQUIRE(!a.accumulate || a.out_dtype == VVAE_F32, "vvae_gemm: accumulate needs fp32 output");
+  VVAE_REQUIRE(!a.accumulate || a.epilogue == VVAE_EPI_NONE, "vvae_gemm: accumulate excludes fused epilogues");
+  VVAE_REQUIRE((a.epilogue != VVAE_EPI_RESIDUAL && a.epilogue != VVAE_EPI_DSILU) || a.aux_in,
+               "vvae_gemm: epilogue %d needs aux_in", a.epilogue);
+  cudaStream_t s = as_stream(stream);
+  const bool tc_ok = sm100_gemm_supported(a);
+  if (a.backend == VVAE_BACKEND_TCGEN05) {
+    if (!tc_ok) {
+      set_error("vvae_gemm: shape/alignment not supported by the tcgen05 path (M=%d N=%d K=%d)", a.M, a.N, a.K);
+      return VVAE_ERR_UNSUPPORTED;
+    }
+    return sm100_gemm(a, s);
+  }
+  if (a.backend == VVAE_BACKEND_AUTO && tc_ok) return sm100_gemm(a, s);
+  if (a.dtype == VVAE_F32) return gemm_simt_typed<float, float>(a, s);
+  if (a.out_dtype == VVAE_F32) return gemm_simt_typed<bf16, float>(a, s);
+  return gemm_simt_typed<bf16, bf16>(a, s);
+}

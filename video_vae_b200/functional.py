@@ -1,0 +1,464 @@
+"""Autograd shell: one torch.autograd.Function per fused block of the hot path, each with a hand-written backward
+made of libvvae kernels (video_vae_b200/ops.py).  PyTorch contributes tensors, the autograd tape between blocks and
+a handful of scalar ops on [b,t]-sized bookkeeping tensors; all arithmetic on activations and parameters is ours.
+
+Conventions
+  * Parameters are fp32 (Flax layouts: Linear (in,out), conv (kt,kh,kw,Cin,Cout)).  When the compute dtype is bf16 a
+    bf16 shadow copy is made once per parameter version (``shadow``) and used by forward and backward.
+  * Parameter gradients are ACCUMULATED by the kernels straight into ``p.grad`` (fp32; created zero-filled on first
+    use, or a view of a flat buffer when ``flatten_parameters`` was called) and the Functions return None for them,
+    so autograd never runs an add kernel or allocates per-parameter gradient tensors.
+  * Residual adds are fused: block Functions compute ``x + f(LN(x))`` and their backward emits a single dx.
+"""
+import math
+import weakref
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from ._ffi import EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, require_device
+
+# ------------------------------------------------------------------ parameter shadows / gradient buffers
+_shadow_cache = weakref.WeakKeyDictionary()
+_grad_hooks = []  # callables(list_of_params) invoked after a backward Function has finished writing their grads
+
+
+def shadow(p, dtype):
+    """Compute-dtype copy of an fp32 parameter, refreshed when the parameter changes (in-place version bump)."""
+    if p is None:
+        return None
+    if p.dtype == dtype:
+        return p.detach()
+    ent = _shadow_cache.get(p)
+    if ent is not None and ent[0] == p._version and ent[1] == p.data_ptr() and ent[2].dtype == dtype:
+        return ent[2]
+    t = ops.cast(p.detach(), dtype)
+    _shadow_cache[p] = (p._version, p.data_ptr(), t)
+    return t
+
+
+def invalidate_shadows():
+    _shadow_cache.clear()
+
+
+def grad_buf(p):
+    """fp32 accumulation buffer for d(loss)/dp; kernels add into it."""
+    if p.grad is None:
+        p.grad = ops.zeros_f32(p.shape, p.device)
+    return p.grad
+
+
+def _notify(params):
+    for h in _grad_hooks:
+        h(params)
+
+
+def _as_2d(x, D):
+    x2 = x.reshape(-1, D)
+    return x2 if x2.is_contiguous() else x2.contiguous()
+
+
+# ------------------------------------------------------------------ Linear
+class LinearFn(Function):
+    """y = x @ K + b (nnx.Linear); x may arrive in another float dtype (cast to the compute dtype first)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias, dtype):
+        require_device()
+        K, N = kernel.shape
+        x2 = _as_2d(x, K)
+        ctx.in_dtype = x2.dtype
+        if x2.dtype != dtype:
+            x2 = ops.cast(x2, dtype)
+        w = shadow(kernel, dtype)
+        y = ops.gemm(x2, w, bias=bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x2, kernel, bias)
+        ctx.dtype = dtype
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, kernel, bias = ctx.saved_tensors
+        K, N = kernel.shape
+        dy2 = _as_2d(dy, N)
+        if dy2.dtype != ctx.dtype:
+            dy2 = ops.cast(dy2, ctx.dtype)
+        ops.gemm(x2, dy2, transA=True, out=grad_buf(kernel), accumulate=True)
+        if bias is not None:
+            ops.colsum_accum(dy2, grad_buf(bias))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dy2, shadow(kernel, ctx.dtype), transB=True)
+            if dx.dtype != ctx.in_dtype:
+                dx = ops.cast(dx, ctx.in_dtype)
+            dx = dx.view(ctx.x_shape)
+        _notify([kernel, bias])
+        return dx, None, None, None
+
+
+# ------------------------------------------------------------------ LayerNorm (standalone)
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, scale, bias, dtype):
+        require_device()
+        D = x.shape[-1]
+        x2 = _as_2d(x, D)
+        if x2.dtype != dtype:
+            x2 = ops.cast(x2, dtype)
+        y, mean, rstd = ops.layernorm_fwd(x2, scale.detach() if scale is not None else None,
+                                          bias.detach() if bias is not None else None)
+        ctx.save_for_backward(x2, mean, rstd, scale, bias)
+        ctx.x_shape, ctx.in_dtype = x.shape, x.dtype
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, scale, bias = ctx.saved_tensors
+        dy2 = _as_2d(dy, x2.shape[1])
+        dx = ops.layernorm_bwd(dy2, x2, mean, rstd, scale.detach() if scale is not None else None, None,
+                               grad_buf(scale) if scale is not None else None,
+                               grad_buf(bias) if bias is not None else None)
+        if dx.dtype != ctx.in_dtype:
+            dx = ops.cast(dx, ctx.in_dtype)
+        _notify([scale, bias])
+        return dx.view(ctx.x_shape), None, None, None
+
+
+# ------------------------------------------------------------------ attention block
+class AttnCfg:
+    """Static description of one attention call: sequence geometry, heads, RoPE position rule, mask."""
+
+    def __init__(self, geom, heads, hd, pos_div, pos_mod, mask, residual, dtype):
+        self.geom, self.heads, self.hd = geom, heads, hd
+        self.pos_div, self.pos_mod = pos_div, pos_mod
+        self.mask, self.residual, self.dtype = mask, residual, dtype
+        self.scale = 1.0 / math.sqrt(hd)
+
+
+class AttnBlockFn(Function):
+    """[x +] out_proj(attention(rope(qknorm(qkv_proj(LN(x)))))) -- train/layers.py:158-171 (+ residual of :214,220)."""
+
+    @staticmethod
+    def forward(ctx, x, cfg, ln_g, ln_b, w_qkv, b_qkv, q_scale, k_scale, w_o, b_o, cos, sin):
+        require_device()
+        D = x.shape[-1]
+        dtp = cfg.dtype
+        x2 = _as_2d(x, D)
+        if x2.dtype != dtp:
+            x2 = ops.cast(x2, dtp)
+        Q = cfg.heads * cfg.hd
+        h, mean, rstd = ops.layernorm_fwd(x2, ln_g.detach(), ln_b.detach())
+        qkv = ops.gemm(h, shadow(w_qkv, dtp), bias=b_qkv.detach())
+        qk = ops.qknorm_rope_fwd(qkv, q_scale.detach(), k_scale.detach(), cos, sin, cfg.heads, cfg.hd, cfg.pos_div,
+                                 cfg.pos_mod)
+        o, lse = ops.attn_fwd(cfg.geom, cfg.heads, cfg.hd, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], cfg.mask, cfg.scale)
+        if cfg.residual:
+            y = ops.gemm(o, shadow(w_o, dtp), bias=b_o.detach(), epilogue=EPI_RESIDUAL, aux_in=x2)
+        else:
+            y = ops.gemm(o, shadow(w_o, dtp), bias=b_o.detach())
+        ctx.save_for_backward(x2, mean, rstd, h, qkv, qk, o, lse, ln_g, ln_b, w_qkv, b_qkv, q_scale, k_scale, w_o, b_o,
+                              cos, sin)
+        ctx.cfg = cfg
+        ctx.x_shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x2, mean, rstd, h, qkv, qk, o, lse, ln_g, ln_b, w_qkv, b_qkv, q_scale, k_scale, w_o, b_o, cos,
+         sin) = ctx.saved_tensors
+        cfg = ctx.cfg
+        dtp = cfg.dtype
+        D = x2.shape[1]
+        Q = cfg.heads * cfg.hd
+        dy2 = _as_2d(dy, D)
+        # out projection
+        ops.gemm(o, dy2, transA=True, out=grad_buf(w_o), accumulate=True)
+        ops.colsum_accum(dy2, grad_buf(b_o))
+        d_o = ops.gemm(dy2, shadow(w_o, dtp), transB=True)
+        # attention core -> dq | dk | dv written side by side
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(cfg.geom, cfg.heads, cfg.hd, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], o, lse, d_o, dqkv[:, :Q],
+                     dqkv[:, Q:2 * Q], dqkv[:, 2 * Q:], cfg.mask, cfg.scale)
+        ops.qknorm_rope_bwd_(dqkv, qkv, q_scale.detach(), k_scale.detach(), cos, sin, grad_buf(q_scale),
+                             grad_buf(k_scale), cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod)
+        # qkv projection
+        ops.gemm(h, dqkv, transA=True, out=grad_buf(w_qkv), accumulate=True)
+        ops.colsum_accum(dqkv, grad_buf(b_qkv))
+        dh = ops.gemm(dqkv, shadow(w_qkv, dtp), transB=True)
+        dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if cfg.residual else None, grad_buf(ln_g),
+                               grad_buf(ln_b), out=dh)
+        _notify([ln_g, ln_b, w_qkv, b_qkv, q_scale, k_scale, w_o, b_o])
+        return (dx.view(ctx.x_shape),) + (None,) * 11
+
+
+# ------------------------------------------------------------------ MLP block
+class MlpBlockFn(Function):
+    """[x +] linear2(silu(linear1(LN(x)))) -- train/layers.py:191-196 (+ residual of :215,221)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, dtype, ln_g, ln_b, w1, b1, w2, b2):
+        require_device()
+        D = x.shape[-1]
+        x2 = _as_2d(x, D)
+        if x2.dtype != dtype:
+            x2 = ops.cast(x2, dtype)
+        h, mean, rstd = ops.layernorm_fwd(x2, ln_g.detach(), ln_b.detach())
+        u = torch.empty((x2.shape[0], w1.shape[1]), dtype=dtype, device=x2.device)
+        a = ops.gemm(h, shadow(w1, dtype), bias=b1.detach(), epilogue=EPI_SILU, aux_out=u)
+        if residual:
+            y = ops.gemm(a, shadow(w2, dtype), bias=b2.detach(), epilogue=EPI_RESIDUAL, aux_in=x2)
+        else:
+            y = ops.gemm(a, shadow(w2, dtype), bias=b2.detach())
+        ctx.save_for_backward(x2, mean, rstd, h, u, a, ln_g, ln_b, w1, b1, w2, b2)
+        ctx.residual, ctx.dtype, ctx.x_shape = residual, dtype, x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, h, u, a, ln_g, ln_b, w1, b1, w2, b2 = ctx.saved_tensors
+        dtp = ctx.dtype
+        dy2 = _as_2d(dy, x2.shape[1])
+        ops.gemm(a, dy2, transA=True, out=grad_buf(w2), accumulate=True)
+        ops.colsum_accum(dy2, grad_buf(b2))
+        du = ops.gemm(dy2, shadow(w2, dtp), transB=True, epilogue=EPI_DSILU, aux_in=u)
+        ops.gemm(h, du, transA=True, out=grad_buf(w1), accumulate=True)
+        ops.colsum_accum(du, grad_buf(b1))
+        dh = ops.gemm(du, shadow(w1, dtp), transB=True)
+        dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if ctx.residual else None, grad_buf(ln_g),
+                               grad_buf(ln_b), out=dh)
+        _notify([ln_g, ln_b, w1, b1, w2, b2])
+        return (dx.view(ctx.x_shape),) + (None,) * 8
+
+
+# ------------------------------------------------------------------ patch embedding / un-embedding
+class PatchEmbedFn(Function):
+    """rearrange -> cast -> LayerNorm -> Linear (train/layers.py:20-27).  The video needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, video, P, dtype, ln_g, ln_b, kernel, bias):
+        require_device()
+        tok = ops.patchify(video, P, dtype)
+        b, t, hw, D = tok.shape
+        tok2 = tok.view(-1, D)
+        h, mean, rstd = ops.layernorm_fwd(tok2, ln_g.detach(), ln_b.detach())
+        y = ops.gemm(h, shadow(kernel, dtype), bias=bias.detach())
+        ctx.save_for_backward(tok2, mean, rstd, h, ln_g, ln_b, kernel, bias)
+        ctx.dtype = dtype
+        return y.view(b, t, hw, kernel.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        tok2, mean, rstd, h, ln_g, ln_b, kernel, bias = ctx.saved_tensors
+        dy2 = _as_2d(dy, kernel.shape[1])
+        ops.gemm(h, dy2, transA=True, out=grad_buf(kernel), accumulate=True)
+        ops.colsum_accum(dy2, grad_buf(bias))
+        dh = ops.gemm(dy2, shadow(kernel, ctx.dtype), transB=True)
+        ops.layernorm_bwd(dh, tok2, mean, rstd, ln_g.detach(), None, grad_buf(ln_g), grad_buf(ln_b), out=dh)
+        _notify([ln_g, ln_b, kernel, bias])
+        return (None,) * 7
+
+
+class UnembedFn(Function):
+    """Linear -> Linear(x u) -> pixel shuffle -> per-pixel Linear(C*u -> C)  (train/layers.py:45-55).
+    Returns (features [b,t,H,W,C*u], rgb [b,t,H,W,C])."""
+
+    @staticmethod
+    def forward(ctx, x, geo, dtype, wl, bl, wu, bu, wd, bd):
+        require_device()
+        b, t, H, W, P, CU = geo
+        D = x.shape[-1]
+        x2 = _as_2d(x, D)
+        y1 = ops.gemm(x2, shadow(wl, dtype), bias=bl.detach())
+        y2 = ops.gemm(y1, shadow(wu, dtype), bias=bu.detach())
+        feats = ops.pixel_shuffle(y2, b * t, H, W, CU, P, to_tokens=False)
+        rgb = ops.gemm(feats.view(-1, CU), shadow(wd, dtype), bias=bd.detach())
+        ctx.save_for_backward(x2, y1, feats, wl, bl, wu, bu, wd, bd)
+        ctx.geo, ctx.dtype, ctx.x_shape = geo, dtype, x.shape
+        Cc = wd.shape[1]
+        return feats.view(b, t, H, W, CU), rgb.view(b, t, H, W, Cc)
+
+    @staticmethod
+    def backward(ctx, dfeats, drgb):
+        x2, y1, feats, wl, bl, wu, bu, wd, bd = ctx.saved_tensors
+        b, t, H, W, P, CU = ctx.geo
+        dtp = ctx.dtype
+        Cc = wd.shape[1]
+        f2 = feats.view(-1, CU)
+        if drgb is not None:
+            drgb2 = _as_2d(drgb, Cc)
+            ops.gemm(f2, drgb2, transA=True, out=grad_buf(wd), accumulate=True)
+            ops.colsum_accum(drgb2, grad_buf(bd))
+            if dfeats is not None:
+                df = ops.gemm(drgb2, shadow(wd, dtp), transB=True, epilogue=EPI_RESIDUAL, aux_in=_as_2d(dfeats, CU))
+            else:
+                df = ops.gemm(drgb2, shadow(wd, dtp), transB=True)
+        else:
+            df = _as_2d(dfeats, CU)
+        dy2 = ops.pixel_shuffle(df, b * t, H, W, CU, P, to_tokens=True)
+        ops.gemm(y1, dy2, transA=True, out=grad_buf(wu), accumulate=True)
+        ops.colsum_accum(dy2, grad_buf(bu))
+        dy1 = ops.gemm(dy2, shadow(wu, dtp), transB=True)
+        ops.gemm(x2, dy1, transA=True, out=grad_buf(wl), accumulate=True)
+        ops.colsum_accum(dy1, grad_buf(bl))
+        dx = ops.gemm(dy1, shadow(wl, dtp), transB=True)
+        _notify([wl, bl, wu, bu, wd, bd])
+        return (dx.view(ctx.x_shape),) + (None,) * 8
+
+
+# ------------------------------------------------------------------ encoder head, reparameterisation, loss
+class EncoderHeadFn(Function):
+    """mean / log-variance heads and the Gumbel-sigmoid frame gate (train/model.py:53-59, train/layers.py:238-252).
+    Returns (mean [b,t,hw,Dl], logvar, selection [b,t,1,1] fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype, train, temperature, u, seed, offset, wm, bm, wv, bv, w1, b1, w2, b2):
+        require_device()
+        b, t, hw, D = x.shape
+        x2 = _as_2d(x, D)
+        mean = ops.gemm(x2, shadow(wm, dtype), bias=bm.detach())
+        a = ops.gemm(x2, shadow(wv, dtype), bias=bv.detach())
+        lv = ops.softplus_log_fwd(a)
+        s1 = ops.gemm(mean, shadow(w1, dtype), bias=b1.detach())                  # [N,1]
+        if w2.shape[0] != hw:
+            raise ValueError(f"selection_layer2 expects {w2.shape[0]} spatial tokens, got {hw}")
+        logit, p, sel = ops.selection_fwd(s1, w2.detach().reshape(-1), b2.detach(), u, seed, offset, train, temperature,
+                                          b * t, hw)
+        ctx.save_for_backward(x2, mean, a, s1, p, wm, bm, wv, bv, w1, b1, w2, b2)
+        ctx.dtype, ctx.train, ctx.temperature, ctx.shape = dtype, train, temperature, (b, t, hw, D)
+        Dl = wm.shape[1]
+        return mean.view(b, t, hw, Dl), lv.view(b, t, hw, Dl), sel.view(b, t, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dmean, dlv, dsel):
+        x2, mean, a, s1, p, wm, bm, wv, bv, w1, b1, w2, b2 = ctx.saved_tensors
+        b, t, hw, D = ctx.shape
+        dtp = ctx.dtype
+        Dl = wm.shape[1]
+        dmean2 = _as_2d(dmean, Dl) if dmean is not None else None
+        if dmean2 is not None and dmean2.dtype != dtp:
+            dmean2 = ops.cast(dmean2, dtp)
+        if dsel is not None:
+            # round_ste passes the gradient through; d sigmoid((a+g)/T) = p(1-p)/T          [b*t scalars: torch glue]
+            da_sel = dsel.reshape(-1).float() * p * (1.0 - p) / ctx.temperature           # [bt]
+            s1f = s1.view(b * t, hw)
+            w2f = w2.detach().reshape(-1)
+            ds1 = (da_sel[:, None] * w2f[None, :]).to(dtp).reshape(-1, 1).contiguous()    # [N,1]
+            grad_buf(w2).view(-1).add_((s1f.float() * da_sel[:, None]).sum(0))
+            grad_buf(b2).view(-1).add_(da_sel.sum())
+            ops.gemm(mean, ds1, transA=True, out=grad_buf(w1), accumulate=True)
+            ops.colsum_accum(ds1, grad_buf(b1))
+            if dmean2 is not None:
+                dmean2 = ops.gemm(ds1, shadow(w1, dtp), transB=True, epilogue=EPI_RESIDUAL, aux_in=dmean2)
+            else:
+                dmean2 = ops.gemm(ds1, shadow(w1, dtp), transB=True)
+        dx = None
+        if dmean2 is not None:
+            ops.gemm(x2, dmean2, transA=True, out=grad_buf(wm), accumulate=True)
+            ops.colsum_accum(dmean2, grad_buf(bm))
+            dx = ops.gemm(dmean2, shadow(wm, dtp), transB=True)
+        if dlv is not None:
+            dlv2 = _as_2d(dlv, Dl)
+            if dlv2.dtype != dtp:
+                dlv2 = ops.cast(dlv2, dtp)
+            da = ops.softplus_log_bwd(dlv2, a)
+            ops.gemm(x2, da, transA=True, out=grad_buf(wv), accumulate=True)
+            ops.colsum_accum(da, grad_buf(bv))
+            if dx is not None:
+                dx = ops.gemm(da, shadow(wv, dtp), transB=True, epilogue=EPI_RESIDUAL, aux_in=dx)
+            else:
+                dx = ops.gemm(da, shadow(wv, dtp), transB=True)
+        if dx is None:
+            dx = torch.zeros_like(x2)
+        _notify([wm, bm, wv, bv, w1, b1, w2, b2])
+        return (dx.view(b, t, hw, D),) + (None,) * 14
+
+
+class ReparamGateFn(Function):
+    """z = mean + eps*exp(lv/2); c = fill*(1-sel) + z*sel  (train/model.py:124-133).
+    Returns (c fp32 -- what the reference returns --, c in the compute dtype for the decoder)."""
+
+    @staticmethod
+    def forward(ctx, mean, logvar, sel, fill, eps, seed, offset, train):
+        require_device()
+        b, t, hw, Dl = mean.shape
+        lowp = mean.dtype != torch.float32
+        c32, cT, eps_used = ops.reparam_gate_fwd(mean.contiguous(), logvar.contiguous(), eps, seed, offset,
+                                                 sel.reshape(-1).contiguous(), fill.detach().reshape(-1), hw, train, lowp)
+        ctx.save_for_backward(mean, logvar, sel, fill, eps_used if eps_used is not None else mean.new_empty(0))
+        ctx.train, ctx.hw = train, hw
+        return c32, (cT if lowp else None)
+
+    @staticmethod
+    def backward(ctx, dc32, dcT):
+        mean, logvar, sel, fill, eps = ctx.saved_tensors
+        if dcT is None and dc32 is None:
+            return (None,) * 8
+        if dcT is not None and dc32 is not None and dcT.data_ptr() != dc32.data_ptr():
+            dc = dcT + dc32.to(dcT.dtype)
+        else:
+            dc = dcT if dcT is not None else dc32
+        if dc.dtype != mean.dtype:
+            dc = ops.cast(dc.contiguous(), mean.dtype)
+        dsel = ops.zeros_f32((sel.numel(),), mean.device)
+        dmean, dlogvar = ops.reparam_gate_bwd(dc.contiguous(), mean, logvar, eps if ctx.train else None,
+                                              sel.reshape(-1).contiguous(), fill.detach().reshape(-1), None, None,
+                                              grad_buf(fill).view(-1), dsel, ctx.hw, ctx.train)
+        _notify([fill])
+        return dmean, (dlogvar if ctx.train else None), dsel.view(sel.shape), None, None, None, None, None
+
+
+def magnify_negatives(x, rate):
+    return torch.where(x < 0, x * rate, x)
+
+
+class VaeLossFn(Function):
+    """loss_fn of train/legacy/training_loop_adversarial.py:90-124 (+ optional MAE term, rl_nonadversarial.py:114-117).
+    Returns (loss, MSE, MAE, selection_loss, kl_loss, kept_frame_density) -- only ``loss`` is differentiable."""
+
+    @staticmethod
+    def forward(ctx, video, recon, sel, logvar, mean, mask_bt, hp):
+        require_device()
+        B, T = mask_bt.shape
+        dev = recon.device
+        m = mask_bt.to(torch.float32)
+        seq = torch.clamp(m.sum(dim=1), min=1.0)
+        inv_len = (1.0 / seq).contiguous()
+        frame_w = (m * inv_len[:, None]).reshape(-1).contiguous()
+        sums = ops.zeros_f32((3,), dev)
+        video = video.contiguous()
+        recon = recon.contiguous()
+        ops.recon_loss_fwd(video, recon, m.reshape(-1).contiguous(), inv_len, sums[:2])
+        hw = mean.shape[2]
+        ops.kl_fwd(mean.contiguous(), logvar.contiguous(), frame_w, sums[2:], hw)
+        count = float(B * (video.numel() // (B * T)))
+        mse, mae = sums[0] / count, sums[1] / count
+        kl = sums[2] / float(mean.numel())
+        density = (sel.reshape(B, T).to(torch.float32) * m).sum(dim=1) * inv_len
+        diff = density - 1.0 / hp["max_compression_rate"]
+        mag = magnify_negatives(diff, hp["magnify_negatives_rate"])
+        sel_loss = torch.square(mag).mean()
+        g4 = hp.get("gamma4", 0.0)
+        loss = mse + hp["gamma1"] * sel_loss + hp["gamma2"] * kl + g4 * mae
+        ctx.save_for_backward(video, recon, sel, logvar, mean, m, inv_len, frame_w, diff)
+        ctx.hp, ctx.count = hp, count
+        dens = density.mean()
+        ctx.mark_non_differentiable(mse, mae, sel_loss, kl, dens)
+        return loss, mse, mae, sel_loss, kl, dens
+
+    @staticmethod
+    def backward(ctx, gl, *unused):
+        video, recon, sel, logvar, mean, m, inv_len, frame_w, diff = ctx.saved_tensors
+        hp = ctx.hp
+        B, T = m.shape
+        # TODO(perf): gl is read on the host (one sync per step); pass it as a device scalar instead.
+        g = float(gl)
+        drecon = ops.recon_loss_bwd(video, recon, m.reshape(-1).contiguous(), inv_len, g, g * hp.get("gamma4", 0.0),
+                                    1.0 / ctx.count)
+        dmean, dlogvar = ops.kl_bwd(mean, logvar, frame_w, g * hp["gamma2"] / float(mean.numel()), mean.shape[2])
+        rate = hp["magnify_negatives_rate"]
+        slope = torch.where(diff < 0, torch.full_like(diff, rate), torch.ones_like(diff))
+        ddens = (g * hp["gamma1"] / B) * 2.0 * (diff * slope) * slope                      # [B]
+        dsel = (ddens[:, None] * m * inv_len[:, None]).reshape(sel.shape).to(sel.dtype)
+        return None, drecon, dsel, dlogvar, dmean, None, None
