@@ -20,7 +20,7 @@ from . import ops
 from ._ffi import EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, require_device
 
 # ------------------------------------------------------------------ parameter shadows / gradient buffers
-_shadow_cache = weakref.WeakKeyDictionary()
+_shadow_cache = {}  # id(param) -> (weakref(param), version, data_ptr, shadow tensor)
 _grad_hooks = []  # callables(list_of_params) invoked after a backward Function has finished writing their grads
 
 
@@ -30,11 +30,13 @@ def shadow(p, dtype):
         return None
     if p.dtype == dtype:
         return p.detach()
-    ent = _shadow_cache.get(p)
-    if ent is not None and ent[0] == p._version and ent[1] == p.data_ptr() and ent[2].dtype == dtype:
-        return ent[2]
+    key = id(p)
+    ent = _shadow_cache.get(key)
+    if (ent is not None and ent[0]() is p and ent[1] == p._version and ent[2] == p.data_ptr()
+            and ent[3].dtype == dtype):
+        return ent[3]
     t = ops.cast(p.detach(), dtype)
-    _shadow_cache[p] = (p._version, p.data_ptr(), t)
+    _shadow_cache[key] = (weakref.ref(p, lambda _r, k=key: _shadow_cache.pop(k, None)), p._version, p.data_ptr(), t)
     return t
 
 
