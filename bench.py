@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""Headline benchmark: train clips/sec of the video-VAE hot path (fwd + loss + bwd [+ all-reduce] + Adam) at
+16x256x256, bf16, batch 8 per GPU (BASELINE.json configs[1]), production hyper-parameters
+(train/rl_nonadversarial.py:234-236).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.  `--impl reference` times the
+CPU oracle (the reference is JAX/Flax and cannot be installed offline) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PROD = dict(patch_size=16, encoder_depth=9, decoder_depth=12, mlp_dim=1536, num_heads=8, qkv_features=512,
+            max_temporal_len=64, spatial_compression_rate=8, unembedding_upsample_rate=4)
+METRIC = "train clips/sec at 16x256x256 fwd+bwd"
+FLOP_PER_CLIP = {256: 5.10e12, 128: 1.25e12}   # SURVEY.md section 8(d), fwd+bwd = 3x fwd, remat not counted
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="clips per GPU")
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--enc-depth", type=int, default=PROD["encoder_depth"])
+    ap.add_argument("--dec-depth", type=int, default=PROD["decoder_depth"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- CPU oracle arm
+def oracle_step_time(size, frames, steps, warmup, enc, dec, threads):
+    import torch
+    from oracle import Rngs as ORngs
+    from oracle.losses import DEFAULT_HPARAMS, loss_fn
+    from oracle.model import VideoVAE as OVAE
+    torch.set_num_threads(threads)
+    m = OVAE(size, size, 3, PROD["patch_size"], enc, dec, PROD["mlp_dim"], PROD["num_heads"], PROD["qkv_features"],
+             PROD["max_temporal_len"], PROD["spatial_compression_rate"], PROD["unembedding_upsample_rate"], ORngs(2))
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(1, frames, size, size, 3, generator=g)
+    mask = torch.ones(1, frames, dtype=torch.bool)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in m.parameters():
+            p.grad = None
+        loss, _ = loss_fn(m, x, mask[:, None, None, :], mask, ORngs(i), DEFAULT_HPARAMS)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def cpu_sample(args, total_steps, budget_s=170.0):
+    """Pick the bounded sample: one full 16xSxS clip if the budget allows, else a 128x128 crop (FLOP-scaled)."""
+    per_step = budget_s / max(1, total_steps)
+    if args.size <= 128 or per_step >= 25.0:
+        return args.size, 1.0, f"1 clip of {args.frames}x{args.size}x{args.size} per step, fp32, fwd+loss+bwd"
+    scale = FLOP_PER_CLIP[128] / FLOP_PER_CLIP[256]
+    return 128, scale, (f"1 crop of {args.frames}x128x128 per step, fp32, fwd+loss+bwd; clips/s scaled by the "
+                        f"algorithmic FLOP ratio {scale:.3f} (1.25/5.10 TFLOP per clip) to 16x256x256 clips")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    size, scale, sample = cpu_sample(args, args.steps + args.warmup)
+    t = oracle_step_time(size, args.frames, args.steps, args.warmup, args.enc_depth, args.dec_depth, threads)
+    value = scale / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"VideoVAE train step {args.frames}x{args.size}x{args.size}, CPU oracle port of the "
+                               "JAX/Flax reference (JAX not installable offline)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import video_vae_b200 as V
+    from video_vae_b200 import _ffi, ops
+    from video_vae_b200.ddp import FlatAdam, FlatParams, GradAllReducer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _ffi.require_device()
+
+    S, Tn, B = args.size, args.frames, args.batch
+    model = V.VideoVAE(S, S, 3, PROD["patch_size"], args.enc_depth, args.dec_depth, PROD["mlp_dim"], PROD["num_heads"],
+                       PROD["qkv_features"], PROD["max_temporal_len"], PROD["spatial_compression_rate"],
+                       PROD["unembedding_upsample_rate"], V.Rngs(2), dtype=torch.bfloat16, device=dev)
+    with torch.no_grad():   # exercise the UNet backward (the reference zero-inits final_conv: SURVEY.md 7.3)
+        model.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7))
+    flat = FlatParams(model)
+    flat.enable_bf16_shadow()
+    reducer = GradAllReducer(flat) if world > 1 else None
+    opt = None if args.no_optimizer else FlatAdam(flat, lr=5e-5)
+    hp = dict(V.DEFAULT_HPARAMS, gamma4=0.1)   # MSE + selection + KL + MAE terms
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_video = torch.rand(B, Tn, S, S, 3, generator=g).to(torch.bfloat16).pin_memory()   # reference casts to bf16 on host
+    host_mask = torch.ones(B, Tn, dtype=torch.bool).pin_memory()
+    video = host_video.to(dev, non_blocking=True)
+    mask = host_mask.to(dev, non_blocking=True)
+    rngs = V.Rngs(3 + rank)
+
+    def step(v, m):
+        flat.zero_grad()
+        if reducer:
+            reducer.start_step()
+        loss, aux = V.loss_fn(model, v, m[:, None, None, :], m, rngs, hp, train=True)
+        loss.backward()
+        if reducer:
+            reducer.finish_step()
+        if opt:
+            opt.step(grad_scale=1.0 / world)
+        return loss
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(video, mask)
+    sync_all()
+
+    # ---- device-resident timed region, with per-launch CUDA events on the dominant kernel class (GEMM)
+    clocks = ClockSampler(local) if rank == 0 else None
+    ops.PROFILE = []
+    calls0 = _ffi.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(video, mask)
+    e1.record()
+    sync_all()
+    calls = _ffi.launch_count - calls0
+    prof, ops.PROFILE = ops.PROFILE, None
+    clock_info = clocks.stop() if clocks else None
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = tms.item()
+    value = world * B / (ms * 1e-3)
+
+    # ---- end-to-end: pinned host batch -> device, step, loss -> host, every step
+    e0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        v = host_video.to(dev, non_blocking=True)
+        m = host_mask.to(dev, non_blocking=True)
+        last = step(v, m).item()
+    e1.record()
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        tms = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms_e2e = tms.item()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class
+    classes = {}
+    for name, flops, nbytes, ev0, ev1 in prof:
+        t = ev0.elapsed_time(ev1) * 1e-3
+        c = classes.setdefault(name, [0.0, 0.0, 0.0, 0])
+        c[0] += t; c[1] += flops; c[2] += nbytes; c[3] += 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    roofline = None
+    table = []
+    for name, (t, fl, nb, n) in sorted(classes.items(), key=lambda kv: -kv[1][0]):
+        table.append({"kernel": name, "launches_per_step": n / args.steps, "ms_per_step": t * 1e3 / args.steps,
+                      "share_of_step": t * 1e3 / args.steps / ms, "tflops": fl / t / 1e12 if t > 0 else 0.0})
+    if args.profile_kernels:
+        for row in table:
+            print(json.dumps(row), file=sys.stderr)
+    if "gemm_tcgen05" in classes:
+        t, fl, nb, n = classes["gemm_tcgen05"]
+        ach = fl / t / 1e12
+        roofline = {"kernel": "gemm_sm100_kernel (tcgen05 bf16 GEMM: every Linear fwd/dgrad/wgrad)", "bound": "tensor",
+                    "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                    if peaks else "fallback", "traffic": None, "launches_per_step": n / args.steps,
+                    "share_of_step": t * 1e3 / args.steps / ms}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"VideoVAE train step (fwd+loss+bwd{'' if args.no_optimizer else '+clip+Adam'}) on "
+                               f"{Tn}x{S}x{S} RGB clips, batch {B}/GPU, enc {args.enc_depth}/dec {args.dec_depth}, "
+                               "mlp 1536, 8 heads x 64, latent 96 (BASELINE.json configs[1])",
+                   "global_batch": world * B, "parallelism": f"dp{world}",
+                   "l2": "inputs+activations per step (tens of GB) >> 126 MB L2; no flush needed",
+                   "model_tflop_per_clip": FLOP_PER_CLIP.get(S)},
+        "model_tflops": (value * FLOP_PER_CLIP[S] / 1e12 / world) if S in FLOP_PER_CLIP else None,
+        "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": host_video.numel() * host_video.element_size() + host_mask.numel(),
+                "d2h_bytes_per_step": 4, "last_loss": last},
+        "gpu_launches": calls, "gpu_launches_note": "libvvae C-ABI kernel-launching calls in the timed region (>= kernels/3)",
+        "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        size, scale, sample = cpu_sample(args, 1)
+        t = oracle_step_time(size, Tn, 1, 0, args.enc_depth, args.dec_depth, threads)
+        line["cpu_baseline"] = {"value": scale / t, "unit": "clips/s", "cores": threads, "kind": "port",
+                                "sample": sample + " (1 step, no warm-up)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -78,6 +78,8 @@ typedef struct vvae_gemm_args {
   int backend;
 } vvae_gemm_args;
 int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream);
+/* 1 if vvae_gemm would run these arguments on the tcgen05 kernel, 0 if on the generic SIMT kernel. */
+int vvae_gemm_uses_tcgen05(const vvae_gemm_args* args);
 
 /* ---- LayerNorm (nnx.LayerNorm eps 1e-6: train/layers.py:17,153,178) ------- */
 int vvae_layernorm_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,

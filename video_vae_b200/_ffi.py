@@ -22,7 +22,7 @@ class VvaeError(RuntimeError):
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        f"{LIB_PATH} not found: build it with `python -m video_vae_b200.build` (nvcc, sm_100a). "
+        f"{LIB_PATH} not found: build it with `python video_vae_b200/build.py` (nvcc, sm_100a). "
         "video_vae_b200 has no CPU or PyTorch fallback path.")
 
 lib = C.CDLL(LIB_PATH)
@@ -80,6 +80,7 @@ _SIGS = {
     "vvae_fill_f32": ([vp, f32, ll, vp], i32),
     "vvae_colsum": ([vp, ll, ll, i32, vp, i32, vp], i32),
     "vvae_gemm": ([C.POINTER(GemmArgs), vp], i32),
+    "vvae_gemm_uses_tcgen05": ([C.POINTER(GemmArgs)], i32),
     "vvae_layernorm_fwd": ([vp, vp, vp, vp, vp, vp, ll, i32, f32, i32, vp], i32),
     "vvae_layernorm_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, vp], i32),
     "vvae_qknorm_rope_fwd": ([vp, vp, vp, vp, vp, vp, ll, i32, i32, ll, i32, f32, i32, vp], i32),

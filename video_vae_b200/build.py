@@ -1,6 +1,6 @@
 """Build libvvae.so (in-tree) with nvcc for sm_100a.
 
-    python -m video_vae_b200.build [--force] [--verbose]
+    python video_vae_b200/build.py [--force] [--verbose]
 
 The shared library is written next to this file (video_vae_b200/libvvae.so); it is git-ignored but travels to
 the GPU box with the repo snapshot.  Objects are cached under video_vae_b200/build/ keyed on source mtime.

@@ -28,6 +28,12 @@ static int gemm_simt_typed(const vvae_gemm_args& a, cudaStream_t s) {
 
 using namespace vvae;
 
+extern "C" int vvae_gemm_uses_tcgen05(const vvae_gemm_args* args) {
+  if (!args) return 0;
+  if (args->backend == VVAE_BACKEND_SIMT) return 0;
+  return sm100_gemm_supported(*args) ? 1 : 0;
+}
+
 extern "C" int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream) {
   VVAE_REQUIRE(args, "vvae_gemm: null args");
   const vvae_gemm_args& a = *args;

@@ -1,0 +1,144 @@
+"""Data-parallel plumbing: flat fp32 parameter / gradient storage, bucketed gradient all-reduce overlapped with
+backward, and the fused Adam step.
+
+Mirrors the DP semantics of claude_distributed/distributed_train.py:107-109,189-196,378-380 (parameters replicated,
+batch sharded, loss = mean over the global batch => gradient all-reduce-mean) with one process per GPU and NCCL over
+NVLink (torch.distributed is the plumbing).  The only collective on the path is the gradient all-reduce; it is issued
+per bucket, in the order backward finishes the buckets (decoder first), on a dedicated stream, so it hides under the
+remaining backward kernels.  The 1/world_size scaling is folded into the optimizer's ``grad_scale``.
+"""
+import torch
+import torch.distributed as dist
+
+from . import functional as F_
+from . import ops
+
+
+class FlatParams:
+    """Re-homes every parameter (and its gradient) of ``model`` into one contiguous fp32 buffer each."""
+
+    def __init__(self, model):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.numel = sum(p.numel() for p in self.params)
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 7) // 8 * 8          # keep every fp32 AND bf16-shadow view 16-byte aligned
+        self.total = off
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        self.shadow = None
+        self._shadow_views = {}
+        F_.invalidate_shadows()
+
+    def zero_grad(self):
+        ops.fill_(self.grad, 0.0)
+
+    def enable_bf16_shadow(self):
+        """Keep ONE flat bf16 copy of all parameters, refreshed by a single cast kernel per optimizer step."""
+        self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=self.flat.device)
+        for p, o in zip(self.params, self.offsets):
+            self._shadow_views[id(p)] = self.shadow[o:o + p.numel()].view(p.shape)
+        F_._flat_shadow_views = self._shadow_views
+        self.refresh_shadow()
+
+    def refresh_shadow(self):
+        if self.shadow is not None:
+            ops.cast_into(self.flat, self.shadow)
+
+
+class GradAllReducer:
+    """Bucketed, backward-overlapped all-reduce (sum) of FlatParams.grad."""
+
+    def __init__(self, flat: FlatParams, bucket_bytes=64 << 20, process_group=None):
+        self.flat = flat
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.stream = torch.cuda.Stream() if flat.flat.is_cuda else None
+        # buckets are contiguous slices of the flat gradient, cut in REVERSE parameter order
+        self.buckets = []      # (start, end, n_params)
+        self.bucket_of = {}
+        cur_end, cur_start, cur_n = flat.total, flat.total, 0
+        for idx in range(len(flat.params) - 1, -1, -1):
+            cur_start = flat.offsets[idx]
+            cur_n += 1
+            self.bucket_of[id(flat.params[idx])] = len(self.buckets)
+            if (cur_end - cur_start) * 4 >= bucket_bytes or idx == 0:
+                self.buckets.append((cur_start, cur_end, cur_n))
+                cur_end, cur_n = cur_start, 0
+        self._pending = None
+        self._handles = []
+        self._seen = None
+        F_._grad_hooks.append(self._on_grads_ready)
+
+    def start_step(self):
+        self._pending = [n for (_, _, n) in self.buckets]
+        self._seen = set()
+        self._handles = []
+
+    def _on_grads_ready(self, params):
+        if self._pending is None or self.world == 1:
+            return
+        for p in params:
+            if p is None or id(p) in self._seen or id(p) not in self.bucket_of:
+                continue
+            self._seen.add(id(p))
+            b = self.bucket_of[id(p)]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._launch(b)
+
+    def _launch(self, b):
+        s, e, _ = self.buckets[b]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            self._handles.append(dist.all_reduce(self.flat.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def finish_step(self):
+        """Flush buckets that never filled (unused parameters) and join the communication stream."""
+        if self.world == 1 or self._pending is None:
+            return
+        for b, n in enumerate(self._pending):
+            if n > 0:
+                self._pending[b] = 0
+                self._launch(b)
+        for h in self._handles:
+            h.wait()
+        torch.cuda.current_stream().wait_stream(self.stream)
+        self._pending = None
+
+    def close(self):
+        if self._on_grads_ready in F_._grad_hooks:
+            F_._grad_hooks.remove(self._on_grads_ready)
+
+
+class FlatAdam:
+    """optax.chain(clip_by_global_norm(clip), adam(lr)) on the flat buffers (train/rl_nonadversarial.py:241-253):
+    one reduction kernel + one update kernel per step, no host synchronisation."""
+
+    def __init__(self, flat: FlatParams, lr=5e-5, b1=0.9, b2=0.999, eps=1e-8, clip=1.0):
+        self.flat, self.lr, self.b1, self.b2, self.eps, self.clip = flat, lr, b1, b2, eps, clip
+        self.m = torch.zeros_like(flat.flat)
+        self.v = torch.zeros_like(flat.flat)
+        self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=flat.flat.device)
+        self.t = 0
+
+    def step(self, grad_scale=1.0, lr=None):
+        self.t += 1
+        ops.fill_(self.gnorm_sq, 0.0)
+        ops.sumsq_accum(self.flat.grad, self.gnorm_sq)
+        ops.adam_step_(self.flat.flat, self.flat.grad, self.m, self.v, self.lr if lr is None else lr, self.b1, self.b2,
+                       self.eps, self.t, self.gnorm_sq, self.clip, grad_scale)
+        if self.flat.shadow is not None:
+            self.flat.refresh_shadow()
+        else:
+            F_.invalidate_shadows()

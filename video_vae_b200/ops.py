@@ -13,6 +13,29 @@ from ._ffi import (BACKEND_AUTO, BF16, EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SI
 
 LN_EPS = 1e-6
 
+# bench.py sets PROFILE to a list; instrumented ops then append (class, flops, bytes, start_event, stop_event).
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("name", "flops", "nbytes", "e0")
+
+    def __init__(self, name, flops, nbytes=0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.nbytes, self.e0, e1))
+        return False
+
 
 def empty(shape, dtype, device):
     return torch.empty(shape, dtype=dtype, device=device)
@@ -66,6 +89,11 @@ def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=Non
                  ptr(aux_in), aux_in.stride(0) if aux_in is not None else 0,
                  ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0,
                  int(accumulate), backend)
+    if PROFILE is not None:
+        name = "gemm_tcgen05" if lib.vvae_gemm_uses_tcgen05(C.byref(a)) else "gemm_simt"
+        with _Prof(name, 2.0 * M * N * K):
+            check(lib.vvae_gemm(C.byref(a), stream()), "vvae_gemm")
+        return out
     check(lib.vvae_gemm(C.byref(a), stream()), "vvae_gemm")
     return out
 
@@ -150,7 +178,8 @@ def attn_fwd(geom, heads, hd, q, k, v, mask, scale):
     o = torch.empty((n_tok, heads * hd), dtype=q.dtype, device=q.device)
     lse = torch.empty((geom.n_seq, heads, geom.L), dtype=torch.float32, device=q.device)
     a = _attn_args(geom, heads, hd, q, k, v, o, lse, mask, scale)
-    check(lib.vvae_attn_fwd(C.byref(a), stream()), "vvae_attn_fwd")
+    with _Prof("attn_fwd_L%d" % geom.L, 4.0 * geom.n_seq * heads * geom.L * geom.L * hd):
+        check(lib.vvae_attn_fwd(C.byref(a), stream()), "vvae_attn_fwd")
     return o, lse
 
 
@@ -161,7 +190,8 @@ def attn_bwd(geom, heads, hd, q, k, v, o, lse, d_o, dq, dk, dv, mask, scale):
     a.dq, a.dk, a.dv = ptr(dq), ptr(dk), ptr(dv)
     a.dq_rs, a.dk_rs, a.dv_rs = dq.stride(0), dk.stride(0), dv.stride(0)
     a.delta = ptr(delta)
-    check(lib.vvae_attn_bwd(C.byref(a), stream()), "vvae_attn_bwd")
+    with _Prof("attn_bwd_L%d" % geom.L, 10.0 * geom.n_seq * heads * geom.L * geom.L * hd):
+        check(lib.vvae_attn_bwd(C.byref(a), stream()), "vvae_attn_bwd")
 
 
 # ---------------------------------------------------------------- rearrangements
@@ -202,7 +232,8 @@ def conv3d_fwd(x, w, bias, ks, Cin, Cout, x_ld=None, residual=None):
     y = torch.empty((B, T, H, W, Cout), dtype=x.dtype, device=x.device)
     a = _conv_args(x, x_ld or x.shape[-1], w, bias, y, Cout, B, T, H, W, Cin, Cout, ks,
                    EPI_RESIDUAL if residual is not None else EPI_NONE, residual, Cout)
-    check(lib.vvae_conv3d_fwd(C.byref(a), stream()), "vvae_conv3d_fwd")
+    with _Prof("conv3d_fwd", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
+        check(lib.vvae_conv3d_fwd(C.byref(a), stream()), "vvae_conv3d_fwd")
     return y
 
 
@@ -210,14 +241,16 @@ def conv3d_dgrad(dy, w, ks, Cin, Cout):
     B, T, H, W = dy.shape[:4]
     dx = torch.empty((B, T, H, W, Cin), dtype=dy.dtype, device=dy.device)
     a = _conv_args(dx, Cin, w, None, dy, dy.shape[-1], B, T, H, W, Cin, Cout, ks)
-    check(lib.vvae_conv3d_dgrad(C.byref(a), stream()), "vvae_conv3d_dgrad")
+    with _Prof("conv3d_dgrad", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
+        check(lib.vvae_conv3d_dgrad(C.byref(a), stream()), "vvae_conv3d_dgrad")
     return dx
 
 
 def conv3d_wgrad_accum(x, dy, dw, ks, Cin, Cout, x_ld=None):
     B, T, H, W = x.shape[:4]
     a = _conv_args(x, x_ld or x.shape[-1], None, None, dy, dy.shape[-1], B, T, H, W, Cin, Cout, ks, dw=dw)
-    check(lib.vvae_conv3d_wgrad(C.byref(a), stream()), "vvae_conv3d_wgrad")
+    with _Prof("conv3d_wgrad", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
+        check(lib.vvae_conv3d_wgrad(C.byref(a), stream()), "vvae_conv3d_wgrad")
 
 
 def convT122_fwd(x, w, bias, Cout, out, out_ld):
