@@ -150,12 +150,18 @@ typedef struct vvae_conv_args {
   float* dw_accum; /* wgrad: fp32 [kt,kh,kw,Cin,Cout], += */
   int dtype;
   int backend;
+  const void* wprep; /* tensor-core path: weight image from vvae_conv3d_wprep (NULL -> generic kernel) */
 } vvae_conv_args;
 int vvae_conv3d_fwd(const vvae_conv_args* args, vvae_stream_t stream);
 /* dgrad: reads dy from args->y (stride y_ld), writes dx to args->x (stride x_ld; cast away const). */
 int vvae_conv3d_dgrad(const vvae_conv_args* args, vvae_stream_t stream);
 /* wgrad: dw_accum += x^T (*) dy with x = args->x, dy = args->y. */
 int vvae_conv3d_wgrad(const vvae_conv_args* args, vvae_stream_t stream);
+/* Tensor-core (tcgen05) path: the weights are re-laid out once per optimizer step into the swizzled per-stage image
+ * the kernel streams with bulk copies.  which = 0 forward, 1 dgrad.  _bytes returns 0 when the shape is not supported
+ * by the tensor-core path (the generic kernel is used then). */
+long long vvae_conv3d_wprep_bytes(const vvae_conv_args* args, int which);
+int vvae_conv3d_wprep(const vvae_conv_args* args, int which, void* out, vvae_stream_t stream);
 
 /* ---- ConvTranspose k=s=(1,2,2) (nnx.ConvTranspose: train/unet.py:61-69) ----
  * x [V,Cin] voxels of a [B_T,H,W] grid; y [B_T,2H,2W,Cout] with channel stride y_ld;

@@ -76,6 +76,13 @@ def run_case(cfg):
         ref = ref * (s * (1 + x * (1 - s)))
     if acc:
         ref = ref + 1.0
+    if cfg.get("row_shift"):
+        rs = cfg["row_shift"]
+        # rows of each 128-row tile should equal the reference rows shifted down by rs (valid while inside the tile)
+        keep = 128 - rs
+        err_s = (Cm.float()[:keep] - ref[rs:rs + keep]).abs()
+        res["shift_max_abs_err"] = err_s.max().item()
+        res["shift_frac_bad"] = (err_s > 0.02 * ref[rs:rs + keep].abs() + 0.05).float().mean().item()
     err = (Cm.float() - ref).abs()
     res["max_abs_err"] = err.max().item()
     res["ref_absmax"] = ref.abs().max().item()
@@ -125,6 +132,11 @@ add("KMN_alt_kadv", M=256, N=256, K=256, tA=0, tB=0, dbg={3: 4096})
 add("KMN_bn64", M=256, N=256, K=256, tA=0, tB=0, dbg={6: 64})
 add("KMN_bn128", M=256, N=256, K=256, tA=0, tB=0, dbg={6: 128})
 add("KK_bn64", M=256, N=256, K=256, tA=0, tB=1, dbg={6: 64})
+# row-shifted A start address inside a 128B-swizzled tile (dbg 7 = byte offset = rows * 128)
+add("shift1", M=128, N=256, K=64, tA=0, tB=1, row_shift=1, dbg={7: 128})
+add("shift3", M=128, N=256, K=64, tA=0, tB=1, row_shift=3, dbg={7: 384})
+add("shift8", M=128, N=256, K=64, tA=0, tB=1, row_shift=8, dbg={7: 1024})
+add("shift13", M=128, N=256, K=256, tA=0, tB=1, row_shift=13, dbg={7: 13 * 128})
 # epilogues
 add("fwd_bias", M=384, N=512, K=320, tA=0, tB=0, bias=1)
 add("fwd_silu", M=384, N=512, K=320, tA=0, tB=0, bias=1, mode=1)

@@ -69,7 +69,8 @@ class ConvArgs(C.Structure):
                 ("epilogue", i32), ("aux_in", vp), ("ld_aux", ll),
                 ("dw_accum", vp),
                 ("dtype", i32),
-                ("backend", i32)]
+                ("backend", i32),
+                ("wprep", vp)]
 
 
 _SIGS = {
@@ -92,6 +93,8 @@ _SIGS = {
     "vvae_conv3d_fwd": ([C.POINTER(ConvArgs), vp], i32),
     "vvae_conv3d_dgrad": ([C.POINTER(ConvArgs), vp], i32),
     "vvae_conv3d_wgrad": ([C.POINTER(ConvArgs), vp], i32),
+    "vvae_conv3d_wprep_bytes": ([C.POINTER(ConvArgs), i32], ll),
+    "vvae_conv3d_wprep": ([C.POINTER(ConvArgs), i32, vp, vp], i32),
     "vvae_convT122_fwd": ([vp, vp, vp, vp, ll, i32, i32, i32, i32, i32, i32, vp], i32),
     "vvae_convT122_bwd": ([vp, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "vvae_groupnorm_silu_fwd": ([vp, vp, ll, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp], i32),

@@ -1,11 +1,414 @@
-// Tensor-core implicit-GEMM conv3d (bf16).  Placeholder dispatch: reports "unsupported" until the kernel lands, so
-// every convolution currently runs on the generic functor GEMM (conv_simt.cu).
+// conv3d (NDHWC, 'SAME', stride 1) as an implicit GEMM on tcgen05, bf16, forward and dgrad.
+//
+// Data flow per output tile (one frame t of one clip, R image rows x Ct columns, NT output channels):
+//   * TMA (5-D tiled map over [B,T,H,W,C], out-of-bounds = zero fill = 'SAME' padding in t, h and w) loads, per
+//     temporal tap dt and channel block cb, ONE zero-padded pixel tile of (R+kh-1) x (Ct+kw-1) pixels x CB channels into
+//     shared memory, pixel-major, swizzled (32/64/128 B = CB*2 bytes per pixel row).
+//   * The tile is addressed as a flat "padded plane" of pitch P = Ct+kw-1: output position m = r*P + c and filter tap
+//     (dh,dw) read plane index m + dh*P + dw, so every tap is the SAME K-major UMMA operand at a different start address
+//     (swizzled operand views may start at any row: measured).  No im2col is ever materialised and the
+//     input tile is read from L2/HBM once per (dt, cb), not once per tap.
+//   * Weights are pre-arranged once per step (conv_wprep_kernel) into the swizzled K-major image of every stage, and a
+//     single cp.async.bulk brings a stage's taps in.
+//   * tcgen05.mma (M=128 positions, N=NT, K=16 channels) accumulates all taps x channel slices in TMEM; accumulators
+//     are double buffered so the epilogue (bias / residual, bf16 store, pad positions dropped) overlaps the next tile.
+// dgrad is the same kernel over dy with flipped, transposed weights.
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace vvae {
-int conv_tc_supported(const vvae_conv_args&, int) { return 0; }
-int conv_tc_launch(const vvae_conv_args&, int, cudaStream_t) {
-  set_error("conv3d tensor-core path not available");
-  return VVAE_ERR_UNSUPPORTED;
+
+struct ConvPlan {
+  int B, T, H, W, kt, kh, kw;
+  int Cin_pad, Cout, CB, nCB, NT, nNT;
+  int R, Ct, P, rows, nblk, Mtot;
+  int rowbytes, layout_type, swizzle_bytes;
+  uint32_t a_bytes, a_stride, w_bytes, w_stride;
+  int stages, smem_bytes;
+  int hblocks, wblocks, total_tiles;
+};
+
+struct ConvParams {
+  ConvPlan pl;
+  const bf16* wimg;
+  bf16* y; long long y_ld;
+  const float* bias;
+  int mode; const bf16* aux; long long ld_aux;
+};
+
+static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+// which: 0 = forward (gathers x, Cin -> Cout), 1 = dgrad (gathers dy, Cout -> Cin)
+static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
+  const int cin = which == 0 ? a.Cin : a.Cout;    // channels of the gathered tensor
+  const int cout = which == 0 ? a.Cout : a.Cin;   // channels produced
+  const long long in_ld = which == 0 ? a.x_ld : a.y_ld;
+  p.B = a.B; p.T = a.T; p.H = a.H; p.W = a.W; p.kt = a.kt; p.kh = a.kh; p.kw = a.kw;
+  p.Cin_pad = (cin + 15) / 16 * 16;
+  p.Cout = cout;
+  if (p.Cin_pad > in_ld) return false;            // padded channels must exist in memory (and be zero / finite)
+  if ((in_ld * 2) % 16) return false;
+  p.CB = p.Cin_pad >= 64 ? 32 : (p.Cin_pad >= 32 ? 32 : 16);
+  if (p.Cin_pad % p.CB) return false;
+  p.nCB = p.Cin_pad / p.CB;
+  const int cout_pad = (cout + 15) / 16 * 16;
+  p.NT = std::min(cout_pad, 64);
+  if (cout_pad % p.NT) return false;
+  p.nNT = cout_pad / p.NT;
+  p.Ct = std::min(a.W, 128);
+  p.R = std::max(1, std::min(128 / p.Ct, a.H));
+  p.P = p.Ct + a.kw - 1;
+  if (p.P > 256) return false;
+  p.rows = p.R + a.kh - 1;
+  if (p.rows > 256) return false;
+  p.Mtot = (p.R - 1) * p.P + p.Ct;
+  p.nblk = (p.Mtot + 127) / 128;
+  if (p.nblk * p.NT > 256) return false;          // TMEM: 2 x nblk x NT columns <= 512
+  p.rowbytes = p.CB * 2;
+  p.swizzle_bytes = p.rowbytes;
+  p.layout_type = p.rowbytes == 128 ? 2 : (p.rowbytes == 64 ? 4 : 6);
+  p.a_bytes = (uint32_t)p.rows * p.P * p.rowbytes;
+  p.a_stride = align_up(p.a_bytes, 1024);
+  p.w_bytes = (uint32_t)a.kh * a.kw * p.NT * p.rowbytes;
+  p.w_stride = align_up(p.w_bytes, 1024);
+  const uint32_t slack = 1024 + 128u * 128u + 512;  // alignment + over-read of pad rows + barriers
+  const uint32_t per_stage = p.a_stride + p.w_stride;
+  int s = (int)((225u * 1024u - slack) / per_stage);
+  if (s < 2) return false;
+  p.stages = std::min(s, 6);
+  p.smem_bytes = (int)std::max<uint32_t>(p.stages * per_stage + slack, 120u * 1024u);  // >= 120 KB: one CTA per SM (TMEM)
+  p.hblocks = (a.H + p.R - 1) / p.R;
+  p.wblocks = (a.W + p.Ct - 1) / p.Ct;
+  const long long tiles = (long long)a.B * a.T * p.hblocks * p.wblocks * p.nNT;
+  if (tiles > 0x7fffffffLL) return false;
+  p.total_tiles = (int)tiles;
+  return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight image: [nNT][kt][nCB][kh*kw][NT rows][CB cols] bf16, each [NT][CB] tile K-major with the stage swizzle applied
+// (Swizzle<B,4,3>: byte-offset bits [4,4+B) ^= bits [7,7+B), B = log2(rowbytes/16)); each stage starts 1024-aligned.
+__global__ void conv_wprep_kernel(const bf16* __restrict__ w, bf16* __restrict__ img, ConvPlan p, int which, int Cin,
+                                  int Cout) {
+  const int taps_hw = p.kh * p.kw;
+  const long long per_stage_el = (long long)p.w_stride / 2;
+  const long long total = (long long)p.nNT * p.kt * p.nCB * per_stage_el;
+  const uint32_t mask = (uint32_t)(p.rowbytes / 16 - 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long stage = i / per_stage_el;
+    const uint32_t byte = (uint32_t)(i % per_stage_el) * 2;
+    float val = 0.f;
+    if (byte < p.w_bytes) {
+      // undo the swizzle to find which logical (tap, n, k) lives at this physical position
+      const uint32_t tile_bytes = (uint32_t)p.NT * p.rowbytes;
+      const uint32_t tap = byte / tile_bytes;
+      uint32_t off = byte % tile_bytes;
+      off ^= ((off >> 7) & mask) << 4;
+      const int n = off / p.rowbytes, k = (off % p.rowbytes) / 2;
+      const int cb = (int)(stage % p.nCB);
+      const int dt = (int)((stage / p.nCB) % p.kt);
+      const int nt = (int)(stage / ((long long)p.nCB * p.kt));
+      const int dh = tap / p.kw, dw = tap % p.kw;
+      const int kin = cb * p.CB + k;      // channel of the gathered tensor
+      const int nout = nt * p.NT + n;     // produced channel
+      if (which == 0) {
+        if (kin < Cin && nout < Cout) val = __bfloat162float(w[((((long long)dt * p.kh + dh) * p.kw + dw) * Cin + kin) * Cout + nout]);
+      } else {  // dgrad: gathered = dy (Cout channels), produced = dx (Cin channels), taps mirrored
+        if (kin < Cout && nout < Cin)
+          val = __bfloat162float(w[((((long long)(p.kt - 1 - dt) * p.kh + (p.kh - 1 - dh)) * p.kw + (p.kw - 1 - dw)) * Cin + nout) * Cout + kin]);
+      }
+      (void)taps_hw;
+    }
+    img[i] = __float2bfloat16_rn(val);
+  }
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)1 << 16;                              // LBO: unused for swizzled K-major
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sm100::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(sm100::smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// store 16 consecutive output channels [n0, n0+16) of one pixel (only those < Cout are written)
+__device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix, int n0, const uint32_t (&r)[16]) {
+  const int cout = q.pl.Cout;
+  if (n0 >= cout) return;
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + ((q.bias && n0 + j < cout) ? __ldg(q.bias + n0 + j) : 0.f);
+  if (q.mode == VVAE_EPI_RESIDUAL) {
+    const bf16* ax = q.aux + pix * q.ld_aux + n0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (n0 + j < cout) v[j] += __bfloat162float(ax[j]);
+  }
+  bf16* dst = q.y + pix * q.y_ld + n0;
+  const int nvalid = min(16, cout - n0);
+  if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      Vec16<bf16> o;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o.set(t, v[j + t]);
+      o.store(dst + j);
+    }
+  } else if ((nvalid % 4) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
+    for (int j = 0; j < nvalid; j += 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(v[j], v[j + 1]), b = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&a);
+      pk.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(dst + j) = pk;
+    }
+  } else {
+    for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
+  const ConvPlan& p = q.pl;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_w = smem + (size_t)S * p.a_stride;
+  // barriers live after the weight stages plus the over-read slack
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * (p.a_stride + p.w_stride) + 128 * 128);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 8;
+  uint64_t* tmem_full = bars + 16;
+  uint64_t* tmem_empty = bars + 18;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_x);
+    for (int i = 0; i < S; ++i) {
+      sm100::mbar_init(&full_bar[i], 1);
+      sm100::mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      sm100::mbar_init(&tmem_full[i], 1);
+      sm100::mbar_init(&tmem_empty[i], 4);
+    }
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = p.nblk * p.NT;
+  const int stages_per_tile = p.kt * p.nCB;
+  const int taps_hw = p.kh * p.kw;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int rest = tile;
+        const int nt = rest % p.nNT; rest /= p.nNT;
+        const int wb = rest % p.wblocks; rest /= p.wblocks;
+        const int hb = rest % p.hblocks; rest /= p.hblocks;
+        const int t = rest % p.T;
+        const int b = rest / p.T;
+        const int w0 = wb * p.Ct - p.kw / 2, h0 = hb * p.R - p.kh / 2;
+        for (int dt = 0; dt < p.kt; ++dt) {
+          for (int cb = 0; cb < p.nCB; ++cb) {
+            sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
+            sm100::mbar_expect_tx(&full_bar[stage], p.a_bytes + p.w_bytes);
+            sm100::tma_load_5d(smem_a + (size_t)stage * p.a_stride, &tma_x, &full_bar[stage], cb * p.CB, w0, h0,
+                               t + dt - p.kt / 2, b);
+            bulk_g2s(smem_w + (size_t)stage * p.w_stride,
+                     reinterpret_cast<const uint8_t*>(q.wimg) + ((size_t)(nt * p.kt + dt) * p.nCB + cb) * p.w_stride,
+                     p.w_bytes, &full_bar[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = sm100::make_idesc_bf16(128, p.NT, false, false);
+      // Descriptors differ only in the 14-bit start-address field of the low word, so the issue loop is pure adds
+      // (a single thread feeds the tensor pipe: instruction count per MMA is what bounds small-N convolutions).
+      const uint32_t rb16 = (uint32_t)p.rowbytes >> 4;                 // row pitch in 16-byte units
+      const uint32_t desc_hi = ((8u * p.rowbytes) >> 4) | (1u << 14) | ((uint32_t)p.layout_type << 29);
+      const uint32_t lo_flags = 1u << 16;                               // LBO field (unused for swizzled K-major)
+      const uint32_t a_row_step = (uint32_t)p.P * rb16, a_blk_step = 128u * rb16, w_tap_step = (uint32_t)p.NT * rb16;
+      const int kh = p.kh, kw = p.kw, nks = p.CB / 16, nblk = p.nblk, NT = p.NT;
+      const uint32_t a_stride = p.a_stride, w_stride = p.w_stride;
+      const uint32_t a_base0 = sm100::smem_u32(smem_a), w_base0 = sm100::smem_u32(smem_w);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        sm100::tc_fence_after();
+        const uint32_t d_base = tmem_base + acc * acc_cols;
+        uint32_t accum = 0;
+        for (int s = 0; s < stages_per_tile; ++s) {
+          sm100::mbar_wait(&full_bar[stage], phase);
+          sm100::tc_fence_after();
+          uint32_t a_row = (((a_base0 + stage * a_stride) >> 4) & 0x3FFFu) | lo_flags;
+          uint32_t w_lo = (((w_base0 + stage * w_stride) >> 4) & 0x3FFFu) | lo_flags;
+          for (int dh = 0; dh < kh; ++dh, a_row += a_row_step) {
+            uint32_t a_tap = a_row;
+            for (int dw = 0; dw < kw; ++dw, a_tap += rb16, w_lo += w_tap_step) {
+              for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo + 2u * ks);
+                uint32_t a_lo = a_tap + 2u * ks;
+                uint32_t d = d_base;
+                for (int blk = 0; blk < nblk; ++blk, a_lo += a_blk_step, d += NT) {
+                  const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)a_lo;
+                  sm100::umma_f16(d, da, db, idesc, accum);
+                }
+                accum = 1;
+              }
+            }
+          }
+          sm100::umma_commit(&empty_bar[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        sm100::umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int rest = tile;
+      const int nt = rest % p.nNT; rest /= p.nNT;
+      const int wb = rest % p.wblocks; rest /= p.wblocks;
+      const int hb = rest % p.hblocks; rest /= p.hblocks;
+      const int t = rest % p.T;
+      const int b = rest / p.T;
+      sm100::mbar_wait(&tmem_full[acc], acc_phase);
+      sm100::tc_fence_after();
+      for (int blk = 0; blk < p.nblk; ++blk) {
+        const int m = blk * 128 + quarter * 32 + lane;
+        const int r = m / p.P, c = m - r * p.P;
+        const int hh = hb * p.R + r, ww = wb * p.Ct + c;
+        const bool valid = (m < p.Mtot) && (c < p.Ct) && (hh < p.H) && (ww < p.W);
+        const long long pix = (((long long)b * p.T + t) * p.H + hh) * p.W + ww;
+        const uint32_t taddr = tmem_base + acc * acc_cols + blk * p.NT + ((uint32_t)(quarter * 32) << 16);
+        for (int cc = 0; cc < p.NT; cc += 16) {
+          uint32_t rr[16];
+          tmem_ld_32x16(taddr + cc, rr);
+          sm100::tmem_ld_wait();
+          if (valid) conv_store16(q, pix, nt * p.NT + cc, rr);
+        }
+      }
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+int conv_tc_supported(const vvae_conv_args& a, int which) {
+  if (a.dtype != VVAE_BF16 || which > 1) return 0;
+  if (!a.wprep) return 0;
+  ConvPlan p;
+  if (!make_plan(a, which, p)) return 0;
+  const void* in = which == 0 ? a.x : a.y;
+  if ((uintptr_t)in % 16) return 0;
+  return 1;
+}
+
+int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
+  ConvParams q;
+  if (!make_plan(a, which, q.pl)) {
+    set_error("conv3d: shape not supported by the tensor-core path");
+    return VVAE_ERR_UNSUPPORTED;
+  }
+  const ConvPlan& p = q.pl;
+  const void* in = which == 0 ? a.x : a.y;
+  const long long in_ld = which == 0 ? a.x_ld : a.y_ld;
+  CUtensorMap tm;
+  uint64_t dims[5] = {(uint64_t)p.Cin_pad, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.T, (uint64_t)a.B};
+  uint64_t str[4] = {(uint64_t)in_ld * 2, (uint64_t)a.W * in_ld * 2, (uint64_t)a.H * a.W * in_ld * 2,
+                     (uint64_t)a.T * a.H * a.W * in_ld * 2};
+  uint32_t box[5] = {(uint32_t)p.CB, (uint32_t)p.P, (uint32_t)p.rows, 1, 1};
+  int rc = encode_tmap_nd_bf16(&tm, in, 5, dims, str, box, p.swizzle_bytes);
+  if (rc) return rc;
+  q.wimg = (const bf16*)a.wprep;
+  if (which == 0) {
+    q.y = (bf16*)a.y; q.y_ld = a.y_ld; q.bias = a.bias; q.mode = a.epilogue; q.aux = (const bf16*)a.aux_in; q.ld_aux = a.ld_aux;
+  } else {
+    q.y = (bf16*)const_cast<void*>(a.x); q.y_ld = a.x_ld; q.bias = nullptr; q.mode = VVAE_EPI_NONE; q.aux = nullptr; q.ld_aux = 0;
+  }
+  static int max_set = 0;
+  if (p.smem_bytes > max_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return VVAE_ERR_CUDA;
+    }
+    max_set = 227 * 1024;
+  }
+  const int grid = std::min(p.total_tiles, 148);
+  conv_sm100_kernel<<<grid, 192, p.smem_bytes, s>>>(tm, q);
+  return check_launch("conv_sm100");
+}
+
 }  // namespace vvae
+
+using namespace vvae;
+
+extern "C" {
+
+long long vvae_conv3d_wprep_bytes(const vvae_conv_args* a, int which) {
+  if (!a || a->dtype != VVAE_BF16 || which < 0 || which > 1) return 0;
+  ConvPlan p;
+  if (!make_plan(*a, which, p)) return 0;
+  return (long long)p.nNT * p.kt * p.nCB * p.w_stride;
+}
+
+int vvae_conv3d_wprep(const vvae_conv_args* a, int which, void* out, vvae_stream_t stream) {
+  VVAE_REQUIRE(a && out && a->w, "conv3d_wprep: null pointer");
+  ConvPlan p;
+  VVAE_REQUIRE(a->dtype == VVAE_BF16 && make_plan(*a, which, p), "conv3d_wprep: shape not supported by the tensor-core path");
+  const long long total = (long long)p.nNT * p.kt * p.nCB * (p.w_stride / 2);
+  const int blocks = (int)std::min<long long>(cdiv(total, 256), 148 * 8);
+  conv_wprep_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)a->w, (bf16*)out, p, which, a->Cin, a->Cout);
+  return check_launch("conv_wprep");
+}
+
+}  // extern "C"

@@ -92,6 +92,7 @@ struct Sm100Params {
   int atomic;
   // descriptor encodings (bytes); overridable through vvae_debug_set for bring-up
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+  uint32_t dbg_a_shift;  // bring-up experiment: byte offset added to the A start address (row-shifted operand views)
 };
 
 template <int BN> struct StageCfg {
@@ -279,7 +280,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           sm100::mbar_wait(&full_bar[stage], phase);
           sm100::tc_fence_after();
-          const uint32_t a_addr = sm100::smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t a_addr = sm100::smem_u32(smem_a + stage * A_STAGE_BYTES) + p.dbg_a_shift;
           const uint32_t b_addr = sm100::smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -383,6 +384,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   // K advance = 16 rows x 128 B.
   p.a_lbo = A_MN ? 8192 : 16;  p.a_sbo = 1024;  p.a_kadv = A_MN ? 2048 : 32;
   p.b_lbo = B_MN ? 8192 : 16;  p.b_sbo = 1024;  p.b_kadv = B_MN ? 2048 : 32;
+  p.dbg_a_shift = (uint32_t)g_dbg[7];
   if (g_dbg[1]) { if (A_MN) p.a_lbo = (uint32_t)g_dbg[1]; if (B_MN) p.b_lbo = (uint32_t)g_dbg[1]; }
   if (g_dbg[2]) { if (A_MN) p.a_sbo = (uint32_t)g_dbg[2]; if (B_MN) p.b_sbo = (uint32_t)g_dbg[2]; }
   if (g_dbg[3]) { if (A_MN) p.a_kadv = (uint32_t)g_dbg[3]; if (B_MN) p.b_kadv = (uint32_t)g_dbg[3]; }

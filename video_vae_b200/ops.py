@@ -13,6 +13,8 @@ from ._ffi import (BACKEND_AUTO, BF16, EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SI
 
 LN_EPS = 1e-6
 
+CONV_BACKEND = BACKEND_AUTO  # tests force BACKEND_SIMT to cross-check the tensor-core conv against the generic one
+
 # bench.py sets PROFILE to a list; instrumented ops then append (class, flops, bytes, start_event, stop_event).
 PROFILE = None
 
@@ -214,41 +216,61 @@ def pixel_shuffle(src, b_t, H, W, CU, P, to_tokens):
 
 
 # ---------------------------------------------------------------- convolutions (channels-last, 5-D [B,T,H,W,C])
-def _conv_args(x, x_ld, w, bias, y, y_ld, B, T, H, W, Cin, Cout, ks, epilogue=EPI_NONE, aux=None, aux_ld=0, dw=None):
+def _conv_args(x, x_ld, w, bias, y, y_ld, B, T, H, W, Cin, Cout, ks, epilogue=EPI_NONE, aux=None, aux_ld=0, dw=None,
+               wprep=None, dtype=None):
     a = ConvArgs()
     a.B, a.T, a.H, a.W, a.Cin, a.Cout = B, T, H, W, Cin, Cout
     a.kt, a.kh, a.kw = ks
     a.x, a.x_ld, a.w, a.bias, a.y, a.y_ld = ptr(x), x_ld, ptr(w), ptr(bias), ptr(y), y_ld
     a.epilogue, a.aux_in, a.ld_aux = epilogue, ptr(aux), aux_ld
     a.dw_accum = ptr(dw)
-    a.dtype = dt(x if x is not None else y)
-    a.backend = BACKEND_AUTO
+    a.dtype = dtype if dtype is not None else dt(x if x is not None else y)
+    a.backend = CONV_BACKEND
+    a.wprep = ptr(wprep)
     return a
 
 
-def conv3d_fwd(x, w, bias, ks, Cin, Cout, x_ld=None, residual=None):
-    """x: [B,T,H,W,x_ld] storage whose first Cin channels are the input; w: [kt,kh,kw,Cin,Cout] (compute dtype)."""
+def conv3d_wprep(w, which, B, T, H, W, Cin, Cout, ks, x_ld, y_ld):
+    """Weight image for the tensor-core conv path (None when the shape runs on the generic kernel)."""
+    if w.dtype != torch.bfloat16:
+        return None
+    a = _conv_args(None, x_ld, w, None, None, y_ld, B, T, H, W, Cin, Cout, ks, dtype=BF16)
+    nbytes = lib.vvae_conv3d_wprep_bytes(C.byref(a), which)
+    if nbytes <= 0:
+        return None
+    img = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    check(lib.vvae_conv3d_wprep(C.byref(a), which, ptr(img), stream()), "vvae_conv3d_wprep")
+    return img
+
+
+def conv3d_fwd(x, w, bias, ks, Cin, Cout, x_ld=None, residual=None, out=None, out_ld=None, wprep=None):
+    """x: [B,T,H,W,x_ld] storage whose first Cin channels are the input; w: [kt,kh,kw,Cin,Cout] (compute dtype).
+    ``out``/``out_ld`` let the result land in (a channel slice of) a wider pre-allocated buffer."""
     B, T, H, W = x.shape[:4]
-    y = torch.empty((B, T, H, W, Cout), dtype=x.dtype, device=x.device)
-    a = _conv_args(x, x_ld or x.shape[-1], w, bias, y, Cout, B, T, H, W, Cin, Cout, ks,
-                   EPI_RESIDUAL if residual is not None else EPI_NONE, residual, Cout)
+    if out is None:
+        out = torch.empty((B, T, H, W, Cout), dtype=x.dtype, device=x.device)
+        out_ld = Cout
+    a = _conv_args(x, x_ld or x.shape[-1], w, bias, out, out_ld, B, T, H, W, Cin, Cout, ks,
+                   EPI_RESIDUAL if residual is not None else EPI_NONE, residual, Cout, wprep=wprep)
     with _Prof("conv3d_fwd", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
         check(lib.vvae_conv3d_fwd(C.byref(a), stream()), "vvae_conv3d_fwd")
-    return y
+    return out
 
 
-def conv3d_dgrad(dy, w, ks, Cin, Cout):
+def conv3d_dgrad(dy, w, ks, Cin, Cout, dy_ld=None, out=None, out_ld=None, wprep=None):
     B, T, H, W = dy.shape[:4]
-    dx = torch.empty((B, T, H, W, Cin), dtype=dy.dtype, device=dy.device)
-    a = _conv_args(dx, Cin, w, None, dy, dy.shape[-1], B, T, H, W, Cin, Cout, ks)
+    if out is None:
+        out = torch.empty((B, T, H, W, Cin), dtype=dy.dtype, device=dy.device)
+        out_ld = Cin
+    a = _conv_args(out, out_ld, w, None, dy, dy_ld or dy.shape[-1], B, T, H, W, Cin, Cout, ks, wprep=wprep)
     with _Prof("conv3d_dgrad", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
         check(lib.vvae_conv3d_dgrad(C.byref(a), stream()), "vvae_conv3d_dgrad")
-    return dx
+    return out
 
 
-def conv3d_wgrad_accum(x, dy, dw, ks, Cin, Cout, x_ld=None):
+def conv3d_wgrad_accum(x, dy, dw, ks, Cin, Cout, x_ld=None, dy_ld=None):
     B, T, H, W = x.shape[:4]
-    a = _conv_args(x, x_ld or x.shape[-1], None, None, dy, dy.shape[-1], B, T, H, W, Cin, Cout, ks, dw=dw)
+    a = _conv_args(x, x_ld or x.shape[-1], None, None, dy, dy_ld or dy.shape[-1], B, T, H, W, Cin, Cout, ks, dw=dw)
     with _Prof("conv3d_wgrad", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
         check(lib.vvae_conv3d_wgrad(C.byref(a), stream()), "vvae_conv3d_wgrad")
 
