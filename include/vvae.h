@@ -151,6 +151,8 @@ typedef struct vvae_conv_args {
   int dtype;
   int backend;
   const void* wprep; /* tensor-core path: weight image from vvae_conv3d_wprep (NULL -> generic kernel) */
+  int pad_out;       /* != 0: the produced tensor has storage for ceil16(channels) channels per voxel and the kernel also
+                      * writes zeros to the pad channels (so a following tensor-core conv may gather them) */
 } vvae_conv_args;
 int vvae_conv3d_fwd(const vvae_conv_args* args, vvae_stream_t stream);
 /* dgrad: reads dy from args->y (stride y_ld), writes dx to args->x (stride x_ld; cast away const). */

@@ -90,13 +90,15 @@ if __name__ == "__main__":
                 r = {"name": c[0], "error": repr(e)[:300]}
             print(json.dumps(r), flush=True)
             f.write(json.dumps(r) + "\n")
-        if not sel:
+        if True:
             for c in [("prod_full16", 8, 16, 256, 256, 16, 16, (3, 3, 3), 16, 16),
                       ("prod_full32_16", 8, 16, 256, 256, 32, 16, (3, 3, 3), 32, 16),
                       ("prod_pm", 8, 16, 256, 256, 12, 12, (3, 7, 7), 16, 16),
                       ("prod_half64_32", 8, 16, 128, 128, 64, 32, (3, 3, 3), 64, 32),
                       ("prod_q128_64", 8, 16, 64, 64, 128, 64, (3, 3, 3), 128, 64),
                       ("prod_b128_128", 8, 16, 32, 32, 128, 128, (3, 3, 3), 128, 128)]:
+                if sel and c[0] not in sel:
+                    continue
                 try:
                     r = run(*c, timed=True)
                 except Exception as e:  # noqa: BLE001

@@ -168,6 +168,48 @@ def test_unet_fwd_bwd_fp32(V):
     _grads_close(m, o, 5e-4, min_checked=30)
 
 
+def test_unet_bf16_tensor_core_convs_match_generic_and_oracle(V):
+    """bf16 U-Net: the tcgen05 implicit-GEMM convs (fwd + dgrad) against the generic kernels on the same bf16
+    data (tight) and against the fp32 oracle (bf16 tolerance), forward and every parameter gradient."""
+    from oracle import Rngs as ORngs
+    from oracle.unet import UNet as OUNet
+    from video_vae_b200 import _ffi, ops
+    o = OUNet(12, 16, 3, 3, ORngs(0))
+    with torch.no_grad():
+        o.final_conv.kernel.copy_(torch.randn(o.final_conv.kernel.shape, generator=_gen(9)) * 0.2)
+    g = _gen(4)
+    shape = (2, 3, 32, 64)
+    x = torch.randn(*shape, 12, generator=g)
+    res = torch.randn(*shape, 3, generator=g)
+    w = torch.randn(*shape, 3, generator=g)
+    xo = x.clone().requires_grad_(True)
+    yo = o(xo) + res
+    (yo * w).sum().backward()
+    outs = {}
+    for backend in (_ffi.BACKEND_SIMT, _ffi.BACKEND_AUTO):
+        ops.CONV_BACKEND = backend
+        try:
+            m = V.UNet(12, 16, 3, 3, V.Rngs(0), dtype=torch.bfloat16)
+            _copy_params(m, o)
+            xm = x.cuda().bfloat16().requires_grad_(True)
+            ym = m(xm, residual=res.cuda().bfloat16())
+            (ym.float() * w.cuda()).sum().backward()
+            outs[backend] = (ym.float().cpu(), xm.grad.float().cpu(), {n: p.grad.cpu() for n, p in m.named_parameters()})
+        finally:
+            ops.CONV_BACKEND = _ffi.BACKEND_AUTO
+    ys, dxs, gs = outs[_ffi.BACKEND_SIMT]
+    yt, dxt, gt = outs[_ffi.BACKEND_AUTO]
+    assert rel_err(yt, ys) < 1e-2 and rel_err(dxt, dxs) < 2e-2
+    assert rel_err(yt, yo) < BF16_TOL
+    # gradients through 15 bf16 conv+GroupNorm layers: the tensor-core path must be as close to the fp32 oracle as
+    # the generic bf16 path is (both carry the same bf16 rounding points)
+    assert rel_err(dxt, xo.grad) < max(0.05, 1.5 * rel_err(dxs, xo.grad))
+    og = dict(o.named_parameters())
+    for n_, gg in gt.items():
+        assert torch.isfinite(gg).all(), n_
+        assert rel_err(gg, og[n_].grad) < max(0.05, 1.5 * rel_err(gs[n_], og[n_].grad)), n_
+
+
 def _small_pair(V, dtype, enc=2, dec=2, seed=2):
     from oracle import Rngs as ORngs
     from oracle.model import VideoVAE as OVAE

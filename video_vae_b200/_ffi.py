@@ -70,7 +70,8 @@ class ConvArgs(C.Structure):
                 ("dw_accum", vp),
                 ("dtype", i32),
                 ("backend", i32),
-                ("wprep", vp)]
+                ("wprep", vp),
+                ("pad_out", i32)]
 
 
 _SIGS = {

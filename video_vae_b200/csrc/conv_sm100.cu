@@ -16,6 +16,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <mutex>
+#include <set>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -38,6 +40,7 @@ struct ConvParams {
   bf16* y; long long y_ld;
   const float* bias;
   int mode; const bf16* aux; long long ld_aux;
+  int store_c;  // channels written per voxel: Cout, or ceil16(Cout) when the caller asked for zeroed pad channels
 };
 
 static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -81,6 +84,7 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   if (s < 2) return false;
   p.stages = std::min(s, 6);
   p.smem_bytes = (int)std::max<uint32_t>(p.stages * per_stage + slack, 120u * 1024u);  // >= 120 KB: one CTA per SM (TMEM)
+  if (p.nblk > 2) return false;
   p.hblocks = (a.H + p.R - 1) / p.R;
   p.wblocks = (a.W + p.Ct - 1) / p.Ct;
   const long long tiles = (long long)a.B * a.T * p.hblocks * p.wblocks * p.nNT;
@@ -155,7 +159,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 // store 16 consecutive output channels [n0, n0+16) of one pixel (only those < Cout are written)
 __device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix, int n0, const uint32_t (&r)[16]) {
   const int cout = q.pl.Cout;
-  if (n0 >= cout) return;
+  if (n0 >= q.store_c) return;
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + ((q.bias && n0 + j < cout) ? __ldg(q.bias + n0 + j) : 0.f);
@@ -166,7 +170,7 @@ __device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix,
       if (n0 + j < cout) v[j] += __bfloat162float(ax[j]);
   }
   bf16* dst = q.y + pix * q.y_ld + n0;
-  const int nvalid = min(16, cout - n0);
+  const int nvalid = min(16, q.store_c - n0);  // accumulators of channels >= Cout are exact zeros (zero weights)
   if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
     for (int j = 0; j < 16; j += 8) {
@@ -176,20 +180,36 @@ __device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix,
       o.store(dst + j);
     }
   } else if ((nvalid % 4) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0)) {
-    for (int j = 0; j < nvalid; j += 4) {
-      __nv_bfloat162 a = __floats2bfloat162_rn(v[j], v[j + 1]), b = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&a);
-      pk.y = *reinterpret_cast<uint32_t*>(&b);
-      *reinterpret_cast<uint2*>(dst + j) = pk;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      if (j < nvalid) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[j], v[j + 1]), b = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a);
+        pk.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(dst + j) = pk;
+      }
     }
   } else {
-    for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
   }
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// KH x KW filter taps per frame, NKS = CB/16 K-slices per tap, NBLK 128-position blocks per tile, NT output channels per
+// MMA.  Everything the single MMA-issuing thread touches is a compile-time constant (or a loop-invariant register), so
+// the issue loop is one descriptor add + one tcgen05.mma per MMA: with N = 16..64 the tensor pipe needs a new
+// instruction every 8..32 cycles and the generic (runtime-loop) version spent ~150 cycles of scalar work per MMA.
+template <int KH, int KW, int NKS, int NBLK, int NT>
 __global__ void __launch_bounds__(192, 1)
-conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
+conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q) {
   const ConvPlan& p = q.pl;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -203,6 +223,10 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
   uint64_t* tmem_full = bars + 16;
   uint64_t* tmem_empty = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  constexpr int ROWBYTES = NKS * 32;
+  constexpr int ACC_COLS = NBLK * NT;
+  constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
+                            : (2 * ACC_COLS <= 256) ? 256 : 512;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -217,14 +241,12 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
     }
     sm100::fence_barrier_init();
   }
-  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(tmem_slot);
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int acc_cols = p.nblk * p.NT;
   const int stages_per_tile = p.kt * p.nCB;
-  const int taps_hw = p.kh * p.kw;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -237,7 +259,7 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
         const int hb = rest % p.hblocks; rest /= p.hblocks;
         const int t = rest % p.T;
         const int b = rest / p.T;
-        const int w0 = wb * p.Ct - p.kw / 2, h0 = hb * p.R - p.kh / 2;
+        const int w0 = wb * p.Ct - KW / 2, h0 = hb * p.R - KH / 2;
         for (int dt = 0; dt < p.kt; ++dt) {
           for (int cb = 0; cb < p.nCB; ++cb) {
             sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -253,52 +275,56 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = sm100::make_idesc_bf16(128, p.NT, false, false);
-      // Descriptors differ only in the 14-bit start-address field of the low word, so the issue loop is pure adds
-      // (a single thread feeds the tensor pipe: instruction count per MMA is what bounds small-N convolutions).
-      const uint32_t rb16 = (uint32_t)p.rowbytes >> 4;                 // row pitch in 16-byte units
-      const uint32_t desc_hi = ((8u * p.rowbytes) >> 4) | (1u << 14) | ((uint32_t)p.layout_type << 29);
-      const uint32_t lo_flags = 1u << 16;                               // LBO field (unused for swizzled K-major)
-      const uint32_t a_row_step = (uint32_t)p.P * rb16, a_blk_step = 128u * rb16, w_tap_step = (uint32_t)p.NT * rb16;
-      const int kh = p.kh, kw = p.kw, nks = p.CB / 16, nblk = p.nblk, NT = p.NT;
-      const uint32_t a_stride = p.a_stride, w_stride = p.w_stride;
-      const uint32_t a_base0 = sm100::smem_u32(smem_a), w_base0 = sm100::smem_u32(smem_w);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // The whole warp walks the loop (warp-uniform control flow keeps the address arithmetic in uniform registers);
+    // one elected lane issues the tensor-core instructions.
+    constexpr uint32_t idesc = sm100::make_idesc_bf16(128, NT, false, false);
+    constexpr uint32_t LAYOUT = ROWBYTES == 128 ? 2u : (ROWBYTES == 64 ? 4u : 6u);
+    constexpr uint32_t RB16 = ROWBYTES >> 4;                             // row pitch in 16-byte units
+    constexpr uint32_t desc_hi = ((8u * ROWBYTES) >> 4) | (1u << 14) | (LAYOUT << 29);
+    constexpr uint32_t lo_flags = 1u << 16;                              // LBO field (unused for swizzled K-major)
+    const uint32_t a_row_step = (uint32_t)p.P * RB16;
+    const uint32_t a_stride16 = p.a_stride >> 4, w_stride16 = p.w_stride >> 4;
+    const uint32_t a_base16 = sm100::smem_u32(smem_a) >> 4, w_base16 = sm100::smem_u32(smem_w) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      sm100::tc_fence_after();
+      const uint32_t d_base = tmem_base + acc * ACC_COLS;
+      for (int s = 0; s < stages_per_tile; ++s) {
+        sm100::mbar_wait(&full_bar[stage], phase);
         sm100::tc_fence_after();
-        const uint32_t d_base = tmem_base + acc * acc_cols;
-        uint32_t accum = 0;
-        for (int s = 0; s < stages_per_tile; ++s) {
-          sm100::mbar_wait(&full_bar[stage], phase);
-          sm100::tc_fence_after();
-          uint32_t a_row = (((a_base0 + stage * a_stride) >> 4) & 0x3FFFu) | lo_flags;
-          uint32_t w_lo = (((w_base0 + stage * w_stride) >> 4) & 0x3FFFu) | lo_flags;
-          for (int dh = 0; dh < kh; ++dh, a_row += a_row_step) {
-            uint32_t a_tap = a_row;
-            for (int dw = 0; dw < kw; ++dw, a_tap += rb16, w_lo += w_tap_step) {
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo + 2u * ks);
-                uint32_t a_lo = a_tap + 2u * ks;
-                uint32_t d = d_base;
-                for (int blk = 0; blk < nblk; ++blk, a_lo += a_blk_step, d += NT) {
-                  const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)a_lo;
-                  sm100::umma_f16(d, da, db, idesc, accum);
+        if (elect_one()) {
+          const uint32_t a_lo0 = ((a_base16 + stage * a_stride16) & 0x3FFFu) | lo_flags;
+          const uint32_t w_lo0 = ((w_base16 + stage * w_stride16) & 0x3FFFu) | lo_flags;
+#pragma unroll
+          for (int dh = 0; dh < KH; ++dh) {
+            const uint32_t a_row = a_lo0 + dh * a_row_step;
+#pragma unroll
+            for (int dw = 0; dw < KW; ++dw) {
+#pragma unroll
+              for (int ks = 0; ks < NKS; ++ks) {
+                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW + dw) * NT * RB16 + 2u * ks);
+#pragma unroll
+                for (int blk = 0; blk < NBLK; ++blk) {
+                  const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + dw * RB16 + 2u * ks + blk * 128u * RB16);
+                  if (dh == 0 && dw == 0 && ks == 0)
+                    sm100::umma_f16(d_base + blk * NT, da, db, idesc, s > 0 ? 1u : 0u);
+                  else
+                    sm100::umma_f16_acc(d_base + blk * NT, da, db, idesc);
                 }
-                accum = 1;
               }
             }
           }
           sm100::umma_commit(&empty_bar[stage]);
-          if (++stage == S) { stage = 0; phase ^= 1; }
+          if (s == stages_per_tile - 1) sm100::umma_commit(&tmem_full[acc]);
         }
-        sm100::umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     const int quarter = warp & 3;
@@ -313,18 +339,21 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
       const int b = rest / p.T;
       sm100::mbar_wait(&tmem_full[acc], acc_phase);
       sm100::tc_fence_after();
-      for (int blk = 0; blk < p.nblk; ++blk) {
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
         const int m = blk * 128 + quarter * 32 + lane;
         const int r = m / p.P, c = m - r * p.P;
         const int hh = hb * p.R + r, ww = wb * p.Ct + c;
         const bool valid = (m < p.Mtot) && (c < p.Ct) && (hh < p.H) && (ww < p.W);
         const long long pix = (((long long)b * p.T + t) * p.H + hh) * p.W + ww;
-        const uint32_t taddr = tmem_base + acc * acc_cols + blk * p.NT + ((uint32_t)(quarter * 32) << 16);
-        for (int cc = 0; cc < p.NT; cc += 16) {
-          uint32_t rr[16];
-          tmem_ld_32x16(taddr + cc, rr);
-          sm100::tmem_ld_wait();
-          if (valid) conv_store16(q, pix, nt * p.NT + cc, rr);
+        const uint32_t taddr = tmem_base + acc * ACC_COLS + blk * NT + ((uint32_t)(quarter * 32) << 16);
+        uint32_t rr[NT / 16][16];
+#pragma unroll
+        for (int cc = 0; cc < NT / 16; ++cc) tmem_ld_32x16(taddr + cc * 16, rr[cc]);
+        sm100::tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int cc = 0; cc < NT / 16; ++cc) conv_store16(q, pix, nt * NT + cc * 16, rr[cc]);
         }
       }
       sm100::tc_fence_before();
@@ -337,8 +366,32 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, ConvParams q) {
   __syncthreads();
   if (warp == 1) {
     sm100::tc_fence_after();
-    sm100::tmem_dealloc<512>(tmem_base);
+    sm100::tmem_dealloc<TMEM_COLS>(tmem_base);
   }
+}
+
+typedef void (*ConvKernelFn)(const CUtensorMap, const ConvParams);
+
+template <int KH, int KW, int NKS>
+static ConvKernelFn pick_conv_kernel2(int nblk, int NT) {
+  if (nblk == 1) {
+    if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 1, 16>;
+    if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 1, 32>;
+    if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 1, 64>;
+  } else if (nblk == 2) {
+    if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 2, 16>;
+    if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 2, 32>;
+    if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 2, 64>;
+  }
+  return nullptr;
+}
+
+static ConvKernelFn pick_conv_kernel(const ConvPlan& p) {
+  const int nks = p.CB / 16;
+  if (p.kh == 3 && p.kw == 3) return nks == 1 ? pick_conv_kernel2<3, 3, 1>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<3, 3, 2>(p.nblk, p.NT) : nullptr;
+  if (p.kh == 1 && p.kw == 1) return nks == 1 ? pick_conv_kernel2<1, 1, 1>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<1, 1, 2>(p.nblk, p.NT) : nullptr;
+  if (p.kh == 7 && p.kw == 7 && nks == 1 && p.nblk == 1 && p.NT == 16) return conv_sm100_kernel<7, 7, 1, 1, 16>;
+  return nullptr;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -346,7 +399,7 @@ int conv_tc_supported(const vvae_conv_args& a, int which) {
   if (a.dtype != VVAE_BF16 || which > 1) return 0;
   if (!a.wprep) return 0;
   ConvPlan p;
-  if (!make_plan(a, which, p)) return 0;
+  if (!make_plan(a, which, p) || !pick_conv_kernel(p)) return 0;
   const void* in = which == 0 ? a.x : a.y;
   if ((uintptr_t)in % 16) return 0;
   return 1;
@@ -374,17 +427,35 @@ int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
   } else {
     q.y = (bf16*)const_cast<void*>(a.x); q.y_ld = a.x_ld; q.bias = nullptr; q.mode = VVAE_EPI_NONE; q.aux = nullptr; q.ld_aux = 0;
   }
-  static int max_set = 0;
-  if (p.smem_bytes > max_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-      set_error("conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return VVAE_ERR_CUDA;
+  q.store_c = p.Cout;
+  if (a.pad_out) {
+    const int padded = (p.Cout + 15) / 16 * 16;
+    if (q.y_ld < padded) {
+      set_error("conv3d: pad_out needs %d channels of storage per voxel, row stride is %lld", padded, q.y_ld);
+      return VVAE_ERR_INVALID;
     }
-    max_set = 227 * 1024;
+    q.store_c = padded;
+  }
+  ConvKernelFn kern = pick_conv_kernel(p);
+  if (!kern) {
+    set_error("conv3d: no tensor-core kernel instance for this shape");
+    return VVAE_ERR_UNSUPPORTED;
+  }
+  {
+    static std::mutex mu;
+    static std::set<ConvKernelFn> configured;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!configured.count(kern)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) {
+        set_error("conv3d: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return VVAE_ERR_CUDA;
+      }
+      configured.insert(kern);
+    }
   }
   const int grid = std::min(p.total_tiles, 148);
-  conv_sm100_kernel<<<grid, 192, p.smem_bytes, s>>>(tm, q);
+  kern<<<grid, 192, p.smem_bytes, s>>>(tm, q);
   return check_launch("conv_sm100");
 }
 
@@ -397,7 +468,7 @@ extern "C" {
 long long vvae_conv3d_wprep_bytes(const vvae_conv_args* a, int which) {
   if (!a || a->dtype != VVAE_BF16 || which < 0 || which > 1) return 0;
   ConvPlan p;
-  if (!make_plan(*a, which, p)) return 0;
+  if (!make_plan(*a, which, p) || !pick_conv_kernel(p)) return 0;
   return (long long)p.nNT * p.kt * p.nCB * p.w_stride;
 }
 

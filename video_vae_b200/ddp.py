@@ -52,6 +52,7 @@ class FlatParams:
     def refresh_shadow(self):
         if self.shadow is not None:
             ops.cast_into(self.flat, self.shadow)
+        F_.params_changed()
 
 
 class GradAllReducer:

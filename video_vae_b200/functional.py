@@ -45,8 +45,31 @@ def shadow(p, dtype):
     return t
 
 
+_param_epoch = [0]  # bumped whenever parameters change behind autograd's back (fused optimizer kernels)
+_derived_cache = {}  # (id(param), key) -> (weakref(param), epoch, version, data_ptr, value)
+
+
 def invalidate_shadows():
     _shadow_cache.clear()
+    _param_epoch[0] += 1
+
+
+def params_changed():
+    """Called by the fused optimizer after it rewrote the flat parameter buffer in place."""
+    _param_epoch[0] += 1
+
+
+def derived(p, key, make):
+    """Cache of a tensor derived from parameter ``p`` (e.g. a re-laid-out weight image); rebuilt when p changes."""
+    k = (id(p), key)
+    ent = _derived_cache.get(k)
+    if (ent is not None and ent[0]() is p and ent[1] == _param_epoch[0] and ent[2] == p._version
+            and ent[3] == p.data_ptr()):
+        return ent[4]
+    val = make()
+    _derived_cache[k] = (weakref.ref(p, lambda _r, kk=k: _derived_cache.pop(kk, None)), _param_epoch[0], p._version,
+                         p.data_ptr(), val)
+    return val
 
 
 def grad_buf(p):

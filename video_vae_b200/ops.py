@@ -217,7 +217,7 @@ def pixel_shuffle(src, b_t, H, W, CU, P, to_tokens):
 
 # ---------------------------------------------------------------- convolutions (channels-last, 5-D [B,T,H,W,C])
 def _conv_args(x, x_ld, w, bias, y, y_ld, B, T, H, W, Cin, Cout, ks, epilogue=EPI_NONE, aux=None, aux_ld=0, dw=None,
-               wprep=None, dtype=None):
+               wprep=None, dtype=None, pad_out=False):
     a = ConvArgs()
     a.B, a.T, a.H, a.W, a.Cin, a.Cout = B, T, H, W, Cin, Cout
     a.kt, a.kh, a.kw = ks
@@ -227,6 +227,7 @@ def _conv_args(x, x_ld, w, bias, y, y_ld, B, T, H, W, Cin, Cout, ks, epilogue=EP
     a.dtype = dtype if dtype is not None else dt(x if x is not None else y)
     a.backend = CONV_BACKEND
     a.wprep = ptr(wprep)
+    a.pad_out = int(pad_out)
     return a
 
 
@@ -243,7 +244,7 @@ def conv3d_wprep(w, which, B, T, H, W, Cin, Cout, ks, x_ld, y_ld):
     return img
 
 
-def conv3d_fwd(x, w, bias, ks, Cin, Cout, x_ld=None, residual=None, out=None, out_ld=None, wprep=None):
+def conv3d_fwd(x, w, bias, ks, Cin, Cout, x_ld=None, residual=None, out=None, out_ld=None, wprep=None, pad_out=False):
     """x: [B,T,H,W,x_ld] storage whose first Cin channels are the input; w: [kt,kh,kw,Cin,Cout] (compute dtype).
     ``out``/``out_ld`` let the result land in (a channel slice of) a wider pre-allocated buffer."""
     B, T, H, W = x.shape[:4]
@@ -251,18 +252,19 @@ def conv3d_fwd(x, w, bias, ks, Cin, Cout, x_ld=None, residual=None, out=None, ou
         out = torch.empty((B, T, H, W, Cout), dtype=x.dtype, device=x.device)
         out_ld = Cout
     a = _conv_args(x, x_ld or x.shape[-1], w, bias, out, out_ld, B, T, H, W, Cin, Cout, ks,
-                   EPI_RESIDUAL if residual is not None else EPI_NONE, residual, Cout, wprep=wprep)
+                   EPI_RESIDUAL if residual is not None else EPI_NONE, residual, Cout, wprep=wprep, pad_out=pad_out)
     with _Prof("conv3d_fwd", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
         check(lib.vvae_conv3d_fwd(C.byref(a), stream()), "vvae_conv3d_fwd")
     return out
 
 
-def conv3d_dgrad(dy, w, ks, Cin, Cout, dy_ld=None, out=None, out_ld=None, wprep=None):
+def conv3d_dgrad(dy, w, ks, Cin, Cout, dy_ld=None, out=None, out_ld=None, wprep=None, pad_out=False):
     B, T, H, W = dy.shape[:4]
     if out is None:
         out = torch.empty((B, T, H, W, Cin), dtype=dy.dtype, device=dy.device)
         out_ld = Cin
-    a = _conv_args(out, out_ld, w, None, dy, dy_ld or dy.shape[-1], B, T, H, W, Cin, Cout, ks, wprep=wprep)
+    a = _conv_args(out, out_ld, w, None, dy, dy_ld or dy.shape[-1], B, T, H, W, Cin, Cout, ks, wprep=wprep,
+                   pad_out=pad_out)
     with _Prof("conv3d_dgrad", 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout):
         check(lib.vvae_conv3d_dgrad(C.byref(a), stream()), "vvae_conv3d_dgrad")
     return out

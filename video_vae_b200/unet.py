@@ -63,18 +63,41 @@ class GroupNorm(nn.Module):
 
 # ---------------------------------------------------------------------------------------------------------------------
 # building blocks used by the Functions below (plain functions over tensors; they record what backward needs)
-def _conv_fwd(x, x_ld, Cin, conv, dtype, residual=None):
+def _wprep(conv, which, dtype, geom, x_ld, y_ld):
+    """Cached tensor-core weight image of ``conv`` (None -> generic kernel); rebuilt when the parameters change."""
+    if dtype != torch.bfloat16:
+        return None
+    kernel = conv.kernel
+    Cin, Cout = kernel.shape[3], kernel.shape[4]
+    key = ("conv_wprep", which, geom, x_ld, y_ld)
+    return F_.derived(kernel, key, lambda: ops.conv3d_wprep(F_.shadow(kernel, dtype), which, *geom, Cin, Cout, conv.ks,
+                                                            x_ld, y_ld))
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+def _conv_fwd(x, x_ld, Cin, conv, dtype, residual=None, out=None, out_ld=None):
     w = F_.shadow(conv.kernel, dtype)
-    return ops.conv3d_fwd(x, w, conv.bias.detach(), conv.ks, Cin, conv.kernel.shape[4], x_ld=x_ld, residual=residual)
-
-
-def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True):
     Cout = conv.kernel.shape[4]
-    ops.conv3d_wgrad_accum(x, dy, F_.grad_buf(conv.kernel), conv.ks, Cin, Cout, x_ld=x_ld)
-    ops.colsum_accum(dy.reshape(-1, Cout), F_.grad_buf(conv.bias))
+    y_ld = out_ld if out is not None else Cout
+    wp = _wprep(conv, 0, dtype, tuple(x.shape[:4]), x_ld, y_ld)
+    return ops.conv3d_fwd(x, w, conv.bias.detach(), conv.ks, Cin, Cout, x_ld=x_ld, residual=residual, out=out,
+                          out_ld=out_ld, wprep=wp, pad_out=out is not None and out_ld >= _pad16(Cout) > Cout)
+
+
+def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=None, dx_ld=None):
+    Cout = conv.kernel.shape[4]
+    dy_ld = dy_ld or dy.shape[-1]
+    ops.conv3d_wgrad_accum(x, dy, F_.grad_buf(conv.kernel), conv.ks, Cin, Cout, x_ld=x_ld, dy_ld=dy_ld)
+    ops.colsum_accum(dy.reshape(-1, dy_ld)[:, :Cout], F_.grad_buf(conv.bias))
     if not need_dx:
         return None
-    return ops.conv3d_dgrad(dy, F_.shadow(conv.kernel, dtype), conv.ks, Cin, Cout)
+    o_ld = dx_ld if dx_out is not None else Cin
+    wp = _wprep(conv, 1, dtype, tuple(dy.shape[:4]), o_ld, dy_ld)
+    return ops.conv3d_dgrad(dy, F_.shadow(conv.kernel, dtype), conv.ks, Cin, Cout, dy_ld=dy_ld, out=dx_out, out_ld=dx_ld,
+                            wprep=wp, pad_out=dx_out is not None and dx_ld >= _pad16(Cin) > Cin)
 
 
 class _BlockTape:
@@ -94,9 +117,14 @@ def _block_fwd(x, x_ld, Cin, blk, dtype, out=None, out_ld=None):
 
 
 def _block_bwd(dy, dy_ld, tp, blk, dtype, need_dx=True):
+    """Returns dx with the channel stride of the block's input (``tp.x_ld``; pad channels, if any, are zero)."""
     dc = ops.groupnorm_silu_bwd(dy, dy_ld, tp.c, blk.norm.scale.detach(), blk.norm.bias.detach(), tp.mean, tp.rstd,
                                 F_.grad_buf(blk.norm.scale), F_.grad_buf(blk.norm.bias), blk.norm.num_groups)
-    return _conv_bwd(dc, tp.x, tp.x_ld, tp.Cin, blk.conv, dtype, need_dx)
+    dx_out = dx_ld = None
+    if need_dx and tp.x_ld != tp.Cin:
+        dx_ld = tp.x_ld
+        dx_out = torch.zeros(tuple(tp.x.shape[:4]) + (dx_ld,), dtype=dc.dtype, device=dc.device)
+    return _conv_bwd(dc, tp.x, tp.x_ld, tp.Cin, blk.conv, dtype, need_dx, dx_out=dx_out, dx_ld=dx_ld)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -246,10 +274,19 @@ class UNetFn(Function):
             x = ops.cast(x.contiguous(), dtype)
         x = x.contiguous()
         B, T, H, W, C0 = x.shape
-        tape = {"x": x}
-        cur = _conv_fwd(x, C0, C0, net.patch_mixer, dtype)
+        # the tensor-core conv gathers channels in blocks of 16: give 12-channel maps a 16-channel pitch (zero pads)
+        C0p = _pad16(C0) if dtype == torch.bfloat16 else C0
+        if C0p != C0:
+            xp = torch.zeros((B, T, H, W, C0p), dtype=dtype, device=x.device)
+            ops.copy_channels(x, C0, 0, xp, C0p, 0, B * T * H * W, C0)
+            x = xp
+            pm = torch.zeros((B, T, H, W, C0p), dtype=dtype, device=x.device)
+            cur = _conv_fwd(x, C0p, C0, net.patch_mixer, dtype, out=pm, out_ld=C0p)
+        else:
+            cur = _conv_fwd(x, C0, C0, net.patch_mixer, dtype)
+        tape = {"x": x, "C0": C0, "C0p": C0p}
         tape["pm"] = cur
-        cur_ld, cur_c = C0, C0
+        cur_ld, cur_c = C0p, C0
         enc_t, cats = [], []
         for enc in net.encoders:
             Cout = enc.conv1.conv.kernel.shape[4]
@@ -311,8 +348,16 @@ class UNetFn(Function):
             da2 = ops.maxpool122_bwd(skip_view, 2 * Cout, dcur, dcat[..., Cout:], 2 * Cout, Cout)
             da1 = _block_bwd(da2, Cout, t2, enc.conv2, dtype)
             dcur = _block_bwd(da1, Cout, t1, enc.conv1, dtype)
-        x = tape["x"]
-        dx = _conv_bwd(dcur, x, x.shape[-1], x.shape[-1], net.patch_mixer, dtype, need_dx=ctx.needs_input_grad[0])
+        x, C0, C0p = tape["x"], tape["C0"], tape["C0p"]
+        need_dx = ctx.needs_input_grad[0]
+        if C0p != C0:
+            dxp = torch.zeros(x.shape, dtype=x.dtype, device=x.device) if need_dx else None
+            dx = _conv_bwd(dcur, x, C0p, C0, net.patch_mixer, dtype, need_dx=need_dx, dy_ld=C0p, dx_out=dxp, dx_ld=C0p)
+            if need_dx:
+                dx = torch.empty(tuple(x.shape[:4]) + (C0,), dtype=x.dtype, device=x.device)
+                ops.copy_channels(dxp, C0p, 0, dx, C0, 0, dx.numel() // C0, C0)
+        else:
+            dx = _conv_bwd(dcur, x, C0, C0, net.patch_mixer, dtype, need_dx=need_dx)
         F_._notify(list(net.parameters()))
         ctx.tape = None
         return (dx, dout if ctx.has_res else None, None) + (None,) * (len(list(net.parameters())))
