@@ -56,6 +56,21 @@ def run(name, B, T, H, W, Cin, Cout, ks, x_ld, y_ld, timed=False):
         ops.conv3d_dgrad(dy, w, ks, Cin, Cout, dy_ld=y_ld, out=dx, out_ld=x_ld, wprep=wpd)
         torch.cuda.synchronize()
         outs[("dgrad", backend)] = dx.float()
+        # wgrad: dw += x^T (*) dy
+        dwt = torch.zeros(*ks, Cin, Cout, device=dev, dtype=torch.float32)
+        ops.conv3d_wgrad_accum(x, dy, dwt, ks, Cin, Cout, x_ld=x_ld, dy_ld=y_ld)
+        torch.cuda.synchronize()
+        outs[("wgrad", backend)] = dwt.clone()
+        if timed and backend != _ffi.BACKEND_SIMT:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                ops.conv3d_wgrad_accum(x, dy, dwt, ks, Cin, Cout, x_ld=x_ld, dy_ld=y_ld)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            res["wgrad_ms"] = ms
+            res["wgrad_tflops"] = 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout / ms / 1e9
         if timed and backend != _ffi.BACKEND_SIMT and wp is not None:
             for kind in ("fwd", "dgrad"):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -71,7 +86,7 @@ def run(name, B, T, H, W, Cin, Cout, ks, x_ld, y_ld, timed=False):
                 fl = 2.0 * B * T * H * W * ks[0] * ks[1] * ks[2] * Cin * Cout
                 res[kind + "_ms"] = ms
                 res[kind + "_tflops"] = fl / ms / 1e9
-    for kind in ("fwd", "dgrad"):
+    for kind in ("fwd", "dgrad", "wgrad"):
         a, b = outs[(kind, _ffi.BACKEND_AUTO)], outs[(kind, _ffi.BACKEND_SIMT)]
         res[kind + "_err"] = ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
     return res

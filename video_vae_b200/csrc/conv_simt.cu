@@ -7,6 +7,8 @@ namespace vvae {
 
 int conv_tc_supported(const vvae_conv_args& a, int which);
 int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s);
+int conv_wgrad_tc_supported(const vvae_conv_args& a);
+int conv_wgrad_tc_launch(const vvae_conv_args& a, cudaStream_t s);
 
 struct ConvGeom {
   int T, H, W, C;       // C = channels of the gathered tensor
@@ -149,7 +151,8 @@ static int conv_run(const vvae_conv_args* a, int which, vvae_stream_t stream) {
   if (rc) return rc;
   if (a->B == 0) return VVAE_OK;
   cudaStream_t s = as_stream(stream);
-  if (a->backend != VVAE_BACKEND_SIMT && conv_tc_supported(*a, which)) return conv_tc_launch(*a, which, s);
+  if (a->backend != VVAE_BACKEND_SIMT && which == 2 && conv_wgrad_tc_supported(*a)) return conv_wgrad_tc_launch(*a, s);
+  if (a->backend != VVAE_BACKEND_SIMT && which < 2 && conv_tc_supported(*a, which)) return conv_tc_launch(*a, which, s);
   if (a->backend == VVAE_BACKEND_TCGEN05) {
     set_error("conv3d: shape not supported by the tensor-core path");
     return VVAE_ERR_UNSUPPORTED;
