@@ -323,6 +323,11 @@ int attn_simt_bwd(const vvae_attn_args& a, cudaStream_t s) {
 
 }  // namespace vvae
 
+namespace vvae {
+int attn_tc_supported(const vvae_attn_args& a);
+int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s);
+}
+
 using namespace vvae;
 
 static int attn_validate(const vvae_attn_args* a, bool bwd) {
@@ -341,6 +346,11 @@ int vvae_attn_fwd(const vvae_attn_args* args, vvae_stream_t stream) {
   int rc = attn_validate(args, false);
   if (rc) return rc;
   if (args->n_outer == 0) return VVAE_OK;
+  if (args->backend != VVAE_BACKEND_SIMT && attn_tc_supported(*args)) return attn_tc_fwd(*args, as_stream(stream));
+  if (args->backend == VVAE_BACKEND_TCGEN05) {
+    set_error("attention: shape not supported by the tensor-core path");
+    return VVAE_ERR_UNSUPPORTED;
+  }
   return attn_simt_fwd(*args, as_stream(stream));
 }
 

@@ -1,0 +1,381 @@
+// Attention on tcgen05 (bf16, head_dim 64): forward.
+//
+// One CTA = one tile of 128 query rows for one head.  A tile is either
+//   * 128 consecutive positions of ONE sequence of length L = 128 or 256 (spatial attention, NK = L keys), or
+//   * G = 128/L whole sequences of length L in {8,16,32,64} packed block-diagonally (temporal attention and small
+//     spatial grids): the TMA box [64 dims][L positions][G sequences] lands the G sequences one after the other, the
+//     tensor core computes the full 128x128 score tile and the softmax only looks at the L columns of its own sequence
+//     (the other columns get P = 0).  Strided temporal sequences (tokens hw apart) are gathered by the TMA tensor map,
+//     nothing is transposed in memory.
+// Pipeline per CTA: TMA(Q,K | V) -> S = Q.K^T (tcgen05, accumulators in TMEM) -> softmax by 128 threads, one query row
+// per thread straight out of TMEM (key-padding mask and the block-diagonal rule applied in-tile, masked logits =
+// -0.7*FLT_MAX as in jax.nn.dot_product_attention) -> P (bf16) written into shared memory in the UMMA K-major
+// 128B-swizzled layout, over the dead Q/K tiles -> O = P.V (tcgen05; V is consumed MN-major as it lies) ->
+// O / rowsum and the log-sum-exp are stored.  Two CTAs share an SM (<= 97 KB smem, <= 256 TMEM columns each) so one
+// CTA's softmax overlaps the other's MMAs and loads.
+#include <cuda.h>
+#include <cfloat>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace vvae {
+
+#define ATC_BIG_NEG (-0.7f * FLT_MAX)
+
+struct AttnTcPlan {
+  int L, heads, G, NK, nqb, pack_inner, n_outer, n_inner;
+  long long ts_o, ts_i, ts_l;
+  long long tiles;
+  int tiles_per_outer;
+};
+
+struct AttnTcParams {
+  AttnTcPlan pl;
+  bf16* o; long long o_rs;
+  float* lse;
+  const unsigned char* mask; long long mask_seq_div, ms_seq, ms_k;
+  float scale;
+};
+
+__host__ __device__ inline bool atc_len_ok(int L) {
+  return L == 8 || L == 16 || L == 32 || L == 64 || L == 128 || L == 256;
+}
+
+static bool atc_make_plan(const vvae_attn_args& a, AttnTcPlan& p) {
+  if (a.dtype != VVAE_BF16 || a.hd != 64 || !atc_len_ok(a.L)) return false;
+  if (a.mask && (a.ms_head != 0 || a.ms_q != 0)) return false;       // key-padding masks only
+  p.L = a.L; p.heads = a.heads; p.n_outer = a.n_outer; p.n_inner = a.n_inner;
+  p.ts_o = a.tok_stride_outer; p.ts_i = a.tok_stride_inner; p.ts_l = a.tok_stride_pos;
+  if (a.L >= 128) {
+    p.G = 1; p.NK = a.L; p.nqb = a.L / 128; p.pack_inner = 0; p.tiles_per_outer = 0;
+    p.tiles = (long long)a.n_outer * a.n_inner * p.nqb;
+  } else {
+    p.G = 128 / a.L; p.NK = 128; p.nqb = 1;
+    p.pack_inner = a.n_inner > 1 ? 1 : 0;
+    if (p.pack_inner) {
+      p.tiles_per_outer = (a.n_inner + p.G - 1) / p.G;
+      p.tiles = (long long)a.n_outer * p.tiles_per_outer;
+    } else {
+      p.tiles_per_outer = 0;
+      p.tiles = (a.n_outer + p.G - 1) / p.G;
+    }
+  }
+  return p.tiles > 0 && p.tiles < 0x7fffffffLL;
+}
+
+// 4-D map (dims, position, inner sequence index, outer sequence index) over a token-major tensor X[token*rs + col]
+static int atc_make_map(CUtensorMap* m, const void* base, long long rs, const AttnTcPlan& p, int box_l, int box_i, int box_o) {
+  const uint64_t rb = (uint64_t)rs * 2;
+  uint64_t dims[4] = {(uint64_t)p.heads * 64, (uint64_t)p.L, (uint64_t)p.n_inner, (uint64_t)p.n_outer};
+  uint64_t str[3] = {(uint64_t)p.ts_l * rb, (uint64_t)p.ts_i * rb, (uint64_t)p.ts_o * rb};
+  if (p.n_inner == 1 || str[1] == 0) str[1] = str[0] * (uint64_t)p.L;   // extent-1 dimension: any legal stride
+  if (p.n_outer == 1 || str[2] == 0) str[2] = str[1] * (uint64_t)p.n_inner;
+  uint32_t box[4] = {64, (uint32_t)box_l, (uint32_t)box_i, (uint32_t)box_o};
+  return encode_tmap_nd_bf16(m, base, 4, dims, str, box, 128);
+}
+
+__device__ __forceinline__ float atc_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(sm100::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(sm100::smem_u32(bar)), "r"(c0), "r"(c1),
+      "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// row r of a tile -> (sequence index, position, token index); returns false for rows beyond the tensor
+struct AtcRow { long long seq, tok; int l; bool ok; };
+template <bool PACKED>
+__device__ __forceinline__ AtcRow atc_row(const AttnTcPlan& p, long long tile, int r) {
+  AtcRow o;
+  if (PACKED) {
+    const int si = r / p.L;
+    o.l = r - si * p.L;
+    long long outer, inner;
+    if (p.pack_inner) {
+      outer = tile / p.tiles_per_outer;
+      inner = (tile % p.tiles_per_outer) * p.G + si;
+      o.ok = inner < p.n_inner;
+    } else {
+      outer = tile * p.G + si;
+      inner = 0;
+      o.ok = outer < p.n_outer;
+    }
+    o.seq = outer * p.n_inner + inner;
+    o.tok = outer * p.ts_o + inner * p.ts_i + (long long)o.l * p.ts_l;
+  } else {
+    const long long seq = tile / p.nqb;
+    const int qb = (int)(tile % p.nqb);
+    o.l = qb * 128 + r;
+    o.seq = seq;
+    o.ok = true;
+    o.tok = (seq / p.n_inner) * p.ts_o + (seq % p.n_inner) * p.ts_i + (long long)o.l * p.ts_l;
+  }
+  return o;
+}
+
+template <int NK, bool PACKED>
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                      const __grid_constant__ CUtensorMap tma_v, const AttnTcParams q) {
+  const AttnTcPlan& p = q.pl;
+  constexpr int P_BYTES = (NK / 64) * 16384;                 // P: NK/64 K-blocks of [128 rows x 128 B]
+  constexpr int QK_BYTES = 16384 + NK * 128;
+  constexpr int R0_BYTES = P_BYTES > QK_BYTES ? P_BYTES : QK_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                 // [128][64] K-major SW128
+  uint8_t* sK = smem + 16384;         // [NK][64]  K-major SW128
+  uint8_t* sP = smem;                 // overlays Q|K once S is complete
+  uint8_t* sV = smem + R0_BYTES;      // [NK][64]  (MN-major B operand of P.V)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NK * 128);
+  uint64_t* qk_full = bars;
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* kpen = reinterpret_cast<float*>(bars + 6);   // [NK] 0 = attend, 1 = masked key
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tile = blockIdx.x;
+  const int h = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_q);
+    sm100::tma_prefetch_desc(&tma_k);
+    sm100::tma_prefetch_desc(&tma_v);
+    sm100::mbar_init(qk_full, 1);
+    sm100::mbar_init(v_full, 1);
+    sm100::mbar_init(s_full, 1);
+    sm100::mbar_init(p_full, 4);
+    sm100::mbar_init(o_full, 1);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<NK>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int c1q, c1k, c2, c3;
+      if (PACKED) {
+        c1q = c1k = 0;
+        if (p.pack_inner) { c3 = (int)(tile / p.tiles_per_outer); c2 = (int)(tile % p.tiles_per_outer) * p.G; }
+        else { c3 = (int)tile * p.G; c2 = 0; }
+      } else {
+        const long long seq = tile / p.nqb;
+        c1q = (int)(tile % p.nqb) * 128; c1k = 0;
+        c3 = (int)(seq / p.n_inner); c2 = (int)(seq % p.n_inner);
+      }
+      sm100::mbar_expect_tx(qk_full, 16384 + NK * 128);
+      tma_load_4d(sQ, &tma_q, qk_full, h * 64, c1q, c2, c3);
+      tma_load_4d(sK, &tma_k, qk_full, h * 64, c1k, c2, c3);
+      sm100::mbar_expect_tx(v_full, NK * 128);
+      tma_load_4d(sV, &tma_v, v_full, h * 64, c1k, c2, c3);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // S[128 x NK] = Q . K^T : both operands K-major (head dim contiguous), 4 K-steps of 16
+      constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, NK, false, false);
+      sm100::mbar_wait(qk_full, 0);
+      sm100::tc_fence_after();
+      const uint32_t qa = sm100::smem_u32(sQ), ka = sm100::smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        sm100::umma_f16(tmem_base, sm100::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                        sm100::make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+      sm100::umma_commit(s_full);
+      // O[128 x 64] = P . V : P K-major (keys contiguous, 64-key blocks 16 KB apart), V MN-major (head dim contiguous)
+      constexpr uint32_t idesc_o = sm100::make_idesc_bf16(128, 64, false, true);
+      sm100::mbar_wait(v_full, 0);
+      sm100::mbar_wait(p_full, 0);
+      sm100::tc_fence_after();
+      const uint32_t pa = sm100::smem_u32(sP), va = sm100::smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < NK / 16; ++k)
+        sm100::umma_f16(tmem_base, sm100::make_smem_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                        sm100::make_smem_desc_sw128(va + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+      sm100::umma_commit(o_full);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // query row == TMEM lane
+    const int tid = threadIdx.x - 64;                  // 0..127
+    // key penalties for the tile's NK key rows
+    for (int c = tid; c < NK; c += 128) {
+      float pen = 0.f;
+      if (q.mask) {
+        AtcRow kr = atc_row<PACKED>(p, PACKED ? tile : (tile / p.nqb) * p.nqb, c);   // unpacked: key c is position c
+        if (kr.ok && q.mask[(kr.seq / q.mask_seq_div) * q.ms_seq + (long long)kr.l * q.ms_k] == 0) pen = 1.f;
+      }
+      kpen[c] = pen;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const AtcRow row = atc_row<PACKED>(p, tile, r);
+    const int seq_c0 = PACKED ? (r / p.L) * p.L : 0;             // first key column of this row's sequence
+    int cbeg = 0, cend = NK;
+    if (PACKED) {
+      if (p.L >= 32) { cbeg = seq_c0; cend = seq_c0 + p.L; }
+      else { cbeg = quarter * 32; cend = cbeg + 32; }
+    }
+    const float k2 = q.scale * 1.4426950408889634f;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+
+    sm100::mbar_wait(s_full, 0);
+    sm100::tc_fence_after();
+    // pass 1: row maximum of the (masked) logits
+    float mx = -INFINITY;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t sr[32];
+      sm100::tmem_ld_32x32(trow + c0, sr);
+      sm100::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = c0 + i;
+        const bool inseq = !PACKED || (unsigned)(c - seq_c0) < (unsigned)p.L;
+        const float s = kpen[c] != 0.f ? ATC_BIG_NEG : __uint_as_float(sr[i]) * q.scale;
+        if (inseq) mx = fmaxf(mx, s);
+      }
+    }
+    // pass 2: p = exp(s - max), row sum, bf16 P into the swizzled K-major operand tile
+    const float mx2 = mx * 1.4426950408889634f;
+    float sum = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const uint32_t sw = (uint32_t)(r & 7);
+    for (int c0 = 0; c0 < NK; c0 += 32) {
+      uint8_t* pblk = prow + (c0 >> 6) * 16384;
+      const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;     // first 16-byte chunk of this 32-key group inside the 128 B row
+      if (c0 < cbeg || c0 >= cend) {                      // warp-uniform
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(pblk + (((ch0 + j) ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      uint32_t sr[32];
+      sm100::tmem_ld_32x32(trow + c0, sr);
+      sm100::tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int c = c0 + i;
+        const bool inseq = !PACKED || (unsigned)(c - seq_c0) < (unsigned)p.L;
+        const float e = kpen[c] != 0.f ? (mx == ATC_BIG_NEG ? 1.f : 0.f) : atc_exp2(__uint_as_float(sr[i]) * k2 - mx2);
+        pv[i] = inseq ? e : 0.f;
+        sum += pv[i];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(pv[8 * j + 0], pv[8 * j + 1]);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(pv[8 * j + 2], pv[8 * j + 3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(pv[8 * j + 4], pv[8 * j + 5]);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(pv[8 * j + 6], pv[8 * j + 7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(pblk + (((ch0 + j) ^ sw) << 4)) = pk;
+      }
+    }
+    sm100::fence_proxy_async();      // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+    sm100::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) sm100::mbar_arrive(p_full);
+
+    // epilogue: O / rowsum -> bf16, log-sum-exp
+    sm100::mbar_wait(o_full, 0);
+    sm100::tc_fence_after();
+    const float inv = 1.f / sum;
+    bf16* orow = q.o + row.tok * q.o_rs + (long long)h * 64;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t orr[32];
+      sm100::tmem_ld_32x32(trow + c0, orr);
+      sm100::tmem_ld_wait();
+      if (row.ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          Vec16<bf16> v;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) v.set(t, __uint_as_float(orr[8 * j + t]) * inv);
+          v.store(orow + c0 + 8 * j);
+        }
+      }
+    }
+    if (row.ok && q.lse) q.lse[(row.seq * p.heads + h) * p.L + row.l] = mx + __logf(sum);
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<NK>(tmem_base);
+  }
+}
+
+template <int NK, bool PACKED>
+static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
+  constexpr int P_BYTES = (NK / 64) * 16384, QK_BYTES = 16384 + NK * 128;
+  constexpr int R0 = P_BYTES > QK_BYTES ? P_BYTES : QK_BYTES;
+  constexpr int SMEM = R0 + NK * 128 + 64 + NK * 4 + 1024;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if (PACKED) {
+    const int bi = p.pack_inner ? p.G : 1, bo = p.pack_inner ? 1 : p.G;
+    if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, p.L, bi, bo))) return rc;
+    if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, p.L, bi, bo))) return rc;
+    if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, p.L, bi, bo))) return rc;
+  } else {
+    if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, 128, 1, 1))) return rc;
+    if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, NK, 1, 1))) return rc;
+    if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, NK, 1, 1))) return rc;
+  }
+  AttnTcParams q;
+  q.pl = p;
+  q.o = (bf16*)a.o; q.o_rs = a.o_rs; q.lse = a.lse;
+  q.mask = a.mask; q.mask_seq_div = a.mask_seq_div > 0 ? a.mask_seq_div : 1; q.ms_seq = a.ms_seq; q.ms_k = a.ms_k;
+  q.scale = a.scale;
+  auto kern = attn_fwd_sm100_kernel<NK, PACKED>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+      return VVAE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)p.tiles, (unsigned)p.heads);
+  kern<<<grid, 192, SMEM, s>>>(mq, mk, mv, q);
+  return check_launch("attn_fwd_sm100");
+}
+
+int attn_tc_supported(const vvae_attn_args& a) {
+  AttnTcPlan p;
+  if (!atc_make_plan(a, p)) return 0;
+  if (((uintptr_t)a.q % 16) || ((uintptr_t)a.k % 16) || ((uintptr_t)a.v % 16) || ((uintptr_t)a.o % 16)) return 0;
+  if ((a.q_rs % 8) || (a.k_rs % 8) || (a.v_rs % 8) || (a.o_rs % 8)) return 0;
+  if (a.heads > 65535) return 0;
+  return 1;
+}
+
+int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s) {
+  AttnTcPlan p;
+  if (!atc_make_plan(a, p)) {
+    set_error("attention: shape not supported by the tensor-core path");
+    return VVAE_ERR_UNSUPPORTED;
+  }
+  if (p.G > 1) return atc_launch_fwd<128, true>(a, p, s);
+  if (p.NK == 128) return atc_launch_fwd<128, false>(a, p, s);
+  return atc_launch_fwd<256, false>(a, p, s);
+}
+
+}  // namespace vvae

@@ -14,6 +14,7 @@ from ._ffi import (BACKEND_AUTO, BF16, EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SI
 LN_EPS = 1e-6
 
 CONV_BACKEND = BACKEND_AUTO  # tests force BACKEND_SIMT to cross-check the tensor-core conv against the generic one
+ATTN_BACKEND = BACKEND_AUTO  # same for attention
 
 # bench.py sets PROFILE to a list; instrumented ops then append (class, flops, bytes, start_event, stop_event).
 PROFILE = None
@@ -170,7 +171,7 @@ def _attn_args(geom, heads, hd, q, k, v, o, lse, mask, scale):
         a.mask, a.mask_seq_div = None, 1
     a.scale = scale
     a.dtype = dt(q)
-    a.backend = BACKEND_AUTO
+    a.backend = ATTN_BACKEND
     return a
 
 
