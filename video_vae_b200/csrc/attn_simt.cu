@@ -161,9 +161,11 @@ attn_bwd_dq_kernel(AttnGeom g, const T* __restrict__ q, const T* __restrict__ k,
       }
       s *= g.scale;
       const bool valid = kj < g.L;
-      if (valid && !g.attend(seq, h, qi, kj)) s = AT_BIG_NEG;
+      const bool masked = valid && !g.attend(seq, h, qi, kj);
+      if (masked) s = AT_BIG_NEG;
       float p = valid ? __expf(s - ls[i]) : 0.f;
-      float ds = p * (dp - dl[i]);
+      if (masked && ls[i] <= 0.5f * AT_BIG_NEG) p = 1.f / (float)g.L;   // fully masked row: uniform
+      float ds = masked ? 0.f : p * (dp - dl[i]);                       // where(mask, logits, const): no gradient
       for (int jj = 0; jj < AT_KB; ++jj) {
         float dj = __shfl_sync(0xffffffffu, ds, jj);
 #pragma unroll
@@ -230,9 +232,11 @@ attn_bwd_dkv_kernel(AttnGeom g, const T* __restrict__ q, const T* __restrict__ k
         dp = fmaf(sdO[lane * ldk + d], vv[d], dp);
       }
       s *= g.scale;
-      if (qvalid && !g.attend(seq, h, qi, kj)) s = AT_BIG_NEG;
+      const bool masked = qvalid && !g.attend(seq, h, qi, kj);
+      if (masked) s = AT_BIG_NEG;
       float p = qvalid ? __expf(s - ls) : 0.f;
-      float ds = p * (dp - dl);
+      if (masked && ls <= 0.5f * AT_BIG_NEG) p = 1.f / (float)g.L;
+      float ds = masked ? 0.f : p * (dp - dl);
       float pr = round_to<T>(p);
       for (int ii = 0; ii < AT_KB; ++ii) {
         float pi = __shfl_sync(0xffffffffu, pr, ii);
@@ -326,6 +330,8 @@ int attn_simt_bwd(const vvae_attn_args& a, cudaStream_t s) {
 namespace vvae {
 int attn_tc_supported(const vvae_attn_args& a);
 int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s);
+int attn_tc_bwd_supported(const vvae_attn_args& a);
+int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s);
 }
 
 using namespace vvae;
@@ -358,6 +364,11 @@ int vvae_attn_bwd(const vvae_attn_args* args, vvae_stream_t stream) {
   int rc = attn_validate(args, true);
   if (rc) return rc;
   if (args->n_outer == 0) return VVAE_OK;
+  if (args->backend != VVAE_BACKEND_SIMT && attn_tc_bwd_supported(*args)) return attn_tc_bwd(*args, as_stream(stream));
+  if (args->backend == VVAE_BACKEND_TCGEN05) {
+    set_error("attention bwd: shape not supported by the tensor-core path");
+    return VVAE_ERR_UNSUPPORTED;
+  }
   return attn_simt_bwd(*args, as_stream(stream));
 }
 

@@ -358,12 +358,366 @@ static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   return check_launch("attn_fwd_sm100");
 }
 
+
+// ====================================================================================================== backward
+// One CTA = one tile set of one head: NB x NB tiles of 128 queries x 128 keys (NB = 1: one 128-row tile, i.e. a
+// sequence of 128 or a block-diagonal pack of short sequences; NB = 2: a sequence of 256).  Everything a tile needs
+// (Q, K, V, dO: NB x 16 KB each) is TMA-staged once; the five contractions of the attention backward run on tcgen05
+// with all accumulators resident in TMEM (512 columns):
+//     S  = Q_i K_j^T          [  0,128)        dP = dO_i V_j^T       [128,256)
+//     dQ_i += dS K_j          [256+64i, +64)   dK_j += dS^T Q_i      [256+64NB, +64)     dV_j += P^T dO_i   [.. +64, +64)
+// 8 softmax warps (warp group g owns key columns [64g, 64g+64) of the tile) read S and dP out of TMEM, rebuild
+// P = exp(S*scale - LSE), form dS = P o (dP - D) * scale with D = rowsum(dO o O), and write bf16 P and dS into shared
+// memory in ONE 128B-swizzled layout that the tensor core reads both K-major (dQ = dS.K) and MN-major (dV = P^T.dO,
+// dK = dS^T.Q), so no transposed copy exists anywhere.  The MMA warp issues S/dP of tile t+1 before the three output
+// contractions of tile t, so the softmax of t+1 overlaps them.  Mask semantics follow the forward: masked logits are
+// the constant -0.7*FLT_MAX, so they receive no gradient; a fully masked row has uniform P (dV only).
+struct AttnTcBwdParams {
+  AttnTcPlan pl;
+  const bf16* o; long long o_rs;
+  const float* lse;
+  const unsigned char* mask; long long mask_seq_div, ms_seq, ms_k;
+  bf16 *dq, *dk, *dv; long long dq_rs, dk_rs, dv_rs;
+  float scale;
+};
+
+// row r of 128-row block `blk` of the CTA's tile set
+template <bool PACKED>
+__device__ __forceinline__ AtcRow atc_bwd_row(const AttnTcPlan& p, long long tile, int blk, int r) {
+  return atc_row<PACKED>(p, PACKED ? tile : tile * p.nqb + blk, r);
+}
+
+__device__ __forceinline__ uint32_t atc_pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int NB, bool PACKED>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                      const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                      const AttnTcBwdParams q) {
+  const AttnTcPlan& p = q.pl;
+  constexpr int BLK = 16384;                       // one [128 rows x 64 bf16] swizzled tile
+  constexpr int NT = NB * NB;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 256 + 64 * NB, COL_DV = COL_DK + 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + NB * BLK;
+  uint8_t* sV = sK + NB * BLK;
+  uint8_t* sdO = sV + NB * BLK;
+  uint8_t* sP = sdO + NB * BLK;                    // [2 key halves][128 q][64 keys] bf16, swizzled
+  uint8_t* sdS = sP + 2 * BLK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * BLK);
+  uint64_t* ld_bar = bars;                         // [NB] block b of Q, K, V, dO has landed
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* mma3_done = bars + 4;
+  uint64_t* kv_drained = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* kpen = reinterpret_cast<float*>(bars + 7);   // [NB*128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long tile = blockIdx.x;
+  const int h = blockIdx.y;
+
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_q);
+    sm100::tma_prefetch_desc(&tma_k);
+    sm100::tma_prefetch_desc(&tma_v);
+    sm100::tma_prefetch_desc(&tma_do);
+    for (int b = 0; b < NB; ++b) sm100::mbar_init(&ld_bar[b], 1);
+    sm100::mbar_init(s_full, 1);
+    sm100::mbar_init(p_full, 8);
+    sm100::mbar_init(mma3_done, 1);
+    sm100::mbar_init(kv_drained, 8);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int c2, c3;
+      if (PACKED) {
+        if (p.pack_inner) { c3 = (int)(tile / p.tiles_per_outer); c2 = (int)(tile % p.tiles_per_outer) * p.G; }
+        else { c3 = (int)tile * p.G; c2 = 0; }
+      } else {
+        c3 = (int)(tile / p.n_inner); c2 = (int)(tile % p.n_inner);
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        sm100::mbar_expect_tx(&ld_bar[b], 4 * BLK);
+        tma_load_4d(sQ + b * BLK, &tma_q, &ld_bar[b], h * 64, b * 128, c2, c3);
+        tma_load_4d(sK + b * BLK, &tma_k, &ld_bar[b], h * 64, b * 128, c2, c3);
+        tma_load_4d(sV + b * BLK, &tma_v, &ld_bar[b], h * 64, b * 128, c2, c3);
+        tma_load_4d(sdO + b * BLK, &tma_do, &ld_bar[b], h * 64, b * 128, c2, c3);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, 128, false, false);   // S, dP: both K-major
+      constexpr uint32_t idesc_kv = sm100::make_idesc_bf16(128, 64, true, true);     // dV, dK: A^T (MN-major), B MN-major
+      constexpr uint32_t idesc_q = sm100::make_idesc_bf16(128, 64, false, true);     // dQ: A K-major, B MN-major
+      const uint32_t aQ = sm100::smem_u32(sQ), aK = sm100::smem_u32(sK), aV = sm100::smem_u32(sV);
+      const uint32_t aO = sm100::smem_u32(sdO), aP = sm100::smem_u32(sP), aS = sm100::smem_u32(sdS);
+      auto issue_sdp = [&](int t) {
+        const int j = t / NB, i = t % NB;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + COL_S, sm100::make_smem_desc_sw128(aQ + i * BLK + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(aK + j * BLK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + COL_DP, sm100::make_smem_desc_sw128(aO + i * BLK + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(aV + j * BLK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        sm100::umma_commit(s_full);
+      };
+      sm100::mbar_wait(&ld_bar[0], 0);
+      sm100::tc_fence_after();
+      issue_sdp(0);
+      int loaded = 1;
+#pragma unroll 1
+      for (int t = 0; t < NT; ++t) {
+        const int j = t / NB, i = t % NB;
+        sm100::mbar_wait(p_full, t & 1);
+        sm100::tc_fence_after();
+        if (t + 1 < NT) {
+          const int need = max((t + 1) / NB, (t + 1) % NB) + 1;
+          while (loaded < need) { sm100::mbar_wait(&ld_bar[loaded], 0); ++loaded; }
+          sm100::tc_fence_after();
+          issue_sdp(t + 1);
+        }
+        if (i == 0 && j > 0) {            // dK/dV of the previous key block must have been read out
+          sm100::mbar_wait(kv_drained, (j - 1) & 1);
+          sm100::tc_fence_after();
+        }
+        // dV_j (+)= P^T dO_i ; dK_j (+)= dS^T Q_i : contraction over the 128 queries, 16 per step
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sm100::umma_f16(tmem_base + COL_DV, sm100::make_smem_desc_sw128(aP + k * 2048, BLK, 1024),
+                          sm100::make_smem_desc_sw128(aO + i * BLK + k * 2048, 8192, 1024), idesc_kv,
+                          (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sm100::umma_f16(tmem_base + COL_DK, sm100::make_smem_desc_sw128(aS + k * 2048, BLK, 1024),
+                          sm100::make_smem_desc_sw128(aQ + i * BLK + k * 2048, 8192, 1024), idesc_kv,
+                          (i > 0 || k > 0) ? 1u : 0u);
+        // dQ_i (+)= dS K_j : contraction over the 128 keys
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sm100::umma_f16(tmem_base + COL_DQ + 64 * i,
+                          sm100::make_smem_desc_sw128(aS + (k >> 2) * BLK + (k & 3) * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(aK + j * BLK + k * 2048, 8192, 1024), idesc_q,
+                          (j > 0 || k > 0) ? 1u : 0u);
+        sm100::umma_commit(mma3_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int g = (warp - 2) >> 2;                     // key-column half of the tile
+    const int r = quarter * 32 + lane;                 // row of the 128-row block == TMEM lane
+    const int tid = threadIdx.x - 64;                  // 0..255
+    for (int c = tid; c < NB * 128; c += 256) {
+      float pen = 0.f;
+      if (q.mask) {
+        AtcRow kr = atc_bwd_row<PACKED>(p, tile, c >> 7, c & 127);
+        if (kr.ok && q.mask[(kr.seq / q.mask_seq_div) * q.ms_seq + (long long)kr.l * q.ms_k] == 0) pen = 1.f;
+      }
+      kpen[c] = pen;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sw = (uint32_t)(r & 7);
+    const int seq_c0 = PACKED ? (r / p.L) * p.L : 0;
+    const float k2 = q.scale * 1.4426950408889634f;
+    const float inv_l = 1.f / (float)p.L;
+
+    // per query block: row validity, LSE (in log2 units), D = rowsum(dO o O)
+    float lse2[NB], dlt[NB];
+    bool rok[NB], allm[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const AtcRow row = atc_bwd_row<PACKED>(p, tile, i, r);
+      rok[i] = row.ok;
+      float l = 0.f, d = 0.f;
+      sm100::mbar_wait(&ld_bar[i], 0);
+      if (row.ok) {
+        l = q.lse[(row.seq * p.heads + h) * p.L + row.l];
+        const bf16* orow = q.o + row.tok * q.o_rs + (long long)h * 64;
+        const uint8_t* drow = sdO + i * BLK + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          Vec16<bf16> a, b;
+          a.load(orow + 8 * ch);
+          b.raw = *reinterpret_cast<const uint4*>(drow + (((uint32_t)ch ^ sw) << 4));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(a.get(e), b.get(e), d);
+        }
+      }
+      allm[i] = l <= 0.5f * ATC_BIG_NEG;
+      lse2[i] = l * 1.4426950408889634f;
+      dlt[i] = d;
+    }
+
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+      const int j = t / NB, i = t % NB;
+      float my_lse2 = lse2[0], my_d = dlt[0];
+      bool my_ok = rok[0], my_allm = allm[0];
+#pragma unroll
+      for (int ii = 1; ii < NB; ++ii)
+        if (i == ii) { my_lse2 = lse2[ii]; my_d = dlt[ii]; my_ok = rok[ii]; my_allm = allm[ii]; }
+      sm100::mbar_wait(s_full, t & 1);
+      sm100::tc_fence_after();
+      uint32_t pkP[32], pkS[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = g * 64 + hf * 32;
+        uint32_t sr[32], dr[32];
+        sm100::tmem_ld_32x32(trow + COL_S + c0, sr);
+        sm100::tmem_ld_32x32(trow + COL_DP + c0, dr);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int c = c0 + e + u;
+            const bool inseq = my_ok && (!PACKED || (unsigned)(c - seq_c0) < (unsigned)p.L);
+            const bool masked = kpen[j * 128 + c] != 0.f;
+            float pr = atc_exp2(__uint_as_float(sr[e + u]) * k2 - my_lse2);
+            if (masked) pr = my_allm ? inv_l : 0.f;
+            if (!inseq) pr = 0.f;
+            pv[u] = pr;
+            dv[u] = masked ? 0.f : pr * (__uint_as_float(dr[e + u]) - my_d) * q.scale;
+          }
+          pkP[hf * 16 + (e >> 1)] = atc_pack2(pv[0], pv[1]);
+          pkS[hf * 16 + (e >> 1)] = atc_pack2(dv[0], dv[1]);
+        }
+      }
+      sm100::tc_fence_before();
+      if (t > 0) sm100::mbar_wait(mma3_done, (t - 1) & 1);      // P / dS tiles of the previous tile are consumed
+      {
+        uint8_t* prow = sP + g * BLK + r * 128;
+        uint8_t* srow = sdS + g * BLK + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t off = (((uint32_t)ch ^ sw) << 4);
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(pkP[4 * ch], pkP[4 * ch + 1], pkP[4 * ch + 2], pkP[4 * ch + 3]);
+          *reinterpret_cast<uint4*>(srow + off) = make_uint4(pkS[4 * ch], pkS[4 * ch + 1], pkS[4 * ch + 2], pkS[4 * ch + 3]);
+        }
+      }
+      sm100::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(p_full);
+
+      if (i == NB - 1) {                    // key block j is complete: warp group 0 drains dK_j, warp group 1 dV_j
+        sm100::mbar_wait(mma3_done, t & 1);
+        sm100::tc_fence_after();
+        const AtcRow kr = atc_bwd_row<PACKED>(p, tile, j, r);
+        bf16* dst = (g == 0 ? q.dk + kr.tok * q.dk_rs : q.dv + kr.tok * q.dv_rs) + (long long)h * 64;
+        const uint32_t col = g == 0 ? COL_DK : COL_DV;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t rr[32];
+          sm100::tmem_ld_32x32(trow + col + c0, rr);
+          sm100::tmem_ld_wait();
+          if (kr.ok) {
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              uint4 o4 = make_uint4(atc_pack2(__uint_as_float(rr[8 * v4 + 0]), __uint_as_float(rr[8 * v4 + 1])),
+                                    atc_pack2(__uint_as_float(rr[8 * v4 + 2]), __uint_as_float(rr[8 * v4 + 3])),
+                                    atc_pack2(__uint_as_float(rr[8 * v4 + 4]), __uint_as_float(rr[8 * v4 + 5])),
+                                    atc_pack2(__uint_as_float(rr[8 * v4 + 6]), __uint_as_float(rr[8 * v4 + 7])));
+              *reinterpret_cast<uint4*>(dst + c0 + 8 * v4) = o4;
+            }
+          }
+        }
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(kv_drained);
+      }
+      if (j == NB - 1) {                    // query block i is complete: each warp group drains 32 of dQ_i's 64 columns
+        sm100::mbar_wait(mma3_done, t & 1);
+        sm100::tc_fence_after();
+        const AtcRow qr = atc_bwd_row<PACKED>(p, tile, i, r);
+        bf16* dst = q.dq + qr.tok * q.dq_rs + (long long)h * 64 + g * 32;
+        uint32_t rr[32];
+        sm100::tmem_ld_32x32(trow + COL_DQ + 64 * i + g * 32, rr);
+        sm100::tmem_ld_wait();
+        if (qr.ok) {
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 o4 = make_uint4(atc_pack2(__uint_as_float(rr[8 * v4 + 0]), __uint_as_float(rr[8 * v4 + 1])),
+                                  atc_pack2(__uint_as_float(rr[8 * v4 + 2]), __uint_as_float(rr[8 * v4 + 3])),
+                                  atc_pack2(__uint_as_float(rr[8 * v4 + 4]), __uint_as_float(rr[8 * v4 + 5])),
+                                  atc_pack2(__uint_as_float(rr[8 * v4 + 6]), __uint_as_float(rr[8 * v4 + 7])));
+            *reinterpret_cast<uint4*>(dst + 8 * v4) = o4;
+          }
+        }
+      }
+    }
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int NB, bool PACKED>
+static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
+  constexpr int SMEM = (4 * NB + 4) * 16384 + 64 + NB * 128 * 4 + 1024;
+  CUtensorMap mq, mk, mv, md;
+  int rc;
+  const int bl = PACKED ? p.L : 128;
+  const int bi = PACKED ? (p.pack_inner ? p.G : 1) : 1, bo = PACKED ? (p.pack_inner ? 1 : p.G) : 1;
+  if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, bl, bi, bo))) return rc;
+  if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, bl, bi, bo))) return rc;
+  if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, bl, bi, bo))) return rc;
+  if ((rc = atc_make_map(&md, a.d_o, a.do_rs, p, bl, bi, bo))) return rc;
+  AttnTcBwdParams q;
+  q.pl = p;
+  q.o = (const bf16*)a.o; q.o_rs = a.o_rs; q.lse = a.lse;
+  q.mask = a.mask; q.mask_seq_div = a.mask_seq_div > 0 ? a.mask_seq_div : 1; q.ms_seq = a.ms_seq; q.ms_k = a.ms_k;
+  q.dq = (bf16*)a.dq; q.dk = (bf16*)a.dk; q.dv = (bf16*)a.dv;
+  q.dq_rs = a.dq_rs; q.dk_rs = a.dk_rs; q.dv_rs = a.dv_rs;
+  q.scale = a.scale;
+  auto kern = attn_bwd_sm100_kernel<NB, PACKED>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention bwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+      return VVAE_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  const long long tiles = PACKED ? p.tiles : (long long)p.n_outer * p.n_inner;
+  dim3 grid((unsigned)tiles, (unsigned)p.heads);
+  kern<<<grid, 320, SMEM, s>>>(mq, mk, mv, md, q);
+  return check_launch("attn_bwd_sm100");
+}
+
 int attn_tc_supported(const vvae_attn_args& a) {
   AttnTcPlan p;
   if (!atc_make_plan(a, p)) return 0;
   if (((uintptr_t)a.q % 16) || ((uintptr_t)a.k % 16) || ((uintptr_t)a.v % 16) || ((uintptr_t)a.o % 16)) return 0;
   if ((a.q_rs % 8) || (a.k_rs % 8) || (a.v_rs % 8) || (a.o_rs % 8)) return 0;
   if (a.heads > 65535) return 0;
+  return 1;
+}
+
+int attn_tc_bwd_supported(const vvae_attn_args& a) {
+  if (!attn_tc_supported(a)) return 0;
+  if (((uintptr_t)a.d_o % 16) || ((uintptr_t)a.dq % 16) || ((uintptr_t)a.dk % 16) || ((uintptr_t)a.dv % 16)) return 0;
+  if ((a.do_rs % 8) || (a.dq_rs % 8) || (a.dk_rs % 8) || (a.dv_rs % 8)) return 0;
   return 1;
 }
 
@@ -376,6 +730,17 @@ int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s) {
   if (p.G > 1) return atc_launch_fwd<128, true>(a, p, s);
   if (p.NK == 128) return atc_launch_fwd<128, false>(a, p, s);
   return atc_launch_fwd<256, false>(a, p, s);
+}
+
+int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s) {
+  AttnTcPlan p;
+  if (!atc_make_plan(a, p)) {
+    set_error("attention bwd: shape not supported by the tensor-core path");
+    return VVAE_ERR_UNSUPPORTED;
+  }
+  if (p.G > 1) return atc_launch_bwd<1, true>(a, p, s);
+  if (p.NK == 128) return atc_launch_bwd<1, false>(a, p, s);
+  return atc_launch_bwd<2, false>(a, p, s);
 }
 
 }  // namespace vvae
