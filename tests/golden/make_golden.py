@@ -1,0 +1,89 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures of tests/golden/ from the CPU oracle (fp32).
+
+    python tests/golden/make_golden.py
+
+The reference (JAX/Flax) cannot be imported in this container, so these vectors pin the ORACLE (oracle/*.py, the CPU
+restatement of train/layers.py, train/model.py, train/unet.py and the loss of
+train/legacy/training_loop_adversarial.py:90-124), not the reference itself ("parity unpinned").
+They make the oracle's behaviour a committed artefact: tests/test_oracle.py re-derives them on CPU and
+tests/test_parity_gpu.py checks the CUDA path against them at the fp32 tolerance of north_star (rel 1e-4).
+Inputs and weights are regenerated from seeds by `build_case`; only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = (64, 64, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4)   # the reference's CPU test config (claude_distributed/test_rl_model.py)
+B, T = 2, 6
+
+
+def build_case():
+    """Seeded oracle model + inputs shared by the generator and the tests."""
+    from oracle import Rngs
+    from oracle.model import VideoVAE
+    torch.manual_seed(0)
+    model = VideoVAE(*CFG, Rngs(2))
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():   # the reference zero-inits final_conv (train/unet.py:144-153): randomise it so the UNet matters
+        model.decoder.unet.final_conv.kernel.copy_(torch.randn(model.decoder.unet.final_conv.kernel.shape, generator=g) * 0.05)
+    hw = (CFG[0] // CFG[3]) * (CFG[1] // CFG[3])
+    video = torch.rand(B, T, CFG[0], CFG[1], 3, generator=g)
+    mask = torch.tensor([[True] * T, [True] * (T - 2) + [False] * 2])
+    noise = torch.randn(B, T, hw, CFG[3] * CFG[3] * 3 // CFG[10], generator=g)
+    gumbel_u = torch.rand(B, T, 1, generator=g)
+    return model, video, mask, noise, gumbel_u, hw
+
+
+def run_oracle():
+    from oracle import Rngs
+    from oracle.losses import DEFAULT_HPARAMS, expand_mask, loss_fn
+    model, video, mask, noise, gumbel_u, hw = build_case()
+    loss, aux = loss_fn(model, video, expand_mask(mask, hw), mask, Rngs(0), DEFAULT_HPARAMS, noise=noise, gumbel_u=gumbel_u)
+    loss.backward()
+    out = {"loss": loss.detach().numpy(), "MSE": aux["MSE"].detach().numpy(), "MAE": aux["MAE"].detach().numpy(),
+           "kl_loss": aux["kl_loss"].detach().numpy(), "selection_loss": aux["selection_loss"].detach().numpy(),
+           "selection": aux["selection"].detach().reshape(B, T).numpy(),
+           "mean_slice": aux["mean"].detach()[:, :, ::5, ::7].numpy(),
+           "logvar_slice": aux["logvar"].detach()[:, :, ::5, ::7].numpy(),
+           "compressed_slice": aux["compressed"].detach()[:, :, ::5, ::7].numpy(),
+           "recon_slice": aux["reconstruction"].detach()[:, :, ::9, ::11, :].numpy()}
+    names, norms = [], []
+    for n, p in model.named_parameters():
+        names.append(n)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms, dtype=np.float64)
+    out["grad_qkv_slice"] = model.encoder.layers[0].TemporalAttention.qkv_projection.kernel.grad[::16, ::32].numpy()
+    out["grad_conv_slice"] = model.decoder.unet.encoders[0].conv1.conv.kernel.grad[:, :, :, ::4, ::4].numpy()
+    return out
+
+
+def run_attention_kat():
+    """train/attention_mask_tests.py shapes: q,k,v [17,15,19,13], the last 5 keys masked."""
+    from oracle.nn import dot_product_attention
+    g = torch.Generator().manual_seed(3)
+    q, k, v = (torch.randn(17, 15, 19, 13, generator=g) for _ in range(3))
+    mask = torch.ones(17, 19, 15, 15, dtype=torch.bool)
+    mask[..., 10:] = False
+    o = dot_product_attention(q, k, v, mask)
+    return {"attn_out_slice": o[::4, :, ::6, :].numpy(), "attn_out_sum": np.float64(o.double().sum())}
+
+
+def main():
+    out = run_oracle()
+    out.update(run_attention_kat())
+    path = os.path.join(HERE, "videovae_cfg64_fp32.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; loss =", float(out["loss"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -185,3 +185,28 @@ def test_loss_finite_grads_nonzero_and_decreases():
         opt.step()
         losses.append(loss.item())
     assert losses[-1] < losses[0]
+
+
+def test_oracle_reproduces_committed_golden_fixture():
+    """tests/golden/videovae_cfg64_fp32.npz was written by tests/golden/make_golden.py from this oracle; a change in
+    the oracle's arithmetic shows up here (CPU, fp32; BLAS reduction order differs between hosts -> rtol 2e-5)."""
+    import importlib.util
+    import os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "videovae_cfg64_fp32.npz"))
+    now = mg.run_oracle()
+    now.update(mg.run_attention_kat())
+    assert sorted(now) == sorted(gold.files)
+    for key in gold.files:
+        if key == "grad_names":
+            assert list(now[key]) == list(gold[key])
+        elif key == "selection":
+            assert np.array_equal(now[key], gold[key])
+        else:
+            ref = np.asarray(gold[key], dtype=np.float64)
+            got = np.asarray(now[key], dtype=np.float64)
+            assert np.allclose(got, ref, rtol=2e-4, atol=2e-5 * max(1e-6, np.abs(ref).max())), key

@@ -293,3 +293,197 @@ def test_philox_noise_statistics_and_determinism(V):
     assert not torch.equal(out1[1], out3[1])
     sel = out1[2]
     assert set(torch.unique(sel).tolist()) <= {0.0, 1.0}
+
+
+# ---------------------------------------------------------------------------------------------- golden fixtures
+def _load_golden():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "videovae_cfg64_fp32.npz"))
+
+
+def test_videovae_fp32_matches_golden_fixture(V):
+    """CUDA path vs the committed oracle outputs of tests/golden/make_golden.py (fp32, rel 1e-4)."""
+    import importlib.util
+    import os
+    import numpy as np
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = _load_golden()
+    o, video, mask, noise, gumbel_u, hw = mg.build_case()
+    m = V.VideoVAE(*mg.CFG, V.Rngs(2), dtype=torch.float32)
+    _copy_params(m, o)
+    loss, aux = V.loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), V.DEFAULT_HPARAMS,
+                          noise=noise.cuda(), gumbel_u=gumbel_u.cuda())
+    loss.backward()
+    for key in ("loss", "MSE", "MAE", "kl_loss", "selection_loss"):
+        got = loss.item() if key == "loss" else aux[key].item()
+        assert abs(got - float(gold[key])) <= FP32_TOL * max(abs(float(gold[key])), 1e-6), key
+    assert np.array_equal(aux["selection"].reshape(mg.B, mg.T).cpu().numpy(), gold["selection"])
+    assert rel_err(aux["mean"][:, :, ::5, ::7], torch.from_numpy(gold["mean_slice"])) < FP32_TOL
+    assert rel_err(aux["logvar"][:, :, ::5, ::7], torch.from_numpy(gold["logvar_slice"])) < FP32_TOL
+    assert rel_err(aux["compressed"][:, :, ::5, ::7], torch.from_numpy(gold["compressed_slice"])) < FP32_TOL
+    assert rel_err(aux["reconstruction"][:, :, ::9, ::11, :], torch.from_numpy(gold["recon_slice"])) < FP32_TOL
+    norms = dict(zip([str(n) for n in gold["grad_names"]], gold["grad_norms"]))
+    checked = 0
+    for name, p in m.named_parameters():
+        ref = norms[name]
+        if ref == 0.0:
+            continue
+        got = p.grad.double().norm().item()
+        assert abs(got - ref) <= 1e-3 * ref, (name, got, ref)
+        checked += 1
+    assert checked >= 100
+    gq = m.encoder.layers[0].TemporalAttention.qkv_projection.kernel.grad[::16, ::32]
+    assert rel_err(gq, torch.from_numpy(gold["grad_qkv_slice"])) < 1e-3
+    gc = m.decoder.unet.encoders[0].conv1.conv.kernel.grad[:, :, :, ::4, ::4]
+    assert rel_err(gc, torch.from_numpy(gold["grad_conv_slice"])) < 1e-3
+
+
+def test_attention_kat_matches_golden_fixture(V):
+    """train/attention_mask_tests.py shapes (hd = 13: generic kernel) against the committed oracle output."""
+    gold = _load_golden()
+    from video_vae_b200 import ops
+    from video_vae_b200.ops import AttnGeom, AttnMask
+    g = _gen(3)
+    q, k, v = (torch.randn(17, 15, 19, 13, generator=g) for _ in range(3))
+    qc, kc, vc = (t.reshape(17 * 15, 19 * 13).cuda() for t in (q, k, v))
+    m = torch.ones(17, 15, dtype=torch.uint8)
+    m[:, 10:] = 0
+    geom = AttnGeom(17, 1, 15, 15, 0, 1)
+    o, _ = ops.attn_fwd(geom, 19, 13, qc, kc, vc, AttnMask(m.cuda(), 1, 15, 0, 0, 1), 1.0 / math.sqrt(13))
+    o = o.reshape(17, 15, 19, 13)
+    assert rel_err(o[::4, :, ::6, :], torch.from_numpy(gold["attn_out_slice"])) < FP32_TOL
+    assert abs(o.double().sum().item() - float(gold["attn_out_sum"])) < 1e-3 * max(1.0, abs(float(gold["attn_out_sum"])))
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 attention
+def _attention_reference(qk, qkv, d_o, geom, temporal, b, t, hw, H, HD, mask_bl):
+    """Oracle attention + autograd on the same bf16-rounded data, fp32 math.  Returns o, dq, dk, dv token-major."""
+    from oracle.nn import dot_product_attention
+    Q = H * HD
+
+    def to_seq(x):   # [N, Q] -> [n_seq, L, H, HD]
+        x = x.float().cpu().reshape(b, t, hw, H, HD)
+        return (x.permute(0, 2, 1, 3, 4).reshape(b * hw, t, H, HD) if temporal else x.reshape(b * t, hw, H, HD)).contiguous()
+
+    def from_seq(x):
+        if temporal:
+            return x.reshape(b, hw, t, H, HD).permute(0, 2, 1, 3, 4).reshape(b * t * hw, Q)
+        return x.reshape(b * t * hw, Q)
+
+    q = to_seq(qk[:, :Q]).requires_grad_()
+    k = to_seq(qk[:, Q:]).requires_grad_()
+    v = to_seq(qkv[:, 2 * Q:]).requires_grad_()
+    mask = None
+    if mask_bl is not None:      # [n_masks, L] -> [n_seq, 1, 1, L]
+        mm = mask_bl.cpu().bool()
+        if temporal:
+            mm = mm[:, None, :].expand(b, hw, t).reshape(b * hw, t)
+        mask = mm[:, None, None, :]
+    o = dot_product_attention(q, k, v, mask)
+    o.backward(to_seq(d_o))
+    return from_seq(o.detach()), from_seq(q.grad), from_seq(k.grad), from_seq(v.grad)
+
+
+@pytest.mark.parametrize("name,b,t,hw,temporal,masked", [
+    ("spatial_L256", 1, 3, 256, False, False),
+    ("spatial_L128", 1, 2, 128, False, False),
+    ("spatial_L64_pack2_tail", 1, 5, 64, False, False),
+    ("temporal_L16_masked", 2, 16, 16, True, True),
+    ("temporal_L16_hw12_tail", 1, 16, 12, True, True),
+    ("temporal_L32_masked", 3, 32, 8, True, True),
+    ("temporal_L64", 1, 64, 4, True, True),
+    ("temporal_allmasked_clip", 2, 16, 16, True, True),
+])
+def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked):
+    """bf16, head_dim 64: the tensor-core attention (forward AND backward) against oracle autograd on identical data.
+    Covers 128/256-row tiles, block-diagonal packing of short sequences, ragged tails, key-padding masks and a fully
+    masked clip (uniform attention, no gradient to q/k)."""
+    from video_vae_b200 import _ffi, ops
+    from video_vae_b200.ops import AttnGeom, AttnMask
+    H, HD = 8, 64
+    Q = H * HD
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(1)
+    N = b * t * hw
+    qkv = torch.randn(N, 3 * Q, device=dev, generator=g).bfloat16()
+    qk = (torch.randn(N, 2 * Q, device=dev, generator=g) * 1.5).bfloat16()
+    d_o = torch.randn(N, Q, device=dev, generator=g).bfloat16()
+    if temporal:
+        geom, L = AttnGeom(b, hw, t, t * hw, 1, hw), t
+    else:
+        geom, L = AttnGeom(b * t, 1, hw, hw, 0, 1), hw
+    mask = mask_bl = None
+    if masked:
+        keep = torch.randint(1, L + 1, (geom.n_outer,), device=dev, generator=g)
+        mask_bl = torch.arange(L, device=dev)[None, :] < keep[:, None]
+        if name == "temporal_allmasked_clip":
+            mask_bl[0] = False
+        mask = AttnMask(mask_bl.to(torch.uint8).contiguous(), hw if temporal else 1, L, 0, 0, 1)
+    ops.ATTN_BACKEND = _ffi.BACKEND_TCGEN05          # fail loudly if the shape would fall back to the generic kernel
+    try:
+        o, lse = ops.attn_fwd(geom, H, HD, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], mask, 1.0 / math.sqrt(HD))
+        dqkv = torch.zeros(N, 3 * Q, device=dev, dtype=torch.bfloat16)
+        ops.attn_bwd(geom, H, HD, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], o, lse, d_o, dqkv[:, :Q], dqkv[:, Q:2 * Q],
+                     dqkv[:, 2 * Q:], mask, 1.0 / math.sqrt(HD))
+    finally:
+        ops.ATTN_BACKEND = _ffi.BACKEND_AUTO
+    torch.cuda.synchronize()
+    o_ref, dq_ref, dk_ref, dv_ref = _attention_reference(qk, qkv, d_o, geom, temporal, b, t, hw, H, HD, mask_bl)
+    assert rel_err(o, o_ref) < BF16_TOL
+    assert rel_err(dqkv[:, :Q], dq_ref) < BF16_TOL, "dq"
+    assert rel_err(dqkv[:, Q:2 * Q], dk_ref) < BF16_TOL, "dk"
+    assert rel_err(dqkv[:, 2 * Q:], dv_ref) < BF16_TOL, "dv"
+    if name == "temporal_allmasked_clip":            # clip 0: uniform attention, q/k receive no gradient
+        rows = (torch.arange(N, device=dev) // (t * hw)) == 0
+        assert dqkv[rows][:, :2 * Q].abs().max().item() == 0.0
+        assert dqkv[rows][:, 2 * Q:].abs().max().item() > 0.0
+
+
+def test_videovae_bf16_head_dim64_tensor_core_path(V):
+    """bf16 model with 64-wide heads so the tcgen05 GEMM, attention (fwd + bwd, packed temporal with a mask, packed
+    spatial) and conv kernels all run inside the full forward/backward; loss + latents within the bf16 tolerance and
+    gradients aligned with the fp32 oracle."""
+    from oracle import Rngs as ORngs
+    from oracle.losses import DEFAULT_HPARAMS, expand_mask, loss_fn as o_loss_fn
+    from oracle.model import VideoVAE as OVAE
+    cfg = (64, 64, 3, 16, 2, 2, 256, 2, 128, 32, 8, 4)        # 2 heads x 64
+    o = OVAE(*cfg, ORngs(2))
+    with torch.no_grad():
+        o.decoder.unet.final_conv.kernel.copy_(torch.randn(o.decoder.unet.final_conv.kernel.shape, generator=_gen(5)) * 0.05)
+    m = V.VideoVAE(*cfg, V.Rngs(2), dtype=torch.bfloat16)
+    _copy_params(m, o)
+    g = _gen(8)
+    b, t, hw = 4, 8, 16
+    video = torch.rand(b, t, 64, 64, 3, generator=g)
+    mask = torch.ones(b, t, dtype=torch.bool)
+    mask[0, 5:] = False
+    mask[2, 2:] = False
+    noise = torch.randn(b, t, hw, 96, generator=g)
+    u = torch.rand(b, t, 1, generator=g)
+    lo, auxo = o_loss_fn(o, video, expand_mask(mask, hw), mask, ORngs(0), DEFAULT_HPARAMS, noise=noise, gumbel_u=u)
+    lo.backward()
+    lm, auxm = V.loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), V.DEFAULT_HPARAMS,
+                         noise=noise.cuda(), gumbel_u=u.cuda())
+    lm.backward()
+    assert rel_err(auxm["mean"], auxo["mean"]) < BF16_TOL
+    assert rel_err(auxm["logvar"], auxo["logvar"]) < BF16_TOL
+    same_gate = torch.equal(auxm["selection"].cpu().reshape(-1), auxo["selection"].reshape(-1))
+    if same_gate:
+        assert abs(lm.item() - lo.item()) <= BF16_TOL * abs(lo.item())
+        og = dict(o.named_parameters())
+        cos_min, n = 1.0, 0
+        for name, p in m.named_parameters():
+            ref = og[name].grad
+            if ref is None or ref.numel() < 64 or ref.abs().max() == 0:
+                continue
+            c = torch.nn.functional.cosine_similarity(p.grad.float().cpu().reshape(1, -1), ref.reshape(1, -1)).item()
+            cos_min = min(cos_min, c)
+            n += 1
+            assert c > 0.98, (name, c)
+        assert n >= 50
+    for n_, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n_

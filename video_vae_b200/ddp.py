@@ -39,7 +39,10 @@ class FlatParams:
         F_.invalidate_shadows()
 
     def zero_grad(self):
-        ops.fill_(self.grad, 0.0)
+        if self.grad.is_cuda:
+            ops.fill_(self.grad, 0.0)
+        else:                      # host-side bookkeeping tests (gloo); no compute ever runs on CPU tensors
+            self.grad.zero_()
 
     def enable_bf16_shadow(self):
         """Keep ONE flat bf16 copy of all parameters, refreshed by a single cast kernel per optimizer step."""
@@ -77,12 +80,14 @@ class GradAllReducer:
         self._pending = None
         self._handles = []
         self._seen = None
+        self.launch_order = []
         F_._grad_hooks.append(self._on_grads_ready)
 
     def start_step(self):
         self._pending = [n for (_, _, n) in self.buckets]
         self._seen = set()
         self._handles = []
+        self.launch_order = []
 
     def _on_grads_ready(self, params):
         if self._pending is None or self.world == 1:
@@ -98,6 +103,10 @@ class GradAllReducer:
 
     def _launch(self, b):
         s, e, _ = self.buckets[b]
+        self.launch_order.append(b)
+        if self.stream is None:    # CPU tensors (gloo tests of the bucketing logic): reduce in place, synchronously
+            dist.all_reduce(self.flat.grad[s:e], op=dist.ReduceOp.SUM, group=self.pg)
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
@@ -114,7 +123,8 @@ class GradAllReducer:
                 self._launch(b)
         for h in self._handles:
             h.wait()
-        torch.cuda.current_stream().wait_stream(self.stream)
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
         self._pending = None
 
     def close(self):
