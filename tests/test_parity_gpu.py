@@ -321,7 +321,7 @@ def test_videovae_fp32_matches_golden_fixture(V):
     for key in ("loss", "MSE", "MAE", "kl_loss", "selection_loss"):
         got = loss.item() if key == "loss" else aux[key].item()
         assert abs(got - float(gold[key])) <= FP32_TOL * max(abs(float(gold[key])), 1e-6), key
-    assert np.array_equal(aux["selection"].reshape(mg.B, mg.T).cpu().numpy(), gold["selection"])
+    assert np.array_equal(aux["selection"].detach().reshape(mg.B, mg.T).cpu().numpy(), gold["selection"])
     assert rel_err(aux["mean"][:, :, ::5, ::7], torch.from_numpy(gold["mean_slice"])) < FP32_TOL
     assert rel_err(aux["logvar"][:, :, ::5, ::7], torch.from_numpy(gold["logvar_slice"])) < FP32_TOL
     assert rel_err(aux["compressed"][:, :, ::5, ::7], torch.from_numpy(gold["compressed_slice"])) < FP32_TOL
