@@ -132,17 +132,19 @@ add("KMN_alt_kadv", M=256, N=256, K=256, tA=0, tB=0, dbg={3: 4096})
 add("KMN_bn64", M=256, N=256, K=256, tA=0, tB=0, dbg={6: 64})
 add("KMN_bn128", M=256, N=256, K=256, tA=0, tB=0, dbg={6: 128})
 add("KK_bn64", M=256, N=256, K=256, tA=0, tB=1, dbg={6: 64})
-# row-shifted A start address inside a 128B-swizzled tile (dbg 7 = byte offset = rows * 128)
-add("shift1", M=128, N=256, K=64, tA=0, tB=1, row_shift=1, dbg={7: 128})
-add("shift3", M=128, N=256, K=64, tA=0, tB=1, row_shift=3, dbg={7: 384})
-add("shift8", M=128, N=256, K=64, tA=0, tB=1, row_shift=8, dbg={7: 1024})
-add("shift13", M=128, N=256, K=256, tA=0, tB=1, row_shift=13, dbg={7: 13 * 128})
 # epilogues
 add("fwd_bias", M=384, N=512, K=320, tA=0, tB=0, bias=1)
 add("fwd_silu", M=384, N=512, K=320, tA=0, tB=0, bias=1, mode=1)
 add("fwd_resid", M=384, N=512, K=320, tA=0, tB=0, bias=1, mode=2)
 add("dgrad_dsilu", M=384, N=512, K=320, tA=0, tB=1, mode=3)
 add("wgrad_acc", M=768, N=1536, K=4096, tA=1, tB=0, out_f32=1, acc=1)
+# the same through single-CTA tiles (dbg 8 = 1 disables CTA pairs)
+add("fwd_silu_cg1", M=384, N=512, K=320, tA=0, tB=0, bias=1, mode=1, dbg={8: 1})
+add("fwd_resid_cg1", M=384, N=512, K=320, tA=0, tB=0, bias=1, mode=2, dbg={8: 1})
+add("wgrad_acc_cg1", M=768, N=1536, K=4096, tA=1, tB=0, out_f32=1, acc=1, dbg={8: 1})
+add("fwd_bias_n96", M=512, N=96, K=768, tA=0, tB=0, bias=1)
+add("fwd_resid_big", M=4096, N=768, K=512, tA=0, tB=0, bias=1, mode=2)
+add("fwd_silu_big", M=4096, N=1536, K=768, tA=0, tB=0, bias=1, mode=1)
 # ragged
 add("tail_M300_N192_K96", M=300, N=192, K=96, tA=0, tB=0, bias=1)
 add("tail_dgrad", M=300, N=96 + 8, K=200, tA=0, tB=1)
@@ -152,6 +154,14 @@ add("prod_qkv_fwd", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, time=1)
 add("prod_mlp_dn_fwd", M=32768, N=768, K=1536, tA=0, tB=0, bias=1, mode=2, time=1)
 add("prod_dgrad", M=32768, N=768, K=1536, tA=0, tB=1, time=1)
 add("prod_wgrad", M=768, N=1536, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1)
+add("prod_out_fwd", M=32768, N=768, K=512, tA=0, tB=0, bias=1, mode=2, time=1)
+add("prod_mlp_up_fwd", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, mode=1, time=1)
+add("prod_do_dgrad", M=32768, N=512, K=768, tA=0, tB=1, time=1)
+add("prod_du_dgrad", M=32768, N=1536, K=768, tA=0, tB=1, mode=3, time=1)
+add("prod_wgrad_o", M=512, N=768, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1)
+add("prod_wgrad_w2", M=1536, N=768, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1)
+add("prod_qkv_fwd_cg1", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, time=1, dbg={8: 1})
+add("prod_mlp_up_fwd_cg1", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, mode=1, time=1, dbg={8: 1})
 add("prod_qkv_fwd_bn128", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, time=1, dbg={6: 128})
 
 

@@ -78,152 +78,215 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
 
 // ------------------------------------------------------------------ device kernel
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB per CTA
+constexpr int STG_BYTES = 128 * 128;        // one epilogue staging buffer: 128 rows x 64 bf16, 128B-swizzled
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu; // shared::cluster address of the same offset in the even CTA of a pair
 
 struct Sm100Params {
   int M, N;                // output extent
-  int m_tiles, n_tiles, splits;
-  int kb_total, kb_per_split;  // K blocks of 64
+  int m_tiles, n_tiles, splits;   // m_tiles counts (128*CG)-row tiles
+  int kb_total, kb_per_split;     // K blocks of 64
   void* C; long long ldc; int out_f32;
   const float* bias;
   int mode;
   const bf16* aux_in; long long ld_ai;
   bf16* aux_out; long long ld_ao;
   int atomic;
+  int tma_epi;             // bf16 output: epilogue goes TMEM -> registers -> swizzled smem -> TMA store
   // descriptor encodings (bytes); overridable through vvae_debug_set for bring-up
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
-  uint32_t dbg_a_shift;  // bring-up experiment: byte offset added to the A start address (row-shifted operand views)
 };
 
-template <int BN> struct StageCfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+// HEAVY epilogues (residual / dSiLU read an aux tile, SiLU writes two tiles) get 4 extra staging buffers: a 4-deep ring of
+// TMA-prefetched aux-input chunks (one whole tile ahead: TMA latency under load is several microseconds), or the second
+// output's double buffer.
+template <int BN, int CG, bool HEAVY> struct StageCfg {
+  static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;          // per CTA
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
+  static constexpr int EPI_BYTES = (HEAVY ? 6 : 2) * STG_BYTES;
+  static constexpr int BAR_BYTES = 256 + 256 * 4;   // barriers + the current tile's bias slice
+  static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - EPI_BYTES;
+  static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 
-__device__ __forceinline__ void epilogue_store_chunk(const Sm100Params& p, long long m, int n0, const uint32_t (&r)[32]) {
-  // one thread owns row m, 32 consecutive columns starting at n0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the barrier at the same offset in the pair's even CTA
+template <int CG>
+__device__ __forceinline__ void tma_load_2d_cg(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (CG == 1) {
+    sm100::tma_load_2d(smem_dst, m, bar, c0, c1);
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(sm100::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(sm100::smem_u32(bar) & PEER_MASK),
+        "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_f16_cg(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc) {
+  if constexpr (CG == 1) {
+    sm100::umma_f16(tmem_d, desc_a, desc_b, idesc, acc);
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc)
+        : "memory");
+  }
+}
+// arrive (once the issuing thread's earlier MMAs have completed) on the barrier at this offset in every CTA of the pair
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    sm100::umma_commit(bar);
+  } else {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(sm100::smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  if constexpr (CG == 1) {
+    sm100::mbar_arrive(bar);
+  } else {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(sm100::smem_u32(bar) & PEER_MASK) : "memory");
+  }
+}
+template <int CG, int NCOLS>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t* slot) {
+  if constexpr (CG == 1) {
+    sm100::tmem_alloc<NCOLS>(slot);
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm100::smem_u32(slot)), "n"(NCOLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG, int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr) {
+  if constexpr (CG == 1) sm100::tmem_dealloc<NCOLS>(taddr);
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(sm100::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// fp32 / atomic outputs (weight gradients): one thread owns row m, 32 consecutive columns starting at n0
+__device__ __forceinline__ void epilogue_store_f32(const Sm100Params& p, long long m, int n0, const uint32_t (&r)[32]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   const bool full = (n0 + 32 <= p.N);
   if (p.bias) {
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+  }
+  float* c = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
+  if (p.atomic) {
     if (full) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(c + j), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]),
+                     "f"(v[j + 3])
+                     : "memory");
     } else {
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
-    }
-  }
-  if (p.mode == VVAE_EPI_SILU) {
-    if (p.aux_out) {
-      bf16* ao = p.aux_out + m * p.ld_ao + n0;
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          Vec16<bf16> o;
-#pragma unroll
-          for (int t = 0; t < 8; ++t) o.set(t, v[j + t]);
-          o.store(ao + j);
-        }
-      } else {
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < p.N) ao[j] = __float2bfloat16_rn(v[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = siluf_(round_to<bf16>(v[j]));
-  } else if (p.mode == VVAE_EPI_RESIDUAL || p.mode == VVAE_EPI_DSILU) {
-    const bf16* ai = p.aux_in + m * p.ld_ai + n0;
-    float a[32];
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        Vec16<bf16> x;
-        x.load(ai + j);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) a[j + t] = x.get(t);
-      }
-    } else {
-      for (int j = 0; j < 32; ++j) a[j] = (n0 + j < p.N) ? __bfloat162float(ai[j]) : 0.f;
-    }
-    if (p.mode == VVAE_EPI_RESIDUAL) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += a[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] *= dsiluf_(a[j]);
-    }
-  }
-  if (p.out_f32) {
-    float* c = reinterpret_cast<float*>(p.C) + m * p.ldc + n0;
-    if (p.atomic) {
       for (int j = 0; j < 32; ++j)
         if (n0 + j < p.N) atomicAdd(c + j, v[j]);
-    } else if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) c[j] = v[j];
     }
+  } else if (full) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
   } else {
-    bf16* c = reinterpret_cast<bf16*>(p.C) + m * p.ldc + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        Vec16<bf16> o;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) o.set(t, v[j + t]);
-        o.store(c + j);
-      }
-    } else {
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) c[j] = __float2bfloat16_rn(v[j]);
-    }
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < p.N) c[j] = v[j];
   }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+__device__ __forceinline__ float fast_sigmoid(float x) {   // 0.5*tanh(x/2)+0.5, one MUFU; |err| < 3e-4 (bf16 outputs)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float fast_silu(float x) { return x * fast_sigmoid(x); }
+__device__ __forceinline__ float fast_dsilu(float x) {
+  const float s = fast_sigmoid(x);
+  return s * fmaf(x, 1.f - s, 1.f);
+}
+
+template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(192, 1)
-gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, Sm100Params p) {
-  using Cfg = StageCfg<BN>;
+gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                  const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_ai,
+                  const __grid_constant__ CUtensorMap tma_ao, Sm100Params p) {
+  constexpr bool HEAVY = MODE != VVAE_EPI_NONE;   // the fused epilogue is compiled in per mode (keeps the code in the I-cache)
+  using Cfg = StageCfg<BN, CG, HEAVY>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NCH = BN / 64;                 // 64-column epilogue chunks per tile
+  constexpr int AUXR = 4;                      // aux-input ring depth (HEAVY only)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stg_out = smem + STAGES * Cfg::STAGE_BYTES;        // [2][128 x 128 B]
+  uint8_t* stg_aux = stg_out + 2 * STG_BYTES;                 // HEAVY: [4][128 x 128 B] aux ring | second output [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* aux_full = bars + 2 * STAGES + 4;   // [4]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     sm100::tma_prefetch_desc(&tma_a);
     sm100::tma_prefetch_desc(&tma_b);
+    if (p.tma_epi) sm100::tma_prefetch_desc(&tma_c);
     for (int i = 0; i < STAGES; ++i) {
       sm100::mbar_init(&full_bar[i], 1);
       sm100::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
-      sm100::mbar_init(&tmem_empty[i], 4);
+      sm100::mbar_init(&tmem_empty[i], 4 * CG);
     }
+    for (int i = 0; i < AUXR; ++i) sm100::mbar_init(&aux_full[i], 1);
     sm100::fence_barrier_init();
   }
-  if (warp == 1) sm100::tmem_alloc<Cfg::TMEM_COLS>(tmem_base_slot);
+  if (warp == 1) tmem_alloc_cg<CG, Cfg::TMEM_COLS>(tmem_base_slot);
   sm100::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -231,46 +294,48 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int total_tiles = tiles_mn * p.splits;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (both CTAs of a pair load their own halves) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int split = tile / tiles_mn, mn = tile % tiles_mn;
-        const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
+        const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM;
+        const int n0 = (mn % p.n_tiles) * BN + (int)cta_rank * (BN / CG);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
-          sm100::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (cta_rank == 0) sm100::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * CG);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
           const int k0 = kb * BK;
           if constexpr (A_MN) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) sm100::tma_load_2d(sa + j * 8192, &tma_a, &full_bar[stage], m0 + 64 * j, k0);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg<CG>(sa + j * 8192, &tma_a, &full_bar[stage], m0 + 64 * j, k0);
           } else {
-            sm100::tma_load_2d(sa, &tma_a, &full_bar[stage], k0, m0);
+            tma_load_2d_cg<CG>(sa, &tma_a, &full_bar[stage], k0, m0);
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) sm100::tma_load_2d(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
+            for (int j = 0; j < BN / CG / 64; ++j)
+              tma_load_2d_cg<CG>(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
           } else {
-            sm100::tma_load_2d(sb, &tma_b, &full_bar[stage], k0, n0);
+            tma_load_2d_cg<CG>(sb, &tma_b, &full_bar[stage], k0, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = sm100::make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // ===================== MMA issuer (the pair's even CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = sm100::make_idesc_bf16(BM * CG, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int split = tile / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -280,53 +345,163 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           sm100::mbar_wait(&full_bar[stage], phase);
           sm100::tc_fence_after();
-          const uint32_t a_addr = sm100::smem_u32(smem_a + stage * A_STAGE_BYTES) + p.dbg_a_shift;
+          const uint32_t a_addr = sm100::smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t b_addr = sm100::smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = sm100::make_smem_desc_sw128(a_addr + k * p.a_kadv, p.a_lbo, p.a_sbo);
             const uint64_t db = sm100::make_smem_desc_sw128(b_addr + k * p.b_kadv, p.b_lbo, p.b_sbo);
-            sm100::umma_f16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16_cg<CG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          sm100::umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          umma_commit_cg<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        sm100::umma_commit(&tmem_full[acc]);  // accumulator complete
+        umma_commit_cg<CG>(&tmem_full[acc]);      // accumulator complete (signals both CTAs' epilogues)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue =====================
+    // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
     const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;           // row inside the CTA's 128-row tile == TMEM lane
+    const int etid = threadIdx.x - 64;           // 0..127
+    const uint32_t sw = (uint32_t)(r & 7);
+    constexpr bool use_aux = MODE == VVAE_EPI_RESIDUAL || MODE == VVAE_EPI_DSILU;
+    const bool two_out = MODE == VVAE_EPI_SILU && p.aux_out != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t g = 0;                               // running chunk counter (staging-buffer / aux-barrier parity)
+    // aux-input prefetch: chunk sequence of this CTA is (tile, c) in order; keep two chunks in flight
+    int pf_tile = cluster_id, pf_c = 0;
+    uint32_t pf_g = 0;
+    auto prefetch_aux = [&]() {
+      if (pf_tile >= total_tiles) return;
+      const int mn = pf_tile % tiles_mn;
+      const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (mn % p.n_tiles) * BN;
+      const uint32_t b = pf_g & (AUXR - 1);
+      sm100::mbar_expect_tx(&aux_full[b], STG_BYTES);
+      sm100::tma_load_2d(stg_aux + b * STG_BYTES, &tma_ai, &aux_full[b], n0 + 64 * pf_c, m0);
+      ++pf_g;
+      if (++pf_c == NCH) { pf_c = 0; pf_tile += num_clusters; }
+    };
+    if (use_aux && etid == 0) {
+      for (int i = 0; i < AUXR; ++i) prefetch_aux();
+    }
+
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int mn = tile % tiles_mn;
-      const int m0 = (mn / p.n_tiles) * BM, n0 = (mn % p.n_tiles) * BN;
+      const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (mn % p.n_tiles) * BN;
+      float* bias_t = s_bias;   // single buffer: every reader of the previous tile's slice has passed that tile's last barrier
+      if (p.tma_epi && p.bias) {                 // this tile's bias slice -> smem (read back as broadcasts)
+        for (int j = etid; j < BN; j += 128) bias_t[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        epi_bar();
+      }
       sm100::mbar_wait(&tmem_full[acc], acc_phase);
       sm100::tc_fence_after();
-      const long long m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      if (!p.tma_epi) {
+        const long long m = (long long)m0 + r;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        sm100::tmem_ld_32x32(taddr + c * 32, r);
-        sm100::tmem_ld_wait();
-        if (m < p.M) epilogue_store_chunk(p, m, n0 + c * 32, r);
+        for (int c = 0; c < BN / 32; ++c) {
+          if (n0 + c * 32 >= p.N) break;  // warp-uniform
+          uint32_t rr[32];
+          sm100::tmem_ld_32x32(taddr + c * 32, rr);
+          sm100::tmem_ld_wait();
+          if (m < p.M) epilogue_store_f32(p, m, n0 + c * 32, rr);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c, ++g) {
+          const int nc = n0 + 64 * c;
+          const uint32_t b = g & 1;
+          uint4 ax[8];
+          if constexpr (use_aux) {
+            const uint32_t ab = g & (AUXR - 1);
+            sm100::mbar_wait(&aux_full[ab], (g >> 2) & 1);
+            const uint8_t* arow = stg_aux + ab * STG_BYTES + r * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) ax[ch] = *reinterpret_cast<const uint4*>(arow + (((uint32_t)ch ^ sw) << 4));
+          }
+          uint32_t pk[32], pk2[32];
+          uint32_t rr0[32], rr1[32];
+          sm100::tmem_ld_32x32(taddr + c * 64, rr0);
+          sm100::tmem_ld_32x32(taddr + c * 64 + 32, rr1);
+          sm100::tmem_ld_wait();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(hf ? rr1[j] : rr0[j]);
+            if (p.bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(bias_t + c * 64 + hf * 32);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 bb = b4[j >> 2];
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+              }
+            }
+            if constexpr (MODE == VVAE_EPI_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint32_t pre = pack_bf16x2(v[j], v[j + 1]);
+                pk2[hf * 16 + (j >> 1)] = pre;
+                const float x0 = __uint_as_float(pre << 16), x1 = __uint_as_float(pre & 0xffff0000u);
+                pk[hf * 16 + (j >> 1)] = pack_bf16x2(fast_silu(x0), fast_silu(x1));
+              }
+            } else {
+              if constexpr (use_aux) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  const uint32_t w = (&ax[hf * 4 + (j >> 3)].x)[(j >> 1) & 3];
+                  const float a0 = __uint_as_float(w << 16), a1 = __uint_as_float(w & 0xffff0000u);
+                  if constexpr (MODE == VVAE_EPI_RESIDUAL) { v[j] += a0; v[j + 1] += a1; }
+                  else { v[j] *= fast_dsilu(a0); v[j + 1] *= fast_dsilu(a1); }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) pk[hf * 16 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
+            }
+          }
+          // staging buffer(s) must have been read out by the TMA store that last used them
+          if (etid == 0) bulk_wait_read<1>();                 // the group that last used staging buffer b has been read out
+          epi_bar();
+          if (use_aux && etid == 0) prefetch_aux();          // every thread has consumed this chunk's aux buffer
+          uint8_t* orow = stg_out + b * STG_BYTES + r * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(orow + (((uint32_t)ch ^ sw) << 4)) =
+                make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+          if (two_out) {
+            uint8_t* prow = stg_aux + b * STG_BYTES + r * 128;
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch)
+              *reinterpret_cast<uint4*>(prow + (((uint32_t)ch ^ sw) << 4)) =
+                  make_uint4(pk2[4 * ch], pk2[4 * ch + 1], pk2[4 * ch + 2], pk2[4 * ch + 3]);
+          }
+          sm100::fence_proxy_async();
+          epi_bar();
+          if (etid == 0) {
+            if (nc < p.N && m0 < p.M) {
+              tma_store_2d(&tma_c, stg_out + b * STG_BYTES, nc, m0);
+              if (two_out) tma_store_2d(&tma_ao, stg_aux + b * STG_BYTES, nc, m0);
+            }
+            bulk_commit();   // one (possibly empty) group per chunk keeps the wait_group accounting uniform
+          }
+        }
       }
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) mbar_arrive_leader<CG>(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_epi && etid == 0) bulk_wait_all();
   }
 
   sm100::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     sm100::tc_fence_after();
-    sm100::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc_cg<CG, Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -343,15 +518,18 @@ bool sm100_gemm_supported(const vvae_gemm_args& a) {
   if (a.aux_out && ((a.ld_aux_out % 8) || ((uintptr_t)a.aux_out % 16))) return false;
   if (a.bias && ((uintptr_t)a.bias % 16)) return false;
   if (a.accumulate && a.out_dtype != VVAE_F32) return false;
+  if (a.out_dtype == VVAE_F32 && a.epilogue != VVAE_EPI_NONE) return false;   // fused epilogues are bf16-out only
+  if (a.transA && a.epilogue != VVAE_EPI_NONE) return false;
   // MN-major operands are fetched in 64-wide boxes along M / N
   if (a.transA && (a.M % 8)) return false;
   return true;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
 static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
-  using Cfg = StageCfg<BN>;
-  CUtensorMap ta, tb;
+  using Cfg = StageCfg<BN, CG, MODE != VVAE_EPI_NONE>;
+  static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
+  CUtensorMap ta, tb, tc, tai, tao;
   int rc;
   // A: op(A)[m,k].  K-major: memory [M rows][K cols];  MN-major (transA): memory [K rows][M cols].
   if (A_MN) rc = encode_tmap_2d_bf16(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 2, 64, BK, 128);
@@ -359,18 +537,19 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   if (rc) return rc;
   // B: op(B)[k,n].  K-major (transB): memory [N rows][K cols];  MN-major: memory [K rows][N cols].
   if (B_MN) rc = encode_tmap_2d_bf16(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * 2, 64, BK, 128);
-  else      rc = encode_tmap_2d_bf16(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, BK, BN, 128);
+  else      rc = encode_tmap_2d_bf16(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, BK, BN / CG, 128);
   if (rc) return rc;
 
   Sm100Params p;
   p.M = a.M; p.N = a.N;
-  p.m_tiles = (int)cdiv(a.M, BM);
+  p.m_tiles = (int)cdiv(a.M, BM * CG);
   p.n_tiles = (int)cdiv(a.N, BN);
   p.kb_total = (int)cdiv(a.K, BK);
+  const int n_clusters = 148 / CG;
   int splits = 1;
   const int tiles_mn = p.m_tiles * p.n_tiles;
-  if (a.accumulate && tiles_mn < 148) {  // weight gradients: few output tiles, very long K -> split K over the SMs
-    splits = std::max(1, std::min(148 / tiles_mn, p.kb_total / 8));
+  if (a.accumulate && tiles_mn < n_clusters) {  // weight gradients: few output tiles, very long K -> split K over the SMs
+    splits = std::max(1, std::min(n_clusters / tiles_mn, p.kb_total / 8));
   }
   p.kb_per_split = (int)cdiv(p.kb_total, splits);
   p.splits = (int)cdiv(p.kb_total, p.kb_per_split);
@@ -379,19 +558,29 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   p.aux_in = (const bf16*)a.aux_in; p.ld_ai = a.ld_aux_in;
   p.aux_out = (bf16*)a.aux_out; p.ld_ao = a.ld_aux_out;
   p.atomic = (a.accumulate || p.splits > 1) ? 1 : 0;
+  p.tma_epi = p.out_f32 ? 0 : 1;
+  tc = ta; tai = ta; tao = ta;   // placeholders for maps a mode does not use
+  if (p.tma_epi) {
+    if ((rc = encode_tmap_2d_bf16(&tc, a.C, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * 2, 64, 128, 128))) return rc;
+    if (a.epilogue == VVAE_EPI_RESIDUAL || a.epilogue == VVAE_EPI_DSILU)
+      if ((rc = encode_tmap_2d_bf16(&tai, a.aux_in, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ld_aux_in * 2, 64, 128, 128)))
+        return rc;
+    if (a.epilogue == VVAE_EPI_SILU && a.aux_out)
+      if ((rc = encode_tmap_2d_bf16(&tao, a.aux_out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ld_aux_out * 2, 64, 128, 128)))
+        return rc;
+  }
   // K-major SW128: 8-row groups 1024 B apart, K advance 32 B inside the swizzled row.
   // MN-major SW128: 64-wide MN chunks one TMA box (64 k-rows x 128 B = 8192 B) apart, 8-k groups 1024 B apart,
   // K advance = 16 rows x 128 B.
   p.a_lbo = A_MN ? 8192 : 16;  p.a_sbo = 1024;  p.a_kadv = A_MN ? 2048 : 32;
   p.b_lbo = B_MN ? 8192 : 16;  p.b_sbo = 1024;  p.b_kadv = B_MN ? 2048 : 32;
-  p.dbg_a_shift = (uint32_t)g_dbg[7];
   if (g_dbg[1]) { if (A_MN) p.a_lbo = (uint32_t)g_dbg[1]; if (B_MN) p.b_lbo = (uint32_t)g_dbg[1]; }
   if (g_dbg[2]) { if (A_MN) p.a_sbo = (uint32_t)g_dbg[2]; if (B_MN) p.b_sbo = (uint32_t)g_dbg[2]; }
   if (g_dbg[3]) { if (A_MN) p.a_kadv = (uint32_t)g_dbg[3]; if (B_MN) p.b_kadv = (uint32_t)g_dbg[3]; }
   if (g_dbg[4]) { if (!A_MN) p.a_lbo = (uint32_t)g_dbg[4]; if (!B_MN) p.b_lbo = (uint32_t)g_dbg[4]; }
   if (g_dbg[5]) { if (!A_MN) p.a_sbo = (uint32_t)g_dbg[5]; if (!B_MN) p.b_sbo = (uint32_t)g_dbg[5]; }
 
-  auto kern = gemm_sm100_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_sm100_kernel<BN, CG, A_MN, B_MN, MODE>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -402,25 +591,56 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
     attr_set = true;
   }
   const int total = tiles_mn * p.splits;
-  int grid = std::min(total, g_dbg[0] ? (int)g_dbg[0] : 148);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, s>>>(ta, tb, p);
+  int clusters = std::min(total, g_dbg[0] ? (int)g_dbg[0] : n_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tai, tao, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_sm100 launch: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return VVAE_ERR_CUDA;
+  }
   return check_launch("gemm_sm100");
 }
 
-template <int BN>
+template <int BN, int CG>
 static int dispatch_major(const vvae_gemm_args& a, cudaStream_t s) {
   const bool a_mn = a.transA != 0;   // op(A)[m,k] = A[k*lda+m]  -> M contiguous
   const bool b_mn = a.transB == 0;   // op(B)[k,n] = B[k*ldb+n]  -> N contiguous
-  if (a_mn) return b_mn ? launch_sm100<BN, true, true>(a, s) : launch_sm100<BN, true, false>(a, s);
-  return b_mn ? launch_sm100<BN, false, true>(a, s) : launch_sm100<BN, false, false>(a, s);
+  if (a_mn) {
+    if (a.epilogue != VVAE_EPI_NONE) { set_error("gemm_sm100: fused epilogues need a K-major A operand"); return VVAE_ERR_UNSUPPORTED; }
+    return b_mn ? launch_sm100<BN, CG, true, true, 0>(a, s) : launch_sm100<BN, CG, true, false, 0>(a, s);
+  }
+  switch (a.epilogue) {
+    case VVAE_EPI_SILU:
+      return b_mn ? launch_sm100<BN, CG, false, true, 1>(a, s) : launch_sm100<BN, CG, false, false, 1>(a, s);
+    case VVAE_EPI_RESIDUAL:
+      return b_mn ? launch_sm100<BN, CG, false, true, 2>(a, s) : launch_sm100<BN, CG, false, false, 2>(a, s);
+    case VVAE_EPI_DSILU:
+      return b_mn ? launch_sm100<BN, CG, false, true, 3>(a, s) : launch_sm100<BN, CG, false, false, 3>(a, s);
+    default:
+      return b_mn ? launch_sm100<BN, CG, false, true, 0>(a, s) : launch_sm100<BN, CG, false, false, 0>(a, s);
+  }
 }
 
 int sm100_gemm(const vvae_gemm_args& a, cudaStream_t s) {
   int bn = (int)g_dbg[6];
   if (!bn) bn = (a.N % 256 == 0 || a.N > 512) ? 256 : (a.N % 128 == 0 || a.N > 192 ? 128 : 64);
-  if (bn == 256) return dispatch_major<256>(a, s);
-  if (bn == 128) return dispatch_major<128>(a, s);
-  return dispatch_major<64>(a, s);
+  // CTA pairs (cta_group::2, 256-row tiles) halve the L2 -> smem operand traffic per FLOP; used whenever there are at
+  // least two 128-row blocks.  vvae_debug_set(8, 1) forces single-CTA tiles.
+  const bool pair = a.M >= 256 && !g_dbg[8];
+  if (bn == 256 && !pair) bn = 128;   // single-CTA 128x256 tiles leave too little smem for a deep pipeline + staging
+  if (bn == 256) return dispatch_major<256, 2>(a, s);
+  if (bn == 128) return pair ? dispatch_major<128, 2>(a, s) : dispatch_major<128, 1>(a, s);
+  return dispatch_major<64, 1>(a, s);
 }
 
 }  // namespace vvae
