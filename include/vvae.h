@@ -91,13 +91,14 @@ int vvae_layernorm_bwd(const void* dy, const void* x, const float* mean, const f
 
 /* ---- QK-LayerNorm + RoPE (train/layers.py:104-129,164-166) ----------------
  * qkv: [rows, 3*H*hd] (q|k|v).  qk_out: [rows, 2*H*hd] = rope(LN(q)) | rope(LN(k)).
- * position of row r = (r / pos_div) % pos_mod; cos/sin: fp32 [>=pos_mod, hd]. */
+ * position of row r = (r / pos_div) % pos_mod; cos/sin: [>=pos_mod, hd] in the compute dtype T (the reference casts
+ * the tables to q's dtype before use, train/layers.py:124-127). */
 int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, const float* k_scale,
-                         const float* cos_tab, const float* sin_tab, long long rows, int heads, int hd,
+                         const void* cos_tab, const void* sin_tab, long long rows, int heads, int hd,
                          long long pos_div, int pos_mod, float eps, int dtype, vvae_stream_t stream);
 /* dqkv: [rows, 3*H*hd]; on entry its q|k part holds d(rotated q|k), on exit d(raw q|k); v part untouched. */
 int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, const float* k_scale,
-                         const float* cos_tab, const float* sin_tab, float* dq_scale_accum, float* dk_scale_accum,
+                         const void* cos_tab, const void* sin_tab, float* dq_scale_accum, float* dk_scale_accum,
                          long long rows, int heads, int hd, long long pos_div, int pos_mod, float eps, int dtype,
                          vvae_stream_t stream);
 

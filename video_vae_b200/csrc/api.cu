@@ -86,6 +86,49 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long ld, long long r
   }
 }
 
+// bf16, n % 8 == 0: each thread owns 8 consecutive columns (one 16-byte load per row), a warp 256 columns, the 8 warps
+// of a block stride over a slab of rows with 4 independent loads in flight per thread.
+__global__ void __launch_bounds__(256)
+colsum_bf16_vec_kernel(const bf16* __restrict__ x, long long ld, long long rows, int n, float* __restrict__ out,
+                       int rows_per_block) {
+  __shared__ float part[8][32][9];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + lane) * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  if (col < n) {
+    long long r = r0 + w;
+    for (; r + 24 < r1; r += 32) {
+      Vec16<bf16> v0, v1, v2, v3;
+      v0.load(x + r * ld + col);
+      v1.load(x + (r + 8) * ld + col);
+      v2.load(x + (r + 16) * ld + col);
+      v3.load(x + (r + 24) * ld + col);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] += (v0.get(t) + v1.get(t)) + (v2.get(t) + v3.get(t));
+    }
+    for (; r < r1; r += 8) {
+      Vec16<bf16> v0;
+      v0.load(x + r * ld + col);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] += v0.get(t);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) part[w][lane][t] = acc[t];
+  __syncthreads();
+  // 256 threads finish the 256 column sums of the block: thread (lane l, t = w) adds the 8 warps' partials
+  if (col < n) {
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += part[j][lane][w];
+    atomicAdd(out + col + w, sum);
+  }
+}
+
 }  // namespace vvae
 
 using namespace vvae;
@@ -136,6 +179,14 @@ int vvae_fill_f32(float* dst, float value, long long n, vvae_stream_t stream) {
 int vvae_colsum(const void* x, long long ld, long long rows, int n, float* out, int dtype, vvae_stream_t stream) {
   if (rows <= 0 || n <= 0) return VVAE_OK;
   VVAE_REQUIRE(x && out, "vvae_colsum: null pointer");
+  if (dtype == VVAE_BF16 && n % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
+    const int cb = (int)cdiv(n, 256);
+    const long long want = cdiv(148 * 4, cb);
+    const long long rpb = std::max<long long>(64, cdiv(rows, want));
+    dim3 grid(cb, (unsigned)cdiv(rows, rpb));
+    colsum_bf16_vec_kernel<<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, ld, rows, n, out, (int)rpb);
+    return check_launch("colsum");
+  }
   int col_blocks = (int)cdiv(n, 32);
   // enough row slabs to fill the machine a few times over, at least 64 rows each
   long long want = cdiv(148 * 8, col_blocks);

@@ -146,11 +146,40 @@ static int conv_validate(const vvae_conv_args* a, int which) {
   return VVAE_OK;
 }
 
+namespace vvae {
+struct SmallLinArgs {
+  const bf16* x; long long x_ld;
+  const bf16* w; long long wk, wn;
+  const float* bias;
+  bf16* y; long long y_ld;
+  const bf16* aux; long long aux_ld;
+  long long M; int K, N;
+};
+bool small_linear_ok(int K, int N);
+bool small_linear_wgrad_ok(int K, int N);
+int small_linear_fwd(const SmallLinArgs& a, cudaStream_t s);
+int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dk, long long dn,
+                       long long M, int K, int N, cudaStream_t s);
+}  // namespace vvae
+
 static int conv_run(const vvae_conv_args* a, int which, vvae_stream_t stream) {
   int rc = conv_validate(a, which);
   if (rc) return rc;
   if (a->B == 0) return VVAE_OK;
   cudaStream_t s = as_stream(stream);
+  // 1x1x1 convs with a handful of channels (the U-Net's output conv) are per-voxel streams: small_linear.cu
+  if (a->backend == VVAE_BACKEND_AUTO && a->dtype == VVAE_BF16 && a->kt == 1 && a->kh == 1 && a->kw == 1 &&
+      small_linear_ok(a->Cin, a->Cout)) {
+    const long long V = (long long)a->B * a->T * a->H * a->W;
+    if (which == 1) {   // dx[v, ci] = sum_co dy[v, co] * w[ci, co]
+      SmallLinArgs q{(const bf16*)a->y, a->y_ld, (const bf16*)a->w, 1, a->Cout, nullptr, (bf16*)const_cast<void*>(a->x),
+                     a->x_ld, nullptr, 0, V, a->Cout, a->Cin};
+      return small_linear_fwd(q, s);
+    }
+    if (which == 2 && small_linear_wgrad_ok(a->Cin, a->Cout))
+      return small_linear_wgrad((const bf16*)a->x, a->x_ld, (const bf16*)a->y, a->y_ld, a->dw_accum, a->Cout, 1, V, a->Cin,
+                                a->Cout, s);
+  }
   if (a->backend != VVAE_BACKEND_SIMT && which == 2 && conv_wgrad_tc_supported(*a)) return conv_wgrad_tc_launch(*a, s);
   if (a->backend != VVAE_BACKEND_SIMT && which < 2 && conv_tc_supported(*a, which)) return conv_tc_launch(*a, which, s);
   if (a->backend == VVAE_BACKEND_TCGEN05) {

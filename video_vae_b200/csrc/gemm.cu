@@ -5,6 +5,39 @@ namespace vvae {
 bool sm100_gemm_supported(const vvae_gemm_args& a);
 int sm100_gemm(const vvae_gemm_args& a, cudaStream_t s);
 
+struct SmallLinArgs {
+  const bf16* x; long long x_ld;
+  const bf16* w; long long wk, wn;
+  const float* bias;
+  bf16* y; long long y_ld;
+  const bf16* aux; long long aux_ld;
+  long long M; int K, N;
+};
+bool small_linear_ok(int K, int N);
+bool small_linear_wgrad_ok(int K, int N);
+int small_linear_fwd(const SmallLinArgs& a, cudaStream_t s);
+int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dk, long long dn,
+                       long long M, int K, int N, cudaStream_t s);
+
+// per-row linears with a handful of features (HBM-bound streams, see small_linear.cu)
+static bool small_route(const vvae_gemm_args& a, cudaStream_t s, int* rc) {
+  if (a.dtype != VVAE_BF16 || a.backend != VVAE_BACKEND_AUTO) return false;
+  if (!a.transA && a.out_dtype == VVAE_BF16 && !a.accumulate && small_linear_ok(a.K, a.N) && a.M >= 4096 &&
+      (a.epilogue == VVAE_EPI_NONE || a.epilogue == VVAE_EPI_RESIDUAL)) {
+    SmallLinArgs q{(const bf16*)a.A, a.lda, (const bf16*)a.B, a.transB ? 1 : a.ldb, a.transB ? a.ldb : 1, a.bias,
+                   (bf16*)a.C, a.ldc, a.epilogue == VVAE_EPI_RESIDUAL ? (const bf16*)a.aux_in : nullptr, a.ld_aux_in,
+                   a.M, a.K, a.N};
+    *rc = small_linear_fwd(q, s);
+    return true;
+  }
+  if (a.transA && !a.transB && a.accumulate && a.out_dtype == VVAE_F32 && a.epilogue == VVAE_EPI_NONE && !a.bias &&
+      small_linear_wgrad_ok(a.M, a.N) && a.K >= 4096) {
+    *rc = small_linear_wgrad((const bf16*)a.A, a.lda, (const bf16*)a.B, a.ldb, (float*)a.C, a.ldc, 1, a.K, a.M, a.N, s);
+    return true;
+  }
+  return false;
+}
+
 template <typename T, typename TO>
 static int gemm_simt_typed(const vvae_gemm_args& a, cudaStream_t s) {
   EpiStore<TO, T> ep{(TO*)a.C, a.ldc, a.bias, a.epilogue, (const T*)a.aux_in, a.ld_aux_in, (T*)a.aux_out, a.ld_aux_out, 0};
@@ -56,6 +89,10 @@ extern "C" int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream) {
     return sm100_gemm(a, s);
   }
   if (a.backend == VVAE_BACKEND_AUTO && tc_ok) return sm100_gemm(a, s);
+  {
+    int rc = 0;
+    if (small_route(a, s, &rc)) return rc;
+  }
   if (a.dtype == VVAE_F32) return gemm_simt_typed<float, float>(a, s);
   if (a.out_dtype == VVAE_F32) return gemm_simt_typed<bf16, float>(a, s);
   return gemm_simt_typed<bf16, bf16>(a, s);

@@ -17,6 +17,21 @@ layernorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = D / V;
+  float gm[NCHUNK][V], bt[NCHUNK][V];      // this lane's slice of gamma / beta, loaded once
+#pragma unroll
+  for (int i = 0; i < NCHUNK; ++i) {
+    const int j = lane + 32 * i;
+#pragma unroll
+    for (int t = 0; t < V; t += 4) {
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < nvec) {
+        if (gamma) g4 = __ldg(reinterpret_cast<const float4*>(gamma + j * V + t));
+        if (beta) b4 = __ldg(reinterpret_cast<const float4*>(beta + j * V + t));
+      }
+      gm[i][t] = g4.x; gm[i][t + 1] = g4.y; gm[i][t + 2] = g4.z; gm[i][t + 3] = g4.w;
+      bt[i][t] = b4.x; bt[i][t + 1] = b4.y; bt[i][t + 2] = b4.z; bt[i][t + 3] = b4.w;
+    }
+  }
   for (long long row = warp0; row < rows; row += nwarps) {
     const T* xr = x + row * D;
     Vec16<T> v[NCHUNK];
@@ -51,11 +66,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __
         Vec16<T> o;
 #pragma unroll
         for (int t = 0; t < V; ++t) {
-          int c = j * V + t;
-          float f = (v[i].get(t) - mu) * r;
-          if (gamma) f *= gamma[c];
-          if (beta) f += beta[c];
-          o.set(t, f);
+          o.set(t, fmaf((v[i].get(t) - mu) * r, gm[i][t], bt[i][t]));
         }
         o.store(yr + j * V);
       }
@@ -76,11 +87,19 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = D / V;
-  float pg[NCHUNK][V], pb[NCHUNK][V];
+  float pg[NCHUNK][V], pb[NCHUNK][V], gm[NCHUNK][V];
 #pragma unroll
-  for (int i = 0; i < NCHUNK; ++i)
+  for (int i = 0; i < NCHUNK; ++i) {
+    const int j = lane + 32 * i;
+#pragma unroll
+    for (int t = 0; t < V; t += 4) {
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (gamma && j < nvec) g4 = __ldg(reinterpret_cast<const float4*>(gamma + j * V + t));
+      gm[i][t] = g4.x; gm[i][t + 1] = g4.y; gm[i][t + 2] = g4.z; gm[i][t + 3] = g4.w;
+    }
 #pragma unroll
     for (int t = 0; t < V; ++t) pg[i][t] = pb[i][t] = 0.f;
+  }
 
   for (long long row = warp0; row < rows; row += nwarps) {
     const float mu = mean[row], r = rstd[row];
@@ -96,7 +115,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
         for (int t = 0; t < V; ++t) {
           float xh = (vx[i].get(t) - mu) * r;
           float d = vd[i].get(t);
-          float g = gamma ? d * gamma[j * V + t] : d;
+          float g = d * gm[i][t];
           sg += g;
           sgx += g * xh;
           pg[i][t] += d * xh;
@@ -116,7 +135,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
         for (int t = 0; t < V; ++t) {
           float xh = (vx[i].get(t) - mu) * r;
           float d = vd[i].get(t);
-          float g = gamma ? d * gamma[j * V + t] : d;
+          float g = d * gm[i][t];
           float f = r * (g - sg - xh * sgx);
           if (dres) f += rs.get(t);
           o.set(t, f);
@@ -155,8 +174,8 @@ constexpr int QK_MAXP = 4;  // pairs per lane -> hd <= 256
 template <typename T>
 __global__ void __launch_bounds__(256)
 qknorm_rope_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, const float* __restrict__ q_scale,
-                       const float* __restrict__ k_scale, const float* __restrict__ cos_tab,
-                       const float* __restrict__ sin_tab, long long rows, int H, int hd, long long pos_div, int pos_mod,
+                       const float* __restrict__ k_scale, const T* __restrict__ cos_tab,
+                       const T* __restrict__ sin_tab, long long rows, int H, int hd, long long pos_div, int pos_mod,
                        float eps) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -194,8 +213,8 @@ qknorm_rope_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, const flo
       if (i < half) {
         float x1 = round_to<T>((a[p] - mu) * r * sc[i]);
         float x2 = round_to<T>((b[p] - mu) * r * sc[i + half]);
-        float c1 = round_to<T>(cos_tab[(long long)pos * hd + i]), c2 = round_to<T>(cos_tab[(long long)pos * hd + i + half]);
-        float s1 = round_to<T>(sin_tab[(long long)pos * hd + i]), sn2 = round_to<T>(sin_tab[(long long)pos * hd + i + half]);
+        float c1 = to_f(cos_tab[(long long)pos * hd + i]), c2 = to_f(cos_tab[(long long)pos * hd + i + half]);
+        float s1 = to_f(sin_tab[(long long)pos * hd + i]), sn2 = to_f(sin_tab[(long long)pos * hd + i + half]);
         // y = x*cos + rotate_half(x)*sin, rotate_half(x) = [-x2, x1]
         float y1 = round_to<T>(x1 * c1) + round_to<T>(-x2 * s1);
         float y2 = round_to<T>(x2 * c2) + round_to<T>(x1 * sn2);
@@ -209,8 +228,8 @@ qknorm_rope_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ out, const flo
 template <typename T>
 __global__ void __launch_bounds__(256)
 qknorm_rope_bwd_kernel(T* __restrict__ dqkv, const T* __restrict__ qkv, const float* __restrict__ q_scale,
-                       const float* __restrict__ k_scale, const float* __restrict__ cos_tab,
-                       const float* __restrict__ sin_tab, float* __restrict__ dq_scale, float* __restrict__ dk_scale,
+                       const float* __restrict__ k_scale, const T* __restrict__ cos_tab,
+                       const T* __restrict__ sin_tab, float* __restrict__ dq_scale, float* __restrict__ dk_scale,
                        long long rows, int H, int hd, long long pos_div, int pos_mod, float eps) {
   __shared__ float red[2][2 * 32 * QK_MAXP];  // [which][hd]
   const int lane = threadIdx.x & 31;
@@ -245,8 +264,8 @@ qknorm_rope_bwd_kernel(T* __restrict__ dqkv, const T* __restrict__ qkv, const fl
         s += a[p] + b[p];
         s2 += a[p] * a[p] + b[p] * b[p];
         float dy1 = to_f(g[i]), dy2 = to_f(g[i + half]);
-        float c1 = round_to<T>(cos_tab[(long long)pos * hd + i]), c2 = round_to<T>(cos_tab[(long long)pos * hd + i + half]);
-        float s1 = round_to<T>(sin_tab[(long long)pos * hd + i]), sn2 = round_to<T>(sin_tab[(long long)pos * hd + i + half]);
+        float c1 = to_f(cos_tab[(long long)pos * hd + i]), c2 = to_f(cos_tab[(long long)pos * hd + i + half]);
+        float s1 = to_f(sin_tab[(long long)pos * hd + i]), sn2 = to_f(sin_tab[(long long)pos * hd + i + half]);
         // y1 = x1*c1 - x2*s1 ; y2 = x2*c2 + x1*sn2
         da[p] = dy1 * c1 + dy2 * sn2;
         db[p] = dy2 * c2 - dy1 * s1;
@@ -298,6 +317,151 @@ qknorm_rope_bwd_kernel(T* __restrict__ dqkv, const T* __restrict__ qkv, const fl
   for (int c = threadIdx.x; c < hd; c += blockDim.x) {
     if (dq_scale) atomicAdd(dq_scale + c, red[0][c]);
     if (dk_scale) atomicAdd(dk_scale + c, red[1][c]);
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Fast path (bf16, head_dim 64): each thread owns 8 consecutive elements (one 16-byte access) of one head vector, 8
+// lanes form a head vector (LayerNorm statistics: 3 shuffle steps), the rotate_half partner is lane ^ 4 (4 packed
+// shuffles).  A thread keeps the same (q|k, head, slice) for every row it visits, so its scale slice lives in registers
+// and its d(scale) partials need one smem atomic per element at the very end.
+// -----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t bf_pack(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+__global__ void __launch_bounds__(256)
+qknorm_rope_fwd_hd64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, const float* __restrict__ q_scale,
+                            const float* __restrict__ k_scale, const bf16* __restrict__ cos_tab,
+                            const bf16* __restrict__ sin_tab, long long rows, int H, long long pos_div, int pos_mod,
+                            float eps) {
+  const int cpr = 16 * H;                       // 16-byte chunks of q|k per row
+  const int c = threadIdx.x % cpr, rpi = blockDim.x / cpr;
+  const int part = c & 7;
+  const bool second = part >= 4;
+  const float* scp = (c >= 8 * H ? k_scale : q_scale) + part * 8;
+  float sc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sc[t] = __ldg(scp + t);
+  const long long in_ld = 192LL * H, out_ld = 128LL * H;
+  for (long long row = (long long)blockIdx.x * rpi + threadIdx.x / cpr; row < rows; row += (long long)gridDim.x * rpi) {
+    const int pos = (int)((row / pos_div) % pos_mod);
+    const uint4 xv = *reinterpret_cast<const uint4*>(qkv + row * in_ld + c * 8);
+    const uint4 cv = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
+    float f[8];
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]); }
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mu = s * (1.f / 64.f);
+    const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
+    uint32_t xn[4], xp[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xn[t] = bf_pack((f[2 * t] - mu) * r * sc[2 * t], (f[2 * t + 1] - mu) * r * sc[2 * t + 1]);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xp[t] = __shfl_xor_sync(0xffffffffu, xn[t], 4);
+    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
+    uint32_t yo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      // y = x*cos + rotate_half(x)*sin, rotate_half(x) = [-x2, x1]; every product is rounded to bf16 like the reference
+      const float a0 = bf_round(bf_lo(xn[t]) * bf_lo(cw[t])), a1 = bf_round(bf_hi(xn[t]) * bf_hi(cw[t]));
+      const float p0 = second ? bf_lo(xp[t]) : -bf_lo(xp[t]), p1 = second ? bf_hi(xp[t]) : -bf_hi(xp[t]);
+      const float b0 = bf_round(p0 * bf_lo(sw_[t])), b1 = bf_round(p1 * bf_hi(sw_[t]));
+      yo[t] = bf_pack(a0 + b0, a1 + b1);
+    }
+    *reinterpret_cast<uint4*>(out + row * out_ld + c * 8) = make_uint4(yo[0], yo[1], yo[2], yo[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv, const float* __restrict__ q_scale,
+                            const float* __restrict__ k_scale, const bf16* __restrict__ cos_tab,
+                            const bf16* __restrict__ sin_tab, float* __restrict__ dq_scale, float* __restrict__ dk_scale,
+                            long long rows, int H, long long pos_div, int pos_mod, float eps) {
+  __shared__ float red[2][64];
+  const int cpr = 16 * H;
+  const int c = threadIdx.x % cpr, rpi = blockDim.x / cpr;
+  const int part = c & 7;
+  const bool second = part >= 4;
+  const int which = c >= 8 * H ? 1 : 0;
+  const float* scp = (which ? k_scale : q_scale) + part * 8;
+  float sc[8], ps[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { sc[t] = __ldg(scp + t); ps[t] = 0.f; }
+  const long long ld = 192LL * H;
+  for (long long row = (long long)blockIdx.x * rpi + threadIdx.x / cpr; row < rows; row += (long long)gridDim.x * rpi) {
+    const int pos = (int)((row / pos_div) % pos_mod);
+    const long long off = row * ld + c * 8;
+    const uint4 xv = *reinterpret_cast<const uint4*>(qkv + off);
+    const uint4 gv = *reinterpret_cast<const uint4*>(dqkv + off);
+    const uint4 cv = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
+    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
+    float f[8], d[8];
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]);
+      const uint32_t gp = __shfl_xor_sync(0xffffffffu, gw[t], 4);      // partner's upstream gradient
+      const uint32_t sp = __shfl_xor_sync(0xffffffffu, sw_[t], 4);     // partner's sin slice
+      // y1 = x1*c1 - x2*s1 ; y2 = x2*c2 + x1*s2  =>  dx1 = dy1*c1 + dy2*s2 ; dx2 = dy2*c2 - dy1*s1
+      const float q0 = bf_lo(gp) * bf_lo(sp), q1 = bf_hi(gp) * bf_hi(sp);
+      d[2 * t] = fmaf(bf_lo(gw[t]), bf_lo(cw[t]), second ? -q0 : q0);
+      d[2 * t + 1] = fmaf(bf_hi(gw[t]), bf_hi(cw[t]), second ? -q1 : q1);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mu = s * (1.f / 64.f);
+    const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
+    float sg = 0.f, sgx = 0.f, xh[8], g[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      xh[t] = (f[t] - mu) * r;
+      g[t] = d[t] * sc[t];
+      sg += g[t];
+      sgx = fmaf(g[t], xh[t], sgx);
+      ps[t] = fmaf(d[t], xh[t], ps[t]);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    sg *= (1.f / 64.f);
+    sgx *= (1.f / 64.f);
+    uint32_t o4[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      o4[t] = bf_pack(r * (g[2 * t] - sg - xh[2 * t] * sgx), r * (g[2 * t + 1] - sg - xh[2 * t + 1] * sgx));
+    *reinterpret_cast<uint4*>(dqkv + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) (&red[0][0])[i] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 8; ++t) atomicAdd(&red[which][part * 8 + t], ps[t]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    if (dq_scale) atomicAdd(dq_scale + i, red[0][i]);
+    if (dk_scale) atomicAdd(dk_scale + i, red[1][i]);
   }
 }
 
@@ -509,32 +673,53 @@ int vvae_layernorm_bwd(const void* dy, const void* x, const float* mean, const f
   return ln_bwd_dispatch<bf16>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, D, as_stream(stream));
 }
 
+static bool qk_fast_ok(int dtype, int heads, int hd, const void* a, const void* b, const void* c, const void* d) {
+  if (dtype != VVAE_BF16 || hd != 64 || heads < 2 || (heads & 1) || 16 * heads > 256 || 256 % (16 * heads) != 0) return false;   // a warp must stay inside one row
+  return ((uintptr_t)a % 16 == 0) && ((uintptr_t)b % 16 == 0) && ((uintptr_t)c % 16 == 0) && ((uintptr_t)d % 16 == 0);
+}
+
 int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, const float* k_scale,
-                         const float* cos_tab, const float* sin_tab, long long rows, int heads, int hd,
+                         const void* cos_tab, const void* sin_tab, long long rows, int heads, int hd,
                          long long pos_div, int pos_mod, float eps, int dtype, vvae_stream_t stream) {
   if (rows <= 0) return VVAE_OK;
   VVAE_REQUIRE(qkv && qk_out && q_scale && k_scale && cos_tab && sin_tab, "qknorm_rope_fwd: null pointer");
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_fwd: bad hd=%d", hd);
+  if (qk_fast_ok(dtype, heads, hd, qkv, qk_out, cos_tab, sin_tab)) {
+    const int rpi = 256 / (16 * heads);
+    const int blocks = (int)std::min<long long>(cdiv(rows, rpi), 148LL * 8);
+    qknorm_rope_fwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+        (const bf16*)qkv, (bf16*)qk_out, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, rows, heads, pos_div,
+        pos_mod, eps);
+    return check_launch("qknorm_rope_fwd");
+  }
   const long long nvec = rows * 2 * heads;
   const int blocks = (int)std::min<long long>(cdiv(nvec, 8), 148LL * 16);
   VVAE_DISPATCH_DTYPE(dtype, T, (qknorm_rope_fwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(
-                                    (const T*)qkv, (T*)qk_out, q_scale, k_scale, cos_tab, sin_tab, rows, heads, hd,
-                                    pos_div, pos_mod, eps)));
+                                    (const T*)qkv, (T*)qk_out, q_scale, k_scale, (const T*)cos_tab, (const T*)sin_tab, rows,
+                                    heads, hd, pos_div, pos_mod, eps)));
   return check_launch("qknorm_rope_fwd");
 }
 
 int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, const float* k_scale,
-                         const float* cos_tab, const float* sin_tab, float* dq_scale, float* dk_scale, long long rows,
+                         const void* cos_tab, const void* sin_tab, float* dq_scale, float* dk_scale, long long rows,
                          int heads, int hd, long long pos_div, int pos_mod, float eps, int dtype,
                          vvae_stream_t stream) {
   if (rows <= 0) return VVAE_OK;
   VVAE_REQUIRE(dqkv && qkv && q_scale && k_scale && cos_tab && sin_tab, "qknorm_rope_bwd: null pointer");
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_bwd: bad hd=%d", hd);
+  if (qk_fast_ok(dtype, heads, hd, qkv, dqkv, cos_tab, sin_tab)) {
+    const int rpi = 256 / (16 * heads);
+    const int blocks = (int)std::min<long long>(cdiv(rows, rpi), 148LL * 4);
+    qknorm_rope_bwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+        (bf16*)dqkv, (const bf16*)qkv, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, dq_scale, dk_scale, rows,
+        heads, pos_div, pos_mod, eps);
+    return check_launch("qknorm_rope_bwd");
+  }
   const long long nvec = rows * 2 * heads;
   const int blocks = (int)std::min<long long>(cdiv(nvec, 8), 148LL * 8);
   VVAE_DISPATCH_DTYPE(dtype, T, (qknorm_rope_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(
-                                    (T*)dqkv, (const T*)qkv, q_scale, k_scale, cos_tab, sin_tab, dq_scale, dk_scale,
-                                    rows, heads, hd, pos_div, pos_mod, eps)));
+                                    (T*)dqkv, (const T*)qkv, q_scale, k_scale, (const T*)cos_tab, (const T*)sin_tab, dq_scale,
+                                    dk_scale, rows, heads, hd, pos_div, pos_mod, eps)));
   return check_launch("qknorm_rope_bwd");
 }
 

@@ -121,6 +121,18 @@ class RotaryEmbedding(nn.Module):
         dev = _default_device(device)
         self.register_buffer("cos_cached", torch.cos(emb).contiguous().to(dev), persistent=False)
         self.register_buffer("sin_cached", torch.sin(emb).contiguous().to(dev), persistent=False)
+        self._typed = {}
+
+    def tables(self, dtype):
+        """cos/sin in the compute dtype (the reference casts them to q's dtype, train/layers.py:124-127)."""
+        if dtype == torch.float32:
+            return self.cos_cached, self.sin_cached
+        ent = self._typed.get(dtype)
+        if ent is None or ent[0].device != self.cos_cached.device:
+            from . import ops
+            ent = (ops.cast(self.cos_cached, dtype), ops.cast(self.sin_cached, dtype))
+            self._typed[dtype] = ent
+        return ent
 
 
 def _mask_rows(mask, n_rows, L):
@@ -150,8 +162,7 @@ class Attention(nn.Module):
     def _run(self, x, cfg):
         return F_.AttnBlockFn.apply(x, cfg, self.input_norm.scale, self.input_norm.bias, self.qkv_projection.kernel,
                                     self.qkv_projection.bias, self.q_norm.scale, self.k_norm.scale,
-                                    self.out_projection.kernel, self.out_projection.bias, self.ROPE.cos_cached,
-                                    self.ROPE.sin_cached)
+                                    self.out_projection.kernel, self.out_projection.bias, *self.ROPE.tables(self.dtype))
 
     def forward(self, x, mask=None):
         a, seq, _ = x.shape
