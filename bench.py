@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--dec-depth", type=int, default=PROD["decoder_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
+                    "of replaying the captured CUDA graph; N > 1 then overlaps the bucketed all-reduce with backward")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
     return ap.parse_args()
 
@@ -154,6 +156,7 @@ def run_ours(args):
     import video_vae_b200 as V
     from video_vae_b200 import _ffi, ops
     from video_vae_b200.ddp import FlatAdam, FlatParams, GradAllReducer
+    from video_vae_b200.graph import GraphedTrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,7 +175,7 @@ def run_ours(args):
         model.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7))
     flat = FlatParams(model)
     flat.enable_bf16_shadow()
-    reducer = GradAllReducer(flat) if world > 1 else None
+    reducer = GradAllReducer(flat) if (world > 1 and args.no_graph) else None
     opt = None if args.no_optimizer else FlatAdam(flat, lr=5e-5)
     hp = dict(V.DEFAULT_HPARAMS, gamma4=0.1)   # MSE + selection + KL + MAE terms
 
@@ -183,7 +186,9 @@ def run_ours(args):
     mask = host_mask.to(dev, non_blocking=True)
     rngs = V.Rngs(3 + rank)
 
-    def step(v, m):
+    graphed = None if args.no_graph else GraphedTrainStep(model, flat, video, mask, hp)
+
+    def eager_step(v, m):
         flat.zero_grad()
         if reducer:
             reducer.start_step()
@@ -191,6 +196,17 @@ def run_ours(args):
         loss.backward()
         if reducer:
             reducer.finish_step()
+        return loss
+
+    def step(v, m):
+        """One training step.  Default: replay the captured graph (zero-grad + fwd + loss + bwd: one launch), then the
+        gradient all-reduce (N > 1) and the fused clip + Adam kernels."""
+        if graphed is not None:
+            loss = graphed(v, m, rngs)
+            if world > 1:
+                dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+        else:
+            loss = eager_step(v, m)
         if opt:
             opt.step(grad_scale=1.0 / world)
         return loss
@@ -207,17 +223,32 @@ def run_ours(args):
 
     # ---- device-resident timed region, with per-launch CUDA events on the dominant kernel class (GEMM)
     clocks = ClockSampler(local) if rank == 0 else None
-    ops.PROFILE = []
+    ops.PROFILE = [] if graphed is None else None
     calls0 = _ffi.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
         step(video, mask)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps      # CPU time to ENQUEUE a step (no sync inside)
     e1.record()
     sync_all()
     calls = _ffi.launch_count - calls0
     prof, ops.PROFILE = ops.PROFILE, None
     clock_info = clocks.stop() if clocks else None
+    kernels_per_step = None
+    if graphed is not None:
+        # The graph hides individual launches from CUDA events: time the SAME kernels with per-launch events in one
+        # eager pass over the same batch (kernel durations do not depend on how they were enqueued).
+        ops.PROFILE = []
+        calls_e0 = _ffi.launch_count
+        eager_step(video, mask)
+        torch.cuda.synchronize()
+        kernels_per_step = _ffi.launch_count - calls_e0
+        prof, ops.PROFILE = ops.PROFILE, None
+        prof_steps = 1
+    else:
+        prof_steps = args.steps
     ms = e0.elapsed_time(e1) / args.steps
     if world > 1:
         tms = torch.tensor([ms], device=dev)
@@ -229,9 +260,12 @@ def run_ours(args):
     e0.record()
     last = 0.0
     for _ in range(args.steps):
-        v = host_video.to(dev, non_blocking=True)
-        m = host_mask.to(dev, non_blocking=True)
-        last = step(v, m).item()
+        if graphed is not None:        # pinned host -> the graph's static input buffers, replay, loss -> host
+            last = step(host_video, host_mask).item()
+        else:
+            v = host_video.to(dev, non_blocking=True)
+            m = host_mask.to(dev, non_blocking=True)
+            last = step(v, m).item()
     e1.record()
     sync_all()
     ms_e2e = e0.elapsed_time(e1) / args.steps
@@ -260,8 +294,8 @@ def run_ours(args):
     roofline = None
     table = []
     for name, (t, fl, nb, n) in sorted(classes.items(), key=lambda kv: -kv[1][0]):
-        table.append({"kernel": name, "launches_per_step": n / args.steps, "ms_per_step": t * 1e3 / args.steps,
-                      "share_of_step": t * 1e3 / args.steps / ms, "tflops": fl / t / 1e12 if t > 0 else 0.0})
+        table.append({"kernel": name, "launches_per_step": n / prof_steps, "ms_per_step": t * 1e3 / prof_steps,
+                      "share_of_step": t * 1e3 / prof_steps / ms, "tflops": fl / t / 1e12 if t > 0 else 0.0})
     if args.profile_kernels:
         for row in table:
             print(json.dumps(row), file=sys.stderr)
@@ -271,8 +305,10 @@ def run_ours(args):
         roofline = {"kernel": "gemm_sm100_kernel (tcgen05 bf16 GEMM: every Linear fwd/dgrad/wgrad)", "bound": "tensor",
                     "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                    if peaks else "fallback", "traffic": None, "launches_per_step": n / args.steps,
-                    "share_of_step": t * 1e3 / args.steps / ms}
+                    if peaks else "fallback", "traffic": None, "launches_per_step": n / prof_steps,
+                    "share_of_step": t * 1e3 / prof_steps / ms,
+                    "timing": "CUDA events around every launch of this kernel in one eager pass after the timed region"
+                    if graphed is not None else "CUDA events around every launch inside the timed region"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -288,7 +324,12 @@ def run_ours(args):
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": host_video.numel() * host_video.element_size() + host_mask.numel(),
                 "d2h_bytes_per_step": 4, "last_loss": last},
-        "gpu_launches": calls, "gpu_launches_note": "libvvae C-ABI kernel-launching calls in the timed region (>= kernels/3)",
+        "host_enqueue_ms_per_step": host_ms,
+        "gpu_launches": (kernels_per_step * args.steps + calls) if graphed is not None else calls,
+        "gpu_launches_note": ("libvvae kernel-launching C-ABI calls executed in the timed region: those captured in the "
+                              "replayed CUDA graph (counted in one eager pass) x steps + those enqueued directly")
+        if graphed is not None else "libvvae C-ABI kernel-launching calls in the timed region",
+        "execution": "cuda-graph replay (zero-grad+fwd+loss+bwd) + eager optimizer" if graphed is not None else "eager",
         "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
     }
     if world == 1 and not args.no_cpu_baseline:

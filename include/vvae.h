@@ -232,16 +232,26 @@ int vvae_reparam_gate_bwd(const void* dc, const void* mean, const void* logvar, 
 int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
                         const float* inv_len, float* out2, int B, int T, long long per_frame, int dtype,
                         vvae_stream_t stream);
-/* drecon[b,t,p] = -(2*w_mse*e + w_mae*sign(e)) * m[b,t] * inv_len[b] * inv_count, e = (video-recon)*m. */
+/* drecon[b,t,p] = -(2*w_mse*e + w_mae*sign(e)) * m[b,t] * inv_len[b] * inv_count * (*gscale), e = (video-recon)*m.
+ * gscale: optional DEVICE fp32 scalar (the upstream d(loss); NULL = 1) so the step never synchronises with the host. */
 int vvae_recon_loss_bwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
-                        const float* inv_len, float w_mse, float w_mae, float inv_count, void* drecon, int B, int T,
+                        const float* inv_len, float w_mse, float w_mae, float inv_count, const float* gscale,
+                        void* drecon, int B, int T,
                         long long per_frame, int dtype, vvae_stream_t stream);
 /* out1[0] += sum 0.5*(exp(lv)-1-lv+mean^2) * frame_w[frame], frame_w = m/len   (caller divides by numel). */
 int vvae_kl_fwd(const void* mean, const void* logvar, const float* frame_w, float* out1, long long n_tok,
                 int tok_per_frame, int Dl, int dtype, vvae_stream_t stream);
-/* dmean = scale*frame_w[frame]*mean ; dlogvar = scale*frame_w[frame]*0.5*(exp(lv)-1)   (scale = dLoss/dKL / numel). */
-int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, void* dmean, void* dlogvar,
+/* dmean = s*frame_w[frame]*mean ; dlogvar = s*frame_w[frame]*0.5*(exp(lv)-1), s = scale * (*gscale)  (gscale: optional
+ * device scalar, NULL = 1; scale = gamma2 / numel). */
+int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, const float* gscale, void* dmean,
+                void* dlogvar,
                 long long n_tok, int tok_per_frame, int Dl, int dtype, vvae_stream_t stream);
+
+/* Materialise the Philox draws the fused kernels would make from (seed, offset): kind 0 = the N(0,1) noise of
+ * vvae_reparam_gate_fwd, kind 1 = the U(0,1) draws of vvae_selection_fwd.  Lets a captured CUDA graph take per-step
+ * randomness from a buffer (the explicit `eps` / `u` arguments) instead of kernel-argument constants. */
+int vvae_philox_fill(float* out, long long n, unsigned long long seed, unsigned long long offset, int kind,
+                     vvae_stream_t stream);
 
 /* ---- optimizer ("next" row f1: optax.chain(clip_by_global_norm, adam), train/rl_nonadversarial.py:241-253) ---- */
 /* out[0] += sum g^2 */

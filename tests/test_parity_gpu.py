@@ -487,3 +487,36 @@ def test_videovae_bf16_head_dim64_tensor_core_path(V):
         assert n >= 50
     for n_, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n_
+
+
+def test_cuda_graph_step_equals_eager_step(V):
+    """video_vae_b200.graph.GraphedTrainStep replays fwd+loss+bwd as one CUDA graph; with the same Rngs it must reproduce
+    the eager step (same Philox draws; fp32 atomics in the split-K weight gradients allow tiny reordering noise)."""
+    from video_vae_b200.ddp import FlatParams
+    from video_vae_b200.graph import GraphedTrainStep
+    cfg = (64, 64, 3, 16, 1, 1, 256, 2, 128, 32, 8, 4)
+    m = V.VideoVAE(*cfg, V.Rngs(2), dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.05, generator=torch.Generator(device="cuda").manual_seed(7))
+    flat = FlatParams(m)
+    flat.enable_bf16_shadow()
+    g = _gen(9)
+    video = torch.rand(2, 4, 64, 64, 3, generator=g).to(torch.bfloat16).cuda()
+    mask = torch.ones(2, 4, dtype=torch.bool).cuda()
+    mask[1, 3:] = False
+    # capture first (as a training script does), then compare against eager steps
+    graphed = GraphedTrainStep(m, flat, video, mask, V.DEFAULT_HPARAMS)
+    outs = []
+    for _ in range(2):                                  # replay twice: the second replay must not depend on the first
+        loss_g = graphed(video, mask, V.Rngs(5))
+        torch.cuda.synchronize()
+        outs.append((loss_g.item(), flat.grad.clone()))
+    loss_o = graphed(video, mask, V.Rngs(6)).item()     # new draws give a different step
+    flat.zero_grad()
+    loss_e, _ = V.loss_fn(m, video, mask[:, None, None, :], mask, V.Rngs(5), V.DEFAULT_HPARAMS, train=True)
+    loss_e.backward()
+    torch.cuda.synchronize()
+    for lg, gg in outs:
+        assert abs(lg - loss_e.item()) <= 1e-3 * abs(loss_e.item())   # fp32 atomics (GroupNorm statistics) reorder
+        assert rel_err(gg, flat.grad) < 2e-3
+    assert loss_o != loss_e.item()

@@ -109,9 +109,10 @@ _SIGS = {
     "vvae_reparam_gate_fwd": ([vp, vp, vp, u64, u64, vp, vp, vp, vp, vp, ll, i32, i32, i32, i32, vp], i32),
     "vvae_reparam_gate_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, i32, i32, vp], i32),
     "vvae_recon_loss_fwd": ([vp, i32, vp, vp, vp, vp, i32, i32, ll, i32, vp], i32),
-    "vvae_recon_loss_bwd": ([vp, i32, vp, vp, vp, f32, f32, f32, vp, i32, i32, ll, i32, vp], i32),
+    "vvae_recon_loss_bwd": ([vp, i32, vp, vp, vp, f32, f32, f32, vp, vp, i32, i32, ll, i32, vp], i32),
     "vvae_kl_fwd": ([vp, vp, vp, vp, ll, i32, i32, i32, vp], i32),
-    "vvae_kl_bwd": ([vp, vp, vp, f32, vp, vp, ll, i32, i32, i32, vp], i32),
+    "vvae_kl_bwd": ([vp, vp, vp, f32, vp, vp, vp, ll, i32, i32, i32, vp], i32),
+    "vvae_philox_fill": ([vp, ll, u64, u64, i32, vp], i32),
     "vvae_sumsq_f32": ([vp, ll, vp, vp], i32),
     "vvae_adam_step": ([vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, vp, f32, f32, vp], i32),
 }

@@ -30,6 +30,23 @@ __device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
   return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
 }
 
+// The same draws the fused kernels make, materialised (kind 0: N(0,1) of the reparameterisation; kind 1: U(0,1) of the
+// Gumbel gate), so a captured CUDA graph can read per-step noise from a buffer instead of baking (seed, offset) in.
+__global__ void philox_fill_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                                   int kind) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  Philox rng(seed);
+  for (; i < n; i += stride) {
+    if (kind == 0) {
+      const uint4 r = rng(offset + (unsigned long long)i, 0x9a55ull);
+      out[i] = normal_from(r.x, r.y);
+    } else {
+      out[i] = u01(rng(offset + (unsigned long long)i, 0x5e1ec7ull).x);
+    }
+  }
+}
+
 // ---------------- tokens <-> voxels rearrangement ----------------
 // tokens [BT, (h w), (p1 p2 c)]  <->  voxels [BT, (h p1), (w p2), c];  runs of P*C elements are contiguous on both sides.
 template <typename TI, typename TO>
@@ -294,10 +311,11 @@ __global__ void recon_loss_fwd_kernel(const TV* __restrict__ video, const T* __r
 template <typename TV, typename T>
 __global__ void recon_loss_bwd_kernel(const TV* __restrict__ video, const T* __restrict__ recon,
                                       const float* __restrict__ fmask, const float* __restrict__ inv_len, float w_mse,
-                                      float w_mae, float inv_count, T* __restrict__ drecon, int Tn, long long per_frame,
-                                      long long total) {
+                                      float w_mae, float inv_count, const float* __restrict__ gscale,
+                                      T* __restrict__ drecon, int Tn, long long per_frame, long long total) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (gscale) inv_count *= __ldg(gscale);   // upstream d(loss) as a device scalar: no host round trip
   for (; i < total; i += stride) {
     const long long frame = i / per_frame;
     const float m = fmask[frame];
@@ -329,10 +347,11 @@ __global__ void kl_fwd_kernel(const T* __restrict__ mean, const T* __restrict__ 
 
 template <typename T>
 __global__ void kl_bwd_kernel(const T* __restrict__ mean, const T* __restrict__ logvar, const float* __restrict__ frame_w,
-                              float scale, T* __restrict__ dmean, T* __restrict__ dlogvar, long long n,
-                              long long per_frame_el) {
+                              float scale, const float* __restrict__ gscale, T* __restrict__ dmean,
+                              T* __restrict__ dlogvar, long long n, long long per_frame_el) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  if (gscale) scale *= __ldg(gscale);
   for (; i < n; i += stride) {
     const float w = frame_w[i / per_frame_el] * scale;
     dmean[i] = from_f<T>(w * to_f(mean[i]));
@@ -522,14 +541,14 @@ int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, c
 }
 
 int vvae_recon_loss_bwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
-                        const float* inv_len, float w_mse, float w_mae, float inv_count, void* drecon, int B, int T,
+                        const float* inv_len, float w_mse, float w_mae, float inv_count, const float* gscale, void* drecon, int B, int T,
                         long long per_frame, int dtype, vvae_stream_t stream) {
   if (B <= 0) return VVAE_OK;
   VVAE_REQUIRE(video && recon && frame_mask && inv_len && drecon, "recon_loss_bwd: null pointer");
   const long long total = (long long)B * T * per_frame;
   const int blocks = ew_blocks(total);
   cudaStream_t s = as_stream(stream);
-#define RL_BWD(TV, TT) recon_loss_bwd_kernel<TV, TT><<<blocks, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask, inv_len, w_mse, w_mae, inv_count, (TT*)drecon, T, per_frame, total)
+#define RL_BWD(TV, TT) recon_loss_bwd_kernel<TV, TT><<<blocks, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask, inv_len, w_mse, w_mae, inv_count, gscale, (TT*)drecon, T, per_frame, total)
   if (video_dtype == VVAE_F32 && dtype == VVAE_F32) RL_BWD(float, float);
   else if (video_dtype == VVAE_F32 && dtype == VVAE_BF16) RL_BWD(float, bf16);
   else if (video_dtype == VVAE_BF16 && dtype == VVAE_BF16) RL_BWD(bf16, bf16);
@@ -549,15 +568,24 @@ int vvae_kl_fwd(const void* mean, const void* logvar, const float* frame_w, floa
   return check_launch("kl_fwd");
 }
 
-int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, void* dmean, void* dlogvar,
+int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, const float* gscale, void* dmean,
+                void* dlogvar,
                 long long n_tok, int tok_per_frame, int Dl, int dtype, vvae_stream_t stream) {
   if (n_tok <= 0) return VVAE_OK;
   VVAE_REQUIRE(mean && logvar && frame_w && dmean && dlogvar, "kl_bwd: null pointer");
   const long long n = n_tok * Dl;
   VVAE_DISPATCH_DTYPE(dtype, T, (kl_bwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
-                                    (const T*)mean, (const T*)logvar, frame_w, scale, (T*)dmean, (T*)dlogvar, n,
+                                    (const T*)mean, (const T*)logvar, frame_w, scale, gscale, (T*)dmean, (T*)dlogvar, n,
                                     (long long)tok_per_frame * Dl)));
   return check_launch("kl_bwd");
+}
+
+int vvae_philox_fill(float* out, long long n, unsigned long long seed, unsigned long long offset, int kind,
+                     vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(out && (kind == 0 || kind == 1), "philox_fill: bad arguments");
+  philox_fill_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(out, n, seed, offset, kind);
+  return check_launch("philox_fill");
 }
 
 int vvae_sumsq_f32(const float* g, long long n, float* out1, vvae_stream_t stream) {

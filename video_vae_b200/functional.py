@@ -482,13 +482,13 @@ class VaeLossFn(Function):
         video, recon, sel, logvar, mean, m, inv_len, frame_w, diff = ctx.saved_tensors
         hp = ctx.hp
         B, T = m.shape
-        # TODO(perf): gl is read on the host (one sync per step); pass it as a device scalar instead.
-        g = float(gl)
-        drecon = ops.recon_loss_bwd(video, recon, m.reshape(-1).contiguous(), inv_len, g, g * hp.get("gamma4", 0.0),
-                                    1.0 / ctx.count)
-        dmean, dlogvar = ops.kl_bwd(mean, logvar, frame_w, g * hp["gamma2"] / float(mean.numel()), mean.shape[2])
+        # the upstream gradient stays on the device (a kernel argument), so the step never waits for the host
+        g = gl.detach().reshape(1).to(torch.float32)
+        drecon = ops.recon_loss_bwd(video, recon, m.reshape(-1).contiguous(), inv_len, 1.0, hp.get("gamma4", 0.0),
+                                    1.0 / ctx.count, gscale=g)
+        dmean, dlogvar = ops.kl_bwd(mean, logvar, frame_w, hp["gamma2"] / float(mean.numel()), mean.shape[2], gscale=g)
         rate = hp["magnify_negatives_rate"]
         slope = torch.where(diff < 0, torch.full_like(diff, rate), torch.ones_like(diff))
-        ddens = (g * hp["gamma1"] / B) * 2.0 * (diff * slope) * slope                      # [B]
+        ddens = g * ((hp["gamma1"] / B) * 2.0) * (diff * slope) * slope                    # [B]
         dsel = (ddens[:, None] * m * inv_len[:, None]).reshape(sel.shape).to(sel.dtype)
         return None, drecon, dsel, dlogvar, dmean, None, None

@@ -1,0 +1,71 @@
+"""CUDA-graph capture of the training step.
+
+One step of the production model is ~1200 kernel launches; enqueuing them from Python costs about as much wall time
+as the B200 needs to execute them, so the whole forward + loss + backward is captured ONCE into a CUDA graph and
+replayed with a single launch per step.  What varies between steps lives in static device buffers the graph reads:
+the input clip and mask (copied in before the replay) and the Philox draws of the step (materialised by
+``vvae_philox_fill`` from the same (seed, offset) pairs the fused kernels would use, so a replay is bit-identical to
+the eager step).  The optimizer (and, for N > 1, the gradient all-reduce) runs outside the graph: the bias-corrected
+Adam constants change every step and are passed by value.
+"""
+import torch
+
+from . import functional as F_
+from . import ops
+from .losses import DEFAULT_HPARAMS, loss_fn
+
+
+class GraphedTrainStep:
+    """fwd + loss + bwd of ``model`` on a fixed (batch, frames, size) shape as one CUDA graph."""
+
+    def __init__(self, model, flat, video_like, mask_like, hparams=None, warmup=2):
+        self.model, self.flat = model, flat
+        self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
+        dev = video_like.device
+        b, t = mask_like.shape
+        hw = (video_like.shape[2] // model.encoder.patch_embedding.patch_size) * \
+             (video_like.shape[3] // model.encoder.patch_embedding.patch_size)
+        lat = model.fill_token.shape[-1]
+        self.video = torch.empty_like(video_like)
+        self.mask = torch.empty_like(mask_like)
+        self.noise = torch.empty(b, t, hw, lat, dtype=torch.float32, device=dev)
+        self.gumbel_u = torch.empty(b, t, 1, dtype=torch.float32, device=dev)
+        self.video.copy_(video_like)
+        self.mask.copy_(mask_like)
+        ops.philox_fill_(self.noise, 0, 1 << 40, "normal")
+        ops.philox_fill_(self.gumbel_u, 0, 2 << 40, "uniform")
+        self.graph = torch.cuda.CUDAGraph()
+        self.loss = None
+        self.aux = None
+        prof, ops.PROFILE = ops.PROFILE, None            # event timing cannot be captured
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            F_.invalidate_shadows()                      # every derived weight image is rebuilt INSIDE the graph
+            with torch.cuda.graph(self.graph):
+                self.loss, self.aux = self._body()
+        finally:
+            ops.PROFILE = prof
+
+    def _body(self):
+        self.flat.zero_grad()
+        loss, aux = loss_fn(self.model, self.video, self.mask[:, None, None, :], self.mask, None, self.hp, train=True,
+                            noise=self.noise, gumbel_u=self.gumbel_u)
+        loss.backward()
+        return loss.detach(), {k: v.detach() for k, v in aux.items()}
+
+    def __call__(self, video, mask, rngs):
+        """Same draws, same order as the eager path: the encoder's gate first, then the reparameterisation."""
+        self.video.copy_(video, non_blocking=True)
+        self.mask.copy_(mask, non_blocking=True)
+        seed, off = rngs.sampling()
+        ops.philox_fill_(self.gumbel_u, seed, off, "uniform")
+        seed, off = rngs.sampling()
+        ops.philox_fill_(self.noise, seed, off, "normal")
+        self.graph.replay()
+        return self.loss

@@ -392,12 +392,13 @@ def recon_loss_fwd(video, recon, frame_mask, inv_len, out2):
                                   per_frame, dt(recon), stream()), "vvae_recon_loss_fwd")
 
 
-def recon_loss_bwd(video, recon, frame_mask, inv_len, w_mse, w_mae, inv_count):
+def recon_loss_bwd(video, recon, frame_mask, inv_len, w_mse, w_mae, inv_count, gscale=None):
+    """gscale: optional fp32 device scalar multiplied in (the upstream gradient), so no host read is needed."""
     B, T = video.shape[:2]
     per_frame = video.numel() // (B * T)
     d = torch.empty_like(recon)
     check(lib.vvae_recon_loss_bwd(ptr(video), dt(video), ptr(recon), ptr(frame_mask), ptr(inv_len), float(w_mse),
-                                  float(w_mae), float(inv_count), ptr(d), B, T, per_frame, dt(recon), stream()),
+                                  float(w_mae), float(inv_count), ptr(gscale), ptr(d), B, T, per_frame, dt(recon), stream()),
           "vvae_recon_loss_bwd")
     return d
 
@@ -408,12 +409,20 @@ def kl_fwd(mean, logvar, frame_w, out1, tok_per_frame):
                           dt(mean), stream()), "vvae_kl_fwd")
 
 
-def kl_bwd(mean, logvar, frame_w, scale, tok_per_frame):
+def kl_bwd(mean, logvar, frame_w, scale, tok_per_frame, gscale=None):
     Dl = mean.shape[-1]
     dmean, dlogvar = torch.empty_like(mean), torch.empty_like(logvar)
-    check(lib.vvae_kl_bwd(ptr(mean), ptr(logvar), ptr(frame_w), float(scale), ptr(dmean), ptr(dlogvar),
+    check(lib.vvae_kl_bwd(ptr(mean), ptr(logvar), ptr(frame_w), float(scale), ptr(gscale), ptr(dmean), ptr(dlogvar),
                           mean.numel() // Dl, tok_per_frame, Dl, dt(mean), stream()), "vvae_kl_bwd")
     return dmean, dlogvar
+
+
+def philox_fill_(out, seed, offset, kind):
+    """kind 'normal' = the reparameterisation draws, 'uniform' = the Gumbel-gate draws of the same (seed, offset)."""
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    check(lib.vvae_philox_fill(ptr(out), out.numel(), int(seed), int(offset), 0 if kind == "normal" else 1, stream()),
+          "vvae_philox_fill")
+    return out
 
 
 def sumsq_accum(g, out1):
