@@ -13,62 +13,75 @@ layernorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __
                      const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      long long rows, int D, float eps) {
   constexpr int V = Vec16<T>::N;
+  constexpr int UR = 2;                     // rows in flight per warp
+  extern __shared__ float ln_sm[];          // gamma[D] | beta[D]: read back as 16-byte broadcasts-free vectors
+  float* sg = ln_sm;
+  float* sb = ln_sm + D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    sg[i] = gamma ? gamma[i] : 1.f;
+    sb[i] = beta ? beta[i] : 0.f;
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = D / V;
-  float gm[NCHUNK][V], bt[NCHUNK][V];      // this lane's slice of gamma / beta, loaded once
+  for (long long row0 = warp0; row0 < rows; row0 += UR * nwarps) {
+    Vec16<T> v[UR][NCHUNK];
 #pragma unroll
-  for (int i = 0; i < NCHUNK; ++i) {
-    const int j = lane + 32 * i;
+    for (int u = 0; u < UR; ++u) {
+      const long long row = row0 + u * nwarps;
+      if (row < rows) {
 #pragma unroll
-    for (int t = 0; t < V; t += 4) {
-      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < nvec) {
-        if (gamma) g4 = __ldg(reinterpret_cast<const float4*>(gamma + j * V + t));
-        if (beta) b4 = __ldg(reinterpret_cast<const float4*>(beta + j * V + t));
-      }
-      gm[i][t] = g4.x; gm[i][t + 1] = g4.y; gm[i][t + 2] = g4.z; gm[i][t + 3] = g4.w;
-      bt[i][t] = b4.x; bt[i][t + 1] = b4.y; bt[i][t + 2] = b4.z; bt[i][t + 3] = b4.w;
-    }
-  }
-  for (long long row = warp0; row < rows; row += nwarps) {
-    const T* xr = x + row * D;
-    Vec16<T> v[NCHUNK];
-    float s = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-      int j = lane + 32 * i;
-      if (j < nvec) {
-        v[i].load(xr + j * V);
-#pragma unroll
-        for (int t = 0; t < V; ++t) {
-          float f = v[i].get(t);
-          s += f;
-          s2 += f * f;
+        for (int i = 0; i < NCHUNK; ++i) {
+          const int j = lane + 32 * i;
+          if (j < nvec) v[u][i].load(x + row * D + j * V);
         }
       }
     }
-    s = warp_sum(s);
-    s2 = warp_sum(s2);
-    const float mu = s / D;
-    const float var = fmaxf(s2 / D - mu * mu, 0.f);
-    const float r = rsqrtf(var + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mu;
-      if (rstd_out) rstd_out[row] = r;
-    }
-    T* yr = y + row * D;
 #pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
-      int j = lane + 32 * i;
-      if (j < nvec) {
-        Vec16<T> o;
+    for (int u = 0; u < UR; ++u) {
+      const long long row = row0 + u * nwarps;
+      if (row >= rows) break;
+      float s = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int t = 0; t < V; ++t) {
-          o.set(t, fmaf((v[i].get(t) - mu) * r, gm[i][t], bt[i][t]));
+      for (int i = 0; i < NCHUNK; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+#pragma unroll
+          for (int t = 0; t < V; ++t) {
+            const float f = v[u][i].get(t);
+            s += f;
+            s2 = fmaf(f, f, s2);
+          }
         }
-        o.store(yr + j * V);
+      }
+      s = warp_sum(s);
+      s2 = warp_sum(s2);
+      const float mu = s / D;
+      const float var = fmaxf(s2 / D - mu * mu, 0.f);
+      const float r = rsqrtf(var + eps);
+      if (lane == 0) {
+        if (mean_out) mean_out[row] = mu;
+        if (rstd_out) rstd_out[row] = r;
+      }
+      T* yr = y + row * D;
+#pragma unroll
+      for (int i = 0; i < NCHUNK; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+          Vec16<T> o;
+#pragma unroll
+          for (int t = 0; t < V; t += 4) {
+            const float4 g4 = *reinterpret_cast<const float4*>(sg + j * V + t);
+            const float4 b4 = *reinterpret_cast<const float4*>(sb + j * V + t);
+            o.set(t, fmaf((v[u][i].get(t) - mu) * r, g4.x, b4.x));
+            o.set(t + 1, fmaf((v[u][i].get(t + 1) - mu) * r, g4.y, b4.y));
+            o.set(t + 2, fmaf((v[u][i].get(t + 2) - mu) * r, g4.z, b4.z));
+            o.set(t + 3, fmaf((v[u][i].get(t + 3) - mu) * r, g4.w, b4.w));
+          }
+          o.store(yr + j * V);
+        }
       }
     }
   }
@@ -87,35 +100,37 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int nvec = D / V;
-  float pg[NCHUNK][V], pb[NCHUNK][V], gm[NCHUNK][V];
+  float pg[NCHUNK][V], pb[NCHUNK][V];
+  float* sgam = red + 2 * D;                 // gamma staged in shared memory (keeps 8*NCHUNK registers free)
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sgam[i] = gamma ? gamma[i] : 1.f;
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < NCHUNK; ++i) {
-    const int j = lane + 32 * i;
-#pragma unroll
-    for (int t = 0; t < V; t += 4) {
-      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-      if (gamma && j < nvec) g4 = __ldg(reinterpret_cast<const float4*>(gamma + j * V + t));
-      gm[i][t] = g4.x; gm[i][t + 1] = g4.y; gm[i][t + 2] = g4.z; gm[i][t + 3] = g4.w;
-    }
+  for (int i = 0; i < NCHUNK; ++i)
 #pragma unroll
     for (int t = 0; t < V; ++t) pg[i][t] = pb[i][t] = 0.f;
-  }
 
   for (long long row = warp0; row < rows; row += nwarps) {
     const float mu = mean[row], r = rstd[row];
-    Vec16<T> vx[NCHUNK], vd[NCHUNK];
+    Vec16<T> vx[NCHUNK], vd[NCHUNK], vr[NCHUNK];
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCHUNK; ++i) {
+    for (int i = 0; i < NCHUNK; ++i) {          // every load of the row is issued before the first use
       int j = lane + 32 * i;
       if (j < nvec) {
         vx[i].load(x + row * D + j * V);
         vd[i].load(dy + row * D + j * V);
+        if (dres) vr[i].load(dres + row * D + j * V);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NCHUNK; ++i) {
+      int j = lane + 32 * i;
+      if (j < nvec) {
 #pragma unroll
         for (int t = 0; t < V; ++t) {
           float xh = (vx[i].get(t) - mu) * r;
           float d = vd[i].get(t);
-          float g = d * gm[i][t];
+          float g = d * sgam[j * V + t];
           sg += g;
           sgx += g * xh;
           pg[i][t] += d * xh;
@@ -129,15 +144,14 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
     for (int i = 0; i < NCHUNK; ++i) {
       int j = lane + 32 * i;
       if (j < nvec) {
-        Vec16<T> o, rs;
-        if (dres) rs.load(dres + row * D + j * V);
+        Vec16<T> o;
 #pragma unroll
         for (int t = 0; t < V; ++t) {
           float xh = (vx[i].get(t) - mu) * r;
           float d = vd[i].get(t);
-          float g = d * gm[i][t];
+          float g = d * sgam[j * V + t];
           float f = r * (g - sg - xh * sgx);
-          if (dres) f += rs.get(t);
+          if (dres) f += vr[i].get(t);
           o.set(t, f);
         }
         o.store(dx + row * D + j * V);
@@ -348,41 +362,55 @@ qknorm_rope_fwd_hd64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out
 #pragma unroll
   for (int t = 0; t < 8; ++t) sc[t] = __ldg(scp + t);
   const long long in_ld = 192LL * H, out_ld = 128LL * H;
-  for (long long row = (long long)blockIdx.x * rpi + threadIdx.x / cpr; row < rows; row += (long long)gridDim.x * rpi) {
-    const int pos = (int)((row / pos_div) % pos_mod);
-    const uint4 xv = *reinterpret_cast<const uint4*>(qkv + row * in_ld + c * 8);
-    const uint4 cv = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
-    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
-    float f[8];
-    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+  constexpr int UR = 2;                          // rows in flight per thread (independent 16-byte loads)
+  const long long rstride = (long long)gridDim.x * rpi;
+  for (long long row0 = (long long)blockIdx.x * rpi + threadIdx.x / cpr; row0 < rows; row0 += UR * rstride) {
+    uint4 xv[UR], cv[UR], sv[UR];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) { f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]); }
-    float s = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int u = 0; u < UR; ++u) {
+      const long long row = row0 + u * rstride;
+      if (row < rows) {
+        const int pos = (int)((row / pos_div) % pos_mod);
+        xv[u] = *reinterpret_cast<const uint4*>(qkv + row * in_ld + c * 8);
+        cv[u] = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+        sv[u] = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
+      }
     }
-    const float mu = s * (1.f / 64.f);
-    const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
-    uint32_t xn[4], xp[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) xn[t] = bf_pack((f[2 * t] - mu) * r * sc[2 * t], (f[2 * t + 1] - mu) * r * sc[2 * t + 1]);
+    for (int u = 0; u < UR; ++u) {
+      const long long row = row0 + u * rstride;
+      if (row >= rows) break;                    // uniform across the warp (a warp stays inside one row)
+      float f[8];
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) xp[t] = __shfl_xor_sync(0xffffffffu, xn[t], 4);
-    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
-    uint32_t yo[4];
+      for (int t = 0; t < 4; ++t) { f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]); }
+      float s = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      // y = x*cos + rotate_half(x)*sin, rotate_half(x) = [-x2, x1]; every product is rounded to bf16 like the reference
-      const float a0 = bf_round(bf_lo(xn[t]) * bf_lo(cw[t])), a1 = bf_round(bf_hi(xn[t]) * bf_hi(cw[t]));
-      const float p0 = second ? bf_lo(xp[t]) : -bf_lo(xp[t]), p1 = second ? bf_hi(xp[t]) : -bf_hi(xp[t]);
-      const float b0 = bf_round(p0 * bf_lo(sw_[t])), b1 = bf_round(p1 * bf_hi(sw_[t]));
-      yo[t] = bf_pack(a0 + b0, a1 + b1);
+      for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float mu = s * (1.f / 64.f);
+      const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
+      uint32_t xn[4], xp[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xn[t] = bf_pack((f[2 * t] - mu) * r * sc[2 * t], (f[2 * t + 1] - mu) * r * sc[2 * t + 1]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) xp[t] = __shfl_xor_sync(0xffffffffu, xn[t], 4);
+      const uint32_t cw[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w}, sw_[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+      uint32_t yo[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        // y = x*cos + rotate_half(x)*sin, rotate_half(x) = [-x2, x1]; every product is rounded to bf16 like the reference
+        const float a0 = bf_round(bf_lo(xn[t]) * bf_lo(cw[t])), a1 = bf_round(bf_hi(xn[t]) * bf_hi(cw[t]));
+        const float p0 = second ? bf_lo(xp[t]) : -bf_lo(xp[t]), p1 = second ? bf_hi(xp[t]) : -bf_hi(xp[t]);
+        const float b0 = bf_round(p0 * bf_lo(sw_[t])), b1 = bf_round(p1 * bf_hi(sw_[t]));
+        yo[t] = bf_pack(a0 + b0, a1 + b1);
+      }
+      *reinterpret_cast<uint4*>(out + row * out_ld + c * 8) = make_uint4(yo[0], yo[1], yo[2], yo[3]);
     }
-    *reinterpret_cast<uint4*>(out + row * out_ld + c * 8) = make_uint4(yo[0], yo[1], yo[2], yo[3]);
   }
 }
 
@@ -402,57 +430,73 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
 #pragma unroll
   for (int t = 0; t < 8; ++t) { sc[t] = __ldg(scp + t); ps[t] = 0.f; }
   const long long ld = 192LL * H;
-  for (long long row = (long long)blockIdx.x * rpi + threadIdx.x / cpr; row < rows; row += (long long)gridDim.x * rpi) {
-    const int pos = (int)((row / pos_div) % pos_mod);
-    const long long off = row * ld + c * 8;
-    const uint4 xv = *reinterpret_cast<const uint4*>(qkv + off);
-    const uint4 gv = *reinterpret_cast<const uint4*>(dqkv + off);
-    const uint4 cv = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
-    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
-    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
-    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
-    float f[8], d[8];
-    float s = 0.f, s2 = 0.f;
+  constexpr int UR = 2;                          // rows in flight per thread
+  const long long rstride = (long long)gridDim.x * rpi;
+  for (long long row0 = (long long)blockIdx.x * rpi + threadIdx.x / cpr; row0 < rows; row0 += UR * rstride) {
+    uint4 xv_[UR], gv_[UR], cv_[UR], sv_[UR];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]);
-      const uint32_t gp = __shfl_xor_sync(0xffffffffu, gw[t], 4);      // partner's upstream gradient
-      const uint32_t sp = __shfl_xor_sync(0xffffffffu, sw_[t], 4);     // partner's sin slice
-      // y1 = x1*c1 - x2*s1 ; y2 = x2*c2 + x1*s2  =>  dx1 = dy1*c1 + dy2*s2 ; dx2 = dy2*c2 - dy1*s1
-      const float q0 = bf_lo(gp) * bf_lo(sp), q1 = bf_hi(gp) * bf_hi(sp);
-      d[2 * t] = fmaf(bf_lo(gw[t]), bf_lo(cw[t]), second ? -q0 : q0);
-      d[2 * t + 1] = fmaf(bf_hi(gw[t]), bf_hi(cw[t]), second ? -q1 : q1);
+    for (int u = 0; u < UR; ++u) {
+      const long long row = row0 + u * rstride;
+      if (row < rows) {
+        const int pos = (int)((row / pos_div) % pos_mod);
+        const long long off = row * ld + c * 8;
+        xv_[u] = *reinterpret_cast<const uint4*>(qkv + off);
+        gv_[u] = *reinterpret_cast<const uint4*>(dqkv + off);
+        cv_[u] = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+        sv_[u] = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
+      }
     }
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
+    for (int u = 0; u < UR; ++u) {
+      const long long row = row0 + u * rstride;
+      if (row >= rows) break;
+      const long long off = row * ld + c * 8;
+      const uint4 xv = xv_[u], gv = gv_[u], cv = cv_[u], sv = sv_[u];
+      const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+      const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
+      float f[8], d[8];
+      float s = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      for (int t = 0; t < 4; ++t) {
+        f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]);
+        const uint32_t gp = __shfl_xor_sync(0xffffffffu, gw[t], 4);      // partner's upstream gradient
+        const uint32_t sp = __shfl_xor_sync(0xffffffffu, sw_[t], 4);     // partner's sin slice
+        // y1 = x1*c1 - x2*s1 ; y2 = x2*c2 + x1*s2  =>  dx1 = dy1*c1 + dy2*s2 ; dx2 = dy2*c2 - dy1*s1
+        const float q0 = bf_lo(gp) * bf_lo(sp), q1 = bf_hi(gp) * bf_hi(sp);
+        d[2 * t] = fmaf(bf_lo(gw[t]), bf_lo(cw[t]), second ? -q0 : q0);
+        d[2 * t + 1] = fmaf(bf_hi(gw[t]), bf_hi(cw[t]), second ? -q1 : q1);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float mu = s * (1.f / 64.f);
+      const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
+      float sg = 0.f, sgx = 0.f, xh[8], g[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        xh[t] = (f[t] - mu) * r;
+        g[t] = d[t] * sc[t];
+        sg += g[t];
+        sgx = fmaf(g[t], xh[t], sgx);
+        ps[t] = fmaf(d[t], xh[t], ps[t]);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+      }
+      sg *= (1.f / 64.f);
+      sgx *= (1.f / 64.f);
+      uint32_t o4[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        o4[t] = bf_pack(r * (g[2 * t] - sg - xh[2 * t] * sgx), r * (g[2 * t + 1] - sg - xh[2 * t + 1] * sgx));
+      *reinterpret_cast<uint4*>(dqkv + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
     }
-    const float mu = s * (1.f / 64.f);
-    const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
-    float sg = 0.f, sgx = 0.f, xh[8], g[8];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      xh[t] = (f[t] - mu) * r;
-      g[t] = d[t] * sc[t];
-      sg += g[t];
-      sgx = fmaf(g[t], xh[t], sgx);
-      ps[t] = fmaf(d[t], xh[t], ps[t]);
-    }
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
-    }
-    sg *= (1.f / 64.f);
-    sgx *= (1.f / 64.f);
-    uint32_t o4[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-      o4[t] = bf_pack(r * (g[2 * t] - sg - xh[2 * t] * sgx), r * (g[2 * t + 1] - sg - xh[2 * t + 1] * sgx));
-    *reinterpret_cast<uint4*>(dqkv + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
@@ -671,17 +715,26 @@ gn_apply_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long 
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
   const bf16* xb = x + (long long)b * S * C + ch * 8;
   bf16* yb = y + (long long)b * S * y_ld + ch * 8;
-  for (long long r = r0 + threadIdx.x / cpr; r < r1; r += rpi) {
-    float f[8];
-    gn_unpack(*reinterpret_cast<const uint4*>(xb + r * C), f);
-    float o[8];
+  constexpr int UR = 4;                          // voxels in flight per thread
+  for (long long rb = r0 + threadIdx.x / cpr; rb < r1; rb += UR * rpi) {
+    uint4 xv[UR];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float z = bf_round(fmaf(f[t], sc[t], sh[t]));
-      o[t] = z * gn_sigmoid(z);
+    for (int u = 0; u < UR; ++u)
+      if (rb + u * rpi < r1) xv[u] = *reinterpret_cast<const uint4*>(xb + (rb + u * rpi) * C);
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const long long r = rb + u * rpi;
+      if (r >= r1) break;
+      float f[8], o[8];
+      gn_unpack(xv[u], f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float z = bf_round(fmaf(f[t], sc[t], sh[t]));
+        o[t] = z * gn_sigmoid(z);
+      }
+      *reinterpret_cast<uint4*>(yb + r * y_ld) =
+          make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
     }
-    *reinterpret_cast<uint4*>(yb + r * y_ld) =
-        make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
   }
 }
 
@@ -708,21 +761,33 @@ gn_bwd_stats_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
   const bf16* xb = x + (long long)b * S * C + ch * 8;
   const bf16* dyb = dy + (long long)b * S * dy_ld + ch * 8;
-  for (long long r = r0 + threadIdx.x / cpr; r < r1; r += rpi) {
-    float f[8], d[8];
-    gn_unpack(*reinterpret_cast<const uint4*>(xb + r * C), f);
-    gn_unpack(*reinterpret_cast<const uint4*>(dyb + r * dy_ld), d);
+  constexpr int UR = 2;
+  for (long long rb = r0 + threadIdx.x / cpr; rb < r1; rb += UR * rpi) {
+    uint4 xv[UR], dv[UR];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float xh = (f[t] - mu[t]) * rs[t];
-      const float z = bf_round(fmaf(xh, ga[t], be[t]));
-      const float sg = gn_sigmoid(z);
-      const float dz = d[t] * sg * fmaf(z, 1.f - sg, 1.f);
-      const float gg = dz * ga[t];
-      s1[t] += gg;
-      s2[t] = fmaf(gg, xh, s2[t]);
-      dg[t] = fmaf(dz, xh, dg[t]);
-      db[t] += dz;
+    for (int u = 0; u < UR; ++u)
+      if (rb + u * rpi < r1) {
+        xv[u] = *reinterpret_cast<const uint4*>(xb + (rb + u * rpi) * C);
+        dv[u] = *reinterpret_cast<const uint4*>(dyb + (rb + u * rpi) * dy_ld);
+      }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      if (rb + u * rpi >= r1) break;
+      float f[8], d[8];
+      gn_unpack(xv[u], f);
+      gn_unpack(dv[u], d);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float xh = (f[t] - mu[t]) * rs[t];
+        const float z = bf_round(fmaf(xh, ga[t], be[t]));
+        const float sg = gn_sigmoid(z);
+        const float dz = d[t] * sg * fmaf(z, 1.f - sg, 1.f);
+        const float gg = dz * ga[t];
+        s1[t] += gg;
+        s2[t] = fmaf(gg, xh, s2[t]);
+        dg[t] = fmaf(dz, xh, dg[t]);
+        db[t] += dz;
+      }
     }
   }
   for (int o = cpr; o < 32; o <<= 1) {
@@ -771,20 +836,33 @@ gn_bwd_apply_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
   const bf16* xb = x + (long long)b * S * C + ch * 8;
   const bf16* dyb = dy + (long long)b * S * dy_ld + ch * 8;
   bf16* dxb = dx + (long long)b * S * C + ch * 8;
-  for (long long r = r0 + threadIdx.x / cpr; r < r1; r += rpi) {
-    float f[8], d[8], o[8];
-    gn_unpack(*reinterpret_cast<const uint4*>(xb + r * C), f);
-    gn_unpack(*reinterpret_cast<const uint4*>(dyb + r * dy_ld), d);
+  constexpr int UR = 2;
+  for (long long rb = r0 + threadIdx.x / cpr; rb < r1; rb += UR * rpi) {
+    uint4 xv[UR], dv[UR];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const float xh = (f[t] - mu[t]) * rs[t];
-      const float z = bf_round(fmaf(xh, ga[t], be[t]));
-      const float sg = gn_sigmoid(z);
-      const float gg = d[t] * sg * fmaf(z, 1.f - sg, 1.f) * ga[t];
-      o[t] = rs[t] * (gg - m1[t] - xh * m2[t]);
+    for (int u = 0; u < UR; ++u)
+      if (rb + u * rpi < r1) {
+        xv[u] = *reinterpret_cast<const uint4*>(xb + (rb + u * rpi) * C);
+        dv[u] = *reinterpret_cast<const uint4*>(dyb + (rb + u * rpi) * dy_ld);
+      }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const long long r = rb + u * rpi;
+      if (r >= r1) break;
+      float f[8], d[8], o[8];
+      gn_unpack(xv[u], f);
+      gn_unpack(dv[u], d);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float xh = (f[t] - mu[t]) * rs[t];
+        const float z = bf_round(fmaf(xh, ga[t], be[t]));
+        const float sg = gn_sigmoid(z);
+        const float gg = d[t] * sg * fmaf(z, 1.f - sg, 1.f) * ga[t];
+        o[t] = rs[t] * (gg - m1[t] - xh * m2[t]);
+      }
+      *reinterpret_cast<uint4*>(dxb + r * C) =
+          make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
     }
-    *reinterpret_cast<uint4*>(dxb + r * C) =
-        make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
   }
 }
 
@@ -799,14 +877,29 @@ static inline int gn_threads(int C) { return C * (256 / C > 0 ? 256 / C : 1); }
 
 using namespace vvae;
 
+// grid = exactly the blocks that are resident at once (persistent grid-stride kernels: no partial second wave)
+template <typename K>
+static int resident_grid(K kern, int threads, size_t smem, long long max_useful) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 2;
+  }
+  return (int)std::max<long long>(1, std::min<long long>(max_useful, 148LL * occ));
+}
+
+
 template <typename T>
 static int ln_fwd_dispatch(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
                            long long rows, int D, float eps, cudaStream_t s) {
   constexpr int V = Vec16<T>::N;
   const int need = (int)cdiv(D / V, 32);
-  const int blocks = (int)std::min<long long>(cdiv(rows, 8), 148LL * 8);
+  const size_t smem = 2 * (size_t)D * sizeof(float);
 #define LN_FWD(NC)                                                                                               \
-  layernorm_fwd_kernel<T, NC><<<blocks, 256, 0, s>>>((const T*)x, (T*)y, gamma, beta, mean, rstd, rows, D, eps)
+  do {                                                                                                           \
+    const int blocks = resident_grid(layernorm_fwd_kernel<T, NC>, 256, smem, cdiv(rows, 16));                    \
+    layernorm_fwd_kernel<T, NC><<<blocks, 256, smem, s>>>((const T*)x, (T*)y, gamma, beta, mean, rstd, rows, D, eps); \
+  } while (0)
   if (need <= 1) LN_FWD(1);
   else if (need <= 2) LN_FWD(2);
   else if (need <= 3) LN_FWD(3);
@@ -827,11 +920,13 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, con
                            cudaStream_t s) {
   constexpr int V = Vec16<T>::N;
   const int need = (int)cdiv(D / V, 32);
-  const int blocks = (int)std::min<long long>(cdiv(rows, 8), 148LL * 4);
-  const size_t smem = 2 * (size_t)D * sizeof(float);
+  const size_t smem = 3 * (size_t)D * sizeof(float);
 #define LN_BWD(NC)                                                                                              \
-  layernorm_bwd_kernel<T, NC><<<blocks, 256, smem, s>>>((const T*)dy, (const T*)x, mean, rstd, gamma, (const T*)dres, \
-                                                        (T*)dx, dgamma, dbeta, rows, D)
+  do {                                                                                                          \
+    const int blocks = resident_grid(layernorm_bwd_kernel<T, NC>, 256, smem, cdiv(rows, 8));                    \
+    layernorm_bwd_kernel<T, NC><<<blocks, 256, smem, s>>>((const T*)dy, (const T*)x, mean, rstd, gamma,         \
+                                                          (const T*)dres, (T*)dx, dgamma, dbeta, rows, D);      \
+  } while (0)
   if (need <= 1) LN_BWD(1);
   else if (need <= 2) LN_BWD(2);
   else if (need <= 3) LN_BWD(3);
@@ -888,7 +983,9 @@ int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, co
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_fwd: bad hd=%d", hd);
   if (qk_fast_ok(dtype, heads, hd, qkv, qk_out, cos_tab, sin_tab)) {
     const int rpi = 256 / (16 * heads);
-    const int blocks = (int)std::min<long long>(cdiv(rows, rpi), 148LL * 8);
+    static int occ_grid = 0;
+    if (!occ_grid) occ_grid = resident_grid(qknorm_rope_fwd_hd64_kernel, 256, 0, 1 << 30);
+    const int blocks = (int)std::min<long long>(cdiv(rows, rpi), occ_grid);
     qknorm_rope_fwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
         (const bf16*)qkv, (bf16*)qk_out, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, rows, heads, pos_div,
         pos_mod, eps);
@@ -911,7 +1008,9 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_bwd: bad hd=%d", hd);
   if (qk_fast_ok(dtype, heads, hd, qkv, dqkv, cos_tab, sin_tab)) {
     const int rpi = 256 / (16 * heads);
-    const int blocks = (int)std::min<long long>(cdiv(rows, rpi), 148LL * 4);
+    static int occ_grid = 0;
+    if (!occ_grid) occ_grid = resident_grid(qknorm_rope_bwd_hd64_kernel, 256, 0, 1 << 30);
+    const int blocks = (int)std::min<long long>(cdiv(rows, rpi), occ_grid);
     qknorm_rope_bwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
         (bf16*)dqkv, (const bf16*)qkv, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, dq_scale, dk_scale, rows,
         heads, pos_div, pos_mod, eps);
