@@ -62,8 +62,35 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   p.NT = std::min(cout_pad, 64);
   if (cout_pad % p.NT) return false;
   p.nNT = cout_pad / p.NT;
-  p.Ct = std::min(a.W, 128);
-  p.R = std::max(1, std::min(128 / p.Ct, a.H));
+  // Tile shape.  A tile of R rows x Ct columns is fetched with its halo ((R+kh-1) x (Ct+kw-1) pixels per temporal tap)
+  // and computed as nblk blocks of 128 positions of the flat padded plane, Mtot = R*Ct + (R-1)*(kw-1) <= 128*nblk.
+  // Short, wide tiles (R = 1) re-read every input row kh times; choose the (nblk, R, Ct) that minimises
+  // halo traffic + padded MMA work per useful output, including the ragged right / bottom edges of the image.
+  {
+    const int max_nblk = (a.kh == 7 ? 2 : 2);
+    double best = 1e30;
+    int bR = 0, bC = 0;
+    for (int nb = 1; nb <= max_nblk; ++nb) {
+      if (nb * p.NT > 256) break;
+      for (int R = 1; R <= std::min(a.H, 32); ++R) {
+        int cmax = (128 * nb - (R - 1) * (a.kw - 1)) / R;
+        cmax = std::min(cmax, std::min(a.W, 256 - (a.kw - 1)));
+        if (cmax < 1) break;
+        for (int C = cmax; C >= std::max(1, cmax - 24); --C) {
+          if (R + a.kh - 1 > 256) continue;
+          const double useful = (double)a.H * a.W;
+          const double tiles = (double)((a.H + R - 1) / R) * ((a.W + C - 1) / C);
+          const double traffic = tiles * (R + a.kh - 1) * (C + a.kw - 1) / useful;
+          const double mma = tiles * 128.0 * nb / useful;
+          const double cost = traffic + mma + 0.02 * nb;       // slight preference for the smaller accumulator
+          if (cost < best) { best = cost; bR = R; bC = C; }
+        }
+      }
+    }
+    if (!bR) return false;
+    p.R = bR;
+    p.Ct = bC;
+  }
   p.P = p.Ct + a.kw - 1;
   if (p.P > 256) return false;
   p.rows = p.R + a.kh - 1;
@@ -390,7 +417,8 @@ static ConvKernelFn pick_conv_kernel(const ConvPlan& p) {
   const int nks = p.CB / 16;
   if (p.kh == 3 && p.kw == 3) return nks == 1 ? pick_conv_kernel2<3, 3, 1>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<3, 3, 2>(p.nblk, p.NT) : nullptr;
   if (p.kh == 1 && p.kw == 1) return nks == 1 ? pick_conv_kernel2<1, 1, 1>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<1, 1, 2>(p.nblk, p.NT) : nullptr;
-  if (p.kh == 7 && p.kw == 7 && nks == 1 && p.nblk == 1 && p.NT == 16) return conv_sm100_kernel<7, 7, 1, 1, 16>;
+  if (p.kh == 7 && p.kw == 7 && nks == 1 && p.NT == 16)
+    return p.nblk == 1 ? conv_sm100_kernel<7, 7, 1, 1, 16> : (p.nblk == 2 ? conv_sm100_kernel<7, 7, 1, 2, 16> : nullptr);
   return nullptr;
 }
 
