@@ -168,12 +168,18 @@ int vvae_conv3d_wprep(const vvae_conv_args* args, int which, void* out, vvae_str
 
 /* ---- ConvTranspose k=s=(1,2,2) (nnx.ConvTranspose: train/unet.py:61-69) ----
  * x [V,Cin] voxels of a [B_T,H,W] grid; y [B_T,2H,2W,Cout] with channel stride y_ld;
- * w [1,2,2,Cin,Cout]; out[2i+a,2j+c] = x[i,j] . w[1-a,1-c] + bias. */
+ * w [1,2,2,Cin,Cout]; out[2i+a,2j+c] = x[i,j] . w[1-a,1-c] + bias.
+ * workspace: caller-provided scratch of vvae_convT122_workspace_bytes(...) bytes (256-byte aligned) for the
+ * tensor-core path (re-laid-out weights, the dense [V, 4*Cout] GEMM-side image of y / dy, fp32 weight-gradient
+ * staging); NULL / too small -> generic kernel. */
+long long vvae_convT122_workspace_bytes(int b_t, int H, int W, int Cin, int Cout);
 int vvae_convT122_fwd(const void* x, const void* w, const float* bias, void* y, long long y_ld,
-                      int b_t, int H, int W, int Cin, int Cout, int dtype, vvae_stream_t stream);
+                      int b_t, int H, int W, int Cin, int Cout, int dtype, void* workspace, long long workspace_bytes,
+                      vvae_stream_t stream);
 /* dx [V,Cin] from dy (stride dy_ld); dw_accum fp32 [1,2,2,Cin,Cout] += ; (bias grad: vvae_colsum on dy). */
 int vvae_convT122_bwd(const void* dy, long long dy_ld, const void* x, const void* w, void* dx, float* dw_accum,
-                      int b_t, int H, int W, int Cin, int Cout, int dtype, vvae_stream_t stream);
+                      int b_t, int H, int W, int Cin, int Cout, int dtype, void* workspace, long long workspace_bytes,
+                      vvae_stream_t stream);
 
 /* ---- GroupNorm + SiLU (nnx.GroupNorm eps 1e-6 + nnx.silu: train/unet.py:22-29) ----
  * x [B, S, C] (S = t*h*w voxels per sample), groups G, statistics per (sample, group).

@@ -96,8 +96,9 @@ _SIGS = {
     "vvae_conv3d_wgrad": ([C.POINTER(ConvArgs), vp], i32),
     "vvae_conv3d_wprep_bytes": ([C.POINTER(ConvArgs), i32], ll),
     "vvae_conv3d_wprep": ([C.POINTER(ConvArgs), i32, vp, vp], i32),
-    "vvae_convT122_fwd": ([vp, vp, vp, vp, ll, i32, i32, i32, i32, i32, i32, vp], i32),
-    "vvae_convT122_bwd": ([vp, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp], i32),
+    "vvae_convT122_workspace_bytes": ([i32, i32, i32, i32, i32], ll),
+    "vvae_convT122_fwd": ([vp, vp, vp, vp, ll, i32, i32, i32, i32, i32, i32, vp, ll, vp], i32),
+    "vvae_convT122_bwd": ([vp, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, ll, vp], i32),
     "vvae_groupnorm_silu_fwd": ([vp, vp, ll, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp], i32),
     "vvae_groupnorm_silu_bwd": ([vp, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, i32, vp], i32),
     "vvae_maxpool122_fwd": ([vp, ll, vp, i32, i32, i32, i32, i32, vp], i32),

@@ -162,6 +162,16 @@ int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long 
                        long long M, int K, int N, cudaStream_t s);
 }  // namespace vvae
 
+namespace vvae {
+long long convt_tc_workspace_bytes(int b_t, int H, int W, int Cin, int Cout);
+bool convt_tc_supported(int dtype, int b_t, int H, int W, int Cin, int Cout, const void* x, const void* y, long long y_ld,
+                        const void* ws, long long ws_bytes);
+int convt_tc_fwd(const void* x, const void* w, const float* bias, void* y, long long y_ld, int b_t, int H, int W, int Cin,
+                 int Cout, void* ws, cudaStream_t s);
+int convt_tc_bwd(const void* dy, long long dy_ld, const void* x, const void* w, void* dx, float* dw_accum, int b_t, int H,
+                 int W, int Cin, int Cout, void* ws, cudaStream_t s);
+}  // namespace vvae
+
 static int conv_run(const vvae_conv_args* a, int which, vvae_stream_t stream) {
   int rc = conv_validate(a, which);
   if (rc) return rc;
@@ -196,10 +206,16 @@ int vvae_conv3d_fwd(const vvae_conv_args* args, vvae_stream_t stream) { return c
 int vvae_conv3d_dgrad(const vvae_conv_args* args, vvae_stream_t stream) { return conv_run(args, 1, stream); }
 int vvae_conv3d_wgrad(const vvae_conv_args* args, vvae_stream_t stream) { return conv_run(args, 2, stream); }
 
+long long vvae_convT122_workspace_bytes(int b_t, int H, int W, int Cin, int Cout) {
+  return convt_tc_workspace_bytes(b_t, H, W, Cin, Cout);
+}
+
 int vvae_convT122_fwd(const void* x, const void* w, const float* bias, void* y, long long y_ld, int b_t, int H, int W,
-                      int Cin, int Cout, int dtype, vvae_stream_t stream) {
+                      int Cin, int Cout, int dtype, void* workspace, long long workspace_bytes, vvae_stream_t stream) {
   if (b_t <= 0) return VVAE_OK;
   VVAE_REQUIRE(x && w && y && y_ld >= Cout, "convT122_fwd: bad arguments");
+  if (convt_tc_supported(dtype, b_t, H, W, Cin, Cout, x, y, y_ld, workspace, workspace_bytes))
+    return convt_tc_fwd(x, w, bias, y, y_ld, b_t, H, W, Cin, Cout, workspace, as_stream(stream));
   const long long V = (long long)b_t * H * W;
   CTGeom g{H, W, Cin, Cout};
   VVAE_DISPATCH_DTYPE(dtype, T,
@@ -209,9 +225,13 @@ int vvae_convT122_fwd(const void* x, const void* w, const float* bias, void* y, 
 }
 
 int vvae_convT122_bwd(const void* dy, long long dy_ld, const void* x, const void* w, void* dx, float* dw_accum, int b_t,
-                      int H, int W, int Cin, int Cout, int dtype, vvae_stream_t stream) {
+                      int H, int W, int Cin, int Cout, int dtype, void* workspace, long long workspace_bytes,
+                      vvae_stream_t stream) {
   if (b_t <= 0) return VVAE_OK;
   VVAE_REQUIRE(dy && x && w && dy_ld >= Cout, "convT122_bwd: bad arguments");
+  if (convt_tc_supported(dtype, b_t, H, W, Cin, Cout, x, dy, dy_ld, workspace, workspace_bytes) &&
+      (!dx || ((uintptr_t)dx % 16 == 0)))
+    return convt_tc_bwd(dy, dy_ld, x, w, dx, dw_accum, b_t, H, W, Cin, Cout, workspace, as_stream(stream));
   const long long V = (long long)b_t * H * W;
   CTGeom g{H, W, Cin, Cout};
   cudaStream_t s = as_stream(stream);

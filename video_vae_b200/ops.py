@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _ffi
-from ._ffi import (BACKEND_AUTO, BF16, EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, F32, AttnArgs, ConvArgs, GemmArgs,
+from ._ffi import (BACKEND_AUTO, BACKEND_SIMT, BF16, EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, F32, AttnArgs, ConvArgs, GemmArgs,
                    check, dt, lib, ptr, stream)
 
 LN_EPS = 1e-6
@@ -278,18 +278,27 @@ def conv3d_wgrad_accum(x, dy, dw, ks, Cin, Cout, x_ld=None, dy_ld=None):
         check(lib.vvae_conv3d_wgrad(C.byref(a), stream()), "vvae_conv3d_wgrad")
 
 
+def _convt_workspace(b_t, H, W, Cin, Cout, device):
+    """Scratch for the tensor-core ConvTranspose path (re-laid-out weights, dense GEMM-side image of y / dy)."""
+    if CONV_BACKEND == BACKEND_SIMT:
+        return None                       # generic kernel requested (tests compare the two paths)
+    return torch.empty(int(lib.vvae_convT122_workspace_bytes(b_t, H, W, Cin, Cout)), dtype=torch.uint8, device=device)
+
+
 def convT122_fwd(x, w, bias, Cout, out, out_ld):
     """x [B,T,H,W,Cin] -> writes out[..., :Cout] of a [B,T,2H,2W,out_ld] buffer."""
     B, T, H, W, Cin = x.shape
-    check(lib.vvae_convT122_fwd(ptr(x), ptr(w), ptr(bias), ptr(out), out_ld, B * T, H, W, Cin, Cout, dt(x), stream()),
-          "vvae_convT122_fwd")
+    ws = _convt_workspace(B * T, H, W, Cin, Cout, x.device)
+    check(lib.vvae_convT122_fwd(ptr(x), ptr(w), ptr(bias), ptr(out), out_ld, B * T, H, W, Cin, Cout, dt(x), ptr(ws),
+                                ws.numel() if ws is not None else 0, stream()), "vvae_convT122_fwd")
 
 
 def convT122_bwd(dy, dy_ld, x, w, dw, Cout):
     B, T, H, W, Cin = x.shape
     dx = torch.empty_like(x)
-    check(lib.vvae_convT122_bwd(ptr(dy), dy_ld, ptr(x), ptr(w), ptr(dx), ptr(dw), B * T, H, W, Cin, Cout, dt(x),
-                                stream()), "vvae_convT122_bwd")
+    ws = _convt_workspace(B * T, H, W, Cin, Cout, x.device)
+    check(lib.vvae_convT122_bwd(ptr(dy), dy_ld, ptr(x), ptr(w), ptr(dx), ptr(dw), B * T, H, W, Cin, Cout, dt(x), ptr(ws),
+                                ws.numel() if ws is not None else 0, stream()), "vvae_convT122_bwd")
     return dx
 
 
