@@ -123,7 +123,7 @@ __device__ __forceinline__ AtcRow atc_row(const AttnTcPlan& p, long long tile, i
   return o;
 }
 
-template <int NK, bool PACKED>
+template <int NK, bool PACKED, bool MASKED>
 __global__ void __launch_bounds__(192, 2)
 attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, const AttnTcParams q) {
@@ -245,7 +245,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       for (int i = 0; i < 32; ++i) {
         const int c = c0 + i;
         const bool inseq = !PACKED || (unsigned)(c - seq_c0) < (unsigned)p.L;
-        const float s = kpen[c] != 0.f ? ATC_BIG_NEG : __uint_as_float(sr[i]) * q.scale;
+        float s = __uint_as_float(sr[i]) * q.scale;
+        if constexpr (MASKED) { if (kpen[c] != 0.f) s = ATC_BIG_NEG; }
         if (inseq) mx = fmaxf(mx, s);
       }
     }
@@ -270,7 +271,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       for (int i = 0; i < 32; ++i) {
         const int c = c0 + i;
         const bool inseq = !PACKED || (unsigned)(c - seq_c0) < (unsigned)p.L;
-        const float e = kpen[c] != 0.f ? (mx == ATC_BIG_NEG ? 1.f : 0.f) : atc_exp2(__uint_as_float(sr[i]) * k2 - mx2);
+        float e = atc_exp2(__uint_as_float(sr[i]) * k2 - mx2);
+        if constexpr (MASKED) { if (kpen[c] != 0.f) e = (mx == ATC_BIG_NEG ? 1.f : 0.f); }
         pv[i] = inseq ? e : 0.f;
         sum += pv[i];
       }
@@ -321,7 +323,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   }
 }
 
-template <int NK, bool PACKED>
+template <int NK, bool PACKED, bool MASKED>
 static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
   constexpr int P_BYTES = (NK / 64) * 16384, QK_BYTES = 16384 + NK * 128;
   constexpr int R0 = P_BYTES > QK_BYTES ? P_BYTES : QK_BYTES;
@@ -343,7 +345,7 @@ static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   q.o = (bf16*)a.o; q.o_rs = a.o_rs; q.lse = a.lse;
   q.mask = a.mask; q.mask_seq_div = a.mask_seq_div > 0 ? a.mask_seq_div : 1; q.ms_seq = a.ms_seq; q.ms_k = a.ms_k;
   q.scale = a.scale;
-  auto kern = attn_fwd_sm100_kernel<NK, PACKED>;
+  auto kern = attn_fwd_sm100_kernel<NK, PACKED, MASKED>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -392,7 +394,7 @@ __device__ __forceinline__ uint32_t atc_pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-template <int NB, bool PACKED>
+template <int NB, bool PACKED, bool MASKED>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                       const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
@@ -537,30 +539,41 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const float k2 = q.scale * 1.4426950408889634f;
     const float inv_l = 1.f / (float)p.L;
 
-    // per query block: row validity, LSE (in log2 units), D = rowsum(dO o O)
+    // per query block: row validity, LSE (in log2 units), D = rowsum(dO o O).  The O rows come straight from global
+    // memory: their loads are issued before the wait for the TMA tiles so both latencies overlap.
     float lse2[NB], dlt[NB];
     bool rok[NB], allm[NB];
+    uint4 ov[NB][8];
+    float lraw[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const AtcRow row = atc_bwd_row<PACKED>(p, tile, i, r);
       rok[i] = row.ok;
-      float l = 0.f, d = 0.f;
-      sm100::mbar_wait(&ld_bar[i], 0);
+      lraw[i] = 0.f;
       if (row.ok) {
-        l = q.lse[(row.seq * p.heads + h) * p.L + row.l];
-        const bf16* orow = q.o + row.tok * q.o_rs + (long long)h * 64;
+        lraw[i] = q.lse[(row.seq * p.heads + h) * p.L + row.l];
+        const uint4* orow = reinterpret_cast<const uint4*>(q.o + row.tok * q.o_rs + (long long)h * 64);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) ov[i][ch] = orow[ch];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      float d = 0.f;
+      sm100::mbar_wait(&ld_bar[i], 0);
+      if (rok[i]) {
         const uint8_t* drow = sdO + i * BLK + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           Vec16<bf16> a, b;
-          a.load(orow + 8 * ch);
+          a.raw = ov[i][ch];
           b.raw = *reinterpret_cast<const uint4*>(drow + (((uint32_t)ch ^ sw) << 4));
 #pragma unroll
           for (int e = 0; e < 8; ++e) d = fmaf(a.get(e), b.get(e), d);
         }
       }
-      allm[i] = l <= 0.5f * ATC_BIG_NEG;
-      lse2[i] = l * 1.4426950408889634f;
+      allm[i] = lraw[i] <= 0.5f * ATC_BIG_NEG;
+      lse2[i] = lraw[i] * 1.4426950408889634f;
       dlt[i] = d;
     }
 
@@ -588,11 +601,17 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int c = c0 + e + u;
-            const bool inseq = my_ok && (!PACKED || (unsigned)(c - seq_c0) < (unsigned)p.L);
-            const bool masked = kpen[j * 128 + c] != 0.f;
             float pr = atc_exp2(__uint_as_float(sr[e + u]) * k2 - my_lse2);
-            if (masked) pr = my_allm ? inv_l : 0.f;
-            if (!inseq) pr = 0.f;
+            bool masked = false;
+            if constexpr (MASKED) {
+              masked = kpen[j * 128 + c] != 0.f;
+              if (masked) pr = my_allm ? inv_l : 0.f;
+            }
+            if constexpr (PACKED) {
+              if (!(my_ok && (unsigned)(c - seq_c0) < (unsigned)p.L)) pr = 0.f;
+            } else {
+              if (!my_ok) pr = 0.f;
+            }
             pv[u] = pr;
             dv[u] = masked ? 0.f : pr * (__uint_as_float(dr[e + u]) - my_d) * q.scale;
           }
@@ -671,7 +690,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   }
 }
 
-template <int NB, bool PACKED>
+template <int NB, bool PACKED, bool MASKED>
 static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
   constexpr int SMEM = (4 * NB + 4) * 16384 + 64 + NB * 128 * 4 + 1024;
   CUtensorMap mq, mk, mv, md;
@@ -689,7 +708,7 @@ static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   q.dq = (bf16*)a.dq; q.dk = (bf16*)a.dk; q.dv = (bf16*)a.dv;
   q.dq_rs = a.dq_rs; q.dk_rs = a.dk_rs; q.dv_rs = a.dv_rs;
   q.scale = a.scale;
-  auto kern = attn_bwd_sm100_kernel<NB, PACKED>;
+  auto kern = attn_bwd_sm100_kernel<NB, PACKED, MASKED>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
@@ -727,9 +746,10 @@ int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s) {
     set_error("attention: shape not supported by the tensor-core path");
     return VVAE_ERR_UNSUPPORTED;
   }
-  if (p.G > 1) return atc_launch_fwd<128, true>(a, p, s);
-  if (p.NK == 128) return atc_launch_fwd<128, false>(a, p, s);
-  return atc_launch_fwd<256, false>(a, p, s);
+  const bool m = a.mask != nullptr;
+  if (p.G > 1) return m ? atc_launch_fwd<128, true, true>(a, p, s) : atc_launch_fwd<128, true, false>(a, p, s);
+  if (p.NK == 128) return m ? atc_launch_fwd<128, false, true>(a, p, s) : atc_launch_fwd<128, false, false>(a, p, s);
+  return m ? atc_launch_fwd<256, false, true>(a, p, s) : atc_launch_fwd<256, false, false>(a, p, s);
 }
 
 int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s) {
@@ -738,9 +758,10 @@ int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s) {
     set_error("attention bwd: shape not supported by the tensor-core path");
     return VVAE_ERR_UNSUPPORTED;
   }
-  if (p.G > 1) return atc_launch_bwd<1, true>(a, p, s);
-  if (p.NK == 128) return atc_launch_bwd<1, false>(a, p, s);
-  return atc_launch_bwd<2, false>(a, p, s);
+  const bool m = a.mask != nullptr;
+  if (p.G > 1) return m ? atc_launch_bwd<1, true, true>(a, p, s) : atc_launch_bwd<1, true, false>(a, p, s);
+  if (p.NK == 128) return m ? atc_launch_bwd<1, false, true>(a, p, s) : atc_launch_bwd<1, false, false>(a, p, s);
+  return m ? atc_launch_bwd<2, false, true>(a, p, s) : atc_launch_bwd<2, false, false>(a, p, s);
 }
 
 }  // namespace vvae
