@@ -96,9 +96,12 @@ int vvae_layernorm_bwd(const void* dy, const void* x, const float* mean, const f
 int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, const float* k_scale,
                          const void* cos_tab, const void* sin_tab, long long rows, int heads, int hd,
                          long long pos_div, int pos_mod, float eps, int dtype, vvae_stream_t stream);
-/* dqkv: [rows, 3*H*hd]; on entry its q|k part holds d(rotated q|k), on exit d(raw q|k); v part untouched. */
+/* dqkv: [rows, 3*H*hd]; on entry its q|k part holds d(rotated q|k), on exit d(raw q|k); v part untouched.
+ * dbias_qk_accum (optional, fp32 [2*H*hd]) += column sums of the produced d(raw q|k): the q|k part of the QKV
+ * projection's bias gradient, accumulated while the gradient is in registers. */
 int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, const float* k_scale,
                          const void* cos_tab, const void* sin_tab, float* dq_scale_accum, float* dk_scale_accum,
+                         float* dbias_qk_accum,
                          long long rows, int heads, int hd, long long pos_div, int pos_mod, float eps, int dtype,
                          vvae_stream_t stream);
 

@@ -86,7 +86,7 @@ _SIGS = {
     "vvae_layernorm_fwd": ([vp, vp, vp, vp, vp, vp, ll, i32, f32, i32, vp], i32),
     "vvae_layernorm_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, vp], i32),
     "vvae_qknorm_rope_fwd": ([vp, vp, vp, vp, vp, vp, ll, i32, i32, ll, i32, f32, i32, vp], i32),
-    "vvae_qknorm_rope_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, ll, i32, f32, i32, vp], i32),
+    "vvae_qknorm_rope_bwd": ([vp, vp, vp, vp, vp, vp, vp, vp, vp, ll, i32, i32, ll, i32, f32, i32, vp], i32),
     "vvae_attn_fwd": ([C.POINTER(AttnArgs), vp], i32),
     "vvae_attn_bwd": ([C.POINTER(AttnArgs), vp], i32),
     "vvae_patchify": ([vp, i32, vp, i32, i32, i32, i32, i32, i32, vp], i32),

@@ -101,14 +101,14 @@ colsum_bf16_vec_kernel(const bf16* __restrict__ x, long long ld, long long rows,
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
   if (col < n) {
     long long r = r0 + w;
-    for (; r + 24 < r1; r += 32) {
-      Vec16<bf16> v0, v1, v2, v3;
-      v0.load(x + r * ld + col);
-      v1.load(x + (r + 8) * ld + col);
-      v2.load(x + (r + 16) * ld + col);
-      v3.load(x + (r + 24) * ld + col);
+    for (; r + 56 < r1; r += 64) {              // 8 independent 16-byte loads in flight per thread
+      Vec16<bf16> v[8];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) acc[t] += (v0.get(t) + v1.get(t)) + (v2.get(t) + v3.get(t));
+      for (int u = 0; u < 8; ++u) v[u].load(x + (r + 8 * u) * ld + col);
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        acc[t] += ((v[0].get(t) + v[1].get(t)) + (v[2].get(t) + v[3].get(t))) +
+                  ((v[4].get(t) + v[5].get(t)) + (v[6].get(t) + v[7].get(t)));
     }
     for (; r < r1; r += 8) {
       Vec16<bf16> v0;
@@ -181,8 +181,8 @@ int vvae_colsum(const void* x, long long ld, long long rows, int n, float* out, 
   VVAE_REQUIRE(x && out, "vvae_colsum: null pointer");
   if (dtype == VVAE_BF16 && n % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
     const int cb = (int)cdiv(n, 256);
-    const long long want = cdiv(148 * 4, cb);
-    const long long rpb = std::max<long long>(64, cdiv(rows, want));
+    const long long want = cdiv(148 * 3, cb);
+    const long long rpb = std::max<long long>(128, (cdiv(rows, want) + 63) / 64 * 64);   // whole 64-row unrolled steps
     dim3 grid(cb, (unsigned)cdiv(rows, rpb));
     colsum_bf16_vec_kernel<<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, ld, rows, n, out, (int)rpb);
     return check_launch("colsum");

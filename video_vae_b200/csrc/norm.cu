@@ -418,17 +418,18 @@ __global__ void __launch_bounds__(256)
 qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv, const float* __restrict__ q_scale,
                             const float* __restrict__ k_scale, const bf16* __restrict__ cos_tab,
                             const bf16* __restrict__ sin_tab, float* __restrict__ dq_scale, float* __restrict__ dk_scale,
-                            long long rows, int H, long long pos_div, int pos_mod, float eps) {
+                            float* __restrict__ dbias, long long rows, int H, long long pos_div, int pos_mod, float eps) {
   __shared__ float red[2][64];
+  __shared__ float redb[2048];                   // column sums of the produced d(q|k) (the QKV bias gradient), [16*H*8]
   const int cpr = 16 * H;
   const int c = threadIdx.x % cpr, rpi = blockDim.x / cpr;
   const int part = c & 7;
   const bool second = part >= 4;
   const int which = c >= 8 * H ? 1 : 0;
   const float* scp = (which ? k_scale : q_scale) + part * 8;
-  float sc[8], ps[8];
+  float sc[8], ps[8], pb[8];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) { sc[t] = __ldg(scp + t); ps[t] = 0.f; }
+  for (int t = 0; t < 8; ++t) { sc[t] = __ldg(scp + t); ps[t] = 0.f; pb[t] = 0.f; }
   const long long ld = 192LL * H;
   constexpr int UR = 2;                          // rows in flight per thread
   const long long rstride = (long long)gridDim.x * rpi;
@@ -493,10 +494,21 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
       sgx *= (1.f / 64.f);
       uint32_t o4[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
+      for (int t = 0; t < 4; ++t) {
         o4[t] = bf_pack(r * (g[2 * t] - sg - xh[2 * t] * sgx), r * (g[2 * t + 1] - sg - xh[2 * t + 1] * sgx));
+        pb[2 * t] += bf_lo(o4[t]);               // sum of the ROUNDED outputs, as a separate column-sum pass would see them
+        pb[2 * t + 1] += bf_hi(o4[t]);
+      }
       *reinterpret_cast<uint4*>(dqkv + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
     }
+  }
+  if (dbias) {
+    for (int i = threadIdx.x; i < cpr * 8; i += blockDim.x) redb[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 8; ++t) atomicAdd(&redb[c * 8 + t], pb[t]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cpr * 8; i += blockDim.x) atomicAdd(dbias + i, redb[i]);
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) (&red[0][0])[i] = 0.f;
   __syncthreads();
@@ -1000,8 +1012,8 @@ int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, co
 }
 
 int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, const float* k_scale,
-                         const void* cos_tab, const void* sin_tab, float* dq_scale, float* dk_scale, long long rows,
-                         int heads, int hd, long long pos_div, int pos_mod, float eps, int dtype,
+                         const void* cos_tab, const void* sin_tab, float* dq_scale, float* dk_scale, float* dbias_qk,
+                         long long rows, int heads, int hd, long long pos_div, int pos_mod, float eps, int dtype,
                          vvae_stream_t stream) {
   if (rows <= 0) return VVAE_OK;
   VVAE_REQUIRE(dqkv && qkv && q_scale && k_scale && cos_tab && sin_tab, "qknorm_rope_bwd: null pointer");
@@ -1012,8 +1024,8 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
     if (!occ_grid) occ_grid = resident_grid(qknorm_rope_bwd_hd64_kernel, 256, 0, 1 << 30);
     const int blocks = (int)std::min<long long>(cdiv(rows, rpi), occ_grid);
     qknorm_rope_bwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
-        (bf16*)dqkv, (const bf16*)qkv, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, dq_scale, dk_scale, rows,
-        heads, pos_div, pos_mod, eps);
+        (bf16*)dqkv, (const bf16*)qkv, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, dq_scale, dk_scale,
+        dbias_qk, rows, heads, pos_div, pos_mod, eps);
     return check_launch("qknorm_rope_bwd");
   }
   const long long nvec = rows * 2 * heads;
@@ -1021,7 +1033,10 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
   VVAE_DISPATCH_DTYPE(dtype, T, (qknorm_rope_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(
                                     (T*)dqkv, (const T*)qkv, q_scale, k_scale, (const T*)cos_tab, (const T*)sin_tab, dq_scale,
                                     dk_scale, rows, heads, hd, pos_div, pos_mod, eps)));
-  return check_launch("qknorm_rope_bwd");
+  int rc = check_launch("qknorm_rope_bwd");
+  if (rc || !dbias_qk) return rc;
+  // generic path: the bias gradient of the q|k columns is a separate column-sum pass over the produced gradient
+  return vvae_colsum(dqkv, 3LL * heads * hd, rows, 2 * heads * hd, dbias_qk, dtype, stream);
 }
 
 int vvae_groupnorm_silu_fwd(const void* x, void* y, long long y_ld, const float* gamma, const float* beta, float* mean,

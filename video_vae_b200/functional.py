@@ -203,19 +203,21 @@ class AttnBlockFn(Function):
         D = x2.shape[1]
         Q = cfg.heads * cfg.hd
         dy2 = _as_2d(dy, D)
-        # out projection
-        ops.gemm(o, dy2, transA=True, out=grad_buf(w_o), accumulate=True)
+        # out projection (the bias gradient first: dy was just written by the previous backward kernel)
         ops.colsum_accum(dy2, grad_buf(b_o))
+        ops.gemm(o, dy2, transA=True, out=grad_buf(w_o), accumulate=True)
         d_o = ops.gemm(dy2, shadow(w_o, dtp), transB=True)
         # attention core -> dq | dk | dv written side by side
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(cfg.geom, cfg.heads, cfg.hd, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], o, lse, d_o, dqkv[:, :Q],
                      dqkv[:, Q:2 * Q], dqkv[:, 2 * Q:], cfg.mask, cfg.scale)
+        # QK-norm + RoPE backward also accumulates the q|k part of the QKV bias gradient; the v part is a column sum
+        gb = grad_buf(b_qkv)
+        ops.colsum_accum(dqkv[:, 2 * Q:], gb[2 * Q:])
         ops.qknorm_rope_bwd_(dqkv, qkv, q_scale.detach(), k_scale.detach(), cos, sin, grad_buf(q_scale),
-                             grad_buf(k_scale), cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod)
+                             grad_buf(k_scale), cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod, dbias_qk=gb[:2 * Q])
         # qkv projection
         ops.gemm(h, dqkv, transA=True, out=grad_buf(w_qkv), accumulate=True)
-        ops.colsum_accum(dqkv, grad_buf(b_qkv))
         dh = ops.gemm(dqkv, shadow(w_qkv, dtp), transB=True)
         dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if cfg.residual else None, grad_buf(ln_g),
                                grad_buf(ln_b), out=dh)
@@ -250,11 +252,11 @@ class MlpBlockFn(Function):
         x2, mean, rstd, h, u, a, ln_g, ln_b, w1, b1, w2, b2 = ctx.saved_tensors
         dtp = ctx.dtype
         dy2 = _as_2d(dy, x2.shape[1])
-        ops.gemm(a, dy2, transA=True, out=grad_buf(w2), accumulate=True)
         ops.colsum_accum(dy2, grad_buf(b2))
+        ops.gemm(a, dy2, transA=True, out=grad_buf(w2), accumulate=True)
         du = ops.gemm(dy2, shadow(w2, dtp), transB=True, epilogue=EPI_DSILU, aux_in=u)
-        ops.gemm(h, du, transA=True, out=grad_buf(w1), accumulate=True)
         ops.colsum_accum(du, grad_buf(b1))
+        ops.gemm(h, du, transA=True, out=grad_buf(w1), accumulate=True)
         dh = ops.gemm(du, shadow(w1, dtp), transB=True)
         dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if ctx.residual else None, grad_buf(ln_g),
                                grad_buf(ln_b), out=dh)

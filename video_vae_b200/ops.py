@@ -128,10 +128,11 @@ def qknorm_rope_fwd(qkv, q_scale, k_scale, cos, sin, heads, hd, pos_div, pos_mod
     return out
 
 
-def qknorm_rope_bwd_(dqkv, qkv, q_scale, k_scale, cos, sin, dq_scale, dk_scale, heads, hd, pos_div, pos_mod):
+def qknorm_rope_bwd_(dqkv, qkv, q_scale, k_scale, cos, sin, dq_scale, dk_scale, heads, hd, pos_div, pos_mod, dbias_qk=None):
+    """In place on the q|k part of dqkv.  dbias_qk (fp32 [2*heads*hd], optional) += column sums of the result."""
     rows = qkv.shape[0]
     check(lib.vvae_qknorm_rope_bwd(ptr(dqkv), ptr(qkv), ptr(q_scale), ptr(k_scale), ptr(cos), ptr(sin), ptr(dq_scale),
-                                   ptr(dk_scale), rows, heads, hd, pos_div, pos_mod, LN_EPS, dt(qkv), stream()),
+                                   ptr(dk_scale), ptr(dbias_qk), rows, heads, hd, pos_div, pos_mod, LN_EPS, dt(qkv), stream()),
           "vvae_qknorm_rope_bwd")
     return dqkv
 
