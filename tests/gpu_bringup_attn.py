@@ -84,6 +84,9 @@ CASES = [
     ("temporal_L32_hw8_masked", 3, 32, 8, True, True),
     ("temporal_L64_hw4", 1, 64, 4, True, True),
     ("temporal_allmasked_row", 2, 16, 16, True, True),
+    ("long_L384", 1, 2, 384, False, False),
+    ("long_L512_masked", 1, 3, 512, False, True),
+    ("long_L1024", 1, 1, 1024, False, False),
 ]
 
 if __name__ == "__main__":
@@ -99,7 +102,8 @@ if __name__ == "__main__":
                 r = {"name": c[0], "error": repr(e)[:300]}
             print(json.dumps(r), flush=True)
             f.write(json.dumps(r) + "\n")
-        for c in [("prod_spatial", 8, 16, 256, False, False), ("prod_temporal", 8, 16, 256, True, True)]:
+        for c in [("prod_spatial", 8, 16, 256, False, False), ("prod_temporal", 8, 16, 256, True, True),
+                  ("prod_cfg5_spatial", 1, 64, 1024, False, False)]:
             if sel and c[0] not in sel:
                 continue
             try:

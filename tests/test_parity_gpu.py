@@ -404,11 +404,13 @@ def _attention_reference(qk, qkv, d_o, geom, temporal, b, t, hw, H, HD, mask_bl)
     ("temporal_L32_masked", 3, 32, 8, True, True),
     ("temporal_L64", 1, 64, 4, True, True),
     ("temporal_allmasked_clip", 2, 16, 16, True, True),
+    ("spatial_long_L384_masked", 1, 2, 384, False, True),
+    ("spatial_long_L512", 1, 1, 512, False, False),
 ])
 def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked):
     """bf16, head_dim 64: the tensor-core attention (forward AND backward) against oracle autograd on identical data.
-    Covers 128/256-row tiles, block-diagonal packing of short sequences, ragged tails, key-padding masks and a fully
-    masked clip (uniform attention, no gradient to q/k)."""
+    Covers 128/256-row tiles, block-diagonal packing of short sequences, ragged tails, key-padding masks, a fully
+    masked clip (uniform attention, no gradient to q/k) and the streaming long-sequence kernels (L > 256)."""
     from video_vae_b200 import _ffi, ops
     from video_vae_b200.ops import AttnGeom, AttnMask
     H, HD = 8, 64

@@ -41,8 +41,9 @@ struct AttnTcParams {
   float scale;
 };
 
+__host__ __device__ inline bool atc_len_long(int L) { return L > 256 && L % 128 == 0 && L <= 8192; }
 __host__ __device__ inline bool atc_len_ok(int L) {
-  return L == 8 || L == 16 || L == 32 || L == 64 || L == 128 || L == 256;
+  return L == 8 || L == 16 || L == 32 || L == 64 || L == 128 || L == 256 || atc_len_long(L);
 }
 
 static bool atc_make_plan(const vvae_attn_args& a, AttnTcPlan& p) {
@@ -724,6 +725,582 @@ static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   return check_launch("attn_bwd_sm100");
 }
 
+
+// ====================================================================================================== long sequences
+// L = 128*NB > 256 (spatial attention at 512x512: L = 1024).  The whole sequence no longer fits one CTA's TMEM, so:
+//   forward : one CTA per (sequence, 128-query block, head) streams the key blocks twice -- pass 1 finds the row maxima
+//             (S = Q.K_j^T only), pass 2 recomputes S, forms P = exp(S - max) and accumulates O += P.V_j in TMEM without
+//             any rescaling; S and P are double buffered so the tensor core runs one block ahead of the softmax warps.
+//   backward: two streaming kernels built from one template.  dK/dV: a CTA owns a key block and streams the query
+//             blocks (dK_j, dV_j stay in TMEM); dQ: a CTA owns a query block and streams the key blocks (dQ_i stays in
+//             TMEM).  S and dP are recomputed in both (2 extra small MMAs per tile) instead of reducing dQ across CTAs
+//             with atomics.  D = rowsum(dO o O) comes from a tiny pre-pass (attn_delta_kernel).
+struct AttnLongParams {
+  AttnTcPlan pl;
+  bf16* o; long long o_rs;
+  float* lse;
+  const float* delta;
+  const unsigned char* mask; long long mask_seq_div, ms_seq, ms_k;
+  bf16 *dq, *dk, *dv; long long dq_rs, dk_rs, dv_rs;
+  float scale;
+};
+
+__device__ __forceinline__ long long atl_tok(const AttnTcPlan& p, long long seq, int l) {
+  return (seq / p.n_inner) * p.ts_o + (seq % p.n_inner) * p.ts_i + (long long)l * p.ts_l;
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_long_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                           const __grid_constant__ CUtensorMap tma_v, const AttnLongParams q) {
+  const AttnTcPlan& p = q.pl;
+  constexpr int BLK = 16384, KS = 3, VS = 2;
+  const int NKB = p.nqb;                               // key blocks of 128 (= query blocks: L = 128*nqb)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + BLK;               // [KS]
+  uint8_t* sV = sK + KS * BLK;          // [VS]
+  uint8_t* sP = sV + VS * BLK;          // [2][2 key halves][128 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * BLK);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;          // [3]
+  uint64_t* k_empty = bars + 4;         // [3]
+  uint64_t* v_full = bars + 7;          // [2]
+  uint64_t* v_empty = bars + 9;         // [2]
+  uint64_t* s_full = bars + 11;         // [2]
+  uint64_t* s_empty = bars + 13;        // [2]
+  uint64_t* p_full = bars + 15;         // [2]
+  uint64_t* p_empty = bars + 17;        // [2]
+  uint64_t* o_full = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* kpen = reinterpret_cast<float*>(bars + 21);   // [L]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long seq = blockIdx.x / p.nqb;
+  const int qb = (int)(blockIdx.x % p.nqb);
+  const int h = blockIdx.y;
+  const int c2 = (int)(seq % p.n_inner), c3 = (int)(seq / p.n_inner);
+
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_q);
+    sm100::tma_prefetch_desc(&tma_k);
+    sm100::tma_prefetch_desc(&tma_v);
+    sm100::mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) { sm100::mbar_init(&k_full[i], 1); sm100::mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      sm100::mbar_init(&v_full[i], 1); sm100::mbar_init(&v_empty[i], 1);
+      sm100::mbar_init(&s_full[i], 1); sm100::mbar_init(&s_empty[i], 4);
+      sm100::mbar_init(&p_full[i], 4); sm100::mbar_init(&p_empty[i], 1);
+    }
+    sm100::mbar_init(o_full, 1);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_O = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      sm100::mbar_expect_tx(q_full, BLK);
+      tma_load_4d(sQ, &tma_q, q_full, h * 64, qb * 128, c2, c3);
+      for (int s = 0; s < 2 * NKB; ++s) {
+        const int j = s % NKB, slot = s % KS;
+        sm100::mbar_wait(&k_empty[slot], ((s / KS) & 1) ^ 1);
+        sm100::mbar_expect_tx(&k_full[slot], BLK);
+        tma_load_4d(sK + slot * BLK, &tma_k, &k_full[slot], h * 64, j * 128, c2, c3);
+        if (s >= NKB) {
+          const int vs = j & 1;
+          sm100::mbar_wait(&v_empty[vs], ((j >> 1) & 1) ^ 1);
+          sm100::mbar_expect_tx(&v_full[vs], BLK);
+          tma_load_4d(sV + vs * BLK, &tma_v, &v_full[vs], h * 64, j * 128, c2, c3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = sm100::make_idesc_bf16(128, 64, false, true);
+      const uint32_t qa = sm100::smem_u32(sQ);
+      auto issue_s = [&](int s) {
+        const int slot = s % KS, b = s & 1;
+        sm100::mbar_wait(&k_full[slot], (s / KS) & 1);
+        if (s >= 2) sm100::mbar_wait(&s_empty[b], ((s >> 1) - 1) & 1);
+        sm100::tc_fence_after();
+        const uint32_t ka = sm100::smem_u32(sK + slot * BLK);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + b * 128, sm100::make_smem_desc_sw128(qa + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        sm100::umma_commit(&k_empty[slot]);
+        sm100::umma_commit(&s_full[b]);
+      };
+      sm100::mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int s = 0; s < 2 * NKB; ++s) {
+        if (s + 1 < 2 * NKB) issue_s(s + 1);
+        if (s >= NKB) {
+          const int j = s - NKB, pb = j & 1;
+          sm100::mbar_wait(&v_full[pb], (j >> 1) & 1);
+          sm100::mbar_wait(&p_full[pb], (j >> 1) & 1);
+          sm100::tc_fence_after();
+          const uint32_t pa = sm100::smem_u32(sP + pb * 2 * BLK), va = sm100::smem_u32(sV + pb * BLK);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            sm100::umma_f16(tmem_base + COL_O, sm100::make_smem_desc_sw128(pa + (k >> 2) * BLK + (k & 3) * 32, 16, 1024),
+                            sm100::make_smem_desc_sw128(va + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+          sm100::umma_commit(&v_empty[pb]);
+          sm100::umma_commit(&p_empty[pb]);
+        }
+      }
+      sm100::umma_commit(o_full);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    if (MASKED) {
+      for (int c = tid; c < p.L; c += 128)
+        kpen[c] = q.mask[(seq / q.mask_seq_div) * q.ms_seq + (long long)c * q.ms_k] == 0 ? 1.f : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    const float k2 = q.scale * 1.4426950408889634f;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sw = (uint32_t)(r & 7);
+    // pass 1: row maximum
+    float mx = -INFINITY;
+    for (int s = 0; s < NKB; ++s) {
+      const int b = s & 1;
+      sm100::mbar_wait(&s_full[b], (s >> 1) & 1);
+      sm100::tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t sr[32];
+        sm100::tmem_ld_32x32(trow + b * 128 + c0, sr);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(sr[i]) * q.scale;
+          if constexpr (MASKED) { if (kpen[s * 128 + c0 + i] != 0.f) v = ATC_BIG_NEG; }
+          mx = fmaxf(mx, v);
+        }
+      }
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&s_empty[b]);
+    }
+    // pass 2: P = exp(S - max) (bf16, swizzled K-major operand tile), row sums
+    const float mx2 = mx * 1.4426950408889634f;
+    float sum = 0.f;
+    for (int j = 0; j < NKB; ++j) {
+      const int s = NKB + j, b = s & 1, pb = j & 1;
+      sm100::mbar_wait(&s_full[b], (s >> 1) & 1);
+      if (j >= 2) sm100::mbar_wait(&p_empty[pb], ((j >> 1) - 1) & 1);
+      sm100::tc_fence_after();
+      uint8_t* prow = sP + pb * 2 * BLK + r * 128;
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t sr[32];
+        sm100::tmem_ld_32x32(trow + b * 128 + c0, sr);
+        sm100::tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = atc_exp2(__uint_as_float(sr[i]) * k2 - mx2);
+          if constexpr (MASKED) { if (kpen[j * 128 + c0 + i] != 0.f) e = (mx == ATC_BIG_NEG ? 1.f : 0.f); }
+          pv[i] = e;
+          sum += e;
+        }
+        uint8_t* pblk = prow + (c0 >> 6) * BLK;
+        const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4)
+          *reinterpret_cast<uint4*>(pblk + (((ch0 + v4) ^ sw) << 4)) =
+              make_uint4(atc_pack2(pv[8 * v4], pv[8 * v4 + 1]), atc_pack2(pv[8 * v4 + 2], pv[8 * v4 + 3]),
+                         atc_pack2(pv[8 * v4 + 4], pv[8 * v4 + 5]), atc_pack2(pv[8 * v4 + 6], pv[8 * v4 + 7]));
+      }
+      sm100::fence_proxy_async();
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { sm100::mbar_arrive(&s_empty[b]); sm100::mbar_arrive(&p_full[pb]); }
+    }
+    sm100::mbar_wait(o_full, 0);
+    sm100::tc_fence_after();
+    const float inv = 1.f / sum;
+    const int l = qb * 128 + r;
+    bf16* orow = q.o + atl_tok(p, seq, l) * q.o_rs + (long long)h * 64;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t orr[32];
+      sm100::tmem_ld_32x32(trow + COL_O + c0, orr);
+      sm100::tmem_ld_wait();
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        *reinterpret_cast<uint4*>(orow + c0 + 8 * v4) =
+            make_uint4(atc_pack2(__uint_as_float(orr[8 * v4]) * inv, __uint_as_float(orr[8 * v4 + 1]) * inv),
+                       atc_pack2(__uint_as_float(orr[8 * v4 + 2]) * inv, __uint_as_float(orr[8 * v4 + 3]) * inv),
+                       atc_pack2(__uint_as_float(orr[8 * v4 + 4]) * inv, __uint_as_float(orr[8 * v4 + 5]) * inv),
+                       atc_pack2(__uint_as_float(orr[8 * v4 + 6]) * inv, __uint_as_float(orr[8 * v4 + 7]) * inv));
+    }
+    if (q.lse) q.lse[(seq * p.heads + h) * p.L + l] = mx + __logf(sum);
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// delta[seq, h, l] = sum_d O[tok, h, d] * dO[tok, h, d]; 8 lanes per (token, head), 16 bytes per lane
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, long long o_rs, const bf16* __restrict__ d_o, long long do_rs,
+                  float* __restrict__ delta, AttnTcPlan p, long long total) {
+  const int cph = 8 * p.heads;
+  const int lane = threadIdx.x & 31;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx - lane < total;
+       idx += (long long)gridDim.x * blockDim.x) {       // whole warps iterate together (shuffles below)
+    const bool act = idx < total;
+    const long long ii = act ? idx : 0;
+    const int chunk = (int)(ii % cph);
+    const long long rowid = ii / cph;
+    const long long seq = rowid / p.L;
+    const int l = (int)(rowid % p.L);
+    const long long tok = atl_tok(p, seq, l);
+    float d = 0.f;
+    if (act) {
+      Vec16<bf16> a, b;
+      a.load(o + tok * o_rs + chunk * 8);
+      b.load(d_o + tok * do_rs + chunk * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d = fmaf(a.get(e), b.get(e), d);
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (act && (chunk & 7) == 0) delta[(seq * p.heads + (chunk >> 3)) * p.L + l] = d;
+  }
+}
+
+// DQ_MODE = false: CTA owns key block `blk`, streams query blocks, produces dK, dV.
+// DQ_MODE = true : CTA owns query block `blk`, streams key blocks, produces dQ.
+template <bool DQ_MODE, bool MASKED>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_long_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                           const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                           const AttnLongParams q) {
+  const AttnTcPlan& p = q.pl;
+  constexpr int BLK = 16384;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_A0 = 256, COL_A1 = 320;
+  const int NB = p.nqb;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sR0 = smem;                  // resident: K_j | Q_i
+  uint8_t* sR1 = sR0 + BLK;             // resident: V_j | dO_i
+  uint8_t* sS0 = sR1 + BLK;             // streamed [2]: Q_x | K_x
+  uint8_t* sS1 = sS0 + 2 * BLK;         // streamed [2]: dO_x | V_x
+  uint8_t* sP = sS1 + 2 * BLK;          // [2 key halves][128 q][64 keys]  (dK/dV mode only)
+  uint8_t* sdS = sP + 2 * BLK;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * BLK);
+  uint64_t* res_full = bars;
+  uint64_t* st_full = bars + 1;         // [2]
+  uint64_t* st_empty = bars + 3;        // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* mma3_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* kpen = reinterpret_cast<float*>(bars + 9);    // [L]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long seq = blockIdx.x / NB;
+  const int blk = (int)(blockIdx.x % NB);
+  const int h = blockIdx.y;
+  const int c2 = (int)(seq % p.n_inner), c3 = (int)(seq / p.n_inner);
+
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_q);
+    sm100::tma_prefetch_desc(&tma_k);
+    sm100::tma_prefetch_desc(&tma_v);
+    sm100::tma_prefetch_desc(&tma_do);
+    sm100::mbar_init(res_full, 1);
+    for (int i = 0; i < 2; ++i) { sm100::mbar_init(&st_full[i], 1); sm100::mbar_init(&st_empty[i], 1); }
+    sm100::mbar_init(s_full, 1);
+    sm100::mbar_init(p_full, 8);
+    sm100::mbar_init(mma3_done, 1);
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      sm100::mbar_expect_tx(res_full, 2 * BLK);
+      if (DQ_MODE) {
+        tma_load_4d(sR0, &tma_q, res_full, h * 64, blk * 128, c2, c3);
+        tma_load_4d(sR1, &tma_do, res_full, h * 64, blk * 128, c2, c3);
+      } else {
+        tma_load_4d(sR0, &tma_k, res_full, h * 64, blk * 128, c2, c3);
+        tma_load_4d(sR1, &tma_v, res_full, h * 64, blk * 128, c2, c3);
+      }
+      for (int x = 0; x < NB; ++x) {
+        const int slot = x & 1;
+        sm100::mbar_wait(&st_empty[slot], ((x >> 1) & 1) ^ 1);
+        sm100::mbar_expect_tx(&st_full[slot], 2 * BLK);
+        if (DQ_MODE) {
+          tma_load_4d(sS0 + slot * BLK, &tma_k, &st_full[slot], h * 64, x * 128, c2, c3);
+          tma_load_4d(sS1 + slot * BLK, &tma_v, &st_full[slot], h * 64, x * 128, c2, c3);
+        } else {
+          tma_load_4d(sS0 + slot * BLK, &tma_q, &st_full[slot], h * 64, x * 128, c2, c3);
+          tma_load_4d(sS1 + slot * BLK, &tma_do, &st_full[slot], h * 64, x * 128, c2, c3);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_kv = sm100::make_idesc_bf16(128, 64, true, true);
+      constexpr uint32_t idesc_q = sm100::make_idesc_bf16(128, 64, false, true);
+      const uint32_t r0 = sm100::smem_u32(sR0), r1 = sm100::smem_u32(sR1);
+      const uint32_t aP = sm100::smem_u32(sP), aS = sm100::smem_u32(sdS);
+      auto issue_sdp = [&](int x) {
+        const int slot = x & 1;
+        sm100::mbar_wait(&st_full[slot], (x >> 1) & 1);
+        sm100::tc_fence_after();
+        const uint32_t s0 = sm100::smem_u32(sS0 + slot * BLK), s1 = sm100::smem_u32(sS1 + slot * BLK);
+        const uint32_t aq = DQ_MODE ? r0 : s0, ak = DQ_MODE ? s0 : r0, ad = DQ_MODE ? r1 : s1, av = DQ_MODE ? s1 : r1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + COL_S, sm100::make_smem_desc_sw128(aq + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(ak + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + COL_DP, sm100::make_smem_desc_sw128(ad + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(av + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        sm100::umma_commit(s_full);
+      };
+      sm100::mbar_wait(res_full, 0);
+      issue_sdp(0);
+      for (int x = 0; x < NB; ++x) {
+        const int slot = x & 1;
+        sm100::mbar_wait(p_full, x & 1);
+        sm100::tc_fence_after();
+        if (x + 1 < NB) issue_sdp(x + 1);
+        const uint32_t s0 = sm100::smem_u32(sS0 + slot * BLK), s1 = sm100::smem_u32(sS1 + slot * BLK);
+        if (DQ_MODE) {        // dQ_i (+)= dS . K_x
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            sm100::umma_f16(tmem_base + COL_A0, sm100::make_smem_desc_sw128(aS + (k >> 2) * BLK + (k & 3) * 32, 16, 1024),
+                            sm100::make_smem_desc_sw128(s0 + k * 2048, 8192, 1024), idesc_q, (x > 0 || k > 0) ? 1u : 0u);
+        } else {              // dV_j (+)= P^T . dO_x ; dK_j (+)= dS^T . Q_x
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            sm100::umma_f16(tmem_base + COL_A1, sm100::make_smem_desc_sw128(aP + k * 2048, BLK, 1024),
+                            sm100::make_smem_desc_sw128(s1 + k * 2048, 8192, 1024), idesc_kv, (x > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            sm100::umma_f16(tmem_base + COL_A0, sm100::make_smem_desc_sw128(aS + k * 2048, BLK, 1024),
+                            sm100::make_smem_desc_sw128(s0 + k * 2048, 8192, 1024), idesc_kv, (x > 0 || k > 0) ? 1u : 0u);
+        }
+        sm100::umma_commit(&st_empty[slot]);
+        sm100::umma_commit(mma3_done);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;
+    const int tid = threadIdx.x - 64;
+    if (MASKED) {
+      for (int c = tid; c < p.L; c += 256)
+        kpen[c] = q.mask[(seq / q.mask_seq_div) * q.ms_seq + (long long)c * q.ms_k] == 0 ? 1.f : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sw = (uint32_t)(r & 7);
+    const float k2 = q.scale * 1.4426950408889634f;
+    const float inv_l = 1.f / (float)p.L;
+    const long long stat_base = (seq * p.heads + h) * p.L;
+    float lse_c = 0.f, dlt_c = 0.f;
+    if (DQ_MODE) { lse_c = q.lse[stat_base + blk * 128 + r]; dlt_c = q.delta[stat_base + blk * 128 + r]; }
+    else { lse_c = q.lse[stat_base + r]; dlt_c = q.delta[stat_base + r]; }
+
+#pragma unroll 1
+    for (int x = 0; x < NB; ++x) {
+      const float lraw = lse_c, my_d = dlt_c;
+      if (!DQ_MODE && x + 1 < NB) {            // prefetch the next query block's statistics
+        lse_c = q.lse[stat_base + (x + 1) * 128 + r];
+        dlt_c = q.delta[stat_base + (x + 1) * 128 + r];
+      }
+      const float my_lse2 = lraw * 1.4426950408889634f;
+      const bool my_allm = lraw <= 0.5f * ATC_BIG_NEG;
+      const int kb = DQ_MODE ? x : blk;        // key block of this tile
+      sm100::mbar_wait(s_full, x & 1);
+      sm100::tc_fence_after();
+      uint32_t pkP[32], pkS[32];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c0 = g * 64 + hf * 32;
+        uint32_t sr[32], dr[32];
+        sm100::tmem_ld_32x32(trow + COL_S + c0, sr);
+        sm100::tmem_ld_32x32(trow + COL_DP + c0, dr);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float pr = atc_exp2(__uint_as_float(sr[e + u]) * k2 - my_lse2);
+            bool masked = false;
+            if constexpr (MASKED) {
+              masked = kpen[kb * 128 + c0 + e + u] != 0.f;
+              if (masked) pr = my_allm ? inv_l : 0.f;
+            }
+            pv[u] = pr;
+            dv[u] = masked ? 0.f : pr * (__uint_as_float(dr[e + u]) - my_d) * q.scale;
+          }
+          pkP[hf * 16 + (e >> 1)] = atc_pack2(pv[0], pv[1]);
+          pkS[hf * 16 + (e >> 1)] = atc_pack2(dv[0], dv[1]);
+        }
+      }
+      sm100::tc_fence_before();
+      if (x > 0) sm100::mbar_wait(mma3_done, (x - 1) & 1);
+      {
+        uint8_t* prow = sP + g * BLK + r * 128;
+        uint8_t* srow = sdS + g * BLK + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t off = (((uint32_t)ch ^ sw) << 4);
+          if (!DQ_MODE)
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(pkP[4 * ch], pkP[4 * ch + 1], pkP[4 * ch + 2], pkP[4 * ch + 3]);
+          *reinterpret_cast<uint4*>(srow + off) = make_uint4(pkS[4 * ch], pkS[4 * ch + 1], pkS[4 * ch + 2], pkS[4 * ch + 3]);
+        }
+      }
+      sm100::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(p_full);
+    }
+    sm100::mbar_wait(mma3_done, (NB - 1) & 1);
+    sm100::tc_fence_after();
+    const long long tok = atl_tok(p, seq, blk * 128 + r);
+    if (DQ_MODE) {            // each warp group drains 32 of dQ's 64 columns
+      bf16* dst = q.dq + tok * q.dq_rs + (long long)h * 64 + g * 32;
+      uint32_t rr[32];
+      sm100::tmem_ld_32x32(trow + COL_A0 + g * 32, rr);
+      sm100::tmem_ld_wait();
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4)
+        *reinterpret_cast<uint4*>(dst + 8 * v4) =
+            make_uint4(atc_pack2(__uint_as_float(rr[8 * v4]), __uint_as_float(rr[8 * v4 + 1])),
+                       atc_pack2(__uint_as_float(rr[8 * v4 + 2]), __uint_as_float(rr[8 * v4 + 3])),
+                       atc_pack2(__uint_as_float(rr[8 * v4 + 4]), __uint_as_float(rr[8 * v4 + 5])),
+                       atc_pack2(__uint_as_float(rr[8 * v4 + 6]), __uint_as_float(rr[8 * v4 + 7])));
+    } else {                  // warp group 0 drains dK, warp group 1 dV
+      bf16* dst = (g == 0 ? q.dk + tok * q.dk_rs : q.dv + tok * q.dv_rs) + (long long)h * 64;
+      const uint32_t col = g == 0 ? COL_A0 : COL_A1;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t rr[32];
+        sm100::tmem_ld_32x32(trow + col + c0, rr);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4)
+          *reinterpret_cast<uint4*>(dst + c0 + 8 * v4) =
+              make_uint4(atc_pack2(__uint_as_float(rr[8 * v4]), __uint_as_float(rr[8 * v4 + 1])),
+                         atc_pack2(__uint_as_float(rr[8 * v4 + 2]), __uint_as_float(rr[8 * v4 + 3])),
+                         atc_pack2(__uint_as_float(rr[8 * v4 + 4]), __uint_as_float(rr[8 * v4 + 5])),
+                         atc_pack2(__uint_as_float(rr[8 * v4 + 6]), __uint_as_float(rr[8 * v4 + 7])));
+      }
+    }
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <typename K>
+static int atl_set_smem(K kern, int bytes, bool* done) {
+  if (*done) return VVAE_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("attention (long): cudaFuncSetAttribute(%d): %s", bytes, cudaGetErrorString(e));
+    return VVAE_ERR_CUDA;
+  }
+  *done = true;
+  return VVAE_OK;
+}
+
+static void atl_fill_params(const vvae_attn_args& a, const AttnTcPlan& p, AttnLongParams& q) {
+  q.pl = p;
+  q.o = (bf16*)a.o; q.o_rs = a.o_rs; q.lse = a.lse; q.delta = a.delta;
+  q.mask = a.mask; q.mask_seq_div = a.mask_seq_div > 0 ? a.mask_seq_div : 1; q.ms_seq = a.ms_seq; q.ms_k = a.ms_k;
+  q.dq = (bf16*)a.dq; q.dk = (bf16*)a.dk; q.dv = (bf16*)a.dv;
+  q.dq_rs = a.dq_rs; q.dk_rs = a.dk_rs; q.dv_rs = a.dv_rs;
+  q.scale = a.scale;
+}
+
+static int atl_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
+  const int SMEM = 10 * 16384 + 256 + p.L * 4 + 1024;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, 128, 1, 1))) return rc;
+  AttnLongParams q;
+  atl_fill_params(a, p, q);
+  static bool set_m = false, set_u = false;
+  dim3 grid((unsigned)((long long)p.n_outer * p.n_inner * p.nqb), (unsigned)p.heads);
+  if (a.mask) {
+    if ((rc = atl_set_smem(attn_fwd_long_sm100_kernel<true>, 227 * 1024, &set_m))) return rc;
+    attn_fwd_long_sm100_kernel<true><<<grid, 192, SMEM, s>>>(mq, mk, mv, q);
+  } else {
+    if ((rc = atl_set_smem(attn_fwd_long_sm100_kernel<false>, 227 * 1024, &set_u))) return rc;
+    attn_fwd_long_sm100_kernel<false><<<grid, 192, SMEM, s>>>(mq, mk, mv, q);
+  }
+  return check_launch("attn_fwd_long_sm100");
+}
+
+static int atl_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
+  const int SMEM = 10 * 16384 + 256 + p.L * 4 + 1024;
+  CUtensorMap mq, mk, mv, md;
+  int rc;
+  if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&md, a.d_o, a.do_rs, p, 128, 1, 1))) return rc;
+  AttnLongParams q;
+  atl_fill_params(a, p, q);
+  const long long n_seq = (long long)p.n_outer * p.n_inner;
+  {
+    const long long total = n_seq * p.L * 8 * p.heads;
+    const int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
+    attn_delta_kernel<<<blocks, 256, 0, s>>>((const bf16*)a.o, a.o_rs, (const bf16*)a.d_o, a.do_rs, a.delta, p, total);
+    if ((rc = check_launch("attn_delta"))) return rc;
+  }
+  static bool set[4] = {false, false, false, false};
+  dim3 grid((unsigned)(n_seq * p.nqb), (unsigned)p.heads);
+  if (a.mask) {
+    if ((rc = atl_set_smem(attn_bwd_long_sm100_kernel<false, true>, 227 * 1024, &set[0]))) return rc;
+    if ((rc = atl_set_smem(attn_bwd_long_sm100_kernel<true, true>, 227 * 1024, &set[1]))) return rc;
+    attn_bwd_long_sm100_kernel<false, true><<<grid, 320, SMEM, s>>>(mq, mk, mv, md, q);
+    attn_bwd_long_sm100_kernel<true, true><<<grid, 320, SMEM, s>>>(mq, mk, mv, md, q);
+  } else {
+    if ((rc = atl_set_smem(attn_bwd_long_sm100_kernel<false, false>, 227 * 1024, &set[2]))) return rc;
+    if ((rc = atl_set_smem(attn_bwd_long_sm100_kernel<true, false>, 227 * 1024, &set[3]))) return rc;
+    attn_bwd_long_sm100_kernel<false, false><<<grid, 320, SMEM, s>>>(mq, mk, mv, md, q);
+    attn_bwd_long_sm100_kernel<true, false><<<grid, 320, SMEM, s>>>(mq, mk, mv, md, q);
+  }
+  return check_launch("attn_bwd_long_sm100");
+}
+
 int attn_tc_supported(const vvae_attn_args& a) {
   AttnTcPlan p;
   if (!atc_make_plan(a, p)) return 0;
@@ -746,6 +1323,7 @@ int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s) {
     set_error("attention: shape not supported by the tensor-core path");
     return VVAE_ERR_UNSUPPORTED;
   }
+  if (atc_len_long(a.L)) return atl_launch_fwd(a, p, s);
   const bool m = a.mask != nullptr;
   if (p.G > 1) return m ? atc_launch_fwd<128, true, true>(a, p, s) : atc_launch_fwd<128, true, false>(a, p, s);
   if (p.NK == 128) return m ? atc_launch_fwd<128, false, true>(a, p, s) : atc_launch_fwd<128, false, false>(a, p, s);
@@ -758,6 +1336,7 @@ int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s) {
     set_error("attention bwd: shape not supported by the tensor-core path");
     return VVAE_ERR_UNSUPPORTED;
   }
+  if (atc_len_long(a.L)) return atl_launch_bwd(a, p, s);
   const bool m = a.mask != nullptr;
   if (p.G > 1) return m ? atc_launch_bwd<1, true, true>(a, p, s) : atc_launch_bwd<1, true, false>(a, p, s);
   if (p.NK == 128) return m ? atc_launch_bwd<1, false, true>(a, p, s) : atc_launch_bwd<1, false, false>(a, p, s);
