@@ -92,8 +92,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"VideoVAE train step {args.frames}x{args.size}x{args.size}, CPU oracle port of the "
-                               "JAX/Flax reference (JAX not installable offline)", "sample": sample},
+        "config": {"workload": f"VideoVAE train step (fwd+loss+bwd) on {args.frames}x{args.size}x{args.size} RGB clips, "
+                               f"enc {args.enc_depth}/dec {args.dec_depth}, mlp 1536, 8 heads x 64, latent 96 "
+                               "(BASELINE.json configs[1]); reference arm = CPU oracle port of the JAX/Flax reference "
+                               "(JAX is not installable offline), fp32, all host cores", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
