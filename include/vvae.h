@@ -76,6 +76,8 @@ typedef struct vvae_gemm_args {
   void* aux_out; long long ld_aux_out;
   int accumulate;
   int backend;
+  float* bsum_accum; /* optional, fp32 [N]: += sum_k op(B)[k, n].  For a weight gradient X^T . dY this is the Linear's bias
+                      * gradient, summed from the dY tiles while they sit in shared memory (no second pass over dY). */
 } vvae_gemm_args;
 int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream);
 /* 1 if vvae_gemm would run these arguments on the tcgen05 kernel, 0 if on the generic SIMT kernel. */

@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
                 ("bias", C.c_void_p), ("epilogue", C.c_int),
                 ("aux_in", C.c_void_p), ("ld_aux_in", C.c_longlong),
                 ("aux_out", C.c_void_p), ("ld_aux_out", C.c_longlong),
-                ("accumulate", C.c_int), ("backend", C.c_int)]
+                ("accumulate", C.c_int), ("backend", C.c_int), ("bsum_accum", C.c_void_p)]
 
 
 def run_case(cfg):
@@ -50,10 +50,12 @@ def run_case(cfg):
     Cm = torch.zeros(M, N, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
     if acc:
         Cm += 1.0
+    bsum = torch.zeros(N, device=dev) if cfg.get("bsum", 0) else None
     a = GemmArgs(M, N, K, A.data_ptr(), A.stride(0), tA, B.data_ptr(), B.stride(0), tB, Cm.data_ptr(), N,
                  1, 0 if out_f32 else 1, bias.data_ptr() if bias is not None else None, mode,
                  aux_in.data_ptr() if aux_in is not None else None, N,
-                 aux_out.data_ptr() if aux_out is not None else None, N, acc, backend)
+                 aux_out.data_ptr() if aux_out is not None else None, N, acc, backend,
+                 bsum.data_ptr() if bsum is not None else None)
     st = torch.cuda.current_stream().cuda_stream
     rc = lib.vvae_gemm(C.byref(a), st)
     if rc != 0:
@@ -65,6 +67,9 @@ def run_case(cfg):
     if bias is not None:
         ref = ref + bias
     res = {"rc": 0}
+    if bsum is not None:
+        refb = B.float().sum(0)
+        res["bsum_err"] = ((bsum - refb).abs().max() / refb.abs().max()).item()
     if mode == 1:
         res["aux_err"] = (aux_out.float() - ref).abs().max().item()
         ref = torch.nn.functional.silu(ref.bfloat16().float())
@@ -160,6 +165,11 @@ add("prod_do_dgrad", M=32768, N=512, K=768, tA=0, tB=1, time=1)
 add("prod_du_dgrad", M=32768, N=1536, K=768, tA=0, tB=1, mode=3, time=1)
 add("prod_wgrad_o", M=512, N=768, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1)
 add("prod_wgrad_w2", M=1536, N=768, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1)
+add("wgrad_bsum_small", M=768, N=1536, K=4096, tA=1, tB=0, out_f32=1, acc=1, bsum=1)
+add("wgrad_bsum_tail", M=200, N=136, K=1000, tA=1, tB=0, out_f32=1, acc=1, bsum=1)
+add("wgrad_bsum_n96", M=768, N=96, K=2048, tA=1, tB=0, out_f32=1, acc=1, bsum=1)
+add("prod_wgrad_bsum", M=768, N=1536, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1, bsum=1)
+add("prod_wgrad_o_bsum", M=512, N=768, K=32768, tA=1, tB=0, out_f32=1, acc=1, time=1, bsum=1)
 add("prod_qkv_fwd_cg1", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, time=1, dbg={8: 1})
 add("prod_mlp_up_fwd_cg1", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, mode=1, time=1, dbg={8: 1})
 add("prod_qkv_fwd_bn128", M=32768, N=1536, K=768, tA=0, tB=0, bias=1, time=1, dbg={6: 128})

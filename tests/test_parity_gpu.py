@@ -38,6 +38,25 @@ def V():
 
 
 # ---------------------------------------------------------------------------------------------- single operators
+@pytest.mark.parametrize("rows,kin,n", [(4096, 768, 1536), (1000, 200, 136), (2048, 512, 96)])
+def test_wgrad_gemm_with_fused_bias_gradient(V, rows, kin, n):
+    """dW += X^T.dY and db += column sums of dY from ONE tensor-core GEMM (bsum), split-K tails and ragged N included;
+    the fp32 generic path (separate column-sum pass) must agree."""
+    from video_vae_b200 import ops
+    g = _gen(21)
+    x = torch.randn(rows, kin, generator=g).bfloat16()
+    dy = torch.randn(rows, n, generator=g).bfloat16()
+    dw = torch.ones(kin, n, device="cuda")
+    db = torch.ones(n, device="cuda")
+    ops.gemm(x.cuda(), dy.cuda(), transA=True, out=dw, accumulate=True, bsum=db)
+    assert rel_err(dw, x.float().t() @ dy.float() + 1.0) < 1e-3
+    assert rel_err(db, dy.float().sum(0) + 1.0) < 1e-4
+    dw32 = torch.zeros(kin, n, device="cuda")
+    db32 = torch.zeros(n, device="cuda")
+    ops.gemm(x.float().cuda(), dy.float().cuda(), transA=True, out=dw32, accumulate=True, bsum=db32)
+    assert rel_err(db32, dy.float().sum(0)) < FP32_TOL and rel_err(dw32, x.float().t() @ dy.float()) < FP32_TOL
+
+
 def test_gemm_all_modes_fp32_and_bf16(V):
     from video_vae_b200 import ops
     from video_vae_b200._ffi import BACKEND_SIMT, BACKEND_TCGEN05

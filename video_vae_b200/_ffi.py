@@ -41,7 +41,8 @@ class GemmArgs(C.Structure):
                 ("aux_in", vp), ("ld_aux_in", ll),
                 ("aux_out", vp), ("ld_aux_out", ll),
                 ("accumulate", i32),
-                ("backend", i32)]
+                ("backend", i32),
+                ("bsum_accum", vp)]
 
 
 class AttnArgs(C.Structure):

@@ -81,6 +81,17 @@ extern "C" int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream) {
                "vvae_gemm: epilogue %d needs aux_in", a.epilogue);
   cudaStream_t s = as_stream(stream);
   const bool tc_ok = sm100_gemm_supported(a);
+  if (a.bsum_accum) {
+    VVAE_REQUIRE(!a.transB, "vvae_gemm: bsum_accum needs op(B) = B (rows = contraction index)");
+    const bool fused = tc_ok && a.backend != VVAE_BACKEND_SIMT && a.transA && a.dtype == VVAE_BF16;
+    if (!fused) {   // generic kernels: the column sums are a separate pass over B
+      int rc = vvae_colsum(a.B, a.ldb, a.K, a.N, a.bsum_accum, a.dtype, stream);
+      if (rc) return rc;
+      vvae_gemm_args b = a;
+      b.bsum_accum = nullptr;
+      return vvae_gemm(&b, stream);
+    }
+  }
   if (a.backend == VVAE_BACKEND_TCGEN05) {
     if (!tc_ok) {
       set_error("vvae_gemm: shape/alignment not supported by the tcgen05 path (M=%d N=%d K=%d)", a.M, a.N, a.K);

@@ -80,7 +80,8 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB per CTA
 constexpr int STG_BYTES = 128 * 128;        // one epilogue staging buffer: 128 rows x 64 bf16, 128B-swizzled
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu; // shared::cluster address of the same offset in the even CTA of a pair
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+constexpr int MODE_BSUM = 4;                // internal: weight-gradient GEMM that also sums the columns of its B operand // shared::cluster address of the same offset in the even CTA of a pair
 
 struct Sm100Params {
   int M, N;                // output extent
@@ -93,6 +94,7 @@ struct Sm100Params {
   bf16* aux_out; long long ld_ao;
   int atomic;
   int tma_epi;             // bf16 output: epilogue goes TMEM -> registers -> swizzled smem -> TMA store
+  float* bsum;             // MODE_BSUM: += column sums of op(B) over K (a Linear's bias gradient, fused into its wgrad)
   // descriptor encodings (bytes); overridable through vvae_debug_set for bring-up
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
 };
@@ -104,7 +106,7 @@ template <int BN, int CG, bool HEAVY> struct StageCfg {
   static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;          // per CTA
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
   static constexpr int EPI_BYTES = (HEAVY ? 6 : 2) * STG_BYTES;
-  static constexpr int BAR_BYTES = 256 + 256 * 4;   // barriers + the current tile's bias slice
+  static constexpr int BAR_BYTES = 320 + 256 * 4;   // barriers + the current tile's bias slice
   static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -241,11 +243,12 @@ __device__ __forceinline__ float fast_dsilu(float x) {
 }
 
 template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(256, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_ai,
                   const __grid_constant__ CUtensorMap tma_ao, Sm100Params p) {
-  constexpr bool HEAVY = MODE != VVAE_EPI_NONE;   // the fused epilogue is compiled in per mode (keeps the code in the I-cache)
+  constexpr bool HEAVY = MODE != VVAE_EPI_NONE && MODE != MODE_BSUM;   // fused epilogues are compiled in per mode
+  constexpr bool BSUM = MODE == MODE_BSUM;        // two extra warps sum the B tiles' columns after the MMAs consumed them
   using Cfg = StageCfg<BN, CG, HEAVY>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NCH = BN / 64;                 // 64-column epilogue chunks per tile
@@ -263,7 +266,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint64_t* aux_full = bars + 2 * STAGES + 4;   // [4]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
-  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [256]
+  uint64_t* mma_done = bars + 2 * STAGES + 9;   // [STAGES] (BSUM): the MMAs reading stage s have completed
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 320);   // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
@@ -275,7 +279,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     if (p.tma_epi) sm100::tma_prefetch_desc(&tma_c);
     for (int i = 0; i < STAGES; ++i) {
       sm100::mbar_init(&full_bar[i], 1);
-      sm100::mbar_init(&empty_bar[i], 1);
+      sm100::mbar_init(&empty_bar[i], BSUM ? 2 : 1);   // BSUM: the two column-sum warps release the slot
+      if (BSUM) sm100::mbar_init(&mma_done[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
@@ -353,11 +358,70 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const uint64_t db = sm100::make_smem_desc_sw128(b_addr + k * p.b_kadv, p.b_lbo, p.b_sbo);
             umma_f16_cg<CG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_cg<CG>(&empty_bar[stage]);  // frees the smem slot (in both CTAs) once these MMAs have read it
+          umma_commit_cg<CG>(BSUM ? &mma_done[stage] : &empty_bar[stage]);  // the MMAs have read the slot (both CTAs)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit_cg<CG>(&tmem_full[acc]);      // accumulator complete (signals both CTAs' epilogues)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== column sums of B (bias gradient), after the tensor core is done with each stage ==========
+    if constexpr (BSUM) {
+      constexpr int NCH_B = BN / CG / 64;          // 64-column chunks of this CTA's B slice
+      const int cw = warp - 6;                     // chunks cw, cw+2, ...
+      const int cc = lane & 7, rg = lane >> 3;     // 16-byte column chunk, row group
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int split = tile / tiles_mn, mn = tile % tiles_mn;
+        const bool mine = (mn / p.n_tiles) == 0;   // only the first row of output tiles contributes (B is shared by all)
+        const int n0 = (mn % p.n_tiles) * BN + (int)cta_rank * (BN / CG);
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        float acc[(NCH_B + 1) / 2][8];
+#pragma unroll
+        for (int j = 0; j < (NCH_B + 1) / 2; ++j)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[j][t] = 0.f;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          sm100::mbar_wait(&mma_done[stage], phase);
+          if (mine) {
+            const uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < (NCH_B + 1) / 2; ++j) {
+              const int ch = cw + 2 * j;
+              if (ch < NCH_B) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int r = rg + 4 * i;
+                  const uint4 v = *reinterpret_cast<const uint4*>(sb + ch * 8192 + r * 128 + (((uint32_t)cc ^ (uint32_t)(r & 7)) << 4));
+                  acc[j][0] += __uint_as_float(v.x << 16); acc[j][1] += __uint_as_float(v.x & 0xffff0000u);
+                  acc[j][2] += __uint_as_float(v.y << 16); acc[j][3] += __uint_as_float(v.y & 0xffff0000u);
+                  acc[j][4] += __uint_as_float(v.z << 16); acc[j][5] += __uint_as_float(v.z & 0xffff0000u);
+                  acc[j][6] += __uint_as_float(v.w << 16); acc[j][7] += __uint_as_float(v.w & 0xffff0000u);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) sm100::mbar_arrive(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (mine) {
+#pragma unroll
+          for (int j = 0; j < (NCH_B + 1) / 2; ++j) {
+            const int ch = cw + 2 * j;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              float v = acc[j][t];
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              const int n = n0 + ch * 64 + cc * 8 + t;
+              if (rg == 0 && ch < NCH_B && n < p.N) atomicAdd(p.bsum + n, v);
+            }
+          }
+        }
       }
     }
   } else {
@@ -527,7 +591,7 @@ bool sm100_gemm_supported(const vvae_gemm_args& a) {
 
 template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
 static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
-  using Cfg = StageCfg<BN, CG, MODE != VVAE_EPI_NONE>;
+  using Cfg = StageCfg<BN, CG, MODE != VVAE_EPI_NONE && MODE != MODE_BSUM>;   // must match the kernel's HEAVY
   static_assert(Cfg::STAGES >= 3, "pipeline too shallow");
   CUtensorMap ta, tb, tc, tai, tao;
   int rc;
@@ -559,6 +623,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   p.aux_out = (bf16*)a.aux_out; p.ld_ao = a.ld_aux_out;
   p.atomic = (a.accumulate || p.splits > 1) ? 1 : 0;
   p.tma_epi = p.out_f32 ? 0 : 1;
+  p.bsum = a.bsum_accum;
   tc = ta; tai = ta; tao = ta;   // placeholders for maps a mode does not use
   if (p.tma_epi) {
     if ((rc = encode_tmap_2d_bf16(&tc, a.C, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * 2, 64, 128, 128))) return rc;
@@ -594,7 +659,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   int clusters = std::min(total, g_dbg[0] ? (int)g_dbg[0] : n_clusters);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(MODE == MODE_BSUM ? 256 : 192);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -617,6 +682,7 @@ static int dispatch_major(const vvae_gemm_args& a, cudaStream_t s) {
   const bool b_mn = a.transB == 0;   // op(B)[k,n] = B[k*ldb+n]  -> N contiguous
   if (a_mn) {
     if (a.epilogue != VVAE_EPI_NONE) { set_error("gemm_sm100: fused epilogues need a K-major A operand"); return VVAE_ERR_UNSUPPORTED; }
+    if (b_mn && a.bsum_accum) return launch_sm100<BN, CG, true, true, MODE_BSUM>(a, s);
     return b_mn ? launch_sm100<BN, CG, true, true, 0>(a, s) : launch_sm100<BN, CG, true, false, 0>(a, s);
   }
   switch (a.epilogue) {

@@ -115,9 +115,8 @@ class LinearFn(Function):
         dy2 = _as_2d(dy, N)
         if dy2.dtype != ctx.dtype:
             dy2 = ops.cast(dy2, ctx.dtype)
-        ops.gemm(x2, dy2, transA=True, out=grad_buf(kernel), accumulate=True)
-        if bias is not None:
-            ops.colsum_accum(dy2, grad_buf(bias))
+        ops.gemm(x2, dy2, transA=True, out=grad_buf(kernel), accumulate=True,
+                 bsum=grad_buf(bias) if bias is not None else None)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy2, shadow(kernel, ctx.dtype), transB=True)
@@ -203,21 +202,17 @@ class AttnBlockFn(Function):
         D = x2.shape[1]
         Q = cfg.heads * cfg.hd
         dy2 = _as_2d(dy, D)
-        # out projection (the bias gradient first: dy was just written by the previous backward kernel)
-        ops.colsum_accum(dy2, grad_buf(b_o))
-        ops.gemm(o, dy2, transA=True, out=grad_buf(w_o), accumulate=True)
+        # out projection; bias gradients ride along with the weight-gradient GEMMs (column sums of their dY tiles)
+        ops.gemm(o, dy2, transA=True, out=grad_buf(w_o), accumulate=True, bsum=grad_buf(b_o))
         d_o = ops.gemm(dy2, shadow(w_o, dtp), transB=True)
         # attention core -> dq | dk | dv written side by side
         dqkv = torch.empty_like(qkv)
         ops.attn_bwd(cfg.geom, cfg.heads, cfg.hd, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], o, lse, d_o, dqkv[:, :Q],
                      dqkv[:, Q:2 * Q], dqkv[:, 2 * Q:], cfg.mask, cfg.scale)
-        # QK-norm + RoPE backward also accumulates the q|k part of the QKV bias gradient; the v part is a column sum
-        gb = grad_buf(b_qkv)
-        ops.colsum_accum(dqkv[:, 2 * Q:], gb[2 * Q:])
         ops.qknorm_rope_bwd_(dqkv, qkv, q_scale.detach(), k_scale.detach(), cos, sin, grad_buf(q_scale),
-                             grad_buf(k_scale), cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod, dbias_qk=gb[:2 * Q])
+                             grad_buf(k_scale), cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod)
         # qkv projection
-        ops.gemm(h, dqkv, transA=True, out=grad_buf(w_qkv), accumulate=True)
+        ops.gemm(h, dqkv, transA=True, out=grad_buf(w_qkv), accumulate=True, bsum=grad_buf(b_qkv))
         dh = ops.gemm(dqkv, shadow(w_qkv, dtp), transB=True)
         dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if cfg.residual else None, grad_buf(ln_g),
                                grad_buf(ln_b), out=dh)
@@ -252,11 +247,9 @@ class MlpBlockFn(Function):
         x2, mean, rstd, h, u, a, ln_g, ln_b, w1, b1, w2, b2 = ctx.saved_tensors
         dtp = ctx.dtype
         dy2 = _as_2d(dy, x2.shape[1])
-        ops.colsum_accum(dy2, grad_buf(b2))
-        ops.gemm(a, dy2, transA=True, out=grad_buf(w2), accumulate=True)
+        ops.gemm(a, dy2, transA=True, out=grad_buf(w2), accumulate=True, bsum=grad_buf(b2))
         du = ops.gemm(dy2, shadow(w2, dtp), transB=True, epilogue=EPI_DSILU, aux_in=u)
-        ops.colsum_accum(du, grad_buf(b1))
-        ops.gemm(h, du, transA=True, out=grad_buf(w1), accumulate=True)
+        ops.gemm(h, du, transA=True, out=grad_buf(w1), accumulate=True, bsum=grad_buf(b1))
         dh = ops.gemm(du, shadow(w1, dtp), transB=True)
         dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if ctx.residual else None, grad_buf(ln_g),
                                grad_buf(ln_b), out=dh)
@@ -284,8 +277,7 @@ class PatchEmbedFn(Function):
     def backward(ctx, dy):
         tok2, mean, rstd, h, ln_g, ln_b, kernel, bias = ctx.saved_tensors
         dy2 = _as_2d(dy, kernel.shape[1])
-        ops.gemm(h, dy2, transA=True, out=grad_buf(kernel), accumulate=True)
-        ops.colsum_accum(dy2, grad_buf(bias))
+        ops.gemm(h, dy2, transA=True, out=grad_buf(kernel), accumulate=True, bsum=grad_buf(bias))
         dh = ops.gemm(dy2, shadow(kernel, ctx.dtype), transB=True)
         ops.layernorm_bwd(dh, tok2, mean, rstd, ln_g.detach(), None, grad_buf(ln_g), grad_buf(ln_b), out=dh)
         _notify([ln_g, ln_b, kernel, bias])
@@ -329,11 +321,9 @@ class UnembedFn(Function):
         else:
             df = _as_2d(dfeats, CU)
         dy2 = ops.pixel_shuffle(df, b * t, H, W, CU, P, to_tokens=True)
-        ops.gemm(y1, dy2, transA=True, out=grad_buf(wu), accumulate=True)
-        ops.colsum_accum(dy2, grad_buf(bu))
+        ops.gemm(y1, dy2, transA=True, out=grad_buf(wu), accumulate=True, bsum=grad_buf(bu))
         dy1 = ops.gemm(dy2, shadow(wu, dtp), transB=True)
-        ops.gemm(x2, dy1, transA=True, out=grad_buf(wl), accumulate=True)
-        ops.colsum_accum(dy1, grad_buf(bl))
+        ops.gemm(x2, dy1, transA=True, out=grad_buf(wl), accumulate=True, bsum=grad_buf(bl))
         dx = ops.gemm(dy1, shadow(wl, dtp), transB=True)
         _notify([wl, bl, wu, bu, wd, bd])
         return (dx.view(ctx.x_shape),) + (None,) * 8
@@ -387,16 +377,14 @@ class EncoderHeadFn(Function):
                 dmean2 = ops.gemm(ds1, shadow(w1, dtp), transB=True)
         dx = None
         if dmean2 is not None:
-            ops.gemm(x2, dmean2, transA=True, out=grad_buf(wm), accumulate=True)
-            ops.colsum_accum(dmean2, grad_buf(bm))
+            ops.gemm(x2, dmean2, transA=True, out=grad_buf(wm), accumulate=True, bsum=grad_buf(bm))
             dx = ops.gemm(dmean2, shadow(wm, dtp), transB=True)
         if dlv is not None:
             dlv2 = _as_2d(dlv, Dl)
             if dlv2.dtype != dtp:
                 dlv2 = ops.cast(dlv2, dtp)
             da = ops.softplus_log_bwd(dlv2, a)
-            ops.gemm(x2, da, transA=True, out=grad_buf(wv), accumulate=True)
-            ops.colsum_accum(da, grad_buf(bv))
+            ops.gemm(x2, da, transA=True, out=grad_buf(wv), accumulate=True, bsum=grad_buf(bv))
             if dx is not None:
                 dx = ops.gemm(da, shadow(wv, dtp), transB=True, epilogue=EPI_RESIDUAL, aux_in=dx)
             else:

@@ -76,8 +76,9 @@ def colsum_accum(x2d, out):
 
 
 def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=None, epilogue=EPI_NONE, aux_in=None,
-         aux_out=None, accumulate=False, backend=BACKEND_AUTO):
-    """C = epilogue(op(A) @ op(B)); A, B 2-D with unit inner stride (views with a row stride are fine)."""
+         aux_out=None, accumulate=False, backend=BACKEND_AUTO, bsum=None):
+    """C = epilogue(op(A) @ op(B)); A, B 2-D with unit inner stride (views with a row stride are fine).
+    bsum (fp32 [N], optional) += column sums of B: the bias gradient of a Linear, fused into its weight-gradient GEMM."""
     assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.dtype == B.dtype
     M, K = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
     Kb, N = (B.shape[1], B.shape[0]) if transB else (B.shape[0], B.shape[1])
@@ -91,7 +92,7 @@ def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=Non
                  dt(A), dt(out), ptr(bias), epilogue,
                  ptr(aux_in), aux_in.stride(0) if aux_in is not None else 0,
                  ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0,
-                 int(accumulate), backend)
+                 int(accumulate), backend, ptr(bsum))
     if PROFILE is not None:
         name = "gemm_tcgen05" if lib.vvae_gemm_uses_tcgen05(C.byref(a)) else "gemm_simt"
         with _Prof(name, 2.0 * M * N * K):
