@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--dec-depth", type=int, default=PROD["decoder_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--graph-allreduce", action="store_true", help="N > 1, EXPERIMENTAL: capture the bucketed all-reduce "
+                    "inside the graph instead of one all-reduce after it (hung at N=2 with NCCL 2.28.9 in round 1)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
                     "of replaying the captured CUDA graph; N > 1 then overlaps the bucketed all-reduce with backward")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
@@ -189,7 +191,7 @@ def run_ours(args):
         model.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7))
     flat = FlatParams(model)
     flat.enable_bf16_shadow()
-    reducer = GradAllReducer(flat) if (world > 1 and args.no_graph) else None
+    reducer = GradAllReducer(flat) if world > 1 else None
     opt = None if args.no_optimizer else FlatAdam(flat, lr=5e-5)
     hp = dict(V.DEFAULT_HPARAMS, gamma4=0.1)   # MSE + selection + KL + MAE terms
 
@@ -200,7 +202,18 @@ def run_ours(args):
     mask = host_mask.to(dev, non_blocking=True)
     rngs = V.Rngs(3 + rank)
 
-    graphed = None if args.no_graph else GraphedTrainStep(model, flat, video, mask, hp)
+    graphed, ar_in_graph = None, False
+    if not args.no_graph:
+        if reducer is not None and args.graph_allreduce:
+            try:      # bucketed all-reduce captured inside the graph: overlaps the rest of backward
+                graphed = GraphedTrainStep(model, flat, video, mask, hp, reducer=reducer)
+                ar_in_graph = True
+            except Exception as e:  # noqa: BLE001  (capture of NCCL work refused: fall back to one all-reduce after the graph)
+                print(f"[bench] all-reduce capture failed ({type(e).__name__}: {str(e)[:200]}); using a post-graph all-reduce",
+                      file=sys.stderr)
+                torch.cuda.synchronize()
+        if graphed is None:
+            graphed = GraphedTrainStep(model, flat, video, mask, hp)
 
     def eager_step(v, m):
         flat.zero_grad()
@@ -217,7 +230,7 @@ def run_ours(args):
         gradient all-reduce (N > 1) and the fused clip + Adam kernels."""
         if graphed is not None:
             loss = graphed(v, m, rngs)
-            if world > 1:
+            if world > 1 and not ar_in_graph:
                 dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
         else:
             loss = eager_step(v, m)
@@ -353,7 +366,9 @@ def run_ours(args):
         "gpu_launches_note": ("libvvae kernel-launching C-ABI calls executed in the timed region: those captured in the "
                               "replayed CUDA graph (counted in one eager pass) x steps + those enqueued directly")
         if graphed is not None else "libvvae C-ABI kernel-launching calls in the timed region",
-        "execution": "cuda-graph replay (zero-grad+fwd+loss+bwd) + eager optimizer" if graphed is not None else "eager",
+        "execution": ("cuda-graph replay (zero-grad+fwd+loss+bwd" + ("+bucketed all-reduce" if ar_in_graph else "") +
+                      ") + eager " + ("all-reduce + " if (world > 1 and not ar_in_graph) else "") + "optimizer")
+        if graphed is not None else "eager",
         "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -18,8 +18,11 @@ from .losses import DEFAULT_HPARAMS, loss_fn
 class GraphedTrainStep:
     """fwd + loss + bwd of ``model`` on a fixed (batch, frames, size) shape as one CUDA graph."""
 
-    def __init__(self, model, flat, video_like, mask_like, hparams=None, warmup=2):
-        self.model, self.flat = model, flat
+    def __init__(self, model, flat, video_like, mask_like, hparams=None, warmup=2, reducer=None):
+        """reducer: an optional ddp.GradAllReducer.  Its bucketed NCCL all-reduces are then captured INSIDE the graph on
+        the reducer's side stream (fork after a bucket's last gradient kernel, join before the graph ends), so the
+        gradient exchange overlaps the rest of backward exactly as in eager mode."""
+        self.model, self.flat, self.reducer = model, flat, reducer
         self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
         dev = video_like.device
         b, t = mask_like.shape
@@ -54,9 +57,13 @@ class GraphedTrainStep:
 
     def _body(self):
         self.flat.zero_grad()
+        if self.reducer is not None:
+            self.reducer.start_step()
         loss, aux = loss_fn(self.model, self.video, self.mask[:, None, None, :], self.mask, None, self.hp, train=True,
                             noise=self.noise, gumbel_u=self.gumbel_u)
         loss.backward()
+        if self.reducer is not None:
+            self.reducer.finish_step()
         return loss.detach(), {k: v.detach() for k, v in aux.items()}
 
     def __call__(self, video, mask, rngs):
