@@ -38,20 +38,16 @@ __global__ void convt_dw_scatter_kernel(const float* __restrict__ dwp, float* __
 __global__ void __launch_bounds__(256)
 convt_shuffle_kernel(bf16* __restrict__ dense, bf16* __restrict__ y, long long y_ld, long long n_vec, int H, int W, int Cout,
                      int dir) {
-  const int cv = Cout >> 3;                     // vectors per (voxel, tap)
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += stride) {
+  const unsigned cv = (unsigned)Cout >> 3;      // vectors per (voxel, tap)
+  const unsigned W2 = 2u * (unsigned)W, H2 = 2u * (unsigned)H;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < (unsigned)n_vec; i += stride) {   // n_vec < 2^31 (host check)
     // enumerate in FULL-RES order (coalesced on the strided side): i = ((bt, y2, x2), v)
-    const int v = (int)(i % cv);
-    long long p = i / cv;
-    const int x2 = (int)(p % (2 * W));
-    p /= (2 * W);
-    const int y2 = (int)(p % (2 * H));
-    const long long bt = p / (2 * H);
-    const long long vox = (bt * H + (y2 >> 1)) * W + (x2 >> 1);
-    const int tap = ((y2 & 1) << 1) | (x2 & 1);
+    const unsigned v = i % cv, p1 = i / cv, x2 = p1 % W2, p2 = p1 / W2, y2 = p2 % H2, bt = p2 / H2;
+    const long long vox = ((long long)bt * H + (y2 >> 1)) * W + (x2 >> 1);
+    const unsigned tap = ((y2 & 1) << 1) | (x2 & 1);
     bf16* d = dense + (vox * 4 + tap) * Cout + v * 8;
-    bf16* f = y + ((bt * 2 * H + y2) * 2 * W + x2) * y_ld + v * 8;
+    bf16* f = y + (((long long)bt * H2 + y2) * W2 + x2) * y_ld + v * 8;
     if (dir == 0) *reinterpret_cast<uint4*>(f) = *reinterpret_cast<const uint4*>(d);
     else          *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(f);
   }
@@ -71,7 +67,7 @@ bool convt_tc_supported(int dtype, int b_t, int H, int W, int Cin, int Cout, con
   if (((uintptr_t)ws % 256) || ((uintptr_t)x % 16) || ((uintptr_t)y % 16)) return false;
   if (Cin % 8 || Cout % 8 || y_ld % 8) return false;
   const long long V = (long long)b_t * H * W;
-  return V >= 128 && V < (1LL << 31) && Cin >= 16 && Cout >= 16;
+  return V >= 128 && V * 4 * (Cout / 8) < (1LL << 31) && Cin >= 16 && Cout >= 16;
 }
 
 static void split_ws(void* ws, int Cin, int Cout, bf16** wp, float** bias4, float** dwp, bf16** dense) {

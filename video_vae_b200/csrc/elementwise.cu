@@ -161,6 +161,74 @@ __global__ void copy_channels_kernel(const T* __restrict__ src, long long src_ld
   }
 }
 
+
+// ---- bf16 fast paths: 8 channels (one 16-byte vector) per thread, 32-bit index arithmetic ----
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__global__ void __launch_bounds__(256)
+maxpool_fwd_vec_kernel(const bf16* __restrict__ x, long long x_ld, bf16* __restrict__ y, unsigned total_vec, int H, int W,
+                       int C) {
+  const unsigned cv = (unsigned)C >> 3, Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += gridDim.x * blockDim.x) {
+    const unsigned v = i % cv, t1 = i / cv, j = t1 % Wo, t2 = t1 / Wo, ii = t2 % Ho, bt = t2 / Ho;
+    const bf16* p = x + (((long long)bt * H + 2 * ii) * W + 2 * j) * x_ld + v * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(p), b = *reinterpret_cast<const uint4*>(p + x_ld);
+    const uint4 c = *reinterpret_cast<const uint4*>(p + (long long)W * x_ld);
+    const uint4 d = *reinterpret_cast<const uint4*>(p + (long long)W * x_ld + x_ld);
+    uint4 o;
+    o.x = bf2_max(bf2_max(a.x, b.x), bf2_max(c.x, d.x));
+    o.y = bf2_max(bf2_max(a.y, b.y), bf2_max(c.y, d.y));
+    o.z = bf2_max(bf2_max(a.z, b.z), bf2_max(c.z, d.z));
+    o.w = bf2_max(bf2_max(a.w, b.w), bf2_max(c.w, d.w));
+    *reinterpret_cast<uint4*>(y + (long long)i * 8) = o;
+  }
+}
+__global__ void __launch_bounds__(256)
+maxpool_bwd_vec_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __restrict__ dy, const bf16* __restrict__ dskip,
+                       long long dskip_ld, bf16* __restrict__ dx, unsigned total_vec, int H, int W, int C) {
+  const unsigned cv = (unsigned)C >> 3, Wo = (unsigned)W >> 1, Ho = (unsigned)H >> 1;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += gridDim.x * blockDim.x) {
+    const unsigned v = i % cv, t1 = i / cv, j = t1 % Wo, t2 = t1 / Wo, ii = t2 % Ho, bt = t2 / Ho;
+    const long long pix = ((long long)bt * H + 2 * ii) * W + 2 * j;
+    const long long offs[4] = {0, 1, (long long)W, (long long)W + 1};
+    Vec16<bf16> xv[4], g, sk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      xv[k].load(x + (pix + offs[k]) * x_ld + v * 8);
+      if (dskip) sk[k].load(dskip + (pix + offs[k]) * dskip_ld + v * 8);
+    }
+    g.load(dy + (long long)i * 8);
+    Vec16<bf16> o[4];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      int arg = 0;
+      float best = xv[0].get(t);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const float f = xv[k].get(t);
+        if (f > best) { best = f; arg = k; }      // strict: the first maximum wins
+      }
+      const float gg = g.get(t);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k].set(t, (k == arg ? gg : 0.f) + (dskip ? sk[k].get(t) : 0.f));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k].store(dx + (pix + offs[k]) * C + v * 8);
+  }
+}
+__global__ void __launch_bounds__(256)
+copy_channels_vec_kernel(const bf16* __restrict__ src, long long src_ld, bf16* __restrict__ dst, long long dst_ld,
+                         unsigned total_vec, int C) {
+  const unsigned cv = (unsigned)C >> 3;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += gridDim.x * blockDim.x) {
+    const unsigned v = i % cv, r = i / cv;
+    *reinterpret_cast<uint4*>(dst + (long long)r * dst_ld + v * 8) =
+        *reinterpret_cast<const uint4*>(src + (long long)r * src_ld + v * 8);
+  }
+}
+
 // ---------------- latent head ----------------
 __device__ __forceinline__ float softplusf_(float a) { return a > 20.f ? a : log1pf(__expf(a)); }
 
@@ -443,6 +511,12 @@ int vvae_maxpool122_fwd(const void* x, long long x_ld, void* y, int b_t, int H, 
   if (b_t <= 0) return VVAE_OK;
   VVAE_REQUIRE(x && y && H % 2 == 0 && W % 2 == 0 && x_ld >= C, "maxpool122_fwd: bad arguments");
   const long long total = (long long)b_t * (H / 2) * (W / 2) * C;
+  if (dtype == VVAE_BF16 && C % 8 == 0 && x_ld % 8 == 0 && total / 8 < (1LL << 31) && ((uintptr_t)x % 16 == 0) &&
+      ((uintptr_t)y % 16 == 0)) {
+    maxpool_fwd_vec_kernel<<<ew_blocks(total / 8), 256, 0, as_stream(stream)>>>((const bf16*)x, x_ld, (bf16*)y,
+                                                                               (unsigned)(total / 8), H, W, C);
+    return check_launch("maxpool_fwd");
+  }
   VVAE_DISPATCH_DTYPE(dtype, T, (maxpool_fwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
                                     (const T*)x, x_ld, (T*)y, total, H, W, C)));
   return check_launch("maxpool_fwd");
@@ -453,6 +527,13 @@ int vvae_maxpool122_bwd(const void* x, long long x_ld, const void* dy, const voi
   if (b_t <= 0) return VVAE_OK;
   VVAE_REQUIRE(x && dy && dx && H % 2 == 0 && W % 2 == 0 && x_ld >= C, "maxpool122_bwd: bad arguments");
   const long long total = (long long)b_t * (H / 2) * (W / 2) * C;
+  if (dtype == VVAE_BF16 && C % 8 == 0 && x_ld % 8 == 0 && total / 8 < (1LL << 31) && ((uintptr_t)x % 16 == 0) &&
+      ((uintptr_t)dy % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
+      (!dskip || (dskip_ld % 8 == 0 && ((uintptr_t)dskip % 16 == 0)))) {
+    maxpool_bwd_vec_kernel<<<ew_blocks(total / 8), 256, 0, as_stream(stream)>>>(
+        (const bf16*)x, x_ld, (const bf16*)dy, (const bf16*)dskip, dskip_ld, (bf16*)dx, (unsigned)(total / 8), H, W, C);
+    return check_launch("maxpool_bwd");
+  }
   VVAE_DISPATCH_DTYPE(dtype, T, (maxpool_bwd_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
                                     (const T*)x, x_ld, (const T*)dy, (const T*)dskip, dskip_ld, (T*)dx, total, H, W, C)));
   return check_launch("maxpool_bwd");
@@ -463,6 +544,12 @@ int vvae_copy_channels(const void* src, long long src_ld, long long src_off, voi
   if (rows <= 0 || C <= 0) return VVAE_OK;
   VVAE_REQUIRE(src && dst, "copy_channels: null pointer");
   const long long total = rows * C;
+  if (dtype == VVAE_BF16 && C % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0 && src_off % 8 == 0 && dst_off % 8 == 0 &&
+      total / 8 < (1LL << 31) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
+    copy_channels_vec_kernel<<<ew_blocks(total / 8), 256, 0, as_stream(stream)>>>(
+        (const bf16*)src + src_off, src_ld, (bf16*)dst + dst_off, dst_ld, (unsigned)(total / 8), C);
+    return check_launch("copy_channels");
+  }
   VVAE_DISPATCH_DTYPE(dtype, T, (copy_channels_kernel<T><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
                                     (const T*)src, src_ld, src_off, (T*)dst, dst_ld, dst_off, total, C)));
   return check_launch("copy_channels");

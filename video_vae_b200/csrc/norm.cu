@@ -368,18 +368,15 @@ qknorm_rope_fwd_hd64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out
     uint4 xv[UR], cv[UR], sv[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
-      const long long row = row0 + u * rstride;
-      if (row < rows) {
-        const int pos = (int)((row / pos_div) % pos_mod);
-        xv[u] = *reinterpret_cast<const uint4*>(qkv + row * in_ld + c * 8);
-        cv[u] = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
-        sv[u] = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
-      }
+      const long long row = min(row0 + u * rstride, rows - 1);   // tail rows are recomputed, never stored twice
+      const int pos = (int)(((unsigned)row / (unsigned)pos_div) % (unsigned)pos_mod);   // 32-bit: rows < 2^31 (host check)
+      xv[u] = *reinterpret_cast<const uint4*>(qkv + row * in_ld + c * 8);
+      cv[u] = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+      sv[u] = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
     }
 #pragma unroll
-    for (int u = 0; u < UR; ++u) {
+    for (int u = 0; u < UR; ++u) {               // straight-line: no divergence around the shuffles
       const long long row = row0 + u * rstride;
-      if (row >= rows) break;                    // uniform across the warp (a warp stays inside one row)
       float f[8];
       const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
 #pragma unroll
@@ -396,20 +393,25 @@ qknorm_rope_fwd_hd64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out
       const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
       uint32_t xn[4], xp[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) xn[t] = bf_pack((f[2 * t] - mu) * r * sc[2 * t], (f[2 * t + 1] - mu) * r * sc[2 * t + 1]);
+      for (int t = 0; t < 4; ++t)
+        xn[t] = bf_pack((f[2 * t] - mu) * (r * sc[2 * t]), (f[2 * t + 1] - mu) * (r * sc[2 * t + 1]));
 #pragma unroll
       for (int t = 0; t < 4; ++t) xp[t] = __shfl_xor_sync(0xffffffffu, xn[t], 4);
       const uint32_t cw[4] = {cv[u].x, cv[u].y, cv[u].z, cv[u].w}, sw_[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
       uint32_t yo[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        // y = x*cos + rotate_half(x)*sin, rotate_half(x) = [-x2, x1]; every product is rounded to bf16 like the reference
-        const float a0 = bf_round(bf_lo(xn[t]) * bf_lo(cw[t])), a1 = bf_round(bf_hi(xn[t]) * bf_hi(cw[t]));
-        const float p0 = second ? bf_lo(xp[t]) : -bf_lo(xp[t]), p1 = second ? bf_hi(xp[t]) : -bf_hi(xp[t]);
-        const float b0 = bf_round(p0 * bf_lo(sw_[t])), b1 = bf_round(p1 * bf_hi(sw_[t]));
-        yo[t] = bf_pack(a0 + b0, a1 + b1);
+        // y = x*cos + rotate_half(x)*sin, rotate_half(x) = [-x2, x1].  The reference does this in bf16 (each product and
+        // the sum rounded to bf16): exactly what the packed bf16 multiply / add instructions compute.
+        const uint32_t rot = second ? xp[t] : (xp[t] ^ 0x80008000u);
+        const __nv_bfloat162 a2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&xn[t]),
+                                          *reinterpret_cast<const __nv_bfloat162*>(&cw[t]));
+        const __nv_bfloat162 b2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&rot),
+                                          *reinterpret_cast<const __nv_bfloat162*>(&sw_[t]));
+        const __nv_bfloat162 y2 = __hadd2(a2, b2);
+        yo[t] = *reinterpret_cast<const uint32_t*>(&y2);
       }
-      *reinterpret_cast<uint4*>(out + row * out_ld + c * 8) = make_uint4(yo[0], yo[1], yo[2], yo[3]);
+      if (row < rows) *reinterpret_cast<uint4*>(out + row * out_ld + c * 8) = make_uint4(yo[0], yo[1], yo[2], yo[3]);
     }
   }
 }
@@ -437,21 +439,19 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
     uint4 xv_[UR], gv_[UR], cv_[UR], sv_[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
-      const long long row = row0 + u * rstride;
-      if (row < rows) {
-        const int pos = (int)((row / pos_div) % pos_mod);
-        const long long off = row * ld + c * 8;
-        xv_[u] = *reinterpret_cast<const uint4*>(qkv + off);
-        gv_[u] = *reinterpret_cast<const uint4*>(dqkv + off);
-        cv_[u] = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
-        sv_[u] = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
-      }
+      const long long row = min(row0 + u * rstride, rows - 1);
+      const int pos = (int)(((unsigned)row / (unsigned)pos_div) % (unsigned)pos_mod);
+      const long long off = row * ld + c * 8;
+      xv_[u] = *reinterpret_cast<const uint4*>(qkv + off);
+      gv_[u] = *reinterpret_cast<const uint4*>(dqkv + off);
+      cv_[u] = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+      sv_[u] = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
     }
 #pragma unroll
-    for (int u = 0; u < UR; ++u) {
+    for (int u = 0; u < UR; ++u) {               // straight-line: tail rows are computed but contribute / store nothing
       const long long row = row0 + u * rstride;
-      if (row >= rows) break;
-      const long long off = row * ld + c * 8;
+      const bool live = row < rows;
+      const long long off = min(row, rows - 1) * ld + c * 8;
       const uint4 xv = xv_[u], gv = gv_[u], cv = cv_[u], sv = sv_[u];
       const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
       const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
@@ -483,7 +483,7 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
         g[t] = d[t] * sc[t];
         sg += g[t];
         sgx = fmaf(g[t], xh[t], sgx);
-        ps[t] = fmaf(d[t], xh[t], ps[t]);
+        if (live) ps[t] = fmaf(d[t], xh[t], ps[t]);
       }
 #pragma unroll
       for (int o = 1; o < 8; o <<= 1) {
@@ -496,10 +496,12 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         o4[t] = bf_pack(r * (g[2 * t] - sg - xh[2 * t] * sgx), r * (g[2 * t + 1] - sg - xh[2 * t + 1] * sgx));
-        pb[2 * t] += bf_lo(o4[t]);               // sum of the ROUNDED outputs, as a separate column-sum pass would see them
-        pb[2 * t + 1] += bf_hi(o4[t]);
+        if (dbias && live) {                     // sum of the ROUNDED outputs, as a column-sum pass sees them
+          pb[2 * t] += bf_lo(o4[t]);
+          pb[2 * t + 1] += bf_hi(o4[t]);
+        }
       }
-      *reinterpret_cast<uint4*>(dqkv + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      if (live) *reinterpret_cast<uint4*>(dqkv + off) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
     }
   }
   if (dbias) {
@@ -993,7 +995,7 @@ int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, co
   if (rows <= 0) return VVAE_OK;
   VVAE_REQUIRE(qkv && qk_out && q_scale && k_scale && cos_tab && sin_tab, "qknorm_rope_fwd: null pointer");
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_fwd: bad hd=%d", hd);
-  if (qk_fast_ok(dtype, heads, hd, qkv, qk_out, cos_tab, sin_tab)) {
+  if (qk_fast_ok(dtype, heads, hd, qkv, qk_out, cos_tab, sin_tab) && rows < (1LL << 31) && pos_div < (1LL << 31)) {
     const int rpi = 256 / (16 * heads);
     static int occ_grid = 0;
     if (!occ_grid) occ_grid = resident_grid(qknorm_rope_fwd_hd64_kernel, 256, 0, 1 << 30);
@@ -1018,7 +1020,7 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
   if (rows <= 0) return VVAE_OK;
   VVAE_REQUIRE(dqkv && qkv && q_scale && k_scale && cos_tab && sin_tab, "qknorm_rope_bwd: null pointer");
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_bwd: bad hd=%d", hd);
-  if (qk_fast_ok(dtype, heads, hd, qkv, dqkv, cos_tab, sin_tab)) {
+  if (qk_fast_ok(dtype, heads, hd, qkv, dqkv, cos_tab, sin_tab) && rows < (1LL << 31) && pos_div < (1LL << 31)) {
     const int rpi = 256 / (16 * heads);
     static int occ_grid = 0;
     if (!occ_grid) occ_grid = resident_grid(qknorm_rope_bwd_hd64_kernel, 256, 0, 1 << 30);
