@@ -132,6 +132,37 @@ class GradAllReducer:
             F_._grad_hooks.remove(self._on_grads_ready)
 
 
+class SplitAllReduce:
+    """Gradient all-reduce for the graph-captured step: the decoder's slice of the flat gradient is reduced on a side
+    stream as soon as the graph's ``decoder_done`` event fires (while the encoder's backward still runs inside the
+    graph); the rest (encoder + fill token) follows the graph.  Parameters are laid out encoder | decoder | fill_token
+    (``model.parameters()`` order), so both parts are contiguous slices."""
+
+    def __init__(self, flat: FlatParams, model, process_group=None):
+        self.flat, self.pg = flat, process_group
+        ids = {id(p) for p in model.decoder.parameters()}
+        idx = [i for i, p in enumerate(flat.params) if id(p) in ids]
+        assert idx and idx == list(range(idx[0], idx[-1] + 1)), "decoder parameters must be contiguous in the flat buffer"
+        self.lo = flat.offsets[idx[0]]
+        self.hi = flat.offsets[idx[-1] + 1] if idx[-1] + 1 < len(flat.params) else flat.total
+        self.stream = torch.cuda.Stream()
+
+    def __call__(self, decoder_done_event):
+        """Call right after graph.replay() was enqueued on the current stream."""
+        g = self.flat.grad
+        works = []
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(decoder_done_event)
+            works.append(dist.all_reduce(g[self.lo:self.hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if self.lo > 0:
+            works.append(dist.all_reduce(g[:self.lo], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if self.hi < self.flat.total:
+            works.append(dist.all_reduce(g[self.hi:], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+
 class FlatAdam:
     """optax.chain(clip_by_global_norm(clip), adam(lr)) on the flat buffers (train/rl_nonadversarial.py:241-253):
     one reduction kernel + one update kernel per step, no host synchronisation."""

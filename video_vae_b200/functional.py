@@ -23,6 +23,7 @@ from ._ffi import EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, require_device
 _shadow_cache = {}  # id(param) -> (weakref(param), version, data_ptr, shadow tensor)
 _flat_shadow_views = {}  # id(param) -> bf16 view into FlatParams.shadow (ddp.FlatParams.enable_bf16_shadow)
 _grad_hooks = []  # callables(list_of_params) invoked after a backward Function has finished writing their grads
+_decoder_done_hooks = []  # callables() invoked when backward reaches the latent: every decoder gradient is written
 
 
 def shadow(p, dtype):
@@ -412,6 +413,8 @@ class ReparamGateFn(Function):
 
     @staticmethod
     def backward(ctx, dc32, dcT):
+        for h in _decoder_done_hooks:      # the decoder's backward (incl. its first Linear) has been enqueued
+            h()
         mean, logvar, sel, fill, eps = ctx.saved_tensors
         if dcT is None and dc32 is None:
             return (None,) * 8

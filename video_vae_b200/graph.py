@@ -18,7 +18,7 @@ from .losses import DEFAULT_HPARAMS, loss_fn
 class GraphedTrainStep:
     """fwd + loss + bwd of ``model`` on a fixed (batch, frames, size) shape as one CUDA graph."""
 
-    def __init__(self, model, flat, video_like, mask_like, hparams=None, warmup=2, reducer=None):
+    def __init__(self, model, flat, video_like, mask_like, hparams=None, warmup=2, reducer=None, mark_decoder_done=False):
         """reducer: an optional ddp.GradAllReducer.  Its bucketed NCCL all-reduces are then captured INSIDE the graph on
         the reducer's side stream (fork after a bucket's last gradient kernel, join before the graph ends), so the
         gradient exchange overlaps the rest of backward exactly as in eager mode."""
@@ -38,6 +38,9 @@ class GraphedTrainStep:
         ops.philox_fill_(self.noise, 0, 1 << 40, "normal")
         ops.philox_fill_(self.gumbel_u, 0, 2 << 40, "uniform")
         self.graph = torch.cuda.CUDAGraph()
+        # external event recorded INSIDE the graph when backward reaches the latent (all decoder gradients written): a
+        # communication stream can start reducing the decoder's gradients while the encoder's backward still runs
+        self.decoder_done = torch.cuda.Event(external=True) if mark_decoder_done else None
         self.loss = None
         self.aux = None
         prof, ops.PROFILE = ops.PROFILE, None            # event timing cannot be captured
@@ -50,8 +53,16 @@ class GraphedTrainStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             F_.invalidate_shadows()                      # every derived weight image is rebuilt INSIDE the graph
-            with torch.cuda.graph(self.graph):
-                self.loss, self.aux = self._body()
+            hook = None
+            if self.decoder_done is not None:
+                hook = lambda: self.decoder_done.record(torch.cuda.current_stream())   # noqa: E731
+                F_._decoder_done_hooks.append(hook)
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.loss, self.aux = self._body()
+            finally:
+                if hook is not None:
+                    F_._decoder_done_hooks.remove(hook)
         finally:
             ops.PROFILE = prof
 
