@@ -210,3 +210,70 @@ def test_oracle_reproduces_committed_golden_fixture():
             ref = np.asarray(gold[key], dtype=np.float64)
             got = np.asarray(now[key], dtype=np.float64)
             assert np.allclose(got, ref, rtol=2e-4, atol=2e-5 * max(1e-6, np.abs(ref).max())), key
+
+
+def test_optimizer_oracle_matches_torch_adam_with_global_norm_clip():
+    """oracle/optim.ClipAdam restates optax.chain(clip_by_global_norm, adam) (rl_nonadversarial.py:248-251); pin it
+    against torch.optim.Adam (same bias-corrected update, eps outside the sqrt) + clip_grad_norm_."""
+    from oracle.optim import ClipAdam
+    g = torch.Generator().manual_seed(0)
+    shapes = [(7, 5), (13,), (3, 3, 3)]
+    p_o = [torch.randn(s, generator=g) for s in shapes]
+    p_t = [torch.nn.Parameter(p.clone()) for p in p_o]
+    opt_o = ClipAdam(p_o, lr=1e-2, clip=1.0)
+    opt_t = torch.optim.Adam(p_t, lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    for step in range(6):
+        scale = 3.0 if step % 2 == 0 else 0.05                   # clip active on even steps, inactive on odd ones
+        grads = [torch.randn(s, generator=g) * scale for s in shapes]
+        gn = opt_o.step([x.clone() for x in grads])
+        for p, x in zip(p_t, grads):
+            p.grad = x.clone()
+        torch.nn.utils.clip_grad_norm_(p_t, 1.0)                 # torch adds 1e-6 to the norm: tolerance below
+        opt_t.step()
+        assert (gn > 1.0) == (step % 2 == 0)
+        for a, b in zip(p_o, p_t):
+            assert torch.allclose(a, b.detach(), rtol=1e-4, atol=1e-6)
+
+
+def test_warmup_cosine_schedule_known_points():
+    """optax.warmup_cosine_decay_schedule(0, peak, warmup, decay, peak/10) (rl_nonadversarial.py:241-247): closed-form
+    points, and the host implementation the product uses must agree with the oracle everywhere."""
+    import importlib.util
+    import math
+    import os
+    from oracle.optim import warmup_cosine_decay_schedule as o_sched
+    spec = importlib.util.spec_from_file_location(
+        "vvae_optim", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "video_vae_b200", "optim.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    peak, warm, decay = 2e-5, 20000 // math.sqrt(2), 1_000_000
+    so, sp = o_sched(0.0, peak, warm, decay, peak / 10), mod.reference_schedule(2)
+    assert so(0) == 0.0 and abs(so(warm / 2) - peak / 2) < 1e-12 and abs(so(warm) - peak) < 1e-12
+    mid = warm + (decay - warm) / 2
+    assert abs(so(mid) - peak * (0.9 * 0.5 + 0.1)) < 1e-12
+    assert abs(so(decay) - peak / 10) < 1e-12 and abs(so(10 * decay) - peak / 10) < 1e-12
+    for c in (0, 1, 17, warm - 1, warm, warm + 1, 12345, 500000, decay, decay + 5):
+        assert so(c) == sp(c)
+
+
+def test_rl_model_variant_shapes_and_binary_keep_mask():
+    """claude_distributed/test_rl_model.py Tests 1-3 on the oracle's rl_model restatement: encoder selection is a
+    probability of shape (b, t, 1); the VAE doubles the batch, the keep-mask is binary, 6 outputs."""
+    from oracle import Rngs
+    from oracle.rl_model import Encoder, VideoVAE
+    B, T, H = 2, 4, 64
+    enc = Encoder(H, H, 3, 16, 2, 256, 4, 128, 32, 8, Rngs(42))
+    x = torch.randn(B, T, H, H, 3, generator=torch.Generator().manual_seed(0)) * 0.02
+    mask = torch.ones(B, 1, 1, T, dtype=torch.bool)
+    mean, logvar, sel = enc(x, mask, Rngs(0), train=True)
+    assert mean.shape == (B, T, 16, 96) and logvar.shape == mean.shape and sel.shape == (B, T, 1)
+    assert (sel > 0).all() and (sel < 1).all()
+    vae = VideoVAE(H, H, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4, Rngs(42))
+    recon, comp, s, smask, lv, mu = vae(x, mask, Rngs(42), train=True)
+    assert recon.shape == (2 * B, T, H, H, 3) and comp.shape == (2 * B, T, 16, 96)
+    assert s.shape == (2 * B, T, 1, 1) and smask.shape == (2 * B, T, 1, 1) and lv.shape == mu.shape == comp.shape
+    assert set(smask.unique().tolist()) <= {0.0, 1.0}
+    assert torch.equal(mu[0], mu[1]) and torch.equal(s[2], s[3])            # 'b ... -> (b 2) ...': copies are adjacent
+    recon.square().mean().backward()
+    g = vae.encoder.spatial_compression.kernel.grad
+    assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0

@@ -175,10 +175,13 @@ class FlatAdam:
         self.t = 0
 
     def step(self, grad_scale=1.0, lr=None):
+        """``self.lr`` may be a float or a schedule ``count -> lr`` (count = 0 for the first update, as in optax)."""
+        if lr is None:
+            lr = self.lr(self.t) if callable(self.lr) else self.lr
         self.t += 1
         ops.fill_(self.gnorm_sq, 0.0)
         ops.sumsq_accum(self.flat.grad, self.gnorm_sq)
-        ops.adam_step_(self.flat.flat, self.flat.grad, self.m, self.v, self.lr if lr is None else lr, self.b1, self.b2,
+        ops.adam_step_(self.flat.flat, self.flat.grad, self.m, self.v, float(lr), self.b1, self.b2,
                        self.eps, self.t, self.gnorm_sq, self.clip, grad_scale)
         if self.flat.shadow is not None:
             self.flat.refresh_shadow()

@@ -333,7 +333,8 @@ class UnembedFn(Function):
 # ------------------------------------------------------------------ encoder head, reparameterisation, loss
 class EncoderHeadFn(Function):
     """mean / log-variance heads and the Gumbel-sigmoid frame gate (train/model.py:53-59, train/layers.py:238-252).
-    Returns (mean [b,t,hw,Dl], logvar, selection [b,t,1,1] fp32)."""
+    Returns (mean [b,t,hw,Dl], logvar, selection [b,t,1,1] fp32).  ``train`` = False / True, or the string "prob" for
+    the rl_model variant (train/rl_model.py:59): selection = sigmoid(logit) itself, no Gumbel noise, no rounding."""
 
     @staticmethod
     def forward(ctx, x, dtype, train, temperature, u, seed, offset, wm, bm, wv, bv, w1, b1, w2, b2):
@@ -346,8 +347,11 @@ class EncoderHeadFn(Function):
         s1 = ops.gemm(mean, shadow(w1, dtype), bias=b1.detach())                  # [N,1]
         if w2.shape[0] != hw:
             raise ValueError(f"selection_layer2 expects {w2.shape[0]} spatial tokens, got {hw}")
-        logit, p, sel = ops.selection_fwd(s1, w2.detach().reshape(-1), b2.detach(), u, seed, offset, train, temperature,
-                                          b * t, hw)
+        prob_mode = train == "prob"
+        logit, p, sel = ops.selection_fwd(s1, w2.detach().reshape(-1), b2.detach(), u, seed, offset,
+                                          False if prob_mode else train, temperature, b * t, hw)
+        if prob_mode:
+            sel = p
         ctx.save_for_backward(x2, mean, a, s1, p, wm, bm, wv, bv, w1, b1, w2, b2)
         ctx.dtype, ctx.train, ctx.temperature, ctx.shape = dtype, train, temperature, (b, t, hw, D)
         Dl = wm.shape[1]
