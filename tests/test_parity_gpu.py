@@ -617,3 +617,24 @@ def test_rl_model_variant_matches_oracle_fp32(V):
     # Philox-driven draws: runs, binary mask, doubled batch
     r2 = m(x.cuda(), mask.cuda(), V.Rngs(7), train=True)
     assert r2[0].shape == (2 * b, t, 64, 64, 3) and set(r2[3].unique().tolist()) <= {0.0, 1.0}
+
+
+def test_encode_latents_driver_matches_oracle_encoder(V, tmp_path):
+    """Config-3 style encode-only loop (video_vae_b200/encode.py, shaped like data_prep/save_latents.py:183-206): chunked,
+    no-grad, eval mode; latents equal the oracle Encoder's (fp32) and the saved file round-trips."""
+    from oracle import Rngs as ORngs
+    from video_vae_b200.encode import save_latents
+    m, o = _small_pair(V, torch.float32)
+    g = _gen(17)
+    clips = torch.rand(5, 4, 64, 64, 3, generator=g)
+    mask = torch.ones(5, 4, dtype=torch.bool)
+    mask[3, 2:] = False
+    out = save_latents(m, clips, str(tmp_path / "lat.pt"), mask=mask, chunk=2)        # ragged last chunk
+    from oracle.losses import expand_mask
+    with torch.no_grad():
+        mean_o, lv_o, sel_o = o.encoder(clips, expand_mask(mask, 16), ORngs(0), train=False)
+    assert out["latents"].shape == (5, 4, 16, 96)
+    assert rel_err(out["latents"], mean_o) < FP32_TOL and rel_err(out["log_variance"], lv_o) < FP32_TOL
+    assert torch.equal(out["selection"], sel_o.reshape(5, 4))
+    back = torch.load(str(tmp_path / "lat.pt"))
+    assert torch.equal(back["latents"], out["latents"])
