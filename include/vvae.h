@@ -243,6 +243,12 @@ int vvae_reparam_gate_bwd(const void* dc, const void* mean, const void* logvar, 
 int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
                         const float* inv_len, float* out2, int B, int T, long long per_frame, int dtype,
                         vvae_stream_t stream);
+/* Per-sample form of the above for the RL loss (train/rl_nonadversarial.py:114-121,161): out_b2 fp32 [B,2],
+ * out_b2[b,0] += sum_p round_T(sum_t e^2) * inv_len[b], out_b2[b,1] the same with |e|.  (A per-sample upstream gradient
+ * g[b] is applied in vvae_recon_loss_bwd by passing inv_len[b]*g[b].) */
+int vvae_recon_loss_per_sample_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
+                                   const float* inv_len, float* out_b2, int B, int T, long long per_frame, int dtype,
+                                   vvae_stream_t stream);
 /* drecon[b,t,p] = -(2*w_mse*e + w_mae*sign(e)) * m[b,t] * inv_len[b] * inv_count * (*gscale), e = (video-recon)*m.
  * gscale: optional DEVICE fp32 scalar (the upstream d(loss); NULL = 1) so the step never synchronises with the host. */
 int vvae_recon_loss_bwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
@@ -252,6 +258,10 @@ int vvae_recon_loss_bwd(const void* video, int video_dtype, const void* recon, c
 /* out1[0] += sum 0.5*(exp(lv)-1-lv+mean^2) * frame_w[frame], frame_w = m/len   (caller divides by numel). */
 int vvae_kl_fwd(const void* mean, const void* logvar, const float* frame_w, float* out1, long long n_tok,
                 int tok_per_frame, int Dl, int dtype, vvae_stream_t stream);
+/* Per-sample KL (train/rl_nonadversarial.py:145-146): out_b fp32 [B], out_b[b] += sum over the sample's tok_per_sample
+ * tokens.  (Per-sample upstream gradients go through frame_w in vvae_kl_bwd.) */
+int vvae_kl_per_sample_fwd(const void* mean, const void* logvar, const float* frame_w, float* out_b, int B,
+                           long long tok_per_sample, int tok_per_frame, int Dl, int dtype, vvae_stream_t stream);
 /* dmean = s*frame_w[frame]*mean ; dlogvar = s*frame_w[frame]*0.5*(exp(lv)-1), s = scale * (*gscale)  (gscale: optional
  * device scalar, NULL = 1; scale = gamma2 / numel). */
 int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, const float* gscale, void* dmean,

@@ -277,3 +277,76 @@ def test_rl_model_variant_shapes_and_binary_keep_mask():
     recon.square().mean().backward()
     g = vae.encoder.spatial_compression.kernel.grad
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
+
+
+def test_rl_loss_training_loop_checks():
+    """claude_distributed/test_training_loop.py Tests 1, 3, 4 (64x64, P16, 2/2, mlp 256, 4 heads, qkv 128, scr 4, up 2,
+    t=8, lr 1e-3, gamma3=0 with a zero perceptual term) on the oracle restatement of rl_nonadversarial.py:100-186:
+    finite positive loss and aux, finite non-zero gradients, loss decreasing over 10 clip+Adam steps."""
+    from oracle import Rngs
+    from oracle.optim import ClipAdam
+    from oracle.rl_losses import loss_fn
+    from oracle.rl_model import VideoVAE
+    hp = {"gamma1": 0.2, "gamma2": 0.001, "gamma3": 0.0, "gamma4": 0.05, "max_compression_rate": 2,
+          "magnify_negatives_rate": 100, "rl_loss_weight": 0.01}
+    vae = VideoVAE(64, 64, 3, 16, 2, 2, 256, 4, 128, 16, 4, 2, Rngs(42))
+    g = torch.Generator().manual_seed(0)
+    B, T = 2, 8
+    video = torch.randn(B, T, 64, 64, 3, generator=g) * 0.1
+    mask = torch.ones(B, T, dtype=torch.bool)
+    zero_perceptual = lambda params, x, target: torch.zeros(x.shape[0])       # noqa: E731  dummy_perceptual (:81-82)
+    loss, aux = loss_fn(vae, video, mask[:, None, None, :], mask, Rngs(1), hp, zero_perceptual, None)
+    assert torch.isfinite(loss) and loss > 0
+    for k in ("MSE", "selection_loss", "kl_loss", "rl_loss", "per_sample_MAE", "kept_frame_density",
+              "mean_trajectory_prob"):
+        assert torch.isfinite(aux[k]), k
+    # normalised probs are 1 in value: the RL term is the mean disadvantage, which is 0 for every pair
+    assert abs(float(aux["rl_loss"].detach())) < 1e-5
+    loss.backward()
+    grads = [p.grad for p in vae.parameters() if p.grad is not None]
+    assert all(torch.isfinite(x).all() for x in grads) and max(float(x.abs().max()) for x in grads) > 0
+    # the gate logits get gradient only through the trajectory-probability term
+    assert vae.encoder.selection_layer2.kernel.grad.abs().max() > 0
+    params = [p for p in vae.parameters()]
+    opt = ClipAdam(params, lr=1e-3, clip=1.0)
+    losses = []
+    for step in range(10):
+        for p in params:
+            p.grad = None
+        loss, _ = loss_fn(vae, video, mask[:, None, None, :], mask, Rngs(step + 100), hp, zero_perceptual, None)
+        loss.backward()
+        opt.step([p.grad if p.grad is not None else torch.zeros_like(p) for p in params])
+        losses.append(float(loss))
+    assert sum(losses[5:]) < sum(losses[:5]), losses
+
+
+def test_rl_loss_pairwise_terms_hand_checked():
+    """rl_nonadversarial.py:149-174 on a hand-sized case: disadvantages of a pair are +-1 (population std), the gradient
+    of the RL term w.r.t. a frame's keep-probability is weight * disadvantage * sign / P(action) / (b*2), masked frames
+    and clipped probabilities get none."""
+    from oracle.rl_losses import loss_terms
+    hp = {"gamma1": 0.0, "gamma2": 0.0, "gamma3": 0.0, "gamma4": 0.0, "max_compression_rate": 2,
+          "magnify_negatives_rate": 100, "rl_loss_weight": 0.5}
+    b, t = 1, 3
+    video = torch.zeros(b, t, 2, 2, 1)
+    recon = torch.zeros(2 * b, t, 2, 2, 1)
+    recon[0] += 1.0                                                    # sample 0 is worse than its twin
+    sel = torch.tensor([0.3, 0.6, 0.0]).repeat(2, 1).reshape(2, t, 1, 1).requires_grad_()
+    smask = torch.tensor([[1.0, 0.0, 1.0], [0.0, 1.0, 1.0]]).reshape(2, t, 1, 1)
+    mask = torch.tensor([[True, True, True]])
+    lv = torch.zeros(2, t, 1, 4)
+    loss, aux = loss_terms(video, recon, sel, smask, lv, lv.clone(), mask, hp)
+    assert abs(float(aux["MSE"]) - 0.5) < 1e-6 and abs(float(loss) - 0.5) < 1e-5
+    loss.backward()
+    gsel = sel.grad.reshape(2, t)
+    w = 0.5 / 2
+    # sample 0 (disadvantage +1): kept frame 0 (P=0.3, d/dp=+1), dropped frame 1 (P=0.4, d/dp=-1), frame 2 clipped
+    exp0 = torch.tensor([w / 0.3, -w / 0.4, 0.0])
+    exp1 = torch.tensor([-w * -1 / 0.7, -w / 0.6, 0.0])               # disadvantage -1: dropped (P=.7), kept (P=.6)
+    assert torch.allclose(gsel[0], exp0, rtol=1e-4, atol=1e-6), gsel
+    assert torch.allclose(gsel[1], exp1, rtol=1e-4, atol=1e-6), gsel
+    # a masked frame contributes nothing
+    sel2 = sel.detach().clone().requires_grad_()
+    loss2, _ = loss_terms(video, recon, sel2, smask, lv, lv.clone(), torch.tensor([[True, False, True]]), hp)
+    loss2.backward()
+    assert float(sel2.grad.reshape(2, t)[:, 1].abs().max()) == 0.0

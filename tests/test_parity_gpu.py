@@ -619,6 +619,76 @@ def test_rl_model_variant_matches_oracle_fp32(V):
     assert r2[0].shape == (2 * b, t, 64, 64, 3) and set(r2[3].unique().tolist()) <= {0.0, 1.0}
 
 
+def test_rl_loss_matches_oracle_fp32(V):
+    """the RL training loss (video_vae_b200.rl_losses, rl_nonadversarial.py:100-186) against its oracle
+    restatement with injected draws, fp32: loss, every aux term, per-sample losses and all parameter gradients
+    (including the gate logits, reached only through the trajectory-probability term), ragged masks."""
+    from oracle import Rngs as ORngs
+    from oracle.rl_losses import loss_fn as o_loss_fn
+    from oracle.rl_model import VideoVAE as ORL
+    from video_vae_b200.rl_losses import DEFAULT_HPARAMS, loss_fn
+    from video_vae_b200.rl_model import VideoVAE as RL
+    cfg = (64, 64, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4)
+    o = ORL(*cfg, ORngs(2))
+    with torch.no_grad():
+        o.decoder.unet.final_conv.kernel.copy_(torch.randn(o.decoder.unet.final_conv.kernel.shape, generator=_gen(5)) * 0.05)
+    m = RL(*cfg, V.Rngs(2), dtype=torch.float32)
+    _copy_params(m, o)
+    g = _gen(21)
+    b, t = 3, 4
+    x = torch.rand(b, t, 64, 64, 3, generator=g)
+    mask = torch.ones(b, t, dtype=torch.bool)
+    mask[1, 3:] = False
+    mask[2, 1:] = False
+    noise = torch.randn(b, t, 16, 96, generator=g)
+    bu = torch.rand(2 * b, t, 1, 1, generator=g)
+    hp = dict(DEFAULT_HPARAMS, gamma3=0.0, rl_loss_weight=0.5)
+    lo, ao = o_loss_fn(o, x, mask[:, None, None, :], mask, ORngs(0), hp, None, None, noise=noise, bernoulli_u=bu)
+    lm, am = loss_fn(m, x.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), hp, None, None,
+                     noise=noise.cuda(), bernoulli_u=bu.cuda())
+    assert abs(float(lm) - float(lo)) <= FP32_TOL * abs(float(lo)) + 1e-7
+    for k in ("MSE", "per_sample_MAE", "selection_loss", "kl_loss", "kept_frame_density", "mean_trajectory_prob"):
+        assert abs(float(am[k]) - float(ao[k])) <= FP32_TOL * abs(float(ao[k])) + 1e-7, k
+    assert rel_err(am["per_sample_loss"], ao["per_sample_loss"]) < FP32_TOL
+    lo.backward()
+    lm.backward()
+    _grads_close(m, o, 1e-3, min_checked=100)
+    ga, gb = m.encoder.selection_layer2.kernel.grad, o.encoder.selection_layer2.kernel.grad
+    assert gb.abs().max() > 0 and rel_err(ga, gb) < 1e-3
+    # a caller-supplied perceptual term participates in the loss and its gradient (stand-in for the VGG term, :125)
+    pfn = lambda params, r, v: ((r - v) ** 2).float().mean(dim=(1, 2, 3, 4)) * params            # noqa: E731
+    hp3 = dict(hp, gamma3=0.1)
+    lo3, _ = o_loss_fn(o, x, mask[:, None, None, :], mask, ORngs(0), hp3, pfn, 2.0, noise=noise, bernoulli_u=bu)
+    lm3, _ = loss_fn(m, x.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), hp3, pfn, 2.0,
+                     noise=noise.cuda(), bernoulli_u=bu.cuda())
+    assert abs(float(lm3) - float(lo3)) <= FP32_TOL * abs(float(lo3)) + 1e-7 and float(lo3) > float(lo)
+
+
+def test_rl_loss_bf16_train_step_and_loss_decrease(V):
+    """claude_distributed/test_training_loop.py Tests 2-4 through the product's train_step in bf16 on the tcgen05 path
+    (2 heads x 64): finite loss / gradients, loss decreasing over 10 clip+Adam steps on a fixed batch."""
+    from video_vae_b200.ddp import FlatAdam, FlatParams
+    from video_vae_b200.rl_losses import DEFAULT_HPARAMS, eval_step, train_step
+    from video_vae_b200.rl_model import VideoVAE as RL
+    m = RL(64, 64, 3, 16, 2, 2, 256, 2, 128, 16, 4, 2, V.Rngs(42), dtype=torch.bfloat16)
+    flat = FlatParams(m)
+    opt = FlatAdam(flat, lr=1e-3, clip=1.0)
+    g = _gen(3)
+    video = (torch.randn(2, 8, 64, 64, 3, generator=g) * 0.1).cuda()
+    mask = torch.ones(2, 8, dtype=torch.bool).cuda()
+    hp = dict(DEFAULT_HPARAMS, gamma3=0.0)
+    losses = []
+    for step in range(10):
+        flat.zero_grad()
+        loss, aux = train_step(m, video, mask, hp, V.Rngs(step + 100))
+        assert torch.isfinite(loss) and torch.isfinite(flat.grad).all() and flat.grad.abs().max() > 0
+        opt.step()
+        losses.append(float(loss))
+    assert sum(losses[5:]) < sum(losses[:5]), losses
+    le, ae = eval_step(m, video, mask, hp, V.Rngs(1))
+    assert torch.isfinite(le) and ae["reconstruction"].shape == (4, 8, 64, 64, 3)
+
+
 def test_encode_latents_driver_matches_oracle_encoder(V, tmp_path):
     """Config-3 style encode-only loop (video_vae_b200/encode.py, shaped like data_prep/save_latents.py:183-206): chunked,
     no-grad, eval mode; latents equal the oracle Encoder's (fp32) and the saved file round-trips."""

@@ -345,18 +345,19 @@ __global__ void reparam_gate_bwd_kernel(const T* __restrict__ dc, const T* __res
 
 // ---------------- losses ----------------
 // one thread per (b, p) position: time-sum in fp32, rounded to T (XLA reduces bf16 with fp32 accumulation), / len.
-template <typename TV, typename T>
+// PS (per-sample, rl_nonadversarial.py:114-121): blockIdx.y is the sample, out2 is [B,2].
+template <typename TV, typename T, bool PS>
 __global__ void recon_loss_fwd_kernel(const TV* __restrict__ video, const T* __restrict__ recon,
                                       const float* __restrict__ fmask, const float* __restrict__ inv_len,
                                       float* __restrict__ out2, int B, int Tn, long long per_frame) {
   __shared__ float scratch[33];
-  const long long total = (long long)B * per_frame;
+  const long long total = PS ? per_frame : (long long)B * per_frame;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   float a_sq = 0.f, a_ab = 0.f;
   for (; i < total; i += stride) {
-    const int b = (int)(i / per_frame);
-    const long long p = i % per_frame;
+    const int b = PS ? (int)blockIdx.y : (int)(i / per_frame);
+    const long long p = PS ? i : i % per_frame;
     float ssq = 0.f, sab = 0.f;
     for (int t = 0; t < Tn; ++t) {
       const float m = fmask[b * Tn + t];
@@ -372,8 +373,9 @@ __global__ void recon_loss_fwd_kernel(const TV* __restrict__ video, const T* __r
   a_sq = block_sum(a_sq, scratch);
   a_ab = block_sum(a_ab, scratch);
   if (threadIdx.x == 0) {
-    atomicAdd(out2, a_sq);
-    atomicAdd(out2 + 1, a_ab);
+    float* o = PS ? out2 + 2 * blockIdx.y : out2;
+    atomicAdd(o, a_sq);
+    atomicAdd(o + 1, a_ab);
   }
 }
 template <typename TV, typename T>
@@ -396,21 +398,23 @@ __global__ void recon_loss_bwd_kernel(const TV* __restrict__ video, const T* __r
     drecon[i] = from_f<T>(g);
   }
 }
-template <typename T>
+// PS: blockIdx.y is the sample (n = elements per sample), out1 is [B].
+template <typename T, bool PS>
 __global__ void kl_fwd_kernel(const T* __restrict__ mean, const T* __restrict__ logvar, const float* __restrict__ frame_w,
                               float* __restrict__ out1, long long n, long long per_frame_el) {
   __shared__ float scratch[33];
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long base = PS ? blockIdx.y * n : 0;
   float acc = 0.f;
   for (; i < n; i += stride) {
-    const float w = frame_w[i / per_frame_el];
+    const float w = frame_w[(base + i) / per_frame_el];
     if (w == 0.f) continue;
-    const float mu = to_f(mean[i]), lv = to_f(logvar[i]);
+    const float mu = to_f(mean[base + i]), lv = to_f(logvar[base + i]);
     acc += round_to<T>(0.5f * (__expf(lv) - 1.f - lv + mu * mu)) * w;
   }
   acc = block_sum(acc, scratch);
-  if (threadIdx.x == 0) atomicAdd(out1, acc);
+  if (threadIdx.x == 0) atomicAdd(PS ? out1 + blockIdx.y : out1, acc);
 }
 
 template <typename T>
@@ -610,14 +614,24 @@ int vvae_reparam_gate_bwd(const void* dc, const void* mean, const void* logvar, 
   return check_launch("reparam_gate_bwd");
 }
 
-int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
-                        const float* inv_len, float* out2, int B, int T, long long per_frame, int dtype,
-                        vvae_stream_t stream) {
+static int recon_loss_fwd_impl(const void* video, int video_dtype, const void* recon, const float* frame_mask,
+                               const float* inv_len, float* out, int B, int T, long long per_frame, int dtype,
+                               bool per_sample, vvae_stream_t stream) {
   if (B <= 0) return VVAE_OK;
-  VVAE_REQUIRE(video && recon && frame_mask && inv_len && out2, "recon_loss_fwd: null pointer");
-  const int blocks = ew_blocks((long long)B * per_frame);
+  VVAE_REQUIRE(video && recon && frame_mask && inv_len && out, "recon_loss_fwd: null pointer");
+  VVAE_REQUIRE(!per_sample || B <= 65535, "recon_loss_per_sample_fwd: B > 65535");
   cudaStream_t s = as_stream(stream);
-#define RL_FWD(TV, TT) recon_loss_fwd_kernel<TV, TT><<<blocks, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask, inv_len, out2, B, T, per_frame)
+  dim3 grid(per_sample ? (unsigned)std::max(1, ew_blocks(per_frame) / std::min(B, 8)) : (unsigned)ew_blocks((long long)B * per_frame),
+            per_sample ? (unsigned)B : 1u);
+#define RL_FWD(TV, TT)                                                                                                 \
+  do {                                                                                                                 \
+    if (per_sample)                                                                                                    \
+      recon_loss_fwd_kernel<TV, TT, true><<<grid, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask, inv_len, \
+                                                               out, B, T, per_frame);                                  \
+    else                                                                                                               \
+      recon_loss_fwd_kernel<TV, TT, false><<<grid, 256, 0, s>>>((const TV*)video, (const TT*)recon, frame_mask,        \
+                                                                inv_len, out, B, T, per_frame);                        \
+  } while (0)
   if (video_dtype == VVAE_F32 && dtype == VVAE_F32) RL_FWD(float, float);
   else if (video_dtype == VVAE_F32 && dtype == VVAE_BF16) RL_FWD(float, bf16);
   else if (video_dtype == VVAE_BF16 && dtype == VVAE_BF16) RL_FWD(bf16, bf16);
@@ -625,6 +639,18 @@ int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, c
   else VVAE_REQUIRE(false, "recon_loss_fwd: bad dtypes");
 #undef RL_FWD
   return check_launch("recon_loss_fwd");
+}
+
+int vvae_recon_loss_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
+                        const float* inv_len, float* out2, int B, int T, long long per_frame, int dtype,
+                        vvae_stream_t stream) {
+  return recon_loss_fwd_impl(video, video_dtype, recon, frame_mask, inv_len, out2, B, T, per_frame, dtype, false, stream);
+}
+
+int vvae_recon_loss_per_sample_fwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
+                                   const float* inv_len, float* out_b2, int B, int T, long long per_frame, int dtype,
+                                   vvae_stream_t stream) {
+  return recon_loss_fwd_impl(video, video_dtype, recon, frame_mask, inv_len, out_b2, B, T, per_frame, dtype, true, stream);
 }
 
 int vvae_recon_loss_bwd(const void* video, int video_dtype, const void* recon, const float* frame_mask,
@@ -650,9 +676,21 @@ int vvae_kl_fwd(const void* mean, const void* logvar, const float* frame_w, floa
   if (n_tok <= 0) return VVAE_OK;
   VVAE_REQUIRE(mean && logvar && frame_w && out1, "kl_fwd: null pointer");
   const long long n = n_tok * Dl;
-  VVAE_DISPATCH_DTYPE(dtype, T, (kl_fwd_kernel<T><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
+  VVAE_DISPATCH_DTYPE(dtype, T, (kl_fwd_kernel<T, false><<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
                                     (const T*)mean, (const T*)logvar, frame_w, out1, n, (long long)tok_per_frame * Dl)));
   return check_launch("kl_fwd");
+}
+
+int vvae_kl_per_sample_fwd(const void* mean, const void* logvar, const float* frame_w, float* out_b, int B,
+                           long long tok_per_sample, int tok_per_frame, int Dl, int dtype, vvae_stream_t stream) {
+  if (B <= 0 || tok_per_sample <= 0) return VVAE_OK;
+  VVAE_REQUIRE(mean && logvar && frame_w && out_b, "kl_per_sample_fwd: null pointer");
+  VVAE_REQUIRE(B <= 65535, "kl_per_sample_fwd: B > 65535");
+  const long long n = tok_per_sample * Dl;
+  dim3 grid((unsigned)std::max(1, ew_blocks(n) / std::min(B, 8)), (unsigned)B);
+  VVAE_DISPATCH_DTYPE(dtype, T, (kl_fwd_kernel<T, true><<<grid, 256, 0, as_stream(stream)>>>(
+                                    (const T*)mean, (const T*)logvar, frame_w, out_b, n, (long long)tok_per_frame * Dl)));
+  return check_launch("kl_per_sample_fwd");
 }
 
 int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, float scale, const float* gscale, void* dmean,

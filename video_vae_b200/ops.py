@@ -403,6 +403,15 @@ def recon_loss_fwd(video, recon, frame_mask, inv_len, out2):
                                   per_frame, dt(recon), stream()), "vvae_recon_loss_fwd")
 
 
+def recon_loss_per_sample_fwd(video, recon, frame_mask, inv_len, out_b2):
+    """out_b2 fp32 [B,2] += per-sample (squared, absolute) masked error sums (RL loss, rl_nonadversarial.py:114-121)."""
+    B, T = video.shape[:2]
+    per_frame = video.numel() // (B * T)
+    check(lib.vvae_recon_loss_per_sample_fwd(ptr(video), dt(video), ptr(recon), ptr(frame_mask), ptr(inv_len),
+                                             ptr(out_b2), B, T, per_frame, dt(recon), stream()),
+          "vvae_recon_loss_per_sample_fwd")
+
+
 def recon_loss_bwd(video, recon, frame_mask, inv_len, w_mse, w_mae, inv_count, gscale=None):
     """gscale: optional fp32 device scalar multiplied in (the upstream gradient), so no host read is needed."""
     B, T = video.shape[:2]
@@ -418,6 +427,13 @@ def kl_fwd(mean, logvar, frame_w, out1, tok_per_frame):
     Dl = mean.shape[-1]
     check(lib.vvae_kl_fwd(ptr(mean), ptr(logvar), ptr(frame_w), ptr(out1), mean.numel() // Dl, tok_per_frame, Dl,
                           dt(mean), stream()), "vvae_kl_fwd")
+
+
+def kl_per_sample_fwd(mean, logvar, frame_w, out_b, tok_per_frame):
+    """out_b fp32 [B] += per-sample KL sums (rl_nonadversarial.py:145-146)."""
+    B, Dl = mean.shape[0], mean.shape[-1]
+    check(lib.vvae_kl_per_sample_fwd(ptr(mean), ptr(logvar), ptr(frame_w), ptr(out_b), B, mean.numel() // (Dl * B),
+                                     tok_per_frame, Dl, dt(mean), stream()), "vvae_kl_per_sample_fwd")
 
 
 def kl_bwd(mean, logvar, frame_w, scale, tok_per_frame, gscale=None):
