@@ -1,0 +1,141 @@
+"""Weight import / export against the reference's Flax parameter tree.
+
+The reference checkpoints ``{"model": nnx.state(model), "optimizer": nnx.state(optimizer)}`` with orbax
+(train/rl_nonadversarial.py:62-67, train/model_loader.py:35-42).  ``nnx.state`` is a nested mapping keyed by attribute
+names and list indices whose leaves are arrays (older Flax) or ``{"value": array}`` variable states (Flax >= 0.10).
+This package keeps the reference's attribute names AND Flax array layouts (Linear ``(in, out)``, Conv
+``(kt, kh, kw, Cin, Cout)``, ConvTranspose kernels as stored), so a tree converts with a flat rename: no transposes.
+
+Nothing here touches the GPU.  orbax / jax are not installable in the build image; ``load_checkpoint`` uses orbax when
+it is importable and otherwise reads the ``.npz`` transport format written by ``save_npz`` (a reference maintainer dumps
+``nnx.state(model)`` with ``save_npz(path, jax.tree.map(np.asarray, nnx.state(model).to_pure_dict()))``).
+"""
+import os
+
+import numpy as np
+import torch
+
+_VALUE_KEYS = ("value", "raw_value")
+
+
+def flatten_tree(tree, prefix=""):
+    """Nested mapping / sequence -> {dotted.path: ndarray}.  ``{"value": x}`` variable wrappers are unwrapped."""
+    out = {}
+    if isinstance(tree, dict):
+        keys = list(tree.keys())
+        if len(keys) == 1 and keys[0] in _VALUE_KEYS and not isinstance(tree[keys[0]], (dict, list, tuple)):
+            out[prefix[:-1]] = np.asarray(tree[keys[0]])
+            return out
+        for k in keys:
+            out.update(flatten_tree(tree[k], f"{prefix}{k}."))
+    elif isinstance(tree, (list, tuple)):
+        for i, v in enumerate(tree):
+            out.update(flatten_tree(v, f"{prefix}{i}."))
+    elif tree is not None:
+        out[prefix[:-1]] = np.asarray(tree)
+    return out
+
+
+def _is_rng_state(name):
+    parts = name.split(".")
+    return any(p in ("rngs", "rng", "dropout") for p in parts)
+
+
+def state_dict_from_flax(tree, model, strict=True):
+    """Flax parameter tree (nested or already flat) -> ``state_dict`` for ``model`` (shape- and name-checked)."""
+    flat = flatten_tree(tree)
+    flat = {k: v for k, v in flat.items() if not _is_rng_state(k)}
+    want = model.state_dict()
+    missing = [k for k in want if k not in flat]
+    unexpected = [k for k in flat if k not in want]
+    if strict and (missing or unexpected):
+        raise KeyError(f"checkpoint/model mismatch: missing {missing[:5]} (+{max(0, len(missing) - 5)}), "
+                       f"unexpected {unexpected[:5]} (+{max(0, len(unexpected) - 5)})")
+    sd = {}
+    for k, ref in want.items():
+        if k not in flat:
+            continue
+        a = np.asarray(flat[k])
+        if a.dtype.kind == "V" or str(a.dtype) == "bfloat16":          # ml_dtypes bfloat16 -> fp32 master copy
+            a = a.astype(np.float32)
+        if tuple(a.shape) != tuple(ref.shape):
+            raise ValueError(f"{k}: checkpoint shape {tuple(a.shape)} != model shape {tuple(ref.shape)}")
+        sd[k] = torch.from_numpy(np.ascontiguousarray(a)).to(ref.dtype)
+    return sd
+
+
+def load_flax_tree(model, tree, strict=True, flat=None):
+    """Load a Flax tree into ``model``; ``flat`` (a ``ddp.FlatParams``) gets its compute-dtype shadow refreshed."""
+    sd = state_dict_from_flax(tree, model, strict=strict)
+    with torch.no_grad():
+        own = model.state_dict()
+        for k, v in sd.items():
+            own[k].copy_(v)
+    if flat is not None and getattr(flat, "shadow", None) is not None:
+        flat.refresh_shadow()
+    else:
+        from . import functional as F_
+        F_.invalidate_shadows()
+    return sorted(sd)
+
+
+def to_flax_tree(model, wrap_value=False):
+    """``model`` -> nested dict shaped like ``nnx.state(model)`` (list indices become int keys)."""
+    tree = {}
+    for name, t in model.state_dict().items():
+        node = tree
+        parts = name.split(".")
+        for p in parts[:-1]:
+            node = node.setdefault(int(p) if p.isdigit() else p, {})
+        a = t.detach().to("cpu", torch.float32).numpy()
+        node[parts[-1]] = {"value": a} if wrap_value else a
+    return tree
+
+
+def load_adam_moments(adam, model, mu_tree, nu_tree, count):
+    """optax ``ScaleByAdamState(count, mu, nu)`` (trees shaped like the parameters) -> ``ddp.FlatAdam`` buffers."""
+    fp = adam.flat
+    names = {id(p): n for n, p in model.named_parameters()}
+    mu, nu = flatten_tree(mu_tree), flatten_tree(nu_tree)
+    with torch.no_grad():
+        for i, p in enumerate(fp.params):
+            n = names[id(p)]
+            s, e = fp.offsets[i], fp.offsets[i] + p.numel()
+            for buf, src in ((adam.m, mu), (adam.v, nu)):
+                a = np.asarray(src[n], dtype=np.float32)
+                if a.size != p.numel():
+                    raise ValueError(f"{n}: moment has {a.size} elements, parameter {p.numel()}")
+                buf[s:e].copy_(torch.from_numpy(a.reshape(-1)))
+    adam.t = int(count)
+
+
+def save_npz(path, tree):
+    flat = flatten_tree(tree)
+    np.savez(path, **{k: np.asarray(v, dtype=np.float32) if np.asarray(v).dtype.kind == "f" else np.asarray(v)
+                      for k, v in flat.items()})
+    return sorted(flat)
+
+
+def load_npz(path):
+    with np.load(path) as z:
+        return {k: z[k] for k in z.files}
+
+
+def save_checkpoint(model, path):
+    """Export in the transport format (the reference re-imports it with nnx.update on the unflattened tree)."""
+    return save_npz(path, to_flax_tree(model))
+
+
+def load_checkpoint(model, path, strict=True, flat=None):
+    """train/model_loader.py:35-42 for the model half: an orbax directory (needs orbax) or a ``save_npz`` file."""
+    if os.path.isdir(path):
+        try:
+            import orbax.checkpoint as ocp                                          # noqa: PLC0415
+        except ImportError as e:
+            raise ImportError("reading an orbax checkpoint directory needs orbax-checkpoint (not in this image); "
+                              "convert it to .npz on a JAX box with checkpoint.save_npz") from e
+        restored = ocp.StandardCheckpointer().restore(os.path.abspath(path))
+        tree = restored["model"] if isinstance(restored, dict) and "model" in restored else restored
+    else:
+        tree = load_npz(path)
+    return load_flax_tree(model, tree, strict=strict, flat=flat)
