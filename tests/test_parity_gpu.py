@@ -642,6 +642,10 @@ def test_rl_loss_matches_oracle_fp32(V):
     mask[2, 1:] = False
     noise = torch.randn(b, t, 16, 96, generator=g)
     bu = torch.rand(2 * b, t, 1, 1, generator=g)
+    # twins must differ on a valid frame: with equal keep-masks their losses are equal up to rounding and the reference's
+    # (pair - mean) / (std + 1e-6) turns that rounding into O(0.1) "disadvantages" -- noise in any implementation
+    bu[0::2, 0] = 0.0
+    bu[1::2, 0] = 1.0
     hp = dict(DEFAULT_HPARAMS, gamma3=0.0, rl_loss_weight=0.5)
     lo, ao = o_loss_fn(o, x, mask[:, None, None, :], mask, ORngs(0), hp, None, None, noise=noise, bernoulli_u=bu)
     lm, am = loss_fn(m, x.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), hp, None, None,
