@@ -84,6 +84,9 @@ CASES = [
     ("temporal_L32_hw8_masked", 3, 32, 8, True, True),
     ("temporal_L64_hw4", 1, 64, 4, True, True),
     ("temporal_allmasked_row", 2, 16, 16, True, True),
+    ("temporal_L12_hw20_masked", 2, 12, 20, True, True),
+    ("temporal_L5_hw7", 3, 5, 7, True, False),
+    ("spatial_L9_masked", 1, 6, 9, False, True),
     ("long_L384", 1, 2, 384, False, False),
     ("long_L512_masked", 1, 3, 512, False, True),
     ("long_L1024", 1, 1, 1024, False, False),
@@ -103,9 +106,11 @@ if __name__ == "__main__":
             print(json.dumps(r), flush=True)
             f.write(json.dumps(r) + "\n")
         for c in [("prod_spatial", 8, 16, 256, False, False), ("prod_temporal", 8, 16, 256, True, True),
-                  ("prod_cfg5_spatial", 1, 64, 1024, False, False)]:
+                  ("prod_temporal_tcgen05", 8, 16, 256, True, True), ("prod_cfg5_spatial", 1, 64, 1024, False, False)]:
             if sel and c[0] not in sel:
                 continue
+            # key 9: keep L <= 16 on the packed-tile tcgen05 kernels instead of the one-warp-per-sequence kernel
+            _ffi.lib.vvae_debug_set(9, 1 if c[0].endswith("_tcgen05") else 0)
             try:
                 r = make_case(*c, timed=True)
             except Exception as e:  # noqa: BLE001

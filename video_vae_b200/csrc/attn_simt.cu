@@ -332,6 +332,11 @@ int attn_tc_supported(const vvae_attn_args& a);
 int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s);
 int attn_tc_bwd_supported(const vvae_attn_args& a);
 int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s);
+// attn_warp.cu: one warp per (sequence, head) for L <= 16 (mma.sync, registers only)
+int attn_warp_supported(const vvae_attn_args& a, bool bwd);
+int attn_warp_fwd(const vvae_attn_args& a, cudaStream_t s);
+int attn_warp_bwd(const vvae_attn_args& a, cudaStream_t s);
+extern long long g_dbg[16];      // vvae_debug_set: key 9 != 0 keeps short sequences on the tcgen05 packed-tile kernels
 }
 
 using namespace vvae;
@@ -352,6 +357,8 @@ int vvae_attn_fwd(const vvae_attn_args* args, vvae_stream_t stream) {
   int rc = attn_validate(args, false);
   if (rc) return rc;
   if (args->n_outer == 0) return VVAE_OK;
+  if (args->backend == VVAE_BACKEND_AUTO && !g_dbg[9] && attn_warp_supported(*args, false))
+    return attn_warp_fwd(*args, as_stream(stream));
   if (args->backend != VVAE_BACKEND_SIMT && attn_tc_supported(*args)) return attn_tc_fwd(*args, as_stream(stream));
   if (args->backend == VVAE_BACKEND_TCGEN05) {
     set_error("attention: shape not supported by the tensor-core path");
@@ -364,6 +371,8 @@ int vvae_attn_bwd(const vvae_attn_args* args, vvae_stream_t stream) {
   int rc = attn_validate(args, true);
   if (rc) return rc;
   if (args->n_outer == 0) return VVAE_OK;
+  if (args->backend == VVAE_BACKEND_AUTO && !g_dbg[9] && attn_warp_supported(*args, true))
+    return attn_warp_bwd(*args, as_stream(stream));
   if (args->backend != VVAE_BACKEND_SIMT && attn_tc_bwd_supported(*args)) return attn_tc_bwd(*args, as_stream(stream));
   if (args->backend == VVAE_BACKEND_TCGEN05) {
     set_error("attention bwd: shape not supported by the tensor-core path");

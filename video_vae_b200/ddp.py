@@ -7,6 +7,8 @@ NVLink (torch.distributed is the plumbing).  The only collective on the path is 
 per bucket, in the order backward finishes the buckets (decoder first), on a dedicated stream, so it hides under the
 remaining backward kernels.  The 1/world_size scaling is folded into the optimizer's ``grad_scale``.
 """
+import weakref
+
 import torch
 import torch.distributed as dist
 
@@ -48,7 +50,7 @@ class FlatParams:
         """Keep ONE flat bf16 copy of all parameters, refreshed by a single cast kernel per optimizer step."""
         self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=self.flat.device)
         for p, o in zip(self.params, self.offsets):
-            self._shadow_views[id(p)] = self.shadow[o:o + p.numel()].view(p.shape)
+            self._shadow_views[id(p)] = (weakref.ref(p), self.shadow[o:o + p.numel()].view(p.shape))
         F_._flat_shadow_views = self._shadow_views
         self.refresh_shadow()
 

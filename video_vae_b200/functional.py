@@ -21,7 +21,7 @@ from ._ffi import EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, require_device
 
 # ------------------------------------------------------------------ parameter shadows / gradient buffers
 _shadow_cache = {}  # id(param) -> (weakref(param), version, data_ptr, shadow tensor)
-_flat_shadow_views = {}  # id(param) -> bf16 view into FlatParams.shadow (ddp.FlatParams.enable_bf16_shadow)
+_flat_shadow_views = {}  # id(param) -> (weakref(param), bf16 view into FlatParams.shadow) (ddp.FlatParams.enable_bf16_shadow)
 _grad_hooks = []  # callables(list_of_params) invoked after a backward Function has finished writing their grads
 _decoder_done_hooks = []  # callables() invoked when backward reaches the latent: every decoder gradient is written
 
@@ -35,8 +35,8 @@ def shadow(p, dtype):
     key = id(p)
     if dtype == torch.bfloat16:
         v = _flat_shadow_views.get(key)
-        if v is not None:
-            return v
+        if v is not None and v[0]() is p:       # ids are recycled: the entry must belong to THIS parameter
+            return v[1]
     ent = _shadow_cache.get(key)
     if (ent is not None and ent[0]() is p and ent[1] == p._version and ent[2] == p.data_ptr()
             and ent[3].dtype == dtype):
