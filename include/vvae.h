@@ -193,10 +193,13 @@ int vvae_convT122_bwd(const void* dy, long long dy_ld, const void* x, const void
 int vvae_groupnorm_silu_fwd(const void* x, void* y, long long y_ld, const float* gamma, const float* beta,
                             float* mean, float* rstd, float* stats, int B, long long S, int C, int G, float eps,
                             int dtype, vvae_stream_t stream);
-/* dy has channel stride dy_ld; dx contiguous [B,S,C]; dgamma/dbeta accumulate. */
+/* dy has channel stride dy_ld; dx contiguous [B,S,C]; dgamma/dbeta accumulate.  dx_colsum_accum (optional, fp32 [C])
+ * += per-channel sums of the produced dx: the bias gradient of the convolution that feeds this norm
+ * (ConvBlock3D, train/unet.py:13-29), taken while dx is in registers instead of a second pass over it. */
 int vvae_groupnorm_silu_bwd(const void* dy, long long dy_ld, const void* x, const float* gamma, const float* beta,
                             const float* mean, const float* rstd, void* dx, float* dgamma_accum, float* dbeta_accum,
-                            float* stats, int B, long long S, int C, int G, int dtype, vvae_stream_t stream);
+                            float* stats, float* dx_colsum_accum, int B, long long S, int C, int G, int dtype,
+                            vvae_stream_t stream);
 
 /* ---- max_pool (1,2,2) (train/unet.py:50) and channel concat (train/unet.py:80) ---- */
 /* x [b_t,H,W,C] with channel stride x_ld -> y [b_t,H/2,W/2,C] contiguous. */

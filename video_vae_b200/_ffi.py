@@ -101,7 +101,7 @@ _SIGS = {
     "vvae_convT122_fwd": ([vp, vp, vp, vp, ll, i32, i32, i32, i32, i32, i32, vp, ll, vp], i32),
     "vvae_convT122_bwd": ([vp, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, ll, vp], i32),
     "vvae_groupnorm_silu_fwd": ([vp, vp, ll, vp, vp, vp, vp, vp, i32, ll, i32, i32, f32, i32, vp], i32),
-    "vvae_groupnorm_silu_bwd": ([vp, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, i32, vp], i32),
+    "vvae_groupnorm_silu_bwd": ([vp, ll, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, ll, i32, i32, i32, vp], i32),
     "vvae_maxpool122_fwd": ([vp, ll, vp, i32, i32, i32, i32, i32, vp], i32),
     "vvae_maxpool122_bwd": ([vp, ll, vp, vp, ll, vp, i32, i32, i32, i32, i32, vp], i32),
     "vvae_copy_channels": ([vp, ll, ll, vp, ll, ll, ll, i32, i32, vp], i32),

@@ -834,16 +834,22 @@ gn_bwd_stats_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ x,
                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
-                        const float* __restrict__ rstd, const float* __restrict__ stats, bf16* __restrict__ dx, long long S,
-                        int C, int G, float inv_n, long long rows_per_block) {
+                        const float* __restrict__ rstd, const float* __restrict__ stats, bf16* __restrict__ dx,
+                        float* __restrict__ dxsum, long long S, int C, int G, float inv_n, long long rows_per_block) {
+  __shared__ float smc[256];
   const int b = blockIdx.y, cpr = C >> 3, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
-  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8];
+  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8], cs[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     const int c = ch * 8 + t, g = c / cg;
     mu[t] = mean[b * G + g]; rs[t] = rstd[b * G + g]; ga[t] = gamma[c]; be[t] = beta[c];
     m1[t] = stats[((long long)b * G + g) * 2] * inv_n;
     m2[t] = stats[((long long)b * G + g) * 2 + 1] * inv_n;
+    cs[t] = 0.f;
+  }
+  if (dxsum) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) smc[i] = 0.f;
+    __syncthreads();
   }
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
@@ -873,10 +879,24 @@ gn_bwd_apply_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
         const float sg = gn_sigmoid(z);
         const float gg = d[t] * sg * fmaf(z, 1.f - sg, 1.f) * ga[t];
         o[t] = rs[t] * (gg - m1[t] - xh * m2[t]);
+        cs[t] += bf_round(o[t]);
       }
       *reinterpret_cast<uint4*>(dxb + r * C) =
           make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
     }
+  }
+  // per-channel sums of the produced gradient: the bias gradient of the convolution in front of this norm
+  if (dxsum) {
+    for (int o = cpr; o < 32; o <<= 1) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], o);
+    }
+    if ((threadIdx.x & 31) < cpr) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) atomicAdd(&smc[ch * 8 + t], cs[t]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dxsum + i, smc[i]);
   }
 }
 
@@ -1073,7 +1093,7 @@ int vvae_groupnorm_silu_fwd(const void* x, void* y, long long y_ld, const float*
 
 int vvae_groupnorm_silu_bwd(const void* dy, long long dy_ld, const void* x, const float* gamma, const float* beta,
                             const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* stats,
-                            int B, long long S, int C, int G, int dtype, vvae_stream_t stream) {
+                            float* dx_colsum_accum, int B, long long S, int C, int G, int dtype, vvae_stream_t stream) {
   if (B <= 0 || S <= 0) return VVAE_OK;
   VVAE_REQUIRE(dy && x && gamma && beta && mean && rstd && dx && stats, "groupnorm_silu_bwd: null pointer");
   VVAE_REQUIRE(C > 0 && C <= 256 && G > 0 && G <= 64 && C % G == 0, "groupnorm_silu_bwd: bad C=%d G=%d", C, G);
@@ -1090,7 +1110,8 @@ int vvae_groupnorm_silu_bwd(const void* dy, long long dy_ld, const void* x, cons
     gn_bwd_stats_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
                                                   dgamma, dbeta, S, C, G, vrpb);
     gn_bwd_apply_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
-                                                  (bf16*)dx, S, C, G, 1.f / (float)((double)S * (C / G)), vrpb);
+                                                  (bf16*)dx, dx_colsum_accum, S, C, G,
+                                                  1.f / (float)((double)S * (C / G)), vrpb);
     return check_launch("groupnorm_silu_bwd");
   }
   VVAE_DISPATCH_DTYPE(dtype, T, (groupnorm_silu_bwd_stats_kernel<T><<<grid, threads, 0, s>>>(
@@ -1099,7 +1120,9 @@ int vvae_groupnorm_silu_bwd(const void* dy, long long dy_ld, const void* x, cons
   VVAE_DISPATCH_DTYPE(dtype, T, (groupnorm_silu_bwd_apply_kernel<T><<<grid, threads, 0, s>>>(
                                     (const T*)dy, dy_ld, (const T*)x, gamma, beta, mean, rstd, stats, (T*)dx, S, C, G,
                                     1.f / (float)((double)S * (C / G)), rpb)));
-  return check_launch("groupnorm_silu_bwd");
+  rc = check_launch("groupnorm_silu_bwd");
+  if (rc || !dx_colsum_accum) return rc;
+  return vvae_colsum(dx, C, (long long)B * S, C, dx_colsum_accum, dtype, stream);   // generic path: separate pass
 }
 
 }  // extern "C"

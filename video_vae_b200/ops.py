@@ -317,13 +317,14 @@ def groupnorm_silu_fwd(x, gamma, beta, G, out=None, out_ld=None):
     return out, mean, rstd
 
 
-def groupnorm_silu_bwd(dy, dy_ld, x, gamma, beta, mean, rstd, dgamma, dbeta, G):
+def groupnorm_silu_bwd(dy, dy_ld, x, gamma, beta, mean, rstd, dgamma, dbeta, G, dx_colsum=None):
+    """dx_colsum (fp32 [C], optional) += per-channel sums of the returned dx (the preceding conv's bias gradient)."""
     B, Cc = x.shape[0], x.shape[-1]
     S = x.numel() // (B * Cc)
     dx = torch.empty_like(x)
     stats = torch.empty((B, G, 2), dtype=torch.float32, device=x.device)
     check(lib.vvae_groupnorm_silu_bwd(ptr(dy), dy_ld, ptr(x), ptr(gamma), ptr(beta), ptr(mean), ptr(rstd), ptr(dx),
-                                      ptr(dgamma), ptr(dbeta), ptr(stats), B, S, Cc, G, dt(x), stream()),
+                                      ptr(dgamma), ptr(dbeta), ptr(stats), ptr(dx_colsum), B, S, Cc, G, dt(x), stream()),
           "vvae_groupnorm_silu_bwd")
     return dx
 

@@ -87,11 +87,13 @@ def _conv_fwd(x, x_ld, Cin, conv, dtype, residual=None, out=None, out_ld=None):
                           out_ld=out_ld, wprep=wp, pad_out=out is not None and out_ld >= _pad16(Cout) > Cout)
 
 
-def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=None, dx_ld=None):
+def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=None, dx_ld=None, bias_done=False):
+    """``bias_done``: the producer of ``dy`` (GroupNorm backward) already accumulated the bias gradient."""
     Cout = conv.kernel.shape[4]
     dy_ld = dy_ld or dy.shape[-1]
     ops.conv3d_wgrad_accum(x, dy, F_.grad_buf(conv.kernel), conv.ks, Cin, Cout, x_ld=x_ld, dy_ld=dy_ld)
-    ops.colsum_accum(dy.reshape(-1, dy_ld)[:, :Cout], F_.grad_buf(conv.bias))
+    if not bias_done:
+        ops.colsum_accum(dy.reshape(-1, dy_ld)[:, :Cout], F_.grad_buf(conv.bias))
     if not need_dx:
         return None
     o_ld = dx_ld if dx_out is not None else Cin
@@ -119,12 +121,13 @@ def _block_fwd(x, x_ld, Cin, blk, dtype, out=None, out_ld=None):
 def _block_bwd(dy, dy_ld, tp, blk, dtype, need_dx=True):
     """Returns dx with the channel stride of the block's input (``tp.x_ld``; pad channels, if any, are zero)."""
     dc = ops.groupnorm_silu_bwd(dy, dy_ld, tp.c, blk.norm.scale.detach(), blk.norm.bias.detach(), tp.mean, tp.rstd,
-                                F_.grad_buf(blk.norm.scale), F_.grad_buf(blk.norm.bias), blk.norm.num_groups)
+                                F_.grad_buf(blk.norm.scale), F_.grad_buf(blk.norm.bias), blk.norm.num_groups,
+                                dx_colsum=F_.grad_buf(blk.conv.bias))
     dx_out = dx_ld = None
     if need_dx and tp.x_ld != tp.Cin:
         dx_ld = tp.x_ld
         dx_out = torch.zeros(tuple(tp.x.shape[:4]) + (dx_ld,), dtype=dc.dtype, device=dc.device)
-    return _conv_bwd(dc, tp.x, tp.x_ld, tp.Cin, blk.conv, dtype, need_dx, dx_out=dx_out, dx_ld=dx_ld)
+    return _conv_bwd(dc, tp.x, tp.x_ld, tp.Cin, blk.conv, dtype, need_dx, dx_out=dx_out, dx_ld=dx_ld, bias_done=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
