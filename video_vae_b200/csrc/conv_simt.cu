@@ -181,6 +181,11 @@ static int conv_run(const vvae_conv_args* a, int which, vvae_stream_t stream) {
   if (a->backend == VVAE_BACKEND_AUTO && a->dtype == VVAE_BF16 && a->kt == 1 && a->kh == 1 && a->kw == 1 &&
       small_linear_ok(a->Cin, a->Cout)) {
     const long long V = (long long)a->B * a->T * a->H * a->W;
+    if (which == 0 && !a->pad_out) {   // y[v, co] = sum_ci x[v, ci] * w[ci, co] + bias (+ residual)
+      SmallLinArgs q{(const bf16*)a->x, a->x_ld, (const bf16*)a->w, a->Cout, 1, a->bias, (bf16*)a->y, a->y_ld,
+                     a->epilogue == VVAE_EPI_RESIDUAL ? (const bf16*)a->aux_in : nullptr, a->ld_aux, V, a->Cin, a->Cout};
+      return small_linear_fwd(q, s);
+    }
     if (which == 1) {   // dx[v, ci] = sum_co dy[v, co] * w[ci, co]
       SmallLinArgs q{(const bf16*)a->y, a->y_ld, (const bf16*)a->w, 1, a->Cout, nullptr, (bf16*)const_cast<void*>(a->x),
                      a->x_ld, nullptr, 0, V, a->Cout, a->Cin};
