@@ -430,6 +430,30 @@ def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked
     """bf16, head_dim 64: the tensor-core attention (forward AND backward) against oracle autograd on identical data.
     Covers 128/256-row tiles, block-diagonal packing of short sequences, ragged tails, key-padding masks, a fully
     masked clip (uniform attention, no gradient to q/k) and the streaming long-sequence kernels (L > 256)."""
+    from video_vae_b200 import _ffi
+    _attention_case(name, b, t, hw, temporal, masked, _ffi.BACKEND_TCGEN05)
+
+
+@pytest.mark.parametrize("name,b,t,hw,temporal,masked", [
+    ("temporal_L16_masked", 2, 16, 16, True, True),
+    ("temporal_L16_hw12_tail", 1, 16, 12, True, True),
+    ("temporal_L16_nomask", 1, 16, 33, True, False),
+    ("temporal_L12_masked", 2, 12, 20, True, True),
+    ("temporal_L5", 3, 5, 7, True, False),
+    ("temporal_L1", 2, 1, 9, True, True),
+    ("spatial_L9_masked", 1, 6, 9, False, True),
+    ("spatial_L16", 2, 5, 16, False, False),
+    ("temporal_allmasked_clip", 2, 16, 16, True, True),
+])
+def test_short_sequence_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked):
+    """bf16, head_dim 64, L <= 16 (the production temporal attention is L = 16): the one-warp-per-(sequence, head)
+    mma.sync kernels of attn_warp.cu (what BACKEND_AUTO selects) against oracle autograd: every length 1..16 class,
+    ragged sequence counts, key-padding masks, a fully masked clip."""
+    from video_vae_b200 import _ffi
+    _attention_case(name, b, t, hw, temporal, masked, _ffi.BACKEND_AUTO)
+
+
+def _attention_case(name, b, t, hw, temporal, masked, backend):
     from video_vae_b200 import _ffi, ops
     from video_vae_b200.ops import AttnGeom, AttnMask
     H, HD = 8, 64
@@ -451,7 +475,7 @@ def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked
         if name == "temporal_allmasked_clip":
             mask_bl[0] = False
         mask = AttnMask(mask_bl.to(torch.uint8).contiguous(), hw if temporal else 1, L, 0, 0, 1)
-    ops.ATTN_BACKEND = _ffi.BACKEND_TCGEN05          # fail loudly if the shape would fall back to the generic kernel
+    ops.ATTN_BACKEND = backend           # BACKEND_TCGEN05 fails loudly if the shape would fall back to the generic kernel
     try:
         o, lse = ops.attn_fwd(geom, H, HD, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], mask, 1.0 / math.sqrt(HD))
         dqkv = torch.zeros(N, 3 * Q, device=dev, dtype=torch.bfloat16)
@@ -461,10 +485,15 @@ def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked
         ops.ATTN_BACKEND = _ffi.BACKEND_AUTO
     torch.cuda.synchronize()
     o_ref, dq_ref, dk_ref, dv_ref = _attention_reference(qk, qkv, d_o, geom, temporal, b, t, hw, H, HD, mask_bl)
-    assert rel_err(o, o_ref) < BF16_TOL
-    assert rel_err(dqkv[:, :Q], dq_ref) < BF16_TOL, "dq"
-    assert rel_err(dqkv[:, Q:2 * Q], dk_ref) < BF16_TOL, "dk"
-    assert rel_err(dqkv[:, 2 * Q:], dv_ref) < BF16_TOL, "dv"
+    def close(a, ref, what):
+        if float(ref.abs().max()) == 0.0:          # L = 1: softmax over one key has no gradient; allow rounding noise
+            assert float(a.float().abs().max()) < 1e-4, what
+        else:
+            assert rel_err(a, ref) < BF16_TOL, what
+    close(o, o_ref, "o")
+    close(dqkv[:, :Q], dq_ref, "dq")
+    close(dqkv[:, Q:2 * Q], dk_ref, "dk")
+    close(dqkv[:, 2 * Q:], dv_ref, "dv")
     if name == "temporal_allmasked_clip":            # clip 0: uniform attention, q/k receive no gradient
         rows = (torch.arange(N, device=dev) // (t * hw)) == 0
         assert dqkv[rows][:, :2 * Q].abs().max().item() == 0.0
