@@ -277,6 +277,18 @@ int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, floa
 int vvae_philox_fill(float* out, long long n, unsigned long long seed, unsigned long long offset, int kind,
                      vvae_stream_t stream);
 
+/* ---- VGG-16 perceptual features ("next" row f4: train/vgg_tests.py:8-68 over flaxmodels 0.1.3 VGG16) ----
+ * The 3x3 convolutions run on vvae_conv3d_* with kt = 1; these are the pointwise pieces around them. */
+/* y = max(x, 0);  dx = y > 0 ? dy : 0.  n elements, 16-byte aligned pointers. */
+int vvae_relu_fwd(const void* x, void* y, long long n, int dtype, vvae_stream_t stream);
+int vvae_relu_bwd(const void* dy, const void* y, void* dx, long long n, int dtype, vvae_stream_t stream);
+/* x [voxels,3] RGB in [0,1] (x_dtype) -> y [voxels,y_ld] (dtype): (round_T(x) - mean)/std per ImageNet channel
+ * statistics in channels 0..2, zeros in the pad channels 3..y_ld-1 (the tensor-core conv gathers 16 channels). */
+int vvae_vgg_preprocess_fwd(const void* x, int x_dtype, void* y, long long voxels, int y_ld, int dtype,
+                            vvae_stream_t stream);
+/* dx [voxels,3] = dy[voxels,:3] / std */
+int vvae_vgg_preprocess_bwd(const void* dy, void* dx, long long voxels, int dy_ld, int dtype, vvae_stream_t stream);
+
 /* ---- optimizer ("next" row f1: optax.chain(clip_by_global_norm, adam), train/rl_nonadversarial.py:241-253) ---- */
 /* out[0] += sum g^2 */
 int vvae_sumsq_f32(const float* g, long long n, float* out1, vvae_stream_t stream);

@@ -109,6 +109,41 @@ def cfg5(dev):
             "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
 
 
+def rl(dev):
+    """Production RL step of train/rl_nonadversarial.py (:36-57, 100-198): rl_model, batch 2 x 32 frames (duplicated
+    to 4 inside the model), RL loss with and without the VGG perceptual term (random VGG weights)."""
+    from video_vae_b200.perceptual import get_adversarial_perceptual_loss_fn, load_vgg
+    from video_vae_b200.rl_losses import DEFAULT_HPARAMS as RL_HP, loss_fn as rl_loss_fn
+    from video_vae_b200.rl_model import VideoVAE as RLVAE
+    m = RLVAE(256, 256, 3, PROD["patch_size"], PROD["encoder_depth"], PROD["decoder_depth"], PROD["mlp_dim"],
+              PROD["num_heads"], PROD["qkv_features"], PROD["max_temporal_len"], PROD["spatial_compression_rate"],
+              PROD["unembedding_upsample_rate"], V.Rngs(2), dtype=torch.bfloat16, device=dev)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7))
+    flat = FlatParams(m)
+    flat.enable_bf16_shadow()
+    vgg, vgg_params = load_vgg(V.Rngs(5), device=dev)
+    pfn = get_adversarial_perceptual_loss_fn(vgg)
+    B, T = 2, 32
+    g = torch.Generator().manual_seed(1234)
+    video = torch.rand(B, T, 256, 256, 3, generator=g).to(torch.bfloat16).to(dev)
+    mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+    res = {}
+    for name, fn, hp in (("no_perceptual", None, dict(RL_HP, gamma3=0.0)), ("vgg_perceptual", pfn, dict(RL_HP))):
+        rngs = V.Rngs(3)
+
+        def step():
+            flat.zero_grad()
+            loss, aux = rl_loss_fn(m, video, mask[:, None, None, :], mask, rngs, hp, fn, vgg_params, train=True)
+            loss.backward()
+            return loss, aux
+        ms, (loss, aux) = timed(step, 2, 4)
+        res[name] = {"ms_per_step": ms, "clips_per_s": B / (ms * 1e-3), "loss": loss.item(),
+                     "perceptual_loss": float(aux["perceptual_loss"]), "grad_finite": bool(torch.isfinite(flat.grad).all())}
+    return {"config": "rl_nonadversarial production step: rl_model, batch 2 x 32 frames x 256^2 (decoder batch 4), bf16, "
+                      "fwd+loss+bwd eager", **res, "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
+
+
 if __name__ == "__main__":
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -118,7 +153,7 @@ if __name__ == "__main__":
         for name in which:
             t0 = time.time()
             try:
-                r = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5}[name](dev)
+                r = {"cfg3": cfg3, "cfg4": cfg4, "cfg5": cfg5, "rl": rl}[name](dev)
             except Exception as e:  # noqa: BLE001
                 r = {"config": name, "error": repr(e)[:500]}
             r["wall_s"] = round(time.time() - t0, 1)

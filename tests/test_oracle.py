@@ -350,3 +350,34 @@ def test_rl_loss_pairwise_terms_hand_checked():
     loss2, _ = loss_terms(video, recon, sel2, smask, lv, lv.clone(), torch.tensor([[True, False, True]]), hp)
     loss2.backward()
     assert float(sel2.grad.reshape(2, t)[:, 1].abs().max()) == 0.0
+
+
+def test_vgg_perceptual_oracle_shapes_and_loss():
+    """train/vgg_tests.py __main__ checks (:134-201) on the oracle restatement: activation shapes at 64x64 and 128x128,
+    a finite scalar loss for ones vs 0.5*ones, per-sample form averaging to the scalar form, finite non-zero gradient
+    of the input's shape; plus a hand-check of the ImageNet normalisation and 'SAME' zero padding on relu1_1."""
+    from oracle import Rngs
+    from oracle.perceptual import (IMAGENET_MEAN, IMAGENET_STD, VGG16Features, get_adversarial_perceptual_loss_fn,
+                                   get_perceptual_loss_fn)
+    vgg = VGG16Features(Rngs(0))
+    b, t, c = 2, 4, 3
+    for hw in (64, 128):
+        feats = vgg(torch.ones(b * t, hw, hw, c))
+        assert feats["relu1_1"].shape == (b * t, hw, hw, 64) and feats["relu1_2"].shape == (b * t, hw, hw, 64)
+        assert feats["relu2_1"].shape == (b * t, hw // 2, hw // 2, 128)
+        assert all((v >= 0).all() for v in feats.values())
+    x = torch.ones(b, t, 64, 64, c, requires_grad=True)
+    target = torch.ones(b, t, 64, 64, c) * 0.5
+    scalar = get_perceptual_loss_fn(vgg)(None, x, target)
+    per_sample = get_adversarial_perceptual_loss_fn(vgg)(None, x, target)
+    assert scalar.shape == () and torch.isfinite(scalar) and scalar > 0
+    assert per_sample.shape == (b,) and torch.allclose(per_sample.mean(), scalar, rtol=1e-5)
+    scalar.backward()
+    assert x.grad.shape == x.shape and torch.isfinite(x.grad).all() and x.grad.abs().max() > 0
+    # corner pixel of relu1_1 for a constant image: only the 2x2 in-image taps contribute (zero padding is applied to
+    # the NORMALISED image)
+    xn = (torch.ones(3) - torch.tensor(IMAGENET_MEAN)) / torch.tensor(IMAGENET_STD)
+    k = vgg.conv1_1_kernel
+    want = torch.relu(torch.einsum("hwio,i->o", k[1:, 1:], xn) + vgg.conv1_1_bias)
+    got = vgg(torch.ones(1, 8, 8, 3))["relu1_1"][0, 0, 0]
+    assert torch.allclose(got, want, atol=1e-5)

@@ -725,6 +725,41 @@ def test_rl_loss_bf16_train_step_and_loss_decrease(V):
     assert torch.isfinite(le) and ae["reconstruction"].shape == (4, 8, 64, 64, 3)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_vgg_perceptual_loss_matches_oracle(V, dtype, tol):
+    """video_vae_b200.perceptual (train/vgg_tests.py over flaxmodels' VGG16, restated in
+    oracle/perceptual.py): activations, the per-sample and scalar losses and the gradient w.r.t. the reconstruction.
+    fp32 runs the generic conv kernels (1e-4); bf16 the tcgen05 conv path (2e-2 against the fp32 oracle)."""
+    from oracle import Rngs as ORngs
+    from oracle.perceptual import VGG16Features as OVGG, get_adversarial_perceptual_loss_fn as o_fn
+    from video_vae_b200.perceptual import (PERCEPTUAL_LAYERS, VGG16Features, get_adversarial_perceptual_loss_fn,
+                                           get_perceptual_loss_fn)
+    o = OVGG(ORngs(4))
+    m = VGG16Features(V.Rngs(9), dtype=dtype)
+    _copy_params(m, o)
+    g = _gen(31)
+    b, t, hw = 2, 3, 32
+    x = torch.rand(b, t, hw, hw, 3, generator=g)
+    target = torch.rand(b, t, hw, hw, 3, generator=g)
+    fo = o(x.reshape(b * t, hw, hw, 3))
+    fm = m(x.reshape(b * t, hw, hw, 3).cuda())
+    for k in PERCEPTUAL_LAYERS:
+        assert tuple(fm[k].shape) == tuple(fo[k].shape), k
+        assert rel_err(fm[k], fo[k]) < tol, k
+    xo = x.clone().requires_grad_()
+    lo = o_fn(o)(None, xo, target)
+    wgt = torch.tensor([0.3, 1.7])
+    (lo * wgt).sum().backward()
+    xm = x.cuda().to(dtype).requires_grad_()
+    lm = get_adversarial_perceptual_loss_fn(m)(None, xm, target.cuda())
+    assert lm.shape == (b,) and rel_err(lm, lo.detach()) < tol
+    (lm * wgt.cuda()).sum().backward()
+    assert xm.grad.shape == xm.shape
+    assert rel_l2(xm.grad, xo.grad) < (5 * tol if dtype == torch.bfloat16 else tol)
+    ls = get_perceptual_loss_fn(m)(None, xm.detach(), target.cuda())
+    assert abs(float(ls) - float(lo.mean())) <= tol * abs(float(lo.mean()))
+
+
 def test_encode_latents_driver_matches_oracle_encoder(V, tmp_path):
     """Config-3 style encode-only loop (video_vae_b200/encode.py, shaped like data_prep/save_latents.py:183-206): chunked,
     no-grad, eval mode; latents equal the oracle Encoder's (fp32) and the saved file round-trips."""

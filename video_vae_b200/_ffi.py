@@ -113,6 +113,10 @@ _SIGS = {
     "vvae_recon_loss_fwd": ([vp, i32, vp, vp, vp, vp, i32, i32, ll, i32, vp], i32),
     "vvae_recon_loss_bwd": ([vp, i32, vp, vp, vp, f32, f32, f32, vp, vp, i32, i32, ll, i32, vp], i32),
     "vvae_kl_fwd": ([vp, vp, vp, vp, ll, i32, i32, i32, vp], i32),
+    "vvae_relu_fwd": ([vp, vp, ll, i32, vp], i32),
+    "vvae_relu_bwd": ([vp, vp, vp, ll, i32, vp], i32),
+    "vvae_vgg_preprocess_fwd": ([vp, i32, vp, ll, i32, i32, vp], i32),
+    "vvae_vgg_preprocess_bwd": ([vp, vp, ll, i32, i32, vp], i32),
     "vvae_recon_loss_per_sample_fwd": ([vp, i32, vp, vp, vp, vp, i32, i32, ll, i32, vp], i32),
     "vvae_kl_per_sample_fwd": ([vp, vp, vp, vp, i32, ll, i32, i32, i32, vp], i32),
     "vvae_kl_bwd": ([vp, vp, vp, f32, vp, vp, vp, ll, i32, i32, i32, vp], i32),

@@ -431,6 +431,65 @@ __global__ void kl_bwd_kernel(const T* __restrict__ mean, const T* __restrict__ 
   }
 }
 
+// ---------------- VGG-16 perceptual features (train/vgg_tests.py:8-68; flaxmodels 0.1.3 VGG16) ----------------
+// ReLU after a conv (bias already added by the conv kernel) and its backward through the saved output.
+template <typename T>
+__global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n) {
+  constexpr int V = Vec16<T>::N;
+  const long long nv = n / V;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = i; j < nv; j += stride) {
+    Vec16<T> v;
+    v.load(x + j * V);
+#pragma unroll
+    for (int t = 0; t < V; ++t) v.set(t, fmaxf(v.get(t), 0.f));
+    v.store(y + j * V);
+  }
+  for (long long j = nv * V + i; j < n; j += stride) y[j] = from_f<T>(fmaxf(to_f(x[j]), 0.f));
+}
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n) {
+  constexpr int V = Vec16<T>::N;
+  const long long nv = n / V;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long j = i; j < nv; j += stride) {
+    Vec16<T> a, b;
+    a.load(dy + j * V);
+    b.load(y + j * V);
+#pragma unroll
+    for (int t = 0; t < V; ++t) a.set(t, b.get(t) > 0.f ? a.get(t) : 0.f);
+    a.store(dx + j * V);
+  }
+  for (long long j = nv * V + i; j < n; j += stride) dx[j] = to_f(y[j]) > 0.f ? dy[j] : from_f<T>(0.f);
+}
+// ImageNet normalisation of an RGB frame into a 16-channel (zero-padded) tensor the tensor-core conv can gather.
+__constant__ float c_vgg_mean[3] = {0.485f, 0.456f, 0.406f};
+__constant__ float c_vgg_std[3] = {0.229f, 0.224f, 0.225f};
+template <typename TI, typename T>
+__global__ void vgg_pre_fwd_kernel(const TI* __restrict__ x, T* __restrict__ y, long long V, int ld) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < V * ld; i += stride) {
+    const long long v = i / ld;
+    const int c = (int)(i - v * ld);
+    float o = 0.f;
+    if (c < 3) o = (round_to<T>(to_f(x[v * 3 + c])) - c_vgg_mean[c]) / c_vgg_std[c];
+    y[i] = from_f<T>(o);
+  }
+}
+template <typename T>
+__global__ void vgg_pre_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, long long V, int ld) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < V * 3; i += stride) {
+    const long long v = i / 3;
+    const int c = (int)(i - v * 3);
+    dx[i] = from_f<T>(to_f(dy[v * ld + c]) / c_vgg_std[c]);
+  }
+}
+
 // ---------------- optimizer ----------------
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   __shared__ float scratch[33];
@@ -703,6 +762,46 @@ int vvae_kl_bwd(const void* mean, const void* logvar, const float* frame_w, floa
                                     (const T*)mean, (const T*)logvar, frame_w, scale, gscale, (T*)dmean, (T*)dlogvar, n,
                                     (long long)tok_per_frame * Dl)));
   return check_launch("kl_bwd");
+}
+
+int vvae_relu_fwd(const void* x, void* y, long long n, int dtype, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(x && y, "relu_fwd: null pointer");
+  VVAE_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0), "relu_fwd: pointers must be 16-byte aligned");
+  VVAE_DISPATCH_DTYPE(dtype, T, (relu_fwd_kernel<T><<<ew_blocks(n / 8 + 1), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, n)));
+  return check_launch("relu_fwd");
+}
+
+int vvae_relu_bwd(const void* dy, const void* y, void* dx, long long n, int dtype, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(dy && y && dx, "relu_bwd: null pointer");
+  VVAE_REQUIRE(((uintptr_t)dy % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)dx % 16 == 0),
+               "relu_bwd: pointers must be 16-byte aligned");
+  VVAE_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_blocks(n / 8 + 1), 256, 0, as_stream(stream)>>>(
+                                    (const T*)dy, (const T*)y, (T*)dx, n)));
+  return check_launch("relu_bwd");
+}
+
+int vvae_vgg_preprocess_fwd(const void* x, int x_dtype, void* y, long long voxels, int y_ld, int dtype,
+                            vvae_stream_t stream) {
+  if (voxels <= 0) return VVAE_OK;
+  VVAE_REQUIRE(x && y && y_ld >= 3, "vgg_preprocess_fwd: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  const int blocks = ew_blocks(voxels * y_ld);
+  if (x_dtype == VVAE_F32 && dtype == VVAE_F32) vgg_pre_fwd_kernel<float, float><<<blocks, 256, 0, s>>>((const float*)x, (float*)y, voxels, y_ld);
+  else if (x_dtype == VVAE_F32 && dtype == VVAE_BF16) vgg_pre_fwd_kernel<float, bf16><<<blocks, 256, 0, s>>>((const float*)x, (bf16*)y, voxels, y_ld);
+  else if (x_dtype == VVAE_BF16 && dtype == VVAE_BF16) vgg_pre_fwd_kernel<bf16, bf16><<<blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, voxels, y_ld);
+  else if (x_dtype == VVAE_BF16 && dtype == VVAE_F32) vgg_pre_fwd_kernel<bf16, float><<<blocks, 256, 0, s>>>((const bf16*)x, (float*)y, voxels, y_ld);
+  else VVAE_REQUIRE(false, "vgg_preprocess_fwd: bad dtypes");
+  return check_launch("vgg_preprocess_fwd");
+}
+
+int vvae_vgg_preprocess_bwd(const void* dy, void* dx, long long voxels, int dy_ld, int dtype, vvae_stream_t stream) {
+  if (voxels <= 0) return VVAE_OK;
+  VVAE_REQUIRE(dy && dx && dy_ld >= 3, "vgg_preprocess_bwd: bad arguments");
+  VVAE_DISPATCH_DTYPE(dtype, T, (vgg_pre_bwd_kernel<T><<<ew_blocks(voxels * 3), 256, 0, as_stream(stream)>>>(
+                                    (const T*)dy, (T*)dx, voxels, dy_ld)));
+  return check_launch("vgg_preprocess_bwd");
 }
 
 int vvae_philox_fill(float* out, long long n, unsigned long long seed, unsigned long long offset, int kind,

@@ -445,6 +445,34 @@ def kl_bwd(mean, logvar, frame_w, scale, tok_per_frame, gscale=None):
     return dmean, dlogvar
 
 
+def relu_(x):
+    """In-place ReLU (VGG feature extractor, train/vgg_tests.py)."""
+    check(lib.vvae_relu_fwd(ptr(x), ptr(x), x.numel(), dt(x), stream()), "vvae_relu_fwd")
+    return x
+
+
+def relu_bwd(dy, y):
+    dx = torch.empty_like(y)
+    check(lib.vvae_relu_bwd(ptr(dy), ptr(y), ptr(dx), y.numel(), dt(y), stream()), "vvae_relu_bwd")
+    return dx
+
+
+def vgg_preprocess_fwd(x, dtype, ld=16):
+    """x [b,t,H,W,3] in [0,1] -> ImageNet-normalised [b,t,H,W,ld] in ``dtype`` with zero pad channels."""
+    x = x.contiguous()
+    y = torch.empty(tuple(x.shape[:4]) + (ld,), dtype=dtype, device=x.device)
+    check(lib.vvae_vgg_preprocess_fwd(ptr(x), dt(x), ptr(y), x.numel() // 3, ld, dt(y), stream()),
+          "vvae_vgg_preprocess_fwd")
+    return y
+
+
+def vgg_preprocess_bwd(dy):
+    dx = torch.empty(tuple(dy.shape[:4]) + (3,), dtype=dy.dtype, device=dy.device)
+    check(lib.vvae_vgg_preprocess_bwd(ptr(dy), ptr(dx), dy.numel() // dy.shape[-1], dy.shape[-1], dt(dy), stream()),
+          "vvae_vgg_preprocess_bwd")
+    return dx
+
+
 def philox_fill_(out, seed, offset, kind):
     """kind 'normal' = the reparameterisation draws, 'uniform' = the Gumbel-gate draws of the same (seed, offset)."""
     assert out.dtype == torch.float32 and out.is_contiguous()
