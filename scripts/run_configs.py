@@ -129,6 +129,15 @@ def rl(dev):
     video = torch.rand(B, T, 256, 256, 3, generator=g).to(torch.bfloat16).to(dev)
     mask = torch.ones(B, T, dtype=torch.bool, device=dev)
     res = {}
+    # graphs first: a capture after eager backward passes trips over their cross-stream dependencies
+    from video_vae_b200.graph import GraphedRLTrainStep
+    for name, fn, hp in (("graph_no_perceptual", None, dict(RL_HP, gamma3=0.0)), ("graph_vgg_perceptual", pfn, dict(RL_HP))):
+        gs = GraphedRLTrainStep(m, flat, video, mask, hp, perceptual_loss_fn=fn, vgg_params=vgg_params)
+        rngs = V.Rngs(3)
+        ms, loss = timed(lambda: gs(video, mask, rngs), 2, 6)
+        res[name] = {"ms_per_step": ms, "clips_per_s": B / (ms * 1e-3), "loss": loss.item(),
+                     "grad_finite": bool(torch.isfinite(flat.grad).all())}
+        del gs
     for name, fn, hp in (("no_perceptual", None, dict(RL_HP, gamma3=0.0)), ("vgg_perceptual", pfn, dict(RL_HP))):
         rngs = V.Rngs(3)
 
@@ -141,7 +150,7 @@ def rl(dev):
         res[name] = {"ms_per_step": ms, "clips_per_s": B / (ms * 1e-3), "loss": loss.item(),
                      "perceptual_loss": float(aux["perceptual_loss"]), "grad_finite": bool(torch.isfinite(flat.grad).all())}
     return {"config": "rl_nonadversarial production step: rl_model, batch 2 x 32 frames x 256^2 (decoder batch 4), bf16, "
-                      "fwd+loss+bwd eager", **res, "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
+                      "fwd+loss+bwd, eager and CUDA-graph", **res, "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30}
 
 
 if __name__ == "__main__":

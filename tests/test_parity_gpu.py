@@ -579,6 +579,44 @@ def test_cuda_graph_step_equals_eager_step(V):
     assert loss_o != loss_e.item()
 
 
+def test_cuda_graph_rl_step_equals_eager_step(V):
+    """graph.GraphedRLTrainStep (rl_model + RL loss + VGG perceptual term in one CUDA graph) reproduces the eager step
+    under the same Rngs.  rl_loss_weight = 0: with it, twins that draw the same keep-mask turn rounding noise into +-1
+    disadvantages (see test_rl_loss_matches_oracle_fp32), which no two runs reproduce."""
+    from video_vae_b200.ddp import FlatParams
+    from video_vae_b200.graph import GraphedRLTrainStep
+    from video_vae_b200.perceptual import get_adversarial_perceptual_loss_fn, load_vgg
+    from video_vae_b200.rl_losses import DEFAULT_HPARAMS, loss_fn
+    from video_vae_b200.rl_model import VideoVAE as RL
+    m = RL(64, 64, 3, 16, 1, 1, 256, 2, 128, 32, 8, 4, V.Rngs(2), dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.05, generator=torch.Generator(device="cuda").manual_seed(7))
+    flat = FlatParams(m)
+    flat.enable_bf16_shadow()
+    vgg, vp = load_vgg(V.Rngs(3))
+    pfn = get_adversarial_perceptual_loss_fn(vgg)
+    hp = dict(DEFAULT_HPARAMS, rl_loss_weight=0.0)
+    g = _gen(9)
+    video = torch.rand(2, 4, 64, 64, 3, generator=g).to(torch.bfloat16).cuda()
+    mask = torch.ones(2, 4, dtype=torch.bool).cuda()
+    mask[1, 3:] = False
+    graphed = GraphedRLTrainStep(m, flat, video, mask, hp, perceptual_loss_fn=pfn, vgg_params=vp)
+    outs = []
+    for _ in range(2):
+        loss_g = graphed(video, mask, V.Rngs(5))
+        torch.cuda.synchronize()
+        outs.append((loss_g.item(), flat.grad.clone(), graphed.aux["selection_mask"].clone()))
+    flat.zero_grad()
+    loss_e, aux_e = loss_fn(m, video, mask[:, None, None, :], mask, V.Rngs(5), hp, pfn, vp, train=True)
+    loss_e.backward()
+    torch.cuda.synchronize()
+    assert float(aux_e["perceptual_loss"]) > 0
+    for lg, gg, sm in outs:
+        assert torch.equal(sm, aux_e["selection_mask"])                 # same Bernoulli draws
+        assert abs(lg - loss_e.item()) <= 1e-3 * abs(loss_e.item())
+        assert rel_err(gg, flat.grad) < 2e-3
+
+
 def test_fused_clip_adam_matches_optimizer_oracle(V):
     """ddp.FlatAdam (vvae_sumsq_f32 + vvae_adam_step on the flat fp32 buffers) against the oracle's
     optax.chain(clip_by_global_norm(1.0), adam(schedule)) restatement, clip active and inactive, schedule-driven lr."""

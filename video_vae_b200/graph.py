@@ -32,11 +32,11 @@ class GraphedTrainStep:
         self.video = torch.empty_like(video_like)
         self.mask = torch.empty_like(mask_like)
         self.noise = torch.empty(b, t, hw, lat, dtype=torch.float32, device=dev)
-        self.gumbel_u = torch.empty(b, t, 1, dtype=torch.float32, device=dev)
+        self.gate_u = torch.empty(self._gate_shape(b, t), dtype=torch.float32, device=dev)
         self.video.copy_(video_like)
         self.mask.copy_(mask_like)
         ops.philox_fill_(self.noise, 0, 1 << 40, "normal")
-        ops.philox_fill_(self.gumbel_u, 0, 2 << 40, "uniform")
+        ops.philox_fill_(self.gate_u, 0, 2 << 40, "uniform")
         self.graph = torch.cuda.CUDAGraph()
         # external event recorded INSIDE the graph when backward reaches the latent (all decoder gradients written): a
         # communication stream can start reducing the decoder's gradients while the encoder's backward still runs
@@ -66,24 +66,59 @@ class GraphedTrainStep:
         finally:
             ops.PROFILE = prof
 
+    # -- what differs between the model variants: the gate's uniform draws and the loss
+    def _gate_shape(self, b, t):
+        return (b, t, 1)                                # Gumbel-sigmoid gate: one draw per frame (train/model.py:57-59)
+
+    def _loss(self):
+        return loss_fn(self.model, self.video, self.mask[:, None, None, :], self.mask, None, self.hp, train=True,
+                       noise=self.noise, gumbel_u=self.gate_u)
+
+    def _refresh_draws(self, rngs):
+        """Same draws, same order as the eager path: the encoder's gate first, then the reparameterisation."""
+        seed, off = rngs.sampling()
+        ops.philox_fill_(self.gate_u, seed, off, "uniform")
+        seed, off = rngs.sampling()
+        ops.philox_fill_(self.noise, seed, off, "normal")
+
     def _body(self):
         self.flat.zero_grad()
         if self.reducer is not None:
             self.reducer.start_step()
-        loss, aux = loss_fn(self.model, self.video, self.mask[:, None, None, :], self.mask, None, self.hp, train=True,
-                            noise=self.noise, gumbel_u=self.gumbel_u)
+        loss, aux = self._loss()
         loss.backward()
         if self.reducer is not None:
             self.reducer.finish_step()
         return loss.detach(), {k: v.detach() for k, v in aux.items()}
 
     def __call__(self, video, mask, rngs):
-        """Same draws, same order as the eager path: the encoder's gate first, then the reparameterisation."""
         self.video.copy_(video, non_blocking=True)
         self.mask.copy_(mask, non_blocking=True)
-        seed, off = rngs.sampling()
-        ops.philox_fill_(self.gumbel_u, seed, off, "uniform")
-        seed, off = rngs.sampling()
-        ops.philox_fill_(self.noise, seed, off, "normal")
+        self._refresh_draws(rngs)
         self.graph.replay()
         return self.loss
+
+
+class GraphedRLTrainStep(GraphedTrainStep):
+    """The RL step (rl_model.VideoVAE + rl_losses.loss_fn, train/rl_nonadversarial.py:100-198) as one CUDA graph.
+    ``perceptual_loss_fn`` / ``vgg_params`` as in the reference's loss_fn (None drops the term)."""
+
+    def __init__(self, model, flat, video_like, mask_like, hparams=None, perceptual_loss_fn=None, vgg_params=None, **kw):
+        from .rl_losses import DEFAULT_HPARAMS as RL_HP
+        self.perceptual_loss_fn, self.vgg_params = perceptual_loss_fn, vgg_params
+        super().__init__(model, flat, video_like, mask_like, dict(RL_HP if hparams is None else hparams), **kw)
+
+    def _gate_shape(self, b, t):
+        return (2 * b, t)                               # Bernoulli keep-mask: one draw per frame of the doubled batch
+
+    def _loss(self):
+        from .rl_losses import loss_fn as rl_loss_fn
+        return rl_loss_fn(self.model, self.video, self.mask[:, None, None, :], self.mask, None, self.hp,
+                          self.perceptual_loss_fn, self.vgg_params, train=True, noise=self.noise, bernoulli_u=self.gate_u)
+
+    def _refresh_draws(self, rngs):
+        """Eager order of rl_model.VideoVAE.forward: the Gaussian latent noise first, then the keep-mask draws."""
+        seed, off = rngs.sampling()
+        ops.philox_fill_(self.noise, seed, off, "normal")
+        seed, off = rngs.sampling()
+        ops.philox_fill_(self.gate_u, seed, off, "uniform")

@@ -15,6 +15,7 @@ from torch.autograd import Function
 
 from . import ops
 from ._ffi import require_device
+from .rl_model import repeat2
 
 DEFAULT_HPARAMS = {  # rl_nonadversarial.py:47-57, 255-263
     "gamma1": 0.2,
@@ -83,10 +84,10 @@ class PerSampleLossFn(Function):
 def loss_terms(video, reconstruction, selection, selection_mask, logvar, mean, original_mask, hparams,
                perceptual_loss_fn=None, vgg_params=None):
     """rl_nonadversarial.py:104-186, everything after the model call."""
-    output_mask = original_mask.repeat_interleave(2, dim=0)                        # :104
+    output_mask = repeat2(original_mask)                                           # :104
     m = output_mask.to(torch.float32)
     seq = torch.clamp(m.sum(dim=1, keepdim=True), min=1.0)                         # :105-106
-    video2 = video.repeat_interleave(2, dim=0)                                     # :110
+    video2 = repeat2(video)                                                        # :110
     rec_ps, kl_loss, per_sample_error, per_sample_mae = PerSampleLossFn.apply(
         video2, reconstruction, logvar, mean, output_mask, hparams["gamma4"])
     if perceptual_loss_fn is not None:
@@ -108,8 +109,12 @@ def loss_terms(video, reconstruction, selection, selection_mask, logvar, mean, o
     raw_probs = torch.clamp(torch.abs(sel + actions - 1), 1e-6, 1.0 - 1e-6)       # :163
     rl_mask = output_mask.reshape(-1, 2, t).to(torch.bool)
     one = torch.ones_like(raw_probs)
-    probs = torch.where(rl_mask, raw_probs / raw_probs.detach(), one).prod(dim=2, keepdim=True)        # :164-171
-    raw_traj = torch.where(rl_mask, raw_probs, one).prod(dim=2, keepdim=True)      # :168-169
+    # :164-171  prod_t(p_t) with every factor p_t = raw/stop_grad(raw) == 1: value 1, d/dp_t = 1.  Written as
+    # 1 + sum_t(p_t - 1), which has exactly that value and gradient; torch's prod backward looks for zeros with a host
+    # read, which a CUDA-graph capture forbids.
+    ratio = torch.where(rl_mask, raw_probs / raw_probs.detach(), one)
+    probs = 1.0 + (ratio - 1.0).sum(dim=2, keepdim=True)
+    raw_traj = torch.where(rl_mask, raw_probs, one).detach().prod(dim=2, keepdim=True)   # :168-169 (logged only)
     rl_loss = probs * disadvantages[:, :, None]
     loss = per_sample_loss.mean() + rl_loss.mean() * hparams["rl_loss_weight"]     # :174
     return loss, {

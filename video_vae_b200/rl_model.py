@@ -15,6 +15,12 @@ from .layers import FactoredAttention, _default_device
 from .model import Decoder, Encoder as _Encoder
 
 
+def repeat2(a):
+    """einops 'b ... -> (b 2) ...' (each sample followed by its copy).  Not ``repeat_interleave``: with an integer
+    count that op sizes its output through a host read, which a CUDA-graph capture forbids."""
+    return a.unsqueeze(1).expand(a.shape[0], 2, *a.shape[1:]).reshape(2 * a.shape[0], *a.shape[1:])
+
+
 class Encoder(_Encoder):
     """train/rl_model.py:14-60.  Returns (mean, log_variance, selection[b,t,1]) with selection a probability."""
 
@@ -53,7 +59,7 @@ class VideoVAE(nn.Module):
     def forward(self, x, mask, rngs, train=True, noise=None, bernoulli_u=None):
         mean, log_variance, selection = self.encoder(x, mask, rngs, train=train)
         b, t = selection.shape[:2]
-        rep = lambda a: a.repeat_interleave(2, dim=0)                      # noqa: E731  'b ... -> (b 2) ...'
+        rep = repeat2                                                      # 'b ... -> (b 2) ...'
         selection = rep(selection).reshape(2 * b, t, 1, 1)
         mean2, lv2, mask2 = rep(mean), rep(log_variance), rep(mask)
         # one Gaussian draw per ORIGINAL sample (the reference samples the latent before duplicating it)
