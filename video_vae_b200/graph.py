@@ -7,6 +7,12 @@ the input clip and mask (copied in before the replay) and the Philox draws of th
 ``vvae_philox_fill`` from the same (seed, offset) pairs the fused kernels would use, so a replay is bit-identical to
 the eager step).  The optimizer (and, for N > 1, the gradient all-reduce) runs outside the graph: the bias-corrected
 Adam constants change every step and are passed by value.
+
+Capture BEFORE running eager backward passes in the same process: after an eager ``loss.backward()`` the autograd
+engine's stream bookkeeping for the leaves makes a later capture fail with "dependency created on uncaptured work in
+another stream" (tests and scripts/run_configs.py capture first, then run their eager comparisons).  Nothing on the
+captured path may read device data from the host: ``repeat_interleave`` with an integer count and the backward of
+``prod`` both do, which is why rl_model / rl_losses avoid them.
 """
 import torch
 
