@@ -87,6 +87,12 @@ CASES = [
     ("temporal_L12_hw20_masked", 2, 12, 20, True, True),
     ("temporal_L5_hw7", 3, 5, 7, True, False),
     ("spatial_L9_masked", 1, 6, 9, False, True),
+    ("temporal_L17_hw5_masked", 2, 17, 5, True, True),
+    ("temporal_L24_hw9", 1, 24, 9, True, False),
+    ("temporal_L40_hw6_masked", 2, 40, 6, True, True),
+    ("temporal_L48_hw3", 1, 48, 3, True, False),
+    ("temporal_L64_hw5_masked", 2, 64, 5, True, True),
+    ("spatial_L36_masked", 1, 3, 36, False, True),
     ("long_L384", 1, 2, 384, False, False),
     ("long_L512_masked", 1, 3, 512, False, True),
     ("long_L1024", 1, 1, 1024, False, False),
@@ -106,7 +112,10 @@ if __name__ == "__main__":
             print(json.dumps(r), flush=True)
             f.write(json.dumps(r) + "\n")
         for c in [("prod_spatial", 8, 16, 256, False, False), ("prod_temporal", 8, 16, 256, True, True),
-                  ("prod_temporal_tcgen05", 8, 16, 256, True, True), ("prod_cfg5_spatial", 1, 64, 1024, False, False)]:
+                  ("prod_temporal_tcgen05", 8, 16, 256, True, True), ("prod_cfg5_spatial", 1, 64, 1024, False, False),
+                  ("prod_rl_temporal_L32", 4, 32, 256, True, True), ("prod_rl_temporal_L32_tcgen05", 4, 32, 256, True, True),
+                  ("prod_cfg5_temporal_L64", 1, 64, 1024, True, False),
+                  ("prod_cfg5_temporal_L64_tcgen05", 1, 64, 1024, True, False)]:
             if sel and c[0] not in sel:
                 continue
             # key 9: keep L <= 16 on the packed-tile tcgen05 kernels instead of the one-warp-per-sequence kernel

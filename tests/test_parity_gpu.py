@@ -444,11 +444,17 @@ def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked
     ("spatial_L9_masked", 1, 6, 9, False, True),
     ("spatial_L16", 2, 5, 16, False, False),
     ("temporal_allmasked_clip", 2, 16, 16, True, True),
+    ("temporal_L17_masked", 2, 17, 5, True, True),
+    ("temporal_L24", 1, 24, 9, True, False),
+    ("temporal_L40_masked", 2, 40, 6, True, True),
+    ("temporal_L63_masked", 1, 63, 3, True, True),
+    ("spatial_L36_masked", 1, 3, 36, False, True),
 ])
 def test_short_sequence_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked):
-    """bf16, head_dim 64, L <= 16 (the production temporal attention is L = 16): the one-warp-per-(sequence, head)
-    mma.sync kernels of attn_warp.cu (what BACKEND_AUTO selects) against oracle autograd: every length 1..16 class,
-    ragged sequence counts, key-padding masks, a fully masked clip."""
+    """bf16, head_dim 64: the mma.sync kernels of attn_warp.cu (what BACKEND_AUTO selects for L <= 16 -- the production
+    temporal attention is L = 16 -- and for every other length up to 64 that the tcgen05 tiles do not take, as the
+    frame-count curriculum produces) against oracle autograd: ragged sequence counts, key-padding masks, a fully masked
+    clip, lengths that are not multiples of 16."""
     from video_vae_b200 import _ffi
     _attention_case(name, b, t, hw, temporal, masked, _ffi.BACKEND_AUTO)
 

@@ -357,7 +357,10 @@ int vvae_attn_fwd(const vvae_attn_args* args, vvae_stream_t stream) {
   int rc = attn_validate(args, false);
   if (rc) return rc;
   if (args->n_outer == 0) return VVAE_OK;
-  if (args->backend == VVAE_BACKEND_AUTO && !g_dbg[9] && attn_warp_supported(*args, false))
+  // L <= 16: one warp per (sequence, head).  L = 32 / 64 (and 128 ..): tcgen05 tiles.  Any other L <= 64 (the frame-count
+  // curriculum of train/rl_nonadversarial.py:287-295 produces them): the multi-block warp kernels.
+  if (args->backend == VVAE_BACKEND_AUTO && !g_dbg[9] && attn_warp_supported(*args, false) &&
+      (args->L <= 16 || !attn_tc_supported(*args)))
     return attn_warp_fwd(*args, as_stream(stream));
   if (args->backend != VVAE_BACKEND_SIMT && attn_tc_supported(*args)) return attn_tc_fwd(*args, as_stream(stream));
   if (args->backend == VVAE_BACKEND_TCGEN05) {
@@ -371,7 +374,8 @@ int vvae_attn_bwd(const vvae_attn_args* args, vvae_stream_t stream) {
   int rc = attn_validate(args, true);
   if (rc) return rc;
   if (args->n_outer == 0) return VVAE_OK;
-  if (args->backend == VVAE_BACKEND_AUTO && !g_dbg[9] && attn_warp_supported(*args, true))
+  if (args->backend == VVAE_BACKEND_AUTO && !g_dbg[9] && attn_warp_supported(*args, true) &&
+      (args->L <= 16 || !attn_tc_bwd_supported(*args)))
     return attn_warp_bwd(*args, as_stream(stream));
   if (args->backend != VVAE_BACKEND_SIMT && attn_tc_bwd_supported(*args)) return attn_tc_bwd(*args, as_stream(stream));
   if (args->backend == VVAE_BACKEND_TCGEN05) {

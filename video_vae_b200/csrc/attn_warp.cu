@@ -1,4 +1,4 @@
-// Short-sequence attention (L <= 16, head_dim 64, bf16): temporal attention over 16 frames (train/layers.py:204-214 at
+// Short-sequence attention (L <= 64, head_dim 64, bf16; the single-warp form below is L <= 16): temporal attention over 16 frames (train/layers.py:204-214 at
 // the production shape: 2048 sequences x 8 heads of 16 tokens).  At this length the work is HBM-bound (10 KB in, 6 KB out
 // per (sequence, head) in the backward), and a 128-row tcgen05 tile holding 8 block-diagonal sequences spends its time
 // in fixed per-tile latency.  Here ONE WARP owns one (sequence, head): every operand lives in registers, the 16x16 score
@@ -97,15 +97,18 @@ __device__ __forceinline__ void mma_RRt(float (&c)[2][4], const RowPair& x, cons
   }
 }
 
-// out[16 x 64] = A[16 x 16] . X, A given as an A fragment, X in P layout; acc[nt][j]: see the header comment
+// out[16 x 64] (+)= A[16 x 16] . X, A given as an A fragment, X in P layout; acc[nt][j]: see the header comment
+template <bool ACCUM = false>
 __device__ __forceinline__ void mma_AP(float (&acc)[8][4], const uint32_t (&a)[4], const RowQuad& x) {
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt) {
     const uint32_t sel = (nt & 1) ? 0x7632u : 0x5410u;
     const uint32_t b0 = __byte_perm(x.r[0][nt >> 1], x.r[1][nt >> 1], sel);
     const uint32_t b1 = __byte_perm(x.r[2][nt >> 1], x.r[3][nt >> 1], sel);
+    if (!ACCUM) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+    }
     mma16816(acc[nt], a[0], a[1], a[2], a[3], b0, b1);
   }
 }
@@ -327,9 +330,259 @@ __global__ void __launch_bounds__(128) attn_warp_bwd_kernel(const AttnWarpParams
   store_acc(p.dk + t.tok0 * p.dk_rs + hoff, p.dk_rs, p.ts_pos, acc, g, tig, L);
 }
 
+// ------------------------------------------------------------------ 16 < L <= 64: NB = ceil(L/16) blocks of 16 rows
+// Forward: one CTA per (sequence, head), warp w owns query block w (scores of all NB key blocks in registers, keys and
+// values streamed block by block).  Backward: 3 NB independent warps per (sequence, head): dQ of a query block (streams
+// the key blocks), dV of a key block and dK of a key block (stream the query blocks).  S and dP are recomputed by each
+// role (tiny MMAs) instead of being reduced across warps; the re-read operands hit L1 (the warps of one sequence are
+// neighbours in the same CTA or the next one).
+struct TaskCtx64 {
+  long long tok0;
+  int head;
+  unsigned long long valid, inlen;
+};
+
+__device__ __forceinline__ TaskCtx64 task_ctx64(const AttnWarpParams& p, long long task, int lane) {
+  TaskCtx64 t;
+  const long long seq = task / p.heads;
+  t.head = (int)(task - seq * p.heads);
+  const long long o = seq / p.n_inner, i = seq - o * p.n_inner;
+  t.tok0 = o * p.ts_outer + i * p.ts_inner;
+  t.inlen = (p.L >= 64) ? ~0ull : ((1ull << p.L) - 1ull);
+  bool ok0 = lane < p.L, ok1 = lane + 32 < p.L;
+  if (p.mask) {
+    const unsigned char* m = p.mask + (seq / p.mask_seq_div) * p.ms_seq;
+    if (ok0) ok0 = m[(long long)lane * p.ms_k] != 0;
+    if (ok1) ok1 = m[(long long)(lane + 32) * p.ms_k] != 0;
+  }
+  const unsigned lo = __ballot_sync(0xffffffffu, ok0), hi = __ballot_sync(0xffffffffu, ok1);
+  t.valid = (unsigned long long)lo | ((unsigned long long)hi << 32);
+  return t;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(32 * NB) attn_warp_fwd_mb_kernel(const AttnWarpParams p) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, g = lane >> 2, tig = lane & 3;
+  const long long task = blockIdx.x;
+  const TaskCtx64 t = task_ctx64(p, task, lane);
+  const int L = p.L, q0 = 16 * w;
+  if (q0 >= L) return;
+  const long long hoff = t.head * 64;
+  const bf16* kb = p.k + t.tok0 * p.k_rs + hoff;
+  const bf16* vb = p.v + t.tok0 * p.v_rs + hoff;
+  RowPair q;
+  load_R(q, p.q + (t.tok0 + (long long)q0 * p.ts_pos) * p.q_rs + hoff, p.q_rs, p.ts_pos, g, tig, L - q0);
+  float s[NB][2][4];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    RowPair k;
+    load_R(k, kb + (long long)(16 * j) * p.ts_pos * p.k_rs, p.k_rs, p.ts_pos, g, tig, L - 16 * j);
+    mma_RRt(s[j], q, k);
+  }
+  float mx[2] = {-FLT_MAX, -FLT_MAX};
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = 16 * j + 8 * nt + 2 * tig + (e & 1);
+        float x = s[j][nt][e] * p.scale;
+        if (!((t.valid >> key) & 1ull)) x = AW_MASKED;
+        if (!((t.inlen >> key) & 1ull)) x = -FLT_MAX;
+        s[j][nt][e] = x;
+        mx[e >> 1] = fmaxf(mx[e >> 1], x);
+      }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = 16 * j + 8 * nt + 2 * tig + (e & 1);
+        float x = aw_exp2((s[j][nt][e] - mx[e >> 1]) * AW_LOG2E);
+        if (!((t.inlen >> key) & 1ull)) x = 0.f;
+        s[j][nt][e] = x;
+        sum[e >> 1] += x;
+      }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 1);
+    sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], 2);
+  }
+  const float inv0 = 1.f / sum[0], inv1 = 1.f / sum[1];
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16(s[j][0][0] * inv0, s[j][0][1] * inv0);
+    pa[1] = pack_bf16(s[j][0][2] * inv1, s[j][0][3] * inv1);
+    pa[2] = pack_bf16(s[j][1][0] * inv0, s[j][1][1] * inv0);
+    pa[3] = pack_bf16(s[j][1][2] * inv1, s[j][1][3] * inv1);
+    RowQuad v;
+    load_P(v, vb + (long long)(16 * j) * p.ts_pos * p.v_rs, p.v_rs, p.ts_pos, g, tig, L - 16 * j);
+    mma_AP<true>(acc, pa, v);
+  }
+  store_acc(p.out_o + (t.tok0 + (long long)q0 * p.ts_pos) * p.o_rs + hoff, p.o_rs, p.ts_pos, acc, g, tig, L - q0);
+  if (tig == 0) {
+    float* lse = p.lse + task * L + q0;
+    if (q0 + g < L) lse[g] = mx[0] + __logf(sum[0]);
+    if (q0 + g + 8 < L) lse[g + 8] = mx[1] + __logf(sum[1]);
+  }
+}
+
+// delta = rowsum(dO o O) and lse (log2 units) of the 16 query rows starting at q0: rows g, g+8 per lane
+__device__ __forceinline__ void aw_row_stats(const AttnWarpParams& p, long long tok0, long long hoff, const float* lse_seq,
+                                             int q0, int L, const RowPair& d_o, int g, int tig, float (&delta)[2],
+                                             float (&lse_r)[2]) {
+  RowPair o;
+  load_R(o, p.o + (tok0 + (long long)q0 * p.ts_pos) * p.o_rs + hoff, p.o_rs, p.ts_pos, g, tig, L - q0);
+  float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    d0 += bf_lo(o.lo[i]) * bf_lo(d_o.lo[i]) + bf_hi(o.lo[i]) * bf_hi(d_o.lo[i]);
+    d1 += bf_lo(o.hi[i]) * bf_lo(d_o.hi[i]) + bf_hi(o.hi[i]) * bf_hi(d_o.hi[i]);
+  }
+  d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+  d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+  delta[0] = d0; delta[1] = d1;
+  lse_r[0] = (q0 + g < L) ? lse_seq[q0 + g] * AW_LOG2E : 0.f;
+  lse_r[1] = (q0 + g + 8 < L) ? lse_seq[q0 + g + 8] * AW_LOG2E : 0.f;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(128, 3) attn_warp_bwd_mb_kernel(const AttnWarpParams p) {
+  // independent warps: (task, role) with role < NB: dQ of query block role; < 2 NB: dV of key block; else dK of key block
+  const int lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+  const long long gw = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const long long task = gw / (3 * NB);
+  if (task >= p.n_tasks) return;
+  const int role = (int)(gw - task * (3 * NB));
+  const TaskCtx64 t = task_ctx64(p, task, lane);
+  const int L = p.L;
+  const bool any_valid = t.valid != 0ull;
+  const float inv_L = 1.f / (float)L;
+  const long long hoff = t.head * 64;
+  const float sl2 = p.scale * AW_LOG2E;
+  const float* lse_seq = p.lse + task * L;
+  const bf16* qb = p.q + t.tok0 * p.q_rs + hoff;
+  const bf16* kb = p.k + t.tok0 * p.k_rs + hoff;
+  const bf16* vb = p.v + t.tok0 * p.v_rs + hoff;
+  const bf16* gb = p.d_o + t.tok0 * p.do_rs + hoff;
+  float acc[8][4];
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  if (role < NB) {
+    // ---------------- dQ of query block `role`: streams the key blocks
+    const int q0 = 16 * role;
+    if (q0 >= L) return;
+    RowPair q, d_o;
+    load_R(q, qb + (long long)q0 * p.ts_pos * p.q_rs, p.q_rs, p.ts_pos, g, tig, L - q0);
+    load_R(d_o, gb + (long long)q0 * p.ts_pos * p.do_rs, p.do_rs, p.ts_pos, g, tig, L - q0);
+    float delta[2], lse_r[2];
+    aw_row_stats(p, t.tok0, hoff, lse_seq, q0, L, d_o, g, tig, delta, lse_r);
+#pragma unroll 1
+    for (int j = 0; j < NB; ++j) {
+      const int k0 = 16 * j;
+      if (k0 >= L) break;
+      RowPair k, v;
+      load_R(k, kb + (long long)k0 * p.ts_pos * p.k_rs, p.k_rs, p.ts_pos, g, tig, L - k0);
+      load_R(v, vb + (long long)k0 * p.ts_pos * p.v_rs, p.v_rs, p.ts_pos, g, tig, L - k0);
+      float s[2][4], dp[2][4], ds[2][4];
+      mma_RRt(s, q, k);
+      mma_RRt(dp, d_o, v);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = k0 + 8 * nt + 2 * tig + (e & 1), h = e >> 1, qrow = q0 + g + 8 * h;
+          const bool kv = (t.valid >> key) & 1ull, kin = (t.inlen >> key) & 1ull;
+          const float pv = aw_prob(s[nt][e] * sl2, lse_r[h], kv, kin, qrow < L, any_valid, inv_L);
+          ds[nt][e] = kv ? pv * (dp[nt][e] - delta[h]) * p.scale : 0.f;
+        }
+      uint32_t dsa[4];
+      dsa[0] = pack_bf16(ds[0][0], ds[0][1]); dsa[1] = pack_bf16(ds[0][2], ds[0][3]);
+      dsa[2] = pack_bf16(ds[1][0], ds[1][1]); dsa[3] = pack_bf16(ds[1][2], ds[1][3]);
+      RowQuad x;
+      load_P(x, kb + (long long)k0 * p.ts_pos * p.k_rs, p.k_rs, p.ts_pos, g, tig, L - k0);
+      mma_AP<true>(acc, dsa, x);
+    }
+    store_acc(p.dq + (t.tok0 + (long long)q0 * p.ts_pos) * p.dq_rs + hoff, p.dq_rs, p.ts_pos, acc, g, tig, L - q0);
+    return;
+  }
+  // ---------------- dV (want_dk = false) or dK (want_dk = true) of one key block: streams the query blocks
+  const bool want_dk = role >= 2 * NB;
+  const int k0 = 16 * (role - (want_dk ? 2 * NB : NB));
+  if (k0 >= L) return;
+  RowPair k, v;
+  load_R(k, kb + (long long)k0 * p.ts_pos * p.k_rs, p.k_rs, p.ts_pos, g, tig, L - k0);
+  if (want_dk) load_R(v, vb + (long long)k0 * p.ts_pos * p.v_rs, p.v_rs, p.ts_pos, g, tig, L - k0);
+#pragma unroll 1
+  for (int i = 0; i < NB; ++i) {
+    const int q0 = 16 * i;
+    if (q0 >= L) break;
+    // per-COLUMN (query) statistics of the transposed tile: columns q0 + 8 nt + 2 tig + e
+    float lse_c[2][2], delta_c[2][2];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int qc = q0 + 8 * nt + 2 * tig + e;
+        lse_c[nt][e] = qc < L ? lse_seq[qc] * AW_LOG2E : 0.f;
+        delta_c[nt][e] = 0.f;
+      }
+    RowPair q;
+    load_R(q, qb + (long long)q0 * p.ts_pos * p.q_rs, p.q_rs, p.ts_pos, g, tig, L - q0);
+    float s[2][4], dp[2][4];
+    mma_RRt(s, k, q);
+    if (want_dk) {
+      RowPair d_o;
+      load_R(d_o, gb + (long long)q0 * p.ts_pos * p.do_rs, p.do_rs, p.ts_pos, g, tig, L - q0);
+      float delta[2], lse_r[2];
+      aw_row_stats(p, t.tok0, hoff, lse_seq, q0, L, d_o, g, tig, delta, lse_r);
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) delta_c[nt][e] = __shfl_sync(0xffffffffu, delta[nt], (2 * tig + e) * 4);
+      mma_RRt(dp, v, d_o);
+    }
+    float o[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qcol = q0 + 8 * nt + 2 * tig + (e & 1), h = e >> 1, key = k0 + g + 8 * h;
+        const bool kv = (t.valid >> key) & 1ull, kin = (t.inlen >> key) & 1ull;
+        const float pv = aw_prob(s[nt][e] * sl2, lse_c[nt][e & 1], kv, kin, qcol < L, any_valid, inv_L);
+        o[nt][e] = want_dk ? (kv ? pv * (dp[nt][e] - delta_c[nt][e & 1]) * p.scale : 0.f) : pv;
+      }
+    uint32_t fa[4];
+    fa[0] = pack_bf16(o[0][0], o[0][1]); fa[1] = pack_bf16(o[0][2], o[0][3]);
+    fa[2] = pack_bf16(o[1][0], o[1][1]); fa[3] = pack_bf16(o[1][2], o[1][3]);
+    RowQuad x;
+    if (want_dk) load_P(x, qb + (long long)q0 * p.ts_pos * p.q_rs, p.q_rs, p.ts_pos, g, tig, L - q0);   // dK += dS^T . Q_i
+    else load_P(x, gb + (long long)q0 * p.ts_pos * p.do_rs, p.do_rs, p.ts_pos, g, tig, L - q0);         // dV += P^T . dO_i
+    mma_AP<true>(acc, fa, x);
+  }
+  if (want_dk) store_acc(p.dk + (t.tok0 + (long long)k0 * p.ts_pos) * p.dk_rs + hoff, p.dk_rs, p.ts_pos, acc, g, tig, L - k0);
+  else store_acc(p.dv + (t.tok0 + (long long)k0 * p.ts_pos) * p.dv_rs + hoff, p.dv_rs, p.ts_pos, acc, g, tig, L - k0);
+}
+
 // ------------------------------------------------------------------ host
 static bool aw_fill(const vvae_attn_args& a, AttnWarpParams& p, bool bwd) {
-  if (a.dtype != VVAE_BF16 || a.hd != 64 || a.L < 1 || a.L > 16) return false;
+  if (a.dtype != VVAE_BF16 || a.hd != 64 || a.L < 1 || a.L > 64) return false;
   if (a.mask && (a.ms_head != 0 || a.ms_q != 0)) return false;       // key-padding masks only
   auto al16 = [](const void* x) { return ((uintptr_t)x % 16) == 0; };
   if (!al16(a.q) || !al16(a.k) || !al16(a.v) || !al16(a.o)) return false;
@@ -339,7 +592,7 @@ static bool aw_fill(const vvae_attn_args& a, AttnWarpParams& p, bool bwd) {
     if ((a.do_rs % 8) || (a.dq_rs % 8) || (a.dk_rs % 8) || (a.dv_rs % 8)) return false;
   }
   const long long n_tasks = (long long)a.n_outer * a.n_inner * a.heads;
-  if (n_tasks <= 0 || cdiv(n_tasks, 4) > 0x7fffffffLL) return false;
+  if (n_tasks <= 0 || n_tasks * 3 > 0x7fffffffLL) return false;
   p.q = (const bf16*)a.q; p.k = (const bf16*)a.k; p.v = (const bf16*)a.v;
   p.q_rs = a.q_rs; p.k_rs = a.k_rs; p.v_rs = a.v_rs; p.o_rs = a.o_rs;
   p.o = (const bf16*)a.o; p.out_o = (bf16*)a.o;
@@ -365,7 +618,11 @@ int attn_warp_fwd(const vvae_attn_args& a, cudaStream_t s) {
     set_error("attention: shape not supported by the short-sequence kernel");
     return VVAE_ERR_UNSUPPORTED;
   }
-  attn_warp_fwd_kernel<<<(unsigned)cdiv(p.n_tasks, 4), 128, 0, s>>>(p);
+  const int nb = (p.L + 15) / 16;
+  if (nb == 1) attn_warp_fwd_kernel<<<(unsigned)cdiv(p.n_tasks, 4), 128, 0, s>>>(p);
+  else if (nb == 2) attn_warp_fwd_mb_kernel<2><<<(unsigned)p.n_tasks, 64, 0, s>>>(p);
+  else if (nb == 3) attn_warp_fwd_mb_kernel<3><<<(unsigned)p.n_tasks, 96, 0, s>>>(p);
+  else attn_warp_fwd_mb_kernel<4><<<(unsigned)p.n_tasks, 128, 0, s>>>(p);
   return check_launch("attn_warp_fwd");
 }
 
@@ -375,7 +632,11 @@ int attn_warp_bwd(const vvae_attn_args& a, cudaStream_t s) {
     set_error("attention bwd: shape not supported by the short-sequence kernel");
     return VVAE_ERR_UNSUPPORTED;
   }
-  attn_warp_bwd_kernel<<<(unsigned)cdiv(p.n_tasks, 4), 128, 0, s>>>(p);
+  const int nb = (p.L + 15) / 16;
+  if (nb == 1) attn_warp_bwd_kernel<<<(unsigned)cdiv(p.n_tasks, 4), 128, 0, s>>>(p);
+  else if (nb == 2) attn_warp_bwd_mb_kernel<2><<<(unsigned)cdiv(p.n_tasks * 6, 4), 128, 0, s>>>(p);
+  else if (nb == 3) attn_warp_bwd_mb_kernel<3><<<(unsigned)cdiv(p.n_tasks * 9, 4), 128, 0, s>>>(p);
+  else attn_warp_bwd_mb_kernel<4><<<(unsigned)cdiv(p.n_tasks * 12, 4), 128, 0, s>>>(p);
   return check_launch("attn_warp_bwd");
 }
 
