@@ -191,6 +191,7 @@ def run_ours(args):
         model.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7))
     flat = FlatParams(model)
     flat.enable_bf16_shadow()
+    flat.broadcast(src=0)     # rank 0's weights everywhere (distributed_train.py:339 broadcast_one_to_all); untimed
     reducer = GradAllReducer(flat) if world > 1 else None
     opt = None if args.no_optimizer else FlatAdam(flat, lr=5e-5)
     hp = dict(V.DEFAULT_HPARAMS, gamma4=0.1)   # MSE + selection + KL + MAE terms

@@ -292,6 +292,10 @@ int vvae_vgg_preprocess_bwd(const void* dy, void* dx, long long voxels, int dy_l
 /* ---- optimizer ("next" row f1: optax.chain(clip_by_global_norm, adam), train/rl_nonadversarial.py:241-253) ---- */
 /* out[0] += sum g^2 */
 int vvae_sumsq_f32(const float* g, long long n, float* out1, vvae_stream_t stream);
+/* Same sum with a fixed summation order (bit-reproducible: data-parallel replicas compute the identical clip scale).
+ * partials: caller scratch of vvae_sumsq_partials(n) floats. */
+int vvae_sumsq_partials(long long n);
+int vvae_sumsq_f32_det(const float* g, long long n, float* partials, float* out1, vvae_stream_t stream);
 /* Adam with bias correction on flat fp32 buffers; grad scaled by min(1, clip/ (sqrt(*gnorm_sq)+1e-6)) if gnorm_sq. */
 int vvae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                    int step, const float* gnorm_sq, float clip, float grad_scale, vvae_stream_t stream);

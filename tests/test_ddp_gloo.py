@@ -48,6 +48,13 @@ def _worker(rank, world, port, out):
             assert torch.equal(p.detach(), ref[n])
             assert p.grad is not None and p.grad.shape == p.shape
         assert all(o % 8 == 0 for o in flat.offsets) and flat.total % 8 == 0
+        # start-up replication: rank 1 perturbs its copy, the broadcast restores rank 0's values everywhere
+        if rank == 1:
+            with torch.no_grad():
+                flat.flat.add_(1.0)
+        flat.broadcast(src=0)
+        for n, p in model.named_parameters():
+            assert torch.equal(p.detach(), ref[n]), n
         red = GradAllReducer(flat, bucket_bytes=128)           # tiny buckets -> several of them
         covered = sorted((s, e) for s, e, _ in red.buckets)
         assert covered[0][0] == 0 and covered[-1][1] == flat.total

@@ -122,6 +122,8 @@ _SIGS = {
     "vvae_kl_bwd": ([vp, vp, vp, f32, vp, vp, vp, ll, i32, i32, i32, vp], i32),
     "vvae_philox_fill": ([vp, ll, u64, u64, i32, vp], i32),
     "vvae_sumsq_f32": ([vp, ll, vp, vp], i32),
+    "vvae_sumsq_partials": ([ll], i32),
+    "vvae_sumsq_f32_det": ([vp, ll, vp, vp, vp], i32),
     "vvae_adam_step": ([vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, vp, f32, f32, vp], i32),
 }
 

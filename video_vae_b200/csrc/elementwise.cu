@@ -500,6 +500,24 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
   acc = block_sum(acc, scratch);
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
+// deterministic form: per-block partials, then ONE block adds them in a fixed order (same bits on every rank for the
+// same input, so the clip scale -- and with it the replicas -- stay bit-identical)
+__global__ void sumsq_partials_kernel(const float* __restrict__ g, long long n, float* __restrict__ partials) {
+  __shared__ float scratch[33];
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  for (; i < n; i += stride) acc += g[i] * g[i];
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+__global__ void sumsq_final_kernel(const float* __restrict__ partials, int count, float* __restrict__ out) {
+  __shared__ float scratch[33];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) acc += partials[i];
+  acc = block_sum(acc, scratch);
+  if (threadIdx.x == 0) *out += acc;
+}
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2, const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
@@ -817,6 +835,17 @@ int vvae_sumsq_f32(const float* g, long long n, float* out1, vvae_stream_t strea
   VVAE_REQUIRE(g && out1, "sumsq: null pointer");
   sumsq_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(g, n, out1);
   return check_launch("sumsq");
+}
+
+int vvae_sumsq_partials(long long n) { return n > 0 ? ew_blocks(n) : 0; }
+
+int vvae_sumsq_f32_det(const float* g, long long n, float* partials, float* out1, vvae_stream_t stream) {
+  if (n <= 0) return VVAE_OK;
+  VVAE_REQUIRE(g && partials && out1, "sumsq_det: null pointer");
+  const int blocks = ew_blocks(n);
+  sumsq_partials_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, n, partials);
+  sumsq_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, blocks, out1);
+  return check_launch("sumsq_det");
 }
 
 int vvae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,

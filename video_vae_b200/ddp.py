@@ -40,6 +40,16 @@ class FlatParams:
         self._shadow_views = {}
         F_.invalidate_shadows()
 
+    def broadcast(self, src=0, group=None):
+        """Replicate rank ``src``'s parameters on every rank (the reference loads on process 0 and calls
+        ``broadcast_one_to_all``, claude_distributed/distributed_train.py:312-341): one collective on the flat buffer."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(self.flat, src=src, group=group)
+            if self.shadow is not None:
+                self.refresh_shadow()
+            else:
+                F_.params_changed()
+
     def zero_grad(self):
         if self.grad.is_cuda:
             ops.fill_(self.grad, 0.0)
@@ -174,6 +184,10 @@ class FlatAdam:
         self.m = torch.zeros_like(flat.flat)
         self.v = torch.zeros_like(flat.flat)
         self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=flat.flat.device)
+        # fixed-order global-norm reduction: replicas that hold the same reduced gradient get the same clip scale bit for
+        # bit and therefore stay identical (atomics would let them drift by an ulp per step)
+        self._partials = (torch.empty(ops.sumsq_partials(flat.total), dtype=torch.float32, device=flat.flat.device)
+                          if flat.flat.is_cuda else None)
         self.t = 0
 
     def step(self, grad_scale=1.0, lr=None):
@@ -182,7 +196,7 @@ class FlatAdam:
             lr = self.lr(self.t) if callable(self.lr) else self.lr
         self.t += 1
         ops.fill_(self.gnorm_sq, 0.0)
-        ops.sumsq_accum(self.flat.grad, self.gnorm_sq)
+        ops.sumsq_accum(self.flat.grad, self.gnorm_sq, self._partials)
         ops.adam_step_(self.flat.flat, self.flat.grad, self.m, self.v, float(lr), self.b1, self.b2,
                        self.eps, self.t, self.gnorm_sq, self.clip, grad_scale)
         if self.flat.shadow is not None:

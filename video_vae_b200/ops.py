@@ -481,8 +481,16 @@ def philox_fill_(out, seed, offset, kind):
     return out
 
 
-def sumsq_accum(g, out1):
-    check(lib.vvae_sumsq_f32(ptr(g), g.numel(), ptr(out1), stream()), "vvae_sumsq_f32")
+def sumsq_accum(g, out1, partials=None):
+    """out1 += sum g^2.  With ``partials`` (fp32 scratch of sumsq_partials(n) elements) the summation order is fixed."""
+    if partials is not None:
+        check(lib.vvae_sumsq_f32_det(ptr(g), g.numel(), ptr(partials), ptr(out1), stream()), "vvae_sumsq_f32_det")
+    else:
+        check(lib.vvae_sumsq_f32(ptr(g), g.numel(), ptr(out1), stream()), "vvae_sumsq_f32")
+
+
+def sumsq_partials(n):
+    return int(lib.vvae_sumsq_partials(int(n)))
 
 
 def adam_step_(p, g, m, v, lr, b1, b2, eps, step, gnorm_sq=None, clip=1.0, grad_scale=1.0):
