@@ -308,6 +308,54 @@ def test_eval_mode_and_encoder_masked_equals_truncated(V):
     assert torch.allclose(mu_m[:, :5], mu_c, atol=5e-2) and torch.allclose(lv_m[:, :5], lv_c, atol=5e-2)
 
 
+def test_full_size_properties_production_config(V):
+    """BASELINE.json configs[1] at FULL size (16x256x256, batch 8, enc 9 / dec 12, mlp 1536, 8 heads x 64, bf16), where
+    the oracle is too slow: size-independent properties.  (1) masked == truncated on the encoder
+    (train/llm_tests.py:390-474): 6 masked frames do not change the latents of the 10 kept ones; (2) batch isolation
+    (train/human_tests.py:60-92): another clip in the batch changes nothing, bit for bit; (3) one training step is
+    finite, deterministic under the same Rngs, and its CUDA-graph replay reproduces it."""
+    from video_vae_b200.ddp import FlatParams
+    from video_vae_b200.graph import GraphedTrainStep
+    prod = (256, 256, 3, 16, 9, 12, 1536, 8, 512, 64, 8, 4)
+    m = V.VideoVAE(*prod, V.Rngs(2), dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device="cuda").manual_seed(7))
+    flat = FlatParams(m)
+    flat.enable_bf16_shadow()
+    g = _gen(1234)
+    B, T = 8, 16
+    video = torch.rand(B, T, 256, 256, 3, generator=g).to(torch.bfloat16).cuda()
+    mask = torch.ones(B, T, dtype=torch.bool).cuda()
+    graphed = GraphedTrainStep(m, flat, video, mask, V.DEFAULT_HPARAMS)          # capture before any eager backward
+    keep = 10
+    mk = mask.clone()
+    mk[:, keep:] = False
+    with torch.no_grad():
+        mu_m, lv_m, _ = m.encoder(video, mk[:, None, None, :], V.Rngs(1), train=False)
+        mu_c, lv_c, _ = m.encoder(video[:, :keep].contiguous(), mask[:, None, None, :keep], V.Rngs(1), train=False)
+        assert rel_l2(mu_m[:, :keep], mu_c) < 3e-2 and rel_l2(lv_m[:, :keep], lv_c) < 3e-2
+        other = video.clone()
+        other[1:] = torch.rand(B - 1, T, 256, 256, 3, generator=g).to(torch.bfloat16).cuda()
+        mu_o, lv_o, _ = m.encoder(other, mk[:, None, None, :], V.Rngs(1), train=False)
+        assert torch.equal(mu_o[0], mu_m[0]) and torch.equal(lv_o[0], lv_m[0])
+        assert not torch.equal(mu_o[1], mu_m[1])
+    lg = graphed(video, mask, V.Rngs(5)).item()
+    torch.cuda.synchronize()
+    gg = flat.grad.clone()
+    losses = []
+    for _ in range(2):
+        flat.zero_grad()
+        loss, aux = V.loss_fn(m, video, mask[:, None, None, :], mask, V.Rngs(5), V.DEFAULT_HPARAMS, train=True)
+        loss.backward()
+        torch.cuda.synchronize()
+        losses.append(loss.item())
+    assert torch.isfinite(flat.grad).all() and flat.grad.abs().max() > 0
+    assert aux["reconstruction"].shape == (B, T, 256, 256, 3)
+    assert abs(losses[0] - losses[1]) <= 1e-3 * abs(losses[0])                   # same draws; atomics reorder
+    assert abs(lg - losses[0]) <= 1e-3 * abs(losses[0])
+    assert rel_l2(gg, flat.grad) < 5e-3
+
+
 def test_philox_noise_statistics_and_determinism(V):
     m, _ = _small_pair(V, torch.float32, enc=1, dec=1)
     video, mask, _, _ = _inputs()
