@@ -47,7 +47,9 @@ const char* vvae_last_error(void);
 int vvae_version(void);
 /* 1 if a CUDA device with compute capability 10.x is visible, else 0. */
 int vvae_device_ok(void);
-/* Debug/tuning knobs (descriptor encodings of the tcgen05 path); see csrc/gemm_sm100.cu. */
+/* Debug/tuning knobs, all 0 by default (bring-up scripts only; never set by the product path).  Keys 0-6: grid size,
+ * UMMA descriptor fields and the N-tile of the tcgen05 GEMM (csrc/gemm_sm100.cu); 8: force single-CTA GEMM tiles;
+ * 9: keep short sequences (L <= 16) on the packed tcgen05 attention tiles instead of the one-warp kernels. */
 int vvae_debug_set(int key, long long value);
 
 /* ---- elementwise plumbing ------------------------------------------------- */

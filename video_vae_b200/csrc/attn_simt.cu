@@ -346,7 +346,6 @@ static int attn_validate(const vvae_attn_args* a, bool bwd) {
   VVAE_REQUIRE(a->n_outer >= 0 && a->n_inner > 0 && a->L > 0 && a->heads > 0, "attention: bad extents");
   VVAE_REQUIRE(a->hd > 0 && a->hd <= 32 * AT_MAXC, "attention: head_dim %d unsupported (max %d)", a->hd, 32 * AT_MAXC);
   VVAE_REQUIRE(a->q && a->k && a->v && a->o && a->lse, "attention: null tensor");
-  VVAE_REQUIRE((long long)a->n_outer * a->n_inner <= 65535 * 1LL || true, "attention: too many sequences");
   if (bwd) VVAE_REQUIRE(a->d_o && a->dq && a->dk && a->dv && a->delta, "attention bwd: null tensor");
   return VVAE_OK;
 }
