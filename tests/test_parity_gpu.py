@@ -79,6 +79,33 @@ def test_gemm_all_modes_fp32_and_bf16(V):
     assert rel_err(o_tc, ref) < 1e-5 and rel_err(o_si, ref) < 1e-5
 
 
+def test_rank1_linear_kernels_match_generic_gemm(V):
+    """The frame-selection head's Linear 96 -> 1 over every token (train/model.py:56-58) and its two gradients run on
+    dedicated streaming kernels (small_linear.cu rank1_*); same calls on the generic GEMM and an fp32 reference."""
+    from video_vae_b200 import ops
+    from video_vae_b200._ffi import BACKEND_SIMT, EPI_RESIDUAL
+    g = _gen(4)
+    M, K = 4099, 96
+    x = torch.randn(M, K, generator=g).bfloat16().cuda()
+    w = (torch.randn(K, 1, generator=g) * 0.2).bfloat16().cuda()
+    b = torch.randn(1, generator=g).cuda()
+    dy = torch.randn(M, 1, generator=g).bfloat16().cuda()
+    aux = torch.randn(M, K, generator=g).bfloat16().cuda()
+    y = ops.gemm(x, w, bias=b)
+    y_ref = x.float() @ w.float() + b
+    assert y.shape == (M, 1) and rel_err(y, y_ref) < BF16_TOL
+    assert rel_err(y, ops.gemm(x, w, bias=b, backend=BACKEND_SIMT)) < BF16_TOL
+    dx = ops.gemm(dy, w, transB=True, epilogue=EPI_RESIDUAL, aux_in=aux)
+    dx_ref = dy.float() @ w.float().t() + aux.float()
+    assert dx.shape == (M, K) and rel_err(dx, dx_ref) < BF16_TOL
+    dx0 = ops.gemm(dy, w, transB=True)
+    assert rel_err(dx0, dy.float() @ w.float().t()) < BF16_TOL
+    dw = torch.zeros(K, 1, device="cuda")
+    ops.gemm(x, dy, transA=True, out=dw, accumulate=True)
+    ops.gemm(x, dy, transA=True, out=dw, accumulate=True)                # accumulates
+    assert rel_err(dw, 2 * (x.float().t() @ dy.float())) < 1e-4
+
+
 def test_attention_mask_tests_property(V):
     """train/attention_mask_tests.py: b=17,s=15,h=19,d=13, keys 10..14 masked == truncated to 10; vs oracle too."""
     from oracle import nn as onn

@@ -18,10 +18,39 @@ bool small_linear_wgrad_ok(int K, int N);
 int small_linear_fwd(const SmallLinArgs& a, cudaStream_t s);
 int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dk, long long dn,
                        long long M, int K, int N, cudaStream_t s);
+bool rank1_ok(int K);
+int rank1_fwd(const bf16* x, long long x_ld, const bf16* w, long long w_st, const float* bias, bf16* y, long long y_ld,
+              long long M, int K, cudaStream_t s);
+int rank1_dgrad(const bf16* dy, long long dy_ld, const bf16* w, long long w_st, const bf16* aux, long long aux_ld, bf16* dx,
+                long long dx_ld, long long M, int K, cudaStream_t s);
+int rank1_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dw_st, long long M, int K,
+                cudaStream_t s);
 
 // per-row linears with a handful of features (HBM-bound streams, see small_linear.cu)
 static bool small_route(const vvae_gemm_args& a, cudaStream_t s, int* rc) {
   if (a.dtype != VVAE_BF16 || a.backend != VVAE_BACKEND_AUTO) return false;
+  auto al16 = [](const void* p_) { return ((uintptr_t)p_ % 16) == 0; };
+  // rank-1 shapes of the frame-selection head (Linear K -> 1 over every token and its two gradients)
+  if (!a.transA && a.N == 1 && rank1_ok(a.K) && a.M >= 1024 && a.out_dtype == VVAE_BF16 && !a.accumulate &&
+      a.epilogue == VVAE_EPI_NONE && !a.bsum_accum && al16(a.A) && a.lda % 8 == 0) {
+    *rc = rank1_fwd((const bf16*)a.A, a.lda, (const bf16*)a.B, a.transB ? 1 : a.ldb, a.bias, (bf16*)a.C, a.ldc, a.M, a.K, s);
+    return true;
+  }
+  if (!a.transA && a.K == 1 && rank1_ok(a.N) && a.M >= 1024 && a.out_dtype == VVAE_BF16 && !a.accumulate && !a.bias &&
+      (a.epilogue == VVAE_EPI_NONE || a.epilogue == VVAE_EPI_RESIDUAL) && !a.bsum_accum && al16(a.C) && a.ldc % 8 == 0 &&
+      (a.epilogue == VVAE_EPI_NONE || (al16(a.aux_in) && a.ld_aux_in % 8 == 0))) {
+    // C[m,n] = A[m,0] * op(B)[0,n]: op(B)[0,n] = B[n*ldb] (transB, B is [N,1]) or B[n] (B is [1,N])
+    *rc = rank1_dgrad((const bf16*)a.A, a.lda, (const bf16*)a.B, a.transB ? a.ldb : 1,
+                      a.epilogue == VVAE_EPI_RESIDUAL ? (const bf16*)a.aux_in : nullptr, a.ld_aux_in, (bf16*)a.C, a.ldc,
+                      a.M, a.N, s);
+    return true;
+  }
+  if (a.transA && !a.transB && a.N == 1 && rank1_ok(a.M) && a.K >= 1024 && a.accumulate && a.out_dtype == VVAE_F32 &&
+      a.epilogue == VVAE_EPI_NONE && !a.bias && !a.bsum_accum && al16(a.A) && a.lda % 8 == 0) {
+    // C[k,0] += sum_rows A[row,k] * B[row,0]   (A is [rows, M'] with M' = a.M the feature count)
+    *rc = rank1_wgrad((const bf16*)a.A, a.lda, (const bf16*)a.B, a.ldb, (float*)a.C, a.ldc, a.K, a.M, s);
+    return true;
+  }
   if (!a.transA && a.out_dtype == VVAE_BF16 && !a.accumulate && small_linear_ok(a.K, a.N) && a.M >= 4096 &&
       (a.epilogue == VVAE_EPI_NONE || a.epilogue == VVAE_EPI_RESIDUAL)) {
     SmallLinArgs q{(const bf16*)a.A, a.lda, (const bf16*)a.B, a.transB ? 1 : a.ldb, a.transB ? a.ldb : 1, a.bias,

@@ -9,6 +9,8 @@
 
 namespace vvae {
 
+__device__ __forceinline__ long long cdiv_dev(long long a, long long b) { return (a + b - 1) / b; }
+
 struct SmallLinArgs {
   const bf16* x; long long x_ld;
   const bf16* w; long long wk, wn;        // W(k, n) = w[k*wk + n*wn]
@@ -158,6 +160,122 @@ int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long 
   else SL_WG(16, 4);
 #undef SL_WG
   return check_launch("small_linear_wgrad");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Rank-1 shapes of the encoder's frame-selection head (train/model.py:56-58: Linear 96 -> 1 over every token):
+//   fwd    y[m]     = x[m,:] . w + b                      (M x K) . (K x 1)
+//   dgrad  dx[m,k]  = dy[m] * w[k] (+ aux[m,k])           (M x 1) . (1 x K)
+//   wgrad  dw[k]   += sum_m x[m,k] * dy[m]                (K x M) . (M x 1)
+// K = 96 (a multiple of 8, <= 256).  8 lanes per row, 16-byte loads; these are 6 MB streams, not GEMMs.
+__global__ void __launch_bounds__(256)
+rank1_fwd_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __restrict__ w, long long w_st,
+                 const float* __restrict__ bias, bf16* __restrict__ y, long long y_ld, long long M, int K) {
+  const int sub = threadIdx.x & 7, nch = K >> 3;
+  const long long row0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long rstride = ((long long)gridDim.x * blockDim.x) >> 3;
+  const long long iters = cdiv_dev(M, rstride);
+  for (long long it = 0; it < iters; ++it) {           // whole warps iterate together (shuffles below)
+    const long long m = row0 + it * rstride;
+    float acc = 0.f;
+    if (m < M) {
+      for (int c = sub; c < nch; c += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + m * x_ld + c * 8);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc = fmaf(__uint_as_float(u[t] << 16), __bfloat162float(w[(long long)(c * 8 + 2 * t) * w_st]), acc);
+          acc = fmaf(__uint_as_float(u[t] & 0xffff0000u), __bfloat162float(w[(long long)(c * 8 + 2 * t + 1) * w_st]), acc);
+        }
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (m < M && sub == 0) y[m * y_ld] = __float2bfloat16_rn(acc + (bias ? bias[0] : 0.f));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+rank1_dgrad_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ w, long long w_st,
+                   const bf16* __restrict__ aux, long long aux_ld, bf16* __restrict__ dx, long long dx_ld, long long M,
+                   int K) {
+  const int nch = K >> 3;
+  const long long total = M * nch;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long m = i / nch;
+    const int c = (int)(i - m * nch);
+    const float d = __bfloat162float(dy[m * dy_ld]);
+    float o[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) o[t] = d * __bfloat162float(w[(long long)(c * 8 + t) * w_st]);
+    if (aux) {
+      const uint4 v = *reinterpret_cast<const uint4*>(aux + m * aux_ld + c * 8);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        o[2 * t] += __uint_as_float(u[t] << 16);
+        o[2 * t + 1] += __uint_as_float(u[t] & 0xffff0000u);
+      }
+    }
+    uint4 r;
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+    r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+    r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+    *reinterpret_cast<uint4*>(dx + m * dx_ld + c * 8) = r;
+  }
+}
+
+// blockDim = 256 = 8 row slots x 32 column chunks (K <= 256); per-thread partials over a grid-stride loop of rows
+__global__ void __launch_bounds__(256)
+rank1_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, const bf16* __restrict__ dy, long long dy_ld,
+                   float* __restrict__ dw, long long dw_st, long long M, int K) {
+  __shared__ float red[256];
+  const int nch = K >> 3, c = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  if (c < nch) {
+    for (long long m = (long long)blockIdx.x * 8 + slot; m < M; m += (long long)gridDim.x * 8) {
+      const float d = __bfloat162float(dy[m * dy_ld]);
+      const uint4 v = *reinterpret_cast<const uint4*>(x + m * x_ld + c * 8);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        acc[2 * t] = fmaf(__uint_as_float(u[t] << 16), d, acc[2 * t]);
+        acc[2 * t + 1] = fmaf(__uint_as_float(u[t] & 0xffff0000u), d, acc[2 * t + 1]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) atomicAdd(&red[c * 8 + t], acc[t]);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(dw + (long long)k * dw_st, red[k]);
+}
+
+bool rank1_ok(int K) { return K >= 8 && K <= 256 && K % 8 == 0; }
+
+int rank1_fwd(const bf16* x, long long x_ld, const bf16* w, long long w_st, const float* bias, bf16* y, long long y_ld,
+              long long M, int K, cudaStream_t s) {
+  const int blocks = (int)std::min<long long>(cdiv(M * 8, 256), 148LL * 8);
+  rank1_fwd_kernel<<<blocks, 256, 0, s>>>(x, x_ld, w, w_st, bias, y, y_ld, M, K);
+  return check_launch("rank1_fwd");
+}
+int rank1_dgrad(const bf16* dy, long long dy_ld, const bf16* w, long long w_st, const bf16* aux, long long aux_ld, bf16* dx,
+                long long dx_ld, long long M, int K, cudaStream_t s) {
+  const int blocks = (int)std::min<long long>(cdiv(M * (K / 8), 256), 148LL * 8);
+  rank1_dgrad_kernel<<<blocks, 256, 0, s>>>(dy, dy_ld, w, w_st, aux, aux_ld, dx, dx_ld, M, K);
+  return check_launch("rank1_dgrad");
+}
+int rank1_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dw_st, long long M, int K,
+                cudaStream_t s) {
+  const int blocks = (int)std::min<long long>(cdiv(M, 8 * 16), 148LL * 4);
+  rank1_wgrad_kernel<<<blocks, 256, 0, s>>>(x, x_ld, dy, dy_ld, dw, dw_st, M, K);
+  return check_launch("rank1_wgrad");
 }
 
 }  // namespace vvae
