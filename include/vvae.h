@@ -49,7 +49,8 @@ int vvae_version(void);
 int vvae_device_ok(void);
 /* Debug/tuning knobs, all 0 by default (bring-up scripts only; never set by the product path).  Keys 0-6: grid size,
  * UMMA descriptor fields and the N-tile of the tcgen05 GEMM (csrc/gemm_sm100.cu); 8: force single-CTA GEMM tiles;
- * 9: keep short sequences (L <= 16) on the packed tcgen05 attention tiles instead of the one-warp kernels. */
+ * 9: keep short sequences (L <= 16) on the packed tcgen05 attention tiles instead of the one-warp kernels;
+ * 12: 192-column GEMM tiles for N = 768 dgrads (measured slower than 256: kept for the record). */
 int vvae_debug_set(int key, long long value);
 
 /* ---- elementwise plumbing ------------------------------------------------- */

@@ -704,6 +704,14 @@ int sm100_gemm(const vvae_gemm_args& a, cudaStream_t s) {
   // least two 128-row blocks.  vvae_debug_set(8, 1) forces single-CTA tiles.
   const bool pair = a.M >= 256 && !g_dbg[8];
   if (bn == 256 && !pair) bn = 128;   // single-CTA 128x256 tiles leave too little smem for a deep pipeline + staging
+  // N = 768 dgrads (K-major B): 192-column tiles give 4 x 128 = 512 tiles = 6.9 waves of 0.75 instead of 384 tiles =
+  // 5.2 -> 6 waves of 1.  Measured: bit-identical, but 72.8 us against 65.7 us (M = 32768, K = 1536): the smaller tile's
+  // extra operand traffic costs more than the partial wave.  Kept behind vvae_debug_set(12, 1).
+  if (g_dbg[12] && bn == 256 && a.N % 192 == 0 && !a.transA && a.transB && a.epilogue == VVAE_EPI_NONE && !a.bsum_accum) {
+    const long long mt = cdiv(a.M, 256), pairs = num_sms() / 2;
+    const double cost256 = (double)cdiv(mt * cdiv(a.N, 256), pairs), cost192 = 0.75 * (double)cdiv(mt * (a.N / 192), pairs);
+    if (cost192 < 0.9 * cost256) return launch_sm100<192, 2, false, false, 0>(a, s);
+  }
   if (bn == 256) return dispatch_major<256, 2>(a, s);
   if (bn == 128) return pair ? dispatch_major<128, 2>(a, s) : dispatch_major<128, 1>(a, s);
   return dispatch_major<64, 1>(a, s);
