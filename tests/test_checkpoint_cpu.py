@@ -69,3 +69,25 @@ def test_adam_moments_import():
     s = flat.offsets[i]
     want = torch.from_numpy(ck.flatten_tree(mu)["decoder.unet.final_conv.bias"])
     assert torch.equal(adam.m[s:s + want.numel()], want)
+
+
+def test_rl_host_helpers_need_no_host_reads():
+    """rl_model.repeat2 == einops 'b ... -> (b 2) ...' (== repeat_interleave), and the capture-safe form of the
+    trajectory-probability product used by rl_losses (1 + sum_t(p_t - 1) with p_t = raw/stop_grad(raw)) has the value
+    and the gradient of prod_t(p_t) (train/rl_nonadversarial.py:164-171)."""
+    from video_vae_b200.rl_model import repeat2
+    a = torch.arange(24.0).reshape(3, 4, 2)
+    assert torch.equal(repeat2(a), a.repeat_interleave(2, dim=0))
+    raw = (torch.rand(2, 2, 5, generator=torch.Generator().manual_seed(0)) * 0.9 + 0.05).requires_grad_()
+    mask = torch.tensor([[True, True, True, False, False]]).expand(2, 2, 5)
+    one = torch.ones_like(raw)
+    w = torch.tensor([[0.7, -0.7], [-1.0, 1.0]])[:, :, None]
+    ratio = torch.where(mask, raw / raw.detach(), one)
+    (ratio.prod(dim=2, keepdim=True) * w).sum().backward()
+    g_prod = raw.grad.clone()
+    raw.grad = None
+    ratio = torch.where(mask, raw / raw.detach(), one)
+    alt = 1.0 + (ratio - 1.0).sum(dim=2, keepdim=True)
+    assert torch.equal(alt.detach(), torch.ones_like(alt))
+    (alt * w).sum().backward()
+    assert torch.allclose(raw.grad, g_prod, rtol=1e-6, atol=0) and float(raw.grad[..., 3:].abs().max()) == 0.0

@@ -17,7 +17,7 @@ import torch
 from torch.autograd import Function
 
 from . import ops
-from ._ffi import EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, require_device
+from ._ffi import EPI_DSILU, EPI_RESIDUAL, EPI_SILU, require_device
 
 # ------------------------------------------------------------------ parameter shadows / gradient buffers
 _shadow_cache = {}  # id(param) -> (weakref(param), version, data_ptr, shadow tensor)

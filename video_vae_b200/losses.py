@@ -4,8 +4,6 @@
 optional MAE term of train/rl_nonadversarial.py:114-117 enabled by ``hparams["gamma4"]``; ``train_step`` mirrors
 :126-136 (mask plumbing + value_and_grad), leaving the optimizer update to the caller.
 """
-import torch
-
 from . import functional as F_
 
 DEFAULT_HPARAMS = {  # training_loop_adversarial.py:47-48,52,54

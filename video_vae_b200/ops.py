@@ -7,8 +7,7 @@ import ctypes as C
 
 import torch
 
-from . import _ffi
-from ._ffi import (BACKEND_AUTO, BACKEND_SIMT, BF16, EPI_DSILU, EPI_NONE, EPI_RESIDUAL, EPI_SILU, F32, AttnArgs, ConvArgs, GemmArgs,
+from ._ffi import (BACKEND_AUTO, BACKEND_SIMT, BF16, EPI_NONE, EPI_RESIDUAL, AttnArgs, ConvArgs, GemmArgs,
                    check, dt, lib, ptr, stream)
 
 LN_EPS = 1e-6
