@@ -77,12 +77,74 @@ def run_attention_kat():
     return {"attn_out_slice": o[::4, :, ::6, :].numpy(), "attn_out_sum": np.float64(o.double().sum())}
 
 
+def build_rl_case():
+    """Seeded oracle RL model, VGG feature extractor and inputs (rows next to the path)."""
+    from oracle import Rngs
+    from oracle.perceptual import VGG16Features
+    from oracle.rl_model import VideoVAE
+    model = VideoVAE(*CFG, Rngs(2))
+    g = torch.Generator().manual_seed(23)
+    with torch.no_grad():
+        model.decoder.unet.final_conv.kernel.copy_(torch.randn(model.decoder.unet.final_conv.kernel.shape, generator=g) * 0.05)
+    vgg = VGG16Features(Rngs(4))
+    hw = (CFG[0] // CFG[3]) * (CFG[1] // CFG[3])
+    b, t = 2, 4
+    video = torch.rand(b, t, CFG[0], CFG[1], 3, generator=g)
+    mask = torch.tensor([[True] * t, [True] * (t - 1) + [False]])
+    noise = torch.randn(b, t, hw, CFG[3] * CFG[3] * 3 // CFG[10], generator=g)
+    bernoulli_u = torch.rand(2 * b, t, 1, 1, generator=g)
+    bernoulli_u[0::2, 0] = 0.0          # twins differ on frame 0, so the pairwise disadvantages are well conditioned
+    bernoulli_u[1::2, 0] = 1.0
+    return model, vgg, video, mask, noise, bernoulli_u
+
+
+RL_HP = {"gamma1": 0.2, "gamma2": 0.001, "gamma3": 0.1, "gamma4": 0.05, "max_compression_rate": 2,
+         "magnify_negatives_rate": 100, "rl_loss_weight": 0.5}
+
+
+def run_rl_oracle():
+    from oracle import Rngs
+    from oracle.optim import ClipAdam
+    from oracle.perceptual import get_adversarial_perceptual_loss_fn
+    from oracle.rl_losses import loss_fn
+    model, vgg, video, mask, noise, bu = build_rl_case()
+    pfn = get_adversarial_perceptual_loss_fn(vgg)
+    loss, aux = loss_fn(model, video, mask[:, None, None, :], mask, Rngs(0), RL_HP, pfn, None, noise=noise, bernoulli_u=bu)
+    loss.backward()
+    out = {"rl_loss_total": loss.detach().numpy(), "rl_per_sample_loss": aux["per_sample_loss"].detach().numpy(),
+           "rl_selection_mask": aux["selection_mask"].detach().reshape(4, -1).numpy(),
+           "rl_selection": aux["selection"].detach().reshape(4, -1).numpy(),
+           "rl_recon_slice": aux["reconstruction"].detach()[:, :, ::9, ::11, :].numpy()}
+    for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density", "mean_trajectory_prob",
+              "per_sample_MAE"):
+        out["rl_" + k] = aux[k].detach().numpy()
+    names, norms = [], []
+    for n, p in model.named_parameters():
+        names.append(n)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    out["rl_grad_names"] = np.array(names)
+    out["rl_grad_norms"] = np.array(norms, dtype=np.float64)
+    out["rl_grad_sel2"] = model.encoder.selection_layer2.kernel.grad.numpy()
+    # one clip+Adam step on those gradients (optax.chain(clip_by_global_norm(1.0), adam(1e-3)))
+    params = [p for p in model.parameters()]
+    opt = ClipAdam(params, lr=1e-3, clip=1.0)
+    gn = opt.step([p.grad if p.grad is not None else torch.zeros_like(p) for p in params])
+    out["rl_grad_global_norm"] = np.float64(gn)
+    out["rl_fill_token_after_step"] = model.fill_token.detach().reshape(-1)[:16].numpy()
+    out["rl_qkv_after_step_slice"] = model.encoder.layers[0].TemporalAttention.qkv_projection.kernel.detach()[::16, ::32].numpy()
+    return out
+
+
 def main():
     out = run_oracle()
     out.update(run_attention_kat())
     path = os.path.join(HERE, "videovae_cfg64_fp32.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes; loss =", float(out["loss"]))
+    out = run_rl_oracle()
+    path = os.path.join(HERE, "rl_step_cfg64_fp32.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; loss =", float(out["rl_loss_total"]))
 
 
 if __name__ == "__main__":

@@ -381,3 +381,27 @@ def test_vgg_perceptual_oracle_shapes_and_loss():
     want = torch.relu(torch.einsum("hwio,i->o", k[1:, 1:], xn) + vgg.conv1_1_bias)
     got = vgg(torch.ones(1, 8, 8, 3))["relu1_1"][0, 0, 0]
     assert torch.allclose(got, want, atol=1e-5)
+
+
+def test_oracle_reproduces_rl_step_golden_fixture():
+    """tests/golden/rl_step_cfg64_fp32.npz: the rows next to the path in one fixture -- rl_model forward, the RL loss
+    with the VGG perceptual term, every gradient norm and one clip+Adam step, as written by make_golden.py."""
+    import importlib.util
+    import os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "rl_step_cfg64_fp32.npz"))
+    now = mg.run_rl_oracle()
+    assert sorted(now) == sorted(gold.files)
+    for key in gold.files:
+        if key == "rl_grad_names":
+            assert list(now[key]) == list(gold[key])
+        elif key == "rl_selection_mask":
+            assert np.array_equal(now[key], gold[key])
+        else:
+            ref = np.asarray(gold[key], dtype=np.float64)
+            got = np.asarray(now[key], dtype=np.float64)
+            assert np.allclose(got, ref, rtol=5e-4, atol=5e-5 * max(1e-6, np.abs(ref).max())), key

@@ -818,6 +818,67 @@ def test_rl_loss_matches_oracle_fp32(V):
     assert abs(float(lm3) - float(lo3)) <= FP32_TOL * abs(float(lo3)) + 1e-7 and float(lo3) > float(lo)
 
 
+def test_rl_step_matches_golden_fixture(V):
+    """tests/golden/rl_step_cfg64_fp32.npz (written from the oracle by tests/golden/make_golden.py): rl_model forward, the
+    RL loss with the VGG perceptual term, every parameter-gradient norm and one fused clip+Adam step of the CUDA path
+    against the committed numbers, fp32."""
+    import importlib.util
+    import os
+    import numpy as np
+    from video_vae_b200.ddp import FlatAdam, FlatParams
+    from video_vae_b200.perceptual import VGG16Features, get_adversarial_perceptual_loss_fn
+    from video_vae_b200.rl_losses import loss_fn
+    from video_vae_b200.rl_model import VideoVAE as RL
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "rl_step_cfg64_fp32.npz"))
+    o, ovgg, video, mask, noise, bu = mg.build_rl_case()
+    m = RL(*mg.CFG, V.Rngs(2), dtype=torch.float32)
+    _copy_params(m, o)
+    vgg = VGG16Features(V.Rngs(4), dtype=torch.float32)
+    _copy_params(vgg, ovgg)
+    flat = FlatParams(m)
+    opt = FlatAdam(flat, lr=1e-3, clip=1.0)
+    flat.zero_grad()
+    loss, aux = loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), mg.RL_HP,
+                        get_adversarial_perceptual_loss_fn(vgg), None, noise=noise.cuda(), bernoulli_u=bu.cuda())
+    loss.backward()
+
+    def close(got, key, tol=FP32_TOL):
+        ref = torch.from_numpy(np.asarray(gold[key], dtype=np.float64))
+        got = got.detach().double().cpu().reshape(ref.shape)
+        assert float((got - ref).abs().max()) <= tol * max(float(ref.abs().max()), 1e-12), key
+
+    assert np.array_equal(aux["selection_mask"].detach().cpu().reshape(4, -1).numpy(), gold["rl_selection_mask"])
+    close(loss, "rl_loss_total")
+    close(aux["per_sample_loss"], "rl_per_sample_loss")
+    close(aux["selection"], "rl_selection")
+    close(aux["reconstruction"][:, :, ::9, ::11, :], "rl_recon_slice")
+    for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density", "mean_trajectory_prob",
+              "per_sample_MAE"):
+        close(aux[k], "rl_" + k)
+    names = list(gold["rl_grad_names"])
+    norms = dict(zip(names, gold["rl_grad_norms"]))
+    checked = 0
+    for n_, p in m.named_parameters():
+        ref = float(norms[n_])
+        if ref == 0.0:
+            continue
+        # (a few gradients are sums that cancel to ~1e-8 of the global norm: absolute slack of 1e-6 x that norm)
+        assert abs(float(p.grad.double().norm()) - ref) <= 2e-3 * ref + 1e-6 * float(gold["rl_grad_global_norm"]), n_
+        checked += 1
+    assert checked >= 100
+    close(m.encoder.selection_layer2.kernel.grad, "rl_grad_sel2", 1e-3)
+    gn = float(flat.grad.double().norm())
+    assert abs(gn - float(gold["rl_grad_global_norm"])) <= 1e-3 * gn
+    opt.step()
+    # first Adam step = lr * g / (|g| + eps) after clipping: 5e-4 of the parameter scale is ~2 % of the update
+    close(m.fill_token.reshape(-1)[:16], "rl_fill_token_after_step", 5e-4)
+    close(m.encoder.layers[0].TemporalAttention.qkv_projection.kernel[::16, ::32], "rl_qkv_after_step_slice", 5e-4)
+
+
 def test_rl_loss_bf16_train_step_and_loss_decrease(V):
     """claude_distributed/test_training_loop.py Tests 2-4 through the product's train_step in bf16 on the tcgen05 path
     (2 heads x 64): finite loss / gradients, loss decreasing over 10 clip+Adam steps on a fixed batch."""
