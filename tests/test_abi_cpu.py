@@ -70,3 +70,27 @@ def test_no_cpu_fallback():
     mask = torch.ones(1, 2, dtype=torch.bool)
     with pytest.raises(_ffi.VvaeError):
         m(x, mask[:, None, None, :], V.Rngs(0), train=False)
+
+
+def test_integration_md_names_exist():
+    """Every replacement named in INTEGRATION.md's mapping table (`video_vae_b200.mod.{a,b}` / `video_vae_b200.mod.name`)
+    imports: the drop-in guide cannot drift from the package."""
+    import importlib
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    found = 0
+    for mod, names in re.findall(r"`video_vae_b200\.([a-z_]+)\.\{([A-Za-z0-9_,]+)\}`", text):
+        m = importlib.import_module("video_vae_b200." + mod)
+        for n in names.split(","):
+            assert hasattr(m, n), f"video_vae_b200.{mod}.{n}"
+            found += 1
+    for mod, name in re.findall(r"`video_vae_b200\.([a-z_]+)\.([A-Za-z_][A-Za-z0-9_]*)`", text):
+        m = importlib.import_module("video_vae_b200." + mod)
+        assert hasattr(m, name), f"video_vae_b200.{mod}.{name}"
+        found += 1
+    assert found >= 30
+    import video_vae_b200 as V
+    for n in ("VideoVAE", "Rngs", "loss_fn", "DEFAULT_HPARAMS"):       # the top-level names the guide's snippet imports
+        assert hasattr(V, n)
