@@ -86,6 +86,20 @@ def _worker(rank, world, port, out):
         xs = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(xs, x)
         assert not torch.equal(xs[0], xs[1])
+        # batch sharding (test_training_loop.py:221-233, test_distributed.py): row block d on rank d, shards are
+        # disjoint, and together they are the global batch (global batch = local x processes)
+        from video_vae_b200.ddp import shard_batch
+        glob = torch.arange(6 * 3, dtype=torch.float32).reshape(6, 3)
+        mine = shard_batch(glob)
+        assert mine.shape == (6 // world, 3) and torch.equal(mine, glob[rank * 3:(rank + 1) * 3])
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine.contiguous())
+        assert torch.equal(torch.cat(parts), glob)
+        try:
+            shard_batch(glob[:5])
+            raise AssertionError("an indivisible global batch must be rejected")
+        except ValueError:
+            pass
         red.close()
         out.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001

@@ -16,6 +16,21 @@ from . import functional as F_
 from . import ops
 
 
+def shard_batch(x, rank=None, world=None):
+    """Rows of a GLOBAL batch this rank owns: axis 0 split evenly over the ranks in rank order (the reference shards the
+    batch over its 1-D ('data',) mesh, row block d on device d: claude_distributed/distributed_train.py:107-109,189-196;
+    test_training_loop.py:221-233).  The global batch must divide by the world size, as the reference requires."""
+    if world is None:
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    n = x.shape[0]
+    if n % world:
+        raise ValueError(f"global batch {n} is not divisible by the world size {world}")
+    per = n // world
+    return x[rank * per:(rank + 1) * per]
+
+
 class FlatParams:
     """Re-homes every parameter (and its gradient) of ``model`` into one contiguous fp32 buffer each."""
 
