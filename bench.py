@@ -319,16 +319,19 @@ def run_ours(args):
     except OSError:
         pass
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    traffic = None
+    traffic, traffic_detail = None, None
     try:   # DRAM bytes of one representative launch of the dominant kernel, from the committed `ncu --set full` capture
         nc = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_qkv_fwd_ncu.json")))
-        traffic = {"dram_bytes_per_launch": (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6,
-                   "launch": "QKV projection forward, M=32768 N=1536 K=768 (algorithmic 153.4 MB: A 50.3 + B 2.4 + C 100.7; "
-                             "half of C is still L2-resident when the launch ends)",
-                   "tensor_pipe_active_pct": float(nc["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
-                   "source": "profiles/r01_gemm_qkv_fwd_ncu.json"}
+        # bytes (dram__bytes_read.sum + dram__bytes_write.sum) of that one launch; the capture reports Mbyte
+        traffic = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
+        traffic_detail = {
+            "launch": "QKV projection forward, M=32768 N=1536 K=768 (algorithmic 153.4 MB: A 50.3 + B 2.4 + C 100.7; "
+                      "half of C is still L2-resident when the launch ends)",
+            "algorithmic_bytes_per_launch": 153.4e6,
+            "tensor_pipe_active_pct": float(nc["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
+            "source": "profiles/r01_gemm_qkv_fwd_ncu.json"}
     except (OSError, KeyError, ValueError):
-        pass
+        traffic, traffic_detail = None, None
     roofline = None
     table = []
     for name, (t, fl, nb, n) in sorted(classes.items(), key=lambda kv: -kv[1][0]):
@@ -343,7 +346,8 @@ def run_ours(args):
         roofline = {"kernel": "gemm_sm100_kernel (tcgen05 bf16 GEMM: every Linear fwd/dgrad/wgrad)", "bound": "tensor",
                     "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                    if peaks else "fallback", "traffic": traffic, "launches_per_step": n / prof_steps,
+                    if peaks else "fallback", "traffic": traffic, "traffic_detail": traffic_detail,
+                    "launches_per_step": n / prof_steps,
                     "share_of_step": t * 1e3 / prof_steps / ms,
                     "timing": "CUDA events around every launch of this kernel in one eager pass after the timed region"
                     if graphed is not None else "CUDA events around every launch inside the timed region"}
