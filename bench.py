@@ -361,7 +361,7 @@ def run_ours(args):
                                "mlp 1536, 8 heads x 64, latent 96 (BASELINE.json configs[1])",
                    "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "inputs+activations per step (tens of GB) >> 126 MB L2; no flush needed",
-                   "model_tflop_per_clip": FLOP_PER_CLIP.get(S)},
+                   "algorithmic_flop_per_clip": FLOP_PER_CLIP.get(S)},
         "model_tflops": (value * FLOP_PER_CLIP[S] / 1e12 / world) if S in FLOP_PER_CLIP else None,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": host_video.numel() * host_video.element_size() + host_mask.numel(),
