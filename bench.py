@@ -3,10 +3,16 @@
 16x256x256, bf16, batch 8 per GPU (BASELINE.json configs[1]), production hyper-parameters
 (train/rl_nonadversarial.py:234-236).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.  `--impl reference` times the
-CPU oracle (the reference is JAX/Flax and cannot be installed offline) on the host cores.
+CPU oracle (the reference is JAX/Flax and cannot be installed offline) on the host cores, on the SAME configuration.
+
+--config selects the BASELINE.json row (same JSON schema; `config.workload` names the row):
+  cfg2 (default)  configs[1]: training step, 16x256x256, batch 8 per GPU           -> the headline metric
+  cfg3            configs[2]: encode-only latent extraction, 32x256x256, batch 32 (chunks of 8), eval mode, no grad
+  cfg4            configs[3]: cfg2 with prefix masks keeping 4/8/12/16 of 16 frames (two clips each; --keep K = all K)
+  cfg5            configs[4]: long clip 64x512x512, batch 1 per GPU (run with --gpus 8 for the BASELINE row)
 """
 import argparse
 import json
@@ -24,6 +30,16 @@ PROD = dict(patch_size=16, encoder_depth=9, decoder_depth=12, mlp_dim=1536, num_
             max_temporal_len=64, spatial_compression_rate=8, unembedding_upsample_rate=4)
 METRIC = "train clips/sec at 16x256x256 fwd+bwd"
 FLOP_PER_CLIP = {256: 5.10e12, 128: 1.25e12}   # SURVEY.md section 8(d), fwd+bwd = 3x fwd, remat not counted
+# BASELINE.json rows other than the headline: (frames, size, batch/GPU, metric, algorithmic FLOP per clip, workload text)
+CONFIGS = {
+    "cfg2": dict(frames=16, size=256, batch=8, metric=METRIC, flop=5.10e12, row="configs[1]"),
+    "cfg3": dict(frames=32, size=256, batch=32, metric="encode-only clips/sec at 32x256x256 (latent extraction)",
+                 flop=1.215e12, row="configs[2]"),
+    "cfg4": dict(frames=16, size=256, batch=8, metric="train clips/sec at 16x256x256 fwd+bwd, 25-100% frames kept",
+                 flop=5.10e12, row="configs[3]"),
+    "cfg5": dict(frames=64, size=512, batch=1, metric="train clips/sec at 64x512x512 fwd+bwd", flop=88.5e12,
+                 row="configs[4]"),
+}
 
 
 def parse():
@@ -32,9 +48,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="clips per GPU")
-    ap.add_argument("--frames", type=int, default=16)
-    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="clips per GPU (default: the BASELINE row's)")
+    ap.add_argument("--frames", type=int, default=None)
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--keep", type=int, default=None, help="cfg4: frames kept in every clip (default 4/8/12/16 mix)")
+    ap.add_argument("--chunk", type=int, default=8, help="cfg3: clips per encoder call (data_prep/save_latents.py:183-206)")
     ap.add_argument("--enc-depth", type=int, default=PROD["encoder_depth"])
     ap.add_argument("--dec-depth", type=int, default=PROD["decoder_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -44,42 +63,92 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
                     "of replaying the captured CUDA graph; N > 1 then overlaps the bucketed all-reduce with backward")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    a.custom_shape = any(v is not None for v in (a.batch, a.frames, a.size))
+    a.batch = c["batch"] if a.batch is None else a.batch
+    a.frames = c["frames"] if a.frames is None else a.frames
+    a.size = c["size"] if a.size is None else a.size
+    return a
+
+
+def keep_per_clip(args):
+    """cfg4: frames kept per clip of the batch (prefix masks, train/dataloader.py:232-234)."""
+    if args.config != "cfg4":
+        return [args.frames] * args.batch
+    if args.keep is not None:
+        return [args.keep] * args.batch
+    q = args.frames // 4
+    return [(q * (1 + i % 4)) for i in range(args.batch)]
+
+
+def workload_text(args, impl_note=""):
+    c = CONFIGS[args.config]
+    shape = f"{args.frames}x{args.size}x{args.size} RGB clips, batch {args.batch}/GPU"
+    hyper = f"enc {args.enc_depth}/dec {args.dec_depth}, mlp 1536, 8 heads x 64, latent 96"
+    if args.config == "cfg3":
+        w = f"Encoder forward (eval, no grad, chunks of {args.chunk}) on {shape}, {hyper}"
+    else:
+        w = f"VideoVAE train step (fwd+loss+bwd{'' if args.no_optimizer else '+clip+Adam'}) on {shape}, {hyper}"
+        if args.config == "cfg4":
+            w += f", prefix masks keeping {sorted(set(keep_per_clip(args)))} of {args.frames} frames"
+    return w + f" (BASELINE.json {c['row']}{', non-default shape' if args.custom_shape else ''}){impl_note}"
 
 
 # ----------------------------------------------------------------------------------------------- CPU oracle arm
-def oracle_step_time(size, frames, steps, warmup, enc, dec, threads):
+def oracle_step_time(args, steps, warmup, threads, budget_s=None):
+    """One clip of the arm's configuration per step on the host cores through the CPU oracle (fp32): fwd + loss + bwd +
+    clip + Adam for the training rows, the eval-mode Encoder forward for cfg3.  With `budget_s` the loop stops early
+    (never before one timed step) so that a slow host still ends in time; returns (seconds per step, steps timed)."""
     import torch
     from oracle import Rngs as ORngs
     from oracle.losses import DEFAULT_HPARAMS, loss_fn
     from oracle.model import VideoVAE as OVAE
+    from oracle.optim import ClipAdam
     torch.set_num_threads(threads)
-    m = OVAE(size, size, 3, PROD["patch_size"], enc, dec, PROD["mlp_dim"], PROD["num_heads"], PROD["qkv_features"],
-             PROD["max_temporal_len"], PROD["spatial_compression_rate"], PROD["unembedding_upsample_rate"], ORngs(2))
+    size, frames = args.size, args.frames
+    m = OVAE(size, size, 3, PROD["patch_size"], args.enc_depth, args.dec_depth, PROD["mlp_dim"], PROD["num_heads"],
+             PROD["qkv_features"], PROD["max_temporal_len"], PROD["spatial_compression_rate"],
+             PROD["unembedding_upsample_rate"], ORngs(2))
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator().manual_seed(7))
+    params = list(m.parameters())
+    opt = None if (args.no_optimizer or args.config == "cfg3") else ClipAdam(params, lr=5e-5, clip=1.0)
     g = torch.Generator().manual_seed(1234)
     x = torch.rand(1, frames, size, size, 3, generator=g)
-    mask = torch.ones(1, frames, dtype=torch.bool)
-    times = []
-    for i in range(warmup + steps):
+    mask = torch.arange(frames)[None, :] < keep_per_clip(args)[0]
+    hp = dict(DEFAULT_HPARAMS, gamma4=0.1)
+    def one(i):
         t0 = time.perf_counter()
-        for p in m.parameters():
-            p.grad = None
-        loss, _ = loss_fn(m, x, mask[:, None, None, :], mask, ORngs(i), DEFAULT_HPARAMS)
-        loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return sum(times) / len(times)
+        if args.config == "cfg3":
+            with torch.no_grad():
+                m.encoder(x, mask[:, None, None, :], ORngs(0), train=False)
+        else:
+            for p in params:
+                p.grad = None
+            loss, _ = loss_fn(m, x, mask[:, None, None, :], mask, ORngs(i), hp)
+            loss.backward()
+            if opt is not None:
+                opt.step([p.grad if p.grad is not None else torch.zeros_like(p) for p in params])
+        return time.perf_counter() - t0
+
+    t_start, times = time.perf_counter(), []
+    for i in range(warmup):
+        dt = one(i)
+        if budget_s is not None and (time.perf_counter() - t_start) + (steps + 1) * dt > budget_s:
+            break                               # host slower than planned: stop warming up, start timing
+    for i in range(steps):
+        dt = one(warmup + i)
+        times.append(dt)
+        if budget_s is not None and (time.perf_counter() - t_start) + dt > budget_s:
+            break
+    return sum(times) / len(times), len(times)
 
 
-def cpu_sample(args, total_steps, budget_s=170.0):
-    """Pick the bounded sample: one full 16xSxS clip if the budget allows, else a 128x128 crop (FLOP-scaled)."""
-    per_step = budget_s / max(1, total_steps)
-    if args.size <= 128 or per_step >= 25.0:
-        return args.size, 1.0, f"1 clip of {args.frames}x{args.size}x{args.size} per step, fp32, fwd+loss+bwd"
-    scale = FLOP_PER_CLIP[128] / FLOP_PER_CLIP[256]
-    return 128, scale, (f"1 crop of {args.frames}x128x128 per step, fp32, fwd+loss+bwd; clips/s scaled by the "
-                        f"algorithmic FLOP ratio {scale:.3f} (1.25/5.10 TFLOP per clip) to 16x256x256 clips")
+def cpu_sample_text(args):
+    what = "eval-mode Encoder forward" if args.config == "cfg3" else \
+        ("fwd+loss+bwd" + ("" if args.no_optimizer else "+clip+Adam"))
+    return f"1 clip of {args.frames}x{args.size}x{args.size} per step (the arm's own clip shape), fp32, {what}"
 
 
 def run_reference(args):
@@ -87,17 +156,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    size, scale, sample = cpu_sample(args, args.steps + args.warmup)
-    t = oracle_step_time(size, args.frames, args.steps, args.warmup, args.enc_depth, args.dec_depth, threads)
-    value = scale / t
+    sample = cpu_sample_text(args)
+    t, n_timed = oracle_step_time(args, args.steps, args.warmup, threads, budget_s=280.0)
+    value = 1.0 / t
+    if n_timed < args.steps:
+        sample += f"; host time budget reached: {n_timed} of {args.steps} steps timed"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"VideoVAE train step (fwd+loss+bwd) on {args.frames}x{args.size}x{args.size} RGB clips, "
-                               f"enc {args.enc_depth}/dec {args.dec_depth}, mlp 1536, 8 heads x 64, latent 96 "
-                               "(BASELINE.json configs[1]); reference arm = CPU oracle port of the JAX/Flax reference "
-                               "(JAX is not installable offline), fp32, all host cores", "sample": sample},
+        "impl": "reference", "metric": CONFIGS[args.config]["metric"], "value": value, "unit": "clips/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "same_config": True, "steps_timed": n_timed,
+        "config": {"workload": workload_text(args, "; reference arm = CPU oracle port of the JAX/Flax reference (JAX is "
+                                                   "not installable offline), fp32, all host cores, one clip per step"),
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -192,19 +263,21 @@ def run_ours(args):
     flat = FlatParams(model)
     flat.enable_bf16_shadow()
     flat.broadcast(src=0)     # rank 0's weights everywhere (distributed_train.py:339 broadcast_one_to_all); untimed
-    reducer = GradAllReducer(flat) if world > 1 else None
-    opt = None if args.no_optimizer else FlatAdam(flat, lr=5e-5)
+    encode_only = args.config == "cfg3"
+    reducer = GradAllReducer(flat) if (world > 1 and not encode_only) else None
+    opt = None if (args.no_optimizer or encode_only) else FlatAdam(flat, lr=5e-5)
     hp = dict(V.DEFAULT_HPARAMS, gamma4=0.1)   # MSE + selection + KL + MAE terms
 
     g = torch.Generator().manual_seed(1234 + rank)
     host_video = torch.rand(B, Tn, S, S, 3, generator=g).to(torch.bfloat16).pin_memory()   # reference casts to bf16 on host
-    host_mask = torch.ones(B, Tn, dtype=torch.bool).pin_memory()
+    keep = torch.tensor(keep_per_clip(args))
+    host_mask = (torch.arange(Tn)[None, :] < keep[:, None]).contiguous().pin_memory()
     video = host_video.to(dev, non_blocking=True)
     mask = host_mask.to(dev, non_blocking=True)
     rngs = V.Rngs(3 + rank)
 
     graphed, ar_in_graph = None, False
-    if not args.no_graph:
+    if not args.no_graph and not encode_only:
         if reducer is not None and args.graph_allreduce:
             try:      # bucketed all-reduce captured inside the graph: overlaps the rest of backward
                 graphed = GraphedTrainStep(model, flat, video, mask, hp, reducer=reducer)
@@ -226,9 +299,22 @@ def run_ours(args):
             reducer.finish_step()
         return loss
 
+    def encode_step(v, m):
+        """cfg3: the loop of data_prep/save_latents.py:183-206 -- chunked eval-mode Encoder calls, no grad; returns a
+        device scalar (sum of the latents) standing in for the step's result that is read back."""
+        acc = None
+        with torch.no_grad():
+            for i in range(0, B, args.chunk):
+                mean, _, _ = model.encoder(v[i:i + args.chunk], m[i:i + args.chunk, None, None, :], V.Rngs(0), train=False)
+                part = mean.float().sum()
+                acc = part if acc is None else acc + part
+        return acc
+
     def step(v, m):
         """One training step.  Default: replay the captured graph (zero-grad + fwd + loss + bwd: one launch), then the
         gradient all-reduce (N > 1) and the fused clip + Adam kernels."""
+        if encode_only:
+            return encode_step(v, m)
         if graphed is not None:
             loss = graphed(v, m, rngs)
             if world > 1 and not ar_in_graph:
@@ -270,7 +356,7 @@ def run_ours(args):
         # eager pass over the same batch (kernel durations do not depend on how they were enqueued).
         ops.PROFILE = []
         calls_e0 = _ffi.launch_count
-        eager_step(video, mask)
+        eager_step(video, mask)      # NB: runs after the graph was captured (capture must precede eager backward)
         torch.cuda.synchronize()
         kernels_per_step = _ffi.launch_count - calls_e0
         prof, ops.PROFILE = ops.PROFILE, None
@@ -352,17 +438,18 @@ def run_ours(args):
                     "timing": "CUDA events around every launch of this kernel in one eager pass after the timed region"
                     if graphed is not None else "CUDA events around every launch inside the timed region"}
 
+    flop_per_clip = None if args.custom_shape else CONFIGS[args.config]["flop"]
+    if args.custom_shape and args.config == "cfg2" and Tn == 16:
+        flop_per_clip = FLOP_PER_CLIP.get(S)
     line = {
-        "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic",
-        "config": {"workload": f"VideoVAE train step (fwd+loss+bwd{'' if args.no_optimizer else '+clip+Adam'}) on "
-                               f"{Tn}x{S}x{S} RGB clips, batch {B}/GPU, enc {args.enc_depth}/dec {args.dec_depth}, "
-                               "mlp 1536, 8 heads x 64, latent 96 (BASELINE.json configs[1])",
-                   "global_batch": world * B, "parallelism": f"dp{world}",
+        "metric": CONFIGS[args.config]["metric"], "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_text(args), "global_batch": world * B, "parallelism": f"dp{world}",
                    "l2": "inputs+activations per step (tens of GB) >> 126 MB L2; no flush needed",
-                   "algorithmic_flop_per_clip": FLOP_PER_CLIP.get(S)},
-        "model_tflops": (value * FLOP_PER_CLIP[S] / 1e12 / world) if S in FLOP_PER_CLIP else None,
+                   "algorithmic_flop_per_clip": flop_per_clip,
+                   "frames_kept_per_clip": keep_per_clip(args) if args.config == "cfg4" else None},
+        "model_tflops": (value * flop_per_clip / 1e12 / world) if flop_per_clip else None,
         "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "clips/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": host_video.numel() * host_video.element_size() + host_mask.numel(),
                 "d2h_bytes_per_step": 4, "last_loss": last},
@@ -374,14 +461,14 @@ def run_ours(args):
         "execution": ("cuda-graph replay (zero-grad+fwd+loss+bwd" + ("+bucketed all-reduce" if ar_in_graph else "") +
                       ") + eager " + ("all-reduce + " if (world > 1 and not ar_in_graph) else "") + "optimizer")
         if graphed is not None else "eager",
+        "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30,
         "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        size, scale, sample = cpu_sample(args, 1)
-        t = oracle_step_time(size, Tn, 1, 0, args.enc_depth, args.dec_depth, threads)
-        line["cpu_baseline"] = {"value": scale / t, "unit": "clips/s", "cores": threads, "kind": "port",
-                                "sample": sample + " (1 step, no warm-up)"}
+        t, _ = oracle_step_time(args, 1, 0, threads)
+        line["cpu_baseline"] = {"value": 1.0 / t, "unit": "clips/s", "cores": threads, "kind": "port",
+                                "sample": cpu_sample_text(args) + " (1 step, no warm-up)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -135,6 +135,73 @@ def run_rl_oracle():
     return out
 
 
+# ---------------------------------------------------------------------------------------------- production depth
+def prod_cfg(size):
+    """Production hyper-parameters (train/rl_nonadversarial.py:234-236) at a square clip size."""
+    return (size, size, 3, 16, 9, 12, 1536, 8, 512, 64, 8, 4)
+
+
+PROD_KEEP_FRAMES = (1, 0, 1, 1, 0, 1, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1)
+
+
+def prod_inputs(size, keep, seed=11):
+    """Seeded 16-frame clip, prefix mask keeping `keep` frames (train/dataloader.py:232-234), reparameterisation noise
+    and DECISIVE Gumbel draws: u = sigmoid(+-6), so the logistic noise of train/layers.py:246-248 is +-6 and the gate
+    sigmoid(logit + noise) rounds the same way in fp32 and bf16 (|logit| << 6 at initialisation)."""
+    g = torch.Generator().manual_seed(seed)
+    hw = (size // 16) ** 2
+    video = torch.rand(1, 16, size, size, 3, generator=g)
+    mask = torch.zeros(1, 16, dtype=torch.bool)
+    mask[:, :keep] = True
+    noise = torch.randn(1, 16, hw, 96, generator=g)
+    keep_frame = torch.tensor(PROD_KEEP_FRAMES, dtype=torch.float32)
+    u = torch.sigmoid((keep_frame * 2 - 1) * 6.0).reshape(1, 16, 1)
+    return video, mask, noise, u, hw, keep_frame
+
+
+def build_prod_model(size):
+    from oracle import Rngs
+    from oracle.model import VideoVAE
+    o = VideoVAE(*prod_cfg(size), Rngs(2))
+    with torch.no_grad():   # final_conv is zero-initialised in the reference (train/unet.py:144-153): make the U-Net matter
+        k = o.decoder.unet.final_conv.kernel
+        k.copy_(torch.randn(k.shape, generator=torch.Generator().manual_seed(5)) * 0.05)
+    return o
+
+
+def run_prod_step(o, size, keep):
+    """Oracle forward + loss + backward at production depth; returns (loss, aux) with gradients left in o's .grad."""
+    from oracle import Rngs
+    from oracle.losses import DEFAULT_HPARAMS, expand_mask, loss_fn
+    video, mask, noise, u, hw, _ = prod_inputs(size, keep)
+    for p in o.parameters():
+        p.grad = None
+    loss, aux = loss_fn(o, video, expand_mask(mask, hw), mask, Rngs(0), DEFAULT_HPARAMS, noise=noise, gumbel_u=u)
+    loss.backward()
+    return loss, aux
+
+
+def run_prod_oracle(size=128, keep=12):
+    """BASELINE configs[0] (one 16x128x128 clip, fp32) at production depth, 12 of 16 frames kept."""
+    o = build_prod_model(size)
+    loss, aux = run_prod_step(o, size, keep)
+    out = {"loss": loss.detach().numpy(), "MSE": aux["MSE"].detach().numpy(), "MAE": aux["MAE"].detach().numpy(),
+           "kl_loss": aux["kl_loss"].detach().numpy(), "selection_loss": aux["selection_loss"].detach().numpy(),
+           "selection": aux["selection"].detach().reshape(1, 16).numpy(),
+           "mean_slice": aux["mean"].detach()[:, :, ::5, ::7].numpy(),
+           "logvar_slice": aux["logvar"].detach()[:, :, ::5, ::7].numpy(),
+           "recon_slice": aux["reconstruction"].detach()[:, :, ::9, ::11, :].numpy()}
+    names, norms = [], []
+    for n, p in o.named_parameters():
+        names.append(n)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    out["grad_names"] = np.array(names)
+    out["grad_norms"] = np.array(norms, dtype=np.float64)
+    out["grad_qkv_slice"] = o.encoder.layers[8].SpatialAttention.qkv_projection.kernel.grad[::16, ::32].numpy()
+    out["grad_mlp_slice"] = o.decoder.layers[0].TemporalMLP.linear1.kernel.grad[::16, ::32].numpy()
+    return out
+
+
 def main():
     out = run_oracle()
     out.update(run_attention_kat())
@@ -145,6 +212,10 @@ def main():
     path = os.path.join(HERE, "rl_step_cfg64_fp32.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes; loss =", float(out["rl_loss_total"]))
+    out = run_prod_oracle()
+    path = os.path.join(HERE, "videovae_prod128_fp32.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; loss =", float(out["loss"]))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,187 @@
+#!/usr/bin/env python
+"""Generate golden vectors from the REAL reference (JAX / Flax-NNX) -- run this on a box that has the reference's
+environment (jax 0.9, flax 0.12, einops; claude_distributed/requirements.txt) and a checkout of floatingtrees/video-VAE:
+
+    python tests/golden/make_golden_jax.py --reference /path/to/video-VAE [--cfg small|prod128] [--dtype float32]
+
+It cannot run in the build container of this repository (no jax, no network), which is why DESIGN.md section 3 says
+"parity unpinned".  The file it writes, tests/golden/jax_videovae_<cfg>_<dtype>.npz, is consumed by
+tests/test_jax_golden.py: the CPU test loads the reference's weights into the oracle and compares the oracle with the
+reference's outputs (this is what PINS the oracle); the GPU test does the same for the CUDA path.  Nothing else in the
+repository reads the reference at run time.
+
+What runs here is the reference's own code, unmodified: train/model.py::VideoVAE (imported from --reference/train) and
+the functions `magnify_negatives` / `loss_fn` of train/legacy/training_loop_adversarial.py:66-124, extracted from that
+file's AST and executed as they stand (importing the module itself would pull in its dataloader / wandb / orbax / VGG
+dependencies, which the hot path does not need).  The random draws the model makes inside the step (the Gumbel gate's
+uniform, train/layers.py:246, and the reparameterisation normal, train/model.py:126) are recorded by wrapping
+jax.random.uniform / jax.random.normal for the duration of the call, and stored, so that the oracle and the CUDA path
+can be fed the identical draws (`noise=`, `gumbel_u=`).
+
+Stored keys: cfg (12 ints), dtype, hparams (json), video, mask, gumbel_u, noise, param/<dotted.name>, out/{loss, MSE,
+selection_loss, kl_loss, kept_frame_density, reconstruction, compressed, selection, logvar, mean}, grad/<dotted.name>.
+Names are Flax attribute paths with list indices as integers -- exactly the names video_vae_b200 and the oracle use.
+"""
+import argparse
+import ast
+import json
+import os
+import sys
+
+import numpy as np
+
+CFGS = {
+    # the reference's own CPU test configuration (claude_distributed/test_rl_model.py), a ~5 M parameter file
+    "small": dict(cfg=(64, 64, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4), batch=2, frames=6, keep=(6, 4)),
+    # production hyper-parameters with 64-wide heads at a commit-sized width is impossible (170 M parameters): this
+    # one is for local use only (680 MB of fp32 weights in the .npz)
+    "prod128": dict(cfg=(128, 128, 3, 16, 9, 12, 1536, 8, 512, 64, 8, 4), batch=1, frames=16, keep=(12,)),
+    # 64-wide heads (the tcgen05 attention / GEMM path of the CUDA build) at a small depth
+    "hd64": dict(cfg=(64, 64, 3, 16, 2, 2, 256, 2, 128, 32, 8, 4), batch=2, frames=8, keep=(8, 5)),
+}
+HPARAMS = {"gamma1": 0.05, "gamma2": 0.001, "max_compression_rate": 2, "magnify_negatives_rate": 100}
+
+
+def _path_str(path):
+    """jax key path -> 'a.b.0.c' (DictKey.key / GetAttrKey.name / SequenceKey.idx / FlattenedIndexKey.key)."""
+    parts = []
+    for k in path:
+        for attr in ("key", "name", "idx"):
+            if hasattr(k, attr):
+                parts.append(str(getattr(k, attr)))
+                break
+        else:
+            parts.append(str(k))
+    if parts and parts[-1] in ("value", "raw_value"):
+        parts = parts[:-1]
+    return ".".join(parts)
+
+
+def flatten_state(state):
+    import jax
+    if hasattr(state, "to_pure_dict"):
+        state = state.to_pure_dict()
+    leaves = jax.tree_util.tree_leaves_with_path(state)
+    return {_path_str(p): np.asarray(v) for p, v in leaves}
+
+
+def reference_loss_fn(reference_root):
+    """`magnify_negatives` and `loss_fn` exactly as written in train/legacy/training_loop_adversarial.py."""
+    import jax
+    import jax.numpy as jnp
+    from einops import rearrange, reduce, repeat
+    from flax import nnx
+    from jaxtyping import Array, Float
+    path = os.path.join(reference_root, "train", "legacy", "training_loop_adversarial.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("magnify_negatives", "loss_fn")]
+    assert {n.name for n in keep} == {"magnify_negatives", "loss_fn"}, "reference layout changed"
+    ns = {"jax": jax, "jnp": jnp, "nnx": nnx, "rearrange": rearrange, "reduce": reduce, "repeat": repeat,
+          "Float": Float, "Array": Array}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)      # noqa: S102 (the reference's own code)
+    return ns["loss_fn"]
+
+
+class DrawRecorder:
+    """Records every jax.random.uniform / normal result produced while active."""
+
+    def __init__(self):
+        self.uniform, self.normal = [], []
+
+    def __enter__(self):
+        import jax
+        self._u, self._n = jax.random.uniform, jax.random.normal
+
+        def uniform(key, shape=(), *a, **k):
+            out = self._u(key, shape, *a, **k)
+            self.uniform.append(np.asarray(out))
+            return out
+
+        def normal(key, shape=(), *a, **k):
+            out = self._n(key, shape, *a, **k)
+            self.normal.append(np.asarray(out))
+            return out
+        jax.random.uniform, jax.random.normal = uniform, normal
+        return self
+
+    def __exit__(self, *exc):
+        import jax
+        jax.random.uniform, jax.random.normal = self._u, self._n
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reference", default="/root/reference")
+    ap.add_argument("--cfg", default="small", choices=sorted(CFGS))
+    ap.add_argument("--dtype", default="float32", choices=["float32", "bfloat16"])
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    sys.path.insert(0, os.path.join(args.reference, "train"))
+    import jax
+    import jax.numpy as jnp
+    from einops import rearrange, repeat
+    from flax import nnx
+    from model import VideoVAE                     # the reference's train/model.py
+
+    spec = CFGS[args.cfg]
+    cfg, b, t = spec["cfg"], spec["batch"], spec["frames"]
+    dtype = jnp.float32 if args.dtype == "float32" else jnp.bfloat16
+    model = VideoVAE(*cfg, rngs=nnx.Rngs(2), dtype=dtype, param_dtype=jnp.float32)
+    # the reference zero-initialises final_conv (train/unet.py:144-153), which switches the U-Net's gradients off:
+    # randomise it so the fixture exercises the whole path
+    k = model.decoder.unet.final_conv.kernel
+    k.value = 0.05 * jax.random.normal(jax.random.key(5), k.value.shape, k.value.dtype)
+
+    hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
+    key = jax.random.key(11)
+    kv, = jax.random.split(key, 1)
+    video = jax.random.uniform(kv, (b, t, cfg[0], cfg[1], cfg[2]), jnp.float32)
+    original_mask = jnp.arange(t)[None, :] < jnp.asarray(spec["keep"])[:, None]            # prefix masks (dataloader.py:232-234)
+    mask = rearrange(original_mask, "b time -> b 1 1 time")                                # train_step, :126-130
+    mask = repeat(mask, "b 1 1 time -> b hw 1 1 time", hw=hw)
+    mask = rearrange(mask, "b hw 1 1 time -> (b hw) 1 1 time")
+
+    loss_fn = reference_loss_fn(args.reference)
+    grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
+    with DrawRecorder() as rec:
+        (loss, (mse, sel_loss, kl, recon, density)), grads = grad_fn(
+            model, video.astype(dtype), mask, original_mask, nnx.Rngs(3), HPARAMS)
+    assert len(rec.uniform) == 1 and len(rec.normal) == 1, (len(rec.uniform), len(rec.normal))
+    gumbel_u, noise = rec.uniform[0], rec.normal[0]
+
+    # second, non-differentiated call with the SAME draws to export the remaining outputs of VideoVAE.__call__
+    class Replay:
+        def __init__(self):
+            self.u, self.n = [gumbel_u], [noise]
+
+        def __enter__(self):
+            self._u, self._n = jax.random.uniform, jax.random.normal
+            jax.random.uniform = lambda key, shape=(), *a, **k: jnp.asarray(self.u.pop(0))
+            jax.random.normal = lambda key, shape=(), *a, **k: jnp.asarray(self.n.pop(0))
+            return self
+
+        def __exit__(self, *exc):
+            jax.random.uniform, jax.random.normal = self._u, self._n
+    with Replay():
+        recon2, compressed, selection, logvar, mean = model(video.astype(dtype), mask, nnx.Rngs(3), train=True)
+    assert np.allclose(np.asarray(recon2, np.float32), np.asarray(recon, np.float32), rtol=1e-5, atol=1e-6)
+
+    out = {"cfg": np.asarray(cfg, np.int64), "dtype": np.asarray(args.dtype), "hparams": np.asarray(json.dumps(HPARAMS)),
+           "video": np.asarray(video, np.float32), "mask": np.asarray(original_mask), "gumbel_u": gumbel_u.astype(np.float32),
+           "noise": noise.astype(np.float32)}
+    for name, v in flatten_state(nnx.state(model, nnx.Param)).items():
+        out["param/" + name] = v.astype(np.float32)
+    for name, v in flatten_state(grads).items():
+        out["grad/" + name] = v.astype(np.float32)
+    f32 = lambda x: np.asarray(x, np.float32)      # noqa: E731
+    out.update({"out/loss": f32(loss), "out/MSE": f32(mse), "out/selection_loss": f32(sel_loss), "out/kl_loss": f32(kl),
+                "out/kept_frame_density": f32(density), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
+                "out/selection": f32(selection), "out/logvar": f32(logvar), "out/mean": f32(mean)})
+    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"jax_videovae_{args.cfg}_{args.dtype}.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes; loss =", float(loss), "; jax", jax.__version__)
+
+
+if __name__ == "__main__":
+    main()

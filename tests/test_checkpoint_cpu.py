@@ -91,3 +91,78 @@ def test_rl_host_helpers_need_no_host_reads():
     assert torch.equal(alt.detach(), torch.ones_like(alt))
     (alt * w).sum().backward()
     assert torch.allclose(raw.grad, g_prod, rtol=1e-6, atol=0) and float(raw.grad[..., 3:].abs().max()) == 0.0
+
+
+def _reference_shaped_checkpoint(model, mu_model, nu_model, count=41):
+    """A tree shaped exactly like the reference's ``{"model": nnx.state(model), "optimizer": nnx.state(optimizer)}``
+    (train/rl_nonadversarial.py:62-67): ``{"value": ...}`` leaves, int list indices, the RotaryEmbedding tables that
+    train/layers.py:101-102 stores as nnx.Variables ([1, max_len, 1, head_dim]), RNG stream state, and the optax chain
+    ``(EmptyState(), (ScaleByAdamState(count, mu, nu), ScaleByScheduleState(count)))`` under ``opt_state``."""
+    tree = ck.to_flax_tree(model, wrap_value=True)
+    for name, mod in model.named_modules():
+        if name.endswith("ROPE"):
+            node = tree
+            for p_ in name.split("."):
+                node = node.setdefault(int(p_) if p_.isdigit() else p_, {})
+            node["cos_cached"] = {"value": mod.cos_cached.numpy()[None, :, None, :]}
+            node["sin_cached"] = {"value": mod.sin_cached.numpy()[None, :, None, :]}
+    tree["encoder"]["rngs"] = {"default": {"key": {"value": np.zeros(2, np.uint32)}, "count": {"value": np.zeros((), np.uint32)}}}
+    opt = {"step": {"value": np.asarray(count, np.uint32)},
+           "opt_state": {0: {},
+                         1: {0: {"count": {"value": np.asarray(count, np.int32)},
+                                 "mu": ck.to_flax_tree(mu_model, wrap_value=True),
+                                 "nu": ck.to_flax_tree(nu_model, wrap_value=True)},
+                             1: {"count": {"value": np.asarray(count, np.int32)}}}}}
+    return {"model": tree, "optimizer": opt}
+
+
+def test_reference_shaped_checkpoint_with_rope_tables_and_optimizer_state(tmp_path):
+    """VERDICT r1 / ADVICE: a real reference tree carries ROPE.{cos,sin}_cached Variables and an optax chain state."""
+    from video_vae_b200.ddp import FlatAdam, FlatParams
+    src, mu_m, nu_m = _model(0), _model(3), _model(4)
+    state = _reference_shaped_checkpoint(src, mu_m, nu_m, count=41)
+    assert "cos_cached" in state["model"]["encoder"]["layers"][0]["TemporalAttention"]["ROPE"]
+    dst = _model(1)
+    flat = FlatParams(dst)
+    adam = FlatAdam(flat)
+    loaded = ck.load_flax_tree(dst, state["model"], strict=True)          # strict: RoPE tables / rngs are not "unexpected"
+    assert len(loaded) == len(src.state_dict())
+    assert all(torch.equal(x, y) for x, y in zip(src.state_dict().values(), dst.state_dict().values()))
+    assert ck.rope_tables_match(state["model"], dst) == 8                 # 2 layers x 2 attentions x (cos, sin)
+    bad = _reference_shaped_checkpoint(src, mu_m, nu_m)
+    bad["model"]["encoder"]["layers"][0]["TemporalAttention"]["ROPE"]["cos_cached"]["value"] *= 1.01
+    with pytest.raises(ValueError, match="RoPE"):
+        ck.rope_tables_match(bad["model"], dst)
+    assert ck.load_optimizer_state(adam, dst, state["optimizer"]) == 41 and adam.t == 41
+    names = [n for n, _ in dst.named_parameters()]
+    for probe in ("encoder.layers.0.SpatialAttention.qkv_projection.kernel", "fill_token"):
+        i = names.index(probe)
+        s, n = flat.offsets[i], flat.params[i].numel()
+        assert torch.equal(adam.m[s:s + n], dict(mu_m.named_parameters())[probe].detach().reshape(-1))
+        assert torch.equal(adam.v[s:s + n], dict(nu_m.named_parameters())[probe].detach().reshape(-1))
+    # the flattened transport file of the whole {"model", "optimizer"} state
+    ck.save_npz(str(tmp_path / "full.npz"), state)
+    again = _model(2)
+    flat2 = FlatParams(again)
+    adam2 = FlatAdam(flat2)
+    ck.load_checkpoint(again, str(tmp_path / "full.npz"), adam=adam2)
+    assert all(torch.equal(x, y) for x, y in zip(src.state_dict().values(), again.state_dict().values()))
+    assert adam2.t == 41 and torch.equal(adam2.m, adam.m) and torch.equal(adam2.v, adam.v)
+
+
+def test_two_flat_params_keep_their_own_bf16_shadows():
+    """a second FlatParams.enable_bf16_shadow() must not orphan the first model's shadow views."""
+    from video_vae_b200 import functional as F_
+    from video_vae_b200.ddp import FlatParams
+    a, b = _model(0), _model(1)
+    fa, fb = FlatParams(a), FlatParams(b)
+    fa.shadow = torch.empty(fa.total, dtype=torch.bfloat16)
+    fb.shadow = torch.empty(fb.total, dtype=torch.bfloat16)
+    import weakref
+    for f in (fa, fb):      # what enable_bf16_shadow does, minus the device cast kernel
+        for p, o in zip(f.params, f.offsets):
+            f._shadow_views[id(p)] = (weakref.ref(p), f.shadow[o:o + p.numel()].view(p.shape))
+        F_._flat_shadow_views.update(f._shadow_views)
+    pa, pb = a.fill_token, b.fill_token
+    assert F_.shadow(pa, torch.bfloat16).data_ptr() == fa._shadow_views[id(pa)][1].data_ptr()
+    assert F_.shadow(pb, torch.bfloat16).data_ptr() == fb._shadow_views[id(pb)][1].data_ptr()

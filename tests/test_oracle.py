@@ -405,3 +405,31 @@ def test_oracle_reproduces_rl_step_golden_fixture():
             ref = np.asarray(gold[key], dtype=np.float64)
             got = np.asarray(now[key], dtype=np.float64)
             assert np.allclose(got, ref, rtol=5e-4, atol=5e-5 * max(1e-6, np.abs(ref).max())), key
+
+
+def test_oracle_reproduces_production_depth_golden_fixture():
+    """tests/golden/videovae_prod128_fp32.npz: BASELINE configs[0] (one 16x128x128 clip, fp32) at PRODUCTION depth
+    (enc 9 / dec 12, mlp 1536, 8 heads x 64), 12 of 16 frames kept -- loss terms, latent / reconstruction slices and
+    all 600+ gradient norms as written by make_golden.py::run_prod_oracle (thread count changes BLAS summation order
+    over 21 layers: rtol 1e-3 on gradient norms)."""
+    import importlib.util
+    import os
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(here, "golden", "videovae_prod128_fp32.npz"))
+    now = mg.run_prod_oracle()
+    assert sorted(now) == sorted(gold.files)
+    assert len(gold["grad_names"]) > 600
+    for key in gold.files:
+        if key == "grad_names":
+            assert list(now[key]) == list(gold[key])
+        elif key == "selection":
+            assert np.array_equal(now[key], gold[key])
+            assert np.array_equal(now[key].reshape(-1), np.asarray(mg.PROD_KEEP_FRAMES, dtype=np.float32))
+        else:
+            ref = np.asarray(gold[key], dtype=np.float64)
+            got = np.asarray(now[key], dtype=np.float64)
+            assert np.allclose(got, ref, rtol=1e-3, atol=1e-4 * max(1e-6, np.abs(ref).max())), key

@@ -286,6 +286,13 @@ def _inputs(b=2, t=4, hw=16, lat=96):
     return video, mask, noise, u
 
 
+def _decisive_u(b, t, seed=13):
+    """Gumbel draws with a +-6 logistic margin (u = sigmoid(+-6)): the frame gate round(sigmoid(logit + noise)) of
+    train/layers.py:246-248 is then decided by the draw, not by rounding differences between fp32 and bf16."""
+    keep = (torch.rand(b, t, 1, generator=_gen(seed)) < 0.6).float()
+    return torch.sigmoid((keep * 2 - 1) * 6.0), keep
+
+
 def test_videovae_loss_and_grads_fp32(V):
     """cfg-1-style correctness: whole model forward + loss + backward, fp32, vs the oracle (reduced depth)."""
     from oracle import Rngs as ORngs
@@ -310,7 +317,8 @@ def test_videovae_bf16_loss_and_latents(V):
     from oracle import Rngs as ORngs
     from oracle.losses import DEFAULT_HPARAMS, expand_mask, loss_fn as o_loss_fn
     m, o = _small_pair(V, torch.bfloat16)
-    video, mask, noise, u = _inputs()
+    video, mask, noise, _ = _inputs()
+    u, keep = _decisive_u(*mask.shape)
     lo, auxo = o_loss_fn(o, video, expand_mask(mask, 16), mask, ORngs(0), DEFAULT_HPARAMS, noise=noise, gumbel_u=u)
     lm, auxm = V.loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), V.DEFAULT_HPARAMS,
                          noise=noise.cuda(), gumbel_u=u.cuda())
@@ -318,8 +326,9 @@ def test_videovae_bf16_loss_and_latents(V):
     assert auxm["mean"].dtype == torch.bfloat16 and auxm["reconstruction"].dtype == torch.bfloat16
     assert rel_err(auxm["mean"], auxo["mean"]) < BF16_TOL
     assert rel_err(auxm["logvar"], auxo["logvar"]) < BF16_TOL
-    if torch.equal(auxm["selection"].cpu().reshape(-1), auxo["selection"].reshape(-1)):
-        assert abs(lm.item() - lo.item()) <= BF16_TOL * abs(lo.item())
+    assert torch.equal(auxo["selection"].reshape(-1), keep.reshape(-1))
+    assert torch.equal(auxm["selection"].float().cpu().reshape(-1), keep.reshape(-1))
+    assert abs(lm.item() - lo.item()) <= BF16_TOL * abs(lo.item())                  # unconditional: the gate is pinned
     for n_, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n_
 
@@ -502,6 +511,8 @@ def _attention_reference(qk, qkv, d_o, geom, temporal, b, t, hw, H, HD, mask_bl)
     ("temporal_allmasked_clip", 2, 16, 16, True, True),
     ("spatial_long_L384_masked", 1, 2, 384, False, True),
     ("spatial_long_L512", 1, 1, 512, False, False),
+    ("spatial_long_L1024", 1, 2, 1024, False, False),          # BASELINE configs[4]: 512x512 clips, hw = 1024
+    ("spatial_long_L1024_masked", 1, 1, 1024, False, True),
 ])
 def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked):
     """bf16, head_dim 64: the tensor-core attention (forward AND backward) against oracle autograd on identical data.
@@ -603,7 +614,7 @@ def test_videovae_bf16_head_dim64_tensor_core_path(V):
     mask[0, 5:] = False
     mask[2, 2:] = False
     noise = torch.randn(b, t, hw, 96, generator=g)
-    u = torch.rand(b, t, 1, generator=g)
+    u, keep = _decisive_u(b, t)
     lo, auxo = o_loss_fn(o, video, expand_mask(mask, hw), mask, ORngs(0), DEFAULT_HPARAMS, noise=noise, gumbel_u=u)
     lo.backward()
     lm, auxm = V.loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), V.DEFAULT_HPARAMS,
@@ -611,20 +622,20 @@ def test_videovae_bf16_head_dim64_tensor_core_path(V):
     lm.backward()
     assert rel_err(auxm["mean"], auxo["mean"]) < BF16_TOL
     assert rel_err(auxm["logvar"], auxo["logvar"]) < BF16_TOL
-    same_gate = torch.equal(auxm["selection"].cpu().reshape(-1), auxo["selection"].reshape(-1))
-    if same_gate:
-        assert abs(lm.item() - lo.item()) <= BF16_TOL * abs(lo.item())
-        og = dict(o.named_parameters())
-        cos_min, n = 1.0, 0
-        for name, p in m.named_parameters():
-            ref = og[name].grad
-            if ref is None or ref.numel() < 64 or ref.abs().max() == 0:
-                continue
-            c = torch.nn.functional.cosine_similarity(p.grad.float().cpu().reshape(1, -1), ref.reshape(1, -1)).item()
-            cos_min = min(cos_min, c)
-            n += 1
-            assert c > 0.98, (name, c)
-        assert n >= 50
+    assert torch.equal(auxo["selection"].reshape(-1), keep.reshape(-1))
+    assert torch.equal(auxm["selection"].float().cpu().reshape(-1), keep.reshape(-1))
+    assert abs(lm.item() - lo.item()) <= BF16_TOL * abs(lo.item())                  # unconditional: the gate is pinned
+    og = dict(o.named_parameters())
+    n = 0
+    for name, p in m.named_parameters():
+        ref = og[name].grad
+        if ref is None or ref.numel() < 64 or ref.abs().max() == 0:
+            continue
+        c = torch.nn.functional.cosine_similarity(p.grad.float().cpu().reshape(1, -1), ref.reshape(1, -1)).item()
+        n += 1
+        assert c > 0.98, (name, c)
+        assert rel_l2(p.grad, ref) < 0.3, (name, rel_l2(p.grad, ref))
+    assert n >= 50
     for n_, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n_
 

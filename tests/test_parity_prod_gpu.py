@@ -1,0 +1,221 @@
+"""GPU parity at PRODUCTION depth/width: libvvae (through the C ABI) vs the CPU oracle, enc 9 / dec 12, mlp 1536,
+8 heads x 64, latent 96 (train/rl_nonadversarial.py:234-236) -- the hyper-parameters BASELINE.json's metric is quoted on.
+
+  * BASELINE configs[0]: one 16x128x128 clip, fp32, rel err <= 1e-4 on reconstruction / mean / logvar / every loss term,
+    <= 1e-3 on every parameter gradient (north_star's fp32 bar; gradients get the extra decade the round-1 tests use).
+  * the same clip and one 16x256x256 clip in bf16 against the fp32 oracle: rel err <= 2e-2 on loss, mean, logvar
+    (north_star's bf16 bar), asserted UNCONDITIONALLY -- the Gumbel draws are injected with a +-6 logistic margin so
+    the frame gate cannot flip between precisions, and the gate is asserted equal.  Gradient rel-L2 per layer depth is
+    reported (train/llm_tests.py:491-502 documents depth-wise error growth in the reference itself).
+  * BASELINE configs[3] shape of masks: prefix masks keeping 4 / 8 / 12 of 16 frames (train/dataloader.py:232-234).
+
+Oracle outputs are computed once per (size, keep) and shared by the fp32 / bf16 / golden tests.  The observed errors
+are printed (pytest -s / the captured log on failure) and written to gpurun_out/parity_prod_report.json.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+FP32_GRAD_TOL = 1e-3
+BF16_TOL = 2e-2
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_REPORT = {}
+
+
+def _mg():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(ROOT, "tests", "golden", "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+MG = _mg()
+prod_cfg, make_inputs = MG.prod_cfg, MG.prod_inputs      # shared with the golden generator: same seeds, same draws
+
+
+def rel_err(a, ref):
+    a, ref = a.detach().float().cpu(), ref.detach().float().cpu()
+    return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+def rel_l2(a, ref):
+    a, ref = a.detach().double().cpu(), ref.detach().double().cpu()
+    return ((a - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
+def _report(key, value):
+    _REPORT[key] = value
+    print(f"[parity-prod] {key}: {value}")
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_prod_report.json"), "w") as f:
+            json.dump(_REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+class _Oracle:
+    """Production-depth oracle models (one per spatial size: selection_layer2 depends on hw) and cached results."""
+
+    def __init__(self):
+        self.models, self.results = {}, {}
+
+    def model(self, size):
+        if size not in self.models:
+            self.models[size] = MG.build_prod_model(size)
+        return self.models[size]
+
+    def run(self, size, keep):
+        if (size, keep) not in self.results:
+            o = self.model(size)
+            loss, aux = MG.run_prod_step(o, size, keep)
+            res = {"loss": loss.detach(), "grads": {n: p.grad.detach().clone() for n, p in o.named_parameters()
+                                                    if p.grad is not None}}
+            for k_, v in aux.items():
+                res[k_] = v.detach()
+            self.results[(size, keep)] = res
+        return self.results[(size, keep)]
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return _Oracle()
+
+
+@pytest.fixture(scope="module")
+def V():
+    import video_vae_b200 as V
+    from video_vae_b200 import _ffi
+    _ffi.require_device()
+    return V
+
+
+def _cuda_model(V, oracle, size, dtype):
+    m = V.VideoVAE(*prod_cfg(size), V.Rngs(2), dtype=dtype)
+    m.load_state_dict({k: v.detach().clone() for k, v in oracle.model(size).state_dict().items()}, strict=True)
+    return m
+
+
+def _cuda_step(V, m, size, keep):
+    video, mask, noise, u, hw, keep_frame = make_inputs(size, keep)
+    for p in m.parameters():
+        p.grad = None
+    loss, aux = V.loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), V.DEFAULT_HPARAMS,
+                          noise=noise.cuda(), gumbel_u=u.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    return loss, aux, keep_frame
+
+
+def _depth_of(name):
+    parts = name.split(".")
+    if len(parts) > 2 and parts[1] == "layers":
+        return f"{parts[0]}.layers.{int(parts[2]):02d}"
+    if "unet" in parts:
+        return "decoder.unet"
+    return parts[0] + "." + parts[1] if len(parts) > 1 else parts[0]
+
+
+def _grad_report(m, ref_grads):
+    """max-norm rel err per tensor (worst) and rel-L2 per layer depth (all tensors of the layer concatenated)."""
+    worst, worst_name, groups = 0.0, None, {}
+    for name, p in m.named_parameters():
+        ref = ref_grads.get(name)
+        if ref is None or float(ref.abs().max()) == 0.0:
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        assert torch.isfinite(p.grad).all(), name
+        e = rel_err(p.grad, ref)
+        if e > worst:
+            worst, worst_name = e, name
+        d = groups.setdefault(_depth_of(name), [0.0, 0.0])
+        d[0] += float((p.grad.detach().double().cpu() - ref.double()).pow(2).sum())
+        d[1] += float(ref.double().pow(2).sum())
+    per_depth = {k: (v[0] / max(v[1], 1e-300)) ** 0.5 for k, v in sorted(groups.items())}
+    return worst, worst_name, per_depth
+
+
+# ------------------------------------------------------------------------------------------------ fp32, configs[0]
+@pytest.mark.parametrize("keep", [16, 12, 8, 4])
+def test_prod_depth_fp32_128_matches_oracle(V, oracle, keep):
+    """BASELINE configs[0] (1x16x128x128, fp32) and its prefix-masked variants (configs[3] masks) at production depth."""
+    ref = oracle.run(128, keep)
+    m = _cuda_model(V, oracle, 128, torch.float32)
+    loss, aux, keep_frame = _cuda_step(V, m, 128, keep)
+    assert torch.equal(aux["selection"].detach().cpu().reshape(-1), ref["selection"].reshape(-1))
+    assert torch.equal(ref["selection"].reshape(-1), keep_frame)                    # the injected margin decides the gate
+    errs = {k: rel_err(aux[k], ref[k]) for k in ("mean", "logvar", "reconstruction", "compressed")}
+    for k in ("MSE", "MAE", "kl_loss", "selection_loss"):
+        errs[k] = abs(aux[k].item() - ref[k].item()) / max(abs(ref[k].item()), 1e-6)
+    errs["loss"] = abs(loss.item() - ref["loss"].item()) / abs(ref["loss"].item())
+    worst, worst_name, per_depth = _grad_report(m, ref["grads"])
+    _report(f"fp32_128_keep{keep}", {"fwd_rel_err": errs, "grad_worst_rel_err": worst, "grad_worst_name": worst_name,
+                                     "grad_rel_l2_per_depth": per_depth})
+    for k, e in errs.items():
+        assert e < FP32_TOL, (k, e)
+    assert worst < FP32_GRAD_TOL, (worst_name, worst)
+
+
+def test_prod_depth_fp32_matches_golden_fixture(V, oracle):
+    """The committed oracle outputs of tests/golden/make_golden.py::run_prod_oracle (keep = 12) -- the CUDA path must
+    reproduce the numbers in the repository, not only an oracle run on the same box."""
+    import numpy as np
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "videovae_prod128_fp32.npz"))
+    m = _cuda_model(V, oracle, 128, torch.float32)
+    loss, aux, _ = _cuda_step(V, m, 128, 12)
+    for key in ("loss", "MSE", "MAE", "kl_loss", "selection_loss"):
+        got = loss.item() if key == "loss" else aux[key].item()
+        assert abs(got - float(gold[key])) <= FP32_TOL * max(abs(float(gold[key])), 1e-6), key
+    assert np.array_equal(aux["selection"].detach().reshape(-1).cpu().numpy(), gold["selection"].reshape(-1))
+    assert rel_err(aux["mean"][:, :, ::5, ::7], torch.from_numpy(gold["mean_slice"])) < FP32_TOL
+    assert rel_err(aux["logvar"][:, :, ::5, ::7], torch.from_numpy(gold["logvar_slice"])) < FP32_TOL
+    assert rel_err(aux["reconstruction"][:, :, ::9, ::11, :], torch.from_numpy(gold["recon_slice"])) < FP32_TOL
+    norms = dict(zip([str(n) for n in gold["grad_names"]], gold["grad_norms"]))
+    checked = 0
+    for name, p in m.named_parameters():
+        ref = float(norms[name])
+        if ref == 0.0:
+            continue
+        got = p.grad.double().norm().item()
+        assert abs(got - ref) <= FP32_GRAD_TOL * ref, (name, got, ref)
+        checked += 1
+    assert checked >= 500
+    gq = m.encoder.layers[8].SpatialAttention.qkv_projection.kernel.grad[::16, ::32]
+    assert rel_err(gq, torch.from_numpy(gold["grad_qkv_slice"])) < FP32_GRAD_TOL
+    gm = m.decoder.layers[0].TemporalMLP.linear1.kernel.grad[::16, ::32]
+    assert rel_err(gm, torch.from_numpy(gold["grad_mlp_slice"])) < FP32_GRAD_TOL
+
+
+# ------------------------------------------------------------------------------------------------ bf16 vs fp32 oracle
+@pytest.mark.parametrize("size,keep", [(128, 16), (128, 12), (128, 8), (128, 4), (256, 16), (256, 8)])
+def test_prod_depth_bf16_matches_fp32_oracle(V, oracle, size, keep):
+    """north_star: bf16 rel err <= 2e-2 on the loss and the latent mean / logvar, production depth, the tcgen05 path
+    (hd = 64, 16 frames: warp-level temporal attention, tcgen05 spatial attention / GEMMs / convs)."""
+    ref = oracle.run(size, keep)
+    m = _cuda_model(V, oracle, size, torch.bfloat16)
+    loss, aux, keep_frame = _cuda_step(V, m, size, keep)
+    assert aux["mean"].dtype == torch.bfloat16 and aux["reconstruction"].dtype == torch.bfloat16
+    assert torch.equal(aux["selection"].detach().float().cpu().reshape(-1), keep_frame)
+    assert torch.equal(ref["selection"].reshape(-1), keep_frame)
+    errs = {"loss": abs(loss.item() - ref["loss"].item()) / abs(ref["loss"].item()),
+            "mean": rel_err(aux["mean"], ref["mean"]), "logvar": rel_err(aux["logvar"], ref["logvar"]),
+            "mean_l2": rel_l2(aux["mean"], ref["mean"]), "logvar_l2": rel_l2(aux["logvar"], ref["logvar"]),
+            "reconstruction_l2": rel_l2(aux["reconstruction"], ref["reconstruction"]),
+            "MSE": abs(aux["MSE"].item() - ref["MSE"].item()) / abs(ref["MSE"].item()),
+            "kl_loss": abs(aux["kl_loss"].item() - ref["kl_loss"].item()) / abs(ref["kl_loss"].item())}
+    worst, worst_name, per_depth = _grad_report(m, ref["grads"])
+    _report(f"bf16_{size}_keep{keep}", {"fwd_rel_err": errs, "grad_worst_rel_err": worst,
+                                        "grad_worst_name": worst_name, "grad_rel_l2_per_depth": per_depth})
+    assert errs["loss"] < BF16_TOL, errs
+    assert errs["mean"] < BF16_TOL, errs
+    assert errs["logvar"] < BF16_TOL, errs
+    # gradients: no tolerance is stated by north_star for bf16; bound the per-depth rel-L2 so a broken backward kernel
+    # (O(1) error) cannot hide, and report the numbers
+    assert max(per_depth.values()) < 0.25, per_depth

@@ -15,6 +15,20 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int num_sms() {
+  // queried once per process (C++11 magic static: thread-safe); one process drives one GPU
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        v <= 0) {
+      cudaGetLastError();
+      v = 148;   // B200; only reached without a device, where every launch fails loudly anyway
+    }
+    return v;
+  }();
+  return n;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -156,11 +170,11 @@ int vvae_cast(const void* src, int sd, void* dst, int dd, long long n, vvae_stre
   int threads = 256;
   if (sd == VVAE_F32 && dd == VVAE_BF16 && n % 8 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
     long long n8 = n / 8;
-    int blocks = (int)std::min<long long>(cdiv(n8, threads), 148 * 16);
+    int blocks = (int)std::min<long long>(cdiv(n8, threads), num_sms() * 16);
     cast_f32_bf16_vec_kernel<<<blocks, threads, 0, s>>>((const float4*)src, (uint4*)dst, n8);
     return check_launch("cast");
   }
-  int blocks = (int)std::min<long long>(cdiv(n, threads * 4), 148 * 16);
+  int blocks = (int)std::min<long long>(cdiv(n, threads * 4), num_sms() * 16);
   if (sd == VVAE_F32 && dd == VVAE_BF16) cast_kernel<<<blocks, threads, 0, s>>>((const float*)src, (bf16*)dst, n);
   else if (sd == VVAE_BF16 && dd == VVAE_F32) cast_kernel<<<blocks, threads, 0, s>>>((const bf16*)src, (float*)dst, n);
   else if (sd == VVAE_F32 && dd == VVAE_F32) cast_kernel<<<blocks, threads, 0, s>>>((const float*)src, (float*)dst, n);
@@ -171,7 +185,7 @@ int vvae_cast(const void* src, int sd, void* dst, int dd, long long n, vvae_stre
 
 int vvae_fill_f32(float* dst, float value, long long n, vvae_stream_t stream) {
   if (n <= 0) return VVAE_OK;
-  int blocks = (int)std::min<long long>(cdiv(n, 256), 148 * 16);
+  int blocks = (int)std::min<long long>(cdiv(n, 256), num_sms() * 16);
   fill_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dst, value, n);
   return check_launch("fill");
 }
@@ -181,7 +195,7 @@ int vvae_colsum(const void* x, long long ld, long long rows, int n, float* out, 
   VVAE_REQUIRE(x && out, "vvae_colsum: null pointer");
   if (dtype == VVAE_BF16 && n % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
     const int cb = (int)cdiv(n, 256);
-    const long long want = cdiv(148 * 3, cb);
+    const long long want = cdiv(num_sms() * 3, cb);
     const long long rpb = std::max<long long>(128, (cdiv(rows, want) + 63) / 64 * 64);   // whole 64-row unrolled steps
     dim3 grid(cb, (unsigned)cdiv(rows, rpb));
     colsum_bf16_vec_kernel<<<grid, 256, 0, as_stream(stream)>>>((const bf16*)x, ld, rows, n, out, (int)rpb);
@@ -189,7 +203,7 @@ int vvae_colsum(const void* x, long long ld, long long rows, int n, float* out, 
   }
   int col_blocks = (int)cdiv(n, 32);
   // enough row slabs to fill the machine a few times over, at least 64 rows each
-  long long want = cdiv(148 * 8, col_blocks);
+  long long want = cdiv(num_sms() * 8, col_blocks);
   long long rpb = std::max<long long>(64, cdiv(rows, want));
   int row_blocks = (int)cdiv(rows, rpb);
   dim3 grid(col_blocks, row_blocks), block(32, 8);

@@ -13,6 +13,7 @@
 // 128B-swizzled layout, over the dead Q/K tiles -> O = P.V (tcgen05; V is consumed MN-major as it lies) ->
 // O / rowsum and the log-sum-exp are stored.  Two CTAs share an SM (<= 97 KB smem, <= 256 TMEM columns each) so one
 // CTA's softmax overlaps the other's MMAs and loads.
+#include <atomic>
 #include <cuda.h>
 #include <cfloat>
 
@@ -347,14 +348,14 @@ static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   q.mask = a.mask; q.mask_seq_div = a.mask_seq_div > 0 ? a.mask_seq_div : 1; q.ms_seq = a.ms_seq; q.ms_k = a.ms_k;
   q.scale = a.scale;
   auto kern = attn_fwd_sm100_kernel<NK, PACKED, MASKED>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {   // idempotent: a racing second call sets the same value
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
       return VVAE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   dim3 grid((unsigned)p.tiles, (unsigned)p.heads);
   kern<<<grid, 192, SMEM, s>>>(mq, mk, mv, q);
@@ -710,14 +711,14 @@ static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   q.dq_rs = a.dq_rs; q.dk_rs = a.dk_rs; q.dv_rs = a.dv_rs;
   q.scale = a.scale;
   auto kern = attn_bwd_sm100_kernel<NB, PACKED, MASKED>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {   // idempotent: a racing second call sets the same value
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
     if (e != cudaSuccess) {
       set_error("attention bwd: cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
       return VVAE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const long long tiles = PACKED ? p.tiles : (long long)p.n_outer * p.n_inner;
   dim3 grid((unsigned)tiles, (unsigned)p.heads);
@@ -1281,7 +1282,7 @@ static int atl_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   const long long n_seq = (long long)p.n_outer * p.n_inner;
   {
     const long long total = n_seq * p.L * 8 * p.heads;
-    const int blocks = (int)std::min<long long>(cdiv(total, 256), 148LL * 16);
+    const int blocks = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 16);
     attn_delta_kernel<<<blocks, 256, 0, s>>>((const bf16*)a.o, a.o_rs, (const bf16*)a.d_o, a.do_rs, a.delta, p, total);
     if ((rc = check_launch("attn_delta"))) return rc;
   }

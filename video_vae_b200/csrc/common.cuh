@@ -37,7 +37,7 @@ int check_launch(const char* what);  // cudaGetLastError -> status
   } while (0)
 
 inline cudaStream_t as_stream(vvae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
-inline int num_sms() { return 148; }
+int num_sms();  // cudaDevAttrMultiProcessorCount of the current device, queried once (api.cu); 148 on B200
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
 // ---- scalar conversion ----

@@ -125,7 +125,7 @@ static int conv_simt(const vvae_conv_args& a, int which, cudaStream_t s) {
   EpiStore<float, T> ep{a.dw_accum, a.Cout, nullptr, VVAE_EPI_NONE, nullptr, 0, nullptr, 0, 1};
   const long long Mp = (long long)taps * a.Cin;
   const long long tiles = cdiv(Mp, SG_BM) * cdiv(a.Cout, SG_BN);
-  int splits = (int)std::max<long long>(1, std::min<long long>((148LL * 8) / tiles, V / 512));
+  int splits = (int)std::max<long long>(1, std::min<long long>(((long long)num_sms() * 8) / tiles, V / 512));
   return launch_gemm_simt(Im2colTLoader<T>{Im2colLoader<T>{(const T*)a.x, g}}, RowMajorLoader<T>{(const T*)a.y, a.y_ld}, ep,
                           Mp, a.Cout, V, splits, s);
 }
@@ -249,7 +249,7 @@ int vvae_convT122_bwd(const void* dy, long long dy_ld, const void* x, const void
     }
     if (dw_accum) {
       const long long tiles = cdiv(Cin, SG_BM) * cdiv(4 * Cout, SG_BN);
-      int splits = (int)std::max<long long>(1, std::min<long long>((148LL * 8) / tiles, V / 512));
+      int splits = (int)std::max<long long>(1, std::min<long long>(((long long)num_sms() * 8) / tiles, V / 512));
       int rc = launch_gemm_simt(ColMajorLoader<T>{(const T*)x, Cin}, CTGatherBLoader<T>{gl}, CTWgradEpi{dw_accum, g}, Cin,
                                 4 * Cout, V, splits, s);
       if (rc) return rc;

@@ -482,7 +482,7 @@ int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
       configured.insert(kern);
     }
   }
-  const int grid = std::min(p.total_tiles, 148);
+  const int grid = std::min(p.total_tiles, num_sms());
   kern<<<grid, 192, p.smem_bytes, s>>>(tm, q);
   return check_launch("conv_sm100");
 }
@@ -505,7 +505,7 @@ int vvae_conv3d_wprep(const vvae_conv_args* a, int which, void* out, vvae_stream
   ConvPlan p;
   VVAE_REQUIRE(a->dtype == VVAE_BF16 && make_plan(*a, which, p), "conv3d_wprep: shape not supported by the tensor-core path");
   const long long total = (long long)p.nNT * p.kt * p.nCB * (p.w_stride / 2);
-  const int blocks = (int)std::min<long long>(cdiv(total, 256), 148 * 8);
+  const int blocks = (int)std::min<long long>(cdiv(total, 256), num_sms() * 8);
   conv_wprep_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const bf16*)a->w, (bf16*)out, p, which, a->Cin, a->Cout);
   return check_launch("conv_wprep");
 }

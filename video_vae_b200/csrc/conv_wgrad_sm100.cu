@@ -82,7 +82,7 @@ static bool wg_make_plan(const vvae_conv_args& a, WgPlan& p) {
   if (s < 2) return false;
   p.stages = std::min(s, 4);
   p.smem_bytes = (int)std::max<uint32_t>(p.stages * p.stage_stride + slack, 120u * 1024u);
-  p.ctas_per_group = (int)std::min<long long>(148 / p.ngroups, p.tiles);
+  p.ctas_per_group = (int)std::min<long long>(num_sms() / p.ngroups, p.tiles);
   return p.ctas_per_group >= 1;
 }
 

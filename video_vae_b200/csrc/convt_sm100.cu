@@ -83,7 +83,7 @@ static void split_ws(void* ws, int Cin, int Cout, bf16** wp, float** bias4, floa
 
 static int shuffle(bf16* dense, void* y, long long y_ld, int b_t, int H, int W, int Cout, int dir, cudaStream_t s) {
   const long long n_vec = (long long)b_t * H * W * 4 * (Cout / 8);
-  const int blocks = (int)std::min<long long>(cdiv(n_vec, 256), 148LL * 16);
+  const int blocks = (int)std::min<long long>(cdiv(n_vec, 256), (long long)num_sms() * 16);
   convt_shuffle_kernel<<<blocks, 256, 0, s>>>(dense, (bf16*)y, y_ld, n_vec, H, W, Cout, dir);
   return check_launch("convt_shuffle");
 }
@@ -92,7 +92,7 @@ int convt_tc_fwd(const void* x, const void* w, const float* bias, void* y, long 
                  int Cout, void* ws, cudaStream_t s) {
   bf16 *wp, *dense; float *bias4, *dwp;
   split_ws(ws, Cin, Cout, &wp, &bias4, &dwp, &dense);
-  convt_wprep_kernel<<<std::min(148, (Cin * 4 * Cout + 255) / 256), 256, 0, s>>>((const bf16*)w, bias, wp, bias4, Cin, Cout);
+  convt_wprep_kernel<<<std::min(num_sms(), (Cin * 4 * Cout + 255) / 256), 256, 0, s>>>((const bf16*)w, bias, wp, bias4, Cin, Cout);
   int rc = check_launch("convt_wprep");
   if (rc) return rc;
   vvae_gemm_args g = {};
@@ -109,7 +109,7 @@ int convt_tc_bwd(const void* dy, long long dy_ld, const void* x, const void* w, 
                  int W, int Cin, int Cout, void* ws, cudaStream_t s) {
   bf16 *wp, *dense; float *bias4, *dwp;
   split_ws(ws, Cin, Cout, &wp, &bias4, &dwp, &dense);
-  convt_wprep_kernel<<<std::min(148, (Cin * 4 * Cout + 255) / 256), 256, 0, s>>>((const bf16*)w, nullptr, wp, nullptr, Cin, Cout);
+  convt_wprep_kernel<<<std::min(num_sms(), (Cin * 4 * Cout + 255) / 256), 256, 0, s>>>((const bf16*)w, nullptr, wp, nullptr, Cin, Cout);
   int rc = check_launch("convt_wprep");
   if (rc) return rc;
   if ((rc = shuffle(dense, const_cast<void*>(dy), dy_ld, b_t, H, W, Cout, 1, s))) return rc;
@@ -132,7 +132,7 @@ int convt_tc_bwd(const void* dy, long long dy_ld, const void* x, const void* w, 
     g.C = dwp; g.ldc = 4 * Cout;
     g.dtype = VVAE_BF16; g.out_dtype = VVAE_F32; g.accumulate = 1; g.epilogue = VVAE_EPI_NONE;
     if ((rc = sm100_gemm(g, s))) return rc;
-    convt_dw_scatter_kernel<<<std::min(148, (Cin * 4 * Cout + 255) / 256), 256, 0, s>>>(dwp, dw_accum, Cin, Cout);
+    convt_dw_scatter_kernel<<<std::min(num_sms(), (Cin * 4 * Cout + 255) / 256), 256, 0, s>>>(dwp, dw_accum, Cin, Cout);
     if ((rc = check_launch("convt_dw_scatter"))) return rc;
   }
   return VVAE_OK;

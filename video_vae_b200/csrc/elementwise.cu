@@ -24,7 +24,8 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
-__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }  // (0,1)
+// 23 random bits: (k + 0.5) / 2^23 is exact in fp32 and strictly inside (0,1) (24 bits would round k = 2^24 - 1 up to 1.0)
+__device__ __forceinline__ float u01(uint32_t x) { return ((x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 __device__ __forceinline__ float normal_from(uint32_t a, uint32_t b) {
   float u1 = u01(a), u2 = u01(b);
   return sqrtf(-2.f * __logf(u1)) * __cosf(6.283185307179586f * u2);
@@ -265,7 +266,7 @@ __global__ void selection_fwd_kernel(const T* __restrict__ s1, const float* __re
     float z = lg;
     if (train) {
       float uu = u ? u[f] : u01(Philox(seed)(offset + (unsigned long long)f, 0x5e1ec7ull).x);
-      uu = fminf(fmaxf(uu, 1e-20f), 1.0f - 1e-20f);
+      uu = fminf(fmaxf(uu, 1e-20f), 1.0f - 5.9604645e-8f);   // largest fp32 below 1 (1 - 1e-20 rounds to 1.0f)
       z += __logf(uu / (1.f - uu));
     }
     float p = 1.f / (1.f + expf(-z / temperature));
@@ -538,7 +539,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-static inline int ew_blocks(long long n, int threads = 256) { return (int)std::min<long long>(cdiv(n, threads), 148LL * 16); }
+static inline int ew_blocks(long long n, int threads = 256) { return (int)std::min<long long>(cdiv(n, threads), (long long)num_sms() * 16); }
 
 }  // namespace vvae
 
@@ -683,7 +684,7 @@ int vvae_reparam_gate_bwd(const void* dc, const void* mean, const void* logvar, 
   VVAE_REQUIRE(Dl > 0 && Dl <= 1024 && n_tok % tok_per_frame == 0, "reparam_gate_bwd: bad extents");
   const int frames = (int)(n_tok / tok_per_frame);
   const int threads = Dl * std::max(1, 256 / Dl);
-  const int slabs = (int)std::max<long long>(1, std::min<long long>(tok_per_frame / (threads / Dl), (148LL * 4) / frames));
+  const int slabs = (int)std::max<long long>(1, std::min<long long>(tok_per_frame / (threads / Dl), ((long long)num_sms() * 4) / frames));
   VVAE_DISPATCH_DTYPE(dtype, T, (reparam_gate_bwd_kernel<T><<<frames * slabs, threads, 0, as_stream(stream)>>>(
                                     (const T*)dc, (const T*)mean, (const T*)logvar, eps, sel, fill, (const T*)dmean_in,
                                     (const T*)dlogvar_in, (T*)dmean, (T*)dlogvar, dfill, dsel, tok_per_frame, Dl, train,

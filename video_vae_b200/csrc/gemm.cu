@@ -74,7 +74,7 @@ static int gemm_simt_typed(const vvae_gemm_args& a, cudaStream_t s) {
   if (a.accumulate) {
     ep.atomic = 1;
     long long tiles = cdiv(a.M, SG_BM) * cdiv(a.N, SG_BN);
-    if (tiles < 148 * 2) splits = (int)std::max<long long>(1, std::min<long long>((148 * 4) / tiles, a.K / 256));
+    if (tiles < num_sms() * 2) splits = (int)std::max<long long>(1, std::min<long long>((num_sms() * 4) / tiles, a.K / 256));
   }
   const T* A = (const T*)a.A;
   const T* B = (const T*)a.B;

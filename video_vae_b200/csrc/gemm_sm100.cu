@@ -6,6 +6,7 @@
 // Both operands may be K-major (contraction index contiguous in memory) or MN-major (row/column index contiguous),
 // so forward (X . W, W is Flax (in,out) = MN-major B), dgrad (dY . W^T, K-major B) and wgrad (X^T . dY, both MN-major,
 // split-K with fp32 atomics) all read the tensors where they lie -- no transposed copies are ever materialised.
+#include <atomic>
 #include <cuda.h>
 
 #include <algorithm>
@@ -609,7 +610,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   p.m_tiles = (int)cdiv(a.M, BM * CG);
   p.n_tiles = (int)cdiv(a.N, BN);
   p.kb_total = (int)cdiv(a.K, BK);
-  const int n_clusters = 148 / CG;
+  const int n_clusters = num_sms() / CG;
   int splits = 1;
   const int tiles_mn = p.m_tiles * p.n_tiles;
   if (a.accumulate && tiles_mn < n_clusters) {  // weight gradients: few output tiles, very long K -> split K over the SMs
@@ -646,14 +647,14 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   if (g_dbg[5]) { if (!A_MN) p.a_sbo = (uint32_t)g_dbg[5]; if (!B_MN) p.b_sbo = (uint32_t)g_dbg[5]; }
 
   auto kern = gemm_sm100_kernel<BN, CG, A_MN, B_MN, MODE>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static std::atomic<bool> attr_set{false};  // per template instantiation
+  if (!attr_set.load(std::memory_order_acquire)) {   // idempotent: a racing second call sets the same value
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
       return VVAE_ERR_CUDA;
     }
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const int total = tiles_mn * p.splits;
   int clusters = std::min(total, g_dbg[0] ? (int)g_dbg[0] : n_clusters);

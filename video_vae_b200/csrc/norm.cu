@@ -919,7 +919,7 @@ static int resident_grid(K kern, int threads, size_t smem, long long max_useful)
     cudaGetLastError();
     occ = 2;
   }
-  return (int)std::max<long long>(1, std::min<long long>(max_useful, 148LL * occ));
+  return (int)std::max<long long>(1, std::min<long long>(max_useful, (long long)num_sms() * occ));
 }
 
 
@@ -1026,7 +1026,7 @@ int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, co
     return check_launch("qknorm_rope_fwd");
   }
   const long long nvec = rows * 2 * heads;
-  const int blocks = (int)std::min<long long>(cdiv(nvec, 8), 148LL * 16);
+  const int blocks = (int)std::min<long long>(cdiv(nvec, 8), (long long)num_sms() * 16);
   VVAE_DISPATCH_DTYPE(dtype, T, (qknorm_rope_fwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(
                                     (const T*)qkv, (T*)qk_out, q_scale, k_scale, (const T*)cos_tab, (const T*)sin_tab, rows,
                                     heads, hd, pos_div, pos_mod, eps)));
@@ -1051,7 +1051,7 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
     return check_launch("qknorm_rope_bwd");
   }
   const long long nvec = rows * 2 * heads;
-  const int blocks = (int)std::min<long long>(cdiv(nvec, 8), 148LL * 8);
+  const int blocks = (int)std::min<long long>(cdiv(nvec, 8), (long long)num_sms() * 8);
   VVAE_DISPATCH_DTYPE(dtype, T, (qknorm_rope_bwd_kernel<T><<<blocks, 256, 0, as_stream(stream)>>>(
                                     (T*)dqkv, (const T*)qkv, q_scale, k_scale, (const T*)cos_tab, (const T*)sin_tab, dq_scale,
                                     dk_scale, rows, heads, hd, pos_div, pos_mod, eps)));
@@ -1069,13 +1069,13 @@ int vvae_groupnorm_silu_fwd(const void* x, void* y, long long y_ld, const float*
   VVAE_REQUIRE(C > 0 && C <= 256 && G > 0 && G <= 64 && C % G == 0, "groupnorm_silu_fwd: bad C=%d G=%d", C, G);
   cudaStream_t s = as_stream(stream);
   const int threads = gn_threads(C);
-  const long long rpb = std::max<long long>(threads / C, cdiv(S, std::max<long long>(1, (148LL * 8) / B)));
+  const long long rpb = std::max<long long>(threads / C, cdiv(S, std::max<long long>(1, ((long long)num_sms() * 8) / B)));
   dim3 grid((unsigned)cdiv(S, rpb), (unsigned)B);
   int rc = vvae_fill_f32(stats, 0.f, (long long)B * G * 2, stream);
   if (rc) return rc;
   if (gn_vec_ok(dtype, C, x, C, y, y_ld)) {
     const int rpi = 256 / (C / 8);
-    const long long vrpb = std::max<long long>(2 * rpi, cdiv(S, std::max<long long>(1, (148LL * 8) / B)));
+    const long long vrpb = std::max<long long>(2 * rpi, cdiv(S, std::max<long long>(1, ((long long)num_sms() * 8) / B)));
     dim3 vgrid((unsigned)cdiv(S, vrpb), (unsigned)B);
     gn_stats_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)x, stats, S, C, G, vrpb);
     groupnorm_finalize_kernel<<<(int)cdiv(B * G, 128), 128, 0, s>>>(stats, mean, rstd, B * G,
@@ -1099,13 +1099,13 @@ int vvae_groupnorm_silu_bwd(const void* dy, long long dy_ld, const void* x, cons
   VVAE_REQUIRE(C > 0 && C <= 256 && G > 0 && G <= 64 && C % G == 0, "groupnorm_silu_bwd: bad C=%d G=%d", C, G);
   cudaStream_t s = as_stream(stream);
   const int threads = gn_threads(C);
-  const long long rpb = std::max<long long>(threads / C, cdiv(S, std::max<long long>(1, (148LL * 8) / B)));
+  const long long rpb = std::max<long long>(threads / C, cdiv(S, std::max<long long>(1, ((long long)num_sms() * 8) / B)));
   dim3 grid((unsigned)cdiv(S, rpb), (unsigned)B);
   int rc = vvae_fill_f32(stats, 0.f, (long long)B * G * 2, stream);
   if (rc) return rc;
   if (gn_vec_ok(dtype, C, dy, dy_ld, x, C) && ((uintptr_t)dx % 16 == 0)) {
     const int rpi = 256 / (C / 8);
-    const long long vrpb = std::max<long long>(2 * rpi, cdiv(S, std::max<long long>(1, (148LL * 8) / B)));
+    const long long vrpb = std::max<long long>(2 * rpi, cdiv(S, std::max<long long>(1, ((long long)num_sms() * 8) / B)));
     dim3 vgrid((unsigned)cdiv(S, vrpb), (unsigned)B);
     gn_bwd_stats_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
                                                   dgamma, dbeta, S, C, G, vrpb);

@@ -128,7 +128,7 @@ int small_linear_fwd(const SmallLinArgs& a, cudaStream_t s) {
   const int xvec = (a.K % 4 == 0 && a.x_ld % 4 == 0 && al8(a.x)) ? 1 : 0;
   const int yvec = (a.N % 4 == 0 && a.y_ld % 4 == 0 && al8(a.y)) ? 1 : 0;
   const int avec = (a.aux && a.N % 4 == 0 && a.aux_ld % 4 == 0 && al8(a.aux)) ? 1 : 0;
-  const int blocks = (int)std::min<long long>(cdiv(a.M, 256), 148LL * 8);
+  const int blocks = (int)std::min<long long>(cdiv(a.M, 256), (long long)num_sms() * 8);
   const int kp = pad4(a.K), np = pad4(a.N);
 #define SL_FWD(KP, NP) small_linear_fwd_kernel<KP, NP><<<blocks, 256, 0, s>>>(a, xvec, yvec, avec)
   if (kp == 4 && np == 4) SL_FWD(4, 4);
@@ -150,7 +150,7 @@ int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long 
                        long long M, int K, int N, cudaStream_t s) {
   const int xvec = (K % 4 == 0 && x_ld % 4 == 0 && al8(x)) ? 1 : 0;
   const int dvec = (N % 4 == 0 && dy_ld % 4 == 0 && al8(dy)) ? 1 : 0;
-  const int blocks = (int)std::min<long long>(cdiv(M, 256), 148LL * 4);
+  const int blocks = (int)std::min<long long>(cdiv(M, 256), (long long)num_sms() * 4);
   const int kp = pad4(K), np = pad4(N);
 #define SL_WG(KP, NP) small_linear_wgrad_kernel<KP, NP><<<blocks, 256, 0, s>>>(x, x_ld, dy, dy_ld, dw, dk, dn, M, K, N, xvec, dvec)
   if (kp == 4 && np == 4) SL_WG(4, 4);
@@ -261,19 +261,19 @@ bool rank1_ok(int K) { return K >= 8 && K <= 256 && K % 8 == 0; }
 
 int rank1_fwd(const bf16* x, long long x_ld, const bf16* w, long long w_st, const float* bias, bf16* y, long long y_ld,
               long long M, int K, cudaStream_t s) {
-  const int blocks = (int)std::min<long long>(cdiv(M * 8, 256), 148LL * 8);
+  const int blocks = (int)std::min<long long>(cdiv(M * 8, 256), (long long)num_sms() * 8);
   rank1_fwd_kernel<<<blocks, 256, 0, s>>>(x, x_ld, w, w_st, bias, y, y_ld, M, K);
   return check_launch("rank1_fwd");
 }
 int rank1_dgrad(const bf16* dy, long long dy_ld, const bf16* w, long long w_st, const bf16* aux, long long aux_ld, bf16* dx,
                 long long dx_ld, long long M, int K, cudaStream_t s) {
-  const int blocks = (int)std::min<long long>(cdiv(M * (K / 8), 256), 148LL * 8);
+  const int blocks = (int)std::min<long long>(cdiv(M * (K / 8), 256), (long long)num_sms() * 8);
   rank1_dgrad_kernel<<<blocks, 256, 0, s>>>(dy, dy_ld, w, w_st, aux, aux_ld, dx, dx_ld, M, K);
   return check_launch("rank1_dgrad");
 }
 int rank1_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dw_st, long long M, int K,
                 cudaStream_t s) {
-  const int blocks = (int)std::min<long long>(cdiv(M, 8 * 16), 148LL * 4);
+  const int blocks = (int)std::min<long long>(cdiv(M, 8 * 16), (long long)num_sms() * 4);
   rank1_wgrad_kernel<<<blocks, 256, 0, s>>>(x, x_ld, dy, dy_ld, dw, dw_st, M, K);
   return check_launch("rank1_wgrad");
 }

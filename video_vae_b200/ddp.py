@@ -76,7 +76,7 @@ class FlatParams:
         self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=self.flat.device)
         for p, o in zip(self.params, self.offsets):
             self._shadow_views[id(p)] = (weakref.ref(p), self.shadow[o:o + p.numel()].view(p.shape))
-        F_._flat_shadow_views = self._shadow_views
+        F_._flat_shadow_views.update(self._shadow_views)     # merge: several FlatParams may live in one process
         self.refresh_shadow()
 
     def refresh_shadow(self):
@@ -86,10 +86,17 @@ class FlatParams:
 
 
 class GradAllReducer:
-    """Bucketed, backward-overlapped all-reduce (sum) of FlatParams.grad."""
+    """Bucketed, backward-overlapped all-reduce (sum) of FlatParams.grad.
 
-    def __init__(self, flat: FlatParams, bucket_bytes=64 << 20, process_group=None):
+    A bucket is launched when every one of its parameters has reported ``uses`` times (default 1: each parameter is
+    produced by exactly one backward Function per step, as in VideoVAE).  With weight sharing, a module called twice
+    or micro-batch accumulation pass ``uses_per_step`` (a dict id(param) -> count, or an int for all) -- or call
+    ``defer()`` to launch every bucket from ``finish_step`` only."""
+
+    def __init__(self, flat: FlatParams, bucket_bytes=64 << 20, process_group=None, uses_per_step=1):
         self.flat = flat
+        self.uses_per_step = uses_per_step
+        self._deferred = False
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.stream = torch.cuda.Stream() if flat.flat.is_cuda else None
@@ -110,19 +117,30 @@ class GradAllReducer:
         self.launch_order = []
         F_._grad_hooks.append(self._on_grads_ready)
 
+    def defer(self, on=True):
+        """Launch nothing during backward; ``finish_step`` reduces every bucket (safe for any gradient-use pattern)."""
+        self._deferred = on
+
+    def _uses(self, p):
+        u = self.uses_per_step
+        return u.get(id(p), 1) if isinstance(u, dict) else int(u)
+
     def start_step(self):
         self._pending = [n for (_, _, n) in self.buckets]
-        self._seen = set()
+        self._seen = {}
         self._handles = []
         self.launch_order = []
 
     def _on_grads_ready(self, params):
-        if self._pending is None or self.world == 1:
+        if self._pending is None or self.world == 1 or self._deferred:
             return
         for p in params:
-            if p is None or id(p) in self._seen or id(p) not in self.bucket_of:
+            if p is None or id(p) not in self.bucket_of:
                 continue
-            self._seen.add(id(p))
+            n = self._seen.get(id(p), 0) + 1
+            self._seen[id(p)] = n
+            if n != self._uses(p):        # not yet its last use this step (or an unexpected extra one: see finish_step)
+                continue
             b = self.bucket_of[id(p)]
             self._pending[b] -= 1
             if self._pending[b] == 0:
@@ -144,6 +162,10 @@ class GradAllReducer:
         """Flush buckets that never filled (unused parameters) and join the communication stream."""
         if self.world == 1 or self._pending is None:
             return
+        extra = [k for k, n in self._seen.items() if not self._deferred and n > self._uses_by_id(k)]
+        if extra:
+            raise RuntimeError(f"{len(extra)} parameter(s) received gradient more often than uses_per_step allows: their "
+                               "bucket was all-reduced before the last accumulation (pass uses_per_step or call defer())")
         for b, n in enumerate(self._pending):
             if n > 0:
                 self._pending[b] = 0
@@ -153,6 +175,16 @@ class GradAllReducer:
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
         self._pending = None
+
+    def _uses_by_id(self, pid):
+        u = self.uses_per_step
+        return u.get(pid, 1) if isinstance(u, dict) else int(u)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def close(self):
         if self._on_grads_ready in F_._grad_hooks:

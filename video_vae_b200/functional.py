@@ -56,7 +56,10 @@ def invalidate_shadows():
 
 
 def params_changed():
-    """Called by the fused optimizer after it rewrote the flat parameter buffer in place."""
+    """Called by the fused optimizer after it rewrote the flat parameter buffer in place.  The kernels write through raw
+    pointers, so ``p._version`` does not move: per-parameter shadow copies made by ``shadow()`` (parameters outside any
+    flat bf16 shadow) must be dropped as well, or they would keep serving the pre-update weights."""
+    _shadow_cache.clear()
     _param_epoch[0] += 1
 
 
