@@ -42,6 +42,17 @@ struct ConvPlan {
   int stages, smem_bytes;
   int hblocks, wblocks, total_tiles;
   int pack, BS;     // pack: horizontal taps in N; BS: plane positions per 128-row MMA block that produce outputs
+  int w_res;        // the whole weight image stays in shared memory (loaded once per CTA) instead of riding along with
+                    // every stage: with ~37k tiles x 3 stages, all 148 SMs re-fetching the same 14 KB hammered a few L2
+                    // slices -- the barrier/weight skeleton alone took 0.21 of 0.34 ms (profiles/r02g_conv_ablate.jsonl)
+  uint32_t w_total; // bytes of the weight image (nNT * kt * nCB stage slots of w_stride)
+  int sub;          // input slabs (dt, cb) per pipeline stage: 1, or all kt*nCB of a tile behind ONE barrier handshake
+                    // (the single-thread producer / issuer loops cost ~450 cycles per handshake: ablation r02h)
+  uint32_t stage_stride;   // bytes between stages of the input ring = sub * a_stride
+  // slide: a CTA walks one spatial tile through Tc consecutive frames and keeps the zero-padded input slabs of frames
+  // t-1, t, t+1 in the ring, so every frame slab is fetched ONCE per tile column instead of once per temporal tap
+  // (3x less L2 -> smem traffic: the TMA-only ablation ran at 6.6 TB/s of L2 reads, profiles/r02i_conv_ablate.jsonl)
+  int slide, Tc, tchunks, units;
 };
 
 struct ConvParams {
@@ -51,6 +62,8 @@ struct ConvParams {
   const float* bias;
   int mode; const bf16* aux; long long ld_aux;
   int store_c;  // channels written per voxel: Cout, or ceil16(Cout) when the caller asked for zeroed pad channels
+  int dbg;      // vvae_debug_set(14): timing ablations (results are WRONG): 1 no global stores, 2 epilogue releases the
+                // accumulator at once, 4 no input-tile TMA, 8 no MMAs
 };
 
 static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
@@ -58,8 +71,11 @@ static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a
 extern long long g_dbg[16];   // vvae_debug_set: key 13 != 0 selects the one-MMA-per-tap kernels (round-1 behaviour)
 constexpr int CONV_THREADS = 320;        // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5 / 6-9: two epilogue groups
 constexpr uint32_t CONV_MISC_BYTES = 1024;   // barriers (256 B) + the layer's bias as fp32 (<= 128 values) behind the stages
-// epilogue row exchange (PACK): [group 2][buffer 2][quarter 4][kw-1 rows][kw-1 taps][16 channels] fp32
-static inline uint32_t conv_xch_bytes(int kw, int pack) { return pack ? 2u * 2u * 4u * (kw - 1) * (kw - 1) * 16u * 4u : 0u; }
+// epilogue row exchange (PACK): [group 2][buffer 2][quarter 4][block][kw-1 rows][kw-1 taps][16 channels] fp32
+// (blocks per epilogue pass: both blocks of a tile for 3-wide filters, one for wider ones -- EB in the kernel; NBLK <= 2)
+static inline uint32_t conv_xch_bytes(int kw, int pack) {
+  return pack ? 2u * 2u * 4u * (kw <= 3 ? 2u : 1u) * (kw - 1) * (kw - 1) * 16u * 4u : 0u;
+}
 
 // which: 0 = forward (gathers x, Cin -> Cout), 1 = dgrad (gathers dy, Cout -> Cin)
 static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
@@ -86,11 +102,13 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   // Short, wide tiles (R = 1) re-read every input row kh times; choose the (nblk, R, Ct) that minimises
   // halo traffic + padded MMA work per useful output, including the ragged right / bottom edges of the image.
   {
-    const int max_nblk = (a.kh == 7 ? 2 : 2);
+    const int max_nblk = (p.pack && g_dbg[15] != 4) ? 4 : 2;   // 4 blocks: four independent accumulator chains (see kernel)
     double best = 1e30;
     int bR = 0, bC = 0;
     for (int nb = 1; nb <= max_nblk; ++nb) {
+      if (nb == 3) continue;                         // kernel instances exist for 1, 2 and 4 blocks
       if (nb * acc_cols_per_blk > 256) break;
+      if (nb == 4 && p.NT != 16) break;
       for (int R = 1; R <= std::min(a.H, 32); ++R) {
         int cmax = (p.BS * nb - (R - 1) * (a.kw - 1)) / R;
         cmax = std::min(cmax, std::min(a.W, 256 - (a.kw - 1)));
@@ -126,12 +144,31 @@ static bool make_plan(const vvae_conv_args& a, int which, ConvPlan& p) {
   p.w_stride = align_up(p.w_bytes, 1024);
   // alignment + over-read of pad rows + barriers / bias + exchange
   const uint32_t slack = 1024 + 128u * 128u + CONV_MISC_BYTES + conv_xch_bytes(a.kw, p.pack);
-  const uint32_t per_stage = p.a_stride + p.w_stride;
-  int s = (int)((225u * 1024u - slack) / per_stage);
+  p.w_total = (uint32_t)(p.nNT * a.kt * p.nCB) * p.w_stride;
+  p.w_res = (g_dbg[15] == 0 && p.nNT == 1 && p.w_total <= 112u * 1024u && p.w_total + 3 * p.a_stride + slack <= 225u * 1024u) ? 1 : 0;
+  const uint32_t fixed = slack + (p.w_res ? p.w_total : 0u);
+  p.sub = 1;
+  if (p.w_res && g_dbg[15] != 2 && (225u * 1024u - fixed) / ((uint32_t)(a.kt * p.nCB) * p.a_stride) >= 3) p.sub = a.kt * p.nCB;
+  p.slide = 0; p.Tc = a.T; p.tchunks = 1; p.units = 0;
+  if (p.w_res && a.kt == 3 && g_dbg[15] != 2 && g_dbg[15] != 3 && (225u * 1024u - fixed) / ((uint32_t)p.nCB * p.a_stride) >= 4) {
+    p.slide = 1;
+    p.sub = p.nCB;                    // a ring slot = one frame slab = all channel blocks of that frame
+    const long long spatial = (long long)a.B * ((a.H + p.R - 1) / p.R) * ((a.W + p.Ct - 1) / p.Ct);
+    // time chunks: long enough to amortise the two extra slabs per chunk, short enough for >= ~3 units per SM
+    p.Tc = a.T;
+    while (p.Tc > 4 && spatial * ((a.T + p.Tc - 1) / p.Tc) < 3LL * num_sms()) p.Tc = (p.Tc + 1) / 2;
+    p.tchunks = (a.T + p.Tc - 1) / p.Tc;
+    if (spatial * p.tchunks > 0x7fffffffLL) return false;
+    p.units = (int)(spatial * p.tchunks);
+  }
+  p.stage_stride = (uint32_t)p.sub * p.a_stride;
+  const uint32_t per_stage = p.stage_stride + (p.w_res ? 0u : p.w_stride);
+  int s = (int)((225u * 1024u - fixed) / per_stage);
   if (s < 2) return false;
-  p.stages = std::min(s, 6);
-  p.smem_bytes = (int)std::max<uint32_t>(p.stages * per_stage + slack, 120u * 1024u);  // >= 120 KB: one CTA per SM (TMEM)
-  if (p.nblk > 2) return false;
+  p.stages = std::min(s, p.slide ? 8 : (p.sub > 1 ? 6 : (p.w_res ? 8 : 6)));
+  p.smem_bytes = (int)std::max<uint32_t>(p.stages * per_stage + fixed, 120u * 1024u);  // >= 120 KB: one CTA per SM (TMEM)
+  if (p.nblk > 4 || p.nblk == 3) p.nblk = p.nblk == 3 ? 4 : 99;   // instances exist for 1, 2 and 4 blocks
+  if (p.nblk > 4 || p.nblk * acc_cols_per_blk > 256) return false;
   p.hblocks = (a.H + p.R - 1) / p.R;
   p.wblocks = (a.W + p.Ct - 1) / p.Ct;
   const long long tiles = (long long)a.B * a.T * p.hblocks * p.wblocks * p.nNT;
@@ -261,6 +298,46 @@ __device__ __forceinline__ void conv_store16(const ConvParams& q, long long pix,
   }
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
+// Walks the tile sequence blockIdx.x, blockIdx.x + gridDim.x, ... in mixed radix (nt, wb, hb, t, b) without a division
+// per tile (five runtime div/mod pairs per tile were ~500 cycles of the single-thread producer loop).
+struct ConvTileIter {
+  int nt, wb, hb, t, b;
+  int s_nt, s_wb, s_hb, s_t, s_b;
+  __device__ __forceinline__ void init(const ConvPlan& p, int tile0, int step) {
+    int r = tile0;
+    nt = r % p.nNT; r /= p.nNT;  wb = r % p.wblocks; r /= p.wblocks;  hb = r % p.hblocks; r /= p.hblocks;  t = r % p.T;  b = r / p.T;
+    r = step;
+    s_nt = r % p.nNT; r /= p.nNT;  s_wb = r % p.wblocks; r /= p.wblocks;  s_hb = r % p.hblocks; r /= p.hblocks;  s_t = r % p.T;  s_b = r / p.T;
+  }
+  __device__ __forceinline__ void advance(const ConvPlan& p) {
+    nt += s_nt;  int c = nt >= p.nNT;      nt -= c ? p.nNT : 0;
+    wb += s_wb + c;  c = wb >= p.wblocks;  wb -= c ? p.wblocks : 0;
+    hb += s_hb + c;  c = hb >= p.hblocks;  hb -= c ? p.hblocks : 0;
+    t += s_t + c;    c = t >= p.T;         t -= c ? p.T : 0;
+    b += s_b + c;
+  }
+};
+
+// slide mode: unit u -> (wb, hb, time chunk, b); one division chain per unit (= per Tc tiles)
+struct ConvUnit {
+  int wb, hb, b, t0, nf;
+  __device__ __forceinline__ void decode(const ConvPlan& p, int u) {
+    wb = u % p.wblocks; u /= p.wblocks;
+    hb = u % p.hblocks; u /= p.hblocks;
+    const int tc = u % p.tchunks;
+    b = u / p.tchunks;
+    t0 = tc * p.Tc;
+    nf = min(p.Tc, p.T - t0);
+  }
+};
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -282,14 +359,16 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
   uint8_t* smem_a = smem;
-  uint8_t* smem_w = smem + (size_t)S * p.a_stride;
-  // barriers live after the weight stages plus the over-read slack
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * (p.a_stride + p.w_stride) + 128 * 128);
+  uint8_t* smem_w = smem + (size_t)S * p.stage_stride;   // per-stage weight slots, or the resident weight image
+  // barriers live after the weights plus the over-read slack
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * p.stage_stride +
+                                               (p.w_res ? (size_t)p.w_total : (size_t)S * p.w_stride) + 128 * 128);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + 8;
   uint64_t* tmem_full = bars + 16;
   uint64_t* tmem_empty = bars + 18;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* w_bar = bars + 22;                                         // resident weights have landed
   float* s_bias = reinterpret_cast<float*>(bars + 32);                 // [nNT * NT] fp32 (zeros without a bias)
   float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + CONV_MISC_BYTES);   // PACK epilogue only
   constexpr int ROWBYTES = NKS * 32;
@@ -310,8 +389,9 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
-      sm100::mbar_init(&tmem_empty[i], 4);
+      sm100::mbar_init(&tmem_empty[i], NBLK >= 2 ? 8 : 4);   // warps that drain one accumulator (SPLIT: both groups)
     }
+    sm100::mbar_init(w_bar, 1);
     sm100::fence_barrier_init();
   }
   for (int i = threadIdx.x; i < p.nNT * NT; i += blockDim.x) s_bias[i] = (q.bias && i < p.Cout) ? __ldg(q.bias + i) : 0.f;
@@ -320,32 +400,59 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int stages_per_tile = p.kt * p.nCB;
+  const int slabs_per_tile = p.kt * p.nCB;
+  const int stages_per_tile = slabs_per_tile / p.sub;
 
   if (warp == 0) {
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int rest = tile;
-        const int nt = rest % p.nNT; rest /= p.nNT;
-        const int wb = rest % p.wblocks; rest /= p.wblocks;
-        const int hb = rest % p.hblocks; rest /= p.hblocks;
-        const int t = rest % p.T;
-        const int b = rest / p.T;
-        const int w0 = wb * p.Ct - KW / 2, h0 = hb * p.R - KH / 2;
-        for (int dt = 0; dt < p.kt; ++dt) {
-          for (int cb = 0; cb < p.nCB; ++cb) {
-            sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
-            sm100::mbar_expect_tx(&full_bar[stage], p.a_bytes + p.w_bytes);
-            sm100::tma_load_5d(smem_a + (size_t)stage * p.a_stride, &tma_x, &full_bar[stage], cb * p.CB, w0, h0,
-                               t + dt - p.kt / 2, b);
-            bulk_g2s(smem_w + (size_t)stage * p.w_stride,
-                     reinterpret_cast<const uint8_t*>(q.wimg) + ((size_t)(nt * p.kt + dt) * p.nCB + cb) * p.w_stride,
-                     p.w_bytes, &full_bar[stage]);
-            if (++stage == S) { stage = 0; phase ^= 1; }
+      if (p.w_res) {     // the whole weight image, once (bulk copies of <= 32 KB each)
+        sm100::mbar_expect_tx(w_bar, p.w_total);
+        for (uint32_t off = 0; off < p.w_total; off += 32768u)
+          bulk_g2s(smem_w + off, reinterpret_cast<const uint8_t*>(q.wimg) + off, min(32768u, p.w_total - off), w_bar);
+      }
+      const uint32_t tx_bytes = ((q.dbg & 4) ? 0u : (uint32_t)p.sub * p.a_bytes) + (p.w_res ? 0u : p.w_bytes);
+      if (p.slide) {
+        uint32_t sq = 0;                                     // slab sequence number of this CTA: slot sq % S, phase (sq / S) & 1
+        int slot = 0;
+        uint32_t ph = 0;
+        for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+          ConvUnit cu;
+          cu.decode(p, u);
+          const int w0 = cu.wb * p.Ct - KW / 2, h0 = cu.hb * p.R - KH / 2;
+          for (int f = -1; f <= cu.nf; ++f, ++sq) {          // frames t0-1 .. t0+nf (out-of-range frames: TMA zero fill)
+            sm100::mbar_wait(&empty_bar[slot], ph ^ 1);
+            sm100::mbar_expect_tx(&full_bar[slot], tx_bytes);
+            if (!(q.dbg & 4))
+              for (int cb = 0; cb < p.nCB; ++cb)
+                sm100::tma_load_5d(smem_a + (size_t)slot * p.stage_stride + (size_t)cb * p.a_stride, &tma_x, &full_bar[slot],
+                                   cb * p.CB, w0, h0, cu.t0 + f, cu.b);
+            if (++slot == S) { slot = 0; ph ^= 1; }
           }
         }
+      } else {
+      int stage = 0;
+      uint32_t phase = 0;
+      ConvTileIter it;
+      it.init(p, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, it.advance(p)) {
+        const int w0 = it.wb * p.Ct - KW / 2, h0 = it.hb * p.R - KH / 2;
+        int dt = 0, cb = 0;
+        for (int s = 0; s < stages_per_tile; ++s) {
+          sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
+          sm100::mbar_expect_tx(&full_bar[stage], tx_bytes);
+          for (int u = 0; u < p.sub; ++u) {
+            if (!(q.dbg & 4))
+              sm100::tma_load_5d(smem_a + (size_t)stage * p.stage_stride + (size_t)u * p.a_stride, &tma_x, &full_bar[stage],
+                                 cb * p.CB, w0, h0, it.t + dt - p.kt / 2, it.b);
+            if (!p.w_res)   // (sub == 1)
+              bulk_g2s(smem_w + (size_t)stage * p.w_stride,
+                       reinterpret_cast<const uint8_t*>(q.wimg) + ((size_t)(it.nt * p.kt + dt) * p.nCB + cb) * p.w_stride,
+                       p.w_bytes, &full_bar[stage]);
+            if (++cb == p.nCB) { cb = 0; ++dt; }
+          }
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
       }
     }
   } else if (warp == 1) {
@@ -357,12 +464,92 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
     constexpr uint32_t desc_hi = ((8u * ROWBYTES) >> 4) | (1u << 14) | (LAYOUT << 29);
     constexpr uint32_t lo_flags = 1u << 16;                              // LBO field (unused for swizzled K-major)
     const uint32_t a_row_step = (uint32_t)p.P * RB16;
-    const uint32_t a_stride16 = p.a_stride >> 4, w_stride16 = p.w_stride >> 4;
+    const uint32_t a_stride16 = p.a_stride >> 4, w_stride16 = p.w_stride >> 4, stage_stride16 = p.stage_stride >> 4;
     const uint32_t a_base16 = sm100::smem_u32(smem_a) >> 4, w_base16 = sm100::smem_u32(smem_w) >> 4;
-    int stage = 0;
-    uint32_t phase = 0;
+    // all MMAs of one input slab (one frame, one channel block): every filter row / k-slice / block, taps packed in N
+    auto issue_slab = [&](uint32_t d_base, uint32_t a_lo0, uint32_t w_lo0, uint32_t accumulate_first) {
+#pragma unroll
+      for (int dh = 0; dh < KH; ++dh) {
+        const uint32_t a_row = a_lo0 + dh * a_row_step;
+        if constexpr (PACK) {
+          // one MMA per (dh, k-slice, block): the B operand spans the KW taps of filter row dh (KW*NT rows of the
+          // weight image, contiguous), the A operand is NOT shifted by dw -- the epilogue applies the shift
+#pragma unroll
+          for (int ks = 0; ks < NKS; ++ks) {
+            const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW) * NT * RB16 + 2u * ks);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+              const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + 2u * ks + blk * (uint32_t)BS * RB16);
+              if (dh == 0 && ks == 0)
+                sm100::umma_f16(d_base + blk * NW, da, db, idesc, accumulate_first);
+              else
+                sm100::umma_f16_acc(d_base + blk * NW, da, db, idesc);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int dw = 0; dw < KW; ++dw) {
+#pragma unroll
+            for (int ks = 0; ks < NKS; ++ks) {
+              const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW + dw) * NT * RB16 + 2u * ks);
+#pragma unroll
+              for (int blk = 0; blk < NBLK; ++blk) {
+                const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + dw * RB16 + 2u * ks + blk * 128u * RB16);
+                if (dh == 0 && dw == 0 && ks == 0)
+                  sm100::umma_f16(d_base + blk * NT, da, db, idesc, accumulate_first);
+                else
+                  sm100::umma_f16_acc(d_base + blk * NT, da, db, idesc);
+              }
+            }
+          }
+        }
+      }
+    };
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.w_res) sm100::mbar_wait(w_bar, 0);
+    if (p.slide) {
+      // output frame t0+ot reads the slabs of frames t0+ot-1, t0+ot, t0+ot+1 = sequence numbers sq+ot .. sq+ot+2
+      uint32_t sq = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        ConvUnit cu;
+        cu.decode(p, u);
+        for (int ot = 0; ot < cu.nf; ++ot) {
+          sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+          const uint32_t d_base = tmem_base + acc * ACC_COLS;
+          uint32_t slots[3];
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt) {
+            const uint32_t sn = sq + ot + dt;
+            slots[dt] = sn % (uint32_t)S;
+            if (ot == 0 || dt == 2) sm100::mbar_wait(&full_bar[slots[dt]], (sn / (uint32_t)S) & 1u);   // older slabs: waited before
+          }
+          sm100::tc_fence_after();
+          if (elect_one()) {
+            if (!(q.dbg & 8)) {
+#pragma unroll
+              for (int dt = 0; dt < 3; ++dt)
+                for (int cb = 0; cb < p.nCB; ++cb) {
+                  const uint32_t a_lo0 = ((a_base16 + slots[dt] * stage_stride16 + cb * a_stride16) & 0x3FFFu) | lo_flags;
+                  const uint32_t w_lo0 = ((w_base16 + (dt * p.nCB + cb) * w_stride16) & 0x3FFFu) | lo_flags;
+                  issue_slab(d_base, a_lo0, w_lo0, (dt > 0 || cb > 0) ? 1u : 0u);
+                }
+            }
+            sm100::umma_commit(&empty_bar[slots[0]]);        // frame t0+ot-1 is not needed again
+            if (ot == cu.nf - 1) {                            // end of the chunk: the last two slabs as well
+              sm100::umma_commit(&empty_bar[slots[1]]);
+              sm100::umma_commit(&empty_bar[slots[2]]);
+            }
+            sm100::umma_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        sq += (uint32_t)cu.nf + 2u;
+      }
+    } else {
+    int stage = 0;
+    uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       sm100::tc_fence_after();
@@ -371,42 +558,12 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
         sm100::mbar_wait(&full_bar[stage], phase);
         sm100::tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_lo0 = ((a_base16 + stage * a_stride16) & 0x3FFFu) | lo_flags;
-          const uint32_t w_lo0 = ((w_base16 + stage * w_stride16) & 0x3FFFu) | lo_flags;
-#pragma unroll
-          for (int dh = 0; dh < KH; ++dh) {
-            const uint32_t a_row = a_lo0 + dh * a_row_step;
-            if constexpr (PACK) {
-              // one MMA per (dh, k-slice, block): the B operand spans the KW taps of filter row dh (KW*NT rows of the
-              // weight image, contiguous), the A operand is NOT shifted by dw -- the epilogue applies the shift
-#pragma unroll
-              for (int ks = 0; ks < NKS; ++ks) {
-                const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW) * NT * RB16 + 2u * ks);
-#pragma unroll
-                for (int blk = 0; blk < NBLK; ++blk) {
-                  const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + 2u * ks + blk * (uint32_t)BS * RB16);
-                  if (dh == 0 && ks == 0)
-                    sm100::umma_f16(d_base + blk * NW, da, db, idesc, s > 0 ? 1u : 0u);
-                  else
-                    sm100::umma_f16_acc(d_base + blk * NW, da, db, idesc);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int dw = 0; dw < KW; ++dw) {
-#pragma unroll
-                for (int ks = 0; ks < NKS; ++ks) {
-                  const uint64_t db = ((uint64_t)desc_hi << 32) | (uint64_t)(w_lo0 + (dh * KW + dw) * NT * RB16 + 2u * ks);
-#pragma unroll
-                  for (int blk = 0; blk < NBLK; ++blk) {
-                    const uint64_t da = ((uint64_t)desc_hi << 32) | (uint64_t)(a_row + dw * RB16 + 2u * ks + blk * 128u * RB16);
-                    if (dh == 0 && dw == 0 && ks == 0)
-                      sm100::umma_f16(d_base + blk * NT, da, db, idesc, s > 0 ? 1u : 0u);
-                    else
-                      sm100::umma_f16_acc(d_base + blk * NT, da, db, idesc);
-                  }
-                }
-              }
+          if (!(q.dbg & 8)) {
+            for (int u = 0; u < p.sub; ++u) {
+              const int slab = s * p.sub + u;                 // (dt, cb) index inside the tile
+              const uint32_t a_lo0 = ((a_base16 + stage * stage_stride16 + u * a_stride16) & 0x3FFFu) | lo_flags;
+              const uint32_t w_lo0 = ((w_base16 + (p.w_res ? slab : stage) * w_stride16) & 0x3FFFu) | lo_flags;
+              issue_slab(d_base, a_lo0, w_lo0, slab > 0 ? 1u : 0u);
             }
           }
           sm100::umma_commit(&empty_bar[stage]);
@@ -417,101 +574,143 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }
   } else {
-    // ===================== epilogue: two groups of four warps; group g drains accumulator g (every other tile) ==========
+    // ===================== epilogue: two groups of four warps =====================
+    // NBLK == 1: group g drains accumulator g (every other tile).  NBLK >= 2 (SPLIT): both groups work on EVERY tile,
+    // group g drains blocks [g*NBLK/2, (g+1)*NBLK/2) -- the epilogue is a latency chain, two groups halve it per tile.
+    constexpr bool SPLIT = NBLK >= 2;
+    constexpr int GB = SPLIT ? NBLK / 2 : NBLK;              // blocks per group and tile
     const int eg = (warp - 2) >> 2;
+    const int gb0 = SPLIT ? eg * GB : 0;
     const int quarter = warp & 3;
     const int mp = quarter * 32 + lane;                      // row of the 128-row MMA block = TMEM lane
     // row -> (image row, column) of the tile, per block; the same for every tile
-    int row_r[NBLK], row_c[NBLK];
+    int row_r[NBLK], row_c[NBLK];                            // (SPLIT: entries [0, GB) describe this group's blocks)
     bool row_ok[NBLK];
 #pragma unroll
     for (int blk = 0; blk < NBLK; ++blk) {
-      const int m = blk * BS + mp;                           // position in the padded plane
+      const int m = ((SPLIT ? ((warp - 2) >> 2) * (NBLK / 2) : 0) + blk) * BS + mp;   // position in the padded plane
       row_r[blk] = m / p.P;
       row_c[blk] = m - row_r[blk] * p.P;
       row_ok[blk] = (mp < BS) && (m < p.Mtot) && (row_c[blk] < p.Ct);
     }
     constexpr int XROW = (KW - 1) * 16;                      // floats per exchanged row: taps 1..KW-1 x 16 channels
     constexpr int XQ = (KW - 1) * XROW;                      // floats per quarter
-    float* xg = xch + eg * (2 * 4 * XQ);                     // this group's two exchange buffers
+    // this group's two exchange buffers (shared-space byte address; sized for NBLK blocks per pass)
+    const uint32_t xg_s = sm100::smem_u32(xch) + (uint32_t)(eg * (2 * 4 * ((KW <= 3) ? 2 : 1) * XQ)) * 4u;
     uint32_t acc_phase = 0;
+    int acc = SPLIT ? 0 : eg;
     uint32_t xch_it = 0;
-    (void)xch_it; (void)xg;
-    int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-      if ((local & 1) != eg) continue;
-      int rest = tile;
-      const int nt = rest % p.nNT; rest /= p.nNT;
-      const int wb = rest % p.wblocks; rest /= p.wblocks;
-      const int hb = rest % p.hblocks; rest /= p.hblocks;
-      const int t = rest % p.T;
-      const int b = rest / p.T;
+    (void)xch_it; (void)xg_s;
+    auto drain = [&](int nt, int wb, int hb, int t, int b) {
       const long long pix0 = (((long long)b * p.T + t) * p.H + hb * p.R) * p.W + wb * p.Ct;
-      sm100::mbar_wait(&tmem_full[eg], acc_phase);
-      acc_phase ^= 1;
+      const int a_cur = acc;
+      sm100::mbar_wait(&tmem_full[a_cur], acc_phase);
+      if (SPLIT) { if (++acc == 2) { acc = 0; acc_phase ^= 1; } } else { acc_phase ^= 1; }
       sm100::tc_fence_after();
+      if (q.dbg & 2) {
+        sm100::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&tmem_empty[a_cur]);
+        return;
+      }
+      bool valid[NBLK];
+      long long pix[NBLK];
 #pragma unroll
       for (int blk = 0; blk < NBLK; ++blk) {
-        const bool valid = row_ok[blk] && (hb * p.R + row_r[blk] < p.H) && (wb * p.Ct + row_c[blk] < p.W);
-        const long long pix = pix0 + (long long)row_r[blk] * p.W + row_c[blk];
-        const uint32_t taddr = tmem_base + eg * ACC_COLS + blk * NW + ((uint32_t)(quarter * 32) << 16);
-        if constexpr (!PACK) {
+        valid[blk] = row_ok[blk] && (hb * p.R + row_r[blk] < p.H) && (wb * p.Ct + row_c[blk] < p.W) && !(q.dbg & 1);
+        pix[blk] = pix0 + (long long)row_r[blk] * p.W + row_c[blk];
+      }
+      const uint32_t taddr0 = tmem_base + a_cur * ACC_COLS + ((uint32_t)(quarter * 32) << 16);
+      if constexpr (!PACK) {
+#pragma unroll
+        for (int j = 0; j < GB; ++j) {
           uint32_t rr[NT / 16][16];
 #pragma unroll
-          for (int cc = 0; cc < NT / 16; ++cc) tmem_ld_32x16(taddr + cc * 16, rr[cc]);
+          for (int cc = 0; cc < NT / 16; ++cc) tmem_ld_32x16(taddr0 + (gb0 + j) * NW + cc * 16, rr[cc]);
           sm100::tmem_ld_wait();
-          if (valid) {
+          if (valid[j]) {
 #pragma unroll
-            for (int cc = 0; cc < NT / 16; ++cc) conv_store16(q, pix, nt * NT + cc * 16, rr[cc], s_bias + nt * NT + cc * 16);
+            for (int cc = 0; cc < NT / 16; ++cc)
+              conv_store16(q, pix[j], nt * NT + cc * 16, rr[cc], s_bias + nt * NT + cc * 16);
           }
-        } else {
-          // out[m][co] = sum_dw D'[m + dw][dw*NT + co]: rows m + dw are the next dw TMEM lanes -> warp shuffles; the
-          // last dw lanes of a quarter take the first rows of the next quarter from shared memory (xch).  Rows
-          // mp >= BS of the block are incomplete by construction and belong to the next block.
+        }
+      } else {
+        // out[m][co] = sum_dw D'[m + dw][dw*NT + co]: rows m + dw are the next dw TMEM lanes -> warp shuffles; the last
+        // dw lanes of a quarter take the first rows of the next quarter from shared memory (xch).  Rows mp >= BS of a
+        // block are incomplete by construction and belong to the next block.  EB blocks are drained per pass (all of the
+        // tile's blocks for 3-wide filters): one TMEM-load batch, one exchange and ONE barrier per pass -- the epilogue is
+        // a latency chain (ncu: 350 instructions but ~1500 cycles per block), so fewer, fatter passes are what counts.
+        constexpr int EB = (KW <= 3) ? (GB < 2 ? GB : 2) : 1;
+        constexpr int XB = (KW - 1) * XROW;                  // floats per (quarter, block): KW-1 rows
+#pragma unroll
+        for (int bp = 0; bp < GB / EB; ++bp) {               // compile-time block index: valid[] / pix[] stay in registers
 #pragma unroll 1
-          for (int cc = 0; cc < NT / 16; ++cc) {
-            uint32_t v[KW][16];
+        for (int cc = 0; cc < NT / 16; ++cc) {
+          const int blk0 = gb0 + bp * EB;
+          uint32_t v[EB][KW][16];
 #pragma unroll
-            for (int dw = 0; dw < KW; ++dw) tmem_ld_32x16(taddr + dw * NT + cc * 16, v[dw]);
-            sm100::tmem_ld_wait();
-            float* mine = xg + ((xch_it & 1) * 4 + quarter) * XQ;
-            if (lane < KW - 1) {
+          for (int e = 0; e < EB; ++e)
 #pragma unroll
-              for (int dw = 1; dw < KW; ++dw) {
-                float4* dst = reinterpret_cast<float4*>(mine + lane * XROW + (dw - 1) * 16);
+            for (int dw = 0; dw < KW; ++dw) tmem_ld_32x16(taddr0 + (blk0 + e) * NW + dw * NT + cc * 16, v[e][dw]);
+          sm100::tmem_ld_wait();
+          const uint32_t mine = xg_s + (uint32_t)(((xch_it & 1) * 4 + quarter) * (EB * XB)) * 4u;
+          if (lane < KW - 1) {
+#pragma unroll
+            for (int e = 0; e < EB; ++e)
+#pragma unroll
+              for (int dw = 1; dw < KW; ++dw)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  dst[j] = make_float4(__uint_as_float(v[dw][4 * j]), __uint_as_float(v[dw][4 * j + 1]),
-                                       __uint_as_float(v[dw][4 * j + 2]), __uint_as_float(v[dw][4 * j + 3]));
-              }
-            }
-            // the four warps of this group (named barrier 1 + group); xch is double buffered, one barrier per chunk
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-            const float* next = xg + ((xch_it & 1) * 4 + ((quarter + 1) & 3)) * XQ;
-            ++xch_it;
+                  st_shared_v4(mine + (uint32_t)(e * XB + lane * XROW + (dw - 1) * 16 + 4 * j) * 4u, v[e][dw][4 * j],
+                               v[e][dw][4 * j + 1], v[e][dw][4 * j + 2], v[e][dw][4 * j + 3]);
+          }
+          // the four warps of this group (named barrier 1 + group); xch is double buffered, one barrier per pass
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+          const uint32_t next = xg_s + (uint32_t)(((xch_it & 1) * 4 + ((quarter + 1) & 3)) * (EB * XB)) * 4u;
+          ++xch_it;
+#pragma unroll
+          for (int e = 0; e < EB; ++e) {
 #pragma unroll
             for (int dw = 1; dw < KW; ++dw) {
               // row m + dw: lane + dw of this warp (shuffle), or row lane + dw - 32 of the next quarter (xch).  No
               // divergent branches: every lane reads xch (clamped address, mostly a broadcast) and selects.
               const int jn = lane + dw - 32;
-              const float4* nx = reinterpret_cast<const float4*>(next + (jn < 0 ? 0 : jn) * XROW + (dw - 1) * 16);
-              const float4 n0 = nx[0], n1 = nx[1], n2 = nx[2], n3 = nx[3];
-              const float nv[16] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w,
-                                    n2.x, n2.y, n2.z, n2.w, n3.x, n3.y, n3.z, n3.w};
+              const uint32_t nrow = next + (uint32_t)(e * XB + (jn < 0 ? 0 : jn) * XROW + (dw - 1) * 16) * 4u;
+              uint32_t nv[16];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ld_shared_v4(nrow + 16u * j, nv[4 * j], nv[4 * j + 1], nv[4 * j + 2], nv[4 * j + 3]);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(v[dw][i]), dw);
-                v[0][i] = __float_as_uint(__uint_as_float(v[0][i]) + (jn >= 0 ? nv[i] : sv));
+                const float sv = __shfl_down_sync(0xffffffffu, __uint_as_float(v[e][dw][i]), dw);
+                v[e][0][i] = __float_as_uint(__uint_as_float(v[e][0][i]) + (jn >= 0 ? __uint_as_float(nv[i]) : sv));
               }
             }
-            if (valid) conv_store16(q, pix, nt * NT + cc * 16, v[0], s_bias + nt * NT + cc * 16);
           }
+#pragma unroll
+          for (int e = 0; e < EB; ++e)
+            if (valid[bp * EB + e]) conv_store16(q, pix[bp * EB + e], nt * NT + cc * 16, v[e][0], s_bias + nt * NT + cc * 16);
+        }
         }
       }
       sm100::tc_fence_before();
       __syncwarp();
-      if (lane == 0) sm100::mbar_arrive(&tmem_empty[eg]);
+      if (lane == 0) sm100::mbar_arrive(&tmem_empty[a_cur]);
+    };
+    int local = 0;
+    if (p.slide) {
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        ConvUnit cu;
+        cu.decode(p, u);
+        for (int ot = 0; ot < cu.nf; ++ot, ++local)
+          if (SPLIT || (local & 1) == eg) drain(0, cu.wb, cu.hb, cu.t0 + ot, cu.b);
+      }
+    } else {
+      ConvTileIter it;
+      it.init(p, blockIdx.x, gridDim.x);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local, it.advance(p))
+        if (SPLIT || (local & 1) == eg) drain(it.nt, it.wb, it.hb, it.t, it.b);
     }
   }
   sm100::tc_fence_before();
@@ -535,6 +734,8 @@ static ConvKernelFn pick_conv_kernel2(int nblk, int NT) {
     if constexpr (2 * F * 16 <= 256) if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 2, 16, PACK>;
     if constexpr (2 * F * 32 <= 256) if (NT == 32) return conv_sm100_kernel<KH, KW, NKS, 2, 32, PACK>;
     if constexpr (2 * F * 64 <= 256) if (NT == 64) return conv_sm100_kernel<KH, KW, NKS, 2, 64, PACK>;
+  } else if (nblk == 4) {
+    if constexpr (PACK && 4 * F * 16 <= 256) if (NT == 16) return conv_sm100_kernel<KH, KW, NKS, 4, 16, PACK>;
   }
   return nullptr;
 }
@@ -588,6 +789,7 @@ int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
     q.y = (bf16*)const_cast<void*>(a.x); q.y_ld = a.x_ld; q.bias = nullptr; q.mode = VVAE_EPI_NONE; q.aux = nullptr; q.ld_aux = 0;
   }
   q.store_c = p.Cout;
+  q.dbg = (int)g_dbg[14];
   if (a.pad_out) {
     const int padded = (p.Cout + 15) / 16 * 16;
     if (q.y_ld < padded) {
@@ -614,7 +816,7 @@ int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
       configured.insert(kern);
     }
   }
-  const int grid = std::min(p.total_tiles, num_sms());
+  const int grid = std::min(p.slide ? p.units : p.total_tiles, num_sms());
   kern<<<grid, CONV_THREADS, p.smem_bytes, s>>>(tm, q);
   return check_launch("conv_sm100");
 }
