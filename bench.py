@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-optimizer", action="store_true")
     ap.add_argument("--graph-allreduce", action="store_true", help="N > 1, EXPERIMENTAL: capture the bucketed all-reduce "
                     "inside the graph instead of one all-reduce after it (hung at N=2 with NCCL 2.28.9 in round 1)")
+    ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="N > 1: dtype of the gradient all-reduce "
+                    "(bf16 halves the bytes on NVLink; the fp32 default matches the reference's XLA all-reduce)")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
                     "of replaying the captured CUDA graph; N > 1 then overlaps the bucketed all-reduce with backward")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
@@ -318,7 +320,7 @@ def run_ours(args):
         if graphed is not None:
             loss = graphed(v, m, rngs)
             if world > 1 and not ar_in_graph:
-                dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+                flat.all_reduce_grads(torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
         else:
             loss = eager_step(v, m)
         if opt:
@@ -361,6 +363,16 @@ def run_ours(args):
         kernels_per_step = _ffi.launch_count - calls_e0
         prof, ops.PROFILE = ops.PROFILE, None
         prof_steps = 1
+        if args.profile_kernels and rank == 0:       # device time of every C-ABI entry point over one eager step
+            with _ffi.AbiProfile() as ap:
+                eager_step(video, mask)
+                if opt:
+                    opt.step(grad_scale=1.0 / world)
+            torch.cuda.synchronize()
+            tot = sum(t for _, _, t in ap.table())
+            for name, calls_, t in ap.table():
+                print(json.dumps({"abi_entry": name, "calls_per_step": calls_, "ms_per_step": round(t, 4),
+                                  "share_of_abi_time": round(t / tot, 4)}), file=sys.stderr)
     else:
         prof_steps = args.steps
     ms = e0.elapsed_time(e1) / args.steps
@@ -462,6 +474,7 @@ def run_ours(args):
                       ") + eager " + ("all-reduce + " if (world > 1 and not ar_in_graph) else "") + "optimizer")
         if graphed is not None else "eager",
         "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30,
+        "grad_comm": (args.grad_comm if world > 1 else None),
         "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
     }
     if world == 1 and not args.no_cpu_baseline:

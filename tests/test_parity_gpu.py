@@ -673,6 +673,36 @@ def test_cuda_graph_step_equals_eager_step(V):
     assert loss_o != loss_e.item()
 
 
+def test_cuda_graph_capture_after_eager_backward(V):
+    """a training script that runs an eager (or eval) step first must still be able to capture.
+    The old loss / aux stay referenced on purpose: they keep the eager autograd graph -- and with it the parameters'
+    AccumulateGrad nodes, bound to the eager stream -- alive, which is what used to break the capture."""
+    from video_vae_b200.ddp import FlatParams
+    from video_vae_b200.graph import GraphedTrainStep
+    cfg = (64, 64, 3, 16, 1, 1, 256, 2, 128, 32, 8, 4)
+    m = V.VideoVAE(*cfg, V.Rngs(2), dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.05, generator=torch.Generator(device="cuda").manual_seed(7))
+    flat = FlatParams(m)
+    flat.enable_bf16_shadow()
+    g = _gen(9)
+    video = torch.rand(2, 4, 64, 64, 3, generator=g).to(torch.bfloat16).cuda()
+    mask = torch.ones(2, 4, dtype=torch.bool).cuda()
+    flat.zero_grad()
+    loss_e, aux_e = V.loss_fn(m, video, mask[:, None, None, :], mask, V.Rngs(5), V.DEFAULT_HPARAMS, train=True)
+    loss_e.backward()                                   # eager step on the default stream, graph kept alive below
+    torch.cuda.synchronize()
+    grad_e = flat.grad.clone()
+    params_before = [id(p) for p in m.parameters()]
+    graphed = GraphedTrainStep(m, flat, video, mask, V.DEFAULT_HPARAMS)
+    assert [id(p) for p in m.parameters()] == params_before          # the private leaves were swapped back out
+    loss_g = graphed(video, mask, V.Rngs(5))
+    torch.cuda.synchronize()
+    assert abs(loss_g.item() - loss_e.item()) <= 1e-3 * abs(loss_e.item())
+    assert rel_err(flat.grad, grad_e) < 2e-3
+    assert aux_e["reconstruction"].shape == (2, 4, 64, 64, 3)
+
+
 def test_cuda_graph_rl_step_equals_eager_step(V):
     """graph.GraphedRLTrainStep (rl_model + RL loss + VGG perceptual term in one CUDA graph) reproduces the eager step
     under the same Rngs.  rl_loss_weight = 0: with it, twins that draw the same keep-mask turn rounding noise into +-1

@@ -170,3 +170,51 @@ def stream():
 def require_device():
     if not torch.cuda.is_available() or not lib.vvae_device_ok():
         raise VvaeError("video_vae_b200 needs a CUDA device of compute capability 10.x (B200); there is no CPU path")
+
+
+# ---------------------------------------------------------------------------------------------------- profiling aid
+class AbiProfile:
+    """CUDA-event timing of EVERY libvvae entry point that takes a stream (bench.py --profile-kernels, scripts/):
+
+        with AbiProfile() as prof: step()
+        torch.cuda.synchronize(); table = prof.table()
+
+    Each call is bracketed by two events on the current stream, so the numbers are device times of that entry point's
+    kernels in an eager pass (launch gaps included in neither).  Not for use under CUDA-graph capture."""
+
+    _NO_STREAM = ("vvae_version", "vvae_device_ok", "vvae_debug_set", "vvae_gemm_uses_tcgen05", "vvae_conv3d_wprep_bytes",
+                  "vvae_convT122_workspace_bytes", "vvae_sumsq_partials")
+
+    def __init__(self, key=None):
+        self.records, self._saved, self.key = [], {}, key
+
+    def __enter__(self):
+        for name in _SIGS:
+            if name in self._NO_STREAM:
+                continue
+            fn = getattr(lib, name)
+            self._saved[name] = fn
+
+            def wrapper(*args, _fn=fn, _name=name):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = _fn(*args)
+                e1.record()
+                self.records.append((self.key(_name, args) if self.key else _name, e0, e1))
+                return rc
+            setattr(lib, name, wrapper)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self._saved.items():
+            setattr(lib, name, fn)
+        return False
+
+    def table(self):
+        """[(entry point, calls, total ms)] sorted by time; call after torch.cuda.synchronize()."""
+        agg = {}
+        for name, e0, e1 in self.records:
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+        return sorted(((n, c, t) for n, (c, t) in agg.items()), key=lambda r: -r[2])

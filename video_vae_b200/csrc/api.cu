@@ -72,6 +72,19 @@ __global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ src, uint4* 
   }
 }
 
+// bf16 -> fp32 with 16-byte accesses (the reduced bf16 gradient back into the fp32 flat buffer).
+__global__ void cast_bf16_f32_vec_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, long long n8) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n8; i += stride) {
+    const uint4 v = src[i];
+    dst[2 * i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                             __uint_as_float(v.y & 0xffff0000u));
+    dst[2 * i + 1] = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u), __uint_as_float(v.w << 16),
+                                 __uint_as_float(v.w & 0xffff0000u));
+  }
+}
+
 __global__ void fill_kernel(float* dst, float v, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -172,6 +185,12 @@ int vvae_cast(const void* src, int sd, void* dst, int dd, long long n, vvae_stre
     long long n8 = n / 8;
     int blocks = (int)std::min<long long>(cdiv(n8, threads), num_sms() * 16);
     cast_f32_bf16_vec_kernel<<<blocks, threads, 0, s>>>((const float4*)src, (uint4*)dst, n8);
+    return check_launch("cast");
+  }
+  if (sd == VVAE_BF16 && dd == VVAE_F32 && n % 8 == 0 && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0)) {
+    long long n8 = n / 8;
+    int blocks = (int)std::min<long long>(cdiv(n8, threads), num_sms() * 16);
+    cast_bf16_f32_vec_kernel<<<blocks, threads, 0, s>>>((const uint4*)src, (float4*)dst, n8);
     return check_launch("cast");
   }
   int blocks = (int)std::min<long long>(cdiv(n, threads * 4), num_sms() * 16);

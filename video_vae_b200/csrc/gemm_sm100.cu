@@ -2,7 +2,11 @@
 // TMEM, double buffered) -> tcgen05.ld epilogue.  Persistent, warp specialised:
 //   warp 0   : TMA producer (one lane)
 //   warp 1   : TMEM allocator + MMA issuer (one lane)
-//   warps 2-5: epilogue (each owns the TMEM lane quarter warp_id % 4)
+//   warps 2-9: epilogue: two warps per TMEM lane quarter (warp_id % 4), each draining one 32-column half of every
+//              64-column chunk.  The epilogue is a latency chain (tcgen05.ld -> convert -> staging -> TMA store), and with
+//              four warps it took longer per tile than the tile's MMAs: with NO operand loads at all the kernel still ran
+//              at only 1.2 PFLOP/s (profiles/r02p_gemm_ablate.jsonl) -- the accumulator drain, not L2, was the limiter.
+//   warps 10-11: (weight-gradient mode) column sums of B
 // Both operands may be K-major (contraction index contiguous in memory) or MN-major (row/column index contiguous),
 // so forward (X . W, W is Flax (in,out) = MN-major B), dgrad (dY . W^T, K-major B) and wgrad (X^T . dY, both MN-major,
 // split-K with fp32 atomics) all read the tensors where they lie -- no transposed copies are ever materialised.
@@ -98,6 +102,7 @@ struct Sm100Params {
   float* bsum;             // MODE_BSUM: += column sums of op(B) over K (a Linear's bias gradient, fused into its wgrad)
   // descriptor encodings (bytes); overridable through vvae_debug_set for bring-up
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+  int dbg;                 // vvae_debug_set(10): TIMING ablations, wrong results (1: skip the A-tile TMA loads, 2: skip B)
 };
 
 // HEAVY epilogues (residual / dSiLU read an aux tile, SiLU writes two tiles) get 4 extra staging buffers: a 4-deep ring of
@@ -194,7 +199,7 @@ template <int N> __device__ __forceinline__ void bulk_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -244,7 +249,7 @@ __device__ __forceinline__ float fast_dsilu(float x) {
 }
 
 template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_ai,
                   const __grid_constant__ CUtensorMap tma_ao, Sm100Params p) {
@@ -285,7 +290,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
-      sm100::mbar_init(&tmem_empty[i], 4 * CG);
+      sm100::mbar_init(&tmem_empty[i], 8 * CG);
     }
     for (int i = 0; i < AUXR; ++i) sm100::mbar_init(&aux_full[i], 1);
     sm100::fence_barrier_init();
@@ -312,17 +317,20 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (cta_rank == 0) sm100::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES * CG);
+          if (cta_rank == 0)
+            sm100::mbar_expect_tx(&full_bar[stage], (((p.dbg & 1) ? 0 : A_STAGE_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_STAGE_BYTES)) * CG);
           uint8_t* sa = smem_a + stage * A_STAGE_BYTES;
           uint8_t* sb = smem_b + stage * Cfg::B_STAGE_BYTES;
           const int k0 = kb * BK;
-          if constexpr (A_MN) {
+          if (p.dbg & 1) {
+          } else if constexpr (A_MN) {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg<CG>(sa + j * 8192, &tma_a, &full_bar[stage], m0 + 64 * j, k0);
           } else {
             tma_load_2d_cg<CG>(sa, &tma_a, &full_bar[stage], k0, m0);
           }
-          if constexpr (B_MN) {
+          if (p.dbg & 2) {
+          } else if constexpr (B_MN) {
 #pragma unroll
             for (int j = 0; j < BN / CG / 64; ++j)
               tma_load_2d_cg<CG>(sb + j * 8192, &tma_b, &full_bar[stage], n0 + 64 * j, k0);
@@ -366,11 +374,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 10) {
     // ===================== column sums of B (bias gradient), after the tensor core is done with each stage ==========
     if constexpr (BSUM) {
       constexpr int NCH_B = BN / CG / 64;          // 64-column chunks of this CTA's B slice
-      const int cw = warp - 6;                     // chunks cw, cw+2, ...
+      const int cw = warp - 10;                    // chunks cw, cw+2, ...
       const int cc = lane & 7, rg = lane >> 3;     // 16-byte column chunk, row group
       int stage = 0;
       uint32_t phase = 0;
@@ -428,8 +436,9 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   } else {
     // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;              // which 32-column half of each 64-column chunk this warp drains
     const int r = quarter * 32 + lane;           // row inside the CTA's 128-row tile == TMEM lane
-    const int etid = threadIdx.x - 64;           // 0..127
+    const int etid = threadIdx.x - 64;           // 0..255
     const uint32_t sw = (uint32_t)(r & 7);
     constexpr bool use_aux = MODE == VVAE_EPI_RESIDUAL || MODE == VVAE_EPI_DSILU;
     const bool two_out = MODE == VVAE_EPI_SILU && p.aux_out != nullptr;
@@ -458,7 +467,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (mn % p.n_tiles) * BN;
       float* bias_t = s_bias;   // single buffer: every reader of the previous tile's slice has passed that tile's last barrier
       if (p.tma_epi && p.bias) {                 // this tile's bias slice -> smem (read back as broadcasts)
-        for (int j = etid; j < BN; j += 128) bias_t[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+        for (int j = etid; j < BN; j += 256) bias_t[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
         epi_bar();
       }
       sm100::mbar_wait(&tmem_full[acc], acc_phase);
@@ -467,7 +476,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (!p.tma_epi) {
         const long long m = (long long)m0 + r;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hf; c < BN / 32; c += 2) {
           if (n0 + c * 32 >= p.N) break;  // warp-uniform
           uint32_t rr[32];
           sm100::tmem_ld_32x32(taddr + c * 32, rr);
@@ -479,24 +488,23 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         for (int c = 0; c < NCH; ++c, ++g) {
           const int nc = n0 + 64 * c;
           const uint32_t b = g & 1;
-          uint4 ax[8];
+          uint4 ax[4];
           if constexpr (use_aux) {
             const uint32_t ab = g & (AUXR - 1);
             sm100::mbar_wait(&aux_full[ab], (g >> 2) & 1);
             const uint8_t* arow = stg_aux + ab * STG_BYTES + r * 128;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) ax[ch] = *reinterpret_cast<const uint4*>(arow + (((uint32_t)ch ^ sw) << 4));
+            for (int ch = 0; ch < 4; ++ch)
+              ax[ch] = *reinterpret_cast<const uint4*>(arow + (((uint32_t)(hf * 4 + ch) ^ sw) << 4));
           }
-          uint32_t pk[32], pk2[32];
-          uint32_t rr0[32], rr1[32];
-          sm100::tmem_ld_32x32(taddr + c * 64, rr0);
-          sm100::tmem_ld_32x32(taddr + c * 64 + 32, rr1);
+          uint32_t pk[16], pk2[16];
+          uint32_t rr[32];
+          sm100::tmem_ld_32x32(taddr + c * 64 + hf * 32, rr);
           sm100::tmem_ld_wait();
-#pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
+          {
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(hf ? rr1[j] : rr0[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
             if (p.bias) {
               const float4* b4 = reinterpret_cast<const float4*>(bias_t + c * 64 + hf * 32);
 #pragma unroll
@@ -509,22 +517,22 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 #pragma unroll
               for (int j = 0; j < 32; j += 2) {
                 const uint32_t pre = pack_bf16x2(v[j], v[j + 1]);
-                pk2[hf * 16 + (j >> 1)] = pre;
+                pk2[j >> 1] = pre;
                 const float x0 = __uint_as_float(pre << 16), x1 = __uint_as_float(pre & 0xffff0000u);
-                pk[hf * 16 + (j >> 1)] = pack_bf16x2(fast_silu(x0), fast_silu(x1));
+                pk[j >> 1] = pack_bf16x2(fast_silu(x0), fast_silu(x1));
               }
             } else {
               if constexpr (use_aux) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                  const uint32_t w = (&ax[hf * 4 + (j >> 3)].x)[(j >> 1) & 3];
+                  const uint32_t w = (&ax[j >> 3].x)[(j >> 1) & 3];
                   const float a0 = __uint_as_float(w << 16), a1 = __uint_as_float(w & 0xffff0000u);
                   if constexpr (MODE == VVAE_EPI_RESIDUAL) { v[j] += a0; v[j + 1] += a1; }
                   else { v[j] *= fast_dsilu(a0); v[j + 1] *= fast_dsilu(a1); }
                 }
               }
 #pragma unroll
-              for (int j = 0; j < 32; j += 2) pk[hf * 16 + (j >> 1)] = pack_bf16x2(v[j], v[j + 1]);
+              for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack_bf16x2(v[j], v[j + 1]);
             }
           }
           // staging buffer(s) must have been read out by the TMA store that last used them
@@ -533,14 +541,14 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           if (use_aux && etid == 0) prefetch_aux();          // every thread has consumed this chunk's aux buffer
           uint8_t* orow = stg_out + b * STG_BYTES + r * 128;
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch)
-            *reinterpret_cast<uint4*>(orow + (((uint32_t)ch ^ sw) << 4)) =
+          for (int ch = 0; ch < 4; ++ch)
+            *reinterpret_cast<uint4*>(orow + (((uint32_t)(hf * 4 + ch) ^ sw) << 4)) =
                 make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
           if (two_out) {
             uint8_t* prow = stg_aux + b * STG_BYTES + r * 128;
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch)
-              *reinterpret_cast<uint4*>(prow + (((uint32_t)ch ^ sw) << 4)) =
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<uint4*>(prow + (((uint32_t)(hf * 4 + ch) ^ sw) << 4)) =
                   make_uint4(pk2[4 * ch], pk2[4 * ch + 1], pk2[4 * ch + 2], pk2[4 * ch + 3]);
           }
           sm100::fence_proxy_async();
@@ -625,6 +633,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   p.atomic = (a.accumulate || p.splits > 1) ? 1 : 0;
   p.tma_epi = p.out_f32 ? 0 : 1;
   p.bsum = a.bsum_accum;
+  p.dbg = (int)g_dbg[10];
   tc = ta; tai = ta; tao = ta;   // placeholders for maps a mode does not use
   if (p.tma_epi) {
     if ((rc = encode_tmap_2d_bf16(&tc, a.C, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * 2, 64, 128, 128))) return rc;
@@ -660,7 +669,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   int clusters = std::min(total, g_dbg[0] ? (int)g_dbg[0] : n_clusters);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
-  cfg.blockDim = dim3(MODE == MODE_BSUM ? 256 : 192);
+  cfg.blockDim = dim3(MODE == MODE_BSUM ? 384 : 320);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];

@@ -65,6 +65,22 @@ class FlatParams:
             else:
                 F_.params_changed()
 
+    def all_reduce_grads(self, comm_dtype=torch.float32, group=None):
+        """Sum the flat gradient over the ranks with ONE collective (the graph-mode exchange step: the reference's XLA
+        SPMD all-reduce of claude_distributed/distributed_train.py:378-380).  ``comm_dtype=torch.bfloat16`` sends a bf16
+        copy (341 MB instead of 682 MB at production size): one cast kernel each way, the sum itself runs in NCCL; the
+        fp32 buffer then holds the bf16-rounded sum -- every rank the SAME values, so replicas stay bit-identical."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        if comm_dtype == torch.float32 or not self.grad.is_cuda:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            return
+        if getattr(self, "_grad_lowp", None) is None or self._grad_lowp.dtype != comm_dtype:
+            self._grad_lowp = torch.empty(self.total, dtype=comm_dtype, device=self.grad.device)
+        ops.cast_into(self.grad, self._grad_lowp)
+        dist.all_reduce(self._grad_lowp, op=dist.ReduceOp.SUM, group=group)
+        ops.cast_into(self._grad_lowp, self.grad)
+
     def zero_grad(self):
         if self.grad.is_cuda:
             ops.fill_(self.grad, 0.0)

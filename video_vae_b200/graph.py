@@ -8,17 +8,54 @@ the input clip and mask (copied in before the replay) and the Philox draws of th
 the eager step).  The optimizer (and, for N > 1, the gradient all-reduce) runs outside the graph: the bias-corrected
 Adam constants change every step and are passed by value.
 
-Capture BEFORE running eager backward passes in the same process: after an eager ``loss.backward()`` the autograd
-engine's stream bookkeeping for the leaves makes a later capture fail with "dependency created on uncaptured work in
-another stream" (tests and scripts/run_configs.py capture first, then run their eager comparisons).  Nothing on the
+Capture works at any point of a process, also after eager ``loss.backward()`` calls.  (The trap, found in round 1 and
+diagnosed in round 2: every leaf's AccumulateGrad node is bound to the stream that was current when it was created and
+lives as long as any old autograd graph references it; the captured backward then synchronises the capture stream with
+that uncaptured stream -> "dependency created on uncaptured work in another stream".  The capture therefore runs on
+PRIVATE LEAVES: for the duration of warm-up + capture every parameter of the model is replaced by a fresh
+``nn.Parameter`` over the same storage and the same gradient view, whose AccumulateGrad nodes are born on the capture
+stream; the recorded kernels only know addresses, so replays serve the original parameters.)  Nothing on the
 captured path may read device data from the host: ``repeat_interleave`` with an integer count and the backward of
 ``prod`` both do, which is why rl_model / rl_losses avoid them.
 """
+import contextlib
+import weakref
+
 import torch
+from torch import nn
 
 from . import functional as F_
 from . import ops
 from .losses import DEFAULT_HPARAMS, loss_fn
+
+
+@contextlib.contextmanager
+def _private_leaves(model, reducer=None):
+    """Swap every parameter of ``model`` for a fresh leaf over the same storage / gradient buffer (see module docstring)."""
+    swapped = []
+    for mod in model.modules():
+        for name, p in list(mod._parameters.items()):
+            if p is None:
+                continue
+            twin = nn.Parameter(p.data, requires_grad=p.requires_grad)
+            twin.grad = p.grad
+            ent = F_._flat_shadow_views.get(id(p))
+            if ent is not None and ent[0]() is p:
+                F_._flat_shadow_views[id(twin)] = (weakref.ref(twin), ent[1])
+            if reducer is not None and id(p) in reducer.bucket_of:
+                reducer.bucket_of[id(twin)] = reducer.bucket_of[id(p)]
+            mod._parameters[name] = twin
+            swapped.append((mod, name, p, twin))
+    try:
+        yield
+    finally:
+        for mod, name, p, twin in swapped:
+            mod._parameters[name] = p
+            if p.grad is None and twin.grad is not None:      # a gradient buffer first created during the capture
+                p.grad = twin.grad
+            F_._flat_shadow_views.pop(id(twin), None)
+            if reducer is not None:
+                reducer.bucket_of.pop(id(twin), None)
 
 
 class GraphedTrainStep:
@@ -51,24 +88,25 @@ class GraphedTrainStep:
         self.aux = None
         prof, ops.PROFILE = ops.PROFILE, None            # event timing cannot be captured
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(warmup):
-                    self._body()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            F_.invalidate_shadows()                      # every derived weight image is rebuilt INSIDE the graph
-            hook = None
-            if self.decoder_done is not None:
-                hook = lambda: self.decoder_done.record(torch.cuda.current_stream())   # noqa: E731
-                F_._decoder_done_hooks.append(hook)
-            try:
-                with torch.cuda.graph(self.graph):
-                    self.loss, self.aux = self._body()
-            finally:
-                if hook is not None:
-                    F_._decoder_done_hooks.remove(hook)
+            with _private_leaves(model, reducer):
+                side = torch.cuda.Stream()               # warm-up AND capture on this one stream
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for _ in range(warmup):
+                        self._body()
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                F_.invalidate_shadows()                  # every derived weight image is rebuilt INSIDE the graph
+                hook = None
+                if self.decoder_done is not None:
+                    hook = lambda: self.decoder_done.record(torch.cuda.current_stream())   # noqa: E731
+                    F_._decoder_done_hooks.append(hook)
+                try:
+                    with torch.cuda.graph(self.graph, stream=side):
+                        self.loss, self.aux = self._body()
+                finally:
+                    if hook is not None:
+                        F_._decoder_done_hooks.remove(hook)
         finally:
             ops.PROFILE = prof
 
