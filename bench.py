@@ -62,6 +62,8 @@ def parse():
                     "inside the graph instead of one all-reduce after it (hung at N=2 with NCCL 2.28.9 in round 1)")
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="N > 1: dtype of the gradient all-reduce "
                     "(bf16 halves the bytes on NVLink; the fp32 default matches the reference's XLA all-reduce)")
+    ap.add_argument("--recompute", action="store_true", help="per-layer activation recompute in every FactoredAttention "
+                    "(the reference's @nnx.remat, train/layers.py:209): one extra forward per layer, ~1.1 GB/layer less")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
                     "of replaying the captured CUDA graph; N > 1 then overlaps the bucketed all-reduce with backward")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
@@ -262,6 +264,8 @@ def run_ours(args):
                        PROD["unembedding_upsample_rate"], V.Rngs(2), dtype=torch.bfloat16, device=dev)
     with torch.no_grad():   # exercise the UNet backward (the reference zero-inits final_conv: SURVEY.md 7.3)
         model.decoder.unet.final_conv.kernel.normal_(0.0, 0.02, generator=torch.Generator(device=dev).manual_seed(7))
+    if args.recompute:
+        model.set_recompute(True)
     flat = FlatParams(model)
     flat.enable_bf16_shadow()
     flat.broadcast(src=0)     # rank 0's weights everywhere (distributed_train.py:339 broadcast_one_to_all); untimed
@@ -474,7 +478,7 @@ def run_ours(args):
                       ") + eager " + ("all-reduce + " if (world > 1 and not ar_in_graph) else "") + "optimizer")
         if graphed is not None else "eager",
         "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30,
-        "grad_comm": (args.grad_comm if world > 1 else None),
+        "grad_comm": (args.grad_comm if world > 1 else None), "recompute": bool(args.recompute),
         "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -673,6 +673,48 @@ def test_cuda_graph_step_equals_eager_step(V):
     assert loss_o != loss_e.item()
 
 
+def test_per_layer_recompute_matches_stored_activations(V):
+    """The reference's @nnx.remat (train/layers.py:209) as a switch: FactoredAttention(recompute=True) keeps only the
+    layer input and re-runs the forward kernels in backward -- same loss, same gradients (bf16 kernels are
+    deterministic up to the fp32 atomics of the split-K weight gradients), less memory, eager and inside a CUDA graph."""
+    from video_vae_b200.ddp import FlatParams
+    from video_vae_b200.graph import GraphedTrainStep
+    cfg = (64, 64, 3, 16, 2, 2, 256, 2, 128, 32, 8, 4)
+    m = V.VideoVAE(*cfg, V.Rngs(2), dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.05, generator=torch.Generator(device="cuda").manual_seed(7))
+    flat = FlatParams(m)
+    flat.enable_bf16_shadow()
+    g = _gen(9)
+    video = torch.rand(2, 8, 64, 64, 3, generator=g).to(torch.bfloat16).cuda()
+    mask = torch.ones(2, 8, dtype=torch.bool).cuda()
+    mask[1, 5:] = False
+
+    def step():
+        flat.zero_grad()
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        loss, _ = V.loss_fn(m, video, mask[:, None, None, :], mask, V.Rngs(5), V.DEFAULT_HPARAMS, train=True)
+        held = torch.cuda.memory_allocated() - base            # activations kept for backward
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.item(), flat.grad.clone(), held
+
+    l0, g0, held0 = step()
+    m.set_recompute(True)
+    assert all(layer.recompute for layer in m.encoder.layers) and all(layer.recompute for layer in m.decoder.layers)
+    l1, g1, held1 = step()
+    print(f"[recompute] loss {l0} / {l1}; activations held for backward {held0 / 2**20:.1f} MiB -> {held1 / 2**20:.1f} MiB")
+    assert abs(l1 - l0) <= 1e-4 * abs(l0)                       # same forward kernels; fp32 atomics (GroupNorm statistics) reorder
+    assert rel_err(g1, g0) < 2e-3
+    assert held1 < held0, (held0, held1)                        # (the U-Net still stores its activations)
+    graphed = GraphedTrainStep(m, flat, video, mask, V.DEFAULT_HPARAMS)
+    lg = graphed(video, mask, V.Rngs(5)).item()
+    torch.cuda.synchronize()
+    assert abs(lg - l0) <= 1e-3 * abs(l0) and rel_err(flat.grad, g0) < 2e-3
+
+
 def test_cuda_graph_capture_after_eager_backward(V):
     """a training script that runs an eager (or eval) step first must still be able to capture.
     The old loss / aux stay referenced on purpose: they keep the eager autograd graph -- and with it the parameters'

@@ -261,6 +261,33 @@ class MlpBlockFn(Function):
         return (dx.view(ctx.x_shape),) + (None,) * 8
 
 
+# ------------------------------------------------------------------ per-layer recompute (the reference's @nnx.remat)
+class RecomputeFn(Function):
+    """y = run(x) keeping ONLY x for backward; backward re-runs ``run`` (the forward kernels) and differentiates it.
+    train/layers.py:209 and train/unet.py:44,76 wrap FactoredAttention / the U-Net blocks in ``@nnx.remat``; here it is a
+    per-layer switch (default off: 180 GB of HBM hold the activations of the BASELINE shapes).
+    ``params`` are passed only so that the output requires grad when x does not; their gradients are accumulated
+    by the kernels into ``p.grad`` during the inner backward, as everywhere else."""
+
+    @staticmethod
+    def forward(ctx, x, run, *params):
+        require_device()
+        with torch.no_grad():
+            y = run(x)
+        ctx.run = run
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        with torch.enable_grad():
+            xd = x.detach().requires_grad_(True)
+            y = ctx.run(xd)
+        torch.autograd.backward(y, dy)
+        return (xd.grad, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
 # ------------------------------------------------------------------ patch embedding / un-embedding
 class PatchEmbedFn(Function):
     """rearrange -> cast -> LayerNorm -> Linear (train/layers.py:20-27).  The video needs no gradient."""

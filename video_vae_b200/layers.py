@@ -205,9 +205,12 @@ class FactoredAttention(nn.Module):
     by train/, (b,1,1,t) as passed by claude_distributed/ (layers.py:213-214), (b,t), or None."""
 
     def __init__(self, mlp_dim, in_features, num_heads, qkv_features, max_temporal_len, max_spatial_len, rngs,
-                 dtype=torch.bfloat16, param_dtype=torch.float32, device=None):
+                 dtype=torch.bfloat16, param_dtype=torch.float32, device=None, recompute=False):
         super().__init__()
         self.dtype = dtype
+        # the reference's @nnx.remat (train/layers.py:209) as a switch: keep only the layer input for backward and re-run
+        # the forward kernels there (saves ~1.1 GB per layer at 16x256x256 x 8 clips for one extra forward)
+        self.recompute = bool(recompute)
         self.SpatialAttention = Attention(in_features, num_heads, qkv_features, max_spatial_len, True, rngs, dtype,
                                           param_dtype, device=device)
         self.SpatialMLP = MLP(in_features, mlp_dim, rngs, dtype, param_dtype, device=device)
@@ -238,13 +241,18 @@ class FactoredAttention(nn.Module):
         tmask = temporal_mask if isinstance(temporal_mask, AttnMask) else self.temporal_mask_arg(temporal_mask, b, t, hw)
         # temporal: sequences (b, hw), positions t, tokens hw apart; RoPE position = frame index
         tcfg = AttnCfg(AttnGeom(b, hw, t, t * hw, 1, hw), ta.num_heads, ta.head_dim, hw, t, tmask, True, self.dtype)
-        x = ta._run(x, tcfg)
-        x = self.TemporalMLP._run(x, True)
         # spatial: sequences (b t), positions hw, contiguous; RoPE position = flattened patch index
         scfg = AttnCfg(AttnGeom(b * t, 1, hw, hw, 0, 1), sa.num_heads, sa.head_dim, 1, hw, None, True, self.dtype)
-        x = sa._run(x, scfg)
-        x = self.SpatialMLP._run(x, True)
-        return x
+
+        def run(h):
+            h = ta._run(h, tcfg)
+            h = self.TemporalMLP._run(h, True)
+            h = sa._run(h, scfg)
+            return self.SpatialMLP._run(h, True)
+
+        if self.recompute and torch.is_grad_enabled():
+            return F_.RecomputeFn.apply(x, run, *[p for p in self.parameters() if p.requires_grad])
+        return run(x)
 
 
 class _RoundSTE(torch.autograd.Function):

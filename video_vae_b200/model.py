@@ -96,6 +96,14 @@ class VideoVAE(nn.Module):
         fill = torch.randn(1, 1, 1, lat, generator=key, dtype=torch.float32) * 0.02
         self.fill_token = nn.Parameter(fill.to(_default_device(device)))
 
+    def set_recompute(self, on=True):
+        """Per-layer activation recompute (the reference's ``@nnx.remat`` on FactoredAttention, train/layers.py:209) for
+        every transformer layer of the encoder and decoder; returns self."""
+        for mod in self.modules():
+            if isinstance(mod, FactoredAttention):
+                mod.recompute = bool(on)
+        return self
+
     def forward(self, x, mask, rngs, train=True, noise=None, gumbel_u=None):
         mean, log_variance, selection = self.encoder(x, mask, rngs, train=train, gumbel_u=gumbel_u)
         seed, offset = rngs.sampling() if (train and noise is None) else (0, 0)
