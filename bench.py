@@ -64,6 +64,8 @@ def parse():
                     "(bf16 halves the bytes on NVLink; the fp32 default matches the reference's XLA all-reduce)")
     ap.add_argument("--recompute", action="store_true", help="per-layer activation recompute in every FactoredAttention "
                     "(the reference's @nnx.remat, train/layers.py:209): one extra forward per layer, ~1.1 GB/layer less")
+    ap.add_argument("--no-pdl", action="store_true", help="launch every kernel fully serialized (vvae_debug_set(11, 1)) "
+                    "instead of with programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
                     "of replaying the captured CUDA graph; N > 1 then overlaps the bucketed all-reduce with backward")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel-class time table to stderr")
@@ -257,6 +259,8 @@ def run_ours(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     _ffi.require_device()
+    if args.no_pdl:
+        _ffi.lib.vvae_debug_set(11, 1)
 
     S, Tn, B = args.size, args.frames, args.batch
     model = V.VideoVAE(S, S, 3, PROD["patch_size"], args.enc_depth, args.dec_depth, PROD["mlp_dim"], PROD["num_heads"],

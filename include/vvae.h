@@ -50,6 +50,8 @@ int vvae_device_ok(void);
 /* Debug/tuning knobs, all 0 by default (bring-up scripts only; never set by the product path).  Keys 0-6: grid size,
  * UMMA descriptor fields and the N-tile of the tcgen05 GEMM (csrc/gemm_sm100.cu); 8: force single-CTA GEMM tiles;
  * 9: keep short sequences (L <= 16) on the packed tcgen05 attention tiles instead of the one-warp kernels;
+ * 10: tcgen05 GEMM TIMING ablations, results are wrong (bit 1: no A-tile TMA loads, 2: no B-tile loads);
+ * 11: launch without programmatic dependent launch (every kernel fully serialized behind its predecessor);
  * 12: 192-column GEMM tiles for N = 768 dgrads (measured slower than 256: kept for the record);
  * 13: conv3d fwd/dgrad: one MMA per filter tap (round-1 kernels) instead of the kw taps packed into N;
  * 14: conv3d fwd/dgrad TIMING ablations, results are wrong (bit 1: no global stores, 2: epilogue releases the accumulator

@@ -168,6 +168,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // PDL (common.cuh): barrier init / TMEM allocation above overlap the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -358,7 +359,7 @@ static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
     attr_set.store(true, std::memory_order_release);
   }
   dim3 grid((unsigned)p.tiles, (unsigned)p.heads);
-  kern<<<grid, 192, SMEM, s>>>(mq, mk, mv, q);
+  launch_pdl(kern, grid, dim3(192), SMEM, s, mq, mk, mv, q);
   return check_launch("attn_fwd_sm100");
 }
 
@@ -443,6 +444,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // PDL (common.cuh)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -722,7 +724,7 @@ static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   }
   const long long tiles = PACKED ? p.tiles : (long long)p.n_outer * p.n_inner;
   dim3 grid((unsigned)tiles, (unsigned)p.heads);
-  kern<<<grid, 320, SMEM, s>>>(mq, mk, mv, md, q);
+  launch_pdl(kern, grid, dim3(320), SMEM, s, mq, mk, mv, md, q);
   return check_launch("attn_bwd_sm100");
 }
 

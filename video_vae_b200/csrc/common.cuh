@@ -40,6 +40,32 @@ inline cudaStream_t as_stream(vvae_stream_t s) { return reinterpret_cast<cudaStr
 int num_sms();  // cudaDevAttrMultiProcessorCount of the current device, queried once (api.cu); 148 on B200
 inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched through launch_pdl may begin while the previous kernel in the stream is still draining: its
+// prologue (barrier init, TMEM allocation, descriptor prefetch, smem staging of constants that no kernel writes) overlaps
+// the predecessor's tail, and pdl_wait() -- which every such kernel executes BEFORE its first access to global memory
+// another kernel may have produced -- blocks until the predecessor has completed and flushed.  pdl_launch_dependents()
+// in a kernel whose CTAs are all resident lets the successor's CTAs take over SMs as they become free.  Inside a captured
+// CUDA graph these launches become programmatic-dependency edges.  vvae_debug_set(11, 1) turns the attribute off.
+extern long long g_dbg[16];
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_dbg[11] ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- scalar conversion ----
 template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }

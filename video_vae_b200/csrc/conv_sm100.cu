@@ -394,8 +394,10 @@ conv_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const ConvParams q)
     sm100::mbar_init(w_bar, 1);
     sm100::fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < p.nNT * NT; i += blockDim.x) s_bias[i] = (q.bias && i < p.Cout) ? __ldg(q.bias + i) : 0.f;
+  pdl_launch_dependents();   // PDL (common.cuh): every CTA of this grid is resident
   if (warp == 1) sm100::tmem_alloc<TMEM_COLS>(tmem_slot);
+  pdl_wait();                // the bias below may be the previous kernel's (optimizer) output
+  for (int i = threadIdx.x; i < p.nNT * NT; i += blockDim.x) s_bias[i] = (q.bias && i < p.Cout) ? __ldg(q.bias + i) : 0.f;
   sm100::tc_fence_before();
   __syncthreads();
   sm100::tc_fence_after();
@@ -817,7 +819,7 @@ int conv_tc_launch(const vvae_conv_args& a, int which, cudaStream_t s) {
     }
   }
   const int grid = std::min(p.slide ? p.units : p.total_tiles, num_sms());
-  kern<<<grid, CONV_THREADS, p.smem_bytes, s>>>(tm, q);
+  launch_pdl(kern, dim3(grid), dim3(CONV_THREADS), (size_t)p.smem_bytes, s, tm, q);
   return check_launch("conv_sm100");
 }
 

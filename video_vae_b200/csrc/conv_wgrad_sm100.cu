@@ -130,6 +130,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();      // every CTA of this grid is resident
   // zero all operand memory once: the pads around every dy row must read as zeros for the whole kernel, and the
   // K-padding over-reads of x must be finite
   {
@@ -153,6 +154,7 @@ conv_wgrad_sm100_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                   // PDL (common.cuh): the smem zero-fill / TMEM allocation above overlap the previous kernel
 
   const int group = blockIdx.x % p.ngroups, cta_in_group = blockIdx.x / p.ngroups;
   const int dh_groups = KH / NDH;
@@ -355,7 +357,7 @@ int conv_wgrad_tc_launch(const vvae_conv_args& a, cudaStream_t s) {
     }
   }
   const int grid = p.ngroups * p.ctas_per_group;
-  kern<<<grid, 192, p.smem_bytes, s>>>(tx, ty, q);
+  launch_pdl(kern, dim3(grid), dim3(192), (size_t)p.smem_bytes, s, tx, ty, q);
   return check_launch("conv_wgrad_sm100");
 }
 

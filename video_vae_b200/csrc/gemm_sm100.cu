@@ -22,7 +22,7 @@
 namespace vvae {
 
 // ---- debug / tuning knobs (vvae_debug_set) ----
-long long g_dbg[16] = {0};
+long long g_dbg[16] = {0};   // (declared in common.cuh)
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -278,6 +278,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+  pdl_launch_dependents();   // every CTA of this grid is resident: the next kernel may move in as SMs free up
 
   if (warp == 0 && lane == 0) {
     sm100::tma_prefetch_desc(&tma_a);
@@ -300,6 +301,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_wait();                // prologue done; from here on global memory of the previous kernel is read / written
 
   const int tiles_mn = p.m_tiles * p.n_tiles;
   const int total_tiles = tiles_mn * p.splits;
@@ -672,11 +674,13 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   cfg.blockDim = dim3(MODE == MODE_BSUM ? 384 : 320);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_dbg[11] ? 1 : 2;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tai, tao, p);
   if (e != cudaSuccess) {
     set_error("gemm_sm100 launch: %s", cudaGetErrorString(e));

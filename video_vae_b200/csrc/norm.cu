@@ -14,6 +14,8 @@ layernorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __
                      long long rows, int D, float eps) {
   constexpr int V = Vec16<T>::N;
   constexpr int UR = 2;                     // rows in flight per warp
+  pdl_launch_dependents();                  // (grid = resident blocks)
+  pdl_wait();
   extern __shared__ float ln_sm[];          // gamma[D] | beta[D]: read back as 16-byte broadcasts-free vectors
   float* sg = ln_sm;
   float* sb = ln_sm + D;
@@ -95,6 +97,8 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const T* __restrict__ dres,
                      T* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int D) {
   constexpr int V = Vec16<T>::N;
+  pdl_launch_dependents();        // (grid = resident blocks)
+  pdl_wait();
   extern __shared__ float red[];  // [2][D]
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -353,6 +357,8 @@ qknorm_rope_fwd_hd64_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out
                             const float* __restrict__ k_scale, const bf16* __restrict__ cos_tab,
                             const bf16* __restrict__ sin_tab, long long rows, int H, long long pos_div, int pos_mod,
                             float eps) {
+  pdl_launch_dependents();                      // (grid = resident blocks)
+  pdl_wait();
   const int cpr = 16 * H;                       // 16-byte chunks of q|k per row
   const int c = threadIdx.x % cpr, rpi = blockDim.x / cpr;
   const int part = c & 7;
@@ -423,6 +429,8 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
                             float* __restrict__ dbias, long long rows, int H, long long pos_div, int pos_mod, float eps) {
   __shared__ float red[2][64];
   __shared__ float redb[2048];                   // column sums of the produced d(q|k) (the QKV bias gradient), [16*H*8]
+  pdl_launch_dependents();                       // (grid = resident blocks)
+  pdl_wait();
   const int cpr = 16 * H;
   const int c = threadIdx.x % cpr, rpi = blockDim.x / cpr;
   const int part = c & 7;
@@ -932,7 +940,8 @@ static int ln_fwd_dispatch(const void* x, void* y, const float* gamma, const flo
 #define LN_FWD(NC)                                                                                               \
   do {                                                                                                           \
     const int blocks = resident_grid(layernorm_fwd_kernel<T, NC>, 256, smem, cdiv(rows, 16));                    \
-    layernorm_fwd_kernel<T, NC><<<blocks, 256, smem, s>>>((const T*)x, (T*)y, gamma, beta, mean, rstd, rows, D, eps); \
+    launch_pdl(layernorm_fwd_kernel<T, NC>, dim3(blocks), dim3(256), smem, s, (const T*)x, (T*)y, gamma, beta, mean, rstd, \
+               rows, D, eps);                                                                                    \
   } while (0)
   if (need <= 1) LN_FWD(1);
   else if (need <= 2) LN_FWD(2);
@@ -958,8 +967,8 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, con
 #define LN_BWD(NC)                                                                                              \
   do {                                                                                                          \
     const int blocks = resident_grid(layernorm_bwd_kernel<T, NC>, 256, smem, cdiv(rows, 8));                    \
-    layernorm_bwd_kernel<T, NC><<<blocks, 256, smem, s>>>((const T*)dy, (const T*)x, mean, rstd, gamma,         \
-                                                          (const T*)dres, (T*)dx, dgamma, dbeta, rows, D);      \
+    launch_pdl(layernorm_bwd_kernel<T, NC>, dim3(blocks), dim3(256), smem, s, (const T*)dy, (const T*)x, mean, rstd,    \
+               gamma, (const T*)dres, (T*)dx, dgamma, dbeta, rows, D);                                          \
   } while (0)
   if (need <= 1) LN_BWD(1);
   else if (need <= 2) LN_BWD(2);
@@ -1020,9 +1029,8 @@ int vvae_qknorm_rope_fwd(const void* qkv, void* qk_out, const float* q_scale, co
     static int occ_grid = 0;
     if (!occ_grid) occ_grid = resident_grid(qknorm_rope_fwd_hd64_kernel, 256, 0, 1 << 30);
     const int blocks = (int)std::min<long long>(cdiv(rows, rpi), occ_grid);
-    qknorm_rope_fwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
-        (const bf16*)qkv, (bf16*)qk_out, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, rows, heads, pos_div,
-        pos_mod, eps);
+    launch_pdl(qknorm_rope_fwd_hd64_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), (const bf16*)qkv, (bf16*)qk_out,
+               q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, rows, heads, pos_div, pos_mod, eps);
     return check_launch("qknorm_rope_fwd");
   }
   const long long nvec = rows * 2 * heads;
@@ -1045,9 +1053,9 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
     static int occ_grid = 0;
     if (!occ_grid) occ_grid = resident_grid(qknorm_rope_bwd_hd64_kernel, 256, 0, 1 << 30);
     const int blocks = (int)std::min<long long>(cdiv(rows, rpi), occ_grid);
-    qknorm_rope_bwd_hd64_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
-        (bf16*)dqkv, (const bf16*)qkv, q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, dq_scale, dk_scale,
-        dbias_qk, rows, heads, pos_div, pos_mod, eps);
+    launch_pdl(qknorm_rope_bwd_hd64_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), (bf16*)dqkv, (const bf16*)qkv,
+               q_scale, k_scale, (const bf16*)cos_tab, (const bf16*)sin_tab, dq_scale, dk_scale, dbias_qk, rows, heads,
+               pos_div, pos_mod, eps);
     return check_launch("qknorm_rope_bwd");
   }
   const long long nvec = rows * 2 * heads;
