@@ -39,7 +39,12 @@ enum vvae_epilogue {
   VVAE_EPI_NONE = 0,     /* C = acc (+bias)                                         */
   VVAE_EPI_SILU = 1,     /* aux_out = acc+bias (pre-activation); C = silu(acc+bias) */
   VVAE_EPI_RESIDUAL = 2, /* C = acc + bias + aux_in            (aux_in may alias C) */
-  VVAE_EPI_DSILU = 3     /* C = acc * silu'(aux_in)   (dgrad through MLP SiLU)      */
+  VVAE_EPI_DSILU = 3,    /* C = acc * silu'(aux_in)   (dgrad through MLP SiLU)      */
+  VVAE_EPI_QKNORM_ROPE = 4 /* the QKV projection of train/layers.py:160-166 in one call: C = acc + bias = q|k|v
+                            * [M, 3*heads*hd] and aux_out [M, 2*heads*hd] = rope(LN(q)) | rope(LN(k)) (per-head LayerNorm
+                            * without bias, eps qk_eps, then RoPE at position (row / rope_pos_div) % rope_pos_mod); the
+                            * tcgen05 kernel does it in its epilogue (one 64-column chunk = one head in one thread's
+                            * registers), every other case runs the GEMM and then vvae_qknorm_rope_fwd */
 };
 enum vvae_backend { VVAE_BACKEND_AUTO = 0, VVAE_BACKEND_SIMT = 1, VVAE_BACKEND_TCGEN05 = 2 };
 
@@ -88,6 +93,12 @@ typedef struct vvae_gemm_args {
   int backend;
   float* bsum_accum; /* optional, fp32 [N]: += sum_k op(B)[k, n].  For a weight gradient X^T . dY this is the Linear's bias
                       * gradient, summed from the dY tiles while they sit in shared memory (no second pass over dY). */
+  /* VVAE_EPI_QKNORM_ROPE only (arguments as in vvae_qknorm_rope_fwd) */
+  const float* qk_q_scale; const float* qk_k_scale;
+  const void* rope_cos; const void* rope_sin;
+  long long rope_pos_div; int rope_pos_mod;
+  int qk_heads, qk_hd;
+  float qk_eps;
 } vvae_gemm_args;
 int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream);
 /* 1 if vvae_gemm would run these arguments on the tcgen05 kernel, 0 if on the generic SIMT kernel. */

@@ -79,6 +79,45 @@ def test_gemm_all_modes_fp32_and_bf16(V):
     assert rel_err(o_tc, ref) < 1e-5 and rel_err(o_si, ref) < 1e-5
 
 
+@pytest.mark.parametrize("rows,heads,pos_div,pos_mod", [(1024, 8, 1, 256), (4096, 8, 256, 16), (640, 2, 1, 64), (300, 4, 7, 5)])
+def test_qkv_projection_fused_epilogue_matches_separate_kernels(V, rows, heads, pos_div, pos_mod):
+    """VVAE_EPI_QKNORM_ROPE: the QKV projection with the per-head QK-LayerNorm + RoPE (train/layers.py:160-166) in the
+    tcgen05 GEMM's epilogue against (a) the GEMM followed by the stand-alone vvae_qknorm_rope_fwd kernel and (b) the
+    oracle's LayerNorm / RotaryEmbedding on the same bf16 projection.  Spatial (pos = row % hw) and temporal
+    (pos = (row / hw) % t) position rules, ragged row counts, 2 / 4 / 8 heads."""
+    from oracle import nn as onn
+    from video_vae_b200 import ops
+    hd, D = 64, 256
+    Q = heads * hd
+    g = _gen(17)
+    h = torch.randn(rows, D, generator=g).bfloat16().cuda()
+    w = (torch.randn(D, 3 * Q, generator=g) * 0.08).bfloat16().cuda()
+    b = torch.randn(3 * Q, generator=g).cuda()
+    qs = (1.0 + 0.2 * torch.randn(hd, generator=g)).cuda()
+    ks = (1.0 + 0.2 * torch.randn(hd, generator=g)).cuda()
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd))
+    emb = torch.cat([torch.arange(pos_mod).float()[:, None] * inv[None]] * 2, -1)
+    cos, sin = torch.cos(emb).bfloat16().cuda().contiguous(), torch.sin(emb).bfloat16().cuda().contiguous()
+    qkv_f, qk_f = ops.qkv_projection(h, w, b, qs, ks, cos, sin, heads, hd, pos_div, pos_mod)
+    qkv_s = ops.gemm(h, w, bias=b)
+    qk_s = ops.qknorm_rope_fwd(qkv_s, qs, ks, cos, sin, heads, hd, pos_div, pos_mod)
+    assert torch.equal(qkv_f, qkv_s)                                      # the projection itself is unchanged
+    # same arithmetic, different summation order of the 64-element statistics: at most a bf16 ulp apart
+    assert rel_err(qk_f, qk_s) < 8e-3 and rel_l2(qk_f, qk_s) < 1e-3
+    # oracle: LayerNorm(64, no bias) per head on the bf16 projection, tables rounded to bf16 (layers.py:124-127)
+    x = qkv_s.float().cpu()[:, :2 * Q].reshape(rows, 2, heads, hd)
+    mu = x.mean(-1, keepdim=True)
+    var = (x * x).mean(-1, keepdim=True) - mu * mu
+    sc = torch.stack([qs.cpu(), ks.cpu()])[None, :, None, :]
+    xn = ((x - mu) * torch.rsqrt(var.clamp_min(0) + 1e-6) * sc).bfloat16().float()
+    pos = (torch.arange(rows) // pos_div) % pos_mod
+    c, s_ = cos.float().cpu()[pos][:, None, None, :], sin.float().cpu()[pos][:, None, None, :]
+    rot = torch.cat([-xn[..., hd // 2:], xn[..., :hd // 2]], -1)
+    ref = (xn * c).bfloat16().float() + (rot * s_).bfloat16().float()
+    assert rel_err(qk_f, ref.reshape(rows, 2 * Q)) < 2e-2
+    assert rel_l2(qk_f, ref.reshape(rows, 2 * Q)) < 5e-3
+
+
 def test_rank1_linear_kernels_match_generic_gemm(V):
     """The frame-selection head's Linear 96 -> 1 over every token (train/model.py:56-58) and its two gradients run on
     dedicated streaming kernels (small_linear.cu rank1_*); same calls on the generic GEMM and an fp32 reference."""

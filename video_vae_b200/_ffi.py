@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VVAE_LIB", os.path.join(_HERE, "libvvae.so"))
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_SILU, EPI_RESIDUAL, EPI_DSILU = 0, 1, 2, 3
+EPI_NONE, EPI_SILU, EPI_RESIDUAL, EPI_DSILU, EPI_QKNORM_ROPE = 0, 1, 2, 3, 4
 BACKEND_AUTO, BACKEND_SIMT, BACKEND_TCGEN05 = 0, 1, 2
 
 
@@ -42,7 +42,9 @@ class GemmArgs(C.Structure):
                 ("aux_out", vp), ("ld_aux_out", ll),
                 ("accumulate", i32),
                 ("backend", i32),
-                ("bsum_accum", vp)]
+                ("bsum_accum", vp),
+                ("qk_q_scale", vp), ("qk_k_scale", vp), ("rope_cos", vp), ("rope_sin", vp),
+                ("rope_pos_div", ll), ("rope_pos_mod", i32), ("qk_heads", i32), ("qk_hd", i32), ("qk_eps", f32)]
 
 
 class AttnArgs(C.Structure):

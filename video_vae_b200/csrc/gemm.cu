@@ -109,6 +109,24 @@ extern "C" int vvae_gemm(const vvae_gemm_args* args, vvae_stream_t stream) {
   VVAE_REQUIRE((a.epilogue != VVAE_EPI_RESIDUAL && a.epilogue != VVAE_EPI_DSILU) || a.aux_in,
                "vvae_gemm: epilogue %d needs aux_in", a.epilogue);
   cudaStream_t s = as_stream(stream);
+  if (a.epilogue == VVAE_EPI_QKNORM_ROPE) {
+    VVAE_REQUIRE(a.aux_out && a.qk_q_scale && a.qk_k_scale && a.rope_cos && a.rope_sin && a.qk_heads > 0 && a.qk_hd > 0 &&
+                     a.N == 3 * a.qk_heads * a.qk_hd && a.ld_aux_out >= 2LL * a.qk_heads * a.qk_hd && !a.accumulate &&
+                     a.out_dtype == a.dtype && a.ldc == a.N,
+                 "vvae_gemm: VVAE_EPI_QKNORM_ROPE needs N = 3*heads*hd, a dense C, aux_out [M, 2*heads*hd], scales and tables");
+    if (!(sm100_gemm_supported(a) && a.backend != VVAE_BACKEND_SIMT)) {
+      // generic route: the projection, then the stand-alone QK-LayerNorm + RoPE kernel over its q|k columns
+      VVAE_REQUIRE(a.ld_aux_out == 2LL * a.qk_heads * a.qk_hd, "vvae_gemm: VVAE_EPI_QKNORM_ROPE generic route needs a dense aux_out");
+      vvae_gemm_args b = a;
+      b.epilogue = VVAE_EPI_NONE;
+      b.aux_out = nullptr;
+      int rc = vvae_gemm(&b, stream);
+      if (rc) return rc;
+      return vvae_qknorm_rope_fwd(a.C, a.aux_out, a.qk_q_scale, a.qk_k_scale, a.rope_cos, a.rope_sin, a.M, a.qk_heads,
+                                  a.qk_hd, a.rope_pos_div, a.rope_pos_mod, a.qk_eps, a.dtype, stream);
+    }
+    return sm100_gemm(a, s);
+  }
   const bool tc_ok = sm100_gemm_supported(a);
   if (a.bsum_accum) {
     VVAE_REQUIRE(!a.transB, "vvae_gemm: bsum_accum needs op(B) = B (rows = contraction index)");

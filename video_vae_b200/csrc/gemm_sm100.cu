@@ -86,7 +86,8 @@ constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB per CTA
 constexpr int STG_BYTES = 128 * 128;        // one epilogue staging buffer: 128 rows x 64 bf16, 128B-swizzled
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
-constexpr int MODE_BSUM = 4;                // internal: weight-gradient GEMM that also sums the columns of its B operand // shared::cluster address of the same offset in the even CTA of a pair
+constexpr int MODE_QKN = VVAE_EPI_QKNORM_ROPE;   // 4: QKV projection with per-head LayerNorm + RoPE of q|k in the epilogue
+constexpr int MODE_BSUM = 100;                // internal: weight-gradient GEMM that also sums the columns of its B operand // shared::cluster address of the same offset in the even CTA of a pair
 
 struct Sm100Params {
   int M, N;                // output extent
@@ -103,6 +104,9 @@ struct Sm100Params {
   // descriptor encodings (bytes); overridable through vvae_debug_set for bring-up
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
   int dbg;                 // vvae_debug_set(10): TIMING ablations, wrong results (1: skip the A-tile TMA loads, 2: skip B)
+  // MODE_QKN
+  const float* qk_qs; const float* qk_ks; const bf16* rope_cos; const bf16* rope_sin;
+  long long pos_div; int pos_mod; int qk_cols; float qk_eps;
 };
 
 // HEAVY epilogues (residual / dSiLU read an aux tile, SiLU writes two tiles) get 4 extra staging buffers: a 4-deep ring of
@@ -112,7 +116,7 @@ template <int BN, int CG, bool HEAVY> struct StageCfg {
   static constexpr int B_STAGE_BYTES = (BN / CG) * BK * 2;          // per CTA
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
   static constexpr int EPI_BYTES = (HEAVY ? 6 : 2) * STG_BYTES;
-  static constexpr int BAR_BYTES = 320 + 256 * 4;   // barriers + the current tile's bias slice
+  static constexpr int BAR_BYTES = 320 + 256 * 4 + 128 * 4;   // barriers + the current tile's bias slice + q|k LayerNorm scales
   static constexpr int BUDGET = 232448 - 1024 - BAR_BYTES - EPI_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -249,7 +253,7 @@ __device__ __forceinline__ float fast_dsilu(float x) {
 }
 
 template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(MODE == MODE_QKN ? 192 : 384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_ai,
                   const __grid_constant__ CUtensorMap tma_ao, Sm100Params p) {
@@ -274,6 +278,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
   uint64_t* mma_done = bars + 2 * STAGES + 9;   // [STAGES] (BSUM): the MMAs reading stage s have completed
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 320);   // [256]
+  float* s_qks = s_bias + 256;                                                         // [2][64] (MODE_QKN)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
@@ -291,7 +296,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       sm100::mbar_init(&tmem_full[i], 1);
-      sm100::mbar_init(&tmem_empty[i], 8 * CG);
+      sm100::mbar_init(&tmem_empty[i], (MODE == MODE_QKN ? 4 : 8) * CG);
     }
     for (int i = 0; i < AUXR; ++i) sm100::mbar_init(&aux_full[i], 1);
     sm100::fence_barrier_init();
@@ -435,6 +440,119 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       }
     }
+  } else if constexpr (MODE == MODE_QKN) {
+    // ===================== epilogue of the QKV projection (train/layers.py:160-166) =====================
+    // Four warps, one thread per accumulator row; a 64-column chunk is ONE head (hd = 64), so the per-head LayerNorm
+    // (fp32 statistics of the bf16-rounded projection, fast variance, scale only) and RoPE (packed bf16 arithmetic, the
+    // rotate_half partner 32 columns away) are thread-local.  Output 1 (C): q|k|v as projected (saved for backward,
+    // v feeds attention); output 2 (aux_out): rope(LN(q)) | rope(LN(k)).  Same arithmetic, instruction for instruction,
+    // as qknorm_rope_fwd_hd64_kernel -- which this makes unnecessary: one read of q|k (67 MB per attention) less.
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int etid = threadIdx.x - 64;           // 0..127
+    const uint32_t sw = (uint32_t)(r & 7);
+    auto qkn_bar = []() { asm volatile("bar.sync 2, 128;" ::: "memory"); };
+    for (int j = etid; j < 128; j += 128) s_qks[j] = j < 64 ? __ldg(p.qk_qs + j) : __ldg(p.qk_ks + j - 64);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t g = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int mn = tile % tiles_mn;
+      const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (mn % p.n_tiles) * BN;
+      for (int j = etid; j < BN; j += 128) s_bias[j] = (p.bias && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      qkn_bar();
+      const long long grow = min((long long)m0 + r, (long long)p.M - 1);
+      const int pos = (int)(((unsigned long long)grow / (unsigned long long)p.pos_div) % (unsigned)p.pos_mod);
+      const uint4* cosp = reinterpret_cast<const uint4*>(p.rope_cos + (long long)pos * 64);
+      const uint4* sinp = reinterpret_cast<const uint4*>(p.rope_sin + (long long)pos * 64);
+      sm100::mbar_wait(&tmem_full[acc], acc_phase);
+      sm100::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c, ++g) {
+        const int nc = n0 + 64 * c;
+        const uint32_t b = g & 1;
+        const bool is_qk = nc < p.qk_cols;                      // warp-uniform
+        uint32_t pk[32], y[32];
+        {
+          uint32_t rr0[32], rr1[32];
+          sm100::tmem_ld_32x32(taddr + c * 64, rr0);
+          sm100::tmem_ld_32x32(taddr + c * 64 + 32, rr1);
+          sm100::tmem_ld_wait();
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + c * 64);
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 bb = b4[j >> 2];
+            const uint32_t* src = j < 32 ? rr0 + j : rr1 + (j - 32);
+            pk[j >> 1] = pack_bf16x2(__uint_as_float(src[0]) + bb.x, __uint_as_float(src[1]) + bb.y);
+            pk[(j >> 1) + 1] = pack_bf16x2(__uint_as_float(src[2]) + bb.z, __uint_as_float(src[3]) + bb.w);
+          }
+        }
+        if (is_qk) {
+          float s = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float f0 = __uint_as_float(pk[j] << 16), f1 = __uint_as_float(pk[j] & 0xffff0000u);
+            s += f0 + f1;
+            s2 = fmaf(f0, f0, fmaf(f1, f1, s2));
+          }
+          const float mu = s * (1.f / 64.f);
+          const float rs = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + p.qk_eps);
+          const float* sc = s_qks + (nc < (p.qk_cols >> 1) ? 0 : 64);
+          uint32_t xn[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float f0 = __uint_as_float(pk[j] << 16), f1 = __uint_as_float(pk[j] & 0xffff0000u);
+            xn[j] = pack_bf16x2((f0 - mu) * (rs * sc[2 * j]), (f1 - mu) * (rs * sc[2 * j + 1]));
+          }
+          // y = x*cos + rotate_half(x)*sin in bf16 (each product and the sum rounded, as the reference's bf16 ops do)
+#pragma unroll
+          for (int v4 = 0; v4 < 8; ++v4) {
+            const uint4 cv = __ldg(cosp + v4), sv = __ldg(sinp + v4);
+            const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw4[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int j = v4 * 4 + t;                                   // bf16 pair index: elements 2j, 2j+1
+              const uint32_t rot = j < 16 ? (xn[j + 16] ^ 0x80008000u) : xn[j - 16];
+              const __nv_bfloat162 a2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&xn[j]),
+                                                *reinterpret_cast<const __nv_bfloat162*>(&cw[t]));
+              const __nv_bfloat162 b2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&rot),
+                                                *reinterpret_cast<const __nv_bfloat162*>(&sw4[t]));
+              const __nv_bfloat162 y2 = __hadd2(a2, b2);
+              y[j] = *reinterpret_cast<const uint32_t*>(&y2);
+            }
+          }
+        }
+        if (etid == 0) bulk_wait_read<1>();
+        qkn_bar();
+        uint8_t* orow = stg_out + b * STG_BYTES + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(orow + (((uint32_t)ch ^ sw) << 4)) =
+              make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        if (is_qk) {
+          uint8_t* prow = stg_aux + b * STG_BYTES + r * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<uint4*>(prow + (((uint32_t)ch ^ sw) << 4)) =
+                make_uint4(y[4 * ch], y[4 * ch + 1], y[4 * ch + 2], y[4 * ch + 3]);
+        }
+        sm100::fence_proxy_async();
+        qkn_bar();
+        if (etid == 0) {
+          if (nc < p.N && m0 < p.M) {
+            tma_store_2d(&tma_c, stg_out + b * STG_BYTES, nc, m0);
+            if (is_qk) tma_store_2d(&tma_ao, stg_aux + b * STG_BYTES, nc, m0);
+          }
+          bulk_commit();
+        }
+      }
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader<CG>(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (etid == 0) bulk_wait_all();
   } else {
     // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
     const int quarter = warp & 3;
@@ -595,6 +713,10 @@ bool sm100_gemm_supported(const vvae_gemm_args& a) {
   if (a.accumulate && a.out_dtype != VVAE_F32) return false;
   if (a.out_dtype == VVAE_F32 && a.epilogue != VVAE_EPI_NONE) return false;   // fused epilogues are bf16-out only
   if (a.transA && a.epilogue != VVAE_EPI_NONE) return false;
+  if (a.epilogue == VVAE_EPI_QKNORM_ROPE) {   // one 64-column epilogue chunk must be one head; tables in bf16, 16-byte rows
+    if (a.qk_hd != 64 || a.transB || !a.aux_out || a.N != 3 * a.qk_heads * 64 || a.M < 256) return false;
+    if (((uintptr_t)a.rope_cos % 16) || ((uintptr_t)a.rope_sin % 16) || a.rope_pos_div <= 0 || a.rope_pos_mod <= 0) return false;
+  }
   // MN-major operands are fetched in 64-wide boxes along M / N
   if (a.transA && (a.M % 8)) return false;
   return true;
@@ -636,6 +758,10 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   p.tma_epi = p.out_f32 ? 0 : 1;
   p.bsum = a.bsum_accum;
   p.dbg = (int)g_dbg[10];
+  p.qk_qs = a.qk_q_scale; p.qk_ks = a.qk_k_scale;
+  p.rope_cos = (const bf16*)a.rope_cos; p.rope_sin = (const bf16*)a.rope_sin;
+  p.pos_div = a.rope_pos_div > 0 ? a.rope_pos_div : 1; p.pos_mod = a.rope_pos_mod > 0 ? a.rope_pos_mod : 1;
+  p.qk_cols = 2 * a.qk_heads * a.qk_hd; p.qk_eps = a.qk_eps;
   tc = ta; tai = ta; tao = ta;   // placeholders for maps a mode does not use
   if (p.tma_epi) {
     if ((rc = encode_tmap_2d_bf16(&tc, a.C, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldc * 2, 64, 128, 128))) return rc;
@@ -644,6 +770,10 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
         return rc;
     if (a.epilogue == VVAE_EPI_SILU && a.aux_out)
       if ((rc = encode_tmap_2d_bf16(&tao, a.aux_out, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ld_aux_out * 2, 64, 128, 128)))
+        return rc;
+    if (a.epilogue == VVAE_EPI_QKNORM_ROPE)
+      if ((rc = encode_tmap_2d_bf16(&tao, a.aux_out, (uint64_t)(2 * a.qk_heads * a.qk_hd), (uint64_t)a.M,
+                                    (uint64_t)a.ld_aux_out * 2, 64, 128, 128)))
         return rc;
   }
   // K-major SW128: 8-row groups 1024 B apart, K advance 32 B inside the swizzled row.
@@ -671,7 +801,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   int clusters = std::min(total, g_dbg[0] ? (int)g_dbg[0] : n_clusters);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
-  cfg.blockDim = dim3(MODE == MODE_BSUM ? 384 : 320);
+  cfg.blockDim = dim3(MODE == MODE_BSUM ? 384 : (MODE == MODE_QKN ? 192 : 320));
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
@@ -706,6 +836,9 @@ static int dispatch_major(const vvae_gemm_args& a, cudaStream_t s) {
       return b_mn ? launch_sm100<BN, CG, false, true, 2>(a, s) : launch_sm100<BN, CG, false, false, 2>(a, s);
     case VVAE_EPI_DSILU:
       return b_mn ? launch_sm100<BN, CG, false, true, 3>(a, s) : launch_sm100<BN, CG, false, false, 3>(a, s);
+    case VVAE_EPI_QKNORM_ROPE:
+      if (!b_mn) { set_error("gemm_sm100: VVAE_EPI_QKNORM_ROPE expects the Flax (in,out) weight layout"); return VVAE_ERR_UNSUPPORTED; }
+      return launch_sm100<BN, CG, false, true, MODE_QKN>(a, s);
     default:
       return b_mn ? launch_sm100<BN, CG, false, true, 0>(a, s) : launch_sm100<BN, CG, false, false, 0>(a, s);
   }

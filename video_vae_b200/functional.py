@@ -183,9 +183,9 @@ class AttnBlockFn(Function):
             x2 = ops.cast(x2, dtp)
         Q = cfg.heads * cfg.hd
         h, mean, rstd = ops.layernorm_fwd(x2, ln_g.detach(), ln_b.detach())
-        qkv = ops.gemm(h, shadow(w_qkv, dtp), bias=b_qkv.detach())
-        qk = ops.qknorm_rope_fwd(qkv, q_scale.detach(), k_scale.detach(), cos, sin, cfg.heads, cfg.hd, cfg.pos_div,
-                                 cfg.pos_mod)
+        # projection + per-head QK-LayerNorm + RoPE in one call (tcgen05 path: in the GEMM epilogue)
+        qkv, qk = ops.qkv_projection(h, shadow(w_qkv, dtp), b_qkv.detach(), q_scale.detach(), k_scale.detach(), cos, sin,
+                                     cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod)
         o, lse = ops.attn_fwd(cfg.geom, cfg.heads, cfg.hd, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], cfg.mask, cfg.scale)
         if cfg.residual:
             y = ops.gemm(o, shadow(w_o, dtp), bias=b_o.detach(), epilogue=EPI_RESIDUAL, aux_in=x2)

@@ -7,7 +7,7 @@ import ctypes as C
 
 import torch
 
-from ._ffi import (BACKEND_AUTO, BACKEND_SIMT, BF16, EPI_NONE, EPI_RESIDUAL, AttnArgs, ConvArgs, GemmArgs,
+from ._ffi import (EPI_QKNORM_ROPE, BACKEND_AUTO, BACKEND_SIMT, BF16, EPI_NONE, EPI_RESIDUAL, AttnArgs, ConvArgs, GemmArgs,
                    check, dt, lib, ptr, stream)
 
 LN_EPS = 1e-6
@@ -75,9 +75,11 @@ def colsum_accum(x2d, out):
 
 
 def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=None, epilogue=EPI_NONE, aux_in=None,
-         aux_out=None, accumulate=False, backend=BACKEND_AUTO, bsum=None):
+         aux_out=None, accumulate=False, backend=BACKEND_AUTO, bsum=None, qknorm=None):
     """C = epilogue(op(A) @ op(B)); A, B 2-D with unit inner stride (views with a row stride are fine).
-    bsum (fp32 [N], optional) += column sums of B: the bias gradient of a Linear, fused into its weight-gradient GEMM."""
+    bsum (fp32 [N], optional) += column sums of B: the bias gradient of a Linear, fused into its weight-gradient GEMM.
+    qknorm = (q_scale, k_scale, cos, sin, heads, hd, pos_div, pos_mod) with epilogue=EPI_QKNORM_ROPE: the QKV
+    projection; aux_out [M, 2*heads*hd] receives rope(LN(q)) | rope(LN(k))."""
     assert A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1 and A.dtype == B.dtype
     M, K = (A.shape[1], A.shape[0]) if transA else (A.shape[0], A.shape[1])
     Kb, N = (B.shape[1], B.shape[0]) if transB else (B.shape[0], B.shape[1])
@@ -92,6 +94,10 @@ def gemm(A, B, *, transA=False, transB=False, out=None, out_dtype=None, bias=Non
                  ptr(aux_in), aux_in.stride(0) if aux_in is not None else 0,
                  ptr(aux_out), aux_out.stride(0) if aux_out is not None else 0,
                  int(accumulate), backend, ptr(bsum))
+    if qknorm is not None:
+        qs, ks, cos, sin, heads, hd, pos_div, pos_mod = qknorm
+        a.qk_q_scale, a.qk_k_scale, a.rope_cos, a.rope_sin = ptr(qs), ptr(ks), ptr(cos), ptr(sin)
+        a.rope_pos_div, a.rope_pos_mod, a.qk_heads, a.qk_hd, a.qk_eps = pos_div, pos_mod, heads, hd, LN_EPS
     if PROFILE is not None:
         name = "gemm_tcgen05" if lib.vvae_gemm_uses_tcgen05(C.byref(a)) else "gemm_simt"
         with _Prof(name, 2.0 * M * N * K):
@@ -118,6 +124,16 @@ def layernorm_bwd(dy, x2d, mean, rstd, gamma, dres, dgamma, dbeta, out=None):
     check(lib.vvae_layernorm_bwd(ptr(dy), ptr(x2d), ptr(mean), ptr(rstd), ptr(gamma), ptr(dres), ptr(dx), ptr(dgamma),
                                  ptr(dbeta), rows, D, dt(x2d), stream()), "vvae_layernorm_bwd")
     return dx
+
+
+def qkv_projection(h, w, bias, q_scale, k_scale, cos, sin, heads, hd, pos_div, pos_mod):
+    """qkv = h @ w + bias  and  qk = rope(LN(q)) | rope(LN(k))  in ONE call (train/layers.py:160-166)."""
+    rows = h.shape[0]
+    qkv = torch.empty((rows, w.shape[1]), dtype=h.dtype, device=h.device)
+    qk = torch.empty((rows, 2 * heads * hd), dtype=h.dtype, device=h.device)
+    gemm(h, w, out=qkv, bias=bias, epilogue=EPI_QKNORM_ROPE, aux_out=qk,
+         qknorm=(q_scale, k_scale, cos, sin, heads, hd, pos_div, pos_mod))
+    return qkv, qk
 
 
 def qknorm_rope_fwd(qkv, q_scale, k_scale, cos, sin, heads, hd, pos_div, pos_mod):
