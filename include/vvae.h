@@ -55,7 +55,8 @@ int vvae_device_ok(void);
 /* Debug/tuning knobs, all 0 by default (bring-up scripts only; never set by the product path).  Keys 0-6: grid size,
  * UMMA descriptor fields and the N-tile of the tcgen05 GEMM (csrc/gemm_sm100.cu); 8: force single-CTA GEMM tiles;
  * 9: keep short sequences (L <= 16) on the packed tcgen05 attention tiles instead of the one-warp kernels;
- * 10: tcgen05 GEMM TIMING ablations, results are wrong (bit 1: no A-tile TMA loads, 2: no B-tile loads);
+ * 10: tcgen05 GEMM TIMING ablations, results are wrong (bit 1: no A-tile TMA loads, 2: no B-tile loads, 4: no loads and
+ *     the issuer never waits for operands, 8: accumulators never drained; 16: record counters for vvae_debug_get);
  * 11: launch without programmatic dependent launch (every kernel fully serialized behind its predecessor);
  * 12: 192-column GEMM tiles for N = 768 dgrads (measured slower than 256: kept for the record);
  * 13: conv3d fwd/dgrad: one MMA per filter tap (round-1 kernels) instead of the kw taps packed into N;
@@ -64,6 +65,9 @@ int vvae_device_ok(void);
  * 15: conv3d fwd/dgrad: stream the filter taps with every stage (round-1 behaviour) instead of keeping the whole
  *     weight image resident in shared memory. */
 int vvae_debug_set(int key, long long value);
+/* what = 0: counters of the last tcgen05 GEMM launched with vvae_debug_set(10, ... | 16): {clock64 ticks, globaltimer ns,
+ * MMAs issued} of CTA 0's issuing thread (synchronises the device). */
+int vvae_debug_get(int what, unsigned long long* out4);
 
 /* ---- elementwise plumbing ------------------------------------------------- */
 /* dst[i] = (dst_dtype) src[i]; the per-step fp32 -> bf16 parameter shadow copy. */

@@ -81,6 +81,7 @@ _SIGS = {
     "vvae_version": ([], i32),
     "vvae_device_ok": ([], i32),
     "vvae_debug_set": ([i32, ll], i32),
+    "vvae_debug_get": ([i32, C.POINTER(u64)], i32),
     "vvae_cast": ([vp, i32, vp, i32, ll, vp], i32),
     "vvae_fill_f32": ([vp, f32, ll, vp], i32),
     "vvae_colsum": ([vp, ll, ll, i32, vp, i32, vp], i32),
@@ -184,7 +185,7 @@ class AbiProfile:
     Each call is bracketed by two events on the current stream, so the numbers are device times of that entry point's
     kernels in an eager pass (launch gaps included in neither).  Not for use under CUDA-graph capture."""
 
-    _NO_STREAM = ("vvae_version", "vvae_device_ok", "vvae_debug_set", "vvae_gemm_uses_tcgen05", "vvae_conv3d_wprep_bytes",
+    _NO_STREAM = ("vvae_version", "vvae_device_ok", "vvae_debug_set", "vvae_debug_get", "vvae_gemm_uses_tcgen05", "vvae_conv3d_wprep_bytes",
                   "vvae_convT122_workspace_bytes", "vvae_sumsq_partials")
 
     def __init__(self, key=None):

@@ -81,6 +81,10 @@ int encode_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint
   return encode_tmap_nd_bf16(out, base, 2, dims, str, box, swizzle_bytes);
 }
 
+// debug counters written by CTA 0's MMA-issuing thread when vvae_debug_set(10, ...) has bit 16 set:
+// [0] clock64 ticks between its first and last MMA issue, [1] globaltimer ns for the same span, [2] MMAs issued
+__device__ unsigned long long g_gemm_dbg[4];
+
 // ------------------------------------------------------------------ device kernel
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB per CTA
@@ -323,6 +327,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (p.dbg & 4) continue;                 // ablation: the issuer does not wait for operands at all
           sm100::mbar_wait(&empty_bar[stage], phase ^ 1);
           if (cta_rank == 0)
             sm100::mbar_expect_tx(&full_bar[stage], (((p.dbg & 1) ? 0 : A_STAGE_BYTES) + ((p.dbg & 2) ? 0 : Cfg::B_STAGE_BYTES)) * CG);
@@ -356,29 +361,55 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      unsigned long long dbg_c0 = 0, dbg_t0 = 0, dbg_n = 0;
+      if (p.dbg & 16) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+      }
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int split = tile / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
-        sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (!(p.dbg & 8)) sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         sm100::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
+        // The issuing thread sits on the tensor pipe's critical path (the MMA queue is shallow: 179 cycles per 128-cycle
+        // MMA in the full kernel against 165 when the thread never waits, profiles/r02z_gemm_mma_rate.jsonl), so the
+        // poll of the NEXT stage's full barrier (~90 cycles even when the phase has completed) is started before the
+        // last MMA of the current stage is issued and only re-checked afterwards.
+        bool ready = (p.dbg & 4) ? true : sm100::mbar_test_wait(&full_bar[stage], phase);
         for (int kb = kb0; kb < kb1; ++kb) {
-          sm100::mbar_wait(&full_bar[stage], phase);
+          if (!ready) sm100::mbar_wait(&full_bar[stage], phase);
           sm100::tc_fence_after();
+          dbg_n += BK / UMMA_K;
           const uint32_t a_addr = sm100::smem_u32(smem_a + stage * A_STAGE_BYTES);
           const uint32_t b_addr = sm100::smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == STAGES) { nstage = 0; nphase ^= 1; }
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = sm100::make_smem_desc_sw128(a_addr + k * p.a_kadv, p.a_lbo, p.a_sbo);
             const uint64_t db = sm100::make_smem_desc_sw128(b_addr + k * p.b_kadv, p.b_lbo, p.b_sbo);
+            if (k == BK / UMMA_K - 1)   // (also valid across tiles: the stage ring does not care about tile borders)
+              ready = (p.dbg & 4) ? true : sm100::mbar_test_wait(&full_bar[nstage], nphase);
             umma_f16_cg<CG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_cg<CG>(BSUM ? &mma_done[stage] : &empty_bar[stage]);  // the MMAs have read the slot (both CTAs)
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          stage = nstage;
+          phase = nphase;
         }
         umma_commit_cg<CG>(&tmem_full[acc]);      // accumulator complete (signals both CTAs' epilogues)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if ((p.dbg & 16) && blockIdx.x == 0) {
+        // wait for the last MMA to finish: one more commit on a scratch use of tmem_full is not available, so time the
+        // issue span only (the queue is a few MMAs deep: the error is a few hundred cycles over ~10^5)
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        g_gemm_dbg[0] = clock64() - dbg_c0;
+        g_gemm_dbg[1] = t1 - dbg_t0;
+        g_gemm_dbg[2] = dbg_n;
       }
     }
   } else if (warp >= 10) {
@@ -589,6 +620,10 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       if (p.tma_epi && p.bias) {                 // this tile's bias slice -> smem (read back as broadcasts)
         for (int j = etid; j < BN; j += 256) bias_t[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
         epi_bar();
+      }
+      if (p.dbg & 8) {                           // ablation: the accumulators are never drained (nor waited for)
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
       }
       sm100::mbar_wait(&tmem_full[acc], acc_phase);
       sm100::tc_fence_after();
@@ -865,6 +900,12 @@ int sm100_gemm(const vvae_gemm_args& a, cudaStream_t s) {
 }
 
 }  // namespace vvae
+
+extern "C" int vvae_debug_get(int what, unsigned long long* out4) {
+  (void)what;
+  if (!out4) return VVAE_ERR_INVALID;
+  return cudaMemcpyFromSymbol(out4, vvae::g_gemm_dbg, 4 * sizeof(unsigned long long)) == cudaSuccess ? VVAE_OK : VVAE_ERR_CUDA;
+}
 
 extern "C" int vvae_debug_set(int key, long long value) {
   if (key < 0 || key >= 16) return VVAE_ERR_INVALID;
