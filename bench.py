@@ -427,15 +427,16 @@ def run_ours(args):
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     traffic, traffic_detail = None, None
     try:   # DRAM bytes of one representative launch of the dominant kernel, from the committed `ncu --set full` capture
-        nc = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_qkv_fwd_ncu.json")))
+        nc = json.load(open(os.path.join(ROOT, "profiles", "r02r_gemm_qkv_fwd_ncu.json")))
         # bytes (dram__bytes_read.sum + dram__bytes_write.sum) of that one launch; the capture reports Mbyte
         traffic = (float(nc["dram__bytes_read.sum"][0]) + float(nc["dram__bytes_write.sum"][0])) * 1e6
         traffic_detail = {
             "launch": "QKV projection forward, M=32768 N=1536 K=768 (algorithmic 153.4 MB: A 50.3 + B 2.4 + C 100.7; "
-                      "half of C is still L2-resident when the launch ends)",
+                      "half of C is still L2-resident when the launch ends); in the step this launch also writes the "
+                      "67 MB of rope(LN(q))|rope(LN(k)) from its epilogue",
             "algorithmic_bytes_per_launch": 153.4e6,
             "tensor_pipe_active_pct": float(nc["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]),
-            "source": "profiles/r01_gemm_qkv_fwd_ncu.json"}
+            "source": "profiles/r02r_gemm_qkv_fwd_ncu.json"}
     except (OSError, KeyError, ValueError):
         traffic, traffic_detail = None, None
     roofline = None
