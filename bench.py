@@ -64,6 +64,8 @@ def parse():
                     "(bf16 halves the bytes on NVLink; the fp32 default matches the reference's XLA all-reduce)")
     ap.add_argument("--recompute", action="store_true", help="per-layer activation recompute in every FactoredAttention "
                     "(the reference's @nnx.remat, train/layers.py:209): one extra forward per layer, ~1.1 GB/layer less")
+    ap.add_argument("--debug-set", action="append", default=[], metavar="KEY=VALUE",
+                    help="A/B switch: vvae_debug_set(KEY, VALUE) before the run (keys in include/vvae.h); not a bench line")
     ap.add_argument("--no-pdl", action="store_true", help="launch every kernel fully serialized (vvae_debug_set(11, 1)) "
                     "instead of with programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
@@ -261,6 +263,9 @@ def run_ours(args):
     _ffi.require_device()
     if args.no_pdl:
         _ffi.lib.vvae_debug_set(11, 1)
+    for kv in args.debug_set:
+        k, v = kv.split("=")
+        _ffi.lib.vvae_debug_set(int(k), int(v))
 
     S, Tn, B = args.size, args.frames, args.batch
     model = V.VideoVAE(S, S, 3, PROD["patch_size"], args.enc_depth, args.dec_depth, PROD["mlp_dim"], PROD["num_heads"],

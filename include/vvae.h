@@ -54,6 +54,8 @@ int vvae_version(void);
 int vvae_device_ok(void);
 /* Debug/tuning knobs, all 0 by default (bring-up scripts only; never set by the product path).  Keys 0-6: grid size,
  * UMMA descriptor fields and the N-tile of the tcgen05 GEMM (csrc/gemm_sm100.cu); 8: force single-CTA GEMM tiles;
+ * 7: LayerNorm D = 768 bf16 kernel choice, low nibble = backward, next nibble = forward (0: bulk-copy staged streaming
+ *    kernel, 1: register-staged kernel, 2: the other warps x stages split of the streaming kernel);
  * 9: keep short sequences (L <= 16) on the packed tcgen05 attention tiles instead of the one-warp kernels;
  * 10: tcgen05 GEMM TIMING ablations, results are wrong (bit 1: no A-tile TMA loads, 2: no B-tile loads, 4: no loads and
  *     the issuer never waits for operands, 8: accumulators never drained; 16: record counters for vvae_debug_get);

@@ -1,6 +1,10 @@
 // HBM-bound normalisation kernels: LayerNorm fwd/bwd, QK-LayerNorm + RoPE fwd/bwd, GroupNorm + SiLU fwd/bwd.
 // Statistics follow Flax: fp32, "fast variance" max(0, E[x^2] - E[x]^2), eps inside the rsqrt.
+#include <atomic>
+#include <type_traits>
+
 #include "common.cuh"
+#include "sm100.cuh"
 
 namespace vvae {
 
@@ -182,6 +186,284 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
       if (dbeta) atomicAdd(dbeta + c, red[D + c]);
     }
   }
+}
+
+
+// =====================================================================================================
+// LayerNorm streaming path (bf16, D = NV * 256): rows are staged in shared memory by 1-D bulk async copies
+// (cp.async.bulk + mbarrier), each warp owns a private ring of STAGES row slots and keeps STAGES rows of every input
+// in flight while it reduces and writes the current one.  The register-staged kernels above hold 9 x 16 bytes per lane
+// per row in registers, so occupancy (23-46 % of the warp slots, profiles/r02w_norm_ncu.json) caps the bytes in flight and
+// they run at 3.7-4.0 TB/s; here the loads in flight cost no registers.
+// =====================================================================================================
+__device__ __forceinline__ float lns_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float lns_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint32_t lns_pack(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__device__ __forceinline__ uint4 lns_lds(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int NV, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+layernorm_bwd_stream_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, const float* __restrict__ gamma, const bf16* __restrict__ dres,
+                            bf16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows) {
+  constexpr int D = NV * 256;
+  constexpr uint32_t ROWB = D * 2;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t lns_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lns_raw) + 127) & ~uintptr_t(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = dres ? 3 : 2;                                   // tensors per row slot: x, dy (, dres)
+  uint8_t* ring = base + (size_t)warp * STAGES * 3 * ROWB;        // [STAGES][3][ROWB]
+  const uint32_t ring_u32 = sm100::smem_u32(ring);
+  float* red = reinterpret_cast<float*>(base + (size_t)WARPS * STAGES * 3 * ROWB);   // [2][D]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 2 * D) + warp * STAGES;
+  if (lane == 0) {
+    for (int i = 0; i < STAGES; ++i) sm100::mbar_init(&bars[i], 1);
+    sm100::fence_barrier_init();
+  }
+  pdl_wait();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) red[c] = 0.f;
+  float gm[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) gm[i][t] = gamma ? gamma[(i * 32 + lane) * 8 + t] : 1.f;
+  __syncthreads();
+
+  const long long warp0 = (long long)blockIdx.x * WARPS + warp;
+  const long long nwarps = (long long)gridDim.x * WARPS;
+  auto issue = [&](long long row, int slot) {                    // lane 0 only
+    sm100::mbar_expect_tx(&bars[slot], (uint32_t)NT * ROWB);
+    uint8_t* dst = ring + (size_t)slot * 3 * ROWB;
+    sm100::bulk_load_1d(dst, x + row * D, ROWB, &bars[slot]);
+    sm100::bulk_load_1d(dst + ROWB, dy + row * D, ROWB, &bars[slot]);
+    if (dres) sm100::bulk_load_1d(dst + 2 * ROWB, dres + row * D, ROWB, &bars[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      const long long row = warp0 + i * nwarps;
+      if (row < rows) issue(row, i);
+    }
+  }
+  float pg[NV][8], pb[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) pg[i][t] = pb[i][t] = 0.f;
+
+  int slot = 0;
+  uint32_t phase = 0;
+  float mu_n = 0.f, r_n = 0.f;
+  if (warp0 < rows) { mu_n = mean[warp0]; r_n = rstd[warp0]; }
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float r = r_n, nmr = -mu_n * r_n;
+    if (row + nwarps < rows) { mu_n = mean[row + nwarps]; r_n = rstd[row + nwarps]; }
+    sm100::mbar_wait(&bars[slot], phase);
+    const uint32_t sx = ring_u32 + (uint32_t)slot * 3u * ROWB + (uint32_t)lane * 16u;
+    float sg = 0.f, sgx = 0.f;
+    uint4 vx[NV], vd[NV], vr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      vx[i] = lns_lds(sx + i * 512);
+      vd[i] = lns_lds(sx + ROWB + i * 512);
+      vr[i] = dres ? lns_lds(sx + 2 * ROWB + i * 512) : make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();                                                // every lane has read this slot: refill it
+    {
+      const long long nxt = row + (long long)STAGES * nwarps;
+      if (lane == 0 && nxt < rows) issue(nxt, slot);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t wx[4] = {vx[i].x, vx[i].y, vx[i].z, vx[i].w}, wd[4] = {vd[i].x, vd[i].y, vd[i].z, vd[i].w};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float xv = (t & 1) ? lns_hi(wx[t >> 1]) : lns_lo(wx[t >> 1]);
+        const float d = (t & 1) ? lns_hi(wd[t >> 1]) : lns_lo(wd[t >> 1]);
+        const float xh = fmaf(xv, r, nmr);
+        const float g = d * gm[i][t];
+        sg += g;
+        sgx = fmaf(g, xh, sgx);
+        pg[i][t] = fmaf(d, xh, pg[i][t]);
+        pb[i][t] += d;
+      }
+    }
+    sg = warp_sum(sg) * (1.f / D);
+    sgx = warp_sum(sgx) * (1.f / D);
+    // dx = (r*gamma)*dy - r*sg - (r*sgx)*xhat (+ dres), xhat = r*x - r*mu  =>  dx = (r*gamma)*dy + cx*x + cc
+    const float cx = -r * sgx * r, cc = -r * sg - r * sgx * nmr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t wx[4] = {vx[i].x, vx[i].y, vx[i].z, vx[i].w}, wd[4] = {vd[i].x, vd[i].y, vd[i].z, vd[i].w};
+      const uint32_t wr[4] = {vr[i].x, vr[i].y, vr[i].z, vr[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float f0 = fmaf(cx, lns_lo(wx[t]), fmaf(r * gm[i][2 * t], lns_lo(wd[t]), cc)) + lns_lo(wr[t]);
+        const float f1 = fmaf(cx, lns_hi(wx[t]), fmaf(r * gm[i][2 * t + 1], lns_hi(wd[t]), cc)) + lns_hi(wr[t]);
+        o[t] = lns_pack(f0, f1);
+      }
+      reinterpret_cast<uint4*>(dx + row * D)[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (++slot == STAGES) { slot = 0; phase ^= 1; }
+  }
+  if (dgamma || dbeta) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int c = (i * 32 + lane) * 8 + t;
+        atomicAdd(&red[c], pg[i][t]);
+        atomicAdd(&red[D + c], pb[i][t]);
+      }
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      if (dgamma) atomicAdd(dgamma + c, red[c]);
+      if (dbeta) atomicAdd(dbeta + c, red[D + c]);
+    }
+  }
+}
+
+
+template <int NV, int WARPS, int STAGES>
+static int launch_ln_bwd_stream(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                                const void* dres, void* dx, float* dgamma, float* dbeta, long long rows, cudaStream_t s) {
+  auto kern = layernorm_bwd_stream_kernel<NV, WARPS, STAGES>;
+  const size_t sm = 128 + (size_t)WARPS * STAGES * 3 * (NV * 512) + 2 * (size_t)(NV * 256) * sizeof(float) + WARPS * STAGES * 8;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+      set_error("layernorm_bwd: cudaFuncSetAttribute(%d)", (int)sm);
+      return VVAE_ERR_CUDA;
+    }
+    attr_set.store(true, std::memory_order_release);
+  }
+  const int blocks = (int)std::min<long long>(num_sms(), cdiv(rows, WARPS));
+  launch_pdl(kern, dim3(blocks), dim3(WARPS * 32), sm, s, (const bf16*)dy, (const bf16*)x, mean, rstd, gamma,
+             (const bf16*)dres, (bf16*)dx, dgamma, dbeta, rows);
+  return VVAE_OK;
+}
+
+
+template <int NV, int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+layernorm_fwd_stream_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                            long long rows, float eps) {
+  constexpr int D = NV * 256;
+  constexpr uint32_t ROWB = D * 2;
+  pdl_launch_dependents();
+  extern __shared__ uint8_t lns_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lns_raw) + 127) & ~uintptr_t(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = base + (size_t)warp * STAGES * ROWB;
+  const uint32_t ring_u32 = sm100::smem_u32(ring);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)WARPS * STAGES * ROWB) + warp * STAGES;
+  if (lane == 0) {
+    for (int i = 0; i < STAGES; ++i) sm100::mbar_init(&bars[i], 1);
+    sm100::fence_barrier_init();
+  }
+  __syncwarp();
+  float gm[NV][8], bt[NV][8];                                     // parameters: not produced by the previous kernel
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      gm[i][t] = gamma ? gamma[(i * 32 + lane) * 8 + t] : 1.f;
+      bt[i][t] = beta ? beta[(i * 32 + lane) * 8 + t] : 0.f;
+    }
+  pdl_wait();
+  const long long warp0 = (long long)blockIdx.x * WARPS + warp;
+  const long long nwarps = (long long)gridDim.x * WARPS;
+  auto issue = [&](long long row, int slot) {                    // lane 0 only
+    sm100::mbar_expect_tx(&bars[slot], ROWB);
+    sm100::bulk_load_1d(ring + (size_t)slot * ROWB, x + row * D, ROWB, &bars[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      const long long row = warp0 + i * nwarps;
+      if (row < rows) issue(row, i);
+    }
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    sm100::mbar_wait(&bars[slot], phase);
+    const uint32_t sx = ring_u32 + (uint32_t)slot * ROWB + (uint32_t)lane * 16u;
+    uint4 vx[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vx[i] = lns_lds(sx + i * 512);
+    __syncwarp();
+    {
+      const long long nxt = row + (long long)STAGES * nwarps;
+      if (lane == 0 && nxt < rows) issue(nxt, slot);
+    }
+    float f[NV][8];
+    float sm = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t wx[4] = {vx[i].x, vx[i].y, vx[i].z, vx[i].w};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        f[i][t] = (t & 1) ? lns_hi(wx[t >> 1]) : lns_lo(wx[t >> 1]);
+        sm += f[i][t];
+        s2 = fmaf(f[i][t], f[i][t], s2);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                           // the two reductions interleaved
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mu = sm / D;
+    const float var = fmaxf(s2 / D - mu * mu, 0.f);
+    const float r = rsqrtf(var + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mu;
+      if (rstd_out) rstd_out[row] = r;
+    }
+    const float nmr = -mu * r;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      uint32_t o[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float a = fmaf(fmaf(f[i][2 * t], r, nmr), gm[i][2 * t], bt[i][2 * t]);
+        const float b = fmaf(fmaf(f[i][2 * t + 1], r, nmr), gm[i][2 * t + 1], bt[i][2 * t + 1]);
+        o[t] = lns_pack(a, b);
+      }
+      reinterpret_cast<uint4*>(y + row * D)[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (++slot == STAGES) { slot = 0; phase ^= 1; }
+  }
+}
+
+template <int NV, int WARPS, int STAGES>
+static int launch_ln_fwd_stream(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
+                                long long rows, float eps, cudaStream_t s) {
+  auto kern = layernorm_fwd_stream_kernel<NV, WARPS, STAGES>;
+  const size_t sm = 128 + (size_t)WARPS * STAGES * (NV * 512) + WARPS * STAGES * 8;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+      set_error("layernorm_fwd: cudaFuncSetAttribute(%d)", (int)sm);
+      return VVAE_ERR_CUDA;
+    }
+    attr_set.store(true, std::memory_order_release);
+  }
+  const int blocks = (int)std::min<long long>(num_sms(), cdiv(rows, WARPS));
+  launch_pdl(kern, dim3(blocks), dim3(WARPS * 32), sm, s, (const bf16*)x, (bf16*)y, gamma, beta, mean, rstd, rows, eps);
+  return VVAE_OK;
 }
 
 // =====================================================================================================
@@ -935,6 +1217,17 @@ template <typename T>
 static int ln_fwd_dispatch(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* rstd,
                            long long rows, int D, float eps, cudaStream_t s) {
   constexpr int V = Vec16<T>::N;
+  if constexpr (std::is_same<T, bf16>::value) {
+    const int mode = (int)(g_dbg[7] >> 4) & 15;      // vvae_debug_set(7, 16): register-staged kernel; (7, 32): 16 warps x 4 stages
+    if (D == 768 && mode != 1) {
+      // 8 warps x 8 stages: 23.4 us at [32768, 768] against 24.6 (16 x 4) and 26.7 (register-staged); a 100 MB copy
+      // under the same protocol takes 23.6 us (scripts/norm_ab.py)
+      const int rc = mode == 2 ? launch_ln_fwd_stream<3, 16, 4>(x, y, gamma, beta, mean, rstd, rows, eps, s)
+                                   : launch_ln_fwd_stream<3, 8, 8>(x, y, gamma, beta, mean, rstd, rows, eps, s);
+      if (rc != VVAE_OK) return rc;
+      return check_launch("layernorm_fwd");
+    }
+  }
   const int need = (int)cdiv(D / V, 32);
   const size_t smem = 2 * (size_t)D * sizeof(float);
 #define LN_FWD(NC)                                                                                               \
@@ -962,6 +1255,18 @@ static int ln_bwd_dispatch(const void* dy, const void* x, const float* mean, con
                            const void* dres, void* dx, float* dgamma, float* dbeta, long long rows, int D,
                            cudaStream_t s) {
   constexpr int V = Vec16<T>::N;
+  if constexpr (std::is_same<T, bf16>::value) {
+    const int mode = (int)g_dbg[7] & 15;
+    if (D == 768 && mode != 1 && ((uintptr_t)dy % 16 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)dx % 16 == 0) &&
+        (!dres || (uintptr_t)dres % 16 == 0)) {      // vvae_debug_set(7, 1): register-staged kernel
+      // vvae_debug_set(7, 2): 8 warps x 4 stages instead of 12 x 3 (same bytes in flight per SM): 50.1 vs 49.2 us
+      // (16 warps x 2 stages is capped at 128 registers, spills and runs at 64 us)
+      const int rc = mode == 2 ? launch_ln_bwd_stream<3, 8, 4>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, s)
+                                   : launch_ln_bwd_stream<3, 12, 3>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, s);
+      if (rc != VVAE_OK) return rc;
+      return check_launch("layernorm_bwd");
+    }
+  }
   const int need = (int)cdiv(D / V, 32);
   const size_t smem = 3 * (size_t)D * sizeof(float);
 #define LN_BWD(NC)                                                                                              \
