@@ -61,3 +61,9 @@ def loss_fn(model, video, mask, original_mask, rngs, hparams=None, train=True, n
     loss, aux = loss_terms(video, reconstruction, selection, logvar, mean, original_mask, hparams)
     aux.update(reconstruction=reconstruction, compressed=compressed, selection=selection, logvar=logvar, mean=mean)
     return loss, aux
+
+
+def eval_step(model, video, mask_bt, hparams, hw, rngs):
+    """training_loop_adversarial.py:139-148."""
+    with torch.no_grad():
+        return loss_fn(model, video, expand_mask(mask_bt, hw), mask_bt, rngs, hparams, train=False)

@@ -279,6 +279,49 @@ def test_rl_model_variant_shapes_and_binary_keep_mask():
     assert g is not None and torch.isfinite(g).all() and g.abs().max() > 0
 
 
+def test_distributed_rl_model_returns_variance():
+    """claude_distributed/rl_model.py:55-60,125-128,147 (the data-parallel trainer's copy): same weights, same draws ->
+    the same reconstruction as train/rl_model.py, with variance = exp(log_variance) in the 5th slot."""
+    from oracle import Rngs
+    from oracle.distributed_rl_model import Encoder, VideoVAE as DVAE
+    from oracle.rl_model import VideoVAE as RVAE
+    B, T, H = 2, 4, 64
+    cfg = (H, H, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4)
+    a, d = RVAE(*cfg, Rngs(42)), DVAE(*cfg, Rngs(42))
+    d.load_state_dict(a.state_dict())
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(B, T, H, H, 3, generator=g) * 0.5
+    mask = torch.ones(B, 1, 1, T, dtype=torch.bool)
+    noise, bu = torch.randn(B, T, 16, 96, generator=g), torch.rand(2 * B, T, 1, 1, generator=g)
+    ra = a(x, mask, Rngs(0), train=True, noise=noise, bernoulli_u=bu)
+    rd = d(x, mask, Rngs(0), train=True, noise=noise, bernoulli_u=bu)
+    assert (rd[4] > 0).all() and torch.allclose(rd[4], torch.exp(ra[4]), rtol=1e-5, atol=0)
+    for i in (0, 1, 2, 3, 5):
+        assert ((rd[i] - ra[i]).abs().max() / ra[i].abs().max()).item() < 1e-5, i
+    mean, var, sel = Encoder(H, H, 3, 16, 2, 256, 4, 128, 32, 8, Rngs(1))(x, mask, Rngs(0))
+    assert var.shape == mean.shape and (var > 0).all() and sel.shape == (B, T, 1)
+
+
+def test_plain_eval_step_is_deterministic_and_uses_the_mean():
+    """training_loop_adversarial.py:139-148: eval_step runs loss_fn with train=False -- no draws: two calls with
+    different rngs agree, the gate is binary, the compressed representation is the mean on kept frames."""
+    from oracle import Rngs
+    from oracle.losses import DEFAULT_HPARAMS, eval_step
+    from oracle.model import VideoVAE
+    cfg = (64, 64, 3, 16, 1, 1, 128, 2, 64, 16, 8, 4)
+    m = VideoVAE(*cfg, Rngs(3))
+    g = torch.Generator().manual_seed(1)
+    video = torch.rand(2, 4, 64, 64, 3, generator=g)
+    mask = torch.tensor([[True] * 4, [True, True, False, False]])
+    l1, a1 = eval_step(m, video, mask, DEFAULT_HPARAMS, 16, Rngs(0))
+    l2, a2 = eval_step(m, video, mask, DEFAULT_HPARAMS, 16, Rngs(99))
+    assert torch.equal(l1, l2) and torch.equal(a1["reconstruction"], a2["reconstruction"]) and not l1.requires_grad
+    sel = a1["selection"]
+    assert set(sel.unique().tolist()) <= {0.0, 1.0}
+    kept = sel.reshape(2, 4) > 0
+    assert torch.equal(a1["compressed"][kept], a1["mean"][kept])
+
+
 def test_rl_loss_training_loop_checks():
     """claude_distributed/test_training_loop.py Tests 1, 3, 4 (64x64, P16, 2/2, mlp 256, 4 heads, qkv 128, scr 4, up 2,
     t=8, lr 1e-3, gamma3=0 with a zero perceptual term) on the oracle restatement of rl_nonadversarial.py:100-186:

@@ -891,6 +891,74 @@ def test_rl_model_variant_matches_oracle_fp32(V):
     assert r2[0].shape == (2 * b, t, 64, 64, 3) and set(r2[3].unique().tolist()) <= {0.0, 1.0}
 
 
+def test_distributed_rl_model_variant_matches_oracle_fp32(V):
+    """claude_distributed/rl_model.py:55-60,147: the variant that returns the VARIANCE.  Outputs against the oracle's
+    restatement, and the gradient of a loss that uses the variance (KL written on it) reaches the encoder."""
+    from oracle import Rngs as ORngs
+    from oracle.distributed_rl_model import VideoVAE as ODRL
+    from video_vae_b200.distributed_rl_model import VideoVAE as DRL
+    cfg = (64, 64, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4)
+    o = ODRL(*cfg, ORngs(2))
+    with torch.no_grad():
+        o.decoder.unet.final_conv.kernel.copy_(torch.randn(o.decoder.unet.final_conv.kernel.shape, generator=_gen(5)) * 0.05)
+    m = DRL(*cfg, V.Rngs(2), dtype=torch.float32)
+    _copy_params(m, o)
+    g = _gen(12)
+    b, t = 2, 4
+    x = torch.rand(b, t, 64, 64, 3, generator=g)
+    mask = torch.ones(b, 1, 1, t, dtype=torch.bool)
+    noise = torch.randn(b, t, 16, 96, generator=g)
+    bu = torch.rand(2 * b, t, 1, 1, generator=g)
+    outs_o = o(x, mask, ORngs(0), train=True, noise=noise, bernoulli_u=bu)
+    outs_m = m(x.cuda(), mask.cuda(), V.Rngs(0), train=True, noise=noise.cuda(), bernoulli_u=bu.cuda())
+    assert torch.equal(outs_m[3].cpu().reshape(-1), outs_o[3].reshape(-1))
+    for n_, a, r in zip(("reconstruction", "compressed", "selection", "selection_mask", "variance", "mean"), outs_m, outs_o):
+        assert tuple(a.shape) == tuple(r.shape), n_
+        assert rel_err(a, r) < FP32_TOL, n_
+    assert (outs_m[4] > 0).all()
+
+    def loss(outs, vid):
+        var, mu = outs[4], outs[5]
+        return (outs[0] - vid).square().mean() + 0.01 * (0.5 * (var - 1 - torch.log(var) + mu.square())).mean()
+    vid2 = x.repeat_interleave(2, dim=0)
+    lo, lm = loss(outs_o, vid2), loss(outs_m, vid2.cuda())
+    assert abs(float(lm) - float(lo)) <= FP32_TOL * abs(float(lo))
+    lo.backward()
+    lm.backward()
+    _grads_close(m, o, 1e-3, min_checked=100)
+    assert m.encoder.variance_estimator.kernel.grad.abs().max() > 0
+    mean, var, sel = m.encode(x.cuda(), mask.cuda(), V.Rngs(0))
+    assert rel_err(var, outs_o[4][::2]) < FP32_TOL and sel.shape == (b, t, 1)
+
+
+def test_plain_eval_step_matches_oracle_fp32(V):
+    """training_loop_adversarial.py:139-148: eval_step (train=False: latent = mean, thresholded gate) against the oracle."""
+    from oracle import Rngs as ORngs
+    from oracle.losses import DEFAULT_HPARAMS, eval_step as o_eval
+    from oracle.model import VideoVAE as OVAE
+    from video_vae_b200.losses import eval_step
+    cfg = (64, 64, 3, 16, 2, 2, 256, 4, 128, 32, 8, 4)
+    o = OVAE(*cfg, ORngs(2))
+    with torch.no_grad():
+        o.decoder.unet.final_conv.kernel.copy_(torch.randn(o.decoder.unet.final_conv.kernel.shape, generator=_gen(5)) * 0.05)
+    m = V.VideoVAE(*cfg, V.Rngs(2), dtype=torch.float32)
+    _copy_params(m, o)
+    g = _gen(4)
+    video = torch.rand(2, 4, 64, 64, 3, generator=g)
+    mask = torch.tensor([[True] * 4, [True, True, True, False]])
+    lo, ao = o_eval(o, video, mask, DEFAULT_HPARAMS, 16, ORngs(0))
+    lm, am = eval_step(m, video.cuda(), mask.cuda(), DEFAULT_HPARAMS, V.Rngs(5))
+    assert not lm.requires_grad
+    assert torch.equal(am["selection"].float().cpu().reshape(-1), ao["selection"].reshape(-1))
+    assert abs(float(lm) - float(lo)) <= FP32_TOL * abs(float(lo))
+    for k in ("MSE", "selection_loss", "kl_loss", "kept_frame_density"):
+        assert abs(float(am[k]) - float(ao[k])) <= FP32_TOL * max(abs(float(ao[k])), 1e-6), k
+    for k in ("reconstruction", "compressed", "mean", "logvar"):
+        assert rel_err(am[k], ao[k]) < FP32_TOL, k
+    lm2, _ = eval_step(m, video.cuda(), mask.cuda(), DEFAULT_HPARAMS, V.Rngs(77))
+    assert torch.equal(lm, lm2)                                            # no draws in eval
+
+
 def test_rl_loss_matches_oracle_fp32(V):
     """the RL training loss (video_vae_b200.rl_losses, rl_nonadversarial.py:100-186) against its oracle
     restatement with injected draws, fp32: loss, every aux term, per-sample losses and all parameter gradients

@@ -2,8 +2,10 @@
 
 ``loss_fn`` mirrors train/legacy/training_loop_adversarial.py:90-124 (signature, loss terms, returned aux), with the
 optional MAE term of train/rl_nonadversarial.py:114-117 enabled by ``hparams["gamma4"]``; ``train_step`` mirrors
-:126-136 (mask plumbing + value_and_grad), leaving the optimizer update to the caller.
+:126-136 (mask plumbing + value_and_grad), leaving the optimizer update to the caller; ``eval_step`` mirrors :139-148.
 """
+import torch
+
 from . import functional as F_
 
 DEFAULT_HPARAMS = {  # training_loop_adversarial.py:47-48,52,54
@@ -39,3 +41,10 @@ def train_step(model, video, mask_bt, hparams, rngs, noise=None, gumbel_u=None):
                         gumbel_u=gumbel_u)
     loss.backward()
     return loss, aux
+
+
+def eval_step(model, video, mask_bt, hparams, rngs):
+    """training_loop_adversarial.py:139-148: the loss with ``train=False`` -- the latent is the mean (model.py:113-125)
+    and the frame gate is the deterministic threshold ``round(sigmoid(logit))`` (layers.py:250-252); no draws, no gradients."""
+    with torch.no_grad():
+        return loss_fn(model, video, mask_bt[:, None, None, :], mask_bt, rngs, hparams, train=False)
