@@ -68,7 +68,9 @@ int vvae_device_ok(void);
  *     weight image resident in shared memory. */
 int vvae_debug_set(int key, long long value);
 /* what = 0: counters of the last tcgen05 GEMM launched with vvae_debug_set(10, ... | 16): {clock64 ticks, globaltimer ns,
- * MMAs issued} of CTA 0's issuing thread (synchronises the device). */
+ * MMAs issued} of CTA 0's issuing thread (synchronises the device).
+ * what = 1: `out4` must hold 32 values: the clock64 timeline of one CTA of the last tcgen05 attention backward launched
+ * with vvae_debug_set(10, 16) (CTA index = vvae_debug_set(0, n)); slots are listed in scripts/attn_timeline.py. */
 int vvae_debug_get(int what, unsigned long long* out4);
 
 /* ---- elementwise plumbing ------------------------------------------------- */

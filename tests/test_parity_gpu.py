@@ -956,7 +956,7 @@ def test_plain_eval_step_matches_oracle_fp32(V):
     for k in ("reconstruction", "compressed", "mean", "logvar"):
         assert rel_err(am[k], ao[k]) < FP32_TOL, k
     lm2, _ = eval_step(m, video.cuda(), mask.cuda(), DEFAULT_HPARAMS, V.Rngs(77))
-    assert torch.equal(lm, lm2)                                            # no draws in eval
+    assert abs(float(lm) - float(lm2)) <= 1e-5 * abs(float(lm))           # no draws in eval (GroupNorm atomics reorder sums)
 
 
 def test_rl_loss_matches_oracle_fp32(V):

@@ -336,7 +336,7 @@ int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s);
 int attn_warp_supported(const vvae_attn_args& a, bool bwd);
 int attn_warp_fwd(const vvae_attn_args& a, cudaStream_t s);
 int attn_warp_bwd(const vvae_attn_args& a, cudaStream_t s);
-extern long long g_dbg[16];      // vvae_debug_set: key 9 != 0 keeps short sequences on the tcgen05 packed-tile kernels
+extern long long g_dbg[32];      // vvae_debug_set: key 9 != 0 keeps short sequences on the tcgen05 packed-tile kernels
 }
 
 using namespace vvae;

@@ -384,7 +384,13 @@ struct AttnTcBwdParams {
   const unsigned char* mask; long long mask_seq_div, ms_seq, ms_k;
   bf16 *dq, *dk, *dv; long long dq_rs, dk_rs, dv_rs;
   float scale;
+  int dbg;     // vvae_debug_set(10, 16): the CTA given by vvae_debug_set(0, n) records a clock64 timeline (vvae_debug_get(1, .))
+  int dbg_cta;
 };
+
+// clock64 stamps of one CTA of attn_bwd_sm100_kernel (see the ATB_STAMP sites); [31] = SM id
+__device__ unsigned long long g_attn_dbg[32];
+#define ATB_STAMP(slot) do { if (dbg_on) g_attn_dbg[slot] = clock64(); } while (0)
 
 // row r of 128-row block `blk` of the CTA's tile set
 template <bool PACKED>
@@ -426,6 +432,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tile = blockIdx.x;
   const int h = blockIdx.y;
+  const bool dbg_on = q.dbg && (int)(blockIdx.y * gridDim.x + blockIdx.x) == q.dbg_cta && lane == 0;
+  if (warp == 0) ATB_STAMP(0);
 
   if (warp == 0 && lane == 0) {
     sm100::tma_prefetch_desc(&tma_q);
@@ -444,7 +452,9 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   __syncthreads();
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) ATB_STAMP(1);
   pdl_wait();   // PDL (common.cuh)
+  if (warp == 0) ATB_STAMP(2);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -485,6 +495,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       };
       sm100::mbar_wait(&ld_bar[0], 0);
       sm100::tc_fence_after();
+      ATB_STAMP(3);
       issue_sdp(0);
       int loaded = 1;
 #pragma unroll 1
@@ -492,6 +503,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         const int j = t / NB, i = t % NB;
         sm100::mbar_wait(p_full, t & 1);
         sm100::tc_fence_after();
+        ATB_STAMP(4 + (t & 3));
         if (t + 1 < NT) {
           const int need = max((t + 1) / NB, (t + 1) % NB) + 1;
           while (loaded < need) { sm100::mbar_wait(&ld_bar[loaded], 0); ++loaded; }
@@ -521,11 +533,13 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
                           sm100::make_smem_desc_sw128(aK + j * BLK + k * 2048, 8192, 1024), idesc_q,
                           (j > 0 || k > 0) ? 1u : 0u);
         sm100::umma_commit(mma3_done);
+        ATB_STAMP(8 + (t & 3));
       }
     }
   } else {
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
     const int g = (warp - 2) >> 2;                     // key-column half of the tile
+    const bool dbg_on2 = dbg_on && warp == 2;
     const int r = quarter * 32 + lane;                 // row of the 128-row block == TMEM lane
     const int tid = threadIdx.x - 64;                  // 0..255
     for (int c = tid; c < NB * 128; c += 256) {
@@ -580,6 +594,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       lse2[i] = lraw[i] * 1.4426950408889634f;
       dlt[i] = d;
     }
+    if (dbg_on2) g_attn_dbg[12] = clock64();
 
 #pragma unroll 1
     for (int t = 0; t < NT; ++t) {
@@ -591,6 +606,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         if (i == ii) { my_lse2 = lse2[ii]; my_d = dlt[ii]; my_ok = rok[ii]; my_allm = allm[ii]; }
       sm100::mbar_wait(s_full, t & 1);
       sm100::tc_fence_after();
+      if (dbg_on2) g_attn_dbg[13 + (t & 3)] = clock64();
       uint32_t pkP[32], pkS[32];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -624,6 +640,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         }
       }
       sm100::tc_fence_before();
+      if (dbg_on2) g_attn_dbg[17 + (t & 3)] = clock64();
       if (t > 0) sm100::mbar_wait(mma3_done, (t - 1) & 1);      // P / dS tiles of the previous tile are consumed
       {
         uint8_t* prow = sP + g * BLK + r * 128;
@@ -638,6 +655,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       sm100::fence_proxy_async();
       __syncwarp();
       if (lane == 0) sm100::mbar_arrive(p_full);
+      if (dbg_on2) g_attn_dbg[21 + (t & 3)] = clock64();
 
       if (i == NB - 1) {                    // key block j is complete: warp group 0 drains dK_j, warp group 1 dV_j
         sm100::mbar_wait(mma3_done, t & 1);
@@ -664,6 +682,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         sm100::tc_fence_before();
         __syncwarp();
         if (lane == 0) sm100::mbar_arrive(kv_drained);
+        if (dbg_on2) g_attn_dbg[25 + (j & 1)] = clock64();
       }
       if (j == NB - 1) {                    // query block i is complete: each warp group drains 32 of dQ_i's 64 columns
         sm100::mbar_wait(mma3_done, t & 1);
@@ -688,10 +707,22 @@ attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   }
   sm100::tc_fence_before();
   __syncthreads();
+  if (warp == 0) {
+    ATB_STAMP(27);
+    if (dbg_on) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_attn_dbg[31] = smid;
+    }
+  }
   if (warp == 1) {
     sm100::tc_fence_after();
     sm100::tmem_dealloc<512>(tmem_base);
   }
+}
+
+int attn_debug_read(unsigned long long* out32) {
+  return cudaMemcpyFromSymbol(out32, g_attn_dbg, 32 * sizeof(unsigned long long)) == cudaSuccess ? VVAE_OK : VVAE_ERR_CUDA;
 }
 
 template <int NB, bool PACKED, bool MASKED>
@@ -712,6 +743,8 @@ static int atc_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   q.dq = (bf16*)a.dq; q.dk = (bf16*)a.dk; q.dv = (bf16*)a.dv;
   q.dq_rs = a.dq_rs; q.dk_rs = a.dk_rs; q.dv_rs = a.dv_rs;
   q.scale = a.scale;
+  q.dbg = (g_dbg[10] & 16) ? 1 : 0;
+  q.dbg_cta = (int)g_dbg[0];
   auto kern = attn_bwd_sm100_kernel<NB, PACKED, MASKED>;
   static std::atomic<bool> attr_set{false};
   if (!attr_set.load(std::memory_order_acquire)) {   // idempotent: a racing second call sets the same value
@@ -964,6 +997,8 @@ attn_delta_kernel(const bf16* __restrict__ o, long long o_rs, const bf16* __rest
                   float* __restrict__ delta, AttnTcPlan p, long long total) {
   const int cph = 8 * p.heads;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();                                            // dO is the previous kernel's output
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx - lane < total;
        idx += (long long)gridDim.x * blockDim.x) {       // whole warps iterate together (shuffles below)
     const bool act = idx < total;
@@ -1304,6 +1339,448 @@ static int atl_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   return check_launch("attn_bwd_long_sm100");
 }
 
+
+// ====================================================================================================== backward, L = 256
+// Persistent variant of the backward for sequences of 256 without a mask (spatial attention at 256x256 pixels: 21 of the
+// 42 attention backward launches of a step).  The one-unit-per-CTA kernel above spends 41 k cycles per (sequence, head)
+// of which the tensor core is busy 12 k (scripts/attn_timeline.py): operand loads, D = rowsum(dO o O), the accumulator
+// drains and the softmax all sit on one serial chain, and 512 TMEM columns + 192 KB of shared memory leave no room for a
+// second CTA to hide it.  Here one CTA per SM walks over its (sequence, head) units and the chain is cut into roles:
+//   warp 0      producer: TMA loads of the NEXT unit's Q/K/V/dO blocks go into each 32 KB group of the operand buffers
+//               as soon as the tile that last reads the group has finished (groups: {K0,V0} {Q0,dO0} {Q1,dO1} {K1,V1});
+//   warp 1      MMA issuer: S/dP of tile T+1 are issued as soon as the softmax warps have READ S/dP of tile T out of
+//               TMEM (s_free), ahead of the three output contractions of tile T, so the tensor pipe never idles behind
+//               the softmax;
+//   warps 4-11  softmax: P = exp2(S*k - LSE), dS = P o (dP - D) * scale, written as bf16 into the one swizzled layout the
+//               tensor core reads K-major and MN-major (as above); D and LSE come from global memory (D from
+//               attn_delta_kernel, a 67 MB pre-pass), prefetched one unit ahead;
+//   warps 12-15 drain: dK_j, dV_j (after each key block) and dQ_i (after each query block's last tile) leave TMEM while
+//               the other roles carry on with the next tile / unit.
+// Register budget by setmaxnreg: softmax warps 184, drain 96, producer / issuer 48.
+// Every mbarrier completes exactly once per unit, so a wait's parity is the unit counter's low bit.
+struct AttnBwd256Params {
+  AttnTcPlan pl;
+  const float* lse; const float* delta;
+  bf16 *dq, *dk, *dv; long long dq_rs, dk_rs, dv_rs;
+  float scale;
+  long long units;
+  int dbg, dbg_cta;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(sm100::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void atb_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void atb_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void atb_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(512, 1)
+attn_bwd256_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                         const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                         const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ CUtensorMap tma_dk,
+                         const __grid_constant__ CUtensorMap tma_dv, const AttnBwd256Params q) {
+  const AttnTcPlan& p = q.pl;
+  constexpr int BLK = 16384;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256, COL_DK = 384, COL_DV = 448;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * BLK;
+  uint8_t* sV = sK + 2 * BLK;
+  uint8_t* sdO = sV + 2 * BLK;
+  uint8_t* sP = sdO + 2 * BLK;                     // [2 key halves][128 q][64 keys] bf16, swizzled
+  uint8_t* sdS = sP + 2 * BLK;
+  uint8_t* stage = sdS + 2 * BLK;                  // [2] gradient tiles on their way out (TMA store)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 2 * BLK);
+  uint64_t* ld_bar = bars;                         // [4] operand groups A..D
+  uint64_t* s_full = bars + 4;                     // [4] S/dP of tile t are in TMEM
+  uint64_t* s_free = bars + 8;                     // [4] ... and have been read out
+  uint64_t* p_full = bars + 12;                    // [4] P/dS of tile t are in shared memory
+  uint64_t* mma_done = bars + 16;                  // [4] output contractions of tile t are complete
+  uint64_t* kv_drained = bars + 20;                // [2] dK_j/dV_j have left TMEM
+  uint64_t* dq_drained = bars + 22;                // [2] dQ_i has left TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dbg_on = (q.dbg & 1) && (int)blockIdx.x == q.dbg_cta && lane == 0;
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_q);
+    sm100::tma_prefetch_desc(&tma_k);
+    sm100::tma_prefetch_desc(&tma_v);
+    sm100::tma_prefetch_desc(&tma_do);
+    sm100::tma_prefetch_desc(&tma_dq);
+    sm100::tma_prefetch_desc(&tma_dk);
+    sm100::tma_prefetch_desc(&tma_dv);
+    for (int b = 0; b < 4; ++b) {
+      sm100::mbar_init(&ld_bar[b], 1);
+      sm100::mbar_init(&s_full[b], 1);
+      sm100::mbar_init(&s_free[b], 8);
+      sm100::mbar_init(&p_full[b], 8);
+      sm100::mbar_init(&mma_done[b], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      sm100::mbar_init(&kv_drained[b], 4);
+      sm100::mbar_init(&dq_drained[b], 4);
+    }
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const int n_it = first < q.units ? (int)((q.units - first + stride - 1) / stride) : 0;
+
+  if (warp < 4) {
+    reg_dealloc<48>();
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------------------------------------------- producer
+      for (int it = 0; it < n_it; ++it) {
+        const long long u = first + (long long)it * stride;
+        const long long seq = u / p.heads;
+        const int h = (int)(u % p.heads);
+        const int c3 = (int)(seq / p.n_inner), c2 = (int)(seq % p.n_inner);
+        const uint32_t pp = (uint32_t)(it - 1) & 1u;
+        if (it > 0) sm100::mbar_wait(&mma_done[1], pp);          // K0, V0: last read by tile 1
+        sm100::mbar_expect_tx(&ld_bar[0], 2 * BLK);
+        tma_load_4d(sK, &tma_k, &ld_bar[0], h * 64, 0, c2, c3);
+        tma_load_4d(sV, &tma_v, &ld_bar[0], h * 64, 0, c2, c3);
+        if (it > 0) sm100::mbar_wait(&mma_done[2], pp);          // Q0, dO0: last read by tile 2
+        sm100::mbar_expect_tx(&ld_bar[1], 2 * BLK);
+        tma_load_4d(sQ, &tma_q, &ld_bar[1], h * 64, 0, c2, c3);
+        tma_load_4d(sdO, &tma_do, &ld_bar[1], h * 64, 0, c2, c3);
+        if (it > 0) sm100::mbar_wait(&mma_done[3], pp);          // Q1, dO1, K1, V1: last read by tile 3
+        sm100::mbar_expect_tx(&ld_bar[2], 2 * BLK);
+        tma_load_4d(sQ + BLK, &tma_q, &ld_bar[2], h * 64, 128, c2, c3);
+        tma_load_4d(sdO + BLK, &tma_do, &ld_bar[2], h * 64, 128, c2, c3);
+        sm100::mbar_expect_tx(&ld_bar[3], 2 * BLK);
+        tma_load_4d(sK + BLK, &tma_k, &ld_bar[3], h * 64, 128, c2, c3);
+        tma_load_4d(sV + BLK, &tma_v, &ld_bar[3], h * 64, 128, c2, c3);
+        // the operand buffers are released one group at a time, only ~1-3 k cycles before the next unit needs them:
+        // pull the next unit's tiles into L2 now, a whole unit ahead, so those loads are L2 hits
+        if (it + 1 < n_it && !(q.dbg & 4)) {
+          const long long u1 = u + stride;
+          const long long seq1 = u1 / p.heads;
+          const int h1 = (int)(u1 % p.heads);
+          const int d3 = (int)(seq1 / p.n_inner), d2 = (int)(seq1 % p.n_inner);
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) {
+            tma_prefetch_l2_4d(&tma_k, h1 * 64, blk * 128, d2, d3);
+            tma_prefetch_l2_4d(&tma_v, h1 * 64, blk * 128, d2, d3);
+            tma_prefetch_l2_4d(&tma_q, h1 * 64, blk * 128, d2, d3);
+            tma_prefetch_l2_4d(&tma_do, h1 * 64, blk * 128, d2, d3);
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---------------------------------------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, 128, false, false);   // S, dP: both K-major
+      constexpr uint32_t idesc_kv = sm100::make_idesc_bf16(128, 64, true, true);     // dV, dK: A^T (MN-major), B MN-major
+      constexpr uint32_t idesc_q = sm100::make_idesc_bf16(128, 64, false, true);     // dQ: A K-major, B MN-major
+      const uint32_t aQ = sm100::smem_u32(sQ), aK = sm100::smem_u32(sK), aV = sm100::smem_u32(sV);
+      const uint32_t aO = sm100::smem_u32(sdO), aP = sm100::smem_u32(sP), aS = sm100::smem_u32(sdS);
+      const int total = 4 * n_it;
+      auto issue_sdp = [&](int T) {                // tile T of the flat sequence: loads, then S and dP
+        const int t = T & 3, j = t >> 1, i = t & 1;
+        const uint32_t ph = (uint32_t)(T >> 2) & 1u;
+        if (t == 0) { sm100::mbar_wait(&ld_bar[0], ph); sm100::mbar_wait(&ld_bar[1], ph); }
+        else if (t == 1) sm100::mbar_wait(&ld_bar[2], ph);
+        else if (t == 2) sm100::mbar_wait(&ld_bar[3], ph);
+        sm100::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + COL_S, sm100::make_smem_desc_sw128(aQ + i * BLK + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(aK + j * BLK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + COL_DP, sm100::make_smem_desc_sw128(aO + i * BLK + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(aV + j * BLK + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        sm100::umma_commit(&s_full[t]);
+      };
+      if (total > 0) issue_sdp(0);
+#pragma unroll 1
+      for (int T = 0; T < total; ++T) {
+        const int it = T >> 2, t = T & 3, j = t >> 1, i = t & 1;
+        const uint32_t ph = (uint32_t)it & 1u;
+        if (dbg_on && it == 1) g_attn_dbg[t] = clock64();
+        if (T + 1 < total) {
+          sm100::mbar_wait(&s_free[t], ph);        // S/dP of tile T are in registers: the columns can be overwritten
+          sm100::tc_fence_after();
+          issue_sdp(T + 1);
+        }
+        sm100::mbar_wait(&p_full[t], ph);
+        if (dbg_on && it == 1) g_attn_dbg[4 + t] = clock64();
+        if (it > 0 && j == 0) sm100::mbar_wait(&dq_drained[i], ph ^ 1u);   // dQ_i of the previous unit has left TMEM
+        sm100::tc_fence_after();
+        // dQ_i (+)= dS K_j : contraction over the 128 keys.  First: it does not wait for the dK/dV drain.
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sm100::umma_f16(tmem_base + COL_DQ + 64 * i,
+                          sm100::make_smem_desc_sw128(aS + (k >> 2) * BLK + (k & 3) * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(aK + j * BLK + k * 2048, 8192, 1024), idesc_q,
+                          (j > 0 || k > 0) ? 1u : 0u);
+        if (i == 0) {                              // dK/dV are about to be overwritten: the previous key block has been read out
+          if (j == 1) sm100::mbar_wait(&kv_drained[0], ph);
+          else if (it > 0) sm100::mbar_wait(&kv_drained[1], ph ^ 1u);
+          sm100::tc_fence_after();
+        }
+        // dV_j (+)= P^T dO_i ; dK_j (+)= dS^T Q_i : contraction over the 128 queries, 16 per step
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sm100::umma_f16(tmem_base + COL_DV, sm100::make_smem_desc_sw128(aP + k * 2048, BLK, 1024),
+                          sm100::make_smem_desc_sw128(aO + i * BLK + k * 2048, 8192, 1024), idesc_kv,
+                          (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          sm100::umma_f16(tmem_base + COL_DK, sm100::make_smem_desc_sw128(aS + k * 2048, BLK, 1024),
+                          sm100::make_smem_desc_sw128(aQ + i * BLK + k * 2048, 8192, 1024), idesc_kv,
+                          (i > 0 || k > 0) ? 1u : 0u);
+        sm100::umma_commit(&mma_done[t]);
+        if (dbg_on && it == 1) g_attn_dbg[8 + t] = clock64();
+      }
+    }
+  } else if (warp < 12) {
+    // ------------------------------------------------------------------------------------------------ softmax
+    reg_alloc<184>();
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int g = (warp - 4) >> 2;                     // key-column half of the tile
+    const int r = quarter * 32 + lane;                 // row of the 128-row block == TMEM lane
+    const bool dbg2 = dbg_on && warp == 4;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t sw = (uint32_t)(r & 7);
+    const float k2 = q.scale * 1.4426950408889634f;
+    float n_lse[2] = {0.f, 0.f}, n_dlt[2] = {0.f, 0.f};
+    if (n_it > 0) {
+      const long long base = first * 256 + r;          // (seq*heads + h) == unit index
+      n_lse[0] = q.lse[base]; n_lse[1] = q.lse[base + 128];
+      n_dlt[0] = q.delta[base]; n_dlt[1] = q.delta[base + 128];
+    }
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const float lse2[2] = {n_lse[0] * 1.4426950408889634f, n_lse[1] * 1.4426950408889634f};
+      const float dlt[2] = {n_dlt[0], n_dlt[1]};
+      if (it + 1 < n_it) {
+        const long long base = (first + (long long)(it + 1) * stride) * 256 + r;
+        n_lse[0] = q.lse[base]; n_lse[1] = q.lse[base + 128];
+        n_dlt[0] = q.delta[base]; n_dlt[1] = q.delta[base + 128];
+      }
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        const int i = t & 1;
+        const float my_lse2 = i ? lse2[1] : lse2[0], my_d = i ? dlt[1] : dlt[0];
+        sm100::mbar_wait(&s_full[t], ph);
+        sm100::tc_fence_after();
+        if (dbg2 && it == 1) g_attn_dbg[12 + t] = clock64();
+        uint32_t pkP[32], pkS[32];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c0 = g * 64 + hf * 32;
+          uint32_t sr[32], dr[32];
+          sm100::tmem_ld_32x32(trow + COL_S + c0, sr);
+          sm100::tmem_ld_32x32(trow + COL_DP + c0, dr);
+          sm100::tmem_ld_wait();
+          if (hf == 1) {                               // this warp's part of S/dP is in registers
+            sm100::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) sm100::mbar_arrive(&s_free[t]);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = atc_exp2(__uint_as_float(sr[e]) * k2 - my_lse2);
+            const float p1 = atc_exp2(__uint_as_float(sr[e + 1]) * k2 - my_lse2);
+            const float d0 = p0 * (__uint_as_float(dr[e]) - my_d) * q.scale;
+            const float d1 = p1 * (__uint_as_float(dr[e + 1]) - my_d) * q.scale;
+            pkP[hf * 16 + (e >> 1)] = atc_pack2(p0, p1);
+            pkS[hf * 16 + (e >> 1)] = atc_pack2(d0, d1);
+          }
+        }
+        if (dbg2 && it == 1) g_attn_dbg[16 + t] = clock64();
+        // P / dS of the previous tile must have been consumed by its three contractions
+        if (t > 0) sm100::mbar_wait(&mma_done[t - 1], ph);
+        else if (it > 0) sm100::mbar_wait(&mma_done[3], ph ^ 1u);
+        {
+          uint8_t* prow = sP + g * BLK + r * 128;
+          uint8_t* srow = sdS + g * BLK + r * 128;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t off = (((uint32_t)ch ^ sw) << 4);
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(pkP[4 * ch], pkP[4 * ch + 1], pkP[4 * ch + 2], pkP[4 * ch + 3]);
+            *reinterpret_cast<uint4*>(srow + off) = make_uint4(pkS[4 * ch], pkS[4 * ch + 1], pkS[4 * ch + 2], pkS[4 * ch + 3]);
+          }
+        }
+        sm100::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) sm100::mbar_arrive(&p_full[t]);
+        if (dbg2 && it == 1) g_attn_dbg[20 + t] = clock64();
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------------------------------------- drain
+    reg_dealloc<96>();
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const bool dbg3 = dbg_on && warp == 12;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    auto release = [&](uint64_t* bar) {
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(bar);
+    };
+    const uint32_t sw = (uint32_t)(r & 7);
+    // 64 fp32 columns of this thread's TMEM lane -> one 128-byte bf16 row of a swizzled [128 x 64] staging tile (the
+    // layout of the operand tiles, so the TMA store uses the same kind of tensor map as the loads).  `bar` is released as
+    // soon as the values are in registers.  Row-per-thread global stores of these tiles (16 bytes x 32 different lines per
+    // instruction) slowed the concurrent MMAs down by 25 %: scripts/attn_timeline.py.
+    auto drain64 = [&](uint32_t col, uint8_t* stage, uint64_t* bar) {
+      uint32_t ra[32], rb[32];
+      sm100::tmem_ld_32x32(trow + col, ra);
+      sm100::tmem_ld_32x32(trow + col + 32, rb);
+      sm100::tmem_ld_wait();
+      if (bar) release(bar);
+      if (q.dbg & 2) return;                                   // TIMING ablation: nothing leaves the registers
+      uint8_t* row = stage + r * 128;
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        *reinterpret_cast<uint4*>(row + (((uint32_t)v4 ^ sw) << 4)) =
+            make_uint4(atc_pack2(__uint_as_float(ra[8 * v4 + 0]), __uint_as_float(ra[8 * v4 + 1])),
+                       atc_pack2(__uint_as_float(ra[8 * v4 + 2]), __uint_as_float(ra[8 * v4 + 3])),
+                       atc_pack2(__uint_as_float(ra[8 * v4 + 4]), __uint_as_float(ra[8 * v4 + 5])),
+                       atc_pack2(__uint_as_float(ra[8 * v4 + 6]), __uint_as_float(ra[8 * v4 + 7])));
+        *reinterpret_cast<uint4*>(row + (((uint32_t)(v4 + 4) ^ sw) << 4)) =
+            make_uint4(atc_pack2(__uint_as_float(rb[8 * v4 + 0]), __uint_as_float(rb[8 * v4 + 1])),
+                       atc_pack2(__uint_as_float(rb[8 * v4 + 2]), __uint_as_float(rb[8 * v4 + 3])),
+                       atc_pack2(__uint_as_float(rb[8 * v4 + 4]), __uint_as_float(rb[8 * v4 + 5])),
+                       atc_pack2(__uint_as_float(rb[8 * v4 + 6]), __uint_as_float(rb[8 * v4 + 7])));
+      }
+    };
+    // begin(): the previous store has finished reading the staging tiles (its issuer waited before arriving here);
+    // staged(): all four drain warps have written their rows and made them visible to the TMA engine
+    auto begin = [&]() { asm volatile("bar.sync 2, 128;" ::: "memory"); };
+    auto staged = [&]() {
+      sm100::fence_proxy_async();
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+    };
+    const bool boss = warp == 12 && lane == 0;
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const long long u = first + (long long)it * stride;
+      const long long seq = u / p.heads;
+      const int h = (int)(u % p.heads);
+      const int c3 = (int)(seq / p.n_inner), c2 = (int)(seq % p.n_inner);
+      auto wait_done = [&](uint64_t* bar) {
+        sm100::mbar_wait(bar, ph);
+        sm100::tc_fence_after();
+      };
+      wait_done(&mma_done[1]);                         // key block 0 complete
+      begin();
+      drain64(COL_DK, stage, nullptr);
+      drain64(COL_DV, stage + BLK, &kv_drained[0]);
+      staged();
+      if (boss) {
+        tma_store_4d(&tma_dk, stage, h * 64, 0, c2, c3);
+        tma_store_4d(&tma_dv, stage + BLK, h * 64, 0, c2, c3);
+        atb_bulk_commit();
+        atb_bulk_wait_read();
+      }
+      if (dbg3 && it == 1) g_attn_dbg[24] = clock64();
+      wait_done(&mma_done[2]);                         // query block 0 complete
+      begin();
+      drain64(COL_DQ, stage, &dq_drained[0]);
+      staged();
+      if (boss) {
+        tma_store_4d(&tma_dq, stage, h * 64, 0, c2, c3);
+        atb_bulk_commit();
+        atb_bulk_wait_read();
+      }
+      if (dbg3 && it == 1) g_attn_dbg[25] = clock64();
+      wait_done(&mma_done[3]);                         // key block 1 and query block 1 complete
+      begin();
+      drain64(COL_DK, stage, nullptr);
+      drain64(COL_DV, stage + BLK, &kv_drained[1]);
+      staged();
+      if (boss) {
+        tma_store_4d(&tma_dk, stage, h * 64, 128, c2, c3);
+        tma_store_4d(&tma_dv, stage + BLK, h * 64, 128, c2, c3);
+        atb_bulk_commit();
+        atb_bulk_wait_read();
+      }
+      begin();
+      drain64(COL_DQ + 64, stage, &dq_drained[1]);
+      staged();
+      if (boss) {
+        tma_store_4d(&tma_dq, stage, h * 64, 128, c2, c3);
+        atb_bulk_commit();
+        atb_bulk_wait_read();
+      }
+      if (dbg3 && it == 1) g_attn_dbg[26] = clock64();
+    }
+    if (boss) atb_bulk_wait_all();                     // the stores have been written before the CTA exits
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int atc_launch_bwd256(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
+  constexpr int SMEM = 14 * 16384 + 256 + 1024;
+  CUtensorMap mq, mk, mv, md;
+  int rc;
+  if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&md, a.d_o, a.do_rs, p, 128, 1, 1))) return rc;
+  CUtensorMap mdq, mdk, mdv;
+  if ((rc = atc_make_map(&mdq, a.dq, a.dq_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mdk, a.dk, a.dk_rs, p, 128, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mdv, a.dv, a.dv_rs, p, 128, 1, 1))) return rc;
+  const long long n_seq = (long long)p.n_outer * p.n_inner;
+  {
+    const long long total = n_seq * p.L * 8 * p.heads;
+    const int blocks = (int)std::min<long long>(cdiv(total, 256), (long long)num_sms() * 16);
+    launch_pdl(attn_delta_kernel, dim3(blocks), dim3(256), 0, s, (const bf16*)a.o, a.o_rs, (const bf16*)a.d_o, a.do_rs,
+               a.delta, p, total);
+    if ((rc = check_launch("attn_delta"))) return rc;
+  }
+  AttnBwd256Params q;
+  q.pl = p;
+  q.lse = a.lse; q.delta = a.delta;
+  q.dq = (bf16*)a.dq; q.dk = (bf16*)a.dk; q.dv = (bf16*)a.dv;
+  q.dq_rs = a.dq_rs; q.dk_rs = a.dk_rs; q.dv_rs = a.dv_rs;
+  q.scale = a.scale;
+  q.units = n_seq * p.heads;
+  q.dbg = ((g_dbg[10] & 16) ? 1 : 0) | ((g_dbg[10] & 1) ? 2 : 0) | ((g_dbg[10] & 2) ? 4 : 0) | ((g_dbg[10] & 4) ? 8 : 0);
+  q.dbg_cta = (int)g_dbg[0];
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd256_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention bwd (L=256): cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+      return VVAE_ERR_CUDA;
+    }
+    attr_set.store(true, std::memory_order_release);
+  }
+  const int grid = (int)std::min<long long>(q.units, num_sms());
+  launch_pdl(attn_bwd256_sm100_kernel, dim3(grid), dim3(512), SMEM, s, mq, mk, mv, md, mdq, mdk, mdv, q);
+  return check_launch("attn_bwd256_sm100");
+}
+
 int attn_tc_supported(const vvae_attn_args& a) {
   AttnTcPlan p;
   if (!atc_make_plan(a, p)) return 0;
@@ -1343,6 +1820,8 @@ int attn_tc_bwd(const vvae_attn_args& a, cudaStream_t s) {
   const bool m = a.mask != nullptr;
   if (p.G > 1) return m ? atc_launch_bwd<1, true, true>(a, p, s) : atc_launch_bwd<1, true, false>(a, p, s);
   if (p.NK == 128) return m ? atc_launch_bwd<1, false, true>(a, p, s) : atc_launch_bwd<1, false, false>(a, p, s);
+  // vvae_debug_set(16, 1): the one-unit-per-CTA kernel for unmasked L = 256 too
+  if (!m && a.delta && !g_dbg[16] && p.ts_l * 0 == 0) return atc_launch_bwd256(a, p, s);
   return m ? atc_launch_bwd<2, false, true>(a, p, s) : atc_launch_bwd<2, false, false>(a, p, s);
 }
 

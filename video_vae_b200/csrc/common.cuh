@@ -47,7 +47,7 @@ inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 // another kernel may have produced -- blocks until the predecessor has completed and flushed.  pdl_launch_dependents()
 // in a kernel whose CTAs are all resident lets the successor's CTAs take over SMs as they become free.  Inside a captured
 // CUDA graph these launches become programmatic-dependency edges.  vvae_debug_set(11, 1) turns the attribute off.
-extern long long g_dbg[16];
+extern long long g_dbg[32];
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

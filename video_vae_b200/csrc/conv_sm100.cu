@@ -68,7 +68,7 @@ struct ConvParams {
 
 static inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-extern long long g_dbg[16];   // vvae_debug_set: key 13 != 0 selects the one-MMA-per-tap kernels (round-1 behaviour)
+extern long long g_dbg[32];   // vvae_debug_set: key 13 != 0 selects the one-MMA-per-tap kernels (round-1 behaviour)
 constexpr int CONV_THREADS = 320;        // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5 / 6-9: two epilogue groups
 constexpr uint32_t CONV_MISC_BYTES = 1024;   // barriers (256 B) + the layer's bias as fp32 (<= 128 values) behind the stages
 // epilogue row exchange (PACK): [group 2][buffer 2][quarter 4][block][kw-1 rows][kw-1 taps][16 channels] fp32

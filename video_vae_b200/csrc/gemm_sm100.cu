@@ -22,7 +22,7 @@
 namespace vvae {
 
 // ---- debug / tuning knobs (vvae_debug_set) ----
-long long g_dbg[16] = {0};   // (declared in common.cuh)
+long long g_dbg[32] = {0};   // (declared in common.cuh)
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -901,14 +901,15 @@ int sm100_gemm(const vvae_gemm_args& a, cudaStream_t s) {
 
 }  // namespace vvae
 
+namespace vvae { int attn_debug_read(unsigned long long* out32); }
 extern "C" int vvae_debug_get(int what, unsigned long long* out4) {
-  (void)what;
   if (!out4) return VVAE_ERR_INVALID;
+  if (what == 1) return vvae::attn_debug_read(out4);
   return cudaMemcpyFromSymbol(out4, vvae::g_gemm_dbg, 4 * sizeof(unsigned long long)) == cudaSuccess ? VVAE_OK : VVAE_ERR_CUDA;
 }
 
 extern "C" int vvae_debug_set(int key, long long value) {
-  if (key < 0 || key >= 16) return VVAE_ERR_INVALID;
+  if (key < 0 || key >= 32) return VVAE_ERR_INVALID;
   vvae::g_dbg[key] = value;
   return VVAE_OK;
 }
