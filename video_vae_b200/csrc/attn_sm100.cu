@@ -1357,6 +1357,11 @@ static int atl_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
 //   warps 12-15 drain: dK_j, dV_j (after each key block) and dQ_i (after each query block's last tile) leave TMEM while
 //               the other roles carry on with the next tile / unit.
 // Register budget by setmaxnreg: softmax warps 184, drain 96, producer / issuer 48.
+// Measured (scripts/attn_timeline.py, 128 sequences x 8 heads): 101 us against 184 us, 17 k cycles per unit = 3.5-3.9 k
+// per tile (contraction 2.5 k + P/dS store 0.7 k: P/dS are single-buffered, so the contraction of tile T cannot overlap
+// the store of tile T+1) plus ~3 k at the start of a unit, where S/dP of the second tile wait for Q1 / dO1, which the
+// last MMAs of the previous unit were still reading.  A second buffer for that group (instead of the staging tiles, with
+// the gradient tiles staged in dead operand buffers) moves the same wait to K1 / V1: tried, no gain, not kept.
 // Every mbarrier completes exactly once per unit, so a wait's parity is the unit counter's low bit.
 struct AttnBwd256Params {
   AttnTcPlan pl;
