@@ -107,6 +107,11 @@ struct Sm100Params {
   float* bsum;             // MODE_BSUM: += column sums of op(B) over K (a Linear's bias gradient, fused into its wgrad)
   // descriptor encodings (bytes); overridable through vvae_debug_set for bring-up
   uint32_t a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv;
+  // Partial last wave: the last `tiles_mn % clusters` output tiles are cut into tail_s column slices of BN / tail_s, so
+  // that the clusters that would idle through the last wave share its work (tail_s = 1: off).  Tiles [0, full_tiles) are
+  // whole, tile full_tiles + s*tail_s + q is slice q of whole-tile index full_tiles + s.
+  int full_tiles, tail_s, total_tiles;
+  uint32_t idesc_tail;     // instruction descriptor with N = BN / tail_s
   int dbg;                 // vvae_debug_set(10): TIMING ablations, wrong results (1: skip the A-tile TMA loads, 2: skip B)
   // MODE_QKN
   const float* qk_qs; const float* qk_ks; const bf16* rope_cos; const bf16* rope_sin;
@@ -256,6 +261,26 @@ __device__ __forceinline__ float fast_dsilu(float x) {
   return s * fmaf(x, 1.f - s, 1.f);
 }
 
+// tile index -> (row block, first column, columns) of the output tile (see Sm100Params::tail_s)
+struct TileGeo { int mblk, n0, ncols; };
+template <int BN>
+__device__ __forceinline__ TileGeo tile_geo(const Sm100Params& p, int tile, int tiles_mn) {
+  TileGeo g;
+  if (p.tail_s == 1 || tile < p.full_tiles) {
+    const int mn = tile % tiles_mn;
+    g.mblk = mn / p.n_tiles;
+    g.n0 = (mn % p.n_tiles) * BN;
+    g.ncols = BN;
+  } else {
+    const int t2 = tile - p.full_tiles;
+    const int mn = p.full_tiles + t2 / p.tail_s, q = t2 % p.tail_s;
+    g.ncols = BN / p.tail_s;
+    g.mblk = mn / p.n_tiles;
+    g.n0 = (mn % p.n_tiles) * BN + q * g.ncols;
+  }
+  return g;
+}
+
 template <int BN, int CG, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(MODE == MODE_QKN ? 192 : 384, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -313,7 +338,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
   pdl_wait();                // prologue done; from here on global memory of the previous kernel is read / written
 
   const int tiles_mn = p.m_tiles * p.n_tiles;
-  const int total_tiles = tiles_mn * p.splits;
+  const int total_tiles = p.total_tiles;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs of a pair load their own halves) =====================
@@ -321,9 +346,11 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int split = tile / tiles_mn, mn = tile % tiles_mn;
-        const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM;
-        const int n0 = (mn % p.n_tiles) * BN + (int)cta_rank * (BN / CG);
+        const int split = p.tail_s == 1 ? tile / tiles_mn : 0;
+        const TileGeo geo = tile_geo<BN>(p, tile, tiles_mn);
+        const int m0 = geo.mblk * (BM * CG) + (int)cta_rank * BM;
+        // (a column slice loads the whole B box from its first row: the MMA reads the first ncols / CG rows of it)
+        const int n0 = geo.n0 + (int)cta_rank * (geo.ncols / CG);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -367,7 +394,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
       }
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int split = tile / tiles_mn;
+        const int split = p.tail_s == 1 ? tile / tiles_mn : 0;
+        const uint32_t idesc_t = (p.tail_s == 1 || tile < p.full_tiles) ? idesc : p.idesc_tail;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         if (!(p.dbg & 8)) sm100::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -393,7 +421,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
             const uint64_t db = sm100::make_smem_desc_sw128(b_addr + k * p.b_kadv, p.b_lbo, p.b_sbo);
             if (k == BK / UMMA_K - 1)   // (also valid across tiles: the stage ring does not care about tile borders)
               ready = (p.dbg & 4) ? true : sm100::mbar_test_wait(&full_bar[nstage], nphase);
-            umma_f16_cg<CG>(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16_cg<CG>(d_tmem, da, db, idesc_t, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_cg<CG>(BSUM ? &mma_done[stage] : &empty_bar[stage]);  // the MMAs have read the slot (both CTAs)
           stage = nstage;
@@ -601,21 +629,22 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
     uint32_t pf_g = 0;
     auto prefetch_aux = [&]() {
       if (pf_tile >= total_tiles) return;
-      const int mn = pf_tile % tiles_mn;
-      const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (mn % p.n_tiles) * BN;
+      const TileGeo pg = tile_geo<BN>(p, pf_tile, tiles_mn);
+      const int m0 = pg.mblk * (BM * CG) + (int)cta_rank * BM;
       const uint32_t b = pf_g & (AUXR - 1);
       sm100::mbar_expect_tx(&aux_full[b], STG_BYTES);
-      sm100::tma_load_2d(stg_aux + b * STG_BYTES, &tma_ai, &aux_full[b], n0 + 64 * pf_c, m0);
+      sm100::tma_load_2d(stg_aux + b * STG_BYTES, &tma_ai, &aux_full[b], pg.n0 + 64 * pf_c, m0);
       ++pf_g;
-      if (++pf_c == NCH) { pf_c = 0; pf_tile += num_clusters; }
+      if (++pf_c == pg.ncols / 64) { pf_c = 0; pf_tile += num_clusters; }
     };
     if (use_aux && etid == 0) {
       for (int i = 0; i < AUXR; ++i) prefetch_aux();
     }
 
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int mn = tile % tiles_mn;
-      const int m0 = (mn / p.n_tiles) * (BM * CG) + (int)cta_rank * BM, n0 = (mn % p.n_tiles) * BN;
+      const TileGeo geo = tile_geo<BN>(p, tile, tiles_mn);
+      const int m0 = geo.mblk * (BM * CG) + (int)cta_rank * BM, n0 = geo.n0;
+      const int nch = p.tma_epi ? geo.ncols / 64 : NCH;   // 64-column chunks of this tile (column slices: fewer)
       float* bias_t = s_bias;   // single buffer: every reader of the previous tile's slice has passed that tile's last barrier
       if (p.tma_epi && p.bias) {                 // this tile's bias slice -> smem (read back as broadcasts)
         for (int j = etid; j < BN; j += 256) bias_t[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
@@ -640,7 +669,7 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < NCH; ++c, ++g) {
+        for (int c = 0; c < nch; ++c, ++g) {
           const int nc = n0 + 64 * c;
           const uint32_t b = g & 1;
           uint4 ax[4];
@@ -793,6 +822,29 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
   p.tma_epi = p.out_f32 ? 0 : 1;
   p.bsum = a.bsum_accum;
   p.dbg = (int)g_dbg[10];
+  p.full_tiles = tiles_mn; p.tail_s = 1; p.total_tiles = tiles_mn * p.splits; p.idesc_tail = 0;
+  if (CG == 2 && BN == 256 && p.splits == 1 && p.tma_epi && MODE != MODE_BSUM && MODE != MODE_QKN &&
+      tiles_mn > n_clusters && !g_dbg[17]) {   // vvae_debug_set(17, 1): whole tiles only
+    // relative cost of one 256 x (256/s) slice: its MMAs fetch the same A operand for fewer columns
+    const double cost[5] = {0, 1.0, 0.6, 0, 0.4};
+    const int R = tiles_mn % n_clusters;
+    int best = 1;
+    double best_t = 1.0;
+    if (R) {
+      for (int sl = 2; sl <= 4; sl *= 2) {
+        if (sl == 4 && B_MN) continue;           // an MN-major B slice must be a whole 64-column box per CTA
+        const double t = (double)cdiv((long long)R * sl, n_clusters) * cost[sl];
+        if (t < best_t - 1e-9) { best_t = t; best = sl; }
+      }
+    }
+    if (g_dbg[17] > 1 && R) best = (int)g_dbg[17] <= 4 && !((int)g_dbg[17] == 4 && B_MN) ? (int)g_dbg[17] : best;
+    if (best > 1) {
+      p.tail_s = best;
+      p.full_tiles = tiles_mn - R;
+      p.total_tiles = p.full_tiles + R * best;
+      p.idesc_tail = sm100::make_idesc_bf16(BM * CG, BN / best, A_MN, B_MN);
+    }
+  }
   p.qk_qs = a.qk_q_scale; p.qk_ks = a.qk_k_scale;
   p.rope_cos = (const bf16*)a.rope_cos; p.rope_sin = (const bf16*)a.rope_sin;
   p.pos_div = a.rope_pos_div > 0 ? a.rope_pos_div : 1; p.pos_mod = a.rope_pos_mod > 0 ? a.rope_pos_mod : 1;
@@ -832,7 +884,7 @@ static int launch_sm100(const vvae_gemm_args& a, cudaStream_t s) {
     }
     attr_set.store(true, std::memory_order_release);
   }
-  const int total = tiles_mn * p.splits;
+  const int total = p.total_tiles;
   int clusters = std::min(total, g_dbg[0] ? (int)g_dbg[0] : n_clusters);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * CG));
