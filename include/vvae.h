@@ -172,6 +172,11 @@ int vvae_patchify(const void* video, int in_dtype, void* tokens, int b_t, int H,
 /* tokens [b_t,(h w),(p1 p2 cu)] <-> voxels [b_t,(h p1),(w p2),cu]; dir 0 = tokens->voxels, 1 = voxels->tokens. */
 int vvae_pixel_shuffle(const void* src, void* dst, int b_t, int H, int W, int CU, int P, int dir, int dtype,
                        vvae_stream_t stream);
+/* The same with `vox_ld` >= cu elements between consecutive voxels (bf16): dir 0 also writes the pad channels
+ * [cu, vox_ld) as zeros, dir 1 ignores them.  The U-Net input (train/unet.py:155-160, 12 channels) is produced at a
+ * pitch of 16, the channel block the tensor-core convolutions gather. */
+int vvae_pixel_shuffle_pitched(const void* src, void* dst, int b_t, int H, int W, int CU, int P, int dir, long long vox_ld,
+                               int dtype, vvae_stream_t stream);
 
 /* ---- conv3d, NDHWC, 'SAME', stride 1 (nnx.Conv: train/unet.py:13-21,111-113,144-153) ----
  * x [B,T,H,W,Cin] with channel stride x_ld (>= Cin, lets x be a slice of a concat buffer),

@@ -95,6 +95,7 @@ _SIGS = {
     "vvae_attn_bwd": ([C.POINTER(AttnArgs), vp], i32),
     "vvae_patchify": ([vp, i32, vp, i32, i32, i32, i32, i32, i32, vp], i32),
     "vvae_pixel_shuffle": ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+    "vvae_pixel_shuffle_pitched": ([vp, vp, i32, i32, i32, i32, i32, i32, ll, i32, vp], i32),
     "vvae_conv3d_fwd": ([C.POINTER(ConvArgs), vp], i32),
     "vvae_conv3d_dgrad": ([C.POINTER(ConvArgs), vp], i32),
     "vvae_conv3d_wgrad": ([C.POINTER(ConvArgs), vp], i32),

@@ -95,6 +95,42 @@ __global__ void rearrange_vec_kernel(const T* __restrict__ src, T* __restrict__ 
   }
 }
 
+// same mapping with a voxel-side pixel pitch vox_ld >= C (bf16, C % 4 == 0, vox_ld % 8 == 0): one thread per pixel; the
+// pad channels [C, vox_ld) are written as zeros (tokens -> voxels) / ignored (voxels -> tokens).  The U-Net's tensor-core
+// convolutions read 16-channel blocks, so its 12-channel input lives at a pitch of 16 from the start.
+template <int CP>
+__global__ void rearrange_pitched_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long pixels, int H, int W,
+                                         int C, int P, int vox_ld, int to_tokens) {
+  const int hp = H / P, wp = W / P;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < pixels; i += stride) {                 // i = voxel-side pixel index (bt, y, x)
+    const int x = (int)(i % W);
+    const long long t1 = i / W;
+    const int y = (int)(t1 % H);
+    const long long bt = t1 / H;
+    const int h = y / P, p1 = y % P, w = x / P, p2 = x % P;
+    const long long tok = ((((bt * hp + h) * wp + w) * P + p1) * P + p2) * C;
+    uint2 v[CP / 4];
+    if (to_tokens) {
+      const bf16* sp = src + i * vox_ld;
+#pragma unroll
+      for (int j = 0; j < CP / 4; ++j)
+        if (4 * j < C) v[j] = *reinterpret_cast<const uint2*>(sp + 4 * j);
+#pragma unroll
+      for (int j = 0; j < CP / 4; ++j)
+        if (4 * j < C) *reinterpret_cast<uint2*>(dst + tok + 4 * j) = v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < CP / 4; ++j) v[j] = 4 * j < C ? *reinterpret_cast<const uint2*>(src + tok + 4 * j) : make_uint2(0u, 0u);
+      bf16* dp = dst + i * vox_ld;
+#pragma unroll
+      for (int j = 0; j < CP / 8; ++j)
+        if (8 * j < vox_ld) *reinterpret_cast<uint4*>(dp + 8 * j) = make_uint4(v[2 * j].x, v[2 * j].y, v[2 * j + 1].x, v[2 * j + 1].y);
+    }
+  }
+}
+
 // ---------------- max-pool (1,2,2) ----------------
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* __restrict__ x, long long x_ld, T* __restrict__ y, long long total, int H,
@@ -586,6 +622,25 @@ int vvae_pixel_shuffle(const void* src, void* dst, int b_t, int H, int W, int CU
   const long long total = (long long)b_t * H * W * CU;
   VVAE_DISPATCH_DTYPE(dtype, T, return rearrange_same<T>(src, dst, total, H, W, CU, P, dir, as_stream(stream)));
   return VVAE_OK;
+}
+
+int vvae_pixel_shuffle_pitched(const void* src, void* dst, int b_t, int H, int W, int CU, int P, int dir, long long vox_ld,
+                               int dtype, vvae_stream_t stream) {
+  if (b_t <= 0) return VVAE_OK;
+  VVAE_REQUIRE(src && dst && P > 0 && H % P == 0 && W % P == 0 && vox_ld >= CU, "pixel_shuffle_pitched: bad arguments");
+  if (vox_ld == CU) return vvae_pixel_shuffle(src, dst, b_t, H, W, CU, P, dir, dtype, stream);
+  VVAE_REQUIRE(dtype == VVAE_BF16 && CU % 4 == 0 && vox_ld % 8 == 0 && vox_ld <= 32 && vox_ld - CU < 8 + (CU % 8) &&
+                   ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0),
+               "pixel_shuffle_pitched: bf16, channels %% 4 == 0 and a pitch of ceil8..ceil16(channels) <= 32 expected "
+               "(CU=%d pitch=%lld)", CU, vox_ld);
+  const long long pixels = (long long)b_t * H * W;
+  const int blocks = ew_blocks(pixels);
+  cudaStream_t s = as_stream(stream);
+  if (vox_ld <= 16)
+    rearrange_pitched_kernel<16><<<blocks, 256, 0, s>>>((const bf16*)src, (bf16*)dst, pixels, H, W, CU, P, (int)vox_ld, dir);
+  else
+    rearrange_pitched_kernel<32><<<blocks, 256, 0, s>>>((const bf16*)src, (bf16*)dst, pixels, H, W, CU, P, (int)vox_ld, dir);
+  return check_launch("pixel_shuffle_pitched");
 }
 
 int vvae_maxpool122_fwd(const void* x, long long x_ld, void* y, int b_t, int H, int W, int C, int dtype,

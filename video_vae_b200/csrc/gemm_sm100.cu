@@ -765,7 +765,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
 // ------------------------------------------------------------------ host launch
 bool sm100_gemm_supported(const vvae_gemm_args& a) {
   if (a.dtype != VVAE_BF16) return false;
-  if (a.M < 128 || a.N < 64 || a.K < 64) return false;
+  // (weight gradients of narrow Linears: M = 96 rows of a 128-row tile; the boxes beyond M are zero-filled by TMA)
+  if (a.M < (a.transA && a.out_dtype == VVAE_F32 ? 64 : 128) || a.N < 64 || a.K < 64) return false;
   if (a.N % 8 != 0) return false;
   if (a.lda % 8 || a.ldb % 8) return false;
   if (((uintptr_t)a.A % 16) || ((uintptr_t)a.B % 16) || ((uintptr_t)a.C % 16)) return false;

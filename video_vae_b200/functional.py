@@ -93,6 +93,24 @@ def _as_2d(x, D):
     return x2 if x2.is_contiguous() else x2.contiguous()
 
 
+def _rows_2d(x, D):
+    """[.., D] -> [rows, D] keeping a row pitch > D when the leading dims are dense over it (no copy); else packed."""
+    if x.stride(-1) == 1 and x.dim() >= 2:
+        ld, ok = x.stride(-2), True
+        for i in range(x.dim() - 2):
+            ok = ok and x.stride(i) == x.stride(i + 1) * x.shape[i + 1]
+        if ok and ld >= D:
+            return torch.as_strided(x, (x.numel() // D, D), (ld, 1), x.storage_offset())
+    return _as_2d(x, D)
+
+
+def unet_input_pitch(C, dtype):
+    """Elements per voxel of the U-Net's input map: ceil16(C) in bf16 (tensor-core conv channel blocks), else C."""
+    if dtype == torch.bfloat16 and C % 16 != 0 and C % 4 == 0 and C < 32:
+        return (C + 15) // 16 * 16
+    return C
+
+
 # ------------------------------------------------------------------ Linear
 class LinearFn(Function):
     """y = x @ K + b (nnx.Linear); x may arrive in another float dtype (cast to the compute dtype first)."""
@@ -327,12 +345,16 @@ class UnembedFn(Function):
         x2 = _as_2d(x, D)
         y1 = ops.gemm(x2, shadow(wl, dtype), bias=bl.detach())
         y2 = ops.gemm(y1, shadow(wu, dtype), bias=bu.detach())
-        feats = ops.pixel_shuffle(y2, b * t, H, W, CU, P, to_tokens=False)
-        rgb = ops.gemm(feats.view(-1, CU), shadow(wd, dtype), bias=bd.detach())
+        # bf16: the features are the U-Net's input, whose tensor-core convolutions gather 16-channel blocks: produce them
+        # at that pitch (zeroed pad channels) instead of re-packing 268 MB later; the returned tensor is the [.., :CU] view
+        ld = unet_input_pitch(CU, dtype)
+        feats = ops.pixel_shuffle(y2, b * t, H, W, CU, P, to_tokens=False, vox_ld=ld)
+        f2 = feats.view(-1, ld)[:, :CU]
+        rgb = ops.gemm(f2, shadow(wd, dtype), bias=bd.detach())
         ctx.save_for_backward(x2, y1, feats, wl, bl, wu, bu, wd, bd)
         ctx.geo, ctx.dtype, ctx.x_shape = geo, dtype, x.shape
         Cc = wd.shape[1]
-        return feats.view(b, t, H, W, CU), rgb.view(b, t, H, W, Cc)
+        return feats.view(b, t, H, W, ld)[..., :CU], rgb.view(b, t, H, W, Cc)
 
     @staticmethod
     def backward(ctx, dfeats, drgb):
@@ -340,18 +362,23 @@ class UnembedFn(Function):
         b, t, H, W, P, CU = ctx.geo
         dtp = ctx.dtype
         Cc = wd.shape[1]
-        f2 = feats.view(-1, CU)
+        ld = feats.shape[-1]
+        f2 = feats.view(-1, ld)[:, :CU]
+        if dfeats is not None:                         # [.., :CU] view of a pitched buffer (U-Net backward) or packed
+            dfeats = _rows_2d(dfeats, CU)
         if drgb is not None:
             drgb2 = _as_2d(drgb, Cc)
             ops.gemm(f2, drgb2, transA=True, out=grad_buf(wd), accumulate=True)
             ops.colsum_accum(drgb2, grad_buf(bd))
             if dfeats is not None:
-                df = ops.gemm(drgb2, shadow(wd, dtp), transB=True, epilogue=EPI_RESIDUAL, aux_in=_as_2d(dfeats, CU))
+                df = ops.gemm(drgb2, shadow(wd, dtp), transB=True, epilogue=EPI_RESIDUAL, aux_in=dfeats)
             else:
                 df = ops.gemm(drgb2, shadow(wd, dtp), transB=True)
+            dy2 = ops.pixel_shuffle(df, b * t, H, W, CU, P, to_tokens=True)
+        elif dfeats.stride(0) != CU and dfeats.stride(0) == unet_input_pitch(CU, dtp):
+            dy2 = ops.pixel_shuffle(dfeats, b * t, H, W, CU, P, to_tokens=True, vox_ld=dfeats.stride(0))
         else:
-            df = _as_2d(dfeats, CU)
-        dy2 = ops.pixel_shuffle(df, b * t, H, W, CU, P, to_tokens=True)
+            dy2 = ops.pixel_shuffle(_as_2d(dfeats, CU), b * t, H, W, CU, P, to_tokens=True)
         ops.gemm(y1, dy2, transA=True, out=grad_buf(wu), accumulate=True, bsum=grad_buf(bu))
         dy1 = ops.gemm(dy2, shadow(wu, dtp), transB=True)
         ops.gemm(x2, dy1, transA=True, out=grad_buf(wl), accumulate=True, bsum=grad_buf(bl))

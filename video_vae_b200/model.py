@@ -75,7 +75,8 @@ class Decoder(nn.Module):
         for layer in self.layers:
             x = layer(x, tmask)
         feats, rgb = self.patch_unembedding(x)
-        return self.unet(feats, residual=rgb)                            # x + unet_output, fused (model.py:95-96)
+        # x + unet_output, fused (model.py:95-96); in bf16 feats is a view of a 16-channel-pitch map (UnembedFn)
+        return self.unet(feats, residual=rgb, zero_padded=feats.stride(-2) != feats.shape[-1])
 
 
 class VideoVAE(nn.Module):

@@ -223,11 +223,18 @@ def patchify(video, P, dtype):
     return out
 
 
-def pixel_shuffle(src, b_t, H, W, CU, P, to_tokens):
+def pixel_shuffle(src, b_t, H, W, CU, P, to_tokens, vox_ld=None):
+    """``vox_ld`` (> CU): the voxel side has that many elements per pixel; to_tokens=False returns the padded buffer
+    [b_t, H, W, vox_ld] with zeroed pad channels."""
+    vox_ld = vox_ld or CU
     if to_tokens:
         dst = torch.empty((b_t * (H // P) * (W // P), P * P * CU), dtype=src.dtype, device=src.device)
     else:
-        dst = torch.empty((b_t, H, W, CU), dtype=src.dtype, device=src.device)
+        dst = torch.empty((b_t, H, W, vox_ld), dtype=src.dtype, device=src.device)
+    if vox_ld != CU:
+        check(lib.vvae_pixel_shuffle_pitched(ptr(src), ptr(dst), b_t, H, W, CU, P, int(to_tokens), vox_ld, dt(src), stream()),
+              "vvae_pixel_shuffle_pitched")
+        return dst
     check(lib.vvae_pixel_shuffle(ptr(src), ptr(dst), b_t, H, W, CU, P, int(to_tokens), dt(src), stream()),
           "vvae_pixel_shuffle")
     return dst

@@ -78,17 +78,31 @@ def _pad16(c):
     return (c + 15) // 16 * 16
 
 
-def _conv_fwd(x, x_ld, Cin, conv, dtype, residual=None, out=None, out_ld=None):
+def _padded_buffer(shape4, ld, dtype, device, kernel_pads):
+    """Map with ``ld`` > C elements per voxel whose pad channels must read as zero: the tensor-core conv kernels write
+    those zeros themselves (``pad_out``), the generic kernels do not."""
+    shape = tuple(shape4) + (ld,)
+    return torch.empty(shape, dtype=dtype, device=device) if kernel_pads else torch.zeros(shape, dtype=dtype, device=device)
+
+
+def _conv_fwd(x, x_ld, Cin, conv, dtype, residual=None, out=None, out_ld=None, alloc_ld=None):
+    """``alloc_ld``: produce the output at that channel pitch (> Cout, pad channels zero) in a fresh buffer."""
     w = F_.shadow(conv.kernel, dtype)
     Cout = conv.kernel.shape[4]
-    y_ld = out_ld if out is not None else Cout
+    if alloc_ld is not None:
+        out_ld = alloc_ld
+    y_ld = out_ld if (out is not None or alloc_ld is not None) else Cout
     wp = _wprep(conv, 0, dtype, tuple(x.shape[:4]), x_ld, y_ld)
+    if alloc_ld is not None:
+        out = _padded_buffer(x.shape[:4], alloc_ld, dtype, x.device, wp is not None and alloc_ld >= _pad16(Cout) > Cout)
     return ops.conv3d_fwd(x, w, conv.bias.detach(), conv.ks, Cin, Cout, x_ld=x_ld, residual=residual, out=out,
                           out_ld=out_ld, wprep=wp, pad_out=out is not None and out_ld >= _pad16(Cout) > Cout)
 
 
-def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=None, dx_ld=None, bias_done=False):
-    """``bias_done``: the producer of ``dy`` (GroupNorm backward) already accumulated the bias gradient."""
+def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=None, dx_ld=None, bias_done=False,
+              dx_alloc_ld=None):
+    """``bias_done``: the producer of ``dy`` (GroupNorm backward) already accumulated the bias gradient.
+    ``dx_alloc_ld``: produce dx at that channel pitch (> Cin, pad channels zero) in a fresh buffer."""
     Cout = conv.kernel.shape[4]
     dy_ld = dy_ld or dy.shape[-1]
     ops.conv3d_wgrad_accum(x, dy, F_.grad_buf(conv.kernel), conv.ks, Cin, Cout, x_ld=x_ld, dy_ld=dy_ld)
@@ -96,8 +110,13 @@ def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=No
         ops.colsum_accum(dy.reshape(-1, dy_ld)[:, :Cout], F_.grad_buf(conv.bias))
     if not need_dx:
         return None
-    o_ld = dx_ld if dx_out is not None else Cin
+    if dx_alloc_ld is not None:
+        dx_ld = dx_alloc_ld
+    o_ld = dx_ld if (dx_out is not None or dx_alloc_ld is not None) else Cin
     wp = _wprep(conv, 1, dtype, tuple(dy.shape[:4]), o_ld, dy_ld)
+    if dx_alloc_ld is not None:
+        dx_out = _padded_buffer(dy.shape[:4], dx_alloc_ld, dy.dtype, dy.device,
+                                wp is not None and dx_alloc_ld >= _pad16(Cin) > Cin)
     return ops.conv3d_dgrad(dy, F_.shadow(conv.kernel, dtype), conv.ks, Cin, Cout, dy_ld=dy_ld, out=dx_out, out_ld=dx_ld,
                             wprep=wp, pad_out=dx_out is not None and dx_ld >= _pad16(Cin) > Cin)
 
@@ -123,11 +142,8 @@ def _block_bwd(dy, dy_ld, tp, blk, dtype, need_dx=True):
     dc = ops.groupnorm_silu_bwd(dy, dy_ld, tp.c, blk.norm.scale.detach(), blk.norm.bias.detach(), tp.mean, tp.rstd,
                                 F_.grad_buf(blk.norm.scale), F_.grad_buf(blk.norm.bias), blk.norm.num_groups,
                                 dx_colsum=F_.grad_buf(blk.conv.bias))
-    dx_out = dx_ld = None
-    if need_dx and tp.x_ld != tp.Cin:
-        dx_ld = tp.x_ld
-        dx_out = torch.zeros(tuple(tp.x.shape[:4]) + (dx_ld,), dtype=dc.dtype, device=dc.device)
-    return _conv_bwd(dc, tp.x, tp.x_ld, tp.Cin, blk.conv, dtype, need_dx, dx_out=dx_out, dx_ld=dx_ld, bias_done=True)
+    alloc_ld = tp.x_ld if (need_dx and tp.x_ld != tp.Cin) else None
+    return _conv_bwd(dc, tp.x, tp.x_ld, tp.Cin, blk.conv, dtype, need_dx, bias_done=True, dx_alloc_ld=alloc_ld)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -270,21 +286,28 @@ class UNetFn(Function):
     """Whole U-Net (train/unet.py:155-188) + fused ``residual + unet(x)`` as a single tape."""
 
     @staticmethod
-    def forward(ctx, x, residual, net, *params):
+    def forward(ctx, x, residual, net, zero_padded, *params):
         require_device()
         dtype = net.dtype
-        if x.dtype != dtype:
-            x = ops.cast(x.contiguous(), dtype)
-        x = x.contiguous()
         B, T, H, W, C0 = x.shape
-        # the tensor-core conv gathers channels in blocks of 16: give 12-channel maps a 16-channel pitch (zero pads)
+        # the tensor-core conv gathers channels in blocks of 16: 12-channel maps get a 16-channel pitch (zero pads)
         C0p = _pad16(C0) if dtype == torch.bfloat16 else C0
+        # ``zero_padded``: x is the [.., :C0] view of such a map already (PatchUnEmbedding produces it that way)
+        pitched = (bool(zero_padded) and C0p != C0 and x.dtype == dtype and
+                   tuple(x.stride()) == (T * H * W * C0p, H * W * C0p, W * C0p, C0p, 1))
+        ctx.x_pitched = pitched
+        if pitched:
+            x = torch.as_strided(x, (B, T, H, W, C0p), x.stride(), x.storage_offset())
+        else:
+            if x.dtype != dtype:
+                x = ops.cast(x.contiguous(), dtype)
+            x = x.contiguous()
         if C0p != C0:
-            xp = torch.zeros((B, T, H, W, C0p), dtype=dtype, device=x.device)
-            ops.copy_channels(x, C0, 0, xp, C0p, 0, B * T * H * W, C0)
-            x = xp
-            pm = torch.zeros((B, T, H, W, C0p), dtype=dtype, device=x.device)
-            cur = _conv_fwd(x, C0p, C0, net.patch_mixer, dtype, out=pm, out_ld=C0p)
+            if not pitched:
+                xp = torch.zeros((B, T, H, W, C0p), dtype=dtype, device=x.device)
+                ops.copy_channels(x, C0, 0, xp, C0p, 0, B * T * H * W, C0)
+                x = xp
+            cur = _conv_fwd(x, C0p, C0, net.patch_mixer, dtype, alloc_ld=C0p)
         else:
             cur = _conv_fwd(x, C0, C0, net.patch_mixer, dtype)
         tape = {"x": x, "C0": C0, "C0p": C0p}
@@ -354,16 +377,19 @@ class UNetFn(Function):
         x, C0, C0p = tape["x"], tape["C0"], tape["C0p"]
         need_dx = ctx.needs_input_grad[0]
         if C0p != C0:
-            dxp = torch.zeros(x.shape, dtype=x.dtype, device=x.device) if need_dx else None
-            dx = _conv_bwd(dcur, x, C0p, C0, net.patch_mixer, dtype, need_dx=need_dx, dy_ld=C0p, dx_out=dxp, dx_ld=C0p)
-            if need_dx:
+            dxp = _conv_bwd(dcur, x, C0p, C0, net.patch_mixer, dtype, need_dx=need_dx, dy_ld=C0p,
+                            dx_alloc_ld=C0p if need_dx else None)
+            dx = None
+            if need_dx and ctx.x_pitched:
+                dx = dxp[..., :C0]                     # the consumer (UnembedFn.backward) reads it at this pitch
+            elif need_dx:
                 dx = torch.empty(tuple(x.shape[:4]) + (C0,), dtype=x.dtype, device=x.device)
                 ops.copy_channels(dxp, C0p, 0, dx, C0, 0, dx.numel() // C0, C0)
         else:
             dx = _conv_bwd(dcur, x, C0, C0, net.patch_mixer, dtype, need_dx=need_dx)
         F_._notify(list(net.parameters()))
         ctx.tape = None
-        return (dx, dout if ctx.has_res else None, None) + (None,) * (len(list(net.parameters())))
+        return (dx, dout if ctx.has_res else None, None, None) + (None,) * (len(list(net.parameters())))
 
 
 class UNet(nn.Module):
@@ -392,6 +418,8 @@ class UNet(nn.Module):
         self.final_conv = Conv(base_features, out_features, (1, 1, 1), rngs, dtype, param_dtype, zero_init=True,
                                device=device)
 
-    def forward(self, x, residual=None):
-        """``residual`` (optional, [b,t,H,W,out]) is added to the output inside final_conv's epilogue."""
-        return UNetFn.apply(x, residual, self, *self.parameters())
+    def forward(self, x, residual=None, zero_padded=False):
+        """``residual`` (optional, [b,t,H,W,out]) is added to the output inside final_conv's epilogue.
+        ``zero_padded``: x is the [.., :C] view of a map with ceil16(C) elements per voxel whose pad channels are zero
+        (what PatchUnEmbedding returns in bf16): it is consumed in place."""
+        return UNetFn.apply(x, residual, self, zero_padded, *self.parameters())
