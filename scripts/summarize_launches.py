@@ -2,6 +2,8 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel: launches, total ms, share.
 
     python scripts/summarize_launches.py gpurun_out/launches.csv [steps_captured] > profiles/rNN_launches.md
+    python scripts/summarize_launches.py gpurun_out/launches.csv --steps-between adam_kernel 2
+        keeps exactly the launches after the 1st occurrence of that kernel up to and including the 3rd (= 2 whole steps)
 """
 import collections
 import csv
@@ -11,11 +13,21 @@ import sys
 
 def main():
     path = sys.argv[1]
-    steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+    marker = None
+    if len(sys.argv) > 3 and sys.argv[2] == "--steps-between":
+        marker, steps = sys.argv[3], float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+    else:
+        steps = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
     with open(path) as f:
         lines = [ln for ln in f if not ln.startswith("==")]
+    rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if marker:
+        hits = [i for i, r in enumerate(rows) if marker in r["Kernel Name"]]
+        if len(hits) < int(steps) + 1:
+            sys.exit(f"only {len(hits)} launches of {marker} in {path}")
+        rows = rows[hits[0] + 1:hits[int(steps)] + 1]
     agg = collections.defaultdict(lambda: [0, 0.0])
-    for r in csv.DictReader(lines):
+    for r in rows:
         if r.get("Metric Name") != "gpu__time_duration.sum":
             continue
         name = re.sub(r"^void ", "", re.sub(r"[<(].*", "", r["Kernel Name"]))
