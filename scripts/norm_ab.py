@@ -64,3 +64,38 @@ for mode in (0, 2):
         out[f"mode{mode}_{nm}_maxrel"] = float(((a - b).abs().max() / b.abs().max()).item())
 out["fwd_bytes"] = N * D * 4; out["bwd_bytes"] = N * D * 8
 print(json.dumps(out))
+
+# ---- QK-norm + RoPE backward at [32768, 1536] (8 heads x 64): register-staged (vvae_debug_set(7, 0x100)) vs streaming
+H, HD = 8, 64
+qkv = torch.randn(N, 3 * H * HD, device="cuda", generator=g).bfloat16()
+dq0 = torch.randn(N, 3 * H * HD, device="cuda", generator=g).bfloat16()
+qs = torch.randn(HD, device="cuda", generator=g); ks = torch.randn(HD, device="cuda", generator=g)
+pos = torch.arange(256, device="cuda").float()[:, None] * torch.exp(-torch.arange(0, HD, 2, device="cuda").float() / HD * 9.2)[None]
+emb = torch.cat([pos, pos], -1)
+cos, sin = torch.cos(emb).bfloat16().contiguous(), torch.sin(emb).bfloat16().contiguous()
+qres = {}
+qout = {}
+for mode in (0x100, 0):
+    lib.vvae_debug_set(7, mode)
+    d = dq0.clone()
+    dqs = torch.zeros(HD, device="cuda"); dks = torch.zeros(HD, device="cuda"); dbqk = torch.zeros(2 * H * HD, device="cuda")
+    ops.qknorm_rope_bwd_(d, qkv, qs, ks, cos, sin, dqs, dks, H, HD, 1, 256, dbias_qk=dbqk)
+    torch.cuda.synchronize()
+    qres[mode] = (d, dqs, dks, dbqk)
+    d2 = dq0.clone()
+    qout["qknorm_bwd_%s_us" % ("stream" if mode == 0 else "regs")] = round(timed(
+        lambda: ops.qknorm_rope_bwd_(d2, qkv, qs, ks, cos, sin, dqs, dks, H, HD, 1, 256, dbias_qk=dbqk)), 2)
+lib.vvae_debug_set(7, 0)
+qout["dqkv_bit_identical"] = bool(torch.equal(qres[0][0], qres[0x100][0]))
+for i, nm in ((1, "dq_scale"), (2, "dk_scale"), (3, "dbias")):
+    qout[nm + "_maxrel"] = float(((qres[0][i] - qres[0x100][i]).abs().max() / qres[0x100][i].abs().max()).item())
+for mode, nm in ((0, "stream_16x2_nobias"), (0x200, "stream_8x4_nobias"), (0x100, "regs_nobias")):
+    lib.vvae_debug_set(7, mode)
+    d2 = dq0.clone()
+    ops.qknorm_rope_bwd_(d2, qkv, qs, ks, cos, sin, dqs, dks, H, HD, 1, 256)
+    qout[nm + "_same"] = bool(torch.equal(d2, qres[0x100][0]))
+    d2 = dq0.clone()
+    qout["qknorm_bwd_%s_us" % nm] = round(timed(lambda: ops.qknorm_rope_bwd_(d2, qkv, qs, ks, cos, sin, dqs, dks, H, HD, 1, 256)), 2)
+lib.vvae_debug_set(7, 0)
+qout["bytes"] = N * 1024 * 2 * 3
+print(json.dumps(qout))

@@ -813,6 +813,180 @@ qknorm_rope_bwd_hd64_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qk
   }
 }
 
+
+// Streaming variant for 8 heads x 64 (one warp per row: 2 x 2 KB of q|k and d(q|k) staged by bulk async copies into a
+// per-warp ring, as the LayerNorm kernels above; the in-place result goes straight to global memory).  Lane l owns the
+// 16-byte chunks l, l+32, l+64, l+96 of the row: the same 8 columns `part` of heads l/8, l/8+4 of q and of k.  The
+// rotate-half partner chunk (8 lanes away) is read from the staged row instead of shuffled.
+template <int WARPS, int STAGES, bool DBIAS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+qknorm_rope_bwd_stream_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv, const float* __restrict__ q_scale,
+                              const float* __restrict__ k_scale, const bf16* __restrict__ cos_tab,
+                              const bf16* __restrict__ sin_tab, float* __restrict__ dq_scale, float* __restrict__ dk_scale,
+                              float* __restrict__ dbias, long long rows, long long pos_div, int pos_mod, float eps) {
+  constexpr int QK = 1024;                       // q|k columns of a row (8 heads x 64 x 2)
+  constexpr long long LD = 1536;
+  constexpr uint32_t HALF = QK * 2;              // bytes of one staged tensor row
+  pdl_launch_dependents();
+  extern __shared__ uint8_t lns_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lns_raw) + 127) & ~uintptr_t(127));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = base + (size_t)warp * STAGES * 2 * HALF;
+  const uint32_t ring_u32 = sm100::smem_u32(ring);
+  float* redb = reinterpret_cast<float*>(base + (size_t)WARPS * STAGES * 2 * HALF);   // [1024] bias-gradient partials
+  float* red = redb + QK;                                                             // [2][64] scale-gradient partials
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 128) + warp * STAGES;
+  if (lane == 0) {
+    for (int i = 0; i < STAGES; ++i) sm100::mbar_init(&bars[i], 1);
+    sm100::fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < QK + 128; i += blockDim.x) redb[i] = 0.f;
+  const int part = lane & 7;
+  const bool second = part >= 4;
+  float sc[2][8], ps[2][8], pb[DBIAS ? 4 : 1][8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    sc[0][t] = __ldg(q_scale + part * 8 + t);
+    sc[1][t] = __ldg(k_scale + part * 8 + t);
+    ps[0][t] = ps[1][t] = 0.f;
+#pragma unroll
+    for (int i = 0; i < (DBIAS ? 4 : 1); ++i) pb[i][t] = 0.f;
+  }
+  __syncthreads();
+  pdl_wait();
+  const long long warp0 = (long long)blockIdx.x * WARPS + warp;
+  const long long nwarps = (long long)gridDim.x * WARPS;
+  auto issue = [&](long long row, int slot) {                    // lane 0 only
+    sm100::mbar_expect_tx(&bars[slot], 2 * HALF);
+    uint8_t* dst = ring + (size_t)slot * 2 * HALF;
+    sm100::bulk_load_1d(dst, qkv + row * LD, HALF, &bars[slot]);
+    sm100::bulk_load_1d(dst + HALF, dqkv + row * LD, HALF, &bars[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      const long long row = warp0 + i * nwarps;
+      if (row < rows) issue(row, i);
+    }
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const int pos = (int)(((unsigned long long)row / (unsigned long long)pos_div) % (unsigned)pos_mod);
+    const uint4 cv = __ldg(reinterpret_cast<const uint4*>(cos_tab + (long long)pos * 64 + part * 8));
+    const uint4 sv = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + part * 8));
+    const uint4 spv = __ldg(reinterpret_cast<const uint4*>(sin_tab + (long long)pos * 64 + (part ^ 4) * 8));
+    const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w}, sw_[4] = {sv.x, sv.y, sv.z, sv.w};
+    const uint32_t spw[4] = {spv.x, spv.y, spv.z, spv.w};
+    (void)sw_;
+    sm100::mbar_wait(&bars[slot], phase);
+    const uint32_t sx = ring_u32 + (uint32_t)slot * 2u * HALF;
+    uint4 xv[4], gv[4], gpv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      xv[i] = lns_lds(sx + (uint32_t)(lane + 32 * i) * 16u);
+      gv[i] = lns_lds(sx + HALF + (uint32_t)(lane + 32 * i) * 16u);
+      gpv[i] = lns_lds(sx + HALF + (uint32_t)((lane ^ 4) + 32 * i) * 16u);     // rotate-half partner's upstream gradient
+    }
+    __syncwarp();                                                // every lane has read this slot: refill it
+    {
+      const long long nxt = row + (long long)STAGES * nwarps;
+      if (lane == 0 && nxt < rows) issue(nxt, slot);
+    }
+    bf16* orow = dqkv + row * LD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int which = i >> 1;                                  // chunks 0..63 are q, 64..127 k
+      const uint32_t xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w}, gw[4] = {gv[i].x, gv[i].y, gv[i].z, gv[i].w};
+      const uint32_t gpw[4] = {gpv[i].x, gpv[i].y, gpv[i].z, gpv[i].w};
+      float f[8], d[8];
+      float s = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        f[2 * t] = bf_lo(xw[t]); f[2 * t + 1] = bf_hi(xw[t]);
+        // y1 = x1*c1 - x2*s1 ; y2 = x2*c2 + x1*s2  =>  dx1 = dy1*c1 + dy2*s2 ; dx2 = dy2*c2 - dy1*s1
+        const float q0 = bf_lo(gpw[t]) * bf_lo(spw[t]), q1 = bf_hi(gpw[t]) * bf_hi(spw[t]);
+        d[2 * t] = fmaf(bf_lo(gw[t]), bf_lo(cw[t]), second ? -q0 : q0);
+        d[2 * t + 1] = fmaf(bf_hi(gw[t]), bf_hi(cw[t]), second ? -q1 : q1);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { s += f[t]; s2 = fmaf(f[t], f[t], s2); }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float mu = s * (1.f / 64.f);
+      const float r = rsqrtf(fmaxf(s2 * (1.f / 64.f) - mu * mu, 0.f) + eps);
+      float sg = 0.f, sgx = 0.f, xh[8], g[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        xh[t] = (f[t] - mu) * r;
+        g[t] = d[t] * sc[which][t];
+        sg += g[t];
+        sgx = fmaf(g[t], xh[t], sgx);
+        ps[which][t] = fmaf(d[t], xh[t], ps[which][t]);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+      }
+      sg *= (1.f / 64.f);
+      sgx *= (1.f / 64.f);
+      uint32_t o4[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        o4[t] = bf_pack(r * (g[2 * t] - sg - xh[2 * t] * sgx), r * (g[2 * t + 1] - sg - xh[2 * t + 1] * sgx));
+        if constexpr (DBIAS) {                                   // sum of the ROUNDED outputs, as a column-sum pass sees them
+          pb[i][2 * t] += bf_lo(o4[t]);
+          pb[i][2 * t + 1] += bf_hi(o4[t]);
+        }
+      }
+      *reinterpret_cast<uint4*>(orow + (lane + 32 * i) * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+    if (++slot == STAGES) { slot = 0; phase ^= 1; }
+  }
+  if constexpr (DBIAS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) atomicAdd(&redb[(lane + 32 * i) * 8 + t], pb[i][t]);
+  }
+#pragma unroll
+  for (int w = 0; w < 2; ++w)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) atomicAdd(&red[w * 64 + part * 8 + t], ps[w][t]);
+  __syncthreads();
+  if constexpr (DBIAS)
+    for (int i = threadIdx.x; i < QK; i += blockDim.x) atomicAdd(dbias + i, redb[i]);
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+    if (dq_scale) atomicAdd(dq_scale + i, red[i]);
+    if (dk_scale) atomicAdd(dk_scale + i, red[64 + i]);
+  }
+}
+
+
+template <int WARPS, int STAGES, bool DBIAS>
+static int launch_qk_bwd_stream(void* dqkv, const void* qkv, const float* q_scale, const float* k_scale, const void* cos_tab,
+                                const void* sin_tab, float* dq_scale, float* dk_scale, float* dbias_qk, long long rows,
+                                long long pos_div, int pos_mod, float eps, cudaStream_t s) {
+  auto kern = qknorm_rope_bwd_stream_kernel<WARPS, STAGES, DBIAS>;
+  const size_t sm = 128 + (size_t)WARPS * STAGES * 4096 + (1024 + 128) * sizeof(float) + WARPS * STAGES * 8;
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) {
+      set_error("qknorm_rope_bwd: cudaFuncSetAttribute(%d)", (int)sm);
+      return VVAE_ERR_CUDA;
+    }
+    attr_set.store(true, std::memory_order_release);
+  }
+  const int blocks = (int)std::min<long long>(num_sms(), cdiv(rows, WARPS));
+  launch_pdl(kern, dim3(blocks), dim3(WARPS * 32), sm, s, (bf16*)dqkv, (const bf16*)qkv, q_scale, k_scale, (const bf16*)cos_tab,
+             (const bf16*)sin_tab, dq_scale, dk_scale, dbias_qk, rows, pos_div, pos_mod, eps);
+  return VVAE_OK;
+}
+
 // =====================================================================================================
 // GroupNorm + SiLU on [B, S, C] (channels last).  blockDim.x is a multiple of C, so a thread always sees the same
 // channel: its gamma/beta/mean/rstd live in registers and group partials need one smem atomic per thread.
@@ -1353,6 +1527,21 @@ int vvae_qknorm_rope_bwd(void* dqkv, const void* qkv, const float* q_scale, cons
   if (rows <= 0) return VVAE_OK;
   VVAE_REQUIRE(dqkv && qkv && q_scale && k_scale && cos_tab && sin_tab, "qknorm_rope_bwd: null pointer");
   VVAE_REQUIRE(hd % 2 == 0 && hd <= 64 * QK_MAXP && pos_div > 0 && pos_mod > 0, "qknorm_rope_bwd: bad hd=%d", hd);
+  if (qk_fast_ok(dtype, heads, hd, qkv, dqkv, cos_tab, sin_tab) && heads == 8 && !(g_dbg[7] & 0x100)) {
+    // vvae_debug_set(7, 0x100): the register-staged kernel below
+    // without the bias-gradient sums (the product takes them from the weight-gradient GEMM) the kernel fits 128 registers:
+    // 16 warps x 2 stages; with them 8 warps x 4 stages
+    int rc;
+    if (dbias_qk) rc = launch_qk_bwd_stream<8, 4, true>(dqkv, qkv, q_scale, k_scale, cos_tab, sin_tab, dq_scale, dk_scale, dbias_qk,
+                                                        rows, pos_div, pos_mod, eps, as_stream(stream));
+    else if (g_dbg[7] & 0x200)
+      rc = launch_qk_bwd_stream<8, 4, false>(dqkv, qkv, q_scale, k_scale, cos_tab, sin_tab, dq_scale, dk_scale, dbias_qk, rows,
+                                             pos_div, pos_mod, eps, as_stream(stream));
+    else rc = launch_qk_bwd_stream<16, 2, false>(dqkv, qkv, q_scale, k_scale, cos_tab, sin_tab, dq_scale, dk_scale, dbias_qk, rows,
+                                                 pos_div, pos_mod, eps, as_stream(stream));
+    if (rc) return rc;
+    return check_launch("qknorm_rope_bwd");
+  }
   if (qk_fast_ok(dtype, heads, hd, qkv, dqkv, cos_tab, sin_tab) && rows < (1LL << 31) && pos_div < (1LL << 31)) {
     const int rpi = 256 / (16 * heads);
     static int occ_grid = 0;
