@@ -433,6 +433,22 @@ def test_full_size_properties_production_config(V):
     assert rel_l2(gg, flat.grad) < 5e-3
 
 
+@pytest.mark.parametrize("rows,n,ld", [(100000, 3, 3), (70001, 5, 5), (4096, 1, 1), (50003, 12, 12), (50000, 12, 16),
+                                       (40001, 16, 32), (8192, 64, 64), (5000, 96, 192), (9000, 16, 16), (300, 3, 3),
+                                       (20000, 256, 256), (6000, 136, 136)])
+def test_colsum_narrow_and_wide_matrices(V, rows, n, ld):
+    """vvae_colsum (bias gradients): the packed / 4-column-chunk kernels for narrow matrices and the wide kernel,
+    against a float64 column sum of the same bf16 values, accumulated on top of a non-zero output."""
+    from video_vae_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + n)
+    buf = torch.randn(rows, ld, device="cuda", generator=g).bfloat16()
+    x = buf[:, :n]
+    out = torch.full((n,), 0.5, device="cuda")
+    ops.colsum_accum(x, out)
+    ref = x.double().sum(0) + 0.5
+    assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
+
+
 def test_philox_noise_statistics_and_determinism(V):
     m, _ = _small_pair(V, torch.float32, enc=1, dec=1)
     video, mask, _, _ = _inputs()

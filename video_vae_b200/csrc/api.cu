@@ -156,6 +156,86 @@ colsum_bf16_vec_kernel(const bf16* __restrict__ x, long long ld, long long rows,
   }
 }
 
+
+// Narrow bf16 matrices (bias gradients of the U-Net convolutions and of the per-pixel Linears: 3..64 columns over
+// millions of rows).  The wide kernel above would use 2 lanes of 32 for 16 columns.
+// (a) n % 4 == 0: thread (row lane, 4-column chunk); consecutive threads read consecutive chunks, then the next row.
+__global__ void __launch_bounds__(256)
+colsum_bf16_chunk4_kernel(const bf16* __restrict__ x, long long ld, long long rows, int n, float* __restrict__ out,
+                          long long rows_per_block) {
+  __shared__ float red[128];
+  const int cpr = n >> 2, rpi = 256 / cpr;           // chunks per row, rows per block iteration
+  const int c = threadIdx.x % cpr, rl = threadIdx.x / cpr;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (rl < rpi) {
+    const bf16* p = x + 4 * c;
+    long long r = r0 + rl;
+    for (; r + 3LL * rpi < r1; r += 4LL * rpi) {     // 4 independent 8-byte loads in flight
+      uint2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint2*>(p + (r + (long long)u * rpi) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a0 += __uint_as_float(v[u].x << 16); a1 += __uint_as_float(v[u].x & 0xffff0000u);
+        a2 += __uint_as_float(v[u].y << 16); a3 += __uint_as_float(v[u].y & 0xffff0000u);
+      }
+    }
+    for (; r < r1; r += rpi) {
+      const uint2 v = *reinterpret_cast<const uint2*>(p + r * ld);
+      a0 += __uint_as_float(v.x << 16); a1 += __uint_as_float(v.x & 0xffff0000u);
+      a2 += __uint_as_float(v.y << 16); a3 += __uint_as_float(v.y & 0xffff0000u);
+    }
+    atomicAdd(&red[4 * c], a0); atomicAdd(&red[4 * c + 1], a1);
+    atomicAdd(&red[4 * c + 2], a2); atomicAdd(&red[4 * c + 3], a3);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(out + i, red[i]);
+}
+// (b) packed rows (ld == n) of N <= 16 columns: the matrix is a flat array; a thread takes lcm(N, 8) consecutive elements
+// (whole rows, 16-byte loads), so the column of each of its elements is a compile-time constant.
+template <int N>
+__global__ void __launch_bounds__(256)
+colsum_bf16_packed_kernel(const bf16* __restrict__ x, long long rows, float* __restrict__ out) {
+  constexpr int G = (N % 8 == 0) ? 8 : (N % 4 == 0) ? 4 : (N % 2 == 0) ? 2 : 1;   // gcd(N, 8)
+  constexpr int E = N * 8 / G;                       // elements per thread step = lcm(N, 8)
+  constexpr int RP = E / N;                          // rows per thread step
+  __shared__ float red[N];
+  if (threadIdx.x < N) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) acc[j] = 0.f;
+  const long long steps = rows / RP;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < steps; i += (long long)gridDim.x * blockDim.x) {
+    const uint4* p = reinterpret_cast<const uint4*>(x + i * E);
+    uint4 v[E / 8];
+#pragma unroll
+    for (int u = 0; u < E / 8; ++u) v[u] = p[u];
+#pragma unroll
+    for (int u = 0; u < E / 8; ++u) {
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        acc[(u * 8 + t) % N] += (t & 1) ? __uint_as_float(w[t >> 1] & 0xffff0000u) : __uint_as_float(w[t >> 1] << 16);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)           // the rows % RP leftover rows
+    for (long long r = steps * RP; r < rows; ++r)
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] += __bfloat162float(x[r * N + j]);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float sres = warp_sum(acc[j]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[j], sres);
+  }
+  __syncthreads();
+  if (threadIdx.x < N) atomicAdd(out + threadIdx.x, red[threadIdx.x]);
+}
+
 }  // namespace vvae
 
 using namespace vvae;
@@ -212,6 +292,24 @@ int vvae_fill_f32(float* dst, float value, long long n, vvae_stream_t stream) {
 int vvae_colsum(const void* x, long long ld, long long rows, int n, float* out, int dtype, vvae_stream_t stream) {
   if (rows <= 0 || n <= 0) return VVAE_OK;
   VVAE_REQUIRE(x && out, "vvae_colsum: null pointer");
+  if (dtype == VVAE_BF16 && ld == n && n <= 16 && rows >= 4096 && ((uintptr_t)x % 16 == 0)) {
+    const int blocks = (int)std::min<long long>(cdiv(rows, 256 * 8), (long long)num_sms() * 8);
+    cudaStream_t s = as_stream(stream);
+#define CS_PACKED(NN) case NN: colsum_bf16_packed_kernel<NN><<<blocks, 256, 0, s>>>((const bf16*)x, rows, out); break;
+    switch (n) {
+      CS_PACKED(1) CS_PACKED(2) CS_PACKED(3) CS_PACKED(4) CS_PACKED(5) CS_PACKED(6) CS_PACKED(7) CS_PACKED(8)
+      CS_PACKED(9) CS_PACKED(10) CS_PACKED(11) CS_PACKED(12) CS_PACKED(13) CS_PACKED(14) CS_PACKED(15) CS_PACKED(16)
+    }
+#undef CS_PACKED
+    return check_launch("colsum");
+  }
+  if (dtype == VVAE_BF16 && n % 4 == 0 && n <= 128 && ld % 4 == 0 && rows >= 4096 && ((uintptr_t)x % 8 == 0)) {
+    const int rpi = 256 / (n / 4);
+    const long long want = (long long)num_sms() * 8;
+    const long long rpb = std::max<long long>(8LL * rpi, (cdiv(rows, want) + 4 * rpi - 1) / (4 * rpi) * (4 * rpi));
+    colsum_bf16_chunk4_kernel<<<(unsigned)cdiv(rows, rpb), 256, 0, as_stream(stream)>>>((const bf16*)x, ld, rows, n, out, rpb);
+    return check_launch("colsum");
+  }
   if (dtype == VVAE_BF16 && n % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x % 16 == 0)) {
     const int cb = (int)cdiv(n, 256);
     const long long want = cdiv(num_sms() * 3, cb);

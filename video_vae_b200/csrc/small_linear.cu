@@ -39,46 +39,89 @@ __device__ __forceinline__ void load_row(const bf16* p, int n, bool vec, float (
   }
 }
 
+// Packed rows of an odd handful of elements (the 3-channel RGB maps: 6 bytes per row) cannot be read or written with
+// vector accesses per thread: a block's 256 consecutive rows are staged through shared memory with 16-byte accesses.
+__device__ __forceinline__ void stage_in(bf16* sdst, const bf16* g, int n) {       // g 16-byte aligned
+  const int nv = n >> 3;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<uint4*>(sdst)[i] = reinterpret_cast<const uint4*>(g)[i];
+  for (int i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) sdst[i] = g[i];
+}
+__device__ __forceinline__ void stage_out(bf16* g, const bf16* ssrc, int n) {      // g 16-byte aligned
+  const int nv = n >> 3;
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) reinterpret_cast<uint4*>(g)[i] = reinterpret_cast<const uint4*>(ssrc)[i];
+  for (int i = (nv << 3) + threadIdx.x; i < n; i += blockDim.x) g[i] = ssrc[i];
+}
+
+// xvec / yvec / avec: 0 = element-wise, 1 = 8-byte vectors per thread, 2 = packed rows staged through shared memory
 template <int KP, int NP>
 __global__ void __launch_bounds__(256)
 small_linear_fwd_kernel(const SmallLinArgs a, int xvec, int yvec, int avec) {
   __shared__ float sw[KP * NP], sb[NP];
+  __shared__ __align__(16) bf16 s_x[256 * KP], s_y[256 * NP], s_a[256 * NP];
   for (int i = threadIdx.x; i < KP * NP; i += blockDim.x) {
     const int k = i / NP, n = i % NP;
     sw[i] = (k < a.K && n < a.N) ? __bfloat162float(a.w[k * a.wk + n * a.wn]) : 0.f;
   }
   for (int i = threadIdx.x; i < NP; i += blockDim.x) sb[i] = (a.bias && i < a.N) ? a.bias[i] : 0.f;
   __syncthreads();
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < a.M; m += stride) {
+  for (long long m0 = (long long)blockIdx.x * 256; m0 < a.M; m0 += (long long)gridDim.x * 256) {   // block-uniform
+    const long long m = m0 + threadIdx.x;
+    const bool live = m < a.M;
+    const int nrows = (int)(a.M - m0 < 256 ? a.M - m0 : 256);
+    if (xvec == 2) stage_in(s_x, a.x + m0 * a.K, nrows * a.K);
+    if (avec == 2) stage_in(s_a, a.aux + m0 * a.N, nrows * a.N);
+    if (xvec == 2 || avec == 2) __syncthreads();
     float xv[KP], acc[NP];
-    load_row<KP>(a.x + m * a.x_ld, a.K, xvec != 0, xv);
+    if (xvec == 2) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) xv[k] = (k < a.K && live) ? __bfloat162float(s_x[threadIdx.x * a.K + k]) : 0.f;
+    } else if (live) {
+      load_row<KP>(a.x + m * a.x_ld, a.K, xvec != 0, xv);
+    }
 #pragma unroll
     for (int n = 0; n < NP; ++n) acc[n] = sb[n];
+    if (live) {
 #pragma unroll
-    for (int k = 0; k < KP; ++k)
+      for (int k = 0; k < KP; ++k)
 #pragma unroll
-      for (int n = 0; n < NP; ++n) acc[n] = fmaf(xv[k], sw[k * NP + n], acc[n]);
-    if (a.aux) {
-      float av[NP];
-      load_row<NP>(a.aux + m * a.aux_ld, a.N, avec != 0, av);
+        for (int n = 0; n < NP; ++n) acc[n] = fmaf(xv[k], sw[k * NP + n], acc[n]);
+      if (a.aux) {
+        float av[NP];
+        if (avec == 2) {
 #pragma unroll
-      for (int n = 0; n < NP; ++n) acc[n] += av[n];
-    }
-    bf16* yr = a.y + m * a.y_ld;
-    if (yvec) {
-#pragma unroll
-      for (int n = 0; n < NP; n += 4) {
-        if (n < a.N) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[n], acc[n + 1]), p1 = __floats2bfloat162_rn(acc[n + 2], acc[n + 3]);
-          *reinterpret_cast<uint2*>(yr + n) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+          for (int n = 0; n < NP; ++n) av[n] = n < a.N ? __bfloat162float(s_a[threadIdx.x * a.N + n]) : 0.f;
+        } else {
+          load_row<NP>(a.aux + m * a.aux_ld, a.N, avec != 0, av);
         }
-      }
-    } else {
 #pragma unroll
-      for (int n = 0; n < NP; ++n)
-        if (n < a.N) yr[n] = __float2bfloat16_rn(acc[n]);
+        for (int n = 0; n < NP; ++n) acc[n] += av[n];
+      }
     }
+    if (yvec == 2) {
+      if (live) {
+#pragma unroll
+        for (int n = 0; n < NP; ++n)
+          if (n < a.N) s_y[threadIdx.x * a.N + n] = __float2bfloat16_rn(acc[n]);
+      }
+      __syncthreads();
+      stage_out(a.y + m0 * a.N, s_y, nrows * a.N);
+    } else if (live) {
+      bf16* yr = a.y + m * a.y_ld;
+      if (yvec) {
+#pragma unroll
+        for (int n = 0; n < NP; n += 4) {
+          if (n < a.N) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(acc[n], acc[n + 1]), p1 = __floats2bfloat162_rn(acc[n + 2], acc[n + 3]);
+            *reinterpret_cast<uint2*>(yr + n) = make_uint2(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < NP; ++n)
+          if (n < a.N) yr[n] = __float2bfloat16_rn(acc[n]);
+      }
+    }
+    __syncthreads();                                  // the staging tiles are reused by the next slab
   }
 }
 
@@ -88,6 +131,7 @@ small_linear_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, const bf16
                           float* __restrict__ dw, long long dk, long long dn, long long M, int K, int N, int xvec,
                           int dvec) {
   __shared__ float red[KP * NP];
+  __shared__ __align__(16) bf16 s_x[256 * KP], s_d[256 * NP];
   for (int i = threadIdx.x; i < KP * NP; i += blockDim.x) red[i] = 0.f;
   __syncthreads();
   float acc[KP][NP];
@@ -95,15 +139,33 @@ small_linear_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, const bf16
   for (int k = 0; k < KP; ++k)
 #pragma unroll
     for (int n = 0; n < NP; ++n) acc[k][n] = 0.f;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += stride) {
-    float xv[KP], dv[NP];
-    load_row<KP>(x + m * x_ld, K, xvec != 0, xv);
-    load_row<NP>(dy + m * dy_ld, N, dvec != 0, dv);
+  for (long long m0 = (long long)blockIdx.x * 256; m0 < M; m0 += (long long)gridDim.x * 256) {   // block-uniform
+    const long long m = m0 + threadIdx.x;
+    const bool live = m < M;
+    const int nrows = (int)(M - m0 < 256 ? M - m0 : 256);
+    if (xvec == 2) stage_in(s_x, x + m0 * K, nrows * K);
+    if (dvec == 2) stage_in(s_d, dy + m0 * N, nrows * N);
+    if (xvec == 2 || dvec == 2) __syncthreads();
+    if (live) {
+      float xv[KP], dv[NP];
+      if (xvec == 2) {
 #pragma unroll
-    for (int k = 0; k < KP; ++k)
+        for (int k = 0; k < KP; ++k) xv[k] = k < K ? __bfloat162float(s_x[threadIdx.x * K + k]) : 0.f;
+      } else {
+        load_row<KP>(x + m * x_ld, K, xvec != 0, xv);
+      }
+      if (dvec == 2) {
 #pragma unroll
-      for (int n = 0; n < NP; ++n) acc[k][n] = fmaf(xv[k], dv[n], acc[k][n]);
+        for (int n = 0; n < NP; ++n) dv[n] = n < N ? __bfloat162float(s_d[threadIdx.x * N + n]) : 0.f;
+      } else {
+        load_row<NP>(dy + m * dy_ld, N, dvec != 0, dv);
+      }
+#pragma unroll
+      for (int k = 0; k < KP; ++k)
+#pragma unroll
+        for (int n = 0; n < NP; ++n) acc[k][n] = fmaf(xv[k], dv[n], acc[k][n]);
+    }
+    if (xvec == 2 || dvec == 2) __syncthreads();
   }
 #pragma unroll
   for (int k = 0; k < KP; ++k)
@@ -120,14 +182,21 @@ small_linear_wgrad_kernel(const bf16* __restrict__ x, long long x_ld, const bf16
 }
 
 static bool al8(const void* p) { return ((uintptr_t)p % 8) == 0; }
+// access mode of a [M, n] operand with row stride ld: 1 = 8-byte vectors per thread, 2 = packed rows staged through
+// shared memory (16-byte aligned base; a slab of 256 rows is 512*n bytes, so every slab starts aligned), 0 = element-wise
+static int access_mode(const void* p, int n, long long ld) {
+  if (n % 4 == 0 && ld % 4 == 0 && al8(p)) return 1;
+  if (ld == n && ((uintptr_t)p % 16) == 0) return 2;
+  return 0;
+}
 static int pad4(int v) { return v <= 4 ? 4 : (v <= 12 ? 12 : 16); }
 
 bool small_linear_ok(int K, int N) { return K >= 1 && N >= 1 && K <= 16 && N <= 16; }
 
 int small_linear_fwd(const SmallLinArgs& a, cudaStream_t s) {
-  const int xvec = (a.K % 4 == 0 && a.x_ld % 4 == 0 && al8(a.x)) ? 1 : 0;
-  const int yvec = (a.N % 4 == 0 && a.y_ld % 4 == 0 && al8(a.y)) ? 1 : 0;
-  const int avec = (a.aux && a.N % 4 == 0 && a.aux_ld % 4 == 0 && al8(a.aux)) ? 1 : 0;
+  const int xvec = access_mode(a.x, a.K, a.x_ld);
+  const int yvec = access_mode(a.y, a.N, a.y_ld);
+  const int avec = a.aux ? access_mode(a.aux, a.N, a.aux_ld) : 0;
   const int blocks = (int)std::min<long long>(cdiv(a.M, 256), (long long)num_sms() * 8);
   const int kp = pad4(a.K), np = pad4(a.N);
 #define SL_FWD(KP, NP) small_linear_fwd_kernel<KP, NP><<<blocks, 256, 0, s>>>(a, xvec, yvec, avec)
@@ -148,8 +217,8 @@ bool small_linear_wgrad_ok(int K, int N) { return small_linear_ok(K, N) && pad4(
 
 int small_linear_wgrad(const bf16* x, long long x_ld, const bf16* dy, long long dy_ld, float* dw, long long dk, long long dn,
                        long long M, int K, int N, cudaStream_t s) {
-  const int xvec = (K % 4 == 0 && x_ld % 4 == 0 && al8(x)) ? 1 : 0;
-  const int dvec = (N % 4 == 0 && dy_ld % 4 == 0 && al8(dy)) ? 1 : 0;
+  const int xvec = access_mode(x, K, x_ld);
+  const int dvec = access_mode(dy, N, dy_ld);
   const int blocks = (int)std::min<long long>(cdiv(M, 256), (long long)num_sms() * 4);
   const int kp = pad4(K), np = pad4(N);
 #define SL_WG(KP, NP) small_linear_wgrad_kernel<KP, NP><<<blocks, 256, 0, s>>>(x, x_ld, dy, dy_ld, dw, dk, dn, M, K, N, xvec, dvec)
