@@ -66,6 +66,8 @@ def parse():
                     "(the reference's @nnx.remat, train/layers.py:209): one extra forward per layer, ~1.1 GB/layer less")
     ap.add_argument("--debug-set", action="append", default=[], metavar="KEY=VALUE",
                     help="A/B switch: vvae_debug_set(KEY, VALUE) before the run (keys in include/vvae.h); not a bench line")
+    ap.add_argument("--wgrad-lane", action="store_true",
+                    help="A/B switch: weight-gradient kernels on a second stream (measured: no gain; off by default)")
     ap.add_argument("--no-pdl", action="store_true", help="launch every kernel fully serialized (vvae_debug_set(11, 1)) "
                     "instead of with programmatic dependent launch")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python each step (eager) instead "
@@ -263,6 +265,9 @@ def run_ours(args):
     _ffi.require_device()
     if args.no_pdl:
         _ffi.lib.vvae_debug_set(11, 1)
+    if args.wgrad_lane:
+        from video_vae_b200 import functional as _F
+        _F.WGRAD_LANE = True
     for kv in args.debug_set:
         k, v = kv.split("=")
         _ffi.lib.vvae_debug_set(int(k), int(v))

@@ -84,8 +84,65 @@ def grad_buf(p):
 
 
 def _notify(params):
+    if _grad_hooks:
+        join_wgrad_lane()            # the hooks (gradient all-reduce) read these gradients on the current stream
     for h in _grad_hooks:
         h(params)
+
+
+# ------------------------------------------------------------------ weight-gradient lane
+# The weight-gradient kernels of a block (GEMMs with K = all tokens, conv3d wgrad) are consumed by nobody before the
+# optimizer step, while the data-gradient kernels form the critical chain of backward.  They are launched on a second
+# stream: every persistent kernel here ends with a partial wave (N = 768 dgrads: 5.2 waves of tiles on 74 CTA pairs) and
+# a drain, during which the other stream's CTAs take the idle SMs.  Ordering: the lane waits for the current stream at
+# the fork (its inputs are complete); the current stream waits for the lane two forks later (by then long finished, the
+# wait is free) -- until then the lane's input tensors are kept alive here, so neither allocator reuse nor an in-place
+# consumer can touch them -- and at the end of the backward pass (autograd callback), before anyone reads a gradient.
+# Measured (bench.py --wgrad-lane, same box, 2 runs each): 70.5 / 71.0 ms per step with the lane against 70.0 / 70.3 ms
+# without: two persistent kernels time-slicing the SMs buy nothing here (the step is power-capped, the kernels' CTAs
+# cannot co-reside -- each takes ~200 KB of shared memory -- and the interleaving costs L2 locality).  OFF by default.
+WGRAD_LANE = False                   # module switch (bench.py --wgrad-lane)
+_lane = {"stream": None, "pending": [], "queued": False}
+
+
+def join_wgrad_lane():
+    """Current stream waits for everything launched on the weight-gradient lane so far."""
+    if _lane["pending"]:
+        main = torch.cuda.current_stream()
+        for ev, _keep in _lane["pending"]:
+            main.wait_event(ev)
+        _lane["pending"].clear()
+    _lane["queued"] = False
+
+
+def wgrad_async(fn, *keep):
+    """Run ``fn()`` (weight-gradient kernels reading ``keep``) on the lane, after all work already on the current stream."""
+    if not WGRAD_LANE or not torch.cuda.is_available():
+        fn()
+        return
+    if not _lane["queued"]:
+        try:                           # join at the end of this backward pass (inside a graph capture: captured)
+            torch.autograd.Variable._execution_engine.queue_callback(join_wgrad_lane)
+            _lane["queued"] = True
+        except RuntimeError:           # not inside a backward pass: no one to join for us
+            fn()
+            return
+    main = torch.cuda.current_stream()
+    if _lane["stream"] is None or _lane["stream"].device != main.device:
+        _lane["stream"] = torch.cuda.Stream(device=main.device)
+    side = _lane["stream"]
+    pend = _lane["pending"]
+    while len(pend) >= 2:
+        ev, _keep = pend.pop(0)
+        main.wait_event(ev)
+    fork = torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        fn()
+        done = torch.cuda.Event()
+        done.record(side)
+    pend.append((done, keep))
 
 
 def _as_2d(x, D):
@@ -225,7 +282,8 @@ class AttnBlockFn(Function):
         Q = cfg.heads * cfg.hd
         dy2 = _as_2d(dy, D)
         # out projection; bias gradients ride along with the weight-gradient GEMMs (column sums of their dY tiles)
-        ops.gemm(o, dy2, transA=True, out=grad_buf(w_o), accumulate=True, bsum=grad_buf(b_o))
+        gw_o, gb_o = grad_buf(w_o), grad_buf(b_o)
+        wgrad_async(lambda: ops.gemm(o, dy2, transA=True, out=gw_o, accumulate=True, bsum=gb_o), o, dy2)
         d_o = ops.gemm(dy2, shadow(w_o, dtp), transB=True)
         # attention core -> dq | dk | dv written side by side
         dqkv = torch.empty_like(qkv)
@@ -234,7 +292,8 @@ class AttnBlockFn(Function):
         ops.qknorm_rope_bwd_(dqkv, qkv, q_scale.detach(), k_scale.detach(), cos, sin, grad_buf(q_scale),
                              grad_buf(k_scale), cfg.heads, cfg.hd, cfg.pos_div, cfg.pos_mod)
         # qkv projection
-        ops.gemm(h, dqkv, transA=True, out=grad_buf(w_qkv), accumulate=True, bsum=grad_buf(b_qkv))
+        gw_qkv, gb_qkv = grad_buf(w_qkv), grad_buf(b_qkv)
+        wgrad_async(lambda: ops.gemm(h, dqkv, transA=True, out=gw_qkv, accumulate=True, bsum=gb_qkv), h, dqkv)
         dh = ops.gemm(dqkv, shadow(w_qkv, dtp), transB=True)
         dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if cfg.residual else None, grad_buf(ln_g),
                                grad_buf(ln_b), out=dh)
@@ -269,9 +328,10 @@ class MlpBlockFn(Function):
         x2, mean, rstd, h, u, a, ln_g, ln_b, w1, b1, w2, b2 = ctx.saved_tensors
         dtp = ctx.dtype
         dy2 = _as_2d(dy, x2.shape[1])
-        ops.gemm(a, dy2, transA=True, out=grad_buf(w2), accumulate=True, bsum=grad_buf(b2))
+        gw2, gb2, gw1, gb1 = grad_buf(w2), grad_buf(b2), grad_buf(w1), grad_buf(b1)
+        wgrad_async(lambda: ops.gemm(a, dy2, transA=True, out=gw2, accumulate=True, bsum=gb2), a, dy2)
         du = ops.gemm(dy2, shadow(w2, dtp), transB=True, epilogue=EPI_DSILU, aux_in=u)
-        ops.gemm(h, du, transA=True, out=grad_buf(w1), accumulate=True, bsum=grad_buf(b1))
+        wgrad_async(lambda: ops.gemm(h, du, transA=True, out=gw1, accumulate=True, bsum=gb1), h, du)
         dh = ops.gemm(du, shadow(w1, dtp), transB=True)
         dx = ops.layernorm_bwd(dh, x2, mean, rstd, ln_g.detach(), dy2 if ctx.residual else None, grad_buf(ln_g),
                                grad_buf(ln_b), out=dh)

@@ -105,7 +105,8 @@ def _conv_bwd(dy, x, x_ld, Cin, conv, dtype, need_dx=True, dy_ld=None, dx_out=No
     ``dx_alloc_ld``: produce dx at that channel pitch (> Cin, pad channels zero) in a fresh buffer."""
     Cout = conv.kernel.shape[4]
     dy_ld = dy_ld or dy.shape[-1]
-    ops.conv3d_wgrad_accum(x, dy, F_.grad_buf(conv.kernel), conv.ks, Cin, Cout, x_ld=x_ld, dy_ld=dy_ld)
+    gk = F_.grad_buf(conv.kernel)
+    F_.wgrad_async(lambda: ops.conv3d_wgrad_accum(x, dy, gk, conv.ks, Cin, Cout, x_ld=x_ld, dy_ld=dy_ld), x, dy)
     if not bias_done:
         ops.colsum_accum(dy.reshape(-1, dy_ld)[:, :Cout], F_.grad_buf(conv.bias))
     if not need_dx:
