@@ -449,6 +449,38 @@ def test_colsum_narrow_and_wide_matrices(V, rows, n, ld):
     assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
 
 
+def test_weight_gradient_lane_gives_the_same_gradients(V):
+    """functional.WGRAD_LANE (weight-gradient kernels on a second stream, joined by an autograd callback): same loss and
+    gradients as the single-stream default, eager and through two consecutive backward passes."""
+    from video_vae_b200 import functional as F_
+    from video_vae_b200.ddp import FlatParams
+    m = V.VideoVAE(64, 64, 3, 16, 2, 2, 256, 2, 128, 16, 8, 4, V.Rngs(2), dtype=torch.bfloat16)
+    with torch.no_grad():
+        m.decoder.unet.final_conv.kernel.normal_(0.0, 0.05, generator=torch.Generator(device="cuda").manual_seed(7))
+    flat = FlatParams(m)
+    video, mask, noise, _ = _inputs()
+    u, _ = _decisive_u(2, 4)
+    grads = {}
+    try:
+        for run, lane in enumerate((False, False, True, True)):
+            F_.WGRAD_LANE = lane
+            flat.zero_grad()
+            loss, _ = V.loss_fn(m, video.cuda(), mask[:, None, None, :].cuda(), mask.cuda(), V.Rngs(0), V.DEFAULT_HPARAMS,
+                                noise=noise.cuda(), gumbel_u=u.cuda())
+            loss.backward()
+            torch.cuda.synchronize()
+            assert not F_._lane["pending"]                      # joined by the end-of-backward callback
+            grads[run] = (float(loss), flat.grad.clone())
+    finally:
+        F_.WGRAD_LANE = False
+    assert abs(grads[2][0] - grads[0][0]) <= 1e-4 * abs(grads[0][0])
+    # bf16 kernels with fp32 atomics: two runs of the SAME configuration differ by summation order (GroupNorm statistics
+    # feed back into every U-Net gradient); the lane must stay within a small multiple of that noise
+    noise_floor = max(rel_l2(grads[1][1], grads[0][1]), rel_l2(grads[3][1], grads[2][1]), 1e-4)
+    assert rel_l2(grads[2][1], grads[0][1]) < max(4 * noise_floor, 1e-3), noise_floor
+    assert rel_l2(grads[3][1], grads[1][1]) < max(4 * noise_floor, 1e-3), noise_floor
+
+
 def test_philox_noise_statistics_and_determinism(V):
     m, _ = _small_pair(V, torch.float32, enc=1, dec=1)
     video, mask, _, _ = _inputs()
