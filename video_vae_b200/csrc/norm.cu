@@ -1128,46 +1128,74 @@ __device__ __forceinline__ void gn_unpack(const uint4& u, float (&f)[8]) {
   f[4] = bf_lo(u.z); f[5] = bf_hi(u.z); f[6] = bf_lo(u.w); f[7] = bf_hi(u.w);
 }
 
+// V (4 or 8) consecutive channels of one voxel: 8- or 16-byte access
+template <int V> struct GnVec;
+template <> struct GnVec<8> {
+  uint4 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const { gn_unpack(u, f); }
+  static __device__ __forceinline__ void store(bf16* p, const float (&o)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
+  }
+};
+template <> struct GnVec<4> {
+  uint2 u;
+  __device__ __forceinline__ void load(const bf16* p) { u = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void unpack(float (&f)[4]) const {
+    f[0] = bf_lo(u.x); f[1] = bf_hi(u.x); f[2] = bf_lo(u.y); f[3] = bf_hi(u.y);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&o)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]));
+  }
+};
+
+template <int V>
 __global__ void __launch_bounds__(256)
 gn_stats_vec_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long long S, int C, int G, long long rows_per_block) {
   __shared__ float sm[2 * 64];
-  const int b = blockIdx.y, cpr = C >> 3, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
+  const int b = blockIdx.y, cpr = C / V, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
-  const bf16* xb = x + (long long)b * S * C + ch * 8;
-  float s[8], s2[8];
+  const bf16* xb = x + (long long)b * S * C + ch * V;
+  float s[V], s2[V];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) s[t] = s2[t] = 0.f;
+  for (int t = 0; t < V; ++t) s[t] = s2[t] = 0.f;
+  constexpr int UR = V == 4 ? 4 : 2;               // independent loads in flight
   long long r = r0 + threadIdx.x / cpr;
-  for (; r + rpi < r1; r += 2 * rpi) {          // two independent loads in flight
-    const uint4 u0 = *reinterpret_cast<const uint4*>(xb + r * C);
-    const uint4 u1 = *reinterpret_cast<const uint4*>(xb + (r + rpi) * C);
-    float f0[8], f1[8];
-    gn_unpack(u0, f0);
-    gn_unpack(u1, f1);
+  for (; r + (UR - 1) * rpi < r1; r += UR * rpi) {
+    GnVec<V> u[UR];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { s[t] += f0[t] + f1[t]; s2[t] = fmaf(f0[t], f0[t], fmaf(f1[t], f1[t], s2[t])); }
+    for (int k = 0; k < UR; ++k) u[k].load(xb + (r + k * rpi) * C);
+#pragma unroll
+    for (int k = 0; k < UR; ++k) {
+      float f[V];
+      u[k].unpack(f);
+#pragma unroll
+      for (int t = 0; t < V; ++t) { s[t] += f[t]; s2[t] = fmaf(f[t], f[t], s2[t]); }
+    }
   }
   for (; r < r1; r += rpi) {
-    float f0[8];
-    gn_unpack(*reinterpret_cast<const uint4*>(xb + r * C), f0);
+    GnVec<V> u;
+    u.load(xb + r * C);
+    float f[V];
+    u.unpack(f);
 #pragma unroll
-    for (int t = 0; t < 8; ++t) { s[t] += f0[t]; s2[t] = fmaf(f0[t], f0[t], s2[t]); }
+    for (int t = 0; t < V; ++t) { s[t] += f[t]; s2[t] = fmaf(f[t], f[t], s2[t]); }
   }
   // lanes l, l+cpr, l+2cpr, ... of a warp hold the same channels: fold them before touching shared memory
   for (int o = cpr; o < 32; o <<= 1) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < V; ++t) {
       s[t] += __shfl_xor_sync(0xffffffffu, s[t], o);
       s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], o);
     }
   }
   if ((threadIdx.x & 31) < cpr) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int g = (ch * 8 + t) / cg;
+    for (int t = 0; t < V; ++t) {
+      const int g = (ch * V + t) / cg;
       atomicAdd(&sm[2 * g], s[t]);
       atomicAdd(&sm[2 * g + 1], s2[t]);
     }
@@ -1176,47 +1204,51 @@ gn_stats_vec_kernel(const bf16* __restrict__ x, float* __restrict__ stats, long 
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(stats + (long long)b * 2 * G + i, sm[i]);
 }
 
+template <int V>
 __global__ void __launch_bounds__(256)
 gn_apply_vec_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long y_ld, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                     long long S, int C, int G, long long rows_per_block) {
-  const int b = blockIdx.y, cpr = C >> 3, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
-  float sc[8], sh[8];     // y = silu(x * sc + sh)
+  const int b = blockIdx.y, cpr = C / V, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
+  float sc[V], sh[V];     // y = silu(x * sc + sh)
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int c = ch * 8 + t, g = c / cg;
+  for (int t = 0; t < V; ++t) {
+    const int c = ch * V + t, g = c / cg;
     const float r = rstd[b * G + g];
     sc[t] = r * gamma[c];
     sh[t] = fmaf(-mean[b * G + g], sc[t], beta[c]);
   }
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
-  const bf16* xb = x + (long long)b * S * C + ch * 8;
-  bf16* yb = y + (long long)b * S * y_ld + ch * 8;
-  constexpr int UR = 4;                          // voxels in flight per thread
+  const bf16* xb = x + (long long)b * S * C + ch * V;
+  bf16* yb = y + (long long)b * S * y_ld + ch * V;
+  constexpr int UR = V == 4 ? 8 : 4;             // voxels in flight per thread
   for (long long rb = r0 + threadIdx.x / cpr; rb < r1; rb += UR * rpi) {
-    uint4 xv[UR];
+    GnVec<V> xv[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u)
-      if (rb + u * rpi < r1) xv[u] = *reinterpret_cast<const uint4*>(xb + (rb + u * rpi) * C);
+      if (rb + u * rpi < r1) xv[u].load(xb + (rb + u * rpi) * C);
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       const long long r = rb + u * rpi;
       if (r >= r1) break;
-      float f[8], o[8];
-      gn_unpack(xv[u], f);
+      float f[V], o[V];
+      xv[u].unpack(f);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < V; ++t) {
         const float z = bf_round(fmaf(f[t], sc[t], sh[t]));
         o[t] = z * gn_sigmoid(z);
       }
-      *reinterpret_cast<uint4*>(yb + r * y_ld) =
-          make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
+      GnVec<V>::store(yb + r * y_ld, o);
     }
   }
 }
 
-// backward pass 1: per-(b,g) sums of g = dz*gamma and g*xhat, plus dgamma / dbeta
+// backward pass 1: dgamma_c = sum dz*xhat, dbeta_c = sum dz per channel; the per-(b,g) sums the second pass needs follow
+// from them (sum of g = dz*gamma over a group is gamma_c*dbeta_c summed over its channels, sum of g*xhat likewise from
+// dgamma_c), so only two accumulators per channel are carried.  V channels per thread: V = 4 for narrow maps (16 / 32
+// channels: the register-heavier V = 8 ran at 24 % of the warp slots and 3.2 TB/s, profiles/r02w_norm_ncu.json).
+template <int V>
 __global__ void __launch_bounds__(256)
 gn_bwd_stats_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ x,
                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
@@ -1224,45 +1256,42 @@ gn_bwd_stats_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
                         float* __restrict__ dbeta, long long S, int C, int G, long long rows_per_block) {
   __shared__ float sm[2 * 64];
   __shared__ float smc[2 * 256];
-  const int b = blockIdx.y, cpr = C >> 3, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
+  const int b = blockIdx.y, cpr = C / V, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
   for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) smc[i] = 0.f;
   __syncthreads();
-  float mu[8], rs[8], ga[8], be[8], s1[8], s2[8], dg[8], db[8];
+  float rs[V], nmr[V], ga[V], be[V], dg[V], db[V];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int c = ch * 8 + t, g = c / cg;
-    mu[t] = mean[b * G + g]; rs[t] = rstd[b * G + g]; ga[t] = gamma[c]; be[t] = beta[c];
-    s1[t] = s2[t] = dg[t] = db[t] = 0.f;
+  for (int t = 0; t < V; ++t) {
+    const int c = ch * V + t, g = c / cg;
+    rs[t] = rstd[b * G + g]; nmr[t] = -mean[b * G + g] * rs[t]; ga[t] = gamma[c]; be[t] = beta[c];
+    dg[t] = db[t] = 0.f;
   }
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
-  const bf16* xb = x + (long long)b * S * C + ch * 8;
-  const bf16* dyb = dy + (long long)b * S * dy_ld + ch * 8;
-  constexpr int UR = 2;
+  const bf16* xb = x + (long long)b * S * C + ch * V;
+  const bf16* dyb = dy + (long long)b * S * dy_ld + ch * V;
+  constexpr int UR = V == 4 ? 4 : 2;
   for (long long rb = r0 + threadIdx.x / cpr; rb < r1; rb += UR * rpi) {
-    uint4 xv[UR], dv[UR];
+    GnVec<V> xv[UR], dv[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u)
       if (rb + u * rpi < r1) {
-        xv[u] = *reinterpret_cast<const uint4*>(xb + (rb + u * rpi) * C);
-        dv[u] = *reinterpret_cast<const uint4*>(dyb + (rb + u * rpi) * dy_ld);
+        xv[u].load(xb + (rb + u * rpi) * C);
+        dv[u].load(dyb + (rb + u * rpi) * dy_ld);
       }
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       if (rb + u * rpi >= r1) break;
-      float f[8], d[8];
-      gn_unpack(xv[u], f);
-      gn_unpack(dv[u], d);
+      float f[V], d[V];
+      xv[u].unpack(f);
+      dv[u].unpack(d);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float xh = (f[t] - mu[t]) * rs[t];
+      for (int t = 0; t < V; ++t) {
+        const float xh = fmaf(f[t], rs[t], nmr[t]);
         const float z = bf_round(fmaf(xh, ga[t], be[t]));
         const float sg = gn_sigmoid(z);
         const float dz = d[t] * sg * fmaf(z, 1.f - sg, 1.f);
-        const float gg = dz * ga[t];
-        s1[t] += gg;
-        s2[t] = fmaf(gg, xh, s2[t]);
         dg[t] = fmaf(dz, xh, dg[t]);
         db[t] += dz;
       }
@@ -1270,19 +1299,17 @@ gn_bwd_stats_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
   }
   for (int o = cpr; o < 32; o <<= 1) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      s1[t] += __shfl_xor_sync(0xffffffffu, s1[t], o);
-      s2[t] += __shfl_xor_sync(0xffffffffu, s2[t], o);
+    for (int t = 0; t < V; ++t) {
       dg[t] += __shfl_xor_sync(0xffffffffu, dg[t], o);
       db[t] += __shfl_xor_sync(0xffffffffu, db[t], o);
     }
   }
   if ((threadIdx.x & 31) < cpr) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int c = ch * 8 + t, g = c / cg;
-      atomicAdd(&sm[2 * g], s1[t]);
-      atomicAdd(&sm[2 * g + 1], s2[t]);
+    for (int t = 0; t < V; ++t) {
+      const int c = ch * V + t, g = c / cg;
+      atomicAdd(&sm[2 * g], ga[t] * db[t]);
+      atomicAdd(&sm[2 * g + 1], ga[t] * dg[t]);
       atomicAdd(&smc[c], dg[t]);
       atomicAdd(&smc[C + c], db[t]);
     }
@@ -1295,20 +1322,23 @@ gn_bwd_stats_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(256)
 gn_bwd_apply_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16* __restrict__ x,
                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean,
                         const float* __restrict__ rstd, const float* __restrict__ stats, bf16* __restrict__ dx,
                         float* __restrict__ dxsum, long long S, int C, int G, float inv_n, long long rows_per_block) {
   __shared__ float smc[256];
-  const int b = blockIdx.y, cpr = C >> 3, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
-  float mu[8], rs[8], ga[8], be[8], m1[8], m2[8], cs[8];
+  const int b = blockIdx.y, cpr = C / V, ch = threadIdx.x % cpr, rpi = blockDim.x / cpr, cg = C / G;
+  // dx = rs*(dz*ga - m1 - xh*m2) = dz*k1 + xh*c2 + c1
+  float rs[V], nmr[V], ga[V], be[V], k1[V], c1[V], c2[V], cs[V];
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int c = ch * 8 + t, g = c / cg;
-    mu[t] = mean[b * G + g]; rs[t] = rstd[b * G + g]; ga[t] = gamma[c]; be[t] = beta[c];
-    m1[t] = stats[((long long)b * G + g) * 2] * inv_n;
-    m2[t] = stats[((long long)b * G + g) * 2 + 1] * inv_n;
+  for (int t = 0; t < V; ++t) {
+    const int c = ch * V + t, g = c / cg;
+    rs[t] = rstd[b * G + g]; nmr[t] = -mean[b * G + g] * rs[t]; ga[t] = gamma[c]; be[t] = beta[c];
+    k1[t] = rs[t] * ga[t];
+    c1[t] = -rs[t] * (stats[((long long)b * G + g) * 2] * inv_n);
+    c2[t] = -rs[t] * (stats[((long long)b * G + g) * 2 + 1] * inv_n);
     cs[t] = 0.f;
   }
   if (dxsum) {
@@ -1317,47 +1347,46 @@ gn_bwd_apply_vec_kernel(const bf16* __restrict__ dy, long long dy_ld, const bf16
   }
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = r0 + rows_per_block < S ? r0 + rows_per_block : S;
-  const bf16* xb = x + (long long)b * S * C + ch * 8;
-  const bf16* dyb = dy + (long long)b * S * dy_ld + ch * 8;
-  bf16* dxb = dx + (long long)b * S * C + ch * 8;
-  constexpr int UR = 2;
+  const bf16* xb = x + (long long)b * S * C + ch * V;
+  const bf16* dyb = dy + (long long)b * S * dy_ld + ch * V;
+  bf16* dxb = dx + (long long)b * S * C + ch * V;
+  constexpr int UR = V == 4 ? 4 : 2;
   for (long long rb = r0 + threadIdx.x / cpr; rb < r1; rb += UR * rpi) {
-    uint4 xv[UR], dv[UR];
+    GnVec<V> xv[UR], dv[UR];
 #pragma unroll
     for (int u = 0; u < UR; ++u)
       if (rb + u * rpi < r1) {
-        xv[u] = *reinterpret_cast<const uint4*>(xb + (rb + u * rpi) * C);
-        dv[u] = *reinterpret_cast<const uint4*>(dyb + (rb + u * rpi) * dy_ld);
+        xv[u].load(xb + (rb + u * rpi) * C);
+        dv[u].load(dyb + (rb + u * rpi) * dy_ld);
       }
 #pragma unroll
     for (int u = 0; u < UR; ++u) {
       const long long r = rb + u * rpi;
       if (r >= r1) break;
-      float f[8], d[8], o[8];
-      gn_unpack(xv[u], f);
-      gn_unpack(dv[u], d);
+      float f[V], d[V], o[V];
+      xv[u].unpack(f);
+      dv[u].unpack(d);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float xh = (f[t] - mu[t]) * rs[t];
+      for (int t = 0; t < V; ++t) {
+        const float xh = fmaf(f[t], rs[t], nmr[t]);
         const float z = bf_round(fmaf(xh, ga[t], be[t]));
         const float sg = gn_sigmoid(z);
-        const float gg = d[t] * sg * fmaf(z, 1.f - sg, 1.f) * ga[t];
-        o[t] = rs[t] * (gg - m1[t] - xh * m2[t]);
+        const float dz = d[t] * sg * fmaf(z, 1.f - sg, 1.f);
+        o[t] = fmaf(dz, k1[t], fmaf(xh, c2[t], c1[t]));
         cs[t] += bf_round(o[t]);
       }
-      *reinterpret_cast<uint4*>(dxb + r * C) =
-          make_uint4(bf_pack(o[0], o[1]), bf_pack(o[2], o[3]), bf_pack(o[4], o[5]), bf_pack(o[6], o[7]));
+      GnVec<V>::store(dxb + r * C, o);
     }
   }
   // per-channel sums of the produced gradient: the bias gradient of the convolution in front of this norm
   if (dxsum) {
     for (int o = cpr; o < 32; o <<= 1) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], o);
+      for (int t = 0; t < V; ++t) cs[t] += __shfl_xor_sync(0xffffffffu, cs[t], o);
     }
     if ((threadIdx.x & 31) < cpr) {
 #pragma unroll
-      for (int t = 0; t < 8; ++t) atomicAdd(&smc[ch * 8 + t], cs[t]);
+      for (int t = 0; t < V; ++t) atomicAdd(&smc[ch * V + t], cs[t]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dxsum + i, smc[i]);
@@ -1579,10 +1608,13 @@ int vvae_groupnorm_silu_fwd(const void* x, void* y, long long y_ld, const float*
     const int rpi = 256 / (C / 8);
     const long long vrpb = std::max<long long>(2 * rpi, cdiv(S, std::max<long long>(1, ((long long)num_sms() * 8) / B)));
     dim3 vgrid((unsigned)cdiv(S, vrpb), (unsigned)B);
-    gn_stats_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)x, stats, S, C, G, vrpb);
+    const bool v4 = C <= 128 && !(g_dbg[7] & 0x400);   // 4 channels per thread (vvae_debug_set(7, 0x400): 8)
+    if (v4) gn_stats_vec_kernel<4><<<vgrid, 256, 0, s>>>((const bf16*)x, stats, S, C, G, vrpb);
+    else gn_stats_vec_kernel<8><<<vgrid, 256, 0, s>>>((const bf16*)x, stats, S, C, G, vrpb);
     groupnorm_finalize_kernel<<<(int)cdiv(B * G, 128), 128, 0, s>>>(stats, mean, rstd, B * G,
                                                                    1.f / (float)((double)S * (C / G)), eps);
-    gn_apply_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)x, (bf16*)y, y_ld, gamma, beta, mean, rstd, S, C, G, vrpb);
+    if (v4) gn_apply_vec_kernel<4><<<vgrid, 256, 0, s>>>((const bf16*)x, (bf16*)y, y_ld, gamma, beta, mean, rstd, S, C, G, vrpb);
+    else gn_apply_vec_kernel<8><<<vgrid, 256, 0, s>>>((const bf16*)x, (bf16*)y, y_ld, gamma, beta, mean, rstd, S, C, G, vrpb);
     return check_launch("groupnorm_silu_fwd");
   }
   VVAE_DISPATCH_DTYPE(dtype, T, (groupnorm_stats_kernel<T><<<grid, threads, 0, s>>>((const T*)x, stats, S, C, G, rpb)));
@@ -1609,11 +1641,20 @@ int vvae_groupnorm_silu_bwd(const void* dy, long long dy_ld, const void* x, cons
     const int rpi = 256 / (C / 8);
     const long long vrpb = std::max<long long>(2 * rpi, cdiv(S, std::max<long long>(1, ((long long)num_sms() * 8) / B)));
     dim3 vgrid((unsigned)cdiv(S, vrpb), (unsigned)B);
-    gn_bwd_stats_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
-                                                  dgamma, dbeta, S, C, G, vrpb);
-    gn_bwd_apply_vec_kernel<<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
-                                                  (bf16*)dx, dx_colsum_accum, S, C, G,
-                                                  1.f / (float)((double)S * (C / G)), vrpb);
+    // narrow maps: 4 channels per thread (vvae_debug_set(7, 0x400) keeps 8)
+    if (C <= 128 && !(g_dbg[7] & 0x400)) {
+      gn_bwd_stats_vec_kernel<4><<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
+                                                       dgamma, dbeta, S, C, G, vrpb);
+      gn_bwd_apply_vec_kernel<4><<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd,
+                                                       stats, (bf16*)dx, dx_colsum_accum, S, C, G,
+                                                       1.f / (float)((double)S * (C / G)), vrpb);
+    } else {
+      gn_bwd_stats_vec_kernel<8><<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd, stats,
+                                                       dgamma, dbeta, S, C, G, vrpb);
+      gn_bwd_apply_vec_kernel<8><<<vgrid, 256, 0, s>>>((const bf16*)dy, dy_ld, (const bf16*)x, gamma, beta, mean, rstd,
+                                                       stats, (bf16*)dx, dx_colsum_accum, S, C, G,
+                                                       1.f / (float)((double)S * (C / G)), vrpb);
+    }
     return check_launch("groupnorm_silu_bwd");
   }
   VVAE_DISPATCH_DTYPE(dtype, T, (groupnorm_silu_bwd_stats_kernel<T><<<grid, threads, 0, s>>>(
