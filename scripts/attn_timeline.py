@@ -91,3 +91,19 @@ for cta in (700,):
 _ffi.lib.vvae_debug_set(10, 0)
 _ffi.lib.vvae_debug_set(0, 0)
 _ffi.lib.vvae_debug_set(16, 0)
+
+# ---- forward kernel (slots: 0 start, 1 after griddepcontrol.wait, 2 Q|K landed (issuer), 3 P ready (issuer), 4 PV issued,
+# 5 softmax warp: S ready, 6 row max done, 7 P written, 8 O ready, 9 O stored)
+_ffi.lib.vvae_debug_set(10, 16)
+for cta in (0, 300, 1000, 2000):
+    _ffi.lib.vvae_debug_set(0, cta)
+    flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); ops.attn_fwd(geom, H, HD, qk[:, :Q], qk[:, Q:], qkv[:, 2 * Q:], None, sc); e1.record()
+    torch.cuda.synchronize()
+    _ffi.lib.vvae_debug_get(1, buf)
+    v = list(buf)
+    print(json.dumps({"fwd_cta": cta, "sm": int(v[31]), "kernel_us": round(e0.elapsed_time(e1) * 1e3, 1),
+                      "cycles": {i: int(v[i] - v[0]) for i in range(1, 10) if v[i]}}), flush=True)
+_ffi.lib.vvae_debug_set(10, 0)
+_ffi.lib.vvae_debug_set(0, 0)

@@ -40,7 +40,10 @@ struct AttnTcParams {
   float* lse;
   const unsigned char* mask; long long mask_seq_div, ms_seq, ms_k;
   float scale;
+  int dbg, dbg_cta;          // vvae_debug_set(10, 16): CTA vvae_debug_set(0, n) records a clock64 timeline (vvae_debug_get(1, .))
 };
+// clock64 stamps of one CTA of the forward / backward tcgen05 kernels (see the stamp sites); [31] = SM id
+__device__ unsigned long long g_attn_dbg[32];
 
 __host__ __device__ inline bool atc_len_long(int L) { return L > 256 && L % 128 == 0 && L <= 8192; }
 __host__ __device__ inline bool atc_len_ok(int L) {
@@ -151,6 +154,10 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tile = blockIdx.x;
   const int h = blockIdx.y;
+  // forward timeline slots: 0 start, 1 after griddepcontrol.wait, 2 Q|K landed (issuer), 3 P ready (issuer), 4 PV issued,
+  // 5 softmax warp 2: S ready, 6 row max done, 7 P written, 8 O ready, 9 O stored
+  const bool fdbg = q.dbg && (int)(blockIdx.y * gridDim.x + blockIdx.x) == q.dbg_cta && lane == 0;
+  if (fdbg && warp == 0) g_attn_dbg[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     sm100::tma_prefetch_desc(&tma_q);
@@ -169,6 +176,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   sm100::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // PDL (common.cuh): barrier init / TMEM allocation above overlap the previous kernel's tail
+  if (fdbg && warp == 0) g_attn_dbg[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -194,6 +202,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, NK, false, false);
       sm100::mbar_wait(qk_full, 0);
       sm100::tc_fence_after();
+      if (fdbg) g_attn_dbg[2] = clock64();
       const uint32_t qa = sm100::smem_u32(sQ), ka = sm100::smem_u32(sK);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -205,17 +214,20 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       sm100::mbar_wait(v_full, 0);
       sm100::mbar_wait(p_full, 0);
       sm100::tc_fence_after();
+      if (fdbg) g_attn_dbg[3] = clock64();
       const uint32_t pa = sm100::smem_u32(sP), va = sm100::smem_u32(sV);
 #pragma unroll
       for (int k = 0; k < NK / 16; ++k)
         sm100::umma_f16(tmem_base, sm100::make_smem_desc_sw128(pa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                         sm100::make_smem_desc_sw128(va + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
       sm100::umma_commit(o_full);
+      if (fdbg) g_attn_dbg[4] = clock64();
     }
   } else {
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;                 // query row == TMEM lane
     const int tid = threadIdx.x - 64;                  // 0..127
+    const bool sdbg = fdbg && warp == 2;
     // key penalties for the tile's NK key rows
     for (int c = tid; c < NK; c += 128) {
       float pen = 0.f;
@@ -238,6 +250,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 
     sm100::mbar_wait(s_full, 0);
     sm100::tc_fence_after();
+    if (sdbg) g_attn_dbg[5] = clock64();
     // pass 1: row maximum of the (masked) logits
     float mx = -INFINITY;
     for (int c0 = cbeg; c0 < cend; c0 += 32) {
@@ -253,6 +266,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         if (inseq) mx = fmaxf(mx, s);
       }
     }
+    if (sdbg) g_attn_dbg[6] = clock64();
     // pass 2: p = exp(s - max), row sum, bf16 P into the swizzled K-major operand tile
     const float mx2 = mx * 1.4426950408889634f;
     float sum = 0.f;
@@ -295,10 +309,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     sm100::tc_fence_before();
     __syncwarp();
     if (lane == 0) sm100::mbar_arrive(p_full);
+    if (sdbg) g_attn_dbg[7] = clock64();
 
     // epilogue: O / rowsum -> bf16, log-sum-exp
     sm100::mbar_wait(o_full, 0);
     sm100::tc_fence_after();
+    if (sdbg) g_attn_dbg[8] = clock64();
     const float inv = 1.f / sum;
     bf16* orow = q.o + row.tok * q.o_rs + (long long)h * 64;
 #pragma unroll
@@ -317,9 +333,16 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       }
     }
     if (row.ok && q.lse) q.lse[(row.seq * p.heads + h) * p.L + row.l] = mx + __logf(sum);
+    if (sdbg) g_attn_dbg[9] = clock64();
   }
   sm100::tc_fence_before();
   __syncthreads();
+  if (fdbg && warp == 0) {
+    g_attn_dbg[10] = clock64();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_attn_dbg[31] = smid;
+  }
   if (warp == 1) {
     sm100::tc_fence_after();
     sm100::tmem_dealloc<NK>(tmem_base);
@@ -348,6 +371,8 @@ static int atc_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   q.o = (bf16*)a.o; q.o_rs = a.o_rs; q.lse = a.lse;
   q.mask = a.mask; q.mask_seq_div = a.mask_seq_div > 0 ? a.mask_seq_div : 1; q.ms_seq = a.ms_seq; q.ms_k = a.ms_k;
   q.scale = a.scale;
+  q.dbg = (g_dbg[10] & 16) ? 1 : 0;
+  q.dbg_cta = (int)g_dbg[0];
   auto kern = attn_fwd_sm100_kernel<NK, PACKED, MASKED>;
   static std::atomic<bool> attr_set{false};
   if (!attr_set.load(std::memory_order_acquire)) {   // idempotent: a racing second call sets the same value
@@ -388,8 +413,6 @@ struct AttnTcBwdParams {
   int dbg_cta;
 };
 
-// clock64 stamps of one CTA of attn_bwd_sm100_kernel (see the ATB_STAMP sites); [31] = SM id
-__device__ unsigned long long g_attn_dbg[32];
 #define ATB_STAMP(slot) do { if (dbg_on) g_attn_dbg[slot] = clock64(); } while (0)
 
 // row r of 128-row block `blk` of the CTA's tile set
