@@ -58,6 +58,10 @@ def parse():
     ap.add_argument("--dec-depth", type=int, default=PROD["decoder_depth"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--split-allreduce", action="store_true",
+                    help="N > 1: reduce the decoder's gradients on a side stream while the encoder's backward still runs "
+                         "inside the graph (ddp.SplitAllReduce); combine with NCCL_MAX_CTAS=<n> in the environment to keep "
+                         "the collective off most SMs")
     ap.add_argument("--graph-allreduce", action="store_true", help="N > 1, EXPERIMENTAL: capture the bucketed all-reduce "
                     "inside the graph instead of one all-reduce after it (hung at N=2 with NCCL 2.28.9 in round 1)")
     ap.add_argument("--grad-comm", default="fp32", choices=["fp32", "bf16"], help="N > 1: dtype of the gradient all-reduce "
@@ -307,7 +311,11 @@ def run_ours(args):
                       file=sys.stderr)
                 torch.cuda.synchronize()
         if graphed is None:
-            graphed = GraphedTrainStep(model, flat, video, mask, hp)
+            graphed = GraphedTrainStep(model, flat, video, mask, hp, mark_decoder_done=bool(world > 1 and args.split_allreduce))
+    split_ar = None
+    if world > 1 and args.split_allreduce and graphed is not None and not ar_in_graph:
+        from video_vae_b200.ddp import SplitAllReduce
+        split_ar = SplitAllReduce(flat, model)
 
     def eager_step(v, m):
         flat.zero_grad()
@@ -337,7 +345,9 @@ def run_ours(args):
             return encode_step(v, m)
         if graphed is not None:
             loss = graphed(v, m, rngs)
-            if world > 1 and not ar_in_graph:
+            if world > 1 and split_ar is not None:
+                split_ar(graphed.decoder_done)
+            elif world > 1 and not ar_in_graph:
                 flat.all_reduce_grads(torch.bfloat16 if args.grad_comm == "bf16" else torch.float32)
         else:
             loss = eager_step(v, m)
@@ -493,7 +503,7 @@ def run_ours(args):
                       ") + eager " + ("all-reduce + " if (world > 1 and not ar_in_graph) else "") + "optimizer")
         if graphed is not None else "eager",
         "peak_mem_GB": torch.cuda.max_memory_allocated() / 2**30,
-        "grad_comm": (args.grad_comm if world > 1 else None), "recompute": bool(args.recompute),
+        "grad_comm": (("split-fp32" if args.split_allreduce else args.grad_comm) if world > 1 else None), "recompute": bool(args.recompute),
         "clocks": clock_info, "roofline": roofline, "kernel_classes": table[:6],
     }
     if world == 1 and not args.no_cpu_baseline:
