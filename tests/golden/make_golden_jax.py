@@ -4,8 +4,11 @@ environment (jax 0.9, flax 0.12, einops; claude_distributed/requirements.txt) an
 
     python tests/golden/make_golden_jax.py --reference /path/to/video-VAE [--cfg small|prod128] [--dtype float32]
 
-It cannot run in the build container of this repository (no jax, no network), which is why DESIGN.md section 3 says
-"parity unpinned".  The file it writes, tests/golden/jax_videovae_<cfg>_<dtype>.npz, is consumed by
+Real JAX does not exist in the build container of this repository (no network).  There the same script runs with
+`--shim`: the reference's files execute unmodified on oracle/jaxshim (jax / flax.nnx / jaxtyping / beartype look-alikes on
+CPU torch, see oracle/jaxshim/README.md) and the file is named refshim_videovae_<cfg>_<dtype>.npz; that pins every line
+the reference itself wrote, while the third-party primitives stay restated.  The file it writes,
+tests/golden/{jax,refshim}_videovae_<cfg>_<dtype>.npz, is consumed by
 tests/test_jax_golden.py: the CPU test loads the reference's weights into the oracle and compares the oracle with the
 reference's outputs (this is what PINS the oracle); the GPU test does the same for the CUDA path.  Nothing else in the
 repository reads the reference at run time.
@@ -20,6 +23,8 @@ can be fed the identical draws (`noise=`, `gumbel_u=`).
 
 Stored keys: cfg (12 ints), dtype, hparams (json), video, mask, gumbel_u, noise, param/<dotted.name>, out/{loss, MSE,
 selection_loss, kl_loss, kept_frame_density, reconstruction, compressed, selection, logvar, mean}, grad/<dotted.name>.
+With --compact (implied by --shim): recipe, video_shape, pshape/<name> instead of video / param/ (the consumer rebuilds
+them with tests/golden/weight_recipe.py) and gnorm/ gsum/ gmax/ gprobe/<name> instead of grad/.
 Names are Flax attribute paths with list indices as integers -- exactly the names video_vae_b200 and the oracle use.
 """
 import argparse
@@ -116,7 +121,19 @@ def main():
     ap.add_argument("--cfg", default="small", choices=sorted(CFGS))
     ap.add_argument("--dtype", default="float32", choices=["float32", "bfloat16"])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--shim", action="store_true",
+                    help="no JAX here: run the reference's files on oracle/jaxshim (jax / flax.nnx look-alikes on CPU torch) "
+                         "and write refshim_videovae_<cfg>_<dtype>.npz")
+    ap.add_argument("--compact", action="store_true",
+                    help="weights from tests/golden/weight_recipe.py (by name), gradients as norm + sum + probe: a "
+                         "commit-sized file at any width (implied by --shim)")
     args = ap.parse_args()
+    args.compact = args.compact or args.shim
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import weight_recipe
+    if args.shim:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
+                                        "oracle", "jaxshim"))
     sys.path.insert(0, os.path.join(args.reference, "train"))
     import jax
     import jax.numpy as jnp
@@ -133,10 +150,32 @@ def main():
     k = model.decoder.unet.final_conv.kernel
     k.value = 0.05 * jax.random.normal(jax.random.key(5), k.value.shape, k.value.dtype)
 
+    if args.compact:
+        state = nnx.state(model, nnx.Param)
+        names = flatten_state(state)
+        pure = state.to_pure_dict()
+
+        def fill(d, path):
+            for kk, vv in d.items():
+                if isinstance(vv, dict):
+                    fill(vv, path + (str(kk),))
+                else:
+                    name = ".".join(path + (str(kk),))
+                    assert name in names, name
+                    d[kk] = jnp.asarray(weight_recipe.param(name, vv.shape))
+        fill(pure, ())
+        if hasattr(nnx, "replace_by_pure_dict"):           # real flax (untested here): State <- pure dict, then update
+            nnx.replace_by_pure_dict(state, pure)
+            nnx.update(model, state)
+        else:
+            nnx.update(model, pure)
+
     hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
     key = jax.random.key(11)
     kv, = jax.random.split(key, 1)
     video = jax.random.uniform(kv, (b, t, cfg[0], cfg[1], cfg[2]), jnp.float32)
+    if args.compact:
+        video = jnp.asarray(weight_recipe.clip((b, t, cfg[0], cfg[1], cfg[2])))
     original_mask = jnp.arange(t)[None, :] < jnp.asarray(spec["keep"])[:, None]            # prefix masks (dataloader.py:232-234)
     mask = rearrange(original_mask, "b time -> b 1 1 time")                                # train_step, :126-130
     mask = repeat(mask, "b 1 1 time -> b hw 1 1 time", hw=hw)
@@ -170,15 +209,38 @@ def main():
     out = {"cfg": np.asarray(cfg, np.int64), "dtype": np.asarray(args.dtype), "hparams": np.asarray(json.dumps(HPARAMS)),
            "video": np.asarray(video, np.float32), "mask": np.asarray(original_mask), "gumbel_u": gumbel_u.astype(np.float32),
            "noise": noise.astype(np.float32)}
-    for name, v in flatten_state(nnx.state(model, nnx.Param)).items():
-        out["param/" + name] = v.astype(np.float32)
-    for name, v in flatten_state(grads).items():
-        out["grad/" + name] = v.astype(np.float32)
+    if args.compact:
+        out["recipe"] = np.asarray(weight_recipe.RECIPE_ID)
+        del out["video"]                                         # weight_recipe.clip(shape)
+        out["video_shape"] = np.asarray(video.shape, np.int64)
+        for name, v in flatten_state(nnx.state(model, nnx.Param)).items():
+            assert np.array_equal(v.astype(np.float32), weight_recipe.param(name, v.shape)), name
+            out["pshape/" + name] = np.asarray(v.shape, np.int64)
+        for name, v in flatten_state(grads).items():
+            g = v.astype(np.float64)
+            out["gnorm/" + name] = np.asarray(np.sqrt((g * g).sum()), np.float64)
+            out["gsum/" + name] = np.asarray(g.sum(), np.float64)
+            out["gmax/" + name] = np.asarray(np.abs(g).max(), np.float64)
+            out["gprobe/" + name] = weight_recipe.grad_probe(v)
+    else:
+        for name, v in flatten_state(nnx.state(model, nnx.Param)).items():
+            out["param/" + name] = v.astype(np.float32)
+        for name, v in flatten_state(grads).items():
+            out["grad/" + name] = v.astype(np.float32)
     f32 = lambda x: np.asarray(x, np.float32)      # noqa: E731
     out.update({"out/loss": f32(loss), "out/MSE": f32(mse), "out/selection_loss": f32(sel_loss), "out/kl_loss": f32(kl),
                 "out/kept_frame_density": f32(density), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
                 "out/selection": f32(selection), "out/logvar": f32(logvar), "out/mean": f32(mean)})
-    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"jax_videovae_{args.cfg}_{args.dtype}.npz")
+    if args.compact:
+        stride = 1 if out["out/reconstruction"].size <= 200_000 else 2          # keep the file commit-sized
+        out["recon_stride"] = np.asarray(stride, np.int64)
+        out["out/reconstruction"] = np.ascontiguousarray(out["out/reconstruction"][:, :, ::stride, ::stride, :])
+    shim = bool(getattr(jax, "IS_SHIM", False))
+    assert shim == args.shim, "a jax look-alike is on sys.path without --shim (or --shim found the real jax first)"
+    out["generator"] = np.asarray(("reference files on oracle/jaxshim (CPU torch), jax " if shim else "reference files on jax ")
+                                  + jax.__version__)
+    prefix = "refshim" if shim else "jax"
+    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{prefix}_videovae_{args.cfg}_{args.dtype}.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes; loss =", float(loss), "; jax", jax.__version__)
 

@@ -1,12 +1,18 @@
-"""Consumes fixtures written by tests/golden/make_golden_jax.py on a box that can run the REAL reference (JAX/Flax).
+"""Consumes fixtures written by tests/golden/make_golden_jax.py: outputs of the REFERENCE'S OWN CODE.
 
-When tests/golden/jax_videovae_*.npz exists:
+Two kinds of file, same schema:
+  * tests/golden/refshim_videovae_*.npz (committed): train/model.py, layers.py, unet.py and the loss_fn of
+    train/legacy/training_loop_adversarial.py executed unmodified on oracle/jaxshim (jax / flax.nnx look-alikes on CPU
+    torch; see oracle/jaxshim/README.md) -- pins every line the reference wrote; the third-party primitives
+    (nnx.Linear / LayerNorm / GroupNorm / Conv / ConvTranspose, jax.nn.dot_product_attention) are restated by the shim;
+  * tests/golden/jax_videovae_*.npz (none yet: needs a box with real jax / flax) -- pins those too.
+
+For every such file:
   * CPU: the reference's weights and recorded draws go through the ORACLE and must reproduce the reference's outputs and
     gradients (fp32: rel 1e-4 / 1e-3) -- this is what turns "parity unpinned" into pinned;
   * GPU: the same through the CUDA path (fp32 fixture -> fp32 kernels at 1e-4 / 1e-3; bf16 fixture -> bf16 at 2e-2 on
     loss / mean / logvar, north_star's bar).
-No such file can be produced in the build container (no jax, no network): those tests then SKIP with that reason, and
-one CPU test checks the consumer itself against a stand-in fixture of the same schema written from the oracle.
+One more CPU test checks the consumer itself against a stand-in fixture of the same schema written from the oracle.
 """
 import glob
 import json
@@ -18,8 +24,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")))
-NO_FIXTURE = "parity unpinned: no tests/golden/jax_videovae_*.npz (needs tests/golden/make_golden_jax.py on a JAX box)"
+import sys
+sys.path.insert(0, GOLDEN)
+import weight_recipe  # noqa: E402
+
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_videovae_*.npz")))
+NO_FIXTURE = "parity unpinned: no tests/golden/{jax,refshim}_videovae_*.npz (tests/golden/make_golden_jax.py [--shim])"
 
 
 def rel_l2(a, ref):
@@ -35,11 +45,21 @@ def rel_err(a, ref):
 def load_fixture(path):
     z = np.load(path)
     fx = {"cfg": tuple(int(v) for v in z["cfg"]), "dtype": str(z["dtype"]), "hparams": json.loads(str(z["hparams"])),
-          "video": torch.from_numpy(z["video"]), "mask": torch.from_numpy(z["mask"]).bool(),
+          "mask": torch.from_numpy(z["mask"]).bool(),
           "gumbel_u": torch.from_numpy(z["gumbel_u"]), "noise": torch.from_numpy(z["noise"]),
-          "params": {k[6:]: z[k] for k in z.files if k.startswith("param/")},
-          "grads": {k[5:]: z[k] for k in z.files if k.startswith("grad/")},
-          "out": {k[4:]: z[k] for k in z.files if k.startswith("out/")}}
+          "out": {k[4:]: z[k] for k in z.files if k.startswith("out/")}, "recon_stride": 1, "compact": "recipe" in z.files}
+    if fx["compact"]:
+        # --compact files: weights and clip by name from tests/golden/weight_recipe.py, gradients as norm + max + probe
+        assert str(z["recipe"]) == weight_recipe.RECIPE_ID
+        fx["video"] = torch.from_numpy(weight_recipe.clip(tuple(int(v) for v in z["video_shape"])))
+        fx["params"] = {k[7:]: weight_recipe.param(k[7:], z[k]) for k in z.files if k.startswith("pshape/")}
+        fx["grads"] = {k[6:]: {"norm": float(z[k]), "max": float(z["gmax/" + k[6:]]), "probe": z["gprobe/" + k[6:]]}
+                       for k in z.files if k.startswith("gnorm/")}
+        fx["recon_stride"] = int(z["recon_stride"])
+    else:
+        fx["video"] = torch.from_numpy(z["video"])
+        fx["params"] = {k[6:]: z[k] for k in z.files if k.startswith("param/")}
+        fx["grads"] = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
     return fx
 
 
@@ -72,8 +92,14 @@ def check_against_fixture(fx, loss, aux, m, tol, grad_tol, lowp=False):
     out = fx["out"]
     assert np.array_equal(aux["selection"].detach().float().cpu().numpy().reshape(-1), out["selection"].reshape(-1))
     keys = ("mean", "logvar") if lowp else ("mean", "logvar", "reconstruction", "compressed")
+    st = fx.get("recon_stride", 1)
+    report = {}
     for k in keys:
-        assert rel_err(aux[k].detach().float().cpu(), out[k]) < tol, k
+        got = aux[k].detach().float().cpu()
+        if k == "reconstruction":
+            got = got[:, :, ::st, ::st, :]
+        report[k] = rel_err(got, out[k])
+        assert report[k] < tol, (k, report[k])
     for k in (("MSE",) if lowp else ("MSE", "selection_loss", "kl_loss")):
         assert abs(float(aux[k]) - float(out[k])) <= tol * max(abs(float(out[k])), 1e-6), k
     assert abs(float(loss) - float(out["loss"])) <= tol * abs(float(out["loss"]))
@@ -81,7 +107,27 @@ def check_against_fixture(fx, loss, aux, m, tol, grad_tol, lowp=False):
         return
     named = dict(m.named_parameters())
     checked = 0
+    worst = (0.0, None)
     for name, ref in fx["grads"].items():
+        if isinstance(ref, dict):                            # compact fixture: norm, max and a strided probe
+            if ref["max"] == 0.0:
+                continue
+            got = named[name].grad.detach().float().cpu().numpy()
+            gn = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+            e_norm = abs(gn - ref["norm"]) / ref["norm"]
+            d_probe = np.abs(weight_recipe.grad_probe(got) - ref["probe"]) / ref["max"]
+            e_probe = float(d_probe.max())
+            assert e_norm < grad_tol, (name, e_norm)
+            # The U-Net has max-pools: when the two candidates of one 2x2 window differ by less than the fp32 noise of
+            # the forward pass (refshim "small": 1 window of 98304 at encoders.1, values 1e-5 apart), two correct
+            # implementations route that window's gradient to different pixels and the few kernel-gradient elements
+            # fed by that pixel move by a few 1e-3 of the tensor's maximum while everything else agrees to 1e-6.  So:
+            # the norm to grad_tol, >= 94 % of the probe to 5 * grad_tol, every probe element to 2e-2.
+            assert float((d_probe < 5 * grad_tol).mean()) >= 0.94, (name, e_probe, float((d_probe < 5 * grad_tol).mean()))
+            assert e_probe < 2e-2, (name, e_probe)
+            worst = max(worst, (max(e_norm, e_probe), name))
+            checked += 1
+            continue
         if float(np.abs(ref).max()) == 0.0:
             continue
         got = named[name].grad.detach().float().cpu()
@@ -91,6 +137,10 @@ def check_against_fixture(fx, loss, aux, m, tol, grad_tol, lowp=False):
         assert rel_err(got, ref) < 5 * grad_tol, name
         checked += 1
     assert checked >= 50
+    report.update(loss=abs(float(loss) - float(out["loss"])) / abs(float(out["loss"])), grads_checked=checked,
+                  worst_grad=worst)
+    print("fixture parity:", report)
+    return report
 
 
 # ------------------------------------------------------------------------------------------------ real fixtures
