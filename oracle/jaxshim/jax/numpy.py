@@ -131,6 +131,16 @@ def var(x, axis=None, keepdims=False):
     return _a(x).var(unbiased=False, **_axis_kw(axis, keepdims))
 
 
+def std(x, axis=None, keepdims=False):
+    """jnp.std: sqrt of the population variance (ddof = 0)."""
+    return torch.sqrt(var(x, axis, keepdims))
+
+
+def prod(x, axis=None, keepdims=False):
+    x = _a(x)
+    return x.prod(**_axis_kw(axis, keepdims)) if axis is not None else x.prod()
+
+
 def concatenate(arrays, axis=0):
     return torch.cat([_a(v) for v in arrays], dim=axis)
 

@@ -45,3 +45,13 @@ def truncated_normal(key, lower, upper, shape=(), dtype=torch.float32):
     t = torch.empty(tuple(shape), dtype=torch.float32)
     torch.nn.init.trunc_normal_(t, 0.0, 1.0, lower, upper, generator=key._generator())
     return t.to(to_dtype(dtype)).as_subclass(Array)
+
+
+def bernoulli(key, p=0.5, shape=None):
+    """jax.random.bernoulli: `uniform(key, shape) < p` (jax/_src/random.py::_bernoulli).  Looks `uniform` up in the module
+    at call time so that a recorder patched over jax.random.uniform sees the draw."""
+    import sys
+    p = p if isinstance(p, torch.Tensor) else torch.as_tensor(p, dtype=torch.float32)
+    shape = tuple(p.shape) if shape is None else tuple(shape)
+    u = sys.modules[__name__].uniform(key, shape, p.dtype if p.is_floating_point() else torch.float32)
+    return (u < p).as_subclass(Array)

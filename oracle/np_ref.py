@@ -2,8 +2,9 @@
 
 Written from the published definitions (not from oracle/nn.py) so that the two
 can be checked against each other in tests/test_oracle.py: the torch oracle is
-"pinned" against these, since the reference has no golden vectors and JAX is not
-installable here (PARITY UNPINNED against the real reference).
+checked against these (and so are the primitives of oracle/jaxshim, tests/test_jaxshim_cpu.py), since the
+reference has no golden vectors and JAX is not installable here (the third-party
+primitives are unpinned against real JAX; see oracle/__init__.py).
 """
 import numpy as np
 

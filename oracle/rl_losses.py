@@ -1,4 +1,5 @@
-"""Oracle restatement of the RL training loss (CPU torch, TEST INFRASTRUCTURE ONLY).  Parity unpinned (no JAX here).
+"""Oracle restatement of the RL training loss (CPU torch, TEST INFRASTRUCTURE ONLY).  Pinned against the reference's own
+loss_fn executed on oracle/jaxshim (tests/golden/refshim_rlvae_*.npz, tests/test_jax_golden.py); not against real JAX.
 
 Follows train/rl_nonadversarial.py:59-60 (per_sample_mean), :70-72 (magnify_negatives), :100-186 (loss_fn) and
 :188-209 (train_step / eval_step mask plumbing) over the 6-tuple of train/rl_model.py.  The VGG perceptual term

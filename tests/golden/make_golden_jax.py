@@ -45,6 +45,9 @@ CFGS = {
     "hd64": dict(cfg=(64, 64, 3, 16, 2, 2, 256, 2, 128, 32, 8, 4), batch=2, frames=8, keep=(8, 5)),
 }
 HPARAMS = {"gamma1": 0.05, "gamma2": 0.001, "max_compression_rate": 2, "magnify_negatives_rate": 100}
+# train/rl_nonadversarial.py:47-57,255-263
+RL_HPARAMS = {"gamma1": 0.2, "gamma2": 0.001, "gamma3": 0.1, "gamma4": 0.05, "max_compression_rate": 2,
+              "magnify_negatives_rate": 100, "rl_loss_weight": 0.01}
 
 
 def _path_str(path):
@@ -70,22 +73,34 @@ def flatten_state(state):
     return {_path_str(p): np.asarray(v) for p, v in leaves}
 
 
-def reference_loss_fn(reference_root):
-    """`magnify_negatives` and `loss_fn` exactly as written in train/legacy/training_loop_adversarial.py."""
+def reference_functions(path, names, want):
+    """The functions `names` exactly as written in the reference file `path` (extracted from its AST and executed
+    unmodified; the rest of the file -- training-loop glue, wandb / orbax imports -- is not run).  Returns `want`."""
     import jax
     import jax.numpy as jnp
     from einops import rearrange, reduce, repeat
     from flax import nnx
     from jaxtyping import Array, Float
-    path = os.path.join(reference_root, "train", "legacy", "training_loop_adversarial.py")
     src = open(path).read()
     tree = ast.parse(src)
-    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("magnify_negatives", "loss_fn")]
-    assert {n.name for n in keep} == {"magnify_negatives", "loss_fn"}, "reference layout changed"
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in keep} == set(names), "reference layout changed"
     ns = {"jax": jax, "jnp": jnp, "nnx": nnx, "rearrange": rearrange, "reduce": reduce, "repeat": repeat,
           "Float": Float, "Array": Array}
     exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)      # noqa: S102 (the reference's own code)
-    return ns["loss_fn"]
+    return ns[want]
+
+
+def reference_loss_fn(reference_root):
+    """`magnify_negatives` and `loss_fn` exactly as written in train/legacy/training_loop_adversarial.py."""
+    return reference_functions(os.path.join(reference_root, "train", "legacy", "training_loop_adversarial.py"),
+                               ("magnify_negatives", "loss_fn"), "loss_fn")
+
+
+def reference_rl_loss_fn(reference_root):
+    """`per_sample_mean`, `magnify_negatives` and `loss_fn` exactly as written in train/rl_nonadversarial.py:59-186."""
+    return reference_functions(os.path.join(reference_root, "train", "rl_nonadversarial.py"),
+                               ("per_sample_mean", "magnify_negatives", "loss_fn"), "loss_fn")
 
 
 class DrawRecorder:
@@ -96,23 +111,30 @@ class DrawRecorder:
 
     def __enter__(self):
         import jax
-        self._u, self._n = jax.random.uniform, jax.random.normal
+        self._u, self._n, self._b = jax.random.uniform, jax.random.normal, jax.random.bernoulli
 
         def uniform(key, shape=(), *a, **k):
             out = self._u(key, shape, *a, **k)
             self.uniform.append(np.asarray(out))
             return out
 
+        def bernoulli(key, p=0.5, shape=None):
+            # jax.random.bernoulli IS `uniform(key, shape) < p` (jax/_src/random.py::_bernoulli); spelled out so that the
+            # uniform draw behind it is recorded
+            import jax.numpy as jnp
+            p = jnp.asarray(p)
+            return uniform(key, tuple(p.shape) if shape is None else tuple(shape)) < p
+
         def normal(key, shape=(), *a, **k):
             out = self._n(key, shape, *a, **k)
             self.normal.append(np.asarray(out))
             return out
-        jax.random.uniform, jax.random.normal = uniform, normal
+        jax.random.uniform, jax.random.normal, jax.random.bernoulli = uniform, normal, bernoulli
         return self
 
     def __exit__(self, *exc):
         import jax
-        jax.random.uniform, jax.random.normal = self._u, self._n
+        jax.random.uniform, jax.random.normal, jax.random.bernoulli = self._u, self._n, self._b
 
 
 def main():
@@ -121,6 +143,9 @@ def main():
     ap.add_argument("--cfg", default="small", choices=sorted(CFGS))
     ap.add_argument("--dtype", default="float32", choices=["float32", "bfloat16"])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--model", default="vae", choices=["vae", "rl"],
+                    help="vae: train/model.py + the loss_fn of train/legacy/training_loop_adversarial.py; rl: "
+                         "train/rl_model.py + the loss_fn of train/rl_nonadversarial.py (writes *_rlvae_*.npz)")
     ap.add_argument("--shim", action="store_true",
                     help="no JAX here: run the reference's files on oracle/jaxshim (jax / flax.nnx look-alikes on CPU torch) "
                          "and write refshim_videovae_<cfg>_<dtype>.npz")
@@ -139,7 +164,10 @@ def main():
     import jax.numpy as jnp
     from einops import rearrange, repeat
     from flax import nnx
-    from model import VideoVAE                     # the reference's train/model.py
+    if args.model == "vae":
+        from model import VideoVAE                 # the reference's train/model.py
+    else:
+        from rl_model import VideoVAE              # the reference's train/rl_model.py
 
     spec = CFGS[args.cfg]
     cfg, b, t = spec["cfg"], spec["batch"], spec["frames"]
@@ -181,13 +209,26 @@ def main():
     mask = repeat(mask, "b 1 1 time -> b hw 1 1 time", hw=hw)
     mask = rearrange(mask, "b hw 1 1 time -> (b hw) 1 1 time")
 
-    loss_fn = reference_loss_fn(args.reference)
-    grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
-    with DrawRecorder() as rec:
-        (loss, (mse, sel_loss, kl, recon, density)), grads = grad_fn(
-            model, video.astype(dtype), mask, original_mask, nnx.Rngs(3), HPARAMS)
+    rl = args.model == "rl"
+    hparams = RL_HPARAMS if rl else HPARAMS
+    if rl:
+        # the VGG term of rl_nonadversarial.py:125 is the caller's function (flaxmodels + downloaded weights in the
+        # reference); a closed-form stand-in with the same signature keeps the gamma3 path and its gradient alive
+        def perceptual(vgg_params, reconstruction, target):
+            return jnp.mean(jnp.abs(reconstruction - target) ** 3, axis=(1, 2, 3, 4))
+        loss_fn = reference_rl_loss_fn(args.reference)
+        grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
+        with DrawRecorder() as rec:
+            (loss, aux), grads = grad_fn(model, video.astype(dtype), mask, original_mask, nnx.Rngs(3), hparams, perceptual, None)
+        recon = aux["reconstruction"]
+    else:
+        loss_fn = reference_loss_fn(args.reference)
+        grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
+        with DrawRecorder() as rec:
+            (loss, (mse, sel_loss, kl, recon, density)), grads = grad_fn(
+                model, video.astype(dtype), mask, original_mask, nnx.Rngs(3), hparams)
     assert len(rec.uniform) == 1 and len(rec.normal) == 1, (len(rec.uniform), len(rec.normal))
-    gumbel_u, noise = rec.uniform[0], rec.normal[0]
+    gumbel_u, noise = rec.uniform[0], rec.normal[0]              # rl: the uniform behind jax.random.bernoulli
 
     # second, non-differentiated call with the SAME draws to export the remaining outputs of VideoVAE.__call__
     class Replay:
@@ -195,20 +236,24 @@ def main():
             self.u, self.n = [gumbel_u], [noise]
 
         def __enter__(self):
-            self._u, self._n = jax.random.uniform, jax.random.normal
+            self._u, self._n, self._b = jax.random.uniform, jax.random.normal, jax.random.bernoulli
             jax.random.uniform = lambda key, shape=(), *a, **k: jnp.asarray(self.u.pop(0))
             jax.random.normal = lambda key, shape=(), *a, **k: jnp.asarray(self.n.pop(0))
+            jax.random.bernoulli = lambda key, p=0.5, shape=None: jnp.asarray(self.u.pop(0)) < p
             return self
 
         def __exit__(self, *exc):
-            jax.random.uniform, jax.random.normal = self._u, self._n
+            jax.random.uniform, jax.random.normal, jax.random.bernoulli = self._u, self._n, self._b
     with Replay():
-        recon2, compressed, selection, logvar, mean = model(video.astype(dtype), mask, nnx.Rngs(3), train=True)
+        if rl:
+            recon2, compressed, selection, selection_mask, logvar, mean = model(video.astype(dtype), mask, nnx.Rngs(3), train=True)
+        else:
+            recon2, compressed, selection, logvar, mean = model(video.astype(dtype), mask, nnx.Rngs(3), train=True)
     assert np.allclose(np.asarray(recon2, np.float32), np.asarray(recon, np.float32), rtol=1e-5, atol=1e-6)
 
-    out = {"cfg": np.asarray(cfg, np.int64), "dtype": np.asarray(args.dtype), "hparams": np.asarray(json.dumps(HPARAMS)),
+    out = {"cfg": np.asarray(cfg, np.int64), "dtype": np.asarray(args.dtype), "hparams": np.asarray(json.dumps(hparams)),
            "video": np.asarray(video, np.float32), "mask": np.asarray(original_mask), "gumbel_u": gumbel_u.astype(np.float32),
-           "noise": noise.astype(np.float32)}
+           "noise": noise.astype(np.float32), "model": np.asarray(args.model)}
     if args.compact:
         out["recipe"] = np.asarray(weight_recipe.RECIPE_ID)
         del out["video"]                                         # weight_recipe.clip(shape)
@@ -228,9 +273,16 @@ def main():
         for name, v in flatten_state(grads).items():
             out["grad/" + name] = v.astype(np.float32)
     f32 = lambda x: np.asarray(x, np.float32)      # noqa: E731
-    out.update({"out/loss": f32(loss), "out/MSE": f32(mse), "out/selection_loss": f32(sel_loss), "out/kl_loss": f32(kl),
-                "out/kept_frame_density": f32(density), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
-                "out/selection": f32(selection), "out/logvar": f32(logvar), "out/mean": f32(mean)})
+    if rl:
+        out.update({"out/" + k: f32(aux[k]) for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density",
+                                                      "mean_trajectory_prob", "rl_loss", "per_sample_MAE")})
+        out.update({"out/loss": f32(loss), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
+                    "out/selection": f32(selection), "out/selection_mask": f32(selection_mask), "out/logvar": f32(logvar),
+                    "out/mean": f32(mean)})
+    else:
+        out.update({"out/loss": f32(loss), "out/MSE": f32(mse), "out/selection_loss": f32(sel_loss), "out/kl_loss": f32(kl),
+                    "out/kept_frame_density": f32(density), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
+                    "out/selection": f32(selection), "out/logvar": f32(logvar), "out/mean": f32(mean)})
     if args.compact:
         stride = 1 if out["out/reconstruction"].size <= 200_000 else 2          # keep the file commit-sized
         out["recon_stride"] = np.asarray(stride, np.int64)
@@ -240,7 +292,7 @@ def main():
     out["generator"] = np.asarray(("reference files on oracle/jaxshim (CPU torch), jax " if shim else "reference files on jax ")
                                   + jax.__version__)
     prefix = "refshim" if shim else "jax"
-    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{prefix}_videovae_{args.cfg}_{args.dtype}.npz")
+    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{prefix}_{'rlvae' if rl else 'videovae'}_{args.cfg}_{args.dtype}.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes; loss =", float(loss), "; jax", jax.__version__)
 

@@ -29,6 +29,7 @@ sys.path.insert(0, GOLDEN)
 import weight_recipe  # noqa: E402
 
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_videovae_*.npz")))
+RL_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rlvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rlvae_*.npz")))
 NO_FIXTURE = "parity unpinned: no tests/golden/{jax,refshim}_videovae_*.npz (tests/golden/make_golden_jax.py [--shim])"
 
 
@@ -47,7 +48,8 @@ def load_fixture(path):
     fx = {"cfg": tuple(int(v) for v in z["cfg"]), "dtype": str(z["dtype"]), "hparams": json.loads(str(z["hparams"])),
           "mask": torch.from_numpy(z["mask"]).bool(),
           "gumbel_u": torch.from_numpy(z["gumbel_u"]), "noise": torch.from_numpy(z["noise"]),
-          "out": {k[4:]: z[k] for k in z.files if k.startswith("out/")}, "recon_stride": 1, "compact": "recipe" in z.files}
+          "out": {k[4:]: z[k] for k in z.files if k.startswith("out/")}, "recon_stride": 1, "compact": "recipe" in z.files,
+          "model": str(z["model"]) if "model" in z.files else "vae"}
     if fx["compact"]:
         # --compact files: weights and clip by name from tests/golden/weight_recipe.py, gradients as norm + max + probe
         assert str(z["recipe"]) == weight_recipe.RECIPE_ID
@@ -61,6 +63,77 @@ def load_fixture(path):
         fx["params"] = {k[6:]: z[k] for k in z.files if k.startswith("param/")}
         fx["grads"] = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
     return fx
+
+
+def cube_perceptual(vgg_params, reconstruction, target):
+    """The closed-form stand-in make_golden_jax.py passes as perceptual_loss_fn (rl_nonadversarial.py:125), in torch."""
+    return ((reconstruction.float() - target.float()).abs() ** 3).mean(dim=(1, 2, 3, 4))
+
+
+def run_impl_rl(fx, impl, dtype):
+    """train/rl_model.py + the RL loss of train/rl_nonadversarial.py:100-186 with the fixture's weights and draws."""
+    from video_vae_b200 import checkpoint as ck
+    cfg = fx["cfg"]
+    hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
+    u = fx["gumbel_u"]                                          # the uniform behind jax.random.bernoulli, ((b 2), t, 1, 1)
+    if impl == "oracle":
+        from oracle import Rngs
+        from oracle.losses import expand_mask
+        from oracle.rl_losses import loss_fn
+        from oracle.rl_model import VideoVAE
+        m = VideoVAE(*cfg, Rngs(0), dtype=dtype)
+        ck.load_flax_tree(m, fx["params"], strict=True)
+        loss, aux = loss_fn(m, fx["video"], expand_mask(fx["mask"], hw), fx["mask"], Rngs(0), fx["hparams"],
+                            cube_perceptual, None, noise=fx["noise"], bernoulli_u=u)
+    else:
+        import video_vae_b200 as V
+        from video_vae_b200.rl_losses import loss_fn
+        from video_vae_b200.rl_model import VideoVAE
+        m = VideoVAE(*cfg, V.Rngs(0), dtype=dtype)
+        ck.load_flax_tree(m, fx["params"], strict=True)
+        loss, aux = loss_fn(m, fx["video"].cuda(), fx["mask"][:, None, None, :].cuda(), fx["mask"].cuda(), V.Rngs(0),
+                            fx["hparams"], cube_perceptual, None, noise=fx["noise"].cuda(), bernoulli_u=u.cuda())
+    loss.backward()
+    return loss, aux, m
+
+
+def check_rl_against_fixture(fx, loss, aux, m, tol, grad_tol):
+    out = fx["out"]
+    f = lambda v: v.detach().float().cpu().numpy()             # noqa: E731
+    assert np.array_equal(f(aux["selection_mask"]).reshape(-1), out["selection_mask"].reshape(-1))
+    report = {"selection": rel_err(torch.from_numpy(f(aux["selection"]).reshape(-1)), out["selection"].reshape(-1))}
+    st = fx.get("recon_stride", 1)
+    report["reconstruction"] = rel_err(aux["reconstruction"].detach().float().cpu()[:, :, ::st, ::st, :], out["reconstruction"])
+    for k in ("selection", "reconstruction"):
+        assert report[k] < tol, (k, report[k])
+    for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density", "mean_trajectory_prob",
+              "per_sample_MAE"):
+        report[k] = abs(float(aux[k]) - float(out[k])) / max(abs(float(out[k])), 1e-6)
+        assert report[k] <= tol, (k, report[k])
+    # rl_loss is mean(probs * disadvantages) with probs == 1 in value and disadvantages centred per pair: zero up to
+    # rounding; it matters through its gradient (the selection layers' gradients below)
+    assert abs(float(aux["rl_loss"]) - float(out["rl_loss"])) <= 1e-5
+    report["loss"] = abs(float(loss) - float(out["loss"])) / abs(float(out["loss"]))
+    assert report["loss"] <= tol
+    named = dict(m.named_parameters())
+    checked, worst = 0, (0.0, None)
+    for name, ref in fx["grads"].items():
+        assert isinstance(ref, dict), "rl fixtures are written with --compact"
+        if ref["max"] == 0.0:
+            continue
+        got = named[name].grad.detach().float().cpu().numpy()
+        gn = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+        e_norm = abs(gn - ref["norm"]) / ref["norm"]
+        d_probe = np.abs(weight_recipe.grad_probe(got) - ref["probe"]) / ref["max"]
+        assert e_norm < grad_tol, (name, e_norm)
+        assert float((d_probe < 5 * grad_tol).mean()) >= 0.94 and float(d_probe.max()) < 2e-2, (name, float(d_probe.max()))
+        worst = max(worst, (max(e_norm, float(d_probe.max())), name))
+        checked += 1
+    assert checked >= 50
+    assert any("selection_layer" in n for n, r in fx["grads"].items() if r["max"] > 0.0)      # the RL term's gradient is there
+    report.update(grads_checked=checked, worst_grad=worst)
+    print("rl fixture parity:", report)
+    return report
 
 
 def run_impl(fx, impl, dtype):
@@ -165,6 +238,26 @@ def test_cuda_path_reproduces_reference_outputs(path):
     else:
         loss, aux, m = run_impl(fx, "cuda", torch.bfloat16)
         check_against_fixture(fx, loss, aux, m, 2e-2, None, lowp=True)
+
+
+@pytest.mark.skipif(not RL_FIXTURES, reason=NO_FIXTURE)
+@pytest.mark.parametrize("path", RL_FIXTURES or [None])
+def test_oracle_reproduces_reference_rl_outputs(path):
+    """train/rl_model.py and the loss_fn of train/rl_nonadversarial.py (the reference's files, executed by
+    tests/golden/make_golden_jax.py --model rl) against their oracle restatements (oracle/rl_model.py, rl_losses.py)."""
+    fx = load_fixture(path)
+    assert fx["model"] == "rl" and fx["dtype"] == "float32"
+    loss, aux, m = run_impl_rl(fx, "oracle", torch.float32)
+    check_rl_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not RL_FIXTURES, reason=NO_FIXTURE)
+@pytest.mark.parametrize("path", RL_FIXTURES or [None])
+def test_cuda_path_reproduces_reference_rl_outputs(path):
+    fx = load_fixture(path)
+    loss, aux, m = run_impl_rl(fx, "cuda", torch.float32)
+    check_rl_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
 
 
 # ------------------------------------------------------------------------------------------------ consumer self-check
