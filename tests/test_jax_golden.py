@@ -177,7 +177,9 @@ def check_against_fixture(fx, loss, aux, m, tol, grad_tol, lowp=False):
         assert abs(float(aux[k]) - float(out[k])) <= tol * max(abs(float(out[k])), 1e-6), k
     assert abs(float(loss) - float(out["loss"])) <= tol * abs(float(out["loss"]))
     if grad_tol is None:
-        return
+        report["loss"] = abs(float(loss) - float(out["loss"])) / abs(float(out["loss"]))
+        print("fixture parity (low precision):", report)
+        return report
     named = dict(m.named_parameters())
     checked = 0
     worst = (0.0, None)
@@ -227,6 +229,26 @@ def test_oracle_reproduces_reference_outputs(path):
     check_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
 
 
+BF16_PAIRS = [(p, p.replace("_bfloat16.npz", "_float32.npz")) for p in FIXTURES
+              if p.endswith("_bfloat16.npz") and os.path.exists(p.replace("_bfloat16.npz", "_float32.npz"))]
+
+
+@pytest.mark.skipif(not BF16_PAIRS, reason="no bf16 / fp32 fixture pair")
+@pytest.mark.parametrize("lowp,full", BF16_PAIRS or [(None, None)])
+def test_reference_bf16_against_its_own_fp32(lowp, full):
+    """The reference's code run with dtype=bfloat16 (flax promote_dtype semantics: bf16 activations and matmul operands,
+    fp32 parameters, fp32 LayerNorm / GroupNorm statistics and attention logits) against the same code in fp32, same
+    weights and draws: the depth-wise growth the reference documents (train/llm_tests.py:491-502) stays inside
+    north_star's 2e-2 at production depth -- the yardstick the CUDA bf16 path is held to."""
+    a, b = np.load(lowp), np.load(full)
+    assert np.array_equal(a["gumbel_u"], b["gumbel_u"]) and np.array_equal(a["noise"], b["noise"])
+    assert np.array_equal(a["out/selection"], b["out/selection"])
+    rep = {k: rel_err(torch.from_numpy(a["out/" + k]), b["out/" + k]) for k in ("mean", "logvar", "reconstruction")}
+    rep["loss"] = abs(float(a["out/loss"]) - float(b["out/loss"])) / abs(float(b["out/loss"]))
+    print("reference bf16 vs its fp32:", os.path.basename(lowp), rep)
+    assert rep["mean"] < 2e-2 and rep["logvar"] < 2e-2 and rep["loss"] < 2e-2 and rep["reconstruction"] < 3e-2
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not FIXTURES, reason=NO_FIXTURE)
 @pytest.mark.parametrize("path", FIXTURES or [None])
@@ -236,8 +258,14 @@ def test_cuda_path_reproduces_reference_outputs(path):
         loss, aux, m = run_impl(fx, "cuda", torch.float32)
         check_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
     else:
+        # bf16 fixture = the reference's code run with dtype=bfloat16.  Two bars: against the reference's fp32 outputs for
+        # the same weights and draws (the sibling *_float32.npz) north_star's 2e-2 on loss / mean / logvar; against the
+        # reference's bf16 outputs 3e-2 (two independent bf16 roundings of a 21-layer network: sqrt(2) x the above)
         loss, aux, m = run_impl(fx, "cuda", torch.bfloat16)
-        check_against_fixture(fx, loss, aux, m, 2e-2, None, lowp=True)
+        check_against_fixture(fx, loss, aux, m, 3e-2, None, lowp=True)
+        sibling = path.replace("_bfloat16.npz", "_float32.npz")
+        if os.path.exists(sibling):
+            check_against_fixture(load_fixture(sibling), loss, aux, m, 2e-2, None, lowp=True)
 
 
 @pytest.mark.skipif(not RL_FIXTURES, reason=NO_FIXTURE)
