@@ -42,6 +42,10 @@ CFGS = {
     # one is for local use only (680 MB of fp32 weights in the .npz)
     "prod128": dict(cfg=(128, 128, 3, 16, 9, 12, 1536, 8, 512, 64, 8, 4), batch=1, frames=16, keep=(12,)),
     # 64-wide heads (the tcgen05 attention / GEMM path of the CUDA build) at a small depth
+    # BASELINE configs[4] shapes at depth 1: 512x512 frames (hw = 1024: the streaming L = 1024 spatial attention, the
+    # full-resolution U-Net maps) and 64-frame clips (temporal attention at L = 64 with a ragged prefix mask)
+    "hw1024": dict(cfg=(512, 512, 3, 16, 1, 1, 1536, 8, 512, 16, 8, 4), batch=1, frames=4, keep=(3,)),
+    "t64": dict(cfg=(64, 64, 3, 16, 1, 1, 1536, 8, 512, 64, 8, 4), batch=2, frames=64, keep=(64, 41)),
     "hd64": dict(cfg=(64, 64, 3, 16, 2, 2, 256, 2, 128, 32, 8, 4), batch=2, frames=8, keep=(8, 5)),
 }
 HPARAMS = {"gamma1": 0.05, "gamma2": 0.001, "max_compression_rate": 2, "magnify_negatives_rate": 100}
@@ -106,8 +110,8 @@ def reference_rl_loss_fn(reference_root):
 class DrawRecorder:
     """Records every jax.random.uniform / normal result produced while active."""
 
-    def __init__(self):
-        self.uniform, self.normal = [], []
+    def __init__(self, normal_fn=None):
+        self.uniform, self.normal, self.normal_fn = [], [], normal_fn
 
     def __enter__(self):
         import jax
@@ -126,7 +130,11 @@ class DrawRecorder:
             return uniform(key, tuple(p.shape) if shape is None else tuple(shape)) < p
 
         def normal(key, shape=(), *a, **k):
-            out = self._n(key, shape, *a, **k)
+            if self.normal_fn is not None:                       # --compact: the draw is a function of the shape
+                import jax.numpy as jnp
+                out = jnp.asarray(self.normal_fn(shape))
+            else:
+                out = self._n(key, shape, *a, **k)
             self.normal.append(np.asarray(out))
             return out
         jax.random.uniform, jax.random.normal, jax.random.bernoulli = uniform, normal, bernoulli
@@ -218,13 +226,13 @@ def main():
             return jnp.mean(jnp.abs(reconstruction - target) ** 3, axis=(1, 2, 3, 4))
         loss_fn = reference_rl_loss_fn(args.reference)
         grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
-        with DrawRecorder() as rec:
+        with DrawRecorder(weight_recipe.normal if args.compact else None) as rec:
             (loss, aux), grads = grad_fn(model, video.astype(dtype), mask, original_mask, nnx.Rngs(3), hparams, perceptual, None)
         recon = aux["reconstruction"]
     else:
         loss_fn = reference_loss_fn(args.reference)
         grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
-        with DrawRecorder() as rec:
+        with DrawRecorder(weight_recipe.normal if args.compact else None) as rec:
             (loss, (mse, sel_loss, kl, recon, density)), grads = grad_fn(
                 model, video.astype(dtype), mask, original_mask, nnx.Rngs(3), hparams)
     assert len(rec.uniform) == 1 and len(rec.normal) == 1, (len(rec.uniform), len(rec.normal))
@@ -258,6 +266,9 @@ def main():
         out["recipe"] = np.asarray(weight_recipe.RECIPE_ID)
         del out["video"]                                         # weight_recipe.clip(shape)
         out["video_shape"] = np.asarray(video.shape, np.int64)
+        assert np.array_equal(out["noise"], weight_recipe.normal(out["noise"].shape))
+        out["noise_shape"] = np.asarray(out["noise"].shape, np.int64)
+        del out["noise"]                                         # weight_recipe.normal(shape)
         for name, v in flatten_state(nnx.state(model, nnx.Param)).items():
             assert np.array_equal(v.astype(np.float32), weight_recipe.param(name, v.shape)), name
             out["pshape/" + name] = np.asarray(v.shape, np.int64)
@@ -284,9 +295,14 @@ def main():
                     "out/kept_frame_density": f32(density), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
                     "out/selection": f32(selection), "out/logvar": f32(logvar), "out/mean": f32(mean)})
     if args.compact:
-        stride = 1 if out["out/reconstruction"].size <= 200_000 else 2          # keep the file commit-sized
+        import math
+        stride = max(1, math.ceil(math.sqrt(out["out/reconstruction"].size / 200_000)))  # keep the file commit-sized
         out["recon_stride"] = np.asarray(stride, np.int64)
         out["out/reconstruction"] = np.ascontiguousarray(out["out/reconstruction"][:, :, ::stride, ::stride, :])
+        lat = 1 if out["out/mean"].size <= 200_000 else -(-out["out/mean"].size // 200_000)   # patches kept: every lat-th
+        out["latent_stride"] = np.asarray(lat, np.int64)
+        for k in ("out/mean", "out/logvar", "out/compressed"):
+            out[k] = np.ascontiguousarray(out[k][:, :, ::lat, :])
     shim = bool(getattr(jax, "IS_SHIM", False))
     assert shim == args.shim, "a jax look-alike is on sys.path without --shim (or --shim found the real jax first)"
     out["generator"] = np.asarray(("reference files on oracle/jaxshim (CPU torch), jax " if shim else "reference files on jax ")

@@ -48,6 +48,12 @@ def clip(shape, seed=11):
     return np.random.RandomState(seed).random_sample(tuple(shape)).astype(np.float32)
 
 
+def normal(shape, seed=13):
+    """The reparameterisation noise of a --compact fixture: N(0, 1) by shape (replaces the model's jax.random.normal draw,
+    so that the file need not carry b * t * hw * latent floats)."""
+    return np.random.RandomState(seed).standard_normal(tuple(int(v) for v in shape)).astype(np.float32)
+
+
 def grad_probe(g):
     """Fixed sample of a gradient tensor: PROBE elements at an even stride over the flattened tensor."""
     flat = np.asarray(g, np.float32).reshape(-1)
