@@ -589,6 +589,7 @@ def _attention_reference(qk, qkv, d_o, geom, temporal, b, t, hw, H, HD, mask_bl)
 
 @pytest.mark.parametrize("name,b,t,hw,temporal,masked", [
     ("spatial_L256", 1, 3, 256, False, False),
+    ("spatial_L256_persistent_3_units_per_sm", 2, 23, 256, False, False),   # 46 sequences x heads > 2 x 148 CTAs, ragged
     ("spatial_L128", 1, 2, 128, False, False),
     ("spatial_L64_pack2_tail", 1, 5, 64, False, False),
     ("temporal_L16_masked", 2, 16, 16, True, True),
@@ -607,6 +608,30 @@ def test_tcgen05_attention_fwd_bwd_vs_oracle(V, name, b, t, hw, temporal, masked
     masked clip (uniform attention, no gradient to q/k) and the streaming long-sequence kernels (L > 256)."""
     from video_vae_b200 import _ffi
     _attention_case(name, b, t, hw, temporal, masked, _ffi.BACKEND_TCGEN05)
+
+
+@pytest.mark.parametrize("nseq", [1, 19, 41])
+def test_persistent_attention_forward_is_bit_identical_to_the_tile_kernel(V, nseq):
+    """Unmasked L = 256: attn_fwd256_sm100_kernel (one CTA per SM looping over (sequence, head) units, two softmax groups)
+    performs the same arithmetic in the same order as the one-tile-per-CTA kernel (vvae_debug_set(18, 1)): outputs and
+    log-sum-exp must be equal bit for bit, for fewer units than SMs and for a ragged multiple."""
+    import math
+    from video_vae_b200 import _ffi, ops
+    from video_vae_b200.ops import AttnGeom
+    H, HD, L = 8, 64, 256
+    g = torch.Generator(device="cuda").manual_seed(nseq)
+    qkv = torch.randn(nseq * L, 3 * H * HD, device="cuda", generator=g).bfloat16()
+    geom = AttnGeom(nseq, 1, L, L, 0, 1)
+    q, k, v = qkv[:, :H * HD], qkv[:, H * HD:2 * H * HD], qkv[:, 2 * H * HD:]
+    try:
+        _ffi.lib.vvae_debug_set(18, 1)
+        o_ref, lse_ref = ops.attn_fwd(geom, H, HD, q, k, v, None, 1.0 / math.sqrt(HD))
+        _ffi.lib.vvae_debug_set(18, 0)
+        o, lse = ops.attn_fwd(geom, H, HD, q, k, v, None, 1.0 / math.sqrt(HD))
+    finally:
+        _ffi.lib.vvae_debug_set(18, 0)
+    assert torch.isfinite(o.float()).all()
+    assert torch.equal(o, o_ref) and torch.equal(lse, lse_ref)
 
 
 @pytest.mark.parametrize("name,b,t,hw,temporal,masked", [

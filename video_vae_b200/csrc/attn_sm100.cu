@@ -1809,6 +1809,340 @@ static int atc_launch_bwd256(const vvae_attn_args& a, const AttnTcPlan& p, cudaS
   return check_launch("attn_bwd256_sm100");
 }
 
+// ============================================================================== forward, unmasked L = 256, persistent
+// One CTA per SM, one UNIT = one (sequence, head): both 128-row query blocks against the 256 keys, K and V staged once.
+//   warp 0     : TMA producer (Q as one [256 x 64] box, K, V); the next unit's Q|K are requested as soon as both score
+//                tiles of the current unit are complete, V as soon as both P.V contractions are
+//   warp 1     : MMA issuer: S_A = Q0.K^T, S_B = Q1.K^T (TMEM columns [0,256) and [256,512)), then O_X = P_X.V into the
+//                first 64 columns of S_X once softmax group X has turned S_X into P_X
+//   warps 4-7  : softmax group A (query block 0), warps 8-11: group B (query block 1): one query row per thread out of
+//                TMEM (row maximum, exp2, bf16 P into the 128B-swizzled K-major operand tile), then O / rowsum staged in
+//                the dead P tile and stored by TMA, log-sum-exp stored directly
+// While one group runs its softmax the tensor core works for the other one, and no per-tile prologue, operand-load wait
+// or row-per-thread global store is left on the critical path (one-tile-per-CTA kernel above: 10.5 k cycles per tile of
+// which 2.6 k prologue + load and 1.6 k output store; two co-resident CTAs reached 8.1 k per tile per SM).
+// Measured (scripts/attn_fwd256_ab.py, cold L2): 128 sequences x 8 heads 64.5 -> 46.1 us, 512 sequences 216 -> 139 us
+// (318 -> 493 TFLOP/s), outputs and log-sum-exp bit-identical to the one-tile-per-CTA kernel.  Timeline
+// (scripts/attn_fwd256_timeline.py): 8.0 k cycles per unit = 4.0 k per tile; per group: row maxima 1.2 k, exp + P store
+// 3.9 k (MUFU: 65 536 exp2 per unit at 16 per clock = 4.1 k per unit is the floor of this phase when both groups are
+// in it), wait for P.V 1.5 k (16 MMAs of N = 64), O drain + store 1.0 k, next S 0.4 k.  Issuing both S at the start
+// of a unit (lock-step, vvae_debug_set(10, 32)) is 12 % slower: both groups then contend for the MUFU at once.
+// Every mbarrier completes exactly once per unit: a wait's parity is the unit counter's low bit.
+struct AttnFwd256Params {
+  AttnTcPlan pl;
+  float* lse;
+  float scale;
+  long long units;
+  int dbg, dbg_cta;
+};
+
+__global__ void __launch_bounds__(384, 1)
+attn_fwd256_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                         const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
+                         const AttnFwd256Params q) {
+  const AttnTcPlan& p = q.pl;
+  constexpr int BLK = 16384;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                              // [256 q][64] K-major SW128 (query block i at + i * BLK)
+  uint8_t* sK = sQ + 2 * BLK;                      // [256 keys][64] K-major SW128
+  uint8_t* sV = sK + 2 * BLK;                      // [256 keys][64] (MN-major B operand of P.V)
+  uint8_t* sP = sV + 2 * BLK;                      // [2 groups][4 key blocks][128 q][64 keys] bf16, swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 8 * BLK);
+  uint64_t* qk_full = bars;                        // Q|K of the unit have landed
+  uint64_t* qk_free = bars + 1;                    // ... and both score tiles have been computed from them
+  uint64_t* v_full = bars + 2;
+  uint64_t* v_free = bars + 3;
+  uint64_t* s_full = bars + 4;                     // [2] S_X is in TMEM
+  uint64_t* s_free = bars + 6;                     // [2] O_X has been read out: the columns of S_X can be overwritten
+  uint64_t* p_full = bars + 8;                     // [2] P_X is in shared memory
+  uint64_t* o_full = bars + 10;                    // [2] O_X is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // vvae_debug_set(10, 16): CTA vvae_debug_set(0, n) stamps clock64 in its 2nd and 3rd unit (slot = 14 * (unit - 1) + k):
+  // issuer k = 0 unit start, 1 P.V_A and the next S_A issued, 2 / 3 P_A / P_B seen; softmax group A k = 4 S seen, 5 row maxima, 6 P stored,
+  // 7 O seen, 8 O store issued; group B k = 9..13 likewise
+  const bool dbg_cta = (q.dbg & 1) && (int)blockIdx.x == q.dbg_cta && lane == 0;
+#define AF_STAMP(k) do { if (dbg_cta && (it == 1 || it == 2)) g_attn_dbg[14 * (it - 1) + (k)] = clock64(); } while (0)
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    sm100::tma_prefetch_desc(&tma_q);
+    sm100::tma_prefetch_desc(&tma_k);
+    sm100::tma_prefetch_desc(&tma_v);
+    sm100::tma_prefetch_desc(&tma_o);
+    sm100::mbar_init(qk_full, 1);
+    sm100::mbar_init(qk_free, 1);
+    sm100::mbar_init(v_full, 1);
+    sm100::mbar_init(v_free, 1);
+    for (int x = 0; x < 2; ++x) {
+      sm100::mbar_init(&s_full[x], 1);
+      sm100::mbar_init(&s_free[x], 4);
+      sm100::mbar_init(&p_full[x], 4);
+      sm100::mbar_init(&o_full[x], 1);
+    }
+    sm100::fence_barrier_init();
+  }
+  if (warp == 1) sm100::tmem_alloc<512>(tmem_slot);
+  sm100::tc_fence_before();
+  __syncthreads();
+  sm100::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const long long first = blockIdx.x, stride = gridDim.x;
+  const int n_it = first < q.units ? (int)((q.units - first + stride - 1) / stride) : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------------------------------------ producer
+      for (int it = 0; it < n_it; ++it) {
+        const long long u = first + (long long)it * stride;
+        const long long seq = u / p.heads;
+        const int h = (int)(u % p.heads);
+        const int c3 = (int)(seq / p.n_inner), c2 = (int)(seq % p.n_inner);
+        const uint32_t pp = (uint32_t)(it - 1) & 1u;
+        if (it > 0) sm100::mbar_wait(qk_free, pp);
+        sm100::mbar_expect_tx(qk_full, 4 * BLK);
+        tma_load_4d(sQ, &tma_q, qk_full, h * 64, 0, c2, c3);
+        tma_load_4d(sK, &tma_k, qk_full, h * 64, 0, c2, c3);
+        if (it > 0) sm100::mbar_wait(v_free, pp);
+        sm100::mbar_expect_tx(v_full, 2 * BLK);
+        tma_load_4d(sV, &tma_v, v_full, h * 64, 0, c2, c3);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc_s = sm100::make_idesc_bf16(128, 256, false, false);   // Q, K both K-major
+      constexpr uint32_t idesc_o = sm100::make_idesc_bf16(128, 64, false, true);     // P K-major, V MN-major
+      const uint32_t qa = sm100::smem_u32(sQ), ka = sm100::smem_u32(sK), va = sm100::smem_u32(sV), pa = sm100::smem_u32(sP);
+      // Software pipeline: ... P.V_A(u), S_A(u+1), P.V_B(u), S_B(u+1) ...  Each group's chain (S -> softmax -> P.V ->
+      // drain -> next S) is independent of the other's, and the alternation staggers the groups by half a period, so
+      // that one group's exp phase (MUFU-bound: 8 cycles per warp instruction) runs while the other group waits for the
+      // tensor core instead of both contending for the MUFU at the same time (vvae_debug_set(10, 32): lock-step order).
+      auto issue_s = [&](int x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sm100::umma_f16(tmem_base + 256 * x, sm100::make_smem_desc_sw128(qa + x * BLK + k * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(ka + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        sm100::umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+          sm100::umma_f16(tmem_base + 256 * x,
+                          sm100::make_smem_desc_sw128(pa + x * 4 * BLK + (k >> 2) * BLK + (k & 3) * 32, 16, 1024),
+                          sm100::make_smem_desc_sw128(va + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+        sm100::umma_commit(&o_full[x]);
+      };
+      const bool lockstep = (q.dbg & 2) != 0;
+      if (n_it > 0) {
+        sm100::mbar_wait(qk_full, 0);
+        sm100::tc_fence_after();
+        issue_s(0);
+        issue_s(1);
+        sm100::umma_commit(qk_free);
+      }
+#pragma unroll 1
+      for (int it = 0; it < n_it; ++it) {
+        const uint32_t ph = (uint32_t)it & 1u;
+        const bool more = it + 1 < n_it;
+        AF_STAMP(0);
+        sm100::mbar_wait(v_full, ph);
+        sm100::mbar_wait(&p_full[0], ph);
+        sm100::tc_fence_after();
+        AF_STAMP(2);
+        issue_pv(0);
+        if (more && !lockstep) {
+          sm100::mbar_wait(qk_full, ph ^ 1u);
+          sm100::mbar_wait(&s_free[0], ph);
+          sm100::tc_fence_after();
+          issue_s(0);
+        }
+        AF_STAMP(1);
+        sm100::mbar_wait(&p_full[1], ph);
+        sm100::tc_fence_after();
+        AF_STAMP(3);
+        issue_pv(1);
+        sm100::umma_commit(v_free);
+        if (more) {
+          if (lockstep) {
+            sm100::mbar_wait(qk_full, ph ^ 1u);
+            sm100::mbar_wait(&s_free[0], ph);
+            sm100::tc_fence_after();
+            issue_s(0);
+          }
+          sm100::mbar_wait(&s_free[1], ph);
+          sm100::tc_fence_after();
+          issue_s(1);
+          sm100::umma_commit(qk_free);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------------------------ softmax groups A and B
+    const int x = (warp - 4) >> 2;                     // group = query block
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // query row of the block == TMEM lane
+    const int gtid = threadIdx.x - 128 - 128 * x;      // 0..127 inside the group
+    const int sk = (quarter == 0) ? 4 + 5 * x : -100;   // stamp slots of this group's first warp
+    const float k2 = q.scale * 1.4426950408889634f;
+    const uint32_t trow = tmem_base + 256 * x + ((uint32_t)(quarter * 32) << 16);
+    uint8_t* sPx = sP + x * 4 * BLK;
+    uint8_t* prow = sPx + r * 128;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const int bar_id = 1 + x;
+#pragma unroll 1
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = (uint32_t)it & 1u;
+      const long long u = first + (long long)it * stride;
+      const long long seq = u / p.heads;
+      const int h = (int)(u % p.heads);
+      sm100::mbar_wait(&s_full[x], ph);
+      sm100::tc_fence_after();
+      if (sk > 0) AF_STAMP(sk);
+      // pass 1: row maximum of the logits
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t sr[32];
+        sm100::tmem_ld_32x32(trow + c0, sr);
+        sm100::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      }
+      // the row maximum of s * scale: scale > 0 is not assumed
+      mx = q.scale >= 0.f ? mx * q.scale : -INFINITY;
+      if (q.scale < 0.f) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t sr[32];
+          sm100::tmem_ld_32x32(trow + c0, sr);
+          sm100::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]) * q.scale);
+        }
+      }
+      if (sk > 0) AF_STAMP(sk + 1);
+      // the previous unit's O tile (staged in this group's P tile) has been read by its TMA store
+      if (gtid == 0) atb_bulk_wait_read();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      // pass 2: p = exp(s - max), row sum, bf16 P into the swizzled K-major operand tile
+      const float mx2 = mx * 1.4426950408889634f;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint8_t* pblk = prow + (c0 >> 6) * BLK;
+        const uint32_t ch0 = (uint32_t)(c0 & 63) >> 3;
+        uint32_t sr[32];
+        sm100::tmem_ld_32x32(trow + c0, sr);
+        sm100::tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pv[i] = atc_exp2(__uint_as_float(sr[i]) * k2 - mx2);
+          sum += pv[i];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          __nv_bfloat162 t0 = __floats2bfloat162_rn(pv[8 * j + 0], pv[8 * j + 1]);
+          __nv_bfloat162 t1 = __floats2bfloat162_rn(pv[8 * j + 2], pv[8 * j + 3]);
+          __nv_bfloat162 t2 = __floats2bfloat162_rn(pv[8 * j + 4], pv[8 * j + 5]);
+          __nv_bfloat162 t3 = __floats2bfloat162_rn(pv[8 * j + 6], pv[8 * j + 7]);
+          pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+          pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+          *reinterpret_cast<uint4*>(pblk + (((ch0 + j) ^ sw) << 4)) = pk;
+        }
+      }
+      sm100::fence_proxy_async();      // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&p_full[x]);
+      if (sk > 0) AF_STAMP(sk + 2);
+
+      // epilogue: O / rowsum -> bf16 rows staged in the (now dead) first block of P_X, stored by TMA; log-sum-exp
+      sm100::mbar_wait(&o_full[x], ph);
+      sm100::tc_fence_after();
+      if (sk > 0) AF_STAMP(sk + 3);
+      uint32_t o0[32], o1[32];
+      sm100::tmem_ld_32x32(trow, o0);
+      sm100::tmem_ld_32x32(trow + 32, o1);
+      sm100::tmem_ld_wait();
+      sm100::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) sm100::mbar_arrive(&s_free[x]);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(prow + (((uint32_t)j ^ sw) << 4)) = pk;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+        __nv_bfloat162 t1 = __floats2bfloat162_rn(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+        __nv_bfloat162 t3 = __floats2bfloat162_rn(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+        pk.x = *reinterpret_cast<uint32_t*>(&t0); pk.y = *reinterpret_cast<uint32_t*>(&t1);
+        pk.z = *reinterpret_cast<uint32_t*>(&t2); pk.w = *reinterpret_cast<uint32_t*>(&t3);
+        *reinterpret_cast<uint4*>(prow + (((uint32_t)(j + 4) ^ sw) << 4)) = pk;
+      }
+      if (q.lse) q.lse[(seq * p.heads + h) * 256 + x * 128 + r] = mx + __logf(sum);
+      sm100::fence_proxy_async();
+      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      if (gtid == 0) {
+        tma_store_4d(&tma_o, sPx, h * 64, x * 128, (int)(seq % p.n_inner), (int)(seq / p.n_inner));
+        atb_bulk_commit();
+      }
+      if (sk > 0) AF_STAMP(sk + 4);
+    }
+    if (gtid == 0) atb_bulk_wait_all();                // the stores have been written before the CTA exits
+  }
+  sm100::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    sm100::tc_fence_after();
+    sm100::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+static int atc_launch_fwd256(const vvae_attn_args& a, const AttnTcPlan& p, cudaStream_t s) {
+  constexpr int SMEM = 14 * 16384 + 256 + 1024;
+  CUtensorMap mq, mk, mv, mo;
+  int rc;
+  if ((rc = atc_make_map(&mq, a.q, a.q_rs, p, 256, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mk, a.k, a.k_rs, p, 256, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, 256, 1, 1))) return rc;
+  if ((rc = atc_make_map(&mo, a.o, a.o_rs, p, 128, 1, 1))) return rc;
+  AttnFwd256Params q;
+  q.pl = p;
+  q.lse = a.lse;
+  q.scale = a.scale;
+  q.units = (long long)p.n_outer * p.n_inner * p.heads;
+  q.dbg = ((g_dbg[10] & 16) ? 1 : 0) | ((g_dbg[10] & 32) ? 2 : 0);
+  q.dbg_cta = (int)g_dbg[0];
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load(std::memory_order_acquire)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd256_sm100_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention fwd (L=256): cudaFuncSetAttribute(%d): %s", SMEM, cudaGetErrorString(e));
+      return VVAE_ERR_CUDA;
+    }
+    attr_set.store(true, std::memory_order_release);
+  }
+  const int grid = (int)std::min<long long>(q.units, num_sms());
+  launch_pdl(attn_fwd256_sm100_kernel, dim3(grid), dim3(384), SMEM, s, mq, mk, mv, mo, q);
+  return check_launch("attn_fwd256_sm100");
+}
+
 int attn_tc_supported(const vvae_attn_args& a) {
   AttnTcPlan p;
   if (!atc_make_plan(a, p)) return 0;
@@ -1835,6 +2169,8 @@ int attn_tc_fwd(const vvae_attn_args& a, cudaStream_t s) {
   const bool m = a.mask != nullptr;
   if (p.G > 1) return m ? atc_launch_fwd<128, true, true>(a, p, s) : atc_launch_fwd<128, true, false>(a, p, s);
   if (p.NK == 128) return m ? atc_launch_fwd<128, false, true>(a, p, s) : atc_launch_fwd<128, false, false>(a, p, s);
+  // vvae_debug_set(18, 1): the one-tile-per-CTA kernel for unmasked L = 256 too
+  if (!m && !g_dbg[18]) return atc_launch_fwd256(a, p, s);
   return m ? atc_launch_fwd<256, false, true>(a, p, s) : atc_launch_fwd<256, false, false>(a, p, s);
 }
 
