@@ -67,7 +67,9 @@ int vvae_device_ok(void);
  * 15: conv3d fwd/dgrad: stream the filter taps with every stage (round-1 behaviour) instead of keeping the whole
  *     weight image resident in shared memory;
  * 16: attention backward, unmasked L = 256: the one-(sequence, head)-per-CTA kernel instead of the persistent one;
- * 17: tcgen05 GEMM: 1 = whole 256-column tiles in a partial last wave (no column slicing), 2 / 4 = force that many slices. */
+ * 17: tcgen05 GEMM: 1 = whole 256-column tiles in a partial last wave (no column slicing), 2 / 4 = force that many slices;
+ * 18: attention forward, unmasked L = 256: the one-tile-per-CTA kernel instead of the persistent one (key 10 bit 32 with
+ *     the persistent kernel: issue both score tiles at the start of a unit instead of the staggered pipeline). */
 int vvae_debug_set(int key, long long value);
 /* what = 0: counters of the last tcgen05 GEMM launched with vvae_debug_set(10, ... | 16): {clock64 ticks, globaltimer ns,
  * MMAs issued} of CTA 0's issuing thread (synchronises the device).
