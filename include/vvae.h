@@ -334,9 +334,12 @@ int vvae_sumsq_f32(const float* g, long long n, float* out1, vvae_stream_t strea
  * partials: caller scratch of vvae_sumsq_partials(n) floats. */
 int vvae_sumsq_partials(long long n);
 int vvae_sumsq_f32_det(const float* g, long long n, float* partials, float* out1, vvae_stream_t stream);
-/* Adam with bias correction on flat fp32 buffers; grad scaled by min(1, clip/ (sqrt(*gnorm_sq)+1e-6)) if gnorm_sq. */
-int vvae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                   int step, const float* gnorm_sq, float clip, float grad_scale, vvae_stream_t stream);
+/* Adam with bias correction on flat fp32 buffers; grad scaled by min(1, clip / sqrt(*gnorm_sq)) if gnorm_sq.
+ * shadow_bf16 (may be NULL): n bf16 values that receive the updated parameters rounded to nearest even -- the copy of the
+ * weights the bf16 kernels read, written in the same pass instead of by a vvae_cast over the whole buffer. */
+int vvae_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float b1,
+                   float b2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
+                   vvae_stream_t stream);
 
 #ifdef __cplusplus
 }

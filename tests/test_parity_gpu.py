@@ -895,9 +895,12 @@ def test_cuda_graph_rl_step_equals_eager_step(V):
         assert rel_err(gg, flat.grad) < 2e-3
 
 
-def test_fused_clip_adam_matches_optimizer_oracle(V):
+@pytest.mark.parametrize("shadow", [False, True])
+def test_fused_clip_adam_matches_optimizer_oracle(V, shadow):
     """ddp.FlatAdam (vvae_sumsq_f32 + vvae_adam_step on the flat fp32 buffers) against the oracle's
-    optax.chain(clip_by_global_norm(1.0), adam(schedule)) restatement, clip active and inactive, schedule-driven lr."""
+    optax.chain(clip_by_global_norm(1.0), adam(schedule)) restatement, clip active and inactive, schedule-driven lr.
+    With the bf16 parameter shadow the update kernel writes it in the same pass: it must equal the rounded parameters
+    bit for bit."""
     from oracle.optim import ClipAdam, warmup_cosine_decay_schedule
     from video_vae_b200.ddp import FlatAdam, FlatParams
 
@@ -912,6 +915,8 @@ def test_fused_clip_adam_matches_optimizer_oracle(V):
     toy = Toy().cuda()
     ref = [p.detach().cpu().clone() for p in toy.parameters()]
     flat = FlatParams(toy)
+    if shadow:
+        flat.enable_bf16_shadow()
     sched = warmup_cosine_decay_schedule(0.0, 1e-2, 3, 20, 1e-3)
     opt = FlatAdam(flat, lr=sched, clip=1.0)
     oracle = ClipAdam(ref, lr=sched, clip=1.0)
@@ -925,6 +930,38 @@ def test_fused_clip_adam_matches_optimizer_oracle(V):
         opt.step()
         for p, r in zip(toy.parameters(), ref):
             assert rel_err(p, r) < 1e-5, step
+        if shadow:
+            assert torch.equal(flat.shadow, flat.flat.to(torch.bfloat16)), step
+
+
+@pytest.mark.parametrize("n", [1001, 1004, 4 * 148 * 8 * 256 * 2 + 12])
+def test_adam_kernels_scalar_and_vector_agree(V, n):
+    """vvae_adam_step: the 16-byte kernel (n % 4 == 0) and the scalar kernel (any n) apply the same element update; both
+    against the formula in torch fp32, and the fused bf16 shadow against a cast of the result."""
+    from video_vae_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(n)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    gr = torch.randn(n, device="cuda", generator=g) * 3
+    m0 = torch.randn(n, device="cuda", generator=g) * 0.1
+    v0 = torch.rand(n, device="cuda", generator=g) * 0.1
+    gsq = (gr.double() ** 2).sum().float().reshape(1)
+    lr, b1, b2, eps, step, clip = 1e-2, 0.9, 0.999, 1e-8, 3, 1.0
+    p, m, v = p0.clone(), m0.clone(), v0.clone()
+    sh = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    ops.adam_step_(p, gr, m, v, lr, b1, b2, eps, step, gsq, clip, 1.0, shadow=sh)
+    scale = min(1.0, clip / float(gsq.sqrt()))
+    gs = gr * scale
+    m_ref = b1 * m0 + (1 - b1) * gs
+    v_ref = b2 * v0 + (1 - b2) * gs * gs
+    p_ref = p0 - lr * (m_ref / (1 - b1 ** step)) / ((v_ref / (1 - b2 ** step)).sqrt() + eps)
+    assert rel_err(m, m_ref) < 1e-6 and rel_err(v, v_ref) < 1e-6 and rel_err(p, p_ref) < 1e-6
+    assert torch.equal(sh, p.to(torch.bfloat16))
+    if n % 4 == 0:                       # the same data through the scalar kernel (misaligned by one element)
+        buf = [torch.empty(n + 1, device="cuda") for _ in range(4)]
+        for b, src in zip(buf, (p0, gr, m0, v0)):
+            b[1:].copy_(src)
+        ops.adam_step_(buf[0][1:], buf[1][1:], buf[2][1:], buf[3][1:], lr, b1, b2, eps, step, gsq, clip, 1.0)
+        assert torch.equal(buf[0][1:], p) and torch.equal(buf[2][1:], m) and torch.equal(buf[3][1:], v)
 
 
 def test_rl_model_variant_matches_oracle_fp32(V):

@@ -128,7 +128,7 @@ _SIGS = {
     "vvae_sumsq_f32": ([vp, ll, vp, vp], i32),
     "vvae_sumsq_partials": ([ll], i32),
     "vvae_sumsq_f32_det": ([vp, ll, vp, vp, vp], i32),
-    "vvae_adam_step": ([vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, vp, f32, f32, vp], i32),
+    "vvae_adam_step": ([vp, vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, vp, f32, f32, vp], i32),
 }
 
 EXPORTED = tuple(_SIGS) + ("vvae_last_error",)

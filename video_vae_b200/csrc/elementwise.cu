@@ -555,24 +555,69 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partials, int count
   acc = block_sum(acc, scratch);
   if (threadIdx.x == 0) *out += acc;
 }
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float bc1,
-                            float bc2, const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+// One Adam element (optax.scale_by_adam + scale(-lr) after clip_by_global_norm); every kernel below goes through it so
+// that the scalar and the vectorised paths are bit-identical.
+__device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, float scale, float lr, float b1, float b2,
+                                          float eps, float bc1, float bc2) {
+  const float gi = g * scale;
+  const float mi = b1 * m + (1.f - b1) * gi;
+  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  m = mi;
+  v = vi;
+  p -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  return p;
+}
+__device__ __forceinline__ float adam_clip_scale(const float* gnorm_sq, float clip, float grad_scale) {
   float scale = grad_scale;
   if (gnorm_sq) {
     float gn = sqrtf(*gnorm_sq) * grad_scale;
     if (gn > clip) scale *= clip / gn;  // optax.clip_by_global_norm
   }
+  return scale;
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, bf16* __restrict__ shadow, long long n, float lr, float b1, float b2,
+                            float eps, float bc1, float bc2, const float* __restrict__ gnorm_sq, float clip,
+                            float grad_scale) {
+  const float scale = adam_clip_scale(gnorm_sq, clip, grad_scale);
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    const float gi = g[i] * scale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    p[i] -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_one(pi, g[i], mi, vi, scale, lr, b1, b2, eps, bc1, bc2);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow) shadow[i] = __float2bfloat16(pi);
   }
+}
+// 16-byte version: four parameters per thread and pass, two passes in flight; streams 7 x 4 B (+ 2 B of bf16 shadow) per
+// parameter, so what matters is bytes in flight: 3 x 2 x 16 B of independent loads per thread before the first use.
+// The bf16 shadow (the copy of the weights the bf16 kernels read) is written here instead of by a separate cast pass
+// over the freshly written parameters.
+__global__ void __launch_bounds__(256)
+adam_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                 uint2* __restrict__ shadow, long long n4, float lr, float b1, float b2, float eps, float bc1, float bc2,
+                 const float* __restrict__ gnorm_sq, float clip, float grad_scale) {
+  const float scale = adam_clip_scale(gnorm_sq, clip, grad_scale);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  auto apply = [&](long long j, float4 pj, float4 gj, float4 mj, float4 vj) {
+    adam_one(pj.x, gj.x, mj.x, vj.x, scale, lr, b1, b2, eps, bc1, bc2);
+    adam_one(pj.y, gj.y, mj.y, vj.y, scale, lr, b1, b2, eps, bc1, bc2);
+    adam_one(pj.z, gj.z, mj.z, vj.z, scale, lr, b1, b2, eps, bc1, bc2);
+    adam_one(pj.w, gj.w, mj.w, vj.w, scale, lr, b1, b2, eps, bc1, bc2);
+    p[j] = pj; m[j] = mj; v[j] = vj;
+    if (shadow) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(pj.x, pj.y), hi = __floats2bfloat162_rn(pj.z, pj.w);
+      shadow[j] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  };
+  for (; i + stride < n4; i += 2 * stride) {
+    const long long j = i + stride;
+    const float4 g0 = g[i], g1 = g[j], p0 = p[i], p1 = p[j], m0 = m[i], m1 = m[j], v0 = v[i], v1 = v[j];
+    apply(i, p0, g0, m0, v0);
+    apply(j, p1, g1, m1, v1);
+  }
+  if (i < n4) apply(i, p[i], g[i], m[i], v[i]);
 }
 
 static inline int ew_blocks(long long n, int threads = 256) { return (int)std::min<long long>(cdiv(n, threads), (long long)num_sms() * 16); }
@@ -904,12 +949,24 @@ int vvae_sumsq_f32_det(const float* g, long long n, float* partials, float* out1
   return check_launch("sumsq_det");
 }
 
-int vvae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                   int step, const float* gnorm_sq, float clip, float grad_scale, vvae_stream_t stream) {
+int vvae_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr, float b1,
+                   float b2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
+                   vvae_stream_t stream) {
   if (n <= 0) return VVAE_OK;
   VVAE_REQUIRE(p && g && m && v && step >= 1, "adam_step: bad arguments");
   const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  adam_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2, gnorm_sq, clip, grad_scale);
+  cudaStream_t s = as_stream(stream);
+  const bool vec = n % 4 == 0 && (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16 == 0) &&
+                   ((uintptr_t)shadow_bf16 % 8 == 0);
+  if (vec) {
+    const long long n4 = n / 4;
+    const int blocks = (int)std::min<long long>(cdiv(n4, 512), (long long)num_sms() * 8);
+    adam_vec4_kernel<<<blocks, 256, 0, s>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)shadow_bf16, n4, lr,
+                                            b1, b2, eps, bc1, bc2, gnorm_sq, clip, grad_scale);
+  } else {
+    adam_kernel<<<ew_blocks(n), 256, 0, s>>>(p, g, m, v, (bf16*)shadow_bf16, n, lr, b1, b2, eps, bc1, bc2, gnorm_sq, clip,
+                                             grad_scale);
+  }
   return check_launch("adam_step");
 }
 

@@ -260,9 +260,10 @@ class FlatAdam:
         self.t += 1
         ops.fill_(self.gnorm_sq, 0.0)
         ops.sumsq_accum(self.flat.grad, self.gnorm_sq, self._partials)
+        # the bf16 shadow of the parameters (what the bf16 kernels read) is written by the same pass
         ops.adam_step_(self.flat.flat, self.flat.grad, self.m, self.v, float(lr), self.b1, self.b2,
-                       self.eps, self.t, self.gnorm_sq, self.clip, grad_scale)
+                       self.eps, self.t, self.gnorm_sq, self.clip, grad_scale, shadow=self.flat.shadow)
         if self.flat.shadow is not None:
-            self.flat.refresh_shadow()
+            F_.params_changed()
         else:
             F_.invalidate_shadows()

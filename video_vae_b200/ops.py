@@ -515,6 +515,9 @@ def sumsq_partials(n):
     return int(lib.vvae_sumsq_partials(int(n)))
 
 
-def adam_step_(p, g, m, v, lr, b1, b2, eps, step, gnorm_sq=None, clip=1.0, grad_scale=1.0):
-    check(lib.vvae_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, b1, b2, eps, step, ptr(gnorm_sq), clip,
-                             grad_scale, stream()), "vvae_adam_step")
+def adam_step_(p, g, m, v, lr, b1, b2, eps, step, gnorm_sq=None, clip=1.0, grad_scale=1.0, shadow=None):
+    """``shadow``: optional bf16 tensor of p's size that receives the updated parameters (same rounding as vvae_cast)."""
+    if shadow is not None:
+        assert shadow.dtype == torch.bfloat16 and shadow.numel() == p.numel() and shadow.is_contiguous()
+    check(lib.vvae_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), p.numel(), lr, b1, b2, eps, step, ptr(gnorm_sq),
+                             clip, grad_scale, stream()), "vvae_adam_step")
