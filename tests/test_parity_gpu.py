@@ -954,7 +954,7 @@ def test_adam_kernels_scalar_and_vector_agree(V, n):
     m_ref = b1 * m0 + (1 - b1) * gs
     v_ref = b2 * v0 + (1 - b2) * gs * gs
     p_ref = p0 - lr * (m_ref / (1 - b1 ** step)) / ((v_ref / (1 - b2 ** step)).sqrt() + eps)
-    assert rel_err(m, m_ref) < 1e-6 and rel_err(v, v_ref) < 1e-6 and rel_err(p, p_ref) < 1e-6
+    assert rel_err(m, m_ref) < 1e-6 and rel_err(v, v_ref) < 1e-6 and rel_err(p, p_ref) < 5e-6   # fp32, other operation order
     assert torch.equal(sh, p.to(torch.bfloat16))
     if n % 4 == 0:                       # the same data through the scalar kernel (misaligned by one element)
         buf = [torch.empty(n + 1, device="cuda") for _ in range(4)]

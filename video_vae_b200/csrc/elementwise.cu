@@ -559,12 +559,13 @@ __global__ void sumsq_final_kernel(const float* __restrict__ partials, int count
 // that the scalar and the vectorised paths are bit-identical.
 __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v, float scale, float lr, float b1, float b2,
                                           float eps, float bc1, float bc2) {
-  const float gi = g * scale;
-  const float mi = b1 * m + (1.f - b1) * gi;
-  const float vi = b2 * v + (1.f - b2) * gi * gi;
+  // explicit roundings: the compiler may not contract these differently in the scalar and the 16-byte kernel
+  const float gi = __fmul_rn(g, scale);
+  const float mi = __fmaf_rn(b1, m, __fmul_rn(1.f - b1, gi));
+  const float vi = __fmaf_rn(b2, v, __fmul_rn(__fmul_rn(1.f - b2, gi), gi));
   m = mi;
   v = vi;
-  p -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr, __fdiv_rn(mi, bc1)), __fadd_rn(__fsqrt_rn(__fdiv_rn(vi, bc2)), eps)));
   return p;
 }
 __device__ __forceinline__ float adam_clip_scale(const float* gnorm_sq, float clip, float grad_scale) {
