@@ -151,9 +151,11 @@ def main():
     ap.add_argument("--cfg", default="small", choices=sorted(CFGS))
     ap.add_argument("--dtype", default="float32", choices=["float32", "bfloat16"])
     ap.add_argument("--out", default=None)
-    ap.add_argument("--model", default="vae", choices=["vae", "rl"],
+    ap.add_argument("--model", default="vae", choices=["vae", "rl", "rl_dist"],
                     help="vae: train/model.py + the loss_fn of train/legacy/training_loop_adversarial.py; rl: "
-                         "train/rl_model.py + the loss_fn of train/rl_nonadversarial.py (writes *_rlvae_*.npz)")
+                         "train/rl_model.py + the loss_fn of train/rl_nonadversarial.py (writes *_rlvae_*.npz); rl_dist: the "
+                         "data-parallel trainer's copy claude_distributed/{rl_model,layers,unet}.py, which returns the "
+                         "VARIANCE (rl_model.py:55-60,147), under a closed-form loss (writes *_rldistvae_*.npz)")
     ap.add_argument("--shim", action="store_true",
                     help="no JAX here: run the reference's files on oracle/jaxshim (jax / flax.nnx look-alikes on CPU torch) "
                          "and write refshim_videovae_<cfg>_<dtype>.npz")
@@ -167,7 +169,7 @@ def main():
     if args.shim:
         sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
                                         "oracle", "jaxshim"))
-    sys.path.insert(0, os.path.join(args.reference, "train"))
+    sys.path.insert(0, os.path.join(args.reference, "claude_distributed" if args.model == "rl_dist" else "train"))
     import jax
     import jax.numpy as jnp
     from einops import rearrange, repeat
@@ -175,7 +177,9 @@ def main():
     if args.model == "vae":
         from model import VideoVAE                 # the reference's train/model.py
     else:
-        from rl_model import VideoVAE              # the reference's train/rl_model.py
+        from rl_model import VideoVAE              # the reference's train/rl_model.py (claude_distributed/ for rl_dist)
+        import rl_model as _rm
+        assert os.path.dirname(os.path.abspath(_rm.__file__)).endswith("claude_distributed" if args.model == "rl_dist" else "train")
 
     spec = CFGS[args.cfg]
     cfg, b, t = spec["cfg"], spec["batch"], spec["frames"]
@@ -216,10 +220,26 @@ def main():
     mask = rearrange(original_mask, "b time -> b 1 1 time")                                # train_step, :126-130
     mask = repeat(mask, "b 1 1 time -> b hw 1 1 time", hw=hw)
     mask = rearrange(mask, "b hw 1 1 time -> (b hw) 1 1 time")
+    if args.model == "rl_dist":       # claude_distributed/layers.py:213-214 expands the (b, 1, 1, t) mask itself
+        mask = rearrange(original_mask, "b time -> b 1 1 time")
 
-    rl = args.model == "rl"
-    hparams = RL_HPARAMS if rl else HPARAMS
-    if rl:
+    rl = args.model in ("rl", "rl_dist")
+    hparams = RL_HPARAMS if args.model == "rl" else HPARAMS
+    if args.model == "rl_dist":
+        # the trainer's loss is a closure inside distributed_train.py's main(); the model is what this fixture pins, under
+        # a closed-form loss that reaches every output (tests/test_jax_golden.py::dist_loss is the same in torch)
+        hparams = {}
+
+        def loss_fn(model, video, mask, rngs):
+            recon, compressed, selection, selection_mask, variance, mean = model(video, mask, rngs, train=True)
+            loss = (jnp.mean(jnp.square(recon - repeat(video, "b ... -> (b 2) ..."))) + 0.01 * jnp.mean(variance)
+                    + 0.01 * jnp.mean(jnp.square(mean)) + 0.1 * jnp.mean(selection))
+            return loss, {"reconstruction": recon}
+        grad_fn = nnx.value_and_grad(loss_fn, has_aux=True)
+        with DrawRecorder(weight_recipe.normal if args.compact else None) as rec:
+            (loss, aux), grads = grad_fn(model, video.astype(dtype), mask, nnx.Rngs(3))
+        recon = aux["reconstruction"]
+    elif rl:
         # the VGG term of rl_nonadversarial.py:125 is the caller's function (flaxmodels + downloaded weights in the
         # reference); a closed-form stand-in with the same signature keeps the gamma3 path and its gradient alive
         def perceptual(vgg_params, reconstruction, target):
@@ -285,8 +305,9 @@ def main():
             out["grad/" + name] = v.astype(np.float32)
     f32 = lambda x: np.asarray(x, np.float32)      # noqa: E731
     if rl:
-        out.update({"out/" + k: f32(aux[k]) for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density",
-                                                      "mean_trajectory_prob", "rl_loss", "per_sample_MAE")})
+        if args.model == "rl":
+            out.update({"out/" + k: f32(aux[k]) for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss",
+                                                          "kept_frame_density", "mean_trajectory_prob", "rl_loss", "per_sample_MAE")})
         out.update({"out/loss": f32(loss), "out/reconstruction": f32(recon), "out/compressed": f32(compressed),
                     "out/selection": f32(selection), "out/selection_mask": f32(selection_mask), "out/logvar": f32(logvar),
                     "out/mean": f32(mean)})
@@ -308,7 +329,7 @@ def main():
     out["generator"] = np.asarray(("reference files on oracle/jaxshim (CPU torch), jax " if shim else "reference files on jax ")
                                   + jax.__version__)
     prefix = "refshim" if shim else "jax"
-    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{prefix}_{'rlvae' if rl else 'videovae'}_{args.cfg}_{args.dtype}.npz")
+    path = args.out or os.path.join(os.path.dirname(os.path.abspath(__file__)), f"{prefix}_{ {'vae': 'videovae', 'rl': 'rlvae', 'rl_dist': 'rldistvae'}[args.model] }_{args.cfg}_{args.dtype}.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes; loss =", float(loss), "; jax", jax.__version__)
 

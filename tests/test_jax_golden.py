@@ -30,6 +30,7 @@ import weight_recipe  # noqa: E402
 
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_videovae_*.npz")))
 RL_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rlvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rlvae_*.npz")))
+DIST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rldistvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rldistvae_*.npz")))
 NO_FIXTURE = "parity unpinned: no tests/golden/{jax,refshim}_videovae_*.npz (tests/golden/make_golden_jax.py [--shim])"
 
 
@@ -135,6 +136,76 @@ def check_rl_against_fixture(fx, loss, aux, m, tol, grad_tol):
     assert any("selection_layer" in n for n, r in fx["grads"].items() if r["max"] > 0.0)      # the RL term's gradient is there
     report.update(grads_checked=checked, worst_grad=worst)
     print("rl fixture parity:", report)
+    return report
+
+
+def dist_loss(video, reconstruction, selection, variance, mean):
+    """The closed-form loss make_golden_jax.py --model rl_dist differentiates (the trainer's own loss is a closure inside
+    claude_distributed/distributed_train.py's main(); this fixture pins the MODEL copy of claude_distributed/)."""
+    v2 = video.repeat_interleave(2, dim=0).to(reconstruction.dtype)
+    return (((reconstruction - v2) ** 2).mean() + 0.01 * variance.float().mean() + 0.01 * (mean.float() ** 2).mean()
+            + 0.1 * selection.float().mean())
+
+
+def run_impl_dist(fx, impl, dtype):
+    """claude_distributed/rl_model.py (returns the variance) with the fixture's weights and draws."""
+    from video_vae_b200 import checkpoint as ck
+    cfg = fx["cfg"]
+    hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
+    u = fx["gumbel_u"]
+    if impl == "oracle":
+        from oracle import Rngs
+        from oracle.distributed_rl_model import VideoVAE
+        from oracle.losses import expand_mask
+        m = VideoVAE(*cfg, Rngs(0), dtype=dtype)
+        ck.load_flax_tree(m, fx["params"], strict=True)
+        video = fx["video"]
+        outs = m(video, expand_mask(fx["mask"], hw), Rngs(0), train=True, noise=fx["noise"], bernoulli_u=u)
+    else:
+        import video_vae_b200 as V
+        from video_vae_b200.distributed_rl_model import VideoVAE
+        m = VideoVAE(*cfg, V.Rngs(0), dtype=dtype)
+        ck.load_flax_tree(m, fx["params"], strict=True)
+        video = fx["video"].cuda()
+        outs = m(video, fx["mask"][:, None, None, :].cuda(), V.Rngs(0), train=True, noise=fx["noise"].cuda(), bernoulli_u=u.cuda())
+    reconstruction, compressed, selection, selection_mask, variance, mean = outs
+    loss = dist_loss(video, reconstruction, selection, variance, mean)
+    loss.backward()
+    return loss, dict(reconstruction=reconstruction, compressed=compressed, selection=selection,
+                      selection_mask=selection_mask, variance=variance, mean=mean), m
+
+
+def check_dist_against_fixture(fx, loss, aux, m, tol, grad_tol):
+    out = fx["out"]
+    f = lambda v: v.detach().float().cpu()                     # noqa: E731
+    assert np.array_equal(f(aux["selection_mask"]).numpy().reshape(-1), out["selection_mask"].reshape(-1))
+    st, lat = fx.get("recon_stride", 1), fx.get("latent_stride", 1)
+    report = {"selection": rel_err(f(aux["selection"]).reshape(-1), out["selection"].reshape(-1)),
+              "reconstruction": rel_err(f(aux["reconstruction"])[:, :, ::st, ::st, :], out["reconstruction"]),
+              # the fixture stores the 5th output of VideoVAE.__call__ under the key "logvar": here it IS the variance
+              "variance": rel_err(f(aux["variance"])[:, :, ::lat, :], out["logvar"]),
+              "mean": rel_err(f(aux["mean"])[:, :, ::lat, :], out["mean"]),
+              "compressed": rel_err(f(aux["compressed"])[:, :, ::lat, :], out["compressed"]),
+              "loss": abs(float(loss) - float(out["loss"])) / abs(float(out["loss"]))}
+    assert float(out["logvar"].min()) > 0.0                   # a variance, not its logarithm
+    for k, v in report.items():
+        assert v < tol, (k, v)
+    named = dict(m.named_parameters())
+    checked, worst = 0, (0.0, None)
+    for name, ref in fx["grads"].items():
+        if ref["max"] == 0.0:
+            continue
+        got = named[name].grad.detach().float().cpu().numpy()
+        gn = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+        e_norm = abs(gn - ref["norm"]) / ref["norm"]
+        d_probe = np.abs(weight_recipe.grad_probe(got) - ref["probe"]) / ref["max"]
+        assert e_norm < grad_tol, (name, e_norm)
+        assert float((d_probe < 5 * grad_tol).mean()) >= 0.94 and float(d_probe.max()) < 2e-2, (name, float(d_probe.max()))
+        worst = max(worst, (max(e_norm, float(d_probe.max())), name))
+        checked += 1
+    assert checked >= 50
+    report.update(grads_checked=checked, worst_grad=worst)
+    print("rl_dist fixture parity:", report)
     return report
 
 
@@ -290,6 +361,27 @@ def test_cuda_path_reproduces_reference_rl_outputs(path):
     fx = load_fixture(path)
     loss, aux, m = run_impl_rl(fx, "cuda", torch.float32)
     check_rl_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
+
+
+@pytest.mark.skipif(not DIST_FIXTURES, reason=NO_FIXTURE)
+@pytest.mark.parametrize("path", DIST_FIXTURES or [None])
+def test_oracle_reproduces_reference_distributed_model_outputs(path):
+    """claude_distributed/{rl_model,layers,unet}.py (the data-parallel trainer's copies: variance instead of log-variance,
+    the mask expanded inside FactoredAttention) executed by make_golden_jax.py --model rl_dist, against
+    oracle/distributed_rl_model.py."""
+    fx = load_fixture(path)
+    assert fx["model"] == "rl_dist" and fx["dtype"] == "float32"
+    loss, aux, m = run_impl_dist(fx, "oracle", torch.float32)
+    check_dist_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not DIST_FIXTURES, reason=NO_FIXTURE)
+@pytest.mark.parametrize("path", DIST_FIXTURES or [None])
+def test_cuda_path_reproduces_reference_distributed_model_outputs(path):
+    fx = load_fixture(path)
+    loss, aux, m = run_impl_dist(fx, "cuda", torch.float32)
+    check_dist_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
 
 
 # ------------------------------------------------------------------------------------------------ consumer self-check

@@ -151,9 +151,9 @@ def test_reference_attention_mask_script_passes_on_the_shim():
 
 
 @needs_reference
-@pytest.mark.parametrize("model,cfg", [("vae", "small"), ("rl", "small")])
+@pytest.mark.parametrize("model,cfg", [("vae", "small"), ("rl", "small"), ("rl_dist", "small")])
 def test_committed_refshim_fixture_is_what_the_generator_writes(tmp_path, model, cfg):
-    name = f"refshim_{'rlvae' if model == 'rl' else 'videovae'}_{cfg}_float32.npz"
+    name = f"refshim_{ {'vae': 'videovae', 'rl': 'rlvae', 'rl_dist': 'rldistvae'}[model] }_{cfg}_float32.npz"
     out = str(tmp_path / name)
     subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden_jax.py"), "--shim", "--cfg", cfg,
                     "--model", model, "--out", out], check=True, capture_output=True, timeout=600, cwd=ROOT)
