@@ -1288,14 +1288,14 @@ attn_bwd_long_sm100_kernel(const __grid_constant__ CUtensorMap tma_q, const __gr
 }
 
 template <typename K>
-static int atl_set_smem(K kern, int bytes, bool* done) {
-  if (*done) return VVAE_OK;
+static int atl_set_smem(K kern, int bytes, std::atomic<bool>* done) {
+  if (done->load(std::memory_order_acquire)) return VVAE_OK;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) {
     set_error("attention (long): cudaFuncSetAttribute(%d): %s", bytes, cudaGetErrorString(e));
     return VVAE_ERR_CUDA;
   }
-  *done = true;
+  done->store(true, std::memory_order_release);
   return VVAE_OK;
 }
 
@@ -1317,7 +1317,7 @@ static int atl_launch_fwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
   if ((rc = atc_make_map(&mv, a.v, a.v_rs, p, 128, 1, 1))) return rc;
   AttnLongParams q;
   atl_fill_params(a, p, q);
-  static bool set_m = false, set_u = false;
+  static std::atomic<bool> set_m{false}, set_u{false};
   dim3 grid((unsigned)((long long)p.n_outer * p.n_inner * p.nqb), (unsigned)p.heads);
   if (a.mask) {
     if ((rc = atl_set_smem(attn_fwd_long_sm100_kernel<true>, 227 * 1024, &set_m))) return rc;
@@ -1346,7 +1346,7 @@ static int atl_launch_bwd(const vvae_attn_args& a, const AttnTcPlan& p, cudaStre
     attn_delta_kernel<<<blocks, 256, 0, s>>>((const bf16*)a.o, a.o_rs, (const bf16*)a.d_o, a.do_rs, a.delta, p, total);
     if ((rc = check_launch("attn_delta"))) return rc;
   }
-  static bool set[4] = {false, false, false, false};
+  static std::atomic<bool> set[4] = {{false}, {false}, {false}, {false}};
   dim3 grid((unsigned)(n_seq * p.nqb), (unsigned)p.heads);
   if (a.mask) {
     if ((rc = atl_set_smem(attn_bwd_long_sm100_kernel<false, true>, 227 * 1024, &set[0]))) return rc;
