@@ -341,6 +341,26 @@ int vvae_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
                    float b2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
                    vvae_stream_t stream);
 
+/* ---- gradient exchange of the data-parallel step ----
+ * The reference's all-reduce is implicit in its jitted SPMD step (claude_distributed/distributed_train.py:107-109,
+ * 378-380,412) and its start-up replication is broadcast_one_to_all (:339).  These calls give a host without
+ * torch.distributed the same two collectives over the flat gradient / parameter buffers.  They wrap NCCL, resolved with
+ * dlopen at the first call (VVAE_ERR_UNSUPPORTED if libnccl.so.2 cannot be loaded); one communicator per process / GPU.
+ * vvae_comm_init is a collective over all `world` ranks and binds the calling thread's current device; it is the one
+ * entry point of this library that blocks.  The Python package itself uses torch.distributed (ddp.py); ddp.NativeComm
+ * wraps these calls. */
+typedef struct vvae_comm* vvae_comm_t;
+/* rank 0: fill the 128-byte rendezvous token; the host carries it to every other rank */
+int vvae_comm_unique_id(void* id128);
+int vvae_comm_init(vvae_comm_t* comm, const void* id128, int rank, int world);
+int vvae_comm_rank(vvae_comm_t comm, int* rank, int* world);
+/* in place over `count` elements of `dtype` (VVAE_F32 / VVAE_BF16): sum, or mean over the ranks if average != 0
+ * (the reference's loss is a mean over the GLOBAL batch => mean of the per-rank gradients) */
+int vvae_comm_allreduce(vvae_comm_t comm, void* buf, long long count, int dtype, int average, vvae_stream_t stream);
+/* in place: every rank's buf becomes root's */
+int vvae_comm_broadcast(vvae_comm_t comm, void* buf, long long count, int dtype, int root, vvae_stream_t stream);
+int vvae_comm_destroy(vvae_comm_t comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,3 +94,48 @@ def test_integration_md_names_exist():
     import video_vae_b200 as V
     for n in ("VideoVAE", "Rngs", "loss_fn", "DEFAULT_HPARAMS"):       # the top-level names the guide's snippet imports
         assert hasattr(V, n)
+
+
+# ---------------------------------------------------------------------------------------------- vvae_comm_* (csrc/comm.cu)
+def test_comm_token_and_argument_checks_without_gpu():
+    """The gradient-exchange entry points: NCCL resolves through dlopen (no link-time dependency), rank
+    0's rendezvous token can be made on the host, and every call that would touch a device or a bogus handle fails with a
+    status and a message instead of crashing."""
+    from video_vae_b200 import _ffi
+    lib = _ffi.lib
+    tok = (ctypes.c_char * 128)()
+    assert lib.vvae_comm_unique_id(ctypes.cast(tok, ctypes.c_void_p)) == 0, lib.vvae_last_error()
+    tok2 = (ctypes.c_char * 128)()
+    assert lib.vvae_comm_unique_id(ctypes.cast(tok2, ctypes.c_void_p)) == 0
+    assert bytes(tok) != bytes(128) and bytes(tok) != bytes(tok2)          # a real, fresh token each time
+    assert lib.vvae_comm_unique_id(None) == 1                              # VVAE_ERR_INVALID
+    h = ctypes.c_void_p()
+    assert lib.vvae_comm_init(ctypes.byref(h), ctypes.cast(tok, ctypes.c_void_p), 2, 2) == 1
+    assert b"rank 2 of 2" in lib.vvae_last_error()
+    if not torch.cuda.is_available():
+        assert lib.vvae_comm_init(ctypes.byref(h), ctypes.cast(tok, ctypes.c_void_p), 0, 1) == 2   # VVAE_ERR_CUDA
+        assert h.value is None
+    assert lib.vvae_comm_allreduce(None, None, 0, 0, 1, None) == 1
+    assert lib.vvae_comm_broadcast(None, None, 0, 0, 0, None) == 1
+    assert b"not a communicator" in lib.vvae_last_error()
+    assert lib.vvae_comm_destroy(None) == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_native_comm_refuses_without_gpu_and_file_exchange(tmp_path):
+    import threading
+    from video_vae_b200 import _ffi, ddp
+    with pytest.raises(_ffi.VvaeError):
+        ddp.NativeComm(0, 1)
+    # the token transport of NativeComm.from_env: rank 0 writes atomically, the others poll
+    path = str(tmp_path / "token")
+    token = bytes(range(128))
+    got = {}
+    t = threading.Thread(target=lambda: got.setdefault("r1", ddp.NativeComm.file_exchange(path, 10.0)(None)))
+    t.start()
+    assert ddp.NativeComm.file_exchange(path)(token) == token
+    t.join(20)
+    assert got["r1"] == token
+    with pytest.raises(TimeoutError):
+        ddp.NativeComm.file_exchange(str(tmp_path / "absent"), 0.2)(None)
+

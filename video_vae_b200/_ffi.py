@@ -129,6 +129,13 @@ _SIGS = {
     "vvae_sumsq_partials": ([ll], i32),
     "vvae_sumsq_f32_det": ([vp, ll, vp, vp, vp], i32),
     "vvae_adam_step": ([vp, vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, vp, f32, f32, vp], i32),
+    # gradient exchange behind the C ABI (NCCL resolved with dlopen; ddp.NativeComm)
+    "vvae_comm_unique_id": ([vp], i32),
+    "vvae_comm_init": ([C.POINTER(vp), vp, i32, i32], i32),
+    "vvae_comm_rank": ([vp, C.POINTER(i32), C.POINTER(i32)], i32),
+    "vvae_comm_allreduce": ([vp, vp, ll, i32, i32, vp], i32),
+    "vvae_comm_broadcast": ([vp, vp, ll, i32, i32, vp], i32),
+    "vvae_comm_destroy": ([vp], i32),
 }
 
 EXPORTED = tuple(_SIGS) + ("vvae_last_error",)

@@ -31,6 +31,105 @@ def shard_batch(x, rank=None, world=None):
     return x[rank * per:(rank + 1) * per]
 
 
+class NativeComm:
+    """The C ABI's own communicator (``vvae_comm_*``, csrc/comm.cu: NCCL resolved with dlopen) for hosts without
+    torch.distributed -- what the jax.ffi binding of INTEGRATION.md would drive.  One per process / GPU.
+
+    ``exchange`` carries rank 0's 128-byte rendezvous token to every rank: a callable ``bytes | None -> bytes`` (rank 0
+    passes the token, the others pass None and receive it).  With torch.distributed initialised the default exchange is
+    ``broadcast_object_list`` (any backend: the token is host data); ``from_env`` transports it through a file.
+    The package's own training path keeps using torch.distributed (``FlatParams.all_reduce_grads``); pass ``comm=`` there
+    to route the same collective through this class instead."""
+
+    TOKEN_BYTES = 128
+
+    def __init__(self, rank, world, exchange=None):
+        import ctypes as C
+        from . import _ffi
+        self._ffi, self._C = _ffi, C
+        self.rank, self.world, self._h = int(rank), int(world), None
+        _ffi.require_device()                                    # no CPU path: fail before any rank blocks in the rendezvous
+        token = None
+        if self.rank == 0:
+            buf = (C.c_char * self.TOKEN_BYTES)()
+            self._check(_ffi.lib.vvae_comm_unique_id(C.cast(buf, C.c_void_p)), "vvae_comm_unique_id")
+            token = bytes(buf)
+        if self.world > 1:
+            token = (exchange or self._torch_exchange)(token)
+        if not isinstance(token, (bytes, bytearray)) or len(token) != self.TOKEN_BYTES:
+            raise ValueError("NativeComm: the exchange must return rank 0's 128-byte token on every rank")
+        buf = (C.c_char * self.TOKEN_BYTES).from_buffer_copy(bytes(token))
+        h = C.c_void_p()
+        self._check(_ffi.lib.vvae_comm_init(C.byref(h), C.cast(buf, C.c_void_p), self.rank, self.world), "vvae_comm_init")
+        self._h = h
+
+    def _check(self, rc, what):          # not _ffi.check: collectives are not counted as kernel launches of this library
+        if rc != 0:
+            raise self._ffi.VvaeError(f"{what} failed (status {rc}): {self._ffi.lib.vvae_last_error().decode()}")
+
+    @staticmethod
+    def _torch_exchange(token):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NativeComm: pass exchange= (no torch.distributed process group to carry the token)")
+        box = [token]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    @classmethod
+    def file_exchange(cls, path, timeout_s=300.0):
+        """A token exchange through the file ``path`` on a filesystem all ranks see: rank 0 writes it atomically, the
+        others poll for it.  Use a fresh path per job (a stale file of an earlier job would be picked up)."""
+        import os
+        import time
+
+        def exchange(token):
+            if token is not None:
+                with open(path + ".tmp", "wb") as f:
+                    f.write(token)
+                os.replace(path + ".tmp", path)
+                return token
+            t0 = time.monotonic()
+            while not (os.path.exists(path) and os.path.getsize(path) == cls.TOKEN_BYTES):
+                if time.monotonic() - t0 > timeout_s:
+                    raise TimeoutError(f"NativeComm: no token at {path} after {timeout_s} s")
+                time.sleep(0.05)
+            with open(path, "rb") as f:
+                return f.read()
+        return exchange
+
+    @classmethod
+    def from_env(cls, path, timeout_s=300.0):
+        """RANK / WORLD_SIZE from the environment (torchrun's names), token through ``file_exchange(path)``."""
+        import os
+        return cls(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), cls.file_exchange(path, timeout_s))
+
+    def _call(self, what, fn, t, *mid):
+        if self._h is None:
+            raise RuntimeError("NativeComm: used after close()")
+        if not (t.is_cuda and t.is_contiguous()):
+            raise ValueError("NativeComm: contiguous CUDA tensors only")
+        f = self._ffi
+        self._check(fn(self._h, f.ptr(t), t.numel(), f.dt(t), *mid, f.stream()), what)
+
+    def all_reduce(self, t, average=False):
+        """In place on the current stream: sum (or mean) over the ranks."""
+        self._call("vvae_comm_allreduce", self._ffi.lib.vvae_comm_allreduce, t, 1 if average else 0)
+
+    def broadcast(self, t, src=0):
+        self._call("vvae_comm_broadcast", self._ffi.lib.vvae_comm_broadcast, t, int(src))
+
+    def close(self):
+        if self._h is not None:
+            h, self._h = self._h, None
+            self._check(self._ffi.lib.vvae_comm_destroy(h), "vvae_comm_destroy")
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:          # interpreter shutdown: the library may already be gone
+            pass
+
+
 class FlatParams:
     """Re-homes every parameter (and its gradient) of ``model`` into one contiguous fp32 buffer each."""
 
@@ -55,9 +154,15 @@ class FlatParams:
         self._shadow_views = {}
         F_.invalidate_shadows()
 
-    def broadcast(self, src=0, group=None):
+    def broadcast(self, src=0, group=None, comm=None):
         """Replicate rank ``src``'s parameters on every rank (the reference loads on process 0 and calls
-        ``broadcast_one_to_all``, claude_distributed/distributed_train.py:312-341): one collective on the flat buffer."""
+        ``broadcast_one_to_all``, claude_distributed/distributed_train.py:312-341): one collective on the flat buffer.
+        ``comm``: a NativeComm to use instead of torch.distributed."""
+        if comm is not None:
+            if comm.world > 1:
+                comm.broadcast(self.flat, src)
+                self.refresh_shadow()
+            return
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.broadcast(self.flat, src=src, group=group)
             if self.shadow is not None:
@@ -65,11 +170,24 @@ class FlatParams:
             else:
                 F_.params_changed()
 
-    def all_reduce_grads(self, comm_dtype=torch.float32, group=None):
+    def all_reduce_grads(self, comm_dtype=torch.float32, group=None, comm=None):
         """Sum the flat gradient over the ranks with ONE collective (the graph-mode exchange step: the reference's XLA
         SPMD all-reduce of claude_distributed/distributed_train.py:378-380).  ``comm_dtype=torch.bfloat16`` sends a bf16
         copy (341 MB instead of 682 MB at production size): one cast kernel each way, the sum itself runs in NCCL; the
-        fp32 buffer then holds the bf16-rounded sum -- every rank the SAME values, so replicas stay bit-identical."""
+        fp32 buffer then holds the bf16-rounded sum -- every rank the SAME values, so replicas stay bit-identical.
+        ``comm``: a NativeComm to use instead of torch.distributed (``vvae_comm_allreduce`` on the current stream)."""
+        if comm is not None:
+            if comm.world == 1:
+                return
+            if comm_dtype == torch.float32:
+                comm.all_reduce(self.grad)
+                return
+            if getattr(self, "_grad_lowp", None) is None or self._grad_lowp.dtype != comm_dtype:
+                self._grad_lowp = torch.empty(self.total, dtype=comm_dtype, device=self.grad.device)
+            ops.cast_into(self.grad, self._grad_lowp)
+            comm.all_reduce(self._grad_lowp)
+            ops.cast_into(self._grad_lowp, self.grad)
+            return
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         if comm_dtype == torch.float32 or not self.grad.is_cuda:
