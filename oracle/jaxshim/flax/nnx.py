@@ -128,7 +128,22 @@ class State:
 
 
 def state(module, *filters):
+    if isinstance(module, State):           # nnx.state(grads): a State is its own state
+        return module
     return State({p: v.value.detach() for p, v in iter_variables(module, *filters)})
+
+
+def split(module, *filters):
+    """nnx.split -> (graphdef, state).  The shim's graphdef is the module object itself: merge() writes the state back
+    into it, which is all the reference's scripts do with the pair (device_put the state, merge, call)."""
+    return module, state(module, *filters)
+
+
+def merge(graphdef, st, *more):
+    update(graphdef, st)
+    for m in more:
+        update(graphdef, m)
+    return graphdef
 
 
 def _flatten_pure(d, path, out):

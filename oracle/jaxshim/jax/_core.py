@@ -22,8 +22,24 @@ class _At:
         return out
 
 
+class _Size(int):
+    """jax's ``x.size`` is the element count (an int); torch's is a method.  This is both: an int that can be called."""
+
+    def __new__(cls, t):
+        obj = int.__new__(cls, t.numel())
+        obj._t = t
+        return obj
+
+    def __call__(self, *a, **k):
+        return torch.Tensor.size(self._t, *a, **k)
+
+
 class Array(torch.Tensor):
     """jax.Array look-alike.  torch's default __torch_function__ keeps the subclass through every op."""
+
+    @property
+    def size(self):
+        return _Size(self)
 
     def astype(self, dtype):
         return self.to(to_dtype(dtype))

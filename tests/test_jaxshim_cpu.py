@@ -150,6 +150,32 @@ def test_reference_attention_mask_script_passes_on_the_shim():
     assert "17, 15, 19, 13" in out and "17, 10, 19, 13" in out            # the two shapes it prints
 
 
+RUN_REFERENCE_SCRIPT = ("import sys, runpy; sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2]); "
+                        "runpy.run_path(sys.argv[3], run_name='__main__')")
+
+
+@needs_reference
+def test_reference_model_test_script_passes_on_the_shim():
+    """claude_distributed/test_rl_model.py, unmodified (its nine checks of the data-parallel trainer's model copy: encoder /
+    decoder / full-model shapes on a ('data',) mesh, parameter count, finite non-zero gradients through nnx.value_and_grad,
+    straight-through gradients and a binary Gumbel gate, FactoredAttention / PatchEmbedding / PatchUnEmbedding / UNet
+    shapes).  The mesh has one device here, where replicated and batch-sharded placements are the arrays themselves."""
+    d = os.path.join(REFERENCE, "claude_distributed")
+    out = run_py(RUN_REFERENCE_SCRIPT, SHIM, d, os.path.join(d, "test_rl_model.py"))
+    assert "MODEL TESTS: 9 passed, 0 failed" in out and "ALL MODEL TESTS PASSED" in out, out[-1500:]
+    assert "FAIL" not in out
+
+
+@needs_reference
+def test_reference_human_test_script_runs_on_the_shim():
+    """train/human_tests.py, unmodified: a 256x256, depth 6 + 6 VideoVAE forward in the default bf16 with a frame mask in
+    the ((b hw), 1, 1, t) convention; the script prints the three shapes and exits (everything after is dead code there)."""
+    d = os.path.join(REFERENCE, "train")
+    out = run_py(RUN_REFERENCE_SCRIPT, SHIM, d, os.path.join(d, "human_tests.py"))
+    assert out.strip().splitlines()[-1].replace("torch.Size", "").replace("(", "").replace(")", "") == \
+        "[3, 11, 256, 256, 3] [3, 11, 256, 256, 3] [3, 11, 1, 1]"
+
+
 @needs_reference
 @pytest.mark.parametrize("model,cfg", [("vae", "small"), ("rl", "small"), ("rl_dist", "small")])
 def test_committed_refshim_fixture_is_what_the_generator_writes(tmp_path, model, cfg):
