@@ -130,6 +130,12 @@ class State:
 def state(module, *filters):
     if isinstance(module, State):           # nnx.state(grads): a State is its own state
         return module
+    if isinstance(module, Optimizer):
+        flat = {("step",): torch.tensor(module.step, dtype=torch.int32)}
+        _opt_state_flat(module.opt_state, ("opt_state",), flat)
+        for p, v in iter_variables(module.model, *filters):
+            flat[("model",) + p] = v.value.detach()
+        return State(flat)
     return State({p: v.value.detach() for p, v in iter_variables(module, *filters)})
 
 
@@ -207,6 +213,39 @@ def jit(fn=None, **kw):
     if fn is None:
         return lambda f: f
     return fn
+
+
+class Optimizer(Module):
+    """nnx.Optimizer(model, tx): ``update(grads)`` (flax 0.10, what the reference calls: train/rl_nonadversarial.py:196) or
+    ``update(model, grads)`` (flax 0.11+).  ``nnx.state(optimizer)`` = {"step", "opt_state": nested tuples by index} next to
+    the model's own variables under "model", the nesting a checkpoint of the reference has."""
+
+    def __init__(self, model, tx, wrt=Param):
+        self.model, self.tx, self.wrt = model, tx, wrt
+        self.step = 0
+        self.opt_state = tx.init(state(model, wrt))
+
+    def update(self, *args, **kwargs):
+        grads = args[-1] if args else kwargs["grads"]
+        params = state(self.model, self.wrt)
+        updates, self.opt_state = self.tx.update(grads, self.opt_state, params)
+        new = {p: (params.flat[p] + u).to(params.flat[p].dtype) for p, u in updates.flat.items()}
+        update(self.model, State(new))
+        self.step += 1
+
+
+def _opt_state_flat(node, path, out):
+    if isinstance(node, State):
+        for p, v in node.flat.items():
+            out[path + p] = v
+    elif isinstance(node, tuple) and hasattr(node, "_fields"):
+        for name in node._fields:
+            _opt_state_flat(getattr(node, name), path + (name,), out)
+    elif isinstance(node, (tuple, list)):
+        for i, v in enumerate(node):
+            _opt_state_flat(v, path + (i,), out)
+    elif isinstance(node, torch.Tensor):
+        out[path] = node
 
 
 # ------------------------------------------------------------------------------------------------ rngs

@@ -34,6 +34,11 @@ class _Size(int):
         return torch.Tensor.size(self._t, *a, **k)
 
 
+class _Shard:
+    def __init__(self, device, data):
+        self.device, self.data, self.index = device, data, (slice(None),) * data.dim()
+
+
 class Array(torch.Tensor):
     """jax.Array look-alike.  torch's default __torch_function__ keeps the subclass through every op."""
 
@@ -60,6 +65,12 @@ class Array(torch.Tensor):
 
     def block_until_ready(self):
         return self
+
+    @property
+    def addressable_shards(self):
+        """One host device: the array is its own single shard."""
+        import jax
+        return [_Shard(jax.devices()[0], self)]
 
 
 _DTYPES = {bool: torch.bool, int: torch.int32, float: torch.float32, "float32": torch.float32,

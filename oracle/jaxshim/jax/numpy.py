@@ -29,7 +29,7 @@ def _a(x):
 
 
 def arange(*args, dtype=None):
-    floaty = any(isinstance(v, float) for v in args)
+    floaty = builtins.any(isinstance(v, float) for v in args)
     dt = to_dtype(dtype) or (torch.float32 if floaty else torch.int32)
     return torch.arange(*args, dtype=dt).as_subclass(Array)
 
@@ -125,6 +125,16 @@ def max(x, axis=None, keepdims=False):
 def min(x, axis=None, keepdims=False):
     x = _a(x)
     return x.amin(**_axis_kw(axis, keepdims)) if axis is not None else x.min()
+
+
+def any(x, axis=None, keepdims=False):        # noqa: A001  (jnp.any; this module reaches the builtin as builtins.any)
+    x = _a(x).bool()
+    return x.any(**_axis_kw(axis, keepdims)) if axis is not None else x.any()
+
+
+def all(x, axis=None, keepdims=False):        # noqa: A001
+    x = _a(x).bool()
+    return x.all(**_axis_kw(axis, keepdims)) if axis is not None else x.all()
 
 
 def var(x, axis=None, keepdims=False):

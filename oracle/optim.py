@@ -15,7 +15,10 @@ offline, so its published algorithms are restated here [optax-recall]:
 * warmup_cosine_decay_schedule = join_schedules([linear 0 -> peak over warmup_steps,
   cosine_decay(peak, decay_steps - warmup_steps, alpha = end / peak)], [warmup_steps]).
 
-Parity unpinned against optax itself; pinned against torch.optim.Adam + clip_grad_norm_ (tests/test_oracle.py).
+Parity unpinned against optax itself; pinned against torch.optim.Adam + clip_grad_norm_ (tests/test_oracle.py), against a
+second restatement that keeps optax's own structure (oracle/jaxshim/optax.py, tests/test_jaxshim_cpu.py) and against the
+reference's own train_step + optimizer construction run on that look-alike for six updates
+(tests/golden/refshim_rltrain_small_float32.npz, tests/test_jax_golden.py).
 """
 import math
 

@@ -31,6 +31,7 @@ import weight_recipe  # noqa: E402
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_videovae_*.npz")))
 RL_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rlvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rlvae_*.npz")))
 DIST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rldistvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rldistvae_*.npz")))
+TRAIN_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rltrain_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rltrain_*.npz")))
 NO_FIXTURE = "parity unpinned: no tests/golden/{jax,refshim}_videovae_*.npz (tests/golden/make_golden_jax.py [--shim])"
 
 
@@ -382,6 +383,134 @@ def test_cuda_path_reproduces_reference_distributed_model_outputs(path):
     fx = load_fixture(path)
     loss, aux, m = run_impl_dist(fx, "cuda", torch.float32)
     check_dist_against_fixture(fx, loss, aux, m, 1e-4, 1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ training trajectory
+def load_train_fixture(path):
+    z = np.load(path)
+    assert str(z["model"]) == "rl_train" and str(z["recipe"]) == weight_recipe.RECIPE_ID
+    names = [k[len("step0/pnorm/"):] for k in z.files if k.startswith("step0/pnorm/")]
+    return z, {"cfg": tuple(int(v) for v in z["cfg"]), "hparams": json.loads(str(z["hparams"])),
+               "schedule": json.loads(str(z["schedule"])), "steps": int(z["steps"]), "names": names,
+               "video": torch.from_numpy(weight_recipe.clip(tuple(int(v) for v in z["video_shape"]))),
+               "mask": torch.from_numpy(z["mask"]).bool()}
+
+
+def check_train_step(z, step, loss, aux, named, tol_loss, tol_param):
+    """Loss terms of update `step` and the norm of every parameter AFTER it, against the fixture."""
+    rep = {"loss": abs(float(loss) - float(z[f"step{step}/loss"])) / abs(float(z[f"step{step}/loss"]))}
+    for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density", "per_sample_MAE"):
+        ref = float(z[f"step{step}/{k}"])
+        rep[k] = abs(float(aux[k]) - ref) / max(abs(ref), 1e-6)
+    for k, v in rep.items():
+        assert v < tol_loss, (step, k, v)
+    worst = 0.0
+    for n, p in named.items():
+        ref = float(z[f"step{step}/pnorm/{n}"])
+        worst = max(worst, abs(float(p.detach().double().norm()) - ref) / max(ref, 1e-12))
+    assert worst < tol_param, (step, worst)
+    rep["worst_param_norm"] = worst
+    return rep
+
+
+def check_train_final(z, fx, named, moments, count, tol):
+    """Final parameters (probe) and the optimizer state the reference checkpoints (nnx.state(optimizer)): count, mu, nu."""
+    from video_vae_b200 import checkpoint as ck
+    worst_p = 0.0
+    for n, p in named.items():
+        ref = z["final/pprobe/" + n]
+        got = weight_recipe.grad_probe(p.detach().float().cpu().numpy())
+        worst_p = max(worst_p, float(np.abs(got - ref).max() / max(float(np.abs(ref).max()), 1e-12)))
+    assert worst_p < tol, worst_p
+    # the key layout of the optimizer state, parsed by the product's own importer (opt_state -> 1 -> 0 -> {count, mu, nu})
+    tree = {k[len("opt_probe/"):]: z[k] for k in z.files if k.startswith("opt_probe/")}
+    tree.update({k[len("opt/"):]: z[k] for k in z.files if k.startswith("opt/")})
+    mu, nu, found = ck._find_adam_state(tree)
+    assert found == fx["steps"] == count and set(mu) == set(nu) == set(named)
+    worst_m = 0.0
+    for n in named:
+        m, v = moments(n)
+        for got, ref_probe, key in ((m, mu[n], "mu"), (v, nu[n], "nu")):
+            scale = max(float(np.abs(ref_probe).max()), 1e-30)
+            worst_m = max(worst_m, float(np.abs(weight_recipe.grad_probe(got) - ref_probe).max() / scale))
+    assert worst_m < 20 * tol, worst_m          # second moments are squares of gradients: twice their relative error, per step
+    return {"final_param_probe": worst_p, "moments_probe": worst_m, "count": found}
+
+
+@pytest.mark.skipif(not TRAIN_FIXTURES, reason=NO_FIXTURE)
+@pytest.mark.parametrize("path", TRAIN_FIXTURES or [None])
+def test_oracle_reproduces_reference_training_trajectory(path):
+    """train_step of train/rl_nonadversarial.py:188-198 + nnx.Optimizer(model, optax.chain(clip_by_global_norm(1.0),
+    adam(warmup_cosine_decay_schedule))) (:241-253) over six updates, written by tests/golden/make_golden_train.py, against
+    oracle/rl_losses.py + oracle/optim.py: lr = 0 on the first update, the clip active on five of six, a selection-loss
+    spike in between -- every loss term and every parameter after every update."""
+    from video_vae_b200 import checkpoint as ck
+    from oracle import Rngs
+    from oracle.losses import expand_mask
+    from oracle.optim import ClipAdam, warmup_cosine_decay_schedule
+    from oracle.rl_losses import loss_fn
+    from oracle.rl_model import VideoVAE
+    z, fx = load_train_fixture(path)
+    cfg = fx["cfg"]
+    hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
+    m = VideoVAE(*cfg, Rngs(0), dtype=torch.float32)
+    shapes = {n: p.shape for n, p in m.named_parameters()}
+    ck.load_flax_tree(m, {n: weight_recipe.param(n, shapes[n]) for n in fx["names"]}, strict=True)
+    named = dict(m.named_parameters())
+    params = list(named.values())
+    opt = ClipAdam(params, lr=warmup_cosine_decay_schedule(**fx["schedule"]), clip=1.0)
+    clipped = 0
+    for step in range(fx["steps"]):
+        for p in params:
+            p.grad = None
+        noise = torch.from_numpy(weight_recipe.normal(z[f"step{step}/noise_shape"]))
+        loss, aux = loss_fn(m, fx["video"], expand_mask(fx["mask"], hw), fx["mask"], Rngs(0), fx["hparams"], cube_perceptual,
+                            None, noise=noise, bernoulli_u=torch.from_numpy(z[f"step{step}/bernoulli_u"]))
+        loss.backward()
+        clipped += opt.step([p.grad if p.grad is not None else torch.zeros_like(p) for p in params]) >= 1.0
+        print(f"train fixture step {step}:", check_train_step(z, step, loss.detach(), aux, named, 1e-5, 1e-5))
+    assert 0 < clipped < fx["steps"]              # both branches of clip_by_global_norm were taken
+    idx = {n: i for i, n in enumerate(named)}
+    print("train fixture end:", check_train_final(z, fx, named, lambda n: (opt.m[idx[n]].numpy(), opt.v[idx[n]].numpy()),
+                                                  opt.count, 1e-4))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: never executed on a GPU; non-strict so "
+                                        "that its first run cannot stop the parity suite")
+@pytest.mark.skipif(not TRAIN_FIXTURES, reason=NO_FIXTURE)
+@pytest.mark.parametrize("path", TRAIN_FIXTURES or [None])
+def test_cuda_path_reproduces_reference_training_trajectory(path):
+    """The same six updates through rl_losses.train_step + ddp.FlatAdam (vvae_sumsq_f32_det + vvae_adam_step)."""
+    import video_vae_b200 as V
+    from video_vae_b200 import checkpoint as ck
+    from video_vae_b200.ddp import FlatAdam, FlatParams
+    from video_vae_b200.optim import warmup_cosine_decay_schedule
+    from video_vae_b200.rl_losses import train_step
+    from video_vae_b200.rl_model import VideoVAE
+    z, fx = load_train_fixture(path)
+    m = VideoVAE(*fx["cfg"], V.Rngs(0), dtype=torch.float32)
+    shapes = {n: p.shape for n, p in m.named_parameters()}
+    ck.load_flax_tree(m, {n: weight_recipe.param(n, shapes[n]) for n in fx["names"]}, strict=True)
+    flat = FlatParams(m)
+    adam = FlatAdam(flat, lr=warmup_cosine_decay_schedule(**fx["schedule"]), clip=1.0)
+    named = dict(m.named_parameters())
+    video, mask = fx["video"].cuda(), fx["mask"].cuda()
+    for step in range(fx["steps"]):
+        flat.zero_grad()
+        noise = torch.from_numpy(weight_recipe.normal(z[f"step{step}/noise_shape"])).cuda()
+        loss, aux = train_step(m, video, mask, fx["hparams"], V.Rngs(0), cube_perceptual, None, noise=noise,
+                               bernoulli_u=torch.from_numpy(z[f"step{step}/bernoulli_u"]).cuda())
+        adam.step()
+        torch.cuda.synchronize()
+        print(f"train fixture (cuda) step {step}:", check_train_step(z, step, loss.detach(), aux, named, 1e-4, 1e-4))
+    off = {id(p): o for p, o in zip(flat.params, flat.offsets)}
+
+    def moments(n):
+        p = named[n]
+        o = off[id(p)]
+        return adam.m[o:o + p.numel()].cpu().numpy(), adam.v[o:o + p.numel()].cpu().numpy()
+    print("train fixture (cuda) end:", check_train_final(z, fx, named, moments, adam.t, 1e-3))
 
 
 # ------------------------------------------------------------------------------------------------ consumer self-check

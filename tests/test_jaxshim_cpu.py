@@ -150,8 +150,10 @@ def test_reference_attention_mask_script_passes_on_the_shim():
     assert "17, 15, 19, 13" in out and "17, 10, 19, 13" in out            # the two shapes it prints
 
 
-RUN_REFERENCE_SCRIPT = ("import sys, runpy; sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2]); "
-                        "runpy.run_path(sys.argv[3], run_name='__main__')")
+# the scripts draw their inputs from numpy's global generator without seeding it: seeded HERE (the files stay untouched) so
+# that the same trajectory is checked on every run
+RUN_REFERENCE_SCRIPT = ("import sys, runpy, numpy; numpy.random.seed(0); sys.path.insert(0, sys.argv[1]); "
+                        "sys.path.insert(0, sys.argv[2]); runpy.run_path(sys.argv[3], run_name='__main__')")
 
 
 @needs_reference
@@ -164,6 +166,22 @@ def test_reference_model_test_script_passes_on_the_shim():
     out = run_py(RUN_REFERENCE_SCRIPT, SHIM, d, os.path.join(d, "test_rl_model.py"))
     assert "MODEL TESTS: 9 passed, 0 failed" in out and "ALL MODEL TESTS PASSED" in out, out[-1500:]
     assert "FAIL" not in out
+
+
+@needs_reference
+def test_reference_training_loop_script_on_the_shim():
+    """claude_distributed/test_training_loop.py, unmodified, over the jax / flax.nnx / optax look-alikes: its loss function,
+    one nnx.Optimizer(chain(clip_by_global_norm, adam)) train step, the loss decrease over ten updates, the gradient sanity
+    check, the signal handlers and the batch-sharding check pass; Test 7 needs the third-party `flaxmodels` VGG (absent
+    here, and its weights are a download), so the script reports 6 passed, 1 failed and exits 1."""
+    d = os.path.join(REFERENCE, "claude_distributed")
+    r = subprocess.run([sys.executable, "-c", RUN_REFERENCE_SCRIPT, SHIM, d, os.path.join(d, "test_training_loop.py")],
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, PYTHONPATH=ROOT), cwd=ROOT)
+    out = r.stdout
+    assert "TRAINING LOOP TESTS: 6 passed, 1 failed" in out, out[-2000:] + r.stderr[-2000:]
+    fails = [ln for ln in out.splitlines() if ln.strip().startswith("FAIL")]
+    assert len(fails) == 1 and "flaxmodels" in fails[0], fails
+    assert "PASS: Loss decreased" in out
 
 
 @needs_reference
@@ -190,6 +208,60 @@ def test_committed_refshim_fixture_is_what_the_generator_writes(tmp_path, model,
             assert np.allclose(new[k], old[k], rtol=1e-5, atol=1e-7), k        # thread-count dependent summation order
         else:
             assert np.array_equal(new[k], old[k]), k
+
+
+@needs_reference
+def test_committed_training_fixture_is_what_the_generator_writes(tmp_path):
+    """tests/golden/make_golden_train.py --shim: the reference's train_step + nnx.Optimizer over the optax look-alike."""
+    name = "refshim_rltrain_small_float32.npz"
+    out = str(tmp_path / name)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden_train.py"), "--shim", "--out", out],
+                   check=True, capture_output=True, timeout=600, cwd=ROOT)
+    new, old = np.load(out), np.load(os.path.join(ROOT, "tests", "golden", name))
+    assert sorted(new.files) == sorted(old.files)
+    for k in new.files:
+        if new[k].dtype.kind in "fc":
+            # six updates deep: thread-count dependent summation order, amplified by Adam's normalisation of small gradients
+            scale = max(float(np.abs(old[k]).max()), 1e-30)
+            assert float(np.abs(new[k] - old[k]).max()) <= 2e-4 * scale, k
+        else:
+            assert np.array_equal(new[k], old[k]), k
+
+
+def test_optax_look_alike_against_the_oracle_optimizer():
+    """Two independent restatements of optax.chain(clip_by_global_norm, adam(schedule)) -- oracle/jaxshim/optax.py keeps
+    optax's structure (GradientTransformation pairs over trees, chain state tuples), oracle/optim.py is one fused loop --
+    on the same random gradients for 12 updates, through lr = 0, the warm-up, clipped and unclipped steps."""
+    code = r"""
+import json, sys
+import numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import optax
+from oracle.optim import ClipAdam, warmup_cosine_decay_schedule
+sch = dict(init_value=0.0, peak_value=3e-3, warmup_steps=4, decay_steps=10, end_value=3e-4)
+rs = np.random.RandomState(0)
+params = {"a": {"w": torch.from_numpy(rs.randn(7, 5).astype(np.float32))}, "b": torch.from_numpy(rs.randn(11).astype(np.float32))}
+ref = [params["a"]["w"].clone(), params["b"].clone()]
+tx = optax.chain(optax.clip_by_global_norm(1.0), optax.adam(learning_rate=optax.warmup_cosine_decay_schedule(**sch)))
+state = tx.init(params)
+opt = ClipAdam(ref, lr=warmup_cosine_decay_schedule(**sch), clip=1.0)
+sched_err, clipped = 0.0, 0
+for t in range(12):
+    scale = 0.05 if t % 3 == 0 else 2.0                       # global norm below / above the clip threshold
+    g = {"a": {"w": torch.from_numpy(rs.randn(7, 5).astype(np.float32)) * scale}, "b": torch.from_numpy(rs.randn(11).astype(np.float32)) * scale}
+    updates, state = tx.update(g, state, params)
+    params = optax.apply_updates(params, updates)
+    clipped += opt.step([g["a"]["w"], g["b"]]) >= 1.0
+    sched_err = max(sched_err, abs(optax.warmup_cosine_decay_schedule(**sch)(t) - warmup_cosine_decay_schedule(**sch)(t)))
+err = max(float((params["a"]["w"] - ref[0]).abs().max()), float((params["b"] - ref[1]).abs().max()))
+adam_state = state[1][0]
+print(json.dumps({"err": err, "sched_err": sched_err, "clipped": int(clipped), "count": int(adam_state.count),
+                  "mu_err": float((adam_state.mu["b"] - opt.m[1]).abs().max()), "nu_err": float((adam_state.nu["b"] - opt.v[1]).abs().max())}))
+"""
+    r = json.loads(run_py(code, SHIM).strip().splitlines()[-1])
+    print(r)
+    assert r["err"] < 1e-6 and r["sched_err"] < 1e-12 and r["mu_err"] < 1e-7 and r["nu_err"] < 1e-7
+    assert 0 < r["clipped"] < 12 and r["count"] == 12
 
 
 def test_product_never_touches_the_shim():
