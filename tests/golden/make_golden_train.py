@@ -16,7 +16,7 @@ Written: per step the loss, its terms, the gradient global norm is NOT exported 
 holds what the step leaves behind -- after every update a 96-element probe + norm of every parameter, and at the end the
 optimizer state as the reference checkpoints it (``nnx.state(optimizer)``, train/rl_nonadversarial.py:62-67): count, and
 norm + probe of every first / second moment.  Inputs are by recipe (tests/golden/weight_recipe.py); the uniform draws
-behind jax.random.bernoulli are recorded per step.  Consumers: tests/test_jax_golden.py (oracle on CPU: oracle/rl_losses.py +
+behind jax.random.bernoulli (rl) / the Gumbel gate (vae) are recorded per step.  Consumers: tests/test_jax_golden.py (oracle on CPU: oracle/rl_losses.py +
 oracle/optim.py; the optimizer-state import of video_vae_b200/checkpoint.py)."""
 import argparse
 import json
@@ -39,6 +39,10 @@ def main():
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--cfg", default="small", choices=["small", "hd64"])
     ap.add_argument("--steps", type=int, default=STEPS)
+    ap.add_argument("--model", default="rl", choices=["rl", "vae"],
+                    help="rl: train/rl_model.py + train_step of train/rl_nonadversarial.py (writes *_rltrain_*.npz); vae: "
+                         "train/model.py + train_step AND eval_step of train/legacy/training_loop_adversarial.py:126-148 -- the "
+                         "step bench.py times (writes *_vaetrain_*.npz)")
     ap.add_argument("--out", default=None)
     ap.add_argument("--shim", action="store_true")
     args = ap.parse_args()
@@ -49,7 +53,10 @@ def main():
     import jax.numpy as jnp
     import optax
     from flax import nnx
-    from rl_model import VideoVAE                                  # the reference's train/rl_model.py
+    if args.model == "rl":
+        from rl_model import VideoVAE                              # the reference's train/rl_model.py
+    else:
+        from model import VideoVAE                                 # the reference's train/model.py
     shim = bool(getattr(jax, "IS_SHIM", False))
     assert shim == args.shim, "a jax look-alike is on sys.path without --shim (or --shim found the real jax first)"
 
@@ -80,8 +87,16 @@ def main():
     optimizer_def = optax.chain(optax.clip_by_global_norm(1.0), optax.adam(learning_rate=schedule_fn))
     optimizer = nnx.Optimizer(model, optimizer_def)
 
-    ref_file = os.path.join(args.reference, "train", "rl_nonadversarial.py")
-    train_step = G.reference_functions(ref_file, ("per_sample_mean", "magnify_negatives", "loss_fn", "train_step"), "train_step")
+    if args.model == "rl":
+        ref_file = os.path.join(args.reference, "train", "rl_nonadversarial.py")
+        train_step = G.reference_functions(ref_file, ("per_sample_mean", "magnify_negatives", "loss_fn", "train_step"), "train_step")
+        hparams = G.RL_HPARAMS
+    else:
+        ref_file = os.path.join(args.reference, "train", "legacy", "training_loop_adversarial.py")
+        fns = ("magnify_negatives", "loss_fn", "train_step", "eval_step")
+        train_step = G.reference_functions(ref_file, fns, "train_step")
+        eval_step = G.reference_functions(ref_file, fns, "eval_step")
+        hparams = G.HPARAMS
 
     def perceptual(vgg_params, reconstruction, target):           # the stand-in of make_golden_jax.py (same reason)
         return jnp.mean(jnp.abs(reconstruction - target) ** 3, axis=(1, 2, 3, 4))
@@ -89,20 +104,26 @@ def main():
     hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
     video = jnp.asarray(weight_recipe.clip((b, t, cfg[0], cfg[1], cfg[2])))
     original_mask = jnp.arange(t)[None, :] < jnp.asarray(spec["keep"])[:, None]
-    out = {"cfg": np.asarray(cfg, np.int64), "dtype": np.asarray("float32"), "model": np.asarray("rl_train"),
-           "hparams": np.asarray(json.dumps(G.RL_HPARAMS)), "schedule": np.asarray(json.dumps(SCHEDULE)),
+    out = {"cfg": np.asarray(cfg, np.int64), "dtype": np.asarray("float32"), "model": np.asarray(args.model + "_train"),
+           "hparams": np.asarray(json.dumps(hparams)), "schedule": np.asarray(json.dumps(SCHEDULE)),
            "steps": np.asarray(args.steps, np.int64), "recipe": np.asarray(weight_recipe.RECIPE_ID),
            "video_shape": np.asarray(video.shape, np.int64), "mask": np.asarray(original_mask)}
     terms = ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density", "per_sample_MAE")
     for step in range(args.steps):
         with G.DrawRecorder(weight_recipe.normal) as rec:
-            loss, aux = train_step(model, optimizer, video, original_mask, G.RL_HPARAMS, hw, nnx.Rngs(100 + step), perceptual, None)
+            if args.model == "rl":
+                loss, aux = train_step(model, optimizer, video, original_mask, hparams, hw, nnx.Rngs(100 + step), perceptual, None)
+            else:
+                loss, mse, sel_loss, kl, _recon, density = train_step(model, optimizer, video, original_mask, hparams, hw,
+                                                                      nnx.Rngs(100 + step))
+                aux = {"MSE": mse, "selection_loss": sel_loss, "kl_loss": kl, "kept_frame_density": density}
         assert len(rec.uniform) == 1 and len(rec.normal) == 1
         out[f"step{step}/bernoulli_u"] = rec.uniform[0].astype(np.float32)
         out[f"step{step}/noise_shape"] = np.asarray(rec.normal[0].shape, np.int64)
         out[f"step{step}/loss"] = np.asarray(loss, np.float32)
         for k in terms:
-            out[f"step{step}/{k}"] = np.asarray(aux[k], np.float32)
+            if k in aux:
+                out[f"step{step}/{k}"] = np.asarray(aux[k], np.float32)
         out[f"step{step}/lr"] = np.asarray(schedule_fn(step), np.float64)
         for name, v in G.flatten_state(nnx.state(model, nnx.Param)).items():
             v64 = v.astype(np.float64)
@@ -110,6 +131,15 @@ def main():
             if step == args.steps - 1:
                 out[f"final/pprobe/{name}"] = weight_recipe.grad_probe(v)
         print(f"step {step}: lr {float(schedule_fn(step)):.2e} loss {float(loss):.6f}", flush=True)
+
+    if args.model == "vae":
+        # eval_step (:139-148: train=False -- the latent is the mean, the gate has no noise) on the trained weights
+        with G.DrawRecorder(weight_recipe.normal) as rec:
+            loss, mse, sel_loss, kl, recon, density = eval_step(model, video, original_mask, hparams, hw, nnx.Rngs(7))
+        assert len(rec.uniform) == 0 and len(rec.normal) == 0, "eval_step drew random numbers"
+        for k, v in (("loss", loss), ("MSE", mse), ("selection_loss", sel_loss), ("kl_loss", kl), ("kept_frame_density", density)):
+            out["eval/" + k] = np.asarray(v, np.float32)
+        out["eval/reconstruction"] = np.ascontiguousarray(np.asarray(recon, np.float32)[:, :, ::3, ::3, :])
 
     # the optimizer half of the reference's checkpoint: nnx.state(optimizer) (train/rl_nonadversarial.py:62-67)
     opt = G.flatten_state(nnx.state(optimizer))
@@ -128,7 +158,7 @@ def main():
     assert n_mu == len(names), (n_mu, len(names))
     out["generator"] = np.asarray(("reference files on oracle/jaxshim (CPU torch), jax " if shim else "reference files on jax ")
                                   + jax.__version__)
-    path = args.out or os.path.join(HERE, f"{'refshim' if shim else 'jax'}_rltrain_{args.cfg}_float32.npz")
+    path = args.out or os.path.join(HERE, f"{'refshim' if shim else 'jax'}_{args.model}train_{args.cfg}_float32.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB")
 

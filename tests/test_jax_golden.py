@@ -31,7 +31,7 @@ import weight_recipe  # noqa: E402
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_videovae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_videovae_*.npz")))
 RL_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rlvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rlvae_*.npz")))
 DIST_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rldistvae_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rldistvae_*.npz")))
-TRAIN_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_rltrain_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_rltrain_*.npz")))
+TRAIN_FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jax_*train_*.npz")) + glob.glob(os.path.join(GOLDEN, "refshim_*train_*.npz")))
 NO_FIXTURE = "parity unpinned: no tests/golden/{jax,refshim}_videovae_*.npz (tests/golden/make_golden_jax.py [--shim])"
 
 
@@ -388,9 +388,9 @@ def test_cuda_path_reproduces_reference_distributed_model_outputs(path):
 # ------------------------------------------------------------------------------------------------ training trajectory
 def load_train_fixture(path):
     z = np.load(path)
-    assert str(z["model"]) == "rl_train" and str(z["recipe"]) == weight_recipe.RECIPE_ID
+    assert str(z["model"]) in ("rl_train", "vae_train") and str(z["recipe"]) == weight_recipe.RECIPE_ID
     names = [k[len("step0/pnorm/"):] for k in z.files if k.startswith("step0/pnorm/")]
-    return z, {"cfg": tuple(int(v) for v in z["cfg"]), "hparams": json.loads(str(z["hparams"])),
+    return z, {"cfg": tuple(int(v) for v in z["cfg"]), "hparams": json.loads(str(z["hparams"])), "rl": str(z["model"]) == "rl_train",
                "schedule": json.loads(str(z["schedule"])), "steps": int(z["steps"]), "names": names,
                "video": torch.from_numpy(weight_recipe.clip(tuple(int(v) for v in z["video_shape"]))),
                "mask": torch.from_numpy(z["mask"]).bool()}
@@ -400,8 +400,9 @@ def check_train_step(z, step, loss, aux, named, tol_loss, tol_param):
     """Loss terms of update `step` and the norm of every parameter AFTER it, against the fixture."""
     rep = {"loss": abs(float(loss) - float(z[f"step{step}/loss"])) / abs(float(z[f"step{step}/loss"]))}
     for k in ("MSE", "perceptual_loss", "selection_loss", "kl_loss", "kept_frame_density", "per_sample_MAE"):
-        ref = float(z[f"step{step}/{k}"])
-        rep[k] = abs(float(aux[k]) - ref) / max(abs(ref), 1e-6)
+        if f"step{step}/{k}" in z.files:              # the plain loss path has no perceptual / per-sample terms
+            ref = float(z[f"step{step}/{k}"])
+            rep[k] = abs(float(aux[k]) - ref) / max(abs(ref), 1e-6)
     for k, v in rep.items():
         assert v < tol_loss, (step, k, v)
     worst = 0.0
@@ -437,6 +438,17 @@ def check_train_final(z, fx, named, moments, count, tol):
     return {"final_param_probe": worst_p, "moments_probe": worst_m, "count": found}
 
 
+def check_eval_step(z, loss, aux, tol):
+    """eval_step of training_loop_adversarial.py:139-148 (train=False) on the weights the six updates left."""
+    rep = {"loss": abs(float(loss) - float(z["eval/loss"])) / abs(float(z["eval/loss"]))}
+    for k in ("MSE", "selection_loss", "kl_loss", "kept_frame_density"):
+        rep[k] = abs(float(aux[k]) - float(z["eval/" + k])) / max(abs(float(z["eval/" + k])), 1e-6)
+    rep["reconstruction"] = rel_err(aux["reconstruction"].detach().float().cpu()[:, :, ::3, ::3, :], z["eval/reconstruction"])
+    for k, v in rep.items():
+        assert v < tol, (k, v)
+    return rep
+
+
 @pytest.mark.skipif(not TRAIN_FIXTURES, reason=NO_FIXTURE)
 @pytest.mark.parametrize("path", TRAIN_FIXTURES or [None])
 def test_oracle_reproduces_reference_training_trajectory(path):
@@ -448,9 +460,19 @@ def test_oracle_reproduces_reference_training_trajectory(path):
     from oracle import Rngs
     from oracle.losses import expand_mask
     from oracle.optim import ClipAdam, warmup_cosine_decay_schedule
-    from oracle.rl_losses import loss_fn
-    from oracle.rl_model import VideoVAE
     z, fx = load_train_fixture(path)
+    if fx["rl"]:
+        from oracle.rl_losses import loss_fn as rl_loss_fn
+        from oracle.rl_model import VideoVAE
+
+        def loss_fn(m, video, mask, original_mask, noise, u):
+            return rl_loss_fn(m, video, mask, original_mask, Rngs(0), fx["hparams"], cube_perceptual, None, noise=noise, bernoulli_u=u)
+    else:                                         # train/model.py + training_loop_adversarial.py:90-136: the step bench.py times
+        from oracle.losses import loss_fn as vae_loss_fn
+        from oracle.model import VideoVAE
+
+        def loss_fn(m, video, mask, original_mask, noise, u):
+            return vae_loss_fn(m, video, mask, original_mask, Rngs(0), fx["hparams"], noise=noise, gumbel_u=u)
     cfg = fx["cfg"]
     hw = (cfg[0] // cfg[3]) * (cfg[1] // cfg[3])
     m = VideoVAE(*cfg, Rngs(0), dtype=torch.float32)
@@ -464,15 +486,19 @@ def test_oracle_reproduces_reference_training_trajectory(path):
         for p in params:
             p.grad = None
         noise = torch.from_numpy(weight_recipe.normal(z[f"step{step}/noise_shape"]))
-        loss, aux = loss_fn(m, fx["video"], expand_mask(fx["mask"], hw), fx["mask"], Rngs(0), fx["hparams"], cube_perceptual,
-                            None, noise=noise, bernoulli_u=torch.from_numpy(z[f"step{step}/bernoulli_u"]))
+        loss, aux = loss_fn(m, fx["video"], expand_mask(fx["mask"], hw), fx["mask"], noise,
+                            torch.from_numpy(z[f"step{step}/bernoulli_u"]))
         loss.backward()
         clipped += opt.step([p.grad if p.grad is not None else torch.zeros_like(p) for p in params]) >= 1.0
         print(f"train fixture step {step}:", check_train_step(z, step, loss.detach(), aux, named, 1e-5, 1e-5))
-    assert 0 < clipped < fx["steps"]              # both branches of clip_by_global_norm were taken
+    assert clipped > 0 and (clipped < fx["steps"] or not fx["rl"])   # rl fixture: both branches of clip_by_global_norm taken
     idx = {n: i for i, n in enumerate(named)}
     print("train fixture end:", check_train_final(z, fx, named, lambda n: (opt.m[idx[n]].numpy(), opt.v[idx[n]].numpy()),
                                                   opt.count, 1e-4))
+    if not fx["rl"]:
+        from oracle.losses import eval_step
+        loss, aux = eval_step(m, fx["video"], fx["mask"], fx["hparams"], hw, Rngs(7))
+        print("train fixture eval_step:", check_eval_step(z, loss, aux, 1e-4))
 
 
 @pytest.mark.gpu
@@ -486,9 +512,21 @@ def test_cuda_path_reproduces_reference_training_trajectory(path):
     from video_vae_b200 import checkpoint as ck
     from video_vae_b200.ddp import FlatAdam, FlatParams
     from video_vae_b200.optim import warmup_cosine_decay_schedule
-    from video_vae_b200.rl_losses import train_step
-    from video_vae_b200.rl_model import VideoVAE
     z, fx = load_train_fixture(path)
+    if fx["rl"]:
+        from video_vae_b200.rl_losses import train_step as rl_train_step
+        from video_vae_b200.rl_model import VideoVAE
+
+        def train_step(m, video, mask, noise, u):
+            return rl_train_step(m, video, mask, fx["hparams"], V.Rngs(0), cube_perceptual, None, noise=noise, bernoulli_u=u)
+    else:
+        from video_vae_b200.losses import loss_fn as vae_loss_fn
+        from video_vae_b200.model import VideoVAE
+
+        def train_step(m, video, mask, noise, u):
+            loss, aux = vae_loss_fn(m, video, mask[:, None, None, :], mask, V.Rngs(0), fx["hparams"], noise=noise, gumbel_u=u)
+            loss.backward()
+            return loss, aux
     m = VideoVAE(*fx["cfg"], V.Rngs(0), dtype=torch.float32)
     shapes = {n: p.shape for n, p in m.named_parameters()}
     ck.load_flax_tree(m, {n: weight_recipe.param(n, shapes[n]) for n in fx["names"]}, strict=True)
@@ -499,8 +537,7 @@ def test_cuda_path_reproduces_reference_training_trajectory(path):
     for step in range(fx["steps"]):
         flat.zero_grad()
         noise = torch.from_numpy(weight_recipe.normal(z[f"step{step}/noise_shape"])).cuda()
-        loss, aux = train_step(m, video, mask, fx["hparams"], V.Rngs(0), cube_perceptual, None, noise=noise,
-                               bernoulli_u=torch.from_numpy(z[f"step{step}/bernoulli_u"]).cuda())
+        loss, aux = train_step(m, video, mask, noise, torch.from_numpy(z[f"step{step}/bernoulli_u"]).cuda())
         adam.step()
         torch.cuda.synchronize()
         print(f"train fixture (cuda) step {step}:", check_train_step(z, step, loss.detach(), aux, named, 1e-4, 1e-4))
@@ -511,6 +548,10 @@ def test_cuda_path_reproduces_reference_training_trajectory(path):
         o = off[id(p)]
         return adam.m[o:o + p.numel()].cpu().numpy(), adam.v[o:o + p.numel()].cpu().numpy()
     print("train fixture (cuda) end:", check_train_final(z, fx, named, moments, adam.t, 1e-3))
+    if not fx["rl"]:
+        from video_vae_b200.losses import eval_step
+        loss, aux = eval_step(m, video, mask, fx["hparams"], V.Rngs(7))
+        print("train fixture (cuda) eval_step:", check_eval_step(z, loss, aux, 1e-3))
 
 
 # ------------------------------------------------------------------------------------------------ consumer self-check

@@ -211,12 +211,14 @@ def test_committed_refshim_fixture_is_what_the_generator_writes(tmp_path, model,
 
 
 @needs_reference
-def test_committed_training_fixture_is_what_the_generator_writes(tmp_path):
-    """tests/golden/make_golden_train.py --shim: the reference's train_step + nnx.Optimizer over the optax look-alike."""
-    name = "refshim_rltrain_small_float32.npz"
+@pytest.mark.parametrize("model", ["rl", "vae"])
+def test_committed_training_fixture_is_what_the_generator_writes(tmp_path, model):
+    """tests/golden/make_golden_train.py --shim: the reference's train_step (+ eval_step for the plain loss path) and
+    nnx.Optimizer over the optax look-alike."""
+    name = f"refshim_{model}train_small_float32.npz"
     out = str(tmp_path / name)
-    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden_train.py"), "--shim", "--out", out],
-                   check=True, capture_output=True, timeout=600, cwd=ROOT)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden_train.py"), "--shim", "--model", model,
+                    "--out", out], check=True, capture_output=True, timeout=600, cwd=ROOT)
     new, old = np.load(out), np.load(os.path.join(ROOT, "tests", "golden", name))
     assert sorted(new.files) == sorted(old.files)
     for k in new.files:
