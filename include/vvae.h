@@ -341,6 +341,15 @@ int vvae_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf
                    float b2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
                    vvae_stream_t stream);
 
+/* ---- scratch sizes in one place (vvae_workspace_bytes(op, shape...)) ----
+ * Nothing in this library allocates: the three entry points that need scratch take it from the caller.  Bytes of scratch
+ * (0 if none is needed for that shape, -1 for an unknown op or a malformed shape):
+ *   VVAE_WS_CONVT122   dims = {b_t, H, W, Cin, Cout}    workspace of vvae_convT122_{fwd,bwd}  (= vvae_convT122_workspace_bytes)
+ *   VVAE_WS_SUMSQ_DET  dims = {n}                       partials of vvae_sumsq_f32_det        (= 4 * vvae_sumsq_partials(n))
+ *   VVAE_WS_ATTN_BWD   dims = {n_seq, heads, L}         vvae_attn_args.delta of vvae_attn_bwd (fp32 [n_seq, heads, L]) */
+enum vvae_workspace_op { VVAE_WS_CONVT122 = 0, VVAE_WS_SUMSQ_DET = 1, VVAE_WS_ATTN_BWD = 2 };
+long long vvae_workspace_bytes(int op, const long long* dims, int ndims);
+
 /* ---- gradient exchange of the data-parallel step ----
  * The reference's all-reduce is implicit in its jitted SPMD step (claude_distributed/distributed_train.py:107-109,
  * 378-380,412) and its start-up replication is broadcast_one_to_all (:339).  These calls give a host without

@@ -139,3 +139,18 @@ def test_native_comm_refuses_without_gpu_and_file_exchange(tmp_path):
     with pytest.raises(TimeoutError):
         ddp.NativeComm.file_exchange(str(tmp_path / "absent"), 0.2)(None)
 
+
+
+def test_workspace_bytes_front_door():
+    """vvae_workspace_bytes(op, dims, ndims) agrees with the per-operator size functions and rejects bad input."""
+    from video_vae_b200 import _ffi
+    lib = _ffi.lib
+
+    def ws(op, *dims):
+        arr = (ctypes.c_longlong * max(len(dims), 1))(*dims)
+        return lib.vvae_workspace_bytes(op, arr, len(dims))
+    assert ws(0, 128, 64, 64, 128, 64) == lib.vvae_convT122_workspace_bytes(128, 64, 64, 128, 64) > 0
+    assert ws(1, 170_630_000) == 4 * lib.vvae_sumsq_partials(170_630_000) > 0
+    assert ws(2, 128, 8, 256) == 4 * 128 * 8 * 256
+    assert ws(2, 128, 8) == -1 and ws(0, 1, 2, 3, 4, 0) == -1 and ws(9, 1) == -1
+    assert lib.vvae_workspace_bytes(1, None, 1) == -1

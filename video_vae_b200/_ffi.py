@@ -130,6 +130,7 @@ _SIGS = {
     "vvae_sumsq_f32_det": ([vp, ll, vp, vp, vp], i32),
     "vvae_adam_step": ([vp, vp, vp, vp, vp, ll, f32, f32, f32, f32, i32, vp, f32, f32, vp], i32),
     # gradient exchange behind the C ABI (NCCL resolved with dlopen; ddp.NativeComm)
+    "vvae_workspace_bytes": ([i32, C.POINTER(ll), i32], ll),
     "vvae_comm_unique_id": ([vp], i32),
     "vvae_comm_init": ([C.POINTER(vp), vp, i32, i32], i32),
     "vvae_comm_rank": ([vp, C.POINTER(i32), C.POINTER(i32)], i32),
@@ -194,7 +195,8 @@ class AbiProfile:
     kernels in an eager pass (launch gaps included in neither).  Not for use under CUDA-graph capture."""
 
     _NO_STREAM = ("vvae_version", "vvae_device_ok", "vvae_debug_set", "vvae_debug_get", "vvae_gemm_uses_tcgen05", "vvae_conv3d_wprep_bytes",
-                  "vvae_convT122_workspace_bytes", "vvae_sumsq_partials")
+                  "vvae_convT122_workspace_bytes", "vvae_sumsq_partials", "vvae_workspace_bytes", "vvae_comm_unique_id",
+                  "vvae_comm_init", "vvae_comm_rank", "vvae_comm_destroy")
 
     def __init__(self, key=None):
         self.records, self._saved, self.key = [], {}, key

@@ -90,6 +90,30 @@ using namespace vvae;
 
 extern "C" {
 
+// One front door for the three caller-provided scratch buffers of the library (declared next to vvae_comm_* in vvae.h).
+long long vvae_workspace_bytes(int op, const long long* dims, int ndims) {
+  auto positive = [&](int n, long long limit) {
+    if (!dims || ndims != n) return false;
+    for (int i = 0; i < n; ++i)
+      if (dims[i] <= 0 || dims[i] > limit) return false;
+    return true;
+  };
+  constexpr long long kInt = 0x7fffffffLL;
+  switch (op) {
+    case VVAE_WS_CONVT122:
+      if (!positive(5, kInt)) return -1;
+      return vvae_convT122_workspace_bytes((int)dims[0], (int)dims[1], (int)dims[2], (int)dims[3], (int)dims[4]);
+    case VVAE_WS_SUMSQ_DET:
+      if (!positive(1, 1LL << 40)) return -1;
+      return 4LL * vvae_sumsq_partials(dims[0]);
+    case VVAE_WS_ATTN_BWD:
+      if (!positive(3, kInt) || dims[0] * dims[1] > (1LL << 40) / dims[2]) return -1;
+      return 4LL * dims[0] * dims[1] * dims[2];
+    default:
+      return -1;
+  }
+}
+
 int vvae_comm_unique_id(void* id128) {
   VVAE_REQUIRE(id128, "vvae_comm_unique_id: null pointer");
   VVAE_COMM_PROLOGUE("vvae_comm_unique_id");
