@@ -120,3 +120,35 @@ def test_flat_params_and_bucketed_allreduce_world2():
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_flat_params_route_collectives_through_a_comm_object():
+    """``FlatParams.all_reduce_grads(comm=)`` / ``.broadcast(comm=)`` (the NativeComm route: vvae_comm_* instead of
+    torch.distributed) hand the flat buffers to the communicator, and do nothing at world size 1."""
+    sys.path.insert(0, ROOT)
+    from video_vae_b200.ddp import FlatParams
+
+    class Comm:
+        def __init__(self, world):
+            self.world, self.calls = world, []
+
+        def all_reduce(self, t, average=False):
+            self.calls.append(("all_reduce", t.data_ptr(), t.numel(), average))
+            t.mul_(self.world)                      # what a sum over identical ranks does
+
+        def broadcast(self, t, src=0):
+            self.calls.append(("broadcast", t.data_ptr(), t.numel(), src))
+
+    m = _Toy()
+    flat = FlatParams(m)
+    flat.grad.fill_(1.5)
+    one = Comm(1)
+    flat.all_reduce_grads(comm=one)
+    flat.broadcast(comm=one)
+    assert one.calls == [] and bool((flat.grad == 1.5).all())
+    two = Comm(2)
+    flat.all_reduce_grads(comm=two)
+    flat.broadcast(src=1, comm=two)
+    assert two.calls == [("all_reduce", flat.grad.data_ptr(), flat.total, False), ("broadcast", flat.flat.data_ptr(), flat.total, 1)]
+    assert bool((flat.grad == 3.0).all())
+    assert all(p.grad.data_ptr() >= flat.grad.data_ptr() for p in m.parameters())      # the views still alias the flat buffer
