@@ -31,8 +31,7 @@ ok_mean = torch.allclose(y, base * (tri / world), rtol=1e-6)
 z = torch.full((n,), float(rank + 7), device="cuda")
 comm.broadcast(z, world - 1)
 ok_bcast = bool((z == float(world - 1 + 7)).all())
-w = (base * (rank + 1)).to(torch.bfloat16)          # small integers: exact in bf16 up to 256 ... use a mask for exactness
-w = (w % 64)
+w = (base * (rank + 1)).to(torch.bfloat16) % 64     # integers below 64: their sums over the ranks are exact in bf16
 expect = sum(((base * (r + 1)).to(torch.bfloat16) % 64).float() for r in range(world)).to(torch.bfloat16)
 comm.all_reduce(w)
 ok_bf16 = torch.equal(w, expect)
