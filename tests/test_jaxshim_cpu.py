@@ -266,6 +266,39 @@ print(json.dumps({"err": err, "sched_err": sched_err, "clipped": int(clipped), "
     assert 0 < r["clipped"] < 12 and r["count"] == 12
 
 
+def test_three_restatements_of_the_learning_rate_schedule_agree():
+    """optax.warmup_cosine_decay_schedule as the look-alike builds it (join_schedules of a linear and a cosine schedule, optax's
+    own structure), as oracle/optim.py and as the product's video_vae_b200/optim.py (closed forms), over 2000 random settings
+    and the counts around every boundary -- including the production schedule of train/rl_nonadversarial.py:241-247."""
+    code = r"""
+import math, random, sys
+sys.path.insert(0, sys.argv[1])
+import optax
+from oracle.optim import warmup_cosine_decay_schedule as O
+from video_vae_b200.optim import reference_schedule, warmup_cosine_decay_schedule as P
+random.seed(0)
+worst = 0.0
+for _ in range(2000):
+    init, peak = random.choice([0.0, 1e-6]), 10 ** random.uniform(-6, -2)
+    warm = random.choice([0, 1, 3, 10, 100, 5000])
+    dec = warm + random.choice([1, 5, 50, 1000, 10 ** 6])
+    end = peak * random.choice([0, 0.1, 0.5, 1.0])
+    fs = [f(init, peak, warm, dec, end) for f in (P, O, optax.warmup_cosine_decay_schedule)]
+    for cnt in (0, 1, 2, warm - 1, warm, warm + 1, dec - 1, dec, dec + 7, 10 ** 7):
+        if cnt >= 0:
+            v = [f(cnt) for f in fs]
+            worst = max(worst, (max(v) - min(v)) / peak)
+batch, lr = 8, 2e-5
+prod = reference_schedule(batch)
+ref = optax.warmup_cosine_decay_schedule(0.0, lr, 20000 // math.sqrt(batch), 1_000_000, lr / 10)
+for cnt in (0, 1, 7070, 7071, 7072, 500_000, 999_999, 1_000_000, 2_000_000):
+    worst = max(worst, abs(prod(cnt) - ref(cnt)) / lr)
+assert prod(0) == 0.0 and abs(prod(2_000_000) - lr / 10) < 1e-18
+print(worst)
+"""
+    assert float(run_py(code, SHIM).strip().splitlines()[-1]) < 1e-12
+
+
 def test_product_never_touches_the_shim():
     for path in glob.glob(os.path.join(ROOT, "video_vae_b200", "**", "*.py"), recursive=True) + [os.path.join(ROOT, "__graft_entry__.py")]:
         assert "jaxshim" not in open(path).read(), path
