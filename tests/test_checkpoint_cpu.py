@@ -166,3 +166,64 @@ def test_two_flat_params_keep_their_own_bf16_shadows():
     pa, pb = a.fill_token, b.fill_token
     assert F_.shadow(pa, torch.bfloat16).data_ptr() == fa._shadow_views[id(pa)][1].data_ptr()
     assert F_.shadow(pb, torch.bfloat16).data_ptr() == fb._shadow_views[id(pb)][1].data_ptr()
+
+
+REFERENCE = "/root/reference"
+WRITE_REFERENCE_CHECKPOINT = r"""
+import sys
+import numpy as np
+import torch
+shim, ref_train, out = sys.argv[1:4]
+sys.path.insert(0, shim)
+sys.path.insert(0, ref_train)
+import jax.numpy as jnp
+import optax
+from flax import nnx
+from model import VideoVAE                                         # the reference's train/model.py
+from video_vae_b200 import checkpoint as ck
+cfg = (64, 64, 3, 16, 1, 1, 128, 2, 128, 16, 8, 4)
+model = VideoVAE(*cfg, rngs=nnx.Rngs(2), dtype=jnp.float32, param_dtype=jnp.float32)
+optimizer = nnx.Optimizer(model, optax.chain(optax.clip_by_global_norm(1.0), optax.adam(learning_rate=1e-3)))   # rl_nonadversarial.py:248-253
+g = torch.Generator().manual_seed(0)
+for _ in range(3):
+    params = nnx.state(model, nnx.Param)
+    grads = nnx.State({p: 0.05 * torch.randn(v.shape, generator=g) for p, v in params.flat.items()})
+    optimizer.update(grads)
+# save_checkpoint of train/rl_nonadversarial.py:62-67, with .npz as the transport instead of orbax
+state = {"model": nnx.state(model).to_pure_dict(), "optimizer": nnx.state(optimizer).to_pure_dict()}
+print(len(ck.save_npz(out, state)))
+"""
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REFERENCE + "/train"), reason="/root/reference is only present in the build container")
+def test_checkpoint_written_by_the_reference_model_code_loads(tmp_path):
+    """{"model": nnx.state(model), "optimizer": nnx.state(optimizer)} as train/rl_nonadversarial.py:62-67 saves it, produced by
+    the reference's OWN train/model.py (run on oracle/jaxshim) after three optimizer updates: the key set is the reference's
+    -- RotaryEmbedding's cos_cached / sin_cached Variables (train/layers.py:101-102) included, the model's parameters a
+    second time under optimizer.model -- and the product loads it strictly, parameters, Adam moments and step count."""
+    import os
+    import subprocess
+    import sys
+    from video_vae_b200.ddp import FlatAdam, FlatParams
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "reference_checkpoint.npz")
+    r = subprocess.run([sys.executable, "-c", WRITE_REFERENCE_CHECKPOINT, os.path.join(root, "oracle", "jaxshim"),
+                        os.path.join(REFERENCE, "train"), path], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, PYTHONPATH=root), cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    raw = ck.load_npz(path)
+    assert any(k.endswith("ROPE.cos_cached") for k in raw) and any(k.startswith("optimizer.opt_state.1.0.mu.") for k in raw)
+    assert any(k.startswith("optimizer.model.") for k in raw)
+    dst = _model(1)
+    flat = FlatParams(dst)
+    adam = FlatAdam(flat)
+    loaded = ck.load_checkpoint(dst, path, strict=True, adam=adam)
+    names = [n for n, _ in dst.named_parameters()]
+    assert sorted(loaded) == sorted(names) and adam.t == 3
+    assert ck.rope_tables_match(ck._unflatten({k[len("model."):]: v for k, v in raw.items() if k.startswith("model.")}), dst) == 8
+    for i, n in enumerate(names):
+        s, cnt = flat.offsets[i], flat.params[i].numel()
+        assert torch.equal(flat.params[i].detach().reshape(-1), torch.from_numpy(raw["model." + n]).reshape(-1)), n
+        assert torch.equal(adam.m[s:s + cnt], torch.from_numpy(raw["optimizer.opt_state.1.0.mu." + n]).reshape(-1)), n
+        assert torch.equal(adam.v[s:s + cnt], torch.from_numpy(raw["optimizer.opt_state.1.0.nu." + n]).reshape(-1)), n
+    assert float(adam.v.abs().max()) > 0.0
